@@ -1,0 +1,192 @@
+// TEST INFRASTRUCTURE ONLY (oracle/): C entry points around the UNMODIFIED reference renderer.
+//
+// build_ref.sh compiles this file together with the reference's own sources (taken from where they lie
+// under /root/reference/VerStarting; never copied into the repo) into oracle/_ref/libmythtracer_ref.so.
+// It is the strongest form of the parity oracle: tests/ compare both the CPU restatement
+// (oracle/mt_oracle.cc) and the CUDA path with what this library returns, and bench.py's `--impl
+// reference` arm and `cpu_baseline` leg time it on the host cores.  Nothing in the product links it.
+//
+// What is called here is the reference's public API only:
+//   MythTracer::LoadObj / GetScene / RayTrace(WorkChunk*)      reference mythtracer.h:55-66
+//   OctTree::Finalize / IntersectRay / GetAABB                  reference octtree.h:16-39
+//   PerPixelDebugInfo tap via WorkChunk::output_debug           reference mythtracer.cc:24-36,299-300
+#include <fcntl.h>
+#include <omp.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cmath>
+#include <memory>
+#include <vector>
+
+#include "mythtracer.h"
+#include "primitive_triangle.h"
+
+namespace raytracer {
+// build_ref.sh rewrites `const int MAX_RECURSION_LEVEL = 5;` (reference mythtracer.h:11) into an extern
+// declaration in a throw-away copy, so that BASELINE.json's depth 2/3/5/8 configs can be served by one
+// binary.  The default stays the reference's 5.
+int MAX_RECURSION_LEVEL = 5;
+}  // namespace raytracer
+
+namespace {
+
+using raytracer::Camera;
+using raytracer::Light;
+using raytracer::MythTracer;
+using raytracer::PerPixelDebugInfo;
+using raytracer::Primitive;
+using raytracer::Ray;
+using raytracer::WorkChunk;
+using math3d::V3D;
+
+std::unique_ptr<MythTracer> g_mt;
+bool g_finalized = false;
+
+// The reference prints progress dots and banners to stdout (mythtracer.cc:282,287,303,309); keep the
+// caller's stdout clean (bench.py prints exactly one JSON line there).
+class StdoutSilencer {
+ public:
+  StdoutSilencer() {
+    fflush(stdout);
+    saved_ = dup(1);
+    int devnull = open("/dev/null", O_WRONLY);
+    if (devnull >= 0) {
+      dup2(devnull, 1);
+      close(devnull);
+    }
+  }
+  ~StdoutSilencer() {
+    fflush(stdout);
+    if (saved_ >= 0) {
+      dup2(saved_, 1);
+      close(saved_);
+    }
+  }
+
+ private:
+  int saved_ = -1;
+};
+
+void EnsureFinalized() {
+  if (!g_finalized) {
+    // RayTrace finalises lazily (mythtracer.cc:281-285); do the same for direct tree queries by
+    // rendering one pixel through the public entry point, so that the private flag stays consistent.
+    WorkChunk chunk{1, 1, 0, 0, 1, 1, Camera{{0, 0, 0}, 0, 0, 0, 90.0}, {}, {}};
+    chunk.output_bitmap.resize(3);
+    g_mt->RayTrace(&chunk);
+    g_finalized = true;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ref_num_threads() { return omp_get_max_threads(); }
+
+void ref_set_depth(int depth) { raytracer::MAX_RECURSION_LEVEL = depth; }
+
+int ref_get_depth() { return raytracer::MAX_RECURSION_LEVEL; }
+
+// Loads an OBJ (+MTL +PPM textures) with the reference's own loader.  Returns 0 on success.
+int ref_load_obj(const char *path) {
+  StdoutSilencer quiet;
+  g_mt.reset(new MythTracer);
+  g_finalized = false;
+  if (!g_mt->LoadObj(path)) {
+    g_mt.reset();
+    return -1;
+  }
+  return 0;
+}
+
+void ref_unload() {
+  g_mt.reset();
+  g_finalized = false;
+}
+
+// lights: n x 12 doubles = position, ambient, diffuse, specular (reference light.h:8-14).
+int ref_set_lights(const double *lights, int n) {
+  if (!g_mt) return -1;
+  auto &dst = g_mt->GetScene()->lights;
+  dst.clear();
+  for (int i = 0; i < n; i++) {
+    const double *l = lights + i * 12;
+    dst.push_back(Light{{l[0], l[1], l[2]}, {l[3], l[4], l[5]}, {l[6], l[7], l[8]}, {l[9], l[10], l[11]}});
+  }
+  return 0;
+}
+
+int ref_scene_aabb(double *out6) {
+  if (!g_mt) return -1;
+  raytracer::AABB b = g_mt->GetScene()->tree.GetAABB();
+  for (int i = 0; i < 3; i++) {
+    out6[i] = b.min.v[i];
+    out6[3 + i] = b.max.v[i];
+  }
+  return 0;
+}
+
+// cam: origin.xyz, pitch, yaw, roll, aov (the 7 doubles of Camera::Serialize, camera.cc:71-81).
+// rgb: chunk_w*chunk_h*3 bytes.  line_no / points (3 doubles per pixel) may be NULL.
+// seconds: wall time of the RayTrace(WorkChunk*) call itself (std::chrono), octree Finalize excluded.
+int ref_render(const double *cam, int image_w, int image_h, int chunk_x, int chunk_y, int chunk_w,
+               int chunk_h, uint8_t *rgb, int32_t *line_no, double *points, double *seconds) {
+  if (!g_mt) return -1;
+  StdoutSilencer quiet;
+  EnsureFinalized();
+  WorkChunk chunk{image_w, image_h, chunk_x, chunk_y, chunk_w, chunk_h,
+                  Camera{{cam[0], cam[1], cam[2]}, cam[3], cam[4], cam[5], cam[6]}, {}, {}};
+  size_t npx = (size_t)chunk_w * (size_t)chunk_h;
+  chunk.output_bitmap.resize(npx * 3);
+  if (line_no != nullptr || points != nullptr) chunk.output_debug.resize(npx);
+  auto t0 = std::chrono::steady_clock::now();
+  bool ok = g_mt->RayTrace(&chunk);
+  auto t1 = std::chrono::steady_clock::now();
+  if (seconds != nullptr) *seconds = std::chrono::duration<double>(t1 - t0).count();
+  if (!ok) return -2;
+  for (size_t i = 0; i < npx * 3; i++) rgb[i] = chunk.output_bitmap[i];
+  for (size_t i = 0; i < npx && !chunk.output_debug.empty(); i++) {
+    if (line_no != nullptr) line_no[i] = chunk.output_debug[i].line_no;
+    if (points != nullptr) {
+      points[i * 3 + 0] = chunk.output_debug[i].point.v[0];
+      points[i * 3 + 1] = chunk.output_debug[i].point.v[1];
+      points[i * 3 + 2] = chunk.output_debug[i].point.v[2];
+    }
+  }
+  return 0;
+}
+
+// Batched OctTree::IntersectRay (octtree.cc:26-40).  line_no[i] = -1 on a miss (t and point untouched).
+int ref_intersect(int64_t n, const double *origins, const double *dirs, int32_t *line_no, double *t,
+                  double *point) {
+  if (!g_mt) return -1;
+  {
+    StdoutSilencer quiet;
+    EnsureFinalized();
+  }
+  const raytracer::OctTree &tree = g_mt->GetScene()->tree;
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int64_t i = 0; i < n; i++) {
+    Ray ray({origins[i * 3], origins[i * 3 + 1], origins[i * 3 + 2]},
+            {dirs[i * 3], dirs[i * 3 + 1], dirs[i * 3 + 2]});
+    V3D p;
+    double dist = 0.0;
+    const Primitive *hit = tree.IntersectRay(ray, &p, &dist);
+    if (hit == nullptr) {
+      line_no[i] = -1;
+      continue;
+    }
+    line_no[i] = hit->debug_line_no;
+    t[i] = dist;
+    point[i * 3 + 0] = p.v[0];
+    point[i * 3 + 1] = p.v[1];
+    point[i * 3 + 2] = p.v[2];
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,193 @@
+/* mythtracer_b200 -- C ABI of the B200-native (sm_100a) replacement for MythTracer's ray-casting hot path.
+ *
+ * The reference has no plugin/FFI layer: its boundary for this path is the public C++ API of
+ * `raytracer::MythTracer` (reference VerStarting/mythtracer.h:55-66) together with the public members of
+ * Scene / OctTree / Camera / Light / Material / WorkChunk.  This header is the thin `extern "C"` layer that
+ * boundary is re-implemented on (plain pointers and sizes, no C++ or torch types); the header-compatible
+ * C++ classes in include/mythtracer/ and the Python mirror in mythtracer_b200/api.py are written on top of
+ * it, and INTEGRATION.md shows how a maintainer of the reference binds it.
+ *
+ * There is NO CPU fallback: every entry point that renders or intersects runs hand-written CUDA kernels
+ * and fails with MTB_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Struct layouts mirror the reference's data members one to one (same order, FP64 throughout).
+ */
+#ifndef MYTHTRACER_B200_H_
+#define MYTHTRACER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTB_OK 0
+#define MTB_ERR_ARG (-1)      /* bad argument / bad state (e.g. render before a scene is uploaded) */
+#define MTB_ERR_CUDA (-2)     /* CUDA runtime error; text in mtb_last_error() */
+#define MTB_ERR_IO (-3)       /* loader: file missing or malformed (the reference's `return false` paths) */
+#define MTB_ERR_LIMIT (-4)    /* scene exceeds a documented limit (octree deeper than MTB_MAX_TREE_DEPTH) */
+
+#define MTB_MAX_TREE_DEPTH 48 /* the reference has no cap (octtree.cc:52-55); deeper trees are refused */
+#define MTB_MAX_RAY_DEPTH 16  /* max_depth argument = the reference's MAX_RECURSION_LEVEL (mythtracer.h:11) */
+
+typedef struct mtb_context mtb_context;
+
+/* reference camera.h:31-33; byte-identical to what Camera::Serialize writes (camera.cc:71-81) */
+typedef struct {
+  double origin[3];
+  double pitch, yaw, roll; /* degrees, X / Y / Z axis */
+  double aov;              /* horizontal angle of view, degrees */
+} mtb_camera;
+
+/* reference light.h:8-14 */
+typedef struct {
+  double position[3], ambient[3], diffuse[3], specular[3];
+} mtb_light;
+
+/* reference material.h:12-48 (`Texture *tex` becomes an index into the texture table, -1 = none) */
+typedef struct {
+  double ambient[3], diffuse[3], specular[3]; /* Ka Kd Ks */
+  double specular_exp;                        /* Ns */
+  double reflectance;                         /* Refl */
+  double transparency;                        /* Tr */
+  double transmission_filter[3];              /* Tf */
+  double refraction_index;                    /* Ni */
+  int32_t texture;
+  int32_t pad_;
+} mtb_material;
+
+/* 8-bit RGBA texels, row-major, top row first: what texture.cc:81-104 holds after SDL's RGBA32 conversion.
+ * The px/255.0 conversion (texture.cc:100-104) happens on the device in FP64. */
+typedef struct {
+  int32_t width, height;
+  const uint8_t *rgba;
+} mtb_texture;
+
+/* reference primitive_triangle.h:26-29 + primitive.h:41-42.  Array order = OctTree::AddPrimitive order
+ * (octtree.cc:8-14); it decides ties exactly as the reference's list order does. */
+typedef struct {
+  double vertex[9];
+  double normal[9];
+  double uvw[9];
+  int32_t material; /* index into the material table, -1 = `mtl == nullptr` */
+  int32_t line_no;  /* Primitive::debug_line_no */
+} mtb_triangle;
+
+/* reference mythtracer.h:13-16 (PerPixelDebugInfo; 32 bytes on x86-64) */
+typedef struct {
+  int32_t line_no; /* -1 on a miss */
+  int32_t pad_;
+  double point[3]; /* NaN on a miss */
+} mtb_debug;
+
+/* Optional per-pixel decision taps (device-computed; used by the parity tests, see oracle/mt_oracle.h). */
+typedef struct {
+  uint64_t *sig_hits;   /* chunk_w*chunk_h, may be NULL */
+  uint64_t *sig_shadow; /* chunk_w*chunk_h, may be NULL */
+  uint32_t *n_rays;     /* chunk_w*chunk_h, may be NULL */
+} mtb_taps;
+
+/* Work done by one render / intersect call.  Counters other than `rays..refract` are only filled by the
+ * counting build of the kernels (MTB_FLAG_COUNT_WORK), which is slower and never timed. */
+typedef struct {
+  uint64_t rays;     /* OctTree::IntersectRay-equivalent queries = primary + shadow + reflect + refract */
+  uint64_t primary, shadow, reflect, refract;
+  uint64_t n_slab;    /* octree child / root box tests */
+  uint64_t n_visit;   /* octree nodes entered */
+  uint64_t n_triaabb; /* exact triangle AABB pre-tests (primitive_triangle.cc:85-108) */
+  uint64_t n_mt;      /* Moller-Trumbore evaluations */
+  uint64_t n_hit;     /* triangle tests that returned true */
+  uint64_t n_shade;   /* shaded hits */
+  uint64_t n_bvh;     /* list-BVH box tests (no reference counterpart: they replace n_triaabb work) */
+  uint64_t n_literal; /* rays that took the literal (NaN-exact) traversal */
+  double kernel_ms;   /* device time of the kernels of this call (CUDA events) */
+  double total_ms;    /* host wall time of the call, copies included */
+} mtb_stats;
+
+typedef struct {
+  int64_t n_triangles, n_nodes, n_bvh_nodes;
+  int32_t tree_depth, n_materials, n_textures, n_lights;
+  int64_t root_list, biggest_list, interior_triangles;
+  double aabb_min[3], aabb_max[3]; /* OctTree::GetAABB (octtree.cc:42-44) */
+  int64_t device_bytes;
+} mtb_scene_summary;
+
+#define MTB_FLAG_COUNT_WORK 1u   /* fill the n_* work counters (counting kernels) */
+#define MTB_FLAG_NO_LIST_BVH 2u  /* scan every node list linearly, like the reference (A/B measurements) */
+#define MTB_FLAG_WAVEFRONT 4u    /* wavefront pipeline instead of the per-pixel megakernel */
+
+/* ---- life cycle -------------------------------------------------------------------------------- */
+
+/* Creates a context on `n_devices` CUDA devices (device ordinals in `devices`; NULL = device 0 only).
+ * One host thread drives one context (the reference's MythTracer is not re-entrant either). */
+int mtb_create(mtb_context **out, const int *devices, int n_devices);
+/* A context without any device: the loader, the octree builder and the inspection calls work (host-side
+ * logic can be tested on a machine without a GPU); every render / intersect call fails with MTB_ERR_CUDA. */
+int mtb_create_host(mtb_context **out);
+void mtb_destroy(mtb_context *ctx);
+/* Text of the last error on this context (or of the last failed mtb_create when ctx == NULL). */
+const char *mtb_last_error(const mtb_context *ctx);
+int mtb_device_count(const mtb_context *ctx);
+
+/* ---- scene ------------------------------------------------------------------------------------- */
+
+/* Replaces OctTree::AddPrimitive + Finalize (octtree.cc:8-24,46-135) and the AoS Scene: builds the
+ * reference's octree (same boxes, same list membership and order), flattens it and uploads SoA buffers to
+ * every device of the context.  Lights are untouched. */
+int mtb_scene_upload(mtb_context *ctx, const mtb_triangle *tris, int64_t n_tris, const mtb_material *mtls,
+                     int32_t n_mtls, const mtb_texture *texs, int32_t n_texs);
+/* MythTracer::LoadObj (mythtracer.cc:247-256): OBJ + MTL (+ PPM map_Ka textures) -> mtb_scene_upload. */
+int mtb_load_obj(mtb_context *ctx, const char *path);
+/* scene.lights (scene.h:14) -- the reference's callers rewrite it every frame (main_local.cc:79-110). */
+int mtb_set_lights(mtb_context *ctx, const mtb_light *lights, int32_t n);
+int mtb_scene_info(const mtb_context *ctx, mtb_scene_summary *out);
+/* Copies out the host-side triangle / material tables the loader produced (NULL = skip). */
+int mtb_scene_read(const mtb_context *ctx, mtb_triangle *tris, mtb_material *mtls);
+/* Octree membership of every triangle (insertion order): the box of the node whose list holds it
+ * (6 doubles: lo.xyz, hi.xyz) and that node's depth.  Either pointer may be NULL. */
+int mtb_scene_triangle_nodes(const mtb_context *ctx, double *node_box, int32_t *node_depth);
+int mtb_set_flags(mtb_context *ctx, uint32_t flags);
+/* Tile partitioning across processes -- the in-process form of the reference's master/worker contract
+ * (main_net_master.cc:195-221: the frame is cut into tiles, every worker holds the whole scene and renders
+ * the tiles it is handed).  The chunk is cut into strips of 8 rows; with (part_index, part_count) this
+ * context renders only the strips s with s % (part_count * n_devices) == part_index * n_devices + g on its
+ * device g and leaves all other pixels of the output untouched.  Default (0, 1): everything. */
+int mtb_set_partition(mtb_context *ctx, int part_index, int part_count);
+
+/* ---- the hot path ------------------------------------------------------------------------------ */
+
+/* MythTracer::RayTrace(WorkChunk*) (mythtracer.cc:280-312): renders chunk [chunk_x, chunk_x+chunk_w) x
+ * [chunk_y, chunk_y+chunk_h) of an image_w x image_h frame.  rgb_out: HOST buffer, chunk_w*chunk_h*3
+ * bytes, row-major RGB24, stride chunk_w*3 (WorkChunk::output_bitmap).  dbg_out (HOST, nullable):
+ * chunk_w*chunk_h PerPixelDebugInfo (WorkChunk::output_debug).  taps / stats nullable.  max_depth is the
+ * reference's compile-time MAX_RECURSION_LEVEL.  With several devices the chunk is split into
+ * interleaved tile rows, rendered concurrently and gathered over NVLink peer copies. */
+int mtb_render_chunk(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h, int chunk_x, int chunk_y,
+                     int chunk_w, int chunk_h, int max_depth, uint8_t *rgb_out, mtb_debug *dbg_out,
+                     const mtb_taps *taps, mtb_stats *stats);
+
+/* Same render, result left in DEVICE memory of device 0 (d_rgb: chunk_w*chunk_h*3 bytes); enqueued on
+ * `stream` (a cudaStream_t of device 0; NULL = the context's own stream) without synchronising when the
+ * context has one device.  This is the entry bench.py times for the HBM-resident figure. */
+int mtb_render_chunk_device(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h, int chunk_x,
+                            int chunk_y, int chunk_w, int chunk_h, int max_depth, void *d_rgb, void *stream,
+                            mtb_stats *stats);
+
+/* Work counters accumulated by mtb_render_chunk_device calls that passed stats == NULL since the last
+ * read; synchronises every device of the context and resets the counters. */
+int mtb_read_counters(mtb_context *ctx, mtb_stats *stats);
+
+/* Batched OctTree::IntersectRay (octtree.cc:26-40).  HOST arrays: origins/dirs n*3, tri_index n (insertion
+ * index, -1 = nullptr), t n, point n*3 (nullable). */
+int mtb_intersect_rays(mtb_context *ctx, int64_t n, const double *origins, const double *dirs, int32_t *tri_index,
+                       double *t, double *point, mtb_stats *stats);
+
+/* Camera::GetSensor (camera.cc:17-63): start_point, delta_scanline, delta_pixel (9 doubles), host side. */
+int mtb_camera_sensor(const mtb_camera *cam, int image_w, int image_h, double out9[9]);
+
+const char *mtb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MYTHTRACER_B200_H_ */

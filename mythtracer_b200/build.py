@@ -1,0 +1,51 @@
+"""Builds libmythtracer_b200.so (hand-written CUDA kernels + C ABI) in-tree for sm_100a with nvcc.
+
+--fmad=false / -ffp-contract=off: the reference binary contains no FMA and every
+deciding computation is reproduced bit for bit, so contraction must stay off on both device and host.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libmythtracer_b200.so")
+SOURCES = ["api.cu", "kernels.cu", "scene_build.cc", "obj_loader.cc"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2,-Wall", "-D_USE_MATH_DEFINES",
+]
+
+
+def _newest_source_mtime() -> float:
+    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "mythtracer_b200.h")]
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def build(force: bool = False, verbose: bool = False, extra=()) -> str:
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    objs = []
+    build_dir = os.path.join(HERE, "build")
+    os.makedirs(build_dir, exist_ok=True)
+    for src in SOURCES:
+        obj = os.path.join(build_dir, src + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-x", "cu" if src.endswith(".cu") else "c++",
+                                                  "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+        objs.append(obj)
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True, extra=["-Xptxas", "-v"] if "--ptxas" in sys.argv else ()))

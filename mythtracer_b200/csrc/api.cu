@@ -1,0 +1,700 @@
+// C ABI of mythtracer_b200 (see include/mythtracer_b200.h): context, scene residency in HBM, and the
+// launch / gather logic around the kernels of kernels.cu.  No CPU rendering path exists in this file.
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "device_scene.h"
+
+namespace {
+
+std::string g_create_error;
+
+#define MTB_CUDA(ctx, expr)                                                                                  \
+  do {                                                                                                       \
+    cudaError_t e__ = (expr);                                                                                \
+    if (e__ != cudaSuccess) {                                                                                \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                                      \
+      return MTB_ERR_CUDA;                                                                                   \
+    }                                                                                                        \
+  } while (0)
+
+template <typename T>
+struct DeviceBuffer {
+  T *ptr = nullptr;
+  size_t count = 0;
+  cudaError_t Reserve(size_t n) {
+    if (n <= count && ptr != nullptr) return cudaSuccess;
+    if (ptr != nullptr) cudaFree(ptr);
+    ptr = nullptr;
+    count = 0;
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ptr), n * sizeof(T));
+    if (e == cudaSuccess) count = n;
+    return e;
+  }
+  cudaError_t Upload(const T *src, size_t n, cudaStream_t s) {
+    cudaError_t e = Reserve(n > 0 ? n : 1);
+    if (e != cudaSuccess || n == 0) return e;
+    return cudaMemcpyAsync(ptr, src, n * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+  void Free() {
+    if (ptr != nullptr) cudaFree(ptr);
+    ptr = nullptr;
+    count = 0;
+  }
+};
+
+struct DeviceState {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  cudaEvent_t ev_gathered = nullptr;  // device 0 only: the last gather has read every peer buffer
+  bool peer_to_dev0 = false;
+  // scene
+  DeviceBuffer<mtb::NodeRec> nodes;
+  DeviceBuffer<mtb::SlotRec> slots;
+  DeviceBuffer<mtb::ShadeRec> shade;
+  DeviceBuffer<mtb::BvhRec> bvh;
+  DeviceBuffer<int32_t> list_order;
+  DeviceBuffer<mtb_material> materials;
+  DeviceBuffer<cudaTextureObject_t> tex_objects;
+  DeviceBuffer<int2> tex_dims;
+  DeviceBuffer<mtb_light> lights;
+  std::vector<cudaArray_t> tex_arrays;
+  std::vector<cudaTextureObject_t> tex_handles;
+  mtb::DeviceScene scene{};
+  // per-render scratch
+  DeviceBuffer<uint8_t> rgb;
+  DeviceBuffer<mtb_debug> dbg;
+  DeviceBuffer<uint64_t> sig_hits, sig_shadow;
+  DeviceBuffer<uint32_t> n_rays;
+  DeviceBuffer<unsigned long long> counters;
+  // intersect scratch
+  DeviceBuffer<double> q_origins, q_dirs, q_t, q_point;
+  DeviceBuffer<int32_t> q_tri;
+};
+
+}  // namespace
+
+struct mtb_context {
+  std::vector<DeviceState> dev;
+  std::string err;
+  uint32_t flags = 0;
+  bool has_scene = false;
+  int part_index = 0, part_count = 1;
+  mtb::FlatScene flat;
+  std::vector<mtb_triangle> triangles;
+  std::vector<mtb_material> materials;
+  std::vector<mtb::LoadedTexture> textures;
+  std::vector<mtb_light> lights;
+  int64_t device_bytes = 0;
+};
+
+namespace {
+
+void DestroyTextures(DeviceState *d) {
+  for (cudaTextureObject_t t : d->tex_handles) cudaDestroyTextureObject(t);
+  for (cudaArray_t a : d->tex_arrays) cudaFreeArray(a);
+  d->tex_handles.clear();
+  d->tex_arrays.clear();
+}
+
+int UploadToDevice(mtb_context *ctx, DeviceState *d) {
+  MTB_CUDA(ctx, cudaSetDevice(d->device));
+  const mtb::FlatScene &f = ctx->flat;
+  MTB_CUDA(ctx, d->nodes.Upload(f.nodes.data(), f.nodes.size(), d->stream));
+  MTB_CUDA(ctx, d->slots.Upload(f.slots.data(), f.slots.size(), d->stream));
+  MTB_CUDA(ctx, d->shade.Upload(f.shade.data(), f.shade.size(), d->stream));
+  MTB_CUDA(ctx, d->bvh.Upload(f.bvh.data(), f.bvh.size(), d->stream));
+  MTB_CUDA(ctx, d->list_order.Upload(f.list_order.data(), f.list_order.size(), d->stream));
+  MTB_CUDA(ctx, d->materials.Upload(ctx->materials.data(), ctx->materials.size(), d->stream));
+  DestroyTextures(d);
+  std::vector<int2> dims;
+  for (const mtb::LoadedTexture &t : ctx->textures) {
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+    cudaArray_t arr = nullptr;
+    MTB_CUDA(ctx, cudaMallocArray(&arr, &desc, (size_t)t.width, (size_t)t.height));
+    d->tex_arrays.push_back(arr);
+    MTB_CUDA(ctx, cudaMemcpy2DToArrayAsync(arr, 0, 0, t.rgba.data(), (size_t)t.width * 4, (size_t)t.width * 4,
+                                           (size_t)t.height, cudaMemcpyHostToDevice, d->stream));
+    cudaResourceDesc res;
+    memset(&res, 0, sizeof(res));
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = arr;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;  // bilinear weights are done in FP64 by the kernel (texture.cc:47-57)
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    cudaTextureObject_t obj = 0;
+    MTB_CUDA(ctx, cudaCreateTextureObject(&obj, &res, &td, nullptr));
+    d->tex_handles.push_back(obj);
+    dims.push_back(make_int2(t.width, t.height));
+  }
+  MTB_CUDA(ctx, d->tex_objects.Upload(d->tex_handles.data(), d->tex_handles.size(), d->stream));
+  MTB_CUDA(ctx, d->tex_dims.Upload(dims.data(), dims.size(), d->stream));
+  MTB_CUDA(ctx, cudaStreamSynchronize(d->stream));
+  d->scene.nodes = d->nodes.ptr;
+  d->scene.slots = d->slots.ptr;
+  d->scene.shade = d->shade.ptr;
+  d->scene.bvh = d->bvh.ptr;
+  d->scene.list_order = d->list_order.ptr;
+  d->scene.materials = d->materials.ptr;
+  d->scene.textures = d->tex_objects.ptr;
+  d->scene.texture_dim = d->tex_dims.ptr;
+  d->scene.n_materials = (int32_t)ctx->materials.size();
+  return MTB_OK;
+}
+
+int UploadLights(mtb_context *ctx, DeviceState *d) {
+  MTB_CUDA(ctx, cudaSetDevice(d->device));
+  MTB_CUDA(ctx, d->lights.Upload(ctx->lights.data(), ctx->lights.size(), d->stream));
+  d->scene.lights = d->lights.ptr;
+  d->scene.n_lights = (int32_t)ctx->lights.size();
+  return MTB_OK;
+}
+
+int BuildAndUpload(mtb_context *ctx) {
+  // material / texture indices are validated here so the kernels never read out of range
+  for (mtb_triangle &t : ctx->triangles) {
+    if (t.material < -1 || t.material >= (int32_t)ctx->materials.size()) {
+      ctx->err = "triangle references a material outside the table";
+      return MTB_ERR_ARG;
+    }
+  }
+  for (mtb_material &m : ctx->materials) {
+    if (m.texture < -1 || m.texture >= (int32_t)ctx->textures.size()) {
+      ctx->err = "material references a texture outside the table";
+      return MTB_ERR_ARG;
+    }
+  }
+  std::string err;
+  const int rc = mtb::BuildFlatScene(ctx->triangles.data(), (int64_t)ctx->triangles.size(),
+                                     (ctx->flags & MTB_FLAG_NO_LIST_BVH) == 0, &ctx->flat, &err);
+  if (rc != MTB_OK) {
+    ctx->err = err;
+    return rc;
+  }
+  ctx->device_bytes = (int64_t)(ctx->flat.nodes.size() * sizeof(mtb::NodeRec) + ctx->flat.slots.size() * sizeof(mtb::SlotRec) +
+                                ctx->flat.shade.size() * sizeof(mtb::ShadeRec) + ctx->flat.bvh.size() * sizeof(mtb::BvhRec) +
+                                ctx->flat.list_order.size() * 4 + ctx->materials.size() * sizeof(mtb_material));
+  for (const mtb::LoadedTexture &t : ctx->textures) ctx->device_bytes += (int64_t)t.rgba.size();
+  for (DeviceState &d : ctx->dev) {
+    const int urc = UploadToDevice(ctx, &d);
+    if (urc != MTB_OK) return urc;
+  }
+  ctx->has_scene = true;
+  return MTB_OK;
+}
+
+void FillStats(const unsigned long long *c, mtb_stats *s) {
+  s->rays = c[mtb::kRays];
+  s->primary = c[mtb::kPrimary];
+  s->shadow = c[mtb::kShadow];
+  s->reflect = c[mtb::kReflect];
+  s->refract = c[mtb::kRefract];
+  s->n_slab = c[mtb::kSlab];
+  s->n_visit = c[mtb::kVisit];
+  s->n_triaabb = c[mtb::kTriAabb];
+  s->n_mt = c[mtb::kMt];
+  s->n_hit = c[mtb::kHit];
+  s->n_shade = c[mtb::kShade];
+  s->n_bvh = c[mtb::kBvh];
+  s->n_literal = c[mtb::kLiteral];
+}
+
+struct StripPlan {
+  int n_strips = 0;   // strips of 8 rows in the chunk
+  int owners = 1;     // part_count * n_devices
+};
+
+// Strips owned by (part p, device g): s % owners == p * n_devices + g.
+int OwnedStrips(const StripPlan &plan, int owner) {
+  if (owner >= plan.n_strips) return 0;
+  return (plan.n_strips - owner + plan.owners - 1) / plan.owners;
+}
+
+// Copies the strips that `owner` rendered from its buffer into device 0's buffer (same layout) with one
+// pitched peer copy (NVLink when peer access is enabled): rows of the 2-D copy are whole strips.
+int GatherStrips(mtb_context *ctx, const StripPlan &plan, int owner, int chunk_w, int chunk_h, size_t elem_bytes,
+                 void *dst_base, const void *src_base, cudaStream_t stream) {
+  const int mine = OwnedStrips(plan, owner);
+  if (mine == 0) return MTB_OK;
+  const size_t strip_bytes = (size_t)8 * chunk_w * elem_bytes;
+  const size_t pitch = strip_bytes * plan.owners;
+  const size_t first = strip_bytes * owner;
+  // all owned strips except possibly a clipped last one
+  int full = mine;
+  const int last_strip = owner + (mine - 1) * plan.owners;
+  const int last_rows = chunk_h - last_strip * 8;
+  if (last_rows < 8) full = mine - 1;
+  if (full > 0) {
+    MTB_CUDA(ctx, cudaMemcpy2DAsync(static_cast<char *>(dst_base) + first, pitch,
+                                    static_cast<const char *>(src_base) + first, pitch, strip_bytes, (size_t)full,
+                                    cudaMemcpyDeviceToDevice, stream));
+  }
+  if (full < mine) {
+    const size_t off = strip_bytes * last_strip;
+    MTB_CUDA(ctx, cudaMemcpyAsync(static_cast<char *>(dst_base) + off, static_cast<const char *>(src_base) + off,
+                                  (size_t)last_rows * chunk_w * elem_bytes, cudaMemcpyDeviceToDevice, stream));
+  }
+  return MTB_OK;
+}
+
+// Core of both render entry points.  d_rgb_user: device-0 buffer to leave the pixels in (may be NULL when
+// rgb_host is given); user_stream: stream of device 0 to enqueue on (NULL = context stream).
+int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h, int chunk_x, int chunk_y,
+               int chunk_w, int chunk_h, int max_depth, uint8_t *rgb_host, void *d_rgb_user, cudaStream_t user_stream,
+               mtb_debug *dbg_host, const mtb_taps *taps, mtb_stats *stats, bool synchronous) {
+  const auto wall0 = std::chrono::steady_clock::now();
+  if (ctx == nullptr) return MTB_ERR_ARG;
+  if (ctx->dev.empty()) {
+    ctx->err = "host-only context: no CUDA device to render on (there is no CPU fallback)";
+    return MTB_ERR_CUDA;
+  }
+  if (!ctx->has_scene) {
+    ctx->err = "no scene uploaded";
+    return MTB_ERR_ARG;
+  }
+  if (cam == nullptr || image_w <= 0 || image_h <= 0 || chunk_w <= 0 || chunk_h <= 0 || chunk_x < 0 || chunk_y < 0 ||
+      max_depth < 0 || max_depth > MTB_MAX_RAY_DEPTH) {
+    ctx->err = "bad render arguments";
+    return MTB_ERR_ARG;
+  }
+  const size_t npx = (size_t)chunk_w * chunk_h;
+  const bool want_taps = taps != nullptr && (taps->sig_hits || taps->sig_shadow || taps->n_rays);
+  const bool debug_build = (ctx->flags & MTB_FLAG_COUNT_WORK) != 0;
+  const int n_dev = (int)ctx->dev.size();
+  StripPlan plan;
+  plan.n_strips = (chunk_h + 7) / 8;
+  plan.owners = ctx->part_count * n_dev;
+
+  mtb::RenderParams rp;
+  memset(&rp, 0, sizeof(rp));
+  mtb::ComputeSensor(*cam, image_w, image_h, rp.sensor);
+  for (int a = 0; a < 3; a++) rp.origin[a] = cam->origin[a];
+  rp.image_w = image_w;
+  rp.image_h = image_h;
+  rp.chunk_x = chunk_x;
+  rp.chunk_y = chunk_y;
+  rp.chunk_w = chunk_w;
+  rp.chunk_h = chunk_h;
+  rp.max_depth = max_depth;
+  rp.tiles_x = (chunk_w + 7) / 8;
+  rp.strip_stride = plan.owners;
+
+  // ---- launch on every device ----
+  for (int g = 0; g < n_dev; g++) {
+    DeviceState &d = ctx->dev[g];
+    MTB_CUDA(ctx, cudaSetDevice(d.device));
+    cudaStream_t s = (g == 0 && user_stream != nullptr) ? user_stream : d.stream;
+    const int owner = ctx->part_index * n_dev + g;
+    mtb::RenderParams p = rp;
+    p.strip_first = owner;
+    const bool direct = (g == 0 && d_rgb_user != nullptr);
+    if (!direct) MTB_CUDA(ctx, d.rgb.Reserve(npx * 3));
+    p.rgb = direct ? static_cast<uint8_t *>(d_rgb_user) : d.rgb.ptr;
+    if (dbg_host != nullptr) {
+      MTB_CUDA(ctx, d.dbg.Reserve(npx));
+      p.dbg = d.dbg.ptr;
+    }
+    if (want_taps) {
+      MTB_CUDA(ctx, d.sig_hits.Reserve(npx));
+      MTB_CUDA(ctx, d.sig_shadow.Reserve(npx));
+      MTB_CUDA(ctx, d.n_rays.Reserve(npx));
+      p.sig_hits = d.sig_hits.ptr;
+      p.sig_shadow = d.sig_shadow.ptr;
+      p.n_rays = d.n_rays.ptr;
+    }
+    MTB_CUDA(ctx, d.counters.Reserve(mtb::kNumCounters));
+    p.counters = d.counters.ptr;
+    if (stats != nullptr || synchronous) {
+      MTB_CUDA(ctx, cudaMemsetAsync(d.counters.ptr, 0, mtb::kNumCounters * sizeof(unsigned long long), s));
+    }
+    const int blocks = OwnedStrips(plan, owner) * rp.tiles_x;
+    // a peer's scratch frame must not be overwritten while device 0 still gathers the previous one
+    if (g > 0) MTB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->dev[0].ev_gathered, 0));
+    MTB_CUDA(ctx, cudaEventRecord(d.ev_start, s));
+    mtb::LaunchRenderMega(d.scene, p, blocks, debug_build, s);
+    MTB_CUDA(ctx, cudaGetLastError());
+    MTB_CUDA(ctx, cudaEventRecord(d.ev_stop, s));
+  }
+
+  // ---- gather on device 0 (peer copies), then device -> host ----
+  DeviceState &d0 = ctx->dev[0];
+  MTB_CUDA(ctx, cudaSetDevice(d0.device));
+  cudaStream_t s0 = user_stream != nullptr ? user_stream : d0.stream;
+  uint8_t *rgb0 = d_rgb_user != nullptr ? static_cast<uint8_t *>(d_rgb_user) : d0.rgb.ptr;
+  for (int g = 1; g < n_dev; g++) {
+    DeviceState &d = ctx->dev[g];
+    const int owner = ctx->part_index * n_dev + g;
+    MTB_CUDA(ctx, cudaStreamWaitEvent(s0, d.ev_stop, 0));
+    int rc = GatherStrips(ctx, plan, owner, chunk_w, chunk_h, 3, rgb0, d.rgb.ptr, s0);
+    if (rc != MTB_OK) return rc;
+    if (dbg_host != nullptr) {
+      rc = GatherStrips(ctx, plan, owner, chunk_w, chunk_h, sizeof(mtb_debug), d0.dbg.ptr, d.dbg.ptr, s0);
+      if (rc != MTB_OK) return rc;
+    }
+    if (want_taps) {
+      rc = GatherStrips(ctx, plan, owner, chunk_w, chunk_h, 8, d0.sig_hits.ptr, d.sig_hits.ptr, s0);
+      if (rc == MTB_OK) rc = GatherStrips(ctx, plan, owner, chunk_w, chunk_h, 8, d0.sig_shadow.ptr, d.sig_shadow.ptr, s0);
+      if (rc == MTB_OK) rc = GatherStrips(ctx, plan, owner, chunk_w, chunk_h, 4, d0.n_rays.ptr, d.n_rays.ptr, s0);
+      if (rc != MTB_OK) return rc;
+    }
+  }
+  if (n_dev > 1) MTB_CUDA(ctx, cudaEventRecord(d0.ev_gathered, s0));
+  if (rgb_host != nullptr) MTB_CUDA(ctx, cudaMemcpyAsync(rgb_host, rgb0, npx * 3, cudaMemcpyDeviceToHost, s0));
+  if (dbg_host != nullptr) {
+    MTB_CUDA(ctx, cudaMemcpyAsync(dbg_host, d0.dbg.ptr, npx * sizeof(mtb_debug), cudaMemcpyDeviceToHost, s0));
+  }
+  if (want_taps) {
+    if (taps->sig_hits) MTB_CUDA(ctx, cudaMemcpyAsync(taps->sig_hits, d0.sig_hits.ptr, npx * 8, cudaMemcpyDeviceToHost, s0));
+    if (taps->sig_shadow) MTB_CUDA(ctx, cudaMemcpyAsync(taps->sig_shadow, d0.sig_shadow.ptr, npx * 8, cudaMemcpyDeviceToHost, s0));
+    if (taps->n_rays) MTB_CUDA(ctx, cudaMemcpyAsync(taps->n_rays, d0.n_rays.ptr, npx * 4, cudaMemcpyDeviceToHost, s0));
+  }
+  if (!synchronous && stats == nullptr) return MTB_OK;
+
+  MTB_CUDA(ctx, cudaStreamSynchronize(s0));
+  if (stats != nullptr) {
+    unsigned long long total[mtb::kNumCounters];
+    memset(total, 0, sizeof(total));
+    double kernel_ms = 0.0;
+    for (int g = 0; g < n_dev; g++) {
+      DeviceState &d = ctx->dev[g];
+      MTB_CUDA(ctx, cudaSetDevice(d.device));
+      cudaStream_t s = (g == 0 && user_stream != nullptr) ? user_stream : d.stream;
+      MTB_CUDA(ctx, cudaStreamSynchronize(s));
+      unsigned long long c[mtb::kNumCounters];
+      MTB_CUDA(ctx, cudaMemcpy(c, d.counters.ptr, sizeof(c), cudaMemcpyDeviceToHost));
+      for (int i = 0; i < mtb::kNumCounters; i++) total[i] += c[i];
+      float ms = 0.f;
+      MTB_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev_start, d.ev_stop));
+      if (ms > kernel_ms) kernel_ms = ms;  // devices run concurrently: the frame takes the slowest
+    }
+    memset(stats, 0, sizeof(*stats));
+    FillStats(total, stats);
+    stats->kernel_ms = kernel_ms;
+    stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+  }
+  return MTB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mtb_version(void) { return "mythtracer_b200 0.1 (sm_100a)"; }
+
+int mtb_create(mtb_context **out, const int *devices, int n_devices) {
+  if (out == nullptr) return MTB_ERR_ARG;
+  *out = nullptr;
+  int available = 0;
+  cudaError_t e = cudaGetDeviceCount(&available);
+  if (e != cudaSuccess || available == 0) {
+    g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0");
+    return MTB_ERR_CUDA;
+  }
+  mtb_context *ctx = new mtb_context;
+  const int n = (devices == nullptr || n_devices <= 0) ? 1 : n_devices;
+  ctx->dev.resize((size_t)n);
+  for (int g = 0; g < n; g++) {
+    DeviceState &d = ctx->dev[(size_t)g];
+    d.device = (devices == nullptr || n_devices <= 0) ? 0 : devices[g];
+    if (d.device < 0 || d.device >= available) {
+      g_create_error = "device ordinal out of range";
+      delete ctx;
+      return MTB_ERR_ARG;
+    }
+    if ((e = cudaSetDevice(d.device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&d.ev_start)) != cudaSuccess || (e = cudaEventCreate(&d.ev_stop)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&d.ev_gathered, cudaEventDisableTiming)) != cudaSuccess) {
+      g_create_error = std::string("device setup failed: ") + cudaGetErrorString(e);
+      delete ctx;
+      return MTB_ERR_CUDA;
+    }
+  }
+  // NVLink peer access towards device 0, the gather target
+  for (int g = 1; g < n; g++) {
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, ctx->dev[0].device, ctx->dev[(size_t)g].device);
+    if (can) {
+      cudaSetDevice(ctx->dev[0].device);
+      e = cudaDeviceEnablePeerAccess(ctx->dev[(size_t)g].device, 0);
+      if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) ctx->dev[(size_t)g].peer_to_dev0 = true;
+      cudaGetLastError();
+    }
+  }
+  *out = ctx;
+  return MTB_OK;
+}
+
+int mtb_create_host(mtb_context **out) {
+  if (out == nullptr) return MTB_ERR_ARG;
+  *out = new mtb_context;
+  return MTB_OK;
+}
+
+void mtb_destroy(mtb_context *ctx) {
+  if (ctx == nullptr) return;
+  for (DeviceState &d : ctx->dev) {
+    cudaSetDevice(d.device);
+    if (d.stream != nullptr) cudaStreamSynchronize(d.stream);
+    DestroyTextures(&d);
+    d.nodes.Free();
+    d.slots.Free();
+    d.shade.Free();
+    d.bvh.Free();
+    d.list_order.Free();
+    d.materials.Free();
+    d.tex_objects.Free();
+    d.tex_dims.Free();
+    d.lights.Free();
+    d.rgb.Free();
+    d.dbg.Free();
+    d.sig_hits.Free();
+    d.sig_shadow.Free();
+    d.n_rays.Free();
+    d.counters.Free();
+    d.q_origins.Free();
+    d.q_dirs.Free();
+    d.q_t.Free();
+    d.q_point.Free();
+    d.q_tri.Free();
+    if (d.ev_start != nullptr) cudaEventDestroy(d.ev_start);
+    if (d.ev_stop != nullptr) cudaEventDestroy(d.ev_stop);
+    if (d.ev_gathered != nullptr) cudaEventDestroy(d.ev_gathered);
+    if (d.stream != nullptr) cudaStreamDestroy(d.stream);
+  }
+  delete ctx;
+}
+
+const char *mtb_last_error(const mtb_context *ctx) { return ctx == nullptr ? g_create_error.c_str() : ctx->err.c_str(); }
+
+int mtb_device_count(const mtb_context *ctx) { return ctx == nullptr ? 0 : (int)ctx->dev.size(); }
+
+int mtb_scene_upload(mtb_context *ctx, const mtb_triangle *tris, int64_t n_tris, const mtb_material *mtls,
+                     int32_t n_mtls, const mtb_texture *texs, int32_t n_texs) {
+  if (ctx == nullptr || n_tris < 0 || n_mtls < 0 || n_texs < 0 || (n_tris > 0 && tris == nullptr) ||
+      (n_mtls > 0 && mtls == nullptr) || (n_texs > 0 && texs == nullptr)) {
+    if (ctx != nullptr) ctx->err = "bad scene arguments";
+    return MTB_ERR_ARG;
+  }
+  ctx->has_scene = false;
+  ctx->triangles.assign(tris, tris + n_tris);
+  ctx->materials.assign(mtls, mtls + n_mtls);
+  ctx->textures.clear();
+  for (int32_t i = 0; i < n_texs; i++) {
+    if (texs[i].width <= 0 || texs[i].height <= 0 || texs[i].rgba == nullptr) {
+      ctx->err = "bad texture";
+      return MTB_ERR_ARG;
+    }
+    mtb::LoadedTexture t;
+    t.width = texs[i].width;
+    t.height = texs[i].height;
+    t.rgba.assign(texs[i].rgba, texs[i].rgba + (size_t)t.width * t.height * 4);
+    ctx->textures.push_back(std::move(t));
+  }
+  return BuildAndUpload(ctx);
+}
+
+int mtb_load_obj(mtb_context *ctx, const char *path) {
+  if (ctx == nullptr || path == nullptr) return MTB_ERR_ARG;
+  mtb::LoadedScene loaded;
+  std::string err;
+  ctx->has_scene = false;
+  if (!mtb::LoadObjFile(path, &loaded, &err)) {
+    ctx->err = err;
+    fprintf(stderr, "error: %s\n", err.c_str());
+    return MTB_ERR_IO;
+  }
+  ctx->triangles.swap(loaded.triangles);
+  ctx->materials.swap(loaded.materials);
+  ctx->textures.swap(loaded.textures);
+  return BuildAndUpload(ctx);
+}
+
+int mtb_set_lights(mtb_context *ctx, const mtb_light *lights, int32_t n) {
+  if (ctx == nullptr || n < 0 || (n > 0 && lights == nullptr)) return MTB_ERR_ARG;
+  ctx->lights.assign(lights, lights + n);
+  for (DeviceState &d : ctx->dev) {
+    const int rc = UploadLights(ctx, &d);
+    if (rc != MTB_OK) return rc;
+    // the render may be enqueued on a caller stream: make the new lights visible first
+    MTB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  }
+  return MTB_OK;
+}
+
+int mtb_scene_info(const mtb_context *ctx, mtb_scene_summary *out) {
+  if (ctx == nullptr || out == nullptr) return MTB_ERR_ARG;
+  memset(out, 0, sizeof(*out));
+  out->n_triangles = (int64_t)ctx->triangles.size();
+  out->n_nodes = (int64_t)ctx->flat.nodes.size();
+  out->n_bvh_nodes = (int64_t)ctx->flat.bvh.size();
+  out->tree_depth = ctx->flat.depth;
+  out->n_materials = (int32_t)ctx->materials.size();
+  out->n_textures = (int32_t)ctx->textures.size();
+  out->n_lights = (int32_t)ctx->lights.size();
+  out->root_list = ctx->flat.root_list;
+  out->biggest_list = ctx->flat.biggest_list;
+  out->interior_triangles = ctx->flat.interior;
+  for (int a = 0; a < 3; a++) {
+    out->aabb_min[a] = ctx->flat.aabb[a];
+    out->aabb_max[a] = ctx->flat.aabb[3 + a];
+  }
+  out->device_bytes = ctx->device_bytes;
+  return MTB_OK;
+}
+
+int mtb_scene_read(const mtb_context *ctx, mtb_triangle *tris, mtb_material *mtls) {
+  if (ctx == nullptr) return MTB_ERR_ARG;
+  if (tris != nullptr && !ctx->triangles.empty()) memcpy(tris, ctx->triangles.data(), ctx->triangles.size() * sizeof(mtb_triangle));
+  if (mtls != nullptr && !ctx->materials.empty()) memcpy(mtls, ctx->materials.data(), ctx->materials.size() * sizeof(mtb_material));
+  return MTB_OK;
+}
+
+int mtb_scene_triangle_nodes(const mtb_context *ctx, double *node_box, int32_t *node_depth) {
+  if (ctx == nullptr) return MTB_ERR_ARG;
+  const mtb::FlatScene &f = ctx->flat;
+  std::vector<int32_t> depth(f.nodes.size(), 0);
+  for (size_t i = 0; i < f.nodes.size(); i++) {
+    const mtb::NodeRec &n = f.nodes[i];
+    if (n.first_child >= 0) {
+      for (int k = 0; k < 8; k++) depth[(size_t)n.first_child + k] = depth[i] + 1;
+    }
+    for (int32_t k = 0; k < n.list_count; k++) {
+      const int32_t tri = f.slots[(size_t)(n.list_first + k)].tri;
+      if (node_depth != nullptr) node_depth[tri] = depth[i];
+      if (node_box != nullptr) {
+        for (int a = 0; a < 3; a++) {
+          node_box[(size_t)tri * 6 + a] = n.planes[a];
+          node_box[(size_t)tri * 6 + 3 + a] = n.planes[6 + a];
+        }
+      }
+    }
+  }
+  return MTB_OK;
+}
+
+int mtb_set_flags(mtb_context *ctx, uint32_t flags) {
+  if (ctx == nullptr) return MTB_ERR_ARG;
+  const bool rebuild = ((ctx->flags ^ flags) & MTB_FLAG_NO_LIST_BVH) != 0 && ctx->has_scene;
+  ctx->flags = flags;
+  return rebuild ? BuildAndUpload(ctx) : MTB_OK;
+}
+
+int mtb_set_partition(mtb_context *ctx, int part_index, int part_count) {
+  if (ctx == nullptr || part_count < 1 || part_index < 0 || part_index >= part_count) return MTB_ERR_ARG;
+  ctx->part_index = part_index;
+  ctx->part_count = part_count;
+  return MTB_OK;
+}
+
+int mtb_render_chunk(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h, int chunk_x, int chunk_y,
+                     int chunk_w, int chunk_h, int max_depth, uint8_t *rgb_out, mtb_debug *dbg_out,
+                     const mtb_taps *taps, mtb_stats *stats) {
+  if (ctx != nullptr && rgb_out == nullptr) {
+    ctx->err = "rgb_out is NULL";
+    return MTB_ERR_ARG;
+  }
+  return RenderImpl(ctx, cam, image_w, image_h, chunk_x, chunk_y, chunk_w, chunk_h, max_depth, rgb_out, nullptr, nullptr,
+                    dbg_out, taps, stats, true);
+}
+
+int mtb_render_chunk_device(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h, int chunk_x,
+                            int chunk_y, int chunk_w, int chunk_h, int max_depth, void *d_rgb, void *stream,
+                            mtb_stats *stats) {
+  if (ctx != nullptr && d_rgb == nullptr) {
+    ctx->err = "d_rgb is NULL";
+    return MTB_ERR_ARG;
+  }
+  return RenderImpl(ctx, cam, image_w, image_h, chunk_x, chunk_y, chunk_w, chunk_h, max_depth, nullptr, d_rgb,
+                    static_cast<cudaStream_t>(stream), nullptr, nullptr, stats, false);
+}
+
+int mtb_read_counters(mtb_context *ctx, mtb_stats *stats) {
+  if (ctx == nullptr || stats == nullptr) return MTB_ERR_ARG;
+  unsigned long long total[mtb::kNumCounters];
+  memset(total, 0, sizeof(total));
+  for (DeviceState &d : ctx->dev) {
+    MTB_CUDA(ctx, cudaSetDevice(d.device));
+    MTB_CUDA(ctx, cudaDeviceSynchronize());
+    if (d.counters.ptr == nullptr) continue;
+    unsigned long long c[mtb::kNumCounters];
+    MTB_CUDA(ctx, cudaMemcpy(c, d.counters.ptr, sizeof(c), cudaMemcpyDeviceToHost));
+    MTB_CUDA(ctx, cudaMemset(d.counters.ptr, 0, sizeof(c)));
+    for (int i = 0; i < mtb::kNumCounters; i++) total[i] += c[i];
+  }
+  memset(stats, 0, sizeof(*stats));
+  FillStats(total, stats);
+  return MTB_OK;
+}
+
+int mtb_intersect_rays(mtb_context *ctx, int64_t n, const double *origins, const double *dirs, int32_t *tri_index,
+                       double *t, double *point, mtb_stats *stats) {
+  const auto wall0 = std::chrono::steady_clock::now();
+  if (ctx == nullptr) return MTB_ERR_ARG;
+  if (ctx->dev.empty()) {
+    ctx->err = "host-only context: no CUDA device to intersect on (there is no CPU fallback)";
+    return MTB_ERR_CUDA;
+  }
+  if (!ctx->has_scene) {
+    ctx->err = "no scene uploaded";
+    return MTB_ERR_ARG;
+  }
+  if (n < 0 || (n > 0 && (origins == nullptr || dirs == nullptr || tri_index == nullptr))) {
+    ctx->err = "bad intersect arguments";
+    return MTB_ERR_ARG;
+  }
+  if (stats != nullptr) memset(stats, 0, sizeof(*stats));
+  if (n == 0) return MTB_OK;
+  DeviceState &d = ctx->dev[0];
+  MTB_CUDA(ctx, cudaSetDevice(d.device));
+  const size_t sn = (size_t)n;
+  MTB_CUDA(ctx, d.q_origins.Upload(origins, sn * 3, d.stream));
+  MTB_CUDA(ctx, d.q_dirs.Upload(dirs, sn * 3, d.stream));
+  MTB_CUDA(ctx, d.q_tri.Reserve(sn));
+  MTB_CUDA(ctx, d.q_t.Reserve(sn));
+  MTB_CUDA(ctx, d.q_point.Reserve(sn * 3));
+  MTB_CUDA(ctx, d.counters.Reserve(mtb::kNumCounters));
+  MTB_CUDA(ctx, cudaMemsetAsync(d.counters.ptr, 0, mtb::kNumCounters * sizeof(unsigned long long), d.stream));
+  mtb::IntersectParams ip;
+  ip.n = n;
+  ip.origins = d.q_origins.ptr;
+  ip.dirs = d.q_dirs.ptr;
+  ip.tri_index = d.q_tri.ptr;
+  ip.t = d.q_t.ptr;
+  ip.point = d.q_point.ptr;
+  ip.counters = d.counters.ptr;
+  MTB_CUDA(ctx, cudaEventRecord(d.ev_start, d.stream));
+  mtb::LaunchIntersect(d.scene, ip, (ctx->flags & MTB_FLAG_COUNT_WORK) != 0, d.stream);
+  MTB_CUDA(ctx, cudaGetLastError());
+  MTB_CUDA(ctx, cudaEventRecord(d.ev_stop, d.stream));
+  MTB_CUDA(ctx, cudaMemcpyAsync(tri_index, d.q_tri.ptr, sn * 4, cudaMemcpyDeviceToHost, d.stream));
+  if (t != nullptr) MTB_CUDA(ctx, cudaMemcpyAsync(t, d.q_t.ptr, sn * 8, cudaMemcpyDeviceToHost, d.stream));
+  if (point != nullptr) MTB_CUDA(ctx, cudaMemcpyAsync(point, d.q_point.ptr, sn * 24, cudaMemcpyDeviceToHost, d.stream));
+  MTB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  if (stats != nullptr) {
+    unsigned long long c[mtb::kNumCounters];
+    MTB_CUDA(ctx, cudaMemcpy(c, d.counters.ptr, sizeof(c), cudaMemcpyDeviceToHost));
+    FillStats(c, stats);
+    if (stats->rays == 0) stats->rays = (uint64_t)n;
+    float ms = 0.f;
+    MTB_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev_start, d.ev_stop));
+    stats->kernel_ms = ms;
+    stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+  }
+  return MTB_OK;
+}
+
+int mtb_camera_sensor(const mtb_camera *cam, int image_w, int image_h, double out9[9]) {
+  if (cam == nullptr || out9 == nullptr || image_w <= 0 || image_h <= 0) return MTB_ERR_ARG;
+  mtb::ComputeSensor(*cam, image_w, image_h, out9);
+  return MTB_OK;
+}
+
+}  // extern "C"

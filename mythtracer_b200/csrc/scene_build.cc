@@ -1,0 +1,328 @@
+// Reference-exact octree construction, flattened for the GPU (see scene_build.h).
+//
+// What must be identical to the reference, because it decides results:
+//   * triangle boxes = exact min/max of the three vertices      (primitive_triangle.cc:18-24, aabb.cc:42-47)
+//   * the root box grows from {0,0,0}-{0,0,0}                    (math3d.h:141, octtree.cc:12-13)
+//   * a node is split iff it holds >= 16 primitives, no depth cap (octtree.h:43, octtree.cc:53-55)
+//   * centre = lo + (hi - lo) / 2.0                               (octtree.cc:46-50)
+//   * child k: bit0 -> upper x half, bit1 -> upper z half, bit2 -> upper y half   (octtree.cc:61-100)
+//   * a primitive moves to the FIRST child whose closed box holds both corners of its box, otherwise it
+//     stays; order inside every list = insertion order             (octtree.cc:106-129, aabb.cc:5-7,29-33)
+// What is free (it only affects speed): the order of nodes in memory, the order of slots inside a list
+// (ties are decided by the insertion index stored in every slot) and the list-BVH.
+#include "scene_build.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace mtb {
+namespace {
+
+struct Box3 {
+  double lo[3], hi[3];
+};
+
+struct BuildNode {
+  Box3 box;
+  double c[3] = {0, 0, 0};
+  int32_t first_child = -1;
+  int32_t level = 0;
+  std::vector<int32_t> list;  // insertion indices, ascending
+};
+
+inline bool HoldsBox(const Box3 &outer, const Box3 &inner) {
+  for (int a = 0; a < 3; a++) {
+    if (!(inner.lo[a] >= outer.lo[a] && inner.lo[a] <= outer.hi[a])) return false;
+    if (!(inner.hi[a] >= outer.lo[a] && inner.hi[a] <= outer.hi[a])) return false;
+  }
+  return true;
+}
+
+// Work-list formulation of Node::AttemptSplit: nodes are appended to `nodes`, eight at a time.
+int SplitAll(const std::vector<Box3> &tri_box, std::vector<BuildNode> *nodes, int32_t *depth, std::string *err) {
+  std::vector<int32_t> todo;
+  todo.push_back(0);
+  std::vector<int32_t> keep;
+  while (!todo.empty()) {
+    const int32_t idx = todo.back();
+    todo.pop_back();
+    if ((*nodes)[idx].level > *depth) *depth = (*nodes)[idx].level;
+    if ((*nodes)[idx].list.size() < 16) continue;
+    if ((*nodes)[idx].level >= MTB_MAX_TREE_DEPTH) {
+      *err = "octree deeper than MTB_MAX_TREE_DEPTH (16 or more coincident primitives?)";
+      return MTB_ERR_LIMIT;
+    }
+    const int32_t first = (int32_t)nodes->size();
+    nodes->resize(nodes->size() + 8);
+    BuildNode &n = (*nodes)[idx];
+    n.first_child = first;
+    for (int a = 0; a < 3; a++) n.c[a] = n.box.lo[a] + (n.box.hi[a] - n.box.lo[a]) / 2.0;
+    for (int k = 0; k < 8; k++) {
+      BuildNode &ch = (*nodes)[first + k];
+      ch.level = n.level + 1;
+      const int upper[3] = {k & 1, (k >> 2) & 1, (k >> 1) & 1};  // x <- bit0, y <- bit2, z <- bit1
+      for (int a = 0; a < 3; a++) {
+        ch.box.lo[a] = upper[a] ? n.c[a] : n.box.lo[a];
+        ch.box.hi[a] = upper[a] ? n.box.hi[a] : n.c[a];
+      }
+    }
+    keep.clear();
+    for (int32_t t : n.list) {
+      int k = 0;
+      for (; k < 8; k++) {
+        if (HoldsBox((*nodes)[first + k].box, tri_box[t])) break;
+      }
+      if (k < 8) {
+        (*nodes)[first + k].list.push_back(t);
+      } else {
+        keep.push_back(t);
+      }
+    }
+    n.list.assign(keep.begin(), keep.end());
+    n.list.shrink_to_fit();
+    for (int k = 7; k >= 0; k--) todo.push_back(first + k);
+  }
+  return MTB_OK;
+}
+
+// Median-split BVH over `ids[b, e)`; emits records depth first and the slot order of the triangles.
+struct BvhBuilder {
+  const std::vector<Box3> &tri_box;
+  std::vector<BvhRec> *out;
+  std::vector<int32_t> ids;  // triangles of the current list; permuted in place into leaf order
+  int32_t slot_base = 0;
+
+  void Build(int32_t b, int32_t e) {
+    const int32_t me = (int32_t)out->size();
+    out->emplace_back();
+    Box3 u;
+    double clo[3], chi[3];
+    for (int a = 0; a < 3; a++) {
+      u.lo[a] = clo[a] = INFINITY;
+      u.hi[a] = chi[a] = -INFINITY;
+    }
+    for (int32_t i = b; i < e; i++) {
+      const Box3 &tb = tri_box[ids[i]];
+      for (int a = 0; a < 3; a++) {
+        u.lo[a] = std::min(u.lo[a], tb.lo[a]);
+        u.hi[a] = std::max(u.hi[a], tb.hi[a]);
+        const double cc = tb.lo[a] + tb.hi[a];
+        clo[a] = std::min(clo[a], cc);
+        chi[a] = std::max(chi[a], cc);
+      }
+    }
+    BvhRec rec;
+    memset(&rec, 0, sizeof(rec));
+    for (int a = 0; a < 3; a++) {
+      rec.box[a] = u.lo[a];
+      rec.box[3 + a] = u.hi[a];
+    }
+    if (e - b <= kBvhLeafSize) {
+      rec.leaf_first = slot_base + b;
+      rec.leaf_count = e - b;
+      rec.skip = me + 1;
+      (*out)[me] = rec;
+      return;
+    }
+    int axis = 0;
+    if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
+    if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
+    const int32_t mid = b + (e - b) / 2;
+    std::nth_element(ids.begin() + b, ids.begin() + mid, ids.begin() + e, [&](int32_t x, int32_t y) {
+      const double cx = tri_box[x].lo[axis] + tri_box[x].hi[axis];
+      const double cy = tri_box[y].lo[axis] + tri_box[y].hi[axis];
+      return cx < cy || (cx == cy && x < y);
+    });
+    Build(b, mid);
+    Build(mid, e);
+    rec.skip = (int32_t)out->size();
+    (*out)[me] = rec;
+  }
+};
+
+}  // namespace
+
+int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, FlatScene *out, std::string *err) {
+  if (n < 0 || n > 0x3fffffff) {
+    *err = "triangle count out of range";
+    return MTB_ERR_ARG;
+  }
+  std::vector<Box3> tri_box((size_t)n);
+  std::vector<BuildNode> nodes(1);
+  for (int a = 0; a < 3; a++) nodes[0].box.lo[a] = nodes[0].box.hi[a] = 0.0;
+  nodes[0].list.resize((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    Box3 &b = tri_box[(size_t)i];
+    const double *v = tris[i].vertex;
+    for (int a = 0; a < 3; a++) {
+      // std::min(a, b) = (b < a) ? b : a and std::max(a, b) = (a < b) ? b : a (aabb.cc:42-47)
+      double lo = v[a], hi = v[a];
+      for (int k = 1; k < 3; k++) {
+        const double x = v[k * 3 + a];
+        lo = (x < lo) ? x : lo;
+        hi = (hi < x) ? x : hi;
+      }
+      b.lo[a] = lo;
+      b.hi[a] = hi;
+      nodes[0].box.lo[a] = (lo < nodes[0].box.lo[a]) ? lo : nodes[0].box.lo[a];
+      nodes[0].box.hi[a] = (nodes[0].box.hi[a] < hi) ? hi : nodes[0].box.hi[a];
+    }
+    nodes[0].list[(size_t)i] = (int32_t)i;
+  }
+  out->depth = 0;
+  const int rc = SplitAll(tri_box, &nodes, &out->depth, err);
+  if (rc != MTB_OK) return rc;
+
+  // ---- flatten ----
+  out->nodes.assign(nodes.size(), NodeRec{});
+  out->slots.assign((size_t)n, SlotRec{});
+  out->shade.assign((size_t)n, ShadeRec{});
+  out->list_order.assign((size_t)n, 0);
+  out->bvh.clear();
+  out->root_list = (int64_t)nodes[0].list.size();
+  out->biggest_list = 0;
+  out->interior = 0;
+  for (int a = 0; a < 3; a++) {
+    out->aabb[a] = nodes[0].box.lo[a];
+    out->aabb[3 + a] = nodes[0].box.hi[a];
+  }
+  std::vector<int32_t> slot_of((size_t)n, -1);
+  BvhBuilder bb{tri_box, &out->bvh, {}, 0};
+  int32_t cursor = 0;
+  for (size_t i = 0; i < nodes.size(); i++) {
+    const BuildNode &bn = nodes[i];
+    NodeRec &nr = out->nodes[i];
+    memset(&nr, 0, sizeof(nr));
+    for (int a = 0; a < 3; a++) {
+      nr.planes[a] = bn.box.lo[a];
+      nr.planes[3 + a] = bn.c[a];
+      nr.planes[6 + a] = bn.box.hi[a];
+    }
+    nr.first_child = bn.first_child;
+    nr.list_first = cursor;
+    nr.list_count = (int32_t)bn.list.size();
+    nr.bvh_root = -1;
+    nr.bvh_end = -1;
+    out->biggest_list = std::max<int64_t>(out->biggest_list, nr.list_count);
+    if (bn.first_child >= 0) out->interior += nr.list_count;
+    const std::vector<int32_t> *order = &bn.list;
+    if (use_list_bvh && nr.list_count >= kBvhMinList) {
+      bb.ids = bn.list;
+      bb.slot_base = cursor;
+      nr.bvh_root = (int32_t)out->bvh.size();
+      bb.Build(0, nr.list_count);
+      nr.bvh_end = (int32_t)out->bvh.size();
+      order = &bb.ids;
+    }
+    for (int32_t k = 0; k < nr.list_count; k++) {
+      const int32_t t = (*order)[(size_t)k];
+      const int32_t s = cursor + k;
+      slot_of[(size_t)t] = s;
+      SlotRec &sr = out->slots[(size_t)s];
+      for (int a = 0; a < 3; a++) {
+        sr.box[a] = tri_box[(size_t)t].lo[a];
+        sr.box[3 + a] = tri_box[(size_t)t].hi[a];
+      }
+      memcpy(sr.vert, tris[t].vertex, sizeof(sr.vert));
+      sr.tri = t;
+      ShadeRec &sh = out->shade[(size_t)s];
+      memcpy(sh.normal, tris[t].normal, sizeof(sh.normal));
+      for (int v = 0; v < 3; v++) {
+        sh.uv[v * 2 + 0] = tris[t].uvw[v * 3 + 0];
+        sh.uv[v * 2 + 1] = tris[t].uvw[v * 3 + 1];
+      }
+      sh.material = tris[t].material;
+      sh.line_no = tris[t].line_no;
+    }
+    for (int32_t k = 0; k < nr.list_count; k++) out->list_order[(size_t)(cursor + k)] = slot_of[(size_t)bn.list[(size_t)k]];
+    cursor += nr.list_count;
+  }
+  // subtree occupancy, children always have larger indices than their parent
+  std::vector<int64_t> subtree(nodes.size(), 0);
+  for (size_t i = nodes.size(); i-- > 0;) {
+    int64_t total = (int64_t)nodes[i].list.size();
+    uint32_t mask = 0;
+    if (nodes[i].first_child >= 0) {
+      for (int k = 0; k < 8; k++) {
+        const int64_t sub = subtree[(size_t)nodes[i].first_child + k];
+        if (sub > 0) mask |= 1u << k;
+        total += sub;
+      }
+    }
+    out->nodes[i].child_mask = mask;
+    subtree[i] = total;
+  }
+  return MTB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Camera::GetSensor / Sensor::Reset (camera.cc:17-63).  Matrix products keep the reference's operand
+// order and left-to-right sums (math3d.h:188-216) so the three vectors come out bit-identical.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct Mat4 {
+  double m[4][4];
+};
+
+Mat4 Mul(const Mat4 &a, const Mat4 &b) {
+  Mat4 r;
+  for (int j = 0; j < 4; j++) {
+    for (int i = 0; i < 4; i++) {
+      r.m[j][i] = a.m[j][0] * b.m[0][i] + a.m[j][1] * b.m[1][i] + a.m[j][2] * b.m[2][i] + a.m[j][3] * b.m[3][i];
+    }
+  }
+  return r;
+}
+
+void Apply(const Mat4 &a, const double in[3], double out[3]) {
+  // math3d.h:210-216 adds m[0][3] to every row; it is always 0 for rotations.
+  const double x = in[0], y = in[1], z = in[2];
+  out[0] = a.m[0][0] * x + a.m[0][1] * y + a.m[0][2] * z + a.m[0][3];
+  out[1] = a.m[1][0] * x + a.m[1][1] * y + a.m[1][2] * z + a.m[0][3];
+  out[2] = a.m[2][0] * x + a.m[2][1] * y + a.m[2][2] * z + a.m[0][3];
+}
+
+double Rad(double deg) { return (deg * M_PI) / 180.0; }
+
+Mat4 RotX(double deg) {
+  const double a = Rad(deg);
+  return Mat4{{{1.0, 0.0, 0.0, 0.0}, {0.0, cos(a), -sin(a), 0.0}, {0.0, sin(a), cos(a), 0.0}, {0.0, 0.0, 0.0, 1.0}}};
+}
+Mat4 RotY(double deg) {
+  const double a = Rad(deg);
+  return Mat4{{{cos(a), 0.0, sin(a), 0.0}, {0.0, 1.0, 0.0, 0.0}, {-sin(a), 0.0, cos(a), 0.0}, {0.0, 0.0, 0.0, 1.0}}};
+}
+Mat4 RotZ(double deg) {
+  const double a = Rad(deg);
+  return Mat4{{{cos(a), -sin(a), 0.0, 0.0}, {sin(a), cos(a), 0.0, 0.0}, {0.0, 0.0, 1.0, 0.0}, {0.0, 0.0, 0.0, 1.0}}};
+}
+
+}  // namespace
+
+void ComputeSensor(const mtb_camera &cam, int image_w, int image_h, double out9[9]) {
+  const double vertical = (double(image_h) / double(image_w)) * cam.aov;  // camera.cc:29
+  const Mat4 left = RotY(cam.aov / 2.0), right = RotY(-cam.aov / 2.0);
+  const Mat4 top = RotZ(vertical / 2.0), bottom = RotZ(-vertical / 2.0);
+  const Mat4 corner_tl = Mul(top, left);
+  const Mat4 corner_tr = Mul(bottom, right);  // the reference pairs "right" with the bottom rotation (camera.cc:38)
+  const Mat4 corner_bl = Mul(bottom, left);
+  const double fwd[3] = {0.0, 0.0, 1.0};
+  double tl[3], tr[3], bl[3];
+  Apply(corner_tl, fwd, tl);
+  Apply(corner_tr, fwd, tr);
+  Apply(corner_bl, fwd, bl);
+  const Mat4 aim = Mul(Mul(RotY(cam.yaw), RotX(cam.pitch)), RotZ(cam.roll));  // camera.cc:48-51
+  Apply(aim, tl, tl);
+  Apply(aim, tr, tr);
+  Apply(aim, bl, bl);
+  for (int a = 0; a < 3; a++) {
+    out9[a] = tl[a];                                  // start_point
+    out9[3 + a] = (bl[a] - tl[a]) / double(image_h);  // delta_scanline
+    out9[6 + a] = (tr[a] - tl[a]) / double(image_w);  // delta_pixel
+  }
+}
+
+}  // namespace mtb

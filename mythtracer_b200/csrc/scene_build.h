@@ -1,0 +1,96 @@
+// Host-side scene preparation: reference-exact octree + flattened, cache-line-aligned device records.
+//
+// Replaces OctTree::AddPrimitive / Finalize / Node::AttemptSplit (reference octtree.cc:8-24,46-135),
+// Triangle::CacheAABB (primitive_triangle.cc:18-24) and the AoS `Triangle` / `Node` objects
+// (primitive_triangle.h:26-29, octtree.h:47-52) with flat arrays that are uploaded to HBM as they are.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "mythtracer_b200.h"
+
+namespace mtb {
+
+// One octree node = one 128-byte line.  The 8 children of a node are contiguous (first_child .. +7) and
+// their boxes are exactly {lo,c} / {c,hi} per axis (octtree.cc:61-100), so a node carries the three
+// planes per axis once instead of eight child boxes.
+struct alignas(128) NodeRec {
+  double planes[9];     // lo.xyz, c.xyz (centre, octtree.cc:46-50), hi.xyz
+  uint32_t child_mask;  // bit k: the subtree of child k holds at least one triangle      (offset 72)
+  int32_t bvh_end;      // one past the last list-BVH record of this list
+  int32_t first_child;  // -1: never split (octtree.cc:53-55)                             (offset 80, int4)
+  int32_t list_first;   // first slot of this node's own primitive list
+  int32_t list_count;
+  int32_t bvh_root;     // first list-BVH record of this list, -1: scan the list linearly
+  int32_t pad_[8];
+};
+static_assert(sizeof(NodeRec) == 128, "NodeRec must be one cache line");
+
+// One triangle as the traversal sees it (exact FP64 AABB + vertices) = one 128-byte line.  Slots of one
+// node list are contiguous; inside a list they are in list-BVH leaf order (or list order without a BVH).
+struct alignas(128) SlotRec {
+  double box[6];   // cached_aabb: lo.xyz, hi.xyz
+  double vert[9];
+  int32_t tri;     // insertion index (decides ties: later in the reference's list order wins)
+  int32_t pad_;
+};
+static_assert(sizeof(SlotRec) == 128, "SlotRec must be one cache line");
+
+// Shading attributes of the triangle in the same slot = one 128-byte line.
+struct alignas(128) ShadeRec {
+  double normal[9];
+  double uv[6];     // u,v of uvw[3] (w is never read downstream: mythtracer.cc:61-62)
+  int32_t material;
+  int32_t line_no;
+};
+static_assert(sizeof(ShadeRec) == 128, "ShadeRec must be one cache line");
+
+// Threaded (stackless) BVH over one long node list, records in depth-first order: on a box hit go to
+// the next record, on a miss jump to `skip`.  Boxes are unions of exact FP64 triangle AABBs.
+struct alignas(64) BvhRec {
+  double box[6];  // lo.xyz, hi.xyz
+  int32_t skip;
+  int32_t leaf_first;  // first slot (leaf only)
+  int32_t leaf_count;  // 0: inner record
+  int32_t pad_;
+};
+static_assert(sizeof(BvhRec) == 64, "BvhRec must be half a cache line");
+
+struct FlatScene {
+  std::vector<NodeRec> nodes;
+  std::vector<SlotRec> slots;
+  std::vector<ShadeRec> shade;
+  std::vector<BvhRec> bvh;
+  std::vector<int32_t> list_order;  // list_order[list_first + k] = slot of the k-th entry in reference order
+  int32_t depth = 0;
+  int64_t root_list = 0, biggest_list = 0, interior = 0;
+  double aabb[6] = {0, 0, 0, 0, 0, 0};
+};
+
+constexpr int kBvhLeafSize = 4;
+constexpr int kBvhMinList = 12;  // shorter lists are scanned linearly
+
+// Returns MTB_OK or an error code with text in *err.
+int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, FlatScene *out, std::string *err);
+
+// Camera::GetSensor / Sensor::Reset (camera.cc:17-63): out9 = start_point, delta_scanline, delta_pixel.
+void ComputeSensor(const mtb_camera &cam, int image_w, int image_h, double out9[9]);
+
+// ObjFileReader::ReadObjFile + MtlFileReader::ReadMtlFile (objreader.cc:201-274,472-549) + a PPM stand-in
+// for Texture::LoadFromFile (texture.cc:60-109; SDL2_image is not available offline).
+struct LoadedTexture {
+  int32_t width = 0, height = 0;
+  std::vector<uint8_t> rgba;
+};
+struct LoadedScene {
+  std::vector<mtb_triangle> triangles;
+  std::vector<mtb_material> materials;
+  std::vector<std::string> material_names;
+  std::vector<LoadedTexture> textures;
+  std::vector<std::string> texture_names;
+};
+bool LoadObjFile(const char *path, LoadedScene *scene, std::string *err);
+
+}  // namespace mtb

@@ -265,6 +265,7 @@ def _write_obj(path, mtl_name, groups):
         f.write("# synthetic scene (mythtracer_b200.scenegen)\n")
         f.write("mtllib %s\n" % mtl_name)
         voff = 0
+        toff = 0
         n_tris = 0
         for mat, (v, n, u, faces), use_uv in groups:
             f.write("o part_%s_%d\n" % (mat, voff))
@@ -275,8 +276,10 @@ def _write_obj(path, mtl_name, groups):
             f.write("usemtl %s\n" % mat)
             fi = faces + voff + 1
             if use_uv:
-                rows = np.repeat(fi, 3, axis=1)
+                ft = faces + toff + 1   # vt entries exist only for textured parts: separate running index
+                rows = np.stack([fi[:, 0], ft[:, 0], fi[:, 0], fi[:, 1], ft[:, 1], fi[:, 1], fi[:, 2], ft[:, 2], fi[:, 2]], 1)
                 f.write(_format_rows("f %d/%d/%d %d/%d/%d %d/%d/%d \n", rows))
+                toff += v.shape[0]
             else:
                 rows = np.repeat(fi, 2, axis=1)
                 f.write(_format_rows("f %d//%d %d//%d %d//%d \n", rows))

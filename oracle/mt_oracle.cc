@@ -680,6 +680,23 @@ void mto_scene_aabb(const mto_scene *s, double out6[6]) {
   }
 }
 
+static void walk_nodes(const mto_scene *s, int32_t idx, int32_t depth, double *node_box, int32_t *node_depth) {
+  const Node &n = s->nodes[idx];
+  for (int32_t p : n.prims) {
+    if (node_depth != nullptr) node_depth[p] = depth;
+    if (node_box != nullptr) {
+      memcpy(node_box + (size_t)p * 6, n.box.lo.v, 24);
+      memcpy(node_box + (size_t)p * 6 + 3, n.box.hi.v, 24);
+    }
+  }
+  if (n.child >= 0)
+    for (int k = 0; k < 8; k++) walk_nodes(s, n.child + k, depth + 1, node_box, node_depth);
+}
+
+void mto_triangle_nodes(const mto_scene *s, double *node_box, int32_t *node_depth) {
+  walk_nodes(s, 0, 0, node_box, node_depth);
+}
+
 int mto_render(const mto_scene *s, const mto_camera *cam, int image_w, int image_h, int chunk_x, int chunk_y,
                int chunk_w, int chunk_h, int max_depth, uint8_t *rgb, int32_t *dbg_line_no, double *dbg_point,
                const mto_taps *taps, mto_stats *stats) {

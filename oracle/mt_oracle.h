@@ -92,6 +92,8 @@ int32_t mto_get_threads(void);
 /* octree shape: nodes, depth, biggest list, root list length, triangles kept in interior nodes */
 void mto_tree_info(const mto_scene *s, int64_t out[5]);
 void mto_scene_aabb(const mto_scene *s, double out6[6]);
+/* per triangle: box (lo.xyz, hi.xyz) and depth of the octree node whose list holds it */
+void mto_triangle_nodes(const mto_scene *s, double *node_box, int32_t *node_depth);
 
 /* MythTracer::RayTrace(WorkChunk*) (mythtracer.cc:280-312) with MAX_RECURSION_LEVEL = max_depth.
  * rgb: chunk_w*chunk_h*3.  dbg_line_no / dbg_point: PerPixelDebugInfo of the primary hit (may be NULL). */

@@ -236,6 +236,7 @@ class Oracle:
             lib.mto_set_lights.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
             lib.mto_tree_info.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
             lib.mto_scene_aabb.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+            lib.mto_triangle_nodes.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
             lib.mto_render.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 7 + [ctypes.c_void_p] * 5
             lib.mto_render_color.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 7 + [ctypes.c_void_p]
             lib.mto_intersect.argtypes = [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 6
@@ -304,6 +305,12 @@ class Oracle:
         out = np.zeros(6)
         self.lib().mto_scene_aabb(self.handle, _ptr(out))
         return out
+
+    def triangle_nodes(self):
+        box = np.zeros((len(self.tris), 6))
+        depth = np.zeros(len(self.tris), np.int32)
+        self.lib().mto_triangle_nodes(self.handle, _ptr(box), _ptr(depth))
+        return box, depth
 
     def render(self, cam, image_w, image_h, chunk=None, depth=5, taps=False, debug=True):
         cx, cy, cw, ch = chunk if chunk is not None else (0, 0, image_w, image_h)

@@ -1,0 +1,243 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): primary-hit ids, hit points, every shadow decision and every ray count
+must agree exactly; RGB is compared byte for byte too -- the one place that can legitimately differ is pow()
+(mythtracer.cc:174: CUDA and glibc differ by <= 2 ulp), so RGB is allowed MAX_RGB_DIFF = 1 LSB on at most
+MAX_RGB_FRACTION of the channels (stated tolerance; north_star allows <= 2/255).  In practice it is 0.
+"""
+import numpy as np
+import pytest
+
+from tests import scenes
+
+pytestmark = pytest.mark.gpu
+
+MAX_RGB_DIFF = 1
+MAX_RGB_FRACTION = 1e-5
+
+
+def _tracer(product_lib, depth, flags=0, devices=None):
+    from mythtracer_b200 import MythTracer
+    return MythTracer(devices=devices, max_depth=depth, flags=flags)
+
+
+def _oracle_for(oracle_mod, mt):
+    """Oracle over exactly the arrays the product loader produced."""
+    tris, mtls = mt.scene_arrays()
+    return tris, mtls
+
+
+def _load_pair(product_lib, oracle_mod, files, depth, flags=0):
+    from mythtracer_b200 import Light
+    mt = _tracer(product_lib, depth, flags)
+    assert mt.LoadObj(files.obj_path), mt.last_error()
+    mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]
+    orc = oracle_mod.Oracle.from_obj(files.obj_path)
+    orc.set_lights(files.lights)
+    return mt, orc
+
+
+def _assert_render_equal(gpu, cpu, what):
+    assert np.array_equal(gpu["line_no"], cpu["line_no"]), "%s: primary hit ids differ at %d pixels" % (
+        what, int((gpu["line_no"] != cpu["line_no"]).sum()))
+    assert np.array_equal(gpu["points"], cpu["points"], equal_nan=True), "%s: hit points differ" % what
+    assert np.array_equal(gpu["n_rays"], cpu["n_rays"]), "%s: per-pixel ray counts differ" % what
+    assert np.array_equal(gpu["sig_hits"], cpu["sig_hits"]), "%s: secondary hit ids differ" % what
+    assert np.array_equal(gpu["sig_shadow"], cpu["sig_shadow"]), "%s: shadow decisions differ" % what
+    diff = np.abs(gpu["rgb"].astype(np.int16) - cpu["rgb"].astype(np.int16))
+    assert diff.max() <= MAX_RGB_DIFF, "%s: max RGB error %d" % (what, diff.max())
+    assert (diff > 0).mean() <= MAX_RGB_FRACTION, "%s: %d channels differ" % (what, int((diff > 0).sum()))
+    for k in ("rays", "primary", "shadow", "reflect", "refract"):
+        if gpu["stats"][k] or k == "rays":
+            assert gpu["stats"][k] == cpu["stats"][k], "%s: %s count %d != %d" % (what, k, gpu["stats"][k], cpu["stats"][k])
+
+
+def test_c1_full_frame(product_lib, oracle_mod, scene_dir):
+    """BASELINE config C1 (2k triangles, 320x240, 1 light, depth 2), every tap compared."""
+    from mythtracer_b200 import MTB_FLAG_COUNT_WORK
+    files, cfg = scenes.config_scene("C1", scene_dir)
+    mt, orc = _load_pair(product_lib, oracle_mod, files, cfg["depth"], MTB_FLAG_COUNT_WORK)
+    w, h = cfg["width"], cfg["height"]
+    gpu = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
+    cpu = orc.render(files.camera, w, h, depth=cfg["depth"], taps=True)
+    _assert_render_equal(gpu, cpu, "C1")
+    assert gpu["stats"]["n_shade"] == cpu["stats"]["n_shade"]
+    # the fast build (no counters) must give the same bytes
+    mt.set_flags(0)
+    fast = mt.render_chunk(files.camera, w, h, 0, 0, w, h)
+    assert np.array_equal(fast["rgb"], gpu["rgb"])
+    assert fast["stats"]["rays"] == cpu["stats"]["rays"]
+
+
+def test_c1_depths_and_lights(product_lib, oracle_mod, scene_dir):
+    """Recursion depth 0..8 and 0..4 lights (main_local.cc's four-light rig) on the C1 scene."""
+    from mythtracer_b200 import Light
+    files, cfg = scenes.config_scene("C1", scene_dir)
+    mt, orc = _load_pair(product_lib, oracle_mod, files, 5)
+    w, h = 160, 120
+    for depth, n_lights in [(0, 1), (1, 2), (3, 0), (5, 4), (8, 3)]:
+        lights = scenes.LIGHT_RIG[:n_lights]
+        mt.max_depth = depth
+        mt.GetScene().lights = [Light.from_tuple(l) for l in lights]
+        orc.set_lights(lights)
+        gpu = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
+        cpu = orc.render(files.camera, w, h, depth=depth, taps=True)
+        _assert_render_equal(gpu, cpu, "C1 depth %d lights %d" % (depth, n_lights))
+
+
+def test_c2_textured(product_lib, oracle_mod, scene_dir):
+    """BASELINE config C2 (100k triangles, map_Ka textures, 2 lights, depth 3) at a test-size resolution."""
+    files, cfg = scenes.config_scene("C2", scene_dir)
+    mt, orc = _load_pair(product_lib, oracle_mod, files, cfg["depth"])
+    w, h = 320, 180
+    gpu = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
+    cpu = orc.render(files.camera, w, h, depth=cfg["depth"], taps=True)
+    _assert_render_equal(gpu, cpu, "C2")
+    info = mt.scene_info()
+    assert info["n_textures"] == 4 and info["n_triangles"] == len(orc.tris)
+
+
+def test_c3_tile_of_full_frame(product_lib, oracle_mod, scene_dir):
+    """BASELINE config C3 (500k triangles, depth 5): WorkChunk tiles of the 1920x1080 frame
+    (main_net_master.cc:24-25 uses 128x128 tiles), compared with the oracle's render of the same tiles."""
+    files, cfg = scenes.config_scene("C3", scene_dir)
+    mt, orc = _load_pair(product_lib, oracle_mod, files, cfg["depth"])
+    W, H = cfg["width"], cfg["height"]
+    for (cx, cy, cw, ch) in [(896, 512, 128, 128), (1792, 1024, 128, 56)]:
+        gpu = mt.render_chunk(files.camera, W, H, cx, cy, cw, ch, debug=True, taps=True)
+        cpu = orc.render(files.camera, W, H, chunk=(cx, cy, cw, ch), depth=cfg["depth"], taps=True)
+        _assert_render_equal(gpu, cpu, "C3 tile %d,%d" % (cx, cy))
+
+
+def test_c3_full_frame_properties(product_lib, oracle_mod, scene_dir):
+    """Full BASELINE size (C3, 1920x1080): properties that do not need the oracle to render 2M pixels --
+    determinism, tiles == whole frame (the master/worker contract), and a random sample of pixels against the
+    oracle rendering them as 1x1 chunks."""
+    files, cfg = scenes.config_scene("C3", scene_dir)
+    mt, orc = _load_pair(product_lib, oracle_mod, files, cfg["depth"])
+    W, H = cfg["width"], cfg["height"]
+    full = mt.render_chunk(files.camera, W, H, 0, 0, W, H, debug=True)
+    again = mt.render_chunk(files.camera, W, H, 0, 0, W, H)
+    assert np.array_equal(full["rgb"], again["rgb"])
+    assert full["stats"]["rays"] == again["stats"]["rays"]
+    # 128x128 tiles, clipped at the edges (main_net_master.cc:202-217)
+    rng = np.random.default_rng(7)
+    tiles = [(x, y) for y in range(0, H, 128) for x in range(0, W, 128)]
+    for i in rng.choice(len(tiles), 12, replace=False):
+        x, y = tiles[i]
+        cw, ch = min(128, W - x), min(128, H - y)
+        tile = mt.render_chunk(files.camera, W, H, x, y, cw, ch)
+        assert np.array_equal(tile["rgb"], full["rgb"][y:y + ch, x:x + cw])
+    for _ in range(400):
+        x, y = int(rng.integers(0, W)), int(rng.integers(0, H))
+        cpu = orc.render(files.camera, W, H, chunk=(x, y, 1, 1), depth=cfg["depth"])
+        assert cpu["line_no"][0, 0] == full["line_no"][y, x]
+        assert np.array_equal(cpu["points"][0, 0], full["points"][y, x], equal_nan=True)
+        assert np.abs(cpu["rgb"][0, 0].astype(int) - full["rgb"][y, x].astype(int)).max() <= MAX_RGB_DIFF
+
+
+def test_lattice_nan_paths(product_lib, oracle_mod, scene_dir):
+    """On-axis camera over integer-lattice boxes: zero direction components, origins on box planes
+    (0 * inf = NaN slab tests), shared-edge ties, transparent stacks.  Exercises the literal traversal."""
+    from mythtracer_b200 import Light, MTB_FLAG_COUNT_WORK
+    path, cam, lights = scenes.lattice_scene(scene_dir)
+    mt = _tracer(product_lib, 5, MTB_FLAG_COUNT_WORK)
+    assert mt.LoadObj(path)
+    mt.GetScene().lights = [Light.from_tuple(l) for l in lights]
+    orc = oracle_mod.Oracle.from_obj(path)
+    orc.set_lights(lights)
+    for (w, h) in [(65, 49), (64, 48)]:   # odd width: the centre column has dir.x == 0 exactly
+        gpu = mt.render_chunk(cam, w, h, 0, 0, w, h, debug=True, taps=True)
+        cpu = orc.render(cam, w, h, depth=5, taps=True)
+        _assert_render_equal(gpu, cpu, "lattice %dx%d" % (w, h))
+    assert gpu["stats"]["n_literal"] >= 0
+    odd = mt.render_chunk(cam, 65, 49, 0, 0, 65, 49)
+    assert odd["stats"]["n_literal"] > 0, "the on-axis column must take the literal traversal"
+
+
+def test_intersect_rays_random(product_lib, oracle_mod, scene_dir):
+    """Batched OctTree::IntersectRay on random interior rays, axis-parallel rays and rays from outside."""
+    files, cfg = scenes.config_scene("C2", scene_dir, scale=0.2)
+    mt, orc = _load_pair(product_lib, oracle_mod, files, 3)
+    rng = np.random.default_rng(11)
+    o, d = scenes.random_rays(rng, orc.aabb(), 40000)
+    # axis-parallel directions (zero components -> +-inf inverse) and un-normalised directions
+    d[:2000] = np.eye(3)[rng.integers(0, 3, 2000)] * rng.choice([-1.0, 1.0], (2000, 1))
+    d[2000:4000] *= rng.uniform(0.1, 7.0, (2000, 1))
+    o[4000:6000] += 1000.0
+    gpu = mt.intersect_rays(o, d)
+    cpu = orc.intersect(o, d)
+    assert np.array_equal(gpu["tri"], cpu["tri"])
+    hit = cpu["tri"] >= 0
+    assert hit.sum() > 10000
+    assert np.array_equal(gpu["t"][hit], cpu["t"][hit])
+    assert np.array_equal(gpu["point"][hit], cpu["point"][hit])
+
+
+def test_list_bvh_is_transparent(product_lib, oracle_mod, scene_dir):
+    """The list-BVH only prunes work: with and without it the results are byte identical."""
+    from mythtracer_b200 import MTB_FLAG_COUNT_WORK, MTB_FLAG_NO_LIST_BVH
+    files, cfg = scenes.config_scene("C2", scene_dir, scale=0.2)
+    mt, orc = _load_pair(product_lib, oracle_mod, files, 3, MTB_FLAG_COUNT_WORK)
+    w, h = 256, 144
+    a = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
+    mt.set_flags(MTB_FLAG_COUNT_WORK | MTB_FLAG_NO_LIST_BVH)
+    b = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
+    for k in ("rgb", "line_no", "n_rays", "sig_hits", "sig_shadow"):
+        assert np.array_equal(a[k], b[k]), k
+    cpu = orc.render(files.camera, w, h, depth=3, taps=True)
+    _assert_render_equal(b, cpu, "no list BVH")
+    # without the BVH the traversal does exactly the reference's triangle tests
+    assert b["stats"]["n_triaabb"] == cpu["stats"]["n_triaabb"]
+    assert b["stats"]["n_mt"] == cpu["stats"]["n_mt"]
+    assert b["stats"]["n_hit"] == cpu["stats"]["n_hit"]
+    assert a["stats"]["n_triaabb"] < b["stats"]["n_triaabb"]
+
+
+def test_reference_octtree_known_answers(product_lib):
+    """The reference's own octtree_test vectors (octtree_test.cc:14-72, with CacheAABB as the loader does)."""
+    from mythtracer_b200 import MythTracer
+    from mythtracer_b200.api import MTL_DTYPE, TRI_DTYPE
+    tris = np.zeros(2, TRI_DTYPE)
+    tris[0]["vertex"] = [1, 1, 0, 1, 0, 0, 0, 0, 0]
+    tris[1]["vertex"] = [1, 1, 1, 1, 0, 1, 0, 0, 1]
+    tris["material"] = -1
+    mt = MythTracer()
+    mt.upload(tris, np.zeros(0, MTL_DTYPE))
+    r = mt.intersect_rays([[0.9, 0.9, -10.0], [0.9, 0.9, 10.0], [5.0, 5.0, 5.0]],
+                          [[0.0, 0.0, 1.0], [0.0, 0.0, -1.0], [0.0, 0.0, 1.0]])
+    assert r["tri"].tolist() == [0, 1, -1]
+    assert r["t"][0] == 10.0 and r["t"][1] == 9.0
+    tri, point, dist = mt.GetScene().tree.IntersectRay([0.9, 0.9, -10.0], [0.0, 0.0, 1.0])
+    assert tri == 0 and dist == 10.0 and point.tolist() == [0.9, 0.9, 0.0]
+
+
+def test_missing_material_and_no_normals(product_lib, oracle_mod, scene_dir):
+    """`usemtl` of an unknown name (mtl == nullptr -> grey n.v shading, mythtracer.cc:49-52) and faces
+    without normals (zero normal vector, primitive_triangle.cc:60)."""
+    from mythtracer_b200 import Light
+    text = "mtllib odd.mtl\n"
+    text += "v 0 0 5\nv 4 0 5\nv 4 4 5\nv 0 4 5\nv 0 0 9\nv 4 0 9\nv 4 4 9\nv 0 4 9\nvn 0 0 -1\n"
+    text += "usemtl matte\nf 1 2 3 \nf 3 4 1 \n"           # no normals
+    text += "usemtl does_not_exist\nf 5//1 6//1 7//1 8//1 \n"  # a quad without material, behind
+    path = scenes.write_obj(scene_dir + "/odd.obj", text, scenes.BASIC_MTL)
+    mt = _tracer(product_lib, 3)
+    assert mt.LoadObj(path)
+    orc = oracle_mod.Oracle.from_obj(path)
+    cam = (2.1, 2.2, -3.0, 0.0, 3.0, 0.0, 100.0)
+    for lights in ([], [(2.0, 2.0, 0.0, 0.2, 0.2, 0.2, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0)]):
+        mt.GetScene().lights = [Light.from_tuple(l) for l in lights]
+        orc.set_lights(lights)
+        gpu = mt.render_chunk(cam, 96, 64, 0, 0, 96, 64, debug=True, taps=True)
+        cpu = orc.render(cam, 96, 64, depth=3, taps=True)
+        _assert_render_equal(gpu, cpu, "odd scene, %d lights" % len(lights))
+
+
+def test_errors_are_reported(product_lib):
+    from mythtracer_b200 import MythTracer, MythTracerError
+    mt = MythTracer()
+    assert mt.LoadObj("/nonexistent/file.obj") is False
+    assert "not found" in mt.last_error()
+    assert mt.RayTrace(32, 32, (0, 0, 0, 0, 0, 0, 90)) is None      # no scene
+    with pytest.raises(MythTracerError):
+        mt.render_chunk((0, 0, 0, 0, 0, 0, 90), 32, 32, 0, 0, 32, 32)

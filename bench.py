@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py -- the measured contract of mythtracer_b200 ("Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels through the C ABI)
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU renderer (oracle/_ref)
+
+Workload: BASELINE.json configs[2] ("C3": ~500k-triangle synthetic interior, 1920x1080, 2 lights, depth 5,
+the configuration the 1080p metric is quoted on; it fits one GPU).  A step = one full frame of the fixed
+BASELINE camera = one pass of the hot path (MythTracer::RayTrace, mythtracer.cc:280-312).
+
+metric   Mrays/s, rays = OctTree::IntersectRay-equivalent queries (primary + shadow segments + reflection
+         + refraction rays), counted on the device; identical to the reference's count (parity tests).
+value    whole-job Mrays/s with everything resident in HBM: K frames rendered into device memory (N > 1:
+         every rank renders its strips of the same frame -- strong scaling -- and the strips are gathered
+         to rank 0 over NCCL inside the timed region), CUDA events, max over ranks.
+e2e      the same metric through the reference-facing call with HOST buffers (mtb_render_chunk: lights
+         and camera go host->device, the RGB24 frame comes back into pinned host memory), per step.
+roofline algorithmic bytes of one frame (SURVEY.md 8d formula over the kernel's own work counters, from
+         the counting build run outside the timed region) / mean kernel time, against the measured HBM
+         copy bandwidth of MEASURED_PEAKS.json.
+cpu_baseline  the unmodified reference (oracle/_ref) on the host cores, on a bounded sample of the same
+         frame (full-width row bands), rays of the sample counted by the oracle restatement.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "C3"
+SCENE_DIR = os.environ.get("MTB_SCENE_DIR", "/tmp/mtb_scenes")
+L2_FLUSH_BYTES = 256 << 20
+FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "B200_PROFILING.md fallback"
+
+
+def alg_bytes(stats) -> float:
+    """operands the reference arithmetic consumes; list-BVH box tests are 48-byte boxes too."""
+    return (48.0 * (stats["n_slab"] + stats["n_triaabb"] + stats.get("n_bvh", 0)) + 72.0 * stats["n_mt"] +
+            384.0 * stats["n_shade"])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for p in self.samples:
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_workload():
+    from mythtracer_b200 import scenegen
+    files, cfg = scenegen.generate_config(WORKLOAD, SCENE_DIR)
+    return files, cfg
+
+
+def config_dict(files, cfg, n_gpus, extra=None):
+    d = {"workload": "%s: %d-triangle synthetic interior (seed %d), %dx%d, %d lights, depth %d, fixed BASELINE camera" % (
+        WORKLOAD, files.n_triangles, cfg["seed"], cfg["width"], cfg["height"], cfg["n_lights"], cfg["depth"]),
+        "triangles": files.n_triangles, "width": cfg["width"], "height": cfg["height"], "lights": cfg["n_lights"],
+        "max_depth": cfg["depth"], "partition": "strips of 8 rows, round-robin over %d GPU(s)" % n_gpus,
+        "l2": "256 MiB device memset between steps (inside the timed region) flushes the 126 MB L2"}
+    if extra:
+        d.update(extra)
+    return d
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ----------------------------------------------------------------------------------------------------
+
+def sample_bands(height, width, n_bands, rows_per_band):
+    """Full-width row bands spread evenly over the frame (the reference renders rectangles only)."""
+    bands = []
+    for i in range(n_bands):
+        y = int((i + 0.5) * height / n_bands) - rows_per_band // 2
+        y = max(0, min(height - rows_per_band, y))
+        bands.append((0, y, width, rows_per_band))
+    return bands
+
+
+def time_reference(files, cfg, target_seconds, steps, warmup):
+    """Times the unmodified reference (oracle/_ref) on a bounded sample of the frame.  Returns dict."""
+    from oracle import oracle_py
+    if not oracle_py.Reference.available():
+        return None
+    ref = oracle_py.Reference(files.obj_path)
+    ref.set_lights(files.lights)
+    threads = ref.threads()
+    W, H = cfg["width"], cfg["height"]
+    # probe: one band, rows = thread count (static OpenMP schedule over rows, mythtracer.cc:292-295)
+    rows = max(8, min(H, threads))
+    probe = ref.render(files.camera, W, H, chunk=(0, H // 2, W, rows), depth=cfg["depth"], debug=False)
+    per_row = probe["seconds"] / rows
+    total_rows = max(rows, int(target_seconds / max(per_row, 1e-9)))
+    n_bands = max(1, min(8, total_rows // rows))
+    rows_per_band = max(rows, min(H // n_bands, total_rows // n_bands))
+    bands = sample_bands(H, W, n_bands, rows_per_band)
+    # rays of the sample: counted by the oracle restatement (bit-identical to the reference, see tests/)
+    orc = oracle_py.Oracle.from_obj(files.obj_path)
+    orc.set_lights(files.lights)
+    rays = 0
+    for b in bands:
+        rays += orc.render(files.camera, W, H, chunk=b, depth=cfg["depth"], debug=False)["stats"]["rays"]
+    times = []
+    for it in range(warmup + steps):
+        t = 0.0
+        for b in bands:
+            t += ref.render(files.camera, W, H, chunk=b, depth=cfg["depth"], debug=False)["seconds"]
+        if it >= warmup:
+            times.append(t)
+    sec = sum(times) / len(times)
+    px = sum(b[2] * b[3] for b in bands)
+    return {"seconds_per_step": sec, "rays_per_step": rays, "pixels": px, "threads": threads,
+            "mrays_s": rays / sec / 1e6,
+            "sample": "%d full-width bands of %d rows (%d of %d pixels, %.2f%% of the frame) of the same frame" % (
+                n_bands, rows_per_band, px, W * H, 100.0 * px / (W * H)),
+            "frame_ms_extrapolated": sec * 1e3 * (W * H) / px}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    files, cfg = load_workload()
+    res = time_reference(files, cfg, target_seconds=4.0, steps=args.steps, warmup=min(args.warmup, 1))
+    if res is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built and /root/reference is absent"}))
+        return 0
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": res["mrays_s"], "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(files, cfg, args.gpus, {"step": "bounded sample: " + res["sample"],
+                                                     "frame_ms_extrapolated": res["frame_ms_extrapolated"]}),
+        "cpu_baseline": {"value": res["mrays_s"], "unit": "Mrays/s", "cores": res["threads"], "kind": "reference",
+                         "sample": res["sample"]},
+        "e2e": {"value": res["mrays_s"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_COUNT_WORK, tiles
+    from mythtracer_b200 import build as mtb_build
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        log("warning: WORLD_SIZE %d != --gpus %d; using WORLD_SIZE" % (world, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    if rank == 0:
+        mtb_build.build()
+    if world > 1:
+        dist.barrier()
+    files, cfg = (load_workload() if rank == 0 else (None, None))
+    if world > 1:
+        dist.barrier()
+        if rank != 0:
+            files, cfg = load_workload()  # reuses the files rank 0 wrote
+    W, H, depth = cfg["width"], cfg["height"], cfg["depth"]
+
+    mt = MythTracer(devices=[local_rank], max_depth=depth)
+    t0 = time.time()
+    if not mt.LoadObj(files.obj_path):
+        raise SystemExit("LoadObj failed: " + mt.last_error())
+    load_s = time.time() - t0
+    mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]
+    mt.push_lights()
+    mt.set_partition(rank, world)
+    info = mt.scene_info()
+
+    stream = torch.cuda.current_stream(dev)
+    hp = tiles.padded_height(H, world)
+    d_local = torch.zeros((hp, W, 3), dtype=torch.uint8, device=dev)
+    d_frame = torch.zeros((hp, W, 3), dtype=torch.uint8, device=dev) if rank == 0 else None
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    h_frame = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+
+    def step_device():
+        flush.zero_()
+        mt.render_device(files.camera, W, H, d_local.data_ptr(), stream.cuda_stream)
+        return tiles.gather_frame(d_local, H, W, rank, world, 0, out=d_frame)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up, then K timed steps (device-resident) ----
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    mt.read_counters()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        frame = step_device()
+    ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    counters = mt.read_counters()
+    t = torch.tensor([elapsed_ms, float(counters["rays"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        elapsed_ms, total_rays = float(tmax[0]), float(tsum[1])
+    else:
+        total_rays = float(t[1])
+    rays_per_frame = total_rays / args.steps
+    value = total_rays / (elapsed_ms * 1e-3) / 1e6
+
+    # ---- kernel-only time of the dominant kernel (RenderMega), this rank, per launch ----
+    kernel_ms = []
+    for _ in range(min(args.steps, 5)):
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        mt.render_device(files.camera, W, H, d_local.data_ptr(), stream.cuda_stream)
+        k1.record(stream)
+        torch.cuda.synchronize(dev)
+        kernel_ms.append(k0.elapsed_time(k1))
+    mt.read_counters()
+    kernel_ms_mean = sum(kernel_ms) / len(kernel_ms)
+
+    # ---- end to end through the host-buffer call (lights + camera H2D, frame D2H into pinned memory) ----
+    h_np = h_frame.numpy()
+    full_chunk_rows = tiles.owned_rows(H, rank, world)
+    for _ in range(2):
+        if world == 1:
+            mt.render_chunk(files.camera, W, H, 0, 0, W, H, out=h_np)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        if world == 1:
+            mt.render_chunk(files.camera, W, H, 0, 0, W, H, out=h_np)
+        else:
+            mt.push_lights()
+            mt.render_device(files.camera, W, H, d_local.data_ptr(), stream.cuda_stream)
+            fr = tiles.gather_frame(d_local, H, W, rank, world, 0, out=d_frame)
+            if rank == 0:
+                h_frame.copy_(fr, non_blocking=True)
+            torch.cuda.synchronize(dev)
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te[0])
+    e2e_value = rays_per_frame * args.steps / e2e_s / 1e6
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- work counters of one frame (counting build, not timed) -> algorithmic bytes ----
+    mt.set_flags(MTB_FLAG_COUNT_WORK)
+    mt.render_device(files.camera, W, H, d_local.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize(dev)
+    work = mt.read_counters()
+    mt.set_flags(0)
+    wt = torch.tensor([float(work[k]) for k in ("n_slab", "n_triaabb", "n_bvh", "n_mt", "n_shade", "n_visit", "n_hit", "rays")],
+                      dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(wt, op=dist.ReduceOp.SUM)
+    work_all = dict(zip(("n_slab", "n_triaabb", "n_bvh", "n_mt", "n_shade", "n_visit", "n_hit", "rays"), [float(x) for x in wt]))
+    my_alg = alg_bytes(work)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    achieved = my_alg / (kernel_ms_mean * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj.get("workload") == WORKLOAD and tj.get("n_gpus", 1) == world:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "RenderMega", "kernel_ms": kernel_ms_mean,
+                "algorithmic_bytes_per_launch": my_alg, "peak_source": peak_src,
+                "note": "algorithmic bytes are served by L1/L2 (broadcast reads of shared nodes); frac > DRAM share is cache reuse",
+                "per_ray": {k: work_all[k] / max(work_all["rays"], 1.0) for k in ("n_slab", "n_visit", "n_triaabb", "n_bvh", "n_mt", "n_hit", "n_shade")}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = time_reference(files, cfg, target_seconds=12.0, steps=1, warmup=0)
+            if r is not None:
+                cpu = {"value": r["mrays_s"], "unit": "Mrays/s", "cores": r["threads"], "kind": "reference",
+                       "sample": r["sample"], "frame_ms_extrapolated": r["frame_ms_extrapolated"]}
+        except Exception as e:  # the baseline is reported, never required
+            log("cpu_baseline failed:", repr(e))
+
+    lights_bytes = 96 * len(files.lights)
+    line = {
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": config_dict(files, cfg, world, {"rays_per_frame": rays_per_frame, "scene_load_s": load_s,
+                                                 "octree_nodes": info["n_nodes"], "tree_depth": info["tree_depth"],
+                                                 "device_scene_bytes": info["device_bytes"]}),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_s * 1e3 / args.steps,
+                "h2d_bytes_per_step": lights_bytes + 256, "d2h_bytes_per_step": W * H * 3},
+        "gpu_launches": args.steps * world,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -797,6 +797,17 @@ void mto_triangle_uvw(const mto_scene *s, int64_t tri, const double point[3], do
 
 void mto_quantize(const double color[3], uint8_t rgb[3]) { quantize(mk(color[0], color[1], color[2]), rgb); }
 
+void mto_math3d(const double a[3], const double b[3], double out[9]) {
+  const V3 va = mk(a[0], a[1], a[2]), vb = mk(b[0], b[1], b[2]);
+  out[0] = std::sqrt(sqrlen(va));  // math3d.h:101-103
+  out[1] = dist(va, vb);
+  out[2] = dot(vb, va);
+  const V3 c = cross(va, vb);
+  const V3 n = normalized(va);
+  memcpy(out + 3, c.v, 24);
+  memcpy(out + 6, n.v, 24);
+}
+
 uint64_t mto_mix64(uint64_t path, uint64_t kind, uint64_t value) { return mix64(path, kind, value); }
 
 }  // extern "C"

@@ -130,6 +130,10 @@ void mto_triangle_uvw(const mto_scene *s, int64_t tri, const double point[3], do
 /* MythTracer::V3DtoRGB (mythtracer.cc:235-241). */
 void mto_quantize(const double color[3], uint8_t rgb[3]);
 
+/* math3d.h known answers (math3d_test.cc:68-89): out = Length(a), a.Distance(b), a.Dot(b), a.Cross(b)[3],
+ * a.DupNorm()[3]  (9 doubles). */
+void mto_math3d(const double a[3], const double b[3], double out[9]);
+
 uint64_t mto_mix64(uint64_t path, uint64_t kind, uint64_t value);
 
 #ifdef __cplusplus

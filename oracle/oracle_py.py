@@ -248,6 +248,7 @@ class Oracle:
             lib.mto_triangle_normal.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
             lib.mto_triangle_uvw.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
             lib.mto_quantize.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+            lib.mto_math3d.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
             lib.mto_mix64.restype = ctypes.c_uint64
             lib.mto_mix64.argtypes = [ctypes.c_uint64] * 3
             lib.mto_set_threads.argtypes = [ctypes.c_int32]
@@ -357,9 +358,10 @@ class Oracle:
             self.lib().mto_intersect(self.handle, n, _ptr(o), _ptr(d), _ptr(tri), _ptr(t), _ptr(p), _ptr(stats))
         return dict(tri=tri, t=t, point=p, stats=dict(zip(STATS_FIELDS, [int(x) for x in stats])))
 
-    def camera_sensor(self, cam, w, h):
+    @classmethod
+    def camera_sensor(cls, cam, w, h):
         out = np.zeros(9)
-        self.lib().mto_camera_sensor(_ptr(make_camera(cam)), w, h, _ptr(out))
+        cls.lib().mto_camera_sensor(_ptr(make_camera(cam)), w, h, _ptr(out))
         return out.reshape(3, 3)
 
     def camera_ray(self, cam, w, h, x, y):
@@ -383,6 +385,14 @@ class Oracle:
         p = np.ascontiguousarray(point, np.float64)
         self.lib().mto_triangle_uvw(self.handle, tri, _ptr(p), _ptr(out))
         return out
+
+
+def math3d(a, b) -> np.ndarray:
+    a = np.ascontiguousarray(a, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    out = np.zeros(9)
+    Oracle.lib().mto_math3d(_ptr(a), _ptr(b), _ptr(out))
+    return out
 
 
 def quantize(color) -> np.ndarray:

@@ -1,0 +1,161 @@
+"""Host-side logic of the product, no GPU needed: the C ABI library loads and exports what the header
+declares, the loader and the octree builder agree with independent implementations, camera / WorkChunk
+(de)serialisation follow the reference's wire forms, and rendering without a device fails loudly."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests import scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(product_lib):
+    from mythtracer_b200 import api
+    header = open(os.path.join(ROOT, "include", "mythtracer_b200.h")).read()
+    declared = set(re.findall(r"\b(mtb_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(api.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert getattr(product_lib, name) is not None
+    assert b"sm_100a" in product_lib.mtb_version()
+
+
+def test_no_cpu_fallback(product_lib):
+    """A context without a device can load and inspect scenes but must refuse to render."""
+    from mythtracer_b200 import MythTracer, MythTracerError
+    files, cfg = scenes.config_scene("C1", "/tmp/mtb_scenes")
+    mt = MythTracer(host_only=True)
+    assert mt.LoadObj(files.obj_path)
+    with pytest.raises(MythTracerError, match="no CPU fallback"):
+        mt.render_chunk(files.camera, 16, 16, 0, 0, 16, 16)
+    with pytest.raises(MythTracerError, match="no CPU fallback"):
+        mt.intersect_rays([[0, 0, 0]], [[0, 0, 1]])
+    assert mt.RayTrace(16, 16, files.camera) is None
+
+
+def test_product_does_not_import_the_oracle():
+    """The product path must never route through oracle/ (checker only)."""
+    pkg = os.path.join(ROOT, "mythtracer_b200")
+    for dirpath, _, names in os.walk(pkg):
+        for n in names:
+            if n.endswith((".py", ".cu", ".cc", ".h")):
+                text = open(os.path.join(dirpath, n), errors="ignore").read()
+                assert "oracle_py" not in text and "mt_oracle" not in text and "libmythtracer_ref" not in text, n
+
+
+@pytest.mark.parametrize("name,scale", [("C1", 1.0), ("C2", 0.1)])
+def test_loader_matches_independent_parser(product_lib, oracle_mod, scene_dir, name, scale):
+    from mythtracer_b200 import MythTracer
+    files, cfg = scenes.config_scene(name, scene_dir, scale)
+    mt = MythTracer(host_only=True)
+    assert mt.LoadObj(files.obj_path)
+    tris, mtls = mt.scene_arrays()
+    ptris, pmtls, ptex = oracle_mod.read_obj(files.obj_path)
+    assert tris.tobytes() == ptris.tobytes()
+    assert mtls.tobytes() == pmtls.tobytes()
+    assert mt.scene_info()["n_textures"] == len(ptex)
+
+
+def test_loader_quirks(product_lib, oracle_mod, scene_dir):
+    """objreader.cc quirks: lost last token, quads, %i indices, 128-byte line pieces, unknown usemtl."""
+    from mythtracer_b200 import MythTracer
+    base = "mtllib q.mtl\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvn 0 0 1\nvt 0.5 0.25\nusemtl matte\n"
+
+    def load(text):
+        path = scenes.write_obj(os.path.join(scene_dir, "q.obj"), base + text, scenes.BASIC_MTL)
+        mt = MythTracer(host_only=True)
+        ok = mt.LoadObj(path)
+        return ok, mt
+
+    ok, mt = load("f 1 2 3\n")                       # no trailing space: third vertex dropped -> rejected
+    assert not ok and "unsupported face count (2)" in mt.last_error()
+    ok, mt = load("f 1 2 3 4\n")                     # quad without trailing space -> ONE triangle
+    assert ok and mt.scene_info()["n_triangles"] == 1
+    ok, mt = load("f 1 2 3 4 \n")                    # proper quad -> (0,1,2) + (2,3,0), same line number
+    tris, _ = mt.scene_arrays()
+    assert ok and len(tris) == 2 and tris["line_no"].tolist() == [8, 8]
+    assert tris[1]["vertex"].tolist() == [1, 1, 0, 0, 1, 0, 0, 0, 0]
+    ok, mt = load("f 0x1//1 02//1 3//1 \n")          # %i accepts hex and octal
+    tris, _ = mt.scene_arrays()
+    assert ok and tris[0]["vertex"].tolist() == [0, 0, 0, 1, 0, 0, 1, 1, 0] and tris[0]["normal"][2] == 1.0
+    ok, mt = load("f 1/1 2/1 3/1 \n")                # v/vt: uvw copied, no normals
+    tris, _ = mt.scene_arrays()
+    assert ok and tris[0]["uvw"][:2].tolist() == [0.5, 0.25] and not tris[0]["normal"].any()
+    ok, mt = load("usemtl nope\nf 1 2 3 \n")         # unknown material -> mtl == nullptr, parsing goes on
+    tris, _ = mt.scene_arrays()
+    assert ok and tris[0]["material"] == -1
+    ok, mt = load("# " + "x" * 200 + "\nf 1 2 3 \n")  # a 203-byte comment line is two fgets pieces (lines 8 and 9)
+    tris, _ = mt.scene_arrays()
+    assert ok and tris[0]["line_no"] == 10
+    ptris, _, _ = oracle_mod.read_obj(os.path.join(scene_dir, "q.obj"))
+    assert ptris.tobytes() == tris.tobytes()
+    ok, mt = load("f 1 2 9 \n")                      # out-of-range index (undefined upstream) is refused
+    assert not ok and "out of range" in mt.last_error()
+
+
+@pytest.mark.parametrize("name,scale", [("C1", 1.0), ("C2", 0.2), ("C4", 0.02)])
+def test_octree_builder_matches_oracle(product_lib, oracle_mod, scene_dir, name, scale):
+    """Same boxes, same list membership, same depth as the reference rules (octtree.cc:46-135)."""
+    from mythtracer_b200 import MythTracer
+    files, cfg = scenes.config_scene(name, scene_dir, scale)
+    mt = MythTracer(host_only=True)
+    assert mt.LoadObj(files.obj_path)
+    tris, mtls = mt.scene_arrays()
+    orc = oracle_mod.Oracle(tris, mtls, [])
+    info, tree = mt.scene_info(), orc.tree_info()
+    assert info["n_nodes"] == tree["nodes"] and info["tree_depth"] == tree["depth"]
+    assert info["root_list"] == tree["root_list"] and info["biggest_list"] == tree["biggest_list"]
+    assert info["interior_triangles"] == tree["interior_tris"]
+    b1, d1 = mt.triangle_nodes()
+    b2, d2 = orc.triangle_nodes()
+    assert np.array_equal(b1, b2) and np.array_equal(d1, d2)
+    assert np.array_equal(orc.aabb(), np.array(info["aabb_min"] + info["aabb_max"]))
+
+
+def test_camera_sensor_and_serialisation(product_lib, oracle_mod):
+    from mythtracer_b200 import Camera
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        cam = Camera(tuple(rng.uniform(-300, 300, 3)), *rng.uniform(-180, 180, 3), rng.uniform(20, 140))
+        w, h = int(rng.integers(16, 4000)), int(rng.integers(16, 2200))
+        t = (*cam.origin, cam.pitch, cam.yaw, cam.roll, cam.aov)
+        assert np.array_equal(cam.GetSensor(w, h), oracle_mod.Oracle.camera_sensor(t, w, h))
+        blob = cam.Serialize()
+        assert len(blob) == Camera.kSerializedSize == 56
+        back = Camera.Deserialize(blob)
+        assert back.Serialize() == blob
+    assert Camera.Deserialize(b"\0" * 55) is None
+
+
+def test_workchunk_wire_forms():
+    """WorkChunk::SerializeInput / DeserializeInput / SerializeOutput / DeserializeOutput (mythtracer.cc:314-429)."""
+    from mythtracer_b200 import WorkChunk
+    c = WorkChunk(1920, 1080, 128, 256, 128, 128)
+    blob = c.SerializeInput()
+    assert blob == np.array([1920, 1080, 128, 256, 128, 128], "<u4").tobytes()
+    d = WorkChunk()
+    assert d.DeserializeInput(blob) and (d.chunk_x, d.chunk_y, d.chunk_width) == (128, 256, 128)
+    for bad in ([0, 1080, 0, 0, 1, 1], [1920, 1080, 1900, 0, 128, 128], [100001, 10, 0, 0, 1, 1], [64, 64, 0, 0, 0, 8]):
+        assert not WorkChunk().DeserializeInput(np.array(bad, "<u4").tobytes())
+    assert not WorkChunk().DeserializeInput(blob[:-1])
+    c.output_bitmap = (np.arange(128 * 128 * 3) % 251).astype(np.uint8).reshape(128, 128, 3)
+    out = c.SerializeOutput()
+    assert out[:4] == np.array([128 * 128 * 3], "<u4").tobytes() and len(out) == 4 + 128 * 128 * 3
+    e = WorkChunk(chunk_width=128, chunk_height=128)
+    assert e.DeserializeOutput(out) and np.array_equal(e.output_bitmap, c.output_bitmap)
+    assert not WorkChunk(chunk_width=64, chunk_height=128).DeserializeOutput(out)
+    assert not e.DeserializeOutput(out[:3])
+
+
+def test_strip_partition_math():
+    from mythtracer_b200 import tiles
+    for h in (1, 7, 8, 9, 270, 1080, 2160):
+        for world in (1, 2, 3, 4, 8):
+            rows = sorted(r for k in range(world) for r in tiles.owned_rows(h, k, world))
+            assert rows == list(range(h))
+            assert tiles.padded_height(h, world) % (8 * world) == 0 and tiles.padded_height(h, world) >= h
+            for k in range(world):
+                assert all(tiles.strip_owner(s, world) == k for s in tiles.owned_strips(h, k, world))

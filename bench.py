@@ -253,7 +253,11 @@ def run_ours(args):
     mt.set_partition(rank, world)
     info = mt.scene_info()
 
-    stream = torch.cuda.current_stream(dev)
+    # a real (non-default) stream: its handle goes through the C ABI, so that the kernels, torch's copies /
+    # collectives and the timing events are all on one stream (torch.cuda.Event only sees torch's stream)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     hp = tiles.padded_height(H, world)
     d_local = torch.zeros((hp, W, 3), dtype=torch.uint8, device=dev)
     d_frame = torch.zeros((hp, W, 3), dtype=torch.uint8, device=dev) if rank == 0 else None
@@ -341,6 +345,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- work counters of one frame (counting build, not timed) -> algorithmic bytes ----
+    mt.read_counters()  # reset
     mt.set_flags(MTB_FLAG_COUNT_WORK)
     mt.render_device(files.camera, W, H, d_local.data_ptr(), stream.cuda_stream)
     torch.cuda.synchronize(dev)

@@ -27,7 +27,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmythtracer_b200.so")
+LIB_PATH = os.environ.get("MTB_LIB_PATH", os.path.join(HERE, "libmythtracer_b200.so"))  # override: development A/B builds
 
 MTB_OK = 0
 MTB_FLAG_COUNT_WORK = 1

@@ -75,6 +75,35 @@ struct DeviceState {
   // intersect scratch
   DeviceBuffer<double> q_origins, q_dirs, q_t, q_point;
   DeviceBuffer<int32_t> q_tri;
+  // wavefront pipeline state (wavefront.cu)
+  DeviceBuffer<double> wf_rq_o[2], wf_rq_d[2], wf_rq_coef[2];
+  DeviceBuffer<unsigned long long> wf_rq_path[2];
+  DeviceBuffer<int32_t> wf_rq_pixel[2];
+  DeviceBuffer<unsigned char> wf_rq_inobj[2];
+  DeviceBuffer<int32_t> wf_ctx_mtl;
+  DeviceBuffer<double> wf_ctx_point, wf_ctx_normal, wf_ctx_surface, wf_ctx_reflected, wf_sh_power;
+  DeviceBuffer<uint32_t> wf_sh_flags;
+  DeviceBuffer<double> wf_act_color;
+  DeviceBuffer<int32_t> wf_act_refl, wf_act_refr, wf_act_mtl;
+  DeviceBuffer<uint32_t> wf_counters;
+  uint32_t *wf_host_counters = nullptr;  // pinned
+  int wf_queue_factor = 2, wf_act_factor = 6;  // capacities in units of the pixel-slot count; grown on overflow
+  mtb::WfBuffers wf{};
+
+  void FreeAll() {
+    nodes.Free(); slots.Free(); shade.Free(); bvh.Free(); list_order.Free(); materials.Free(); tex_objects.Free();
+    tex_dims.Free(); lights.Free(); rgb.Free(); dbg.Free(); sig_hits.Free(); sig_shadow.Free(); n_rays.Free();
+    counters.Free(); q_origins.Free(); q_dirs.Free(); q_t.Free(); q_point.Free(); q_tri.Free();
+    for (int k = 0; k < 2; k++) {
+      wf_rq_o[k].Free(); wf_rq_d[k].Free(); wf_rq_coef[k].Free(); wf_rq_path[k].Free(); wf_rq_pixel[k].Free();
+      wf_rq_inobj[k].Free();
+    }
+    wf_ctx_mtl.Free(); wf_ctx_point.Free(); wf_ctx_normal.Free(); wf_ctx_surface.Free(); wf_ctx_reflected.Free();
+    wf_sh_power.Free(); wf_sh_flags.Free(); wf_act_color.Free(); wf_act_refl.Free(); wf_act_refr.Free();
+    wf_act_mtl.Free(); wf_counters.Free();
+    if (wf_host_counters != nullptr) cudaFreeHost(wf_host_counters);
+    wf_host_counters = nullptr;
+  }
 };
 
 }  // namespace
@@ -147,6 +176,9 @@ int UploadToDevice(mtb_context *ctx, DeviceState *d) {
   d->scene.textures = d->tex_objects.ptr;
   d->scene.texture_dim = d->tex_dims.ptr;
   d->scene.n_materials = (int32_t)ctx->materials.size();
+  // the FP32 cull's error bound assumes coordinates of ordinary magnitude (see kernels.cu, CullBox)
+  const double mac = ctx->flat.max_abs_coord;
+  d->scene.cull_radius = (mac >= 0x1p-10 && mac <= 0x1p20) ? (float)mac * 1.0000002f : 0.0f;
   return MTB_OK;
 }
 
@@ -245,6 +277,108 @@ int GatherStrips(mtb_context *ctx, const StripPlan &plan, int owner, int chunk_w
   return MTB_OK;
 }
 
+// Sizes the wavefront buffers for `slots` pixel slots and the current light count.
+int EnsureWavefront(mtb_context *ctx, DeviceState *d, int slots, int n_lights) {
+  const size_t qcap = (size_t)slots * d->wf_queue_factor;
+  const size_t acap = (size_t)slots * d->wf_act_factor;
+  if (qcap > 0x7fffffffull / 4 || acap > 0x7fffffffull / 4) {
+    ctx->err = "wavefront buffers exceed the 32-bit index range";
+    return MTB_ERR_LIMIT;
+  }
+  for (int k = 0; k < 2; k++) {
+    MTB_CUDA(ctx, d->wf_rq_o[k].Reserve(qcap * 3));
+    MTB_CUDA(ctx, d->wf_rq_d[k].Reserve(qcap * 3));
+    MTB_CUDA(ctx, d->wf_rq_coef[k].Reserve(qcap));
+    MTB_CUDA(ctx, d->wf_rq_path[k].Reserve(qcap));
+    MTB_CUDA(ctx, d->wf_rq_pixel[k].Reserve(qcap));
+    MTB_CUDA(ctx, d->wf_rq_inobj[k].Reserve(qcap));
+    d->wf.rq_o[k] = d->wf_rq_o[k].ptr;
+    d->wf.rq_d[k] = d->wf_rq_d[k].ptr;
+    d->wf.rq_coef[k] = d->wf_rq_coef[k].ptr;
+    d->wf.rq_path[k] = d->wf_rq_path[k].ptr;
+    d->wf.rq_pixel[k] = d->wf_rq_pixel[k].ptr;
+    d->wf.rq_inobj[k] = d->wf_rq_inobj[k].ptr;
+  }
+  MTB_CUDA(ctx, d->wf_ctx_mtl.Reserve(qcap));
+  MTB_CUDA(ctx, d->wf_ctx_point.Reserve(qcap * 3));
+  MTB_CUDA(ctx, d->wf_ctx_normal.Reserve(qcap * 3));
+  MTB_CUDA(ctx, d->wf_ctx_surface.Reserve(qcap * 3));
+  MTB_CUDA(ctx, d->wf_ctx_reflected.Reserve(qcap * 3));
+  const size_t nl = (size_t)(n_lights > 0 ? n_lights : 1);
+  MTB_CUDA(ctx, d->wf_sh_power.Reserve(qcap * 3 * nl));
+  MTB_CUDA(ctx, d->wf_sh_flags.Reserve(qcap * nl));
+  MTB_CUDA(ctx, d->wf_act_color.Reserve(acap * 3));
+  MTB_CUDA(ctx, d->wf_act_refl.Reserve(acap));
+  MTB_CUDA(ctx, d->wf_act_refr.Reserve(acap));
+  MTB_CUDA(ctx, d->wf_act_mtl.Reserve(acap));
+  MTB_CUDA(ctx, d->wf_counters.Reserve(2));
+  if (d->wf_host_counters == nullptr) MTB_CUDA(ctx, cudaMallocHost(reinterpret_cast<void **>(&d->wf_host_counters), 2 * sizeof(uint32_t)));
+  d->wf.ctx_mtl = d->wf_ctx_mtl.ptr;
+  d->wf.ctx_point = d->wf_ctx_point.ptr;
+  d->wf.ctx_normal = d->wf_ctx_normal.ptr;
+  d->wf.ctx_surface = d->wf_ctx_surface.ptr;
+  d->wf.ctx_reflected = d->wf_ctx_reflected.ptr;
+  d->wf.sh_power = d->wf_sh_power.ptr;
+  d->wf.sh_flags = d->wf_sh_flags.ptr;
+  d->wf.act_color = d->wf_act_color.ptr;
+  d->wf.act_refl = d->wf_act_refl.ptr;
+  d->wf.act_refr = d->wf_act_refr.ptr;
+  d->wf.act_mtl = d->wf_act_mtl.ptr;
+  d->wf.counters = d->wf_counters.ptr;
+  d->wf.queue_cap = (int32_t)qcap;
+  d->wf.act_cap = (int32_t)acap;
+  return MTB_OK;
+}
+
+// One frame (this device's strips) through the wavefront pipeline.  The host only reads one counter per
+// level (how many rays the next level holds); everything else stays on the device.
+int RunWavefront(mtb_context *ctx, DeviceState *d, const mtb::RenderParams &p, int n_blocks, bool debug_build,
+                 cudaStream_t s) {
+  const int slots = n_blocks * 64;
+  if (slots <= 0) return MTB_OK;
+  for (int attempt = 0; attempt < 6; attempt++) {
+    const int rc = EnsureWavefront(ctx, d, slots, d->scene.n_lights);
+    if (rc != MTB_OK) return rc;
+    int level_begin[MTB_MAX_RAY_DEPTH + 2];
+    int n = slots, act_base = 0, last_level = 0;
+    bool overflow = false;
+    for (int level = 0; level <= p.max_depth; level++) {
+      last_level = level;
+      level_begin[level] = act_base;
+      MTB_CUDA(ctx, cudaMemsetAsync(d->wf.counters, 0, 2 * sizeof(uint32_t), s));
+      mtb::LaunchWfTraceMain(d->scene, p, d->wf, level, n, act_base, debug_build, s);
+      mtb::LaunchWfShadow(d->scene, p, d->wf, level, n, debug_build, s);
+      mtb::LaunchWfLightSpawn(d->scene, p, d->wf, level, n, act_base, debug_build, s);
+      MTB_CUDA(ctx, cudaGetLastError());
+      if (level == p.max_depth) break;  // no children beyond MAX_RECURSION_LEVEL (mythtracer.cc:181,192)
+      MTB_CUDA(ctx, cudaMemcpyAsync(d->wf_host_counters, d->wf.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      MTB_CUDA(ctx, cudaStreamSynchronize(s));
+      if (d->wf_host_counters[1] != 0u) {
+        overflow = true;
+        break;
+      }
+      const int next = (int)d->wf_host_counters[0];
+      if (next == 0) break;
+      act_base += n;
+      n = next;
+    }
+    if (overflow) {
+      d->wf_queue_factor *= 2;
+      d->wf_act_factor *= 2;
+      continue;  // render the frame again with larger queues
+    }
+    level_begin[last_level + 1] = act_base + n;
+    for (int level = last_level - 1; level >= 0; level--) {
+      mtb::LaunchWfFold(d->scene, d->wf, level_begin[level], level_begin[level + 1], s);
+    }
+    mtb::LaunchWfResolve(p, d->wf, slots, s);
+    MTB_CUDA(ctx, cudaGetLastError());
+    return MTB_OK;
+  }
+  ctx->err = "wavefront queues kept overflowing";
+  return MTB_ERR_LIMIT;
+}
+
 // Core of both render entry points.  d_rgb_user: device-0 buffer to leave the pixels in (may be NULL when
 // rgb_host is given); user_stream: stream of device 0 to enqueue on (NULL = context stream).
 int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h, int chunk_x, int chunk_y,
@@ -319,8 +453,19 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
     // a peer's scratch frame must not be overwritten while device 0 still gathers the previous one
     if (g > 0) MTB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->dev[0].ev_gathered, 0));
     MTB_CUDA(ctx, cudaEventRecord(d.ev_start, s));
-    mtb::LaunchRenderMega(d.scene, p, blocks, debug_build, s);
-    MTB_CUDA(ctx, cudaGetLastError());
+    if ((ctx->flags & MTB_FLAG_WAVEFRONT) != 0) {
+      // the wavefront kernels accumulate the taps with atomics
+      if (want_taps) {
+        MTB_CUDA(ctx, cudaMemsetAsync(d.sig_hits.ptr, 0, npx * 8, s));
+        MTB_CUDA(ctx, cudaMemsetAsync(d.sig_shadow.ptr, 0, npx * 8, s));
+        MTB_CUDA(ctx, cudaMemsetAsync(d.n_rays.ptr, 0, npx * 4, s));
+      }
+      const int wrc = RunWavefront(ctx, &d, p, blocks, debug_build, s);
+      if (wrc != MTB_OK) return wrc;
+    } else {
+      mtb::LaunchRenderMega(d.scene, p, blocks, debug_build, s);
+      MTB_CUDA(ctx, cudaGetLastError());
+    }
     MTB_CUDA(ctx, cudaEventRecord(d.ev_stop, s));
   }
 
@@ -444,26 +589,7 @@ void mtb_destroy(mtb_context *ctx) {
     cudaSetDevice(d.device);
     if (d.stream != nullptr) cudaStreamSynchronize(d.stream);
     DestroyTextures(&d);
-    d.nodes.Free();
-    d.slots.Free();
-    d.shade.Free();
-    d.bvh.Free();
-    d.list_order.Free();
-    d.materials.Free();
-    d.tex_objects.Free();
-    d.tex_dims.Free();
-    d.lights.Free();
-    d.rgb.Free();
-    d.dbg.Free();
-    d.sig_hits.Free();
-    d.sig_shadow.Free();
-    d.n_rays.Free();
-    d.counters.Free();
-    d.q_origins.Free();
-    d.q_dirs.Free();
-    d.q_t.Free();
-    d.q_point.Free();
-    d.q_tri.Free();
+    d.FreeAll();
     if (d.ev_start != nullptr) cudaEventDestroy(d.ev_start);
     if (d.ev_stop != nullptr) cudaEventDestroy(d.ev_stop);
     if (d.ev_gathered != nullptr) cudaEventDestroy(d.ev_gathered);

@@ -21,6 +21,9 @@ struct DeviceScene {
   const mtb_light *lights;
   int32_t n_lights;
   int32_t n_materials;
+  // FP32 list-BVH cull: largest |coordinate| of the scene box; 0 disables the FP32 path (boxes are then
+  // evaluated in FP64, still conservatively)
+  float cull_radius;
 };
 
 // Work counters, one slot per field of mtb_stats' integer part (same order).
@@ -54,7 +57,40 @@ struct IntersectParams {
   unsigned long long *counters;
 };
 
-// kernels.cu
+// Buffers of the wavefront pipeline (wavefront.cu), all resident in HBM.  A "level" is one generation of
+// TraceRayWorker activations (mythtracer.cc:13): level 0 = primary rays, level L+1 = the reflection and
+// refraction children of level L.  Activations are numbered level by level, so activation id =
+// act_base(level) + position in the level's queue, and ids [0, P) are the pixels.
+struct WfBuffers {
+  // ray queues, ping-pong by level parity: origin, direction (3 doubles each), current_reflection_coef,
+  // path code (1 = root, 2p = reflection child, 2p+1 = refraction child), chunk-local pixel, in_object
+  double *rq_o[2], *rq_d[2], *rq_coef[2];
+  unsigned long long *rq_path[2];
+  int32_t *rq_pixel[2];
+  unsigned char *rq_inobj[2];
+  // per-level scratch, indexed by queue position
+  int32_t *ctx_mtl;  // material index of the hit; < 0: nothing to light (miss or mtl == nullptr)
+  double *ctx_point, *ctx_normal, *ctx_surface, *ctx_reflected;  // 3 doubles each
+  double *sh_power;    // [light][queue position][3]  light_power after the shadow walk
+  uint32_t *sh_flags;  // [light][queue position]     in_shadow | segments << 1
+  // activation table
+  double *act_color;   // 3 doubles: local colour, later the folded colour
+  int32_t *act_refl, *act_refr, *act_mtl;  // child activation ids (-1: none), material of the hit
+  uint32_t *counters;  // [0] rays queued for the next level, [1] overflow flag
+  int32_t queue_cap, act_cap;
+};
+
+// wavefront.cu
+void LaunchWfTraceMain(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
+                       int act_base, bool debug_build, cudaStream_t stream);
+void LaunchWfShadow(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
+                    bool debug_build, cudaStream_t stream);
+void LaunchWfLightSpawn(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
+                        int act_base, bool debug_build, cudaStream_t stream);
+void LaunchWfFold(const DeviceScene &sc, const WfBuffers &wf, int begin, int end, cudaStream_t stream);
+void LaunchWfResolve(const RenderParams &rp, const WfBuffers &wf, int n_slots, cudaStream_t stream);
+
+// megakernel.cu
 void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp, int n_blocks, bool debug_build,
                       cudaStream_t stream);
 void LaunchIntersect(const DeviceScene &sc, const IntersectParams &ip, bool debug_build, cudaStream_t stream);

@@ -1,0 +1,368 @@
+// RenderMega (per-pixel megakernel) and the batched intersect kernel; see device_core.cuh for the traversal.
+#include "device_core.cuh"
+
+namespace mtb {
+namespace {
+
+// One suspended TraceRayWorker activation waiting for its reflection / refraction child.
+struct ShadeFrame {
+  D3 color;
+  D3 point;
+  D3 dir;        // ray.direction of this activation (the refraction child continues along it)
+  double coef;   // current_reflection_coef
+  unsigned long long path;
+  int material;
+  unsigned char stage;      // 0: reflection child pending, 1: refraction child pending
+  unsigned char do_refract;
+  unsigned char in_object;
+  unsigned char pad_;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// RenderMega: one thread = one pixel = the whole TraceRay recursion, evaluated in the reference's
+// post-order so that colour sums associate identically.  Every loop iteration issues exactly one
+// OctTree::IntersectRay-equivalent query (a primary / reflection / refraction ray or one shadow segment),
+// so the lanes of a warp reconverge at the single Trace call site.
+// ---------------------------------------------------------------------------------------------------
+#ifndef MTB_MEGA_MIN_BLOCKS
+#define MTB_MEGA_MIN_BLOCKS 16  // measured on B200 (C3): 1 -> 86 ms, 8 -> 80, 12 -> 66, 16 -> 64 (spills stay in L1)
+#endif
+template <bool DBG>
+__global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega(DeviceScene sc, RenderParams rp) {
+  // block -> 8x8 tile of one of this launch's strips (a strip = 8 image rows; strips are interleaved
+  // across devices / processes, the in-process form of the reference's master/worker tiling)
+  const int strip = rp.strip_first + ((int)blockIdx.x / rp.tiles_x) * rp.strip_stride;
+  const int px = ((int)blockIdx.x % rp.tiles_x) * kTile + (int)(threadIdx.x & 7u);
+  const int py = strip * kTile + (int)(threadIdx.x >> 3);
+  const bool live = px < rp.chunk_w && py < rp.chunk_h;
+
+  unsigned long long cnt_store[DBG ? kNumCounters : 1];
+  unsigned long long *cnt = cnt_store;
+  if (DBG) {
+    for (int i = 0; i < kNumCounters; i++) cnt[i] = 0;
+  }
+  unsigned long long sig_hits = 0, sig_shadow = 0;
+  unsigned n_rays = 0;
+
+  if (live) {
+    ShadeFrame stack[kMaxRayStack];
+    int sp = 0;
+
+    // Sensor::GetRay (camera.cc:65-69) with full-image pixel coordinates (mythtracer.cc:298)
+    const D3 start = Load3(rp.sensor), d_scan = Load3(rp.sensor + 3), d_pixel = Load3(rp.sensor + 6);
+    D3 m_o = Load3(rp.origin);
+    D3 m_d = Normalized(Add(Add(start, MulS(d_scan, (double)(rp.chunk_y + py))), MulS(d_pixel, (double)(rp.chunk_x + px))));
+    int level = 0;
+    bool in_object = false;
+    double coef = 1.0;
+    unsigned long long path = 1;
+    Count<DBG>(cnt, kPrimary);
+
+    // shading context of the current activation (valid while its shadow rays are traced)
+    D3 P = Mk(0, 0, 0), normal = Mk(0, 0, 0), surface = Mk(0, 0, 0), reflected = Mk(0, 0, 0), color = Mk(0, 0, 0);
+    int material = -1;
+    // shadow walk state (mythtracer.cc:86-156)
+    int li = 0;
+    D3 ldir = Mk(0, 0, 0), lpos = Mk(0, 0, 0), power = Mk(0, 0, 0), seg_start = Mk(0, 0, 0);
+    bool in_shadow = false, through = false;
+    unsigned segments = 0;
+    bool shadow_mode = false;
+    D3 final_color = Mk(0, 0, 0);
+
+    for (;;) {
+      D3 to, td;
+      double light_distance = 0.0;
+      if (shadow_mode) {
+        to = Add(seg_start, MulS(ldir, 0.00001));  // mythtracer.cc:95-99
+        td = ldir;
+        light_distance = Dist(seg_start, lpos);    // mythtracer.cc:101-102
+        Count<DBG>(cnt, kShadow);
+      } else {
+        to = m_o;
+        td = m_d;
+      }
+      double t = 0.0;
+      const int slot = Trace<DBG>(sc, to, td, &t, cnt);
+      n_rays++;
+
+      bool have_ret = false;
+      D3 ret = Mk(0.0, 0.0, 0.0);
+      if (shadow_mode) {
+        bool light_done = false;
+        segments++;
+        if (slot < 0) {
+          light_done = true;  // mythtracer.cc:109-112
+        } else if (t > light_distance) {
+          light_done = true;  // mythtracer.cc:115-118
+        } else {
+          const int smtl = __ldg(&sc.shade[slot].material);
+          // mtl is dereferenced unconditionally upstream (mythtracer.cc:121); a missing material acts opaque
+          const double str = smtl >= 0 ? __ldg(&sc.materials[smtl].transparency) : 0.0;
+          if (str == 0.0) {
+            power = Mk(0.0, 0.0, 0.0);
+            in_shadow = true;
+            light_done = true;
+          } else {
+            if (!through) {  // light_power *= Tf * Tr (mythtracer.cc:129-132)
+              const D3 tf = Load3(sc.materials[smtl].transmission_filter);
+              power = MulV(power, MulS(tf, str));
+            }
+            through = !through;
+            const D3 hit_point = Add(to, MulS(td, t));               // primitive_triangle.cc:141
+            seg_start = Add(hit_point, MulS(ldir, 0.0000001));       // mythtracer.cc:137
+            if (SqrDist(P, seg_start) > SqrDist(P, lpos)) {          // mythtracer.cc:141-145
+              light_done = true;
+            } else if (power.x <= 0.001 && power.y <= 0.001 && power.z <= 0.001) {
+              power = Mk(0.0, 0.0, 0.0);
+              in_shadow = true;
+              light_done = true;
+            }
+          }
+        }
+        if (!light_done) continue;  // next segment of the same light
+
+        // ---- this light is settled: Phong terms (mythtracer.cc:159-177) ----
+        const mtb_light *lt = sc.lights + li;
+        const mtb_material *m = sc.materials + material;
+        sig_shadow += Mix64(path, 2ull + (unsigned long long)li, (in_shadow ? 1ull : 0ull) | ((unsigned long long)segments << 1));
+        const D3 lamb = Load3(lt->ambient);
+        power.x = SMax(power.x, lamb.x);
+        power.y = SMax(power.y, lamb.y);
+        power.z = SMax(power.z, lamb.z);
+        color = Add(color, MulV(MulV(MulS(MulV(Load3(m->diffuse), surface), Dot(normal, ldir)), Load3(lt->diffuse)), power));
+        if (!in_shadow) {
+          const double refl_dot = Dot(Neg(m_d), reflected);
+          if (refl_dot > 0) {
+            color = Add(color, MulV(MulS(MulV(Load3(m->specular), surface), pow(refl_dot, m->specular_exp)), Load3(lt->specular)));
+          }
+        }
+        li++;
+      } else {
+        // ---- result of a primary / reflection / refraction ray (mythtracer.cc:13-76) ----
+        if (slot < 0) {
+          if (level == 0 && rp.dbg != nullptr) {
+            mtb_debug *dbg = rp.dbg + (size_t)py * rp.chunk_w + px;
+            dbg->line_no = -1;
+            dbg->pad_ = 0;
+            dbg->point[0] = dbg->point[1] = dbg->point[2] = CUDART_NAN;
+          }
+          have_ret = true;  // background colour {0,0,0}
+        } else {
+          const ShadeRec *sh = sc.shade + slot;
+          const SlotRec *sr = sc.slots + slot;
+          P = Add(to, MulS(td, t));
+          const int line_no = __ldg(&sh->line_no);
+          if (level == 0 && rp.dbg != nullptr) {
+            mtb_debug *dbg = rp.dbg + (size_t)py * rp.chunk_w + px;
+            dbg->line_no = line_no;
+            dbg->pad_ = 0;
+            dbg->point[0] = P.x;
+            dbg->point[1] = P.y;
+            dbg->point[2] = P.z;
+          }
+          sig_hits += Mix64(path, 1ull, (unsigned long long)(long long)line_no);
+          Count<DBG>(cnt, kShade);
+          const D3 v0 = Load3(sr->vert), v1 = Load3(sr->vert + 3), v2 = Load3(sr->vert + 6);
+          const BaryWeights w = Barycentric(v0, v1, v2, P);
+          // (normal[0]*n0 + normal[1]*n1 + normal[2]*n2) / n, not normalised (primitive_triangle.cc:60)
+          normal = DivS(Add(Add(MulS(Load3(sh->normal), w.n0), MulS(Load3(sh->normal + 3), w.n1)), MulS(Load3(sh->normal + 6), w.n2)), w.n);
+          const D3 towards_camera = Neg(m_d);
+          double normal_ray_dot = Dot(towards_camera, normal);
+          if (normal_ray_dot < 0.0) {
+            normal = Neg(normal);
+            normal_ray_dot = Dot(towards_camera, normal);
+          }
+          material = __ldg(&sh->material);
+          if (material < 0) {  // mythtracer.cc:49-52
+            normal_ray_dot = (normal_ray_dot + 1.0) * 0.5;
+            ret = Mk(normal_ray_dot, normal_ray_dot, normal_ray_dot);
+            have_ret = true;
+          } else {
+            const mtb_material *m = sc.materials + material;
+            surface = Load3(m->ambient);
+            const int tex = m->texture;
+            if (tex >= 0) {  // mythtracer.cc:59-64
+              const double u = (sh->uv[0] * w.n0 + sh->uv[2] * w.n1 + sh->uv[4] * w.n2) / w.n;
+              const double v = (sh->uv[1] * w.n0 + sh->uv[3] * w.n1 + sh->uv[5] * w.n2) / w.n;
+              surface = MulV(surface, SampleTexture(sc.textures[tex], sc.texture_dim[tex], u, v));
+            }
+            // ray.direction - normal * (2 * ray.direction.Dot(normal)) (mythtracer.cc:68-69)
+            reflected = Sub(m_d, MulS(normal, 2 * Dot(normal, m_d)));
+            color = Mk(0.0, 0.0, 0.0);
+            li = 0;
+          }
+        }
+      }
+
+      if (!have_ret) {
+        if (li < sc.n_lights) {
+          // ---- start the shadow walk of light li (mythtracer.cc:79-94) ----
+          const mtb_light *lt = sc.lights + li;
+          lpos = Load3(lt->position);
+          ldir = Normalized(Sub(lpos, P));
+          color = Add(color, MulV(Load3(lt->ambient), surface));  // mythtracer.cc:83-84
+          power = Mk(1.0, 1.0, 1.0);
+          in_shadow = false;
+          through = false;
+          segments = 0;
+          seg_start = P;
+          shadow_mode = true;
+          continue;
+        }
+        // ---- all lights done: secondary rays (mythtracer.cc:181-225) ----
+        shadow_mode = false;
+        const mtb_material *m = sc.materials + material;
+        const double refl = m->reflectance, tr = m->transparency;
+        const bool do_reflect = level < rp.max_depth && refl > 0.0 && coef > 0.01 && !in_object;
+        const bool do_refract = level < rp.max_depth && tr > 0.0;
+        if (do_reflect || do_refract) {
+          ShadeFrame &f = stack[sp];
+          f.color = color;
+          f.point = P;
+          f.dir = m_d;
+          f.coef = coef;
+          f.path = path;
+          f.material = material;
+          f.stage = do_reflect ? 0 : 1;
+          f.do_refract = do_refract ? 1 : 0;
+          f.in_object = in_object ? 1 : 0;
+          sp++;
+          level++;
+          if (do_reflect) {
+            Count<DBG>(cnt, kReflect);
+            m_o = Add(P, MulS(reflected, 0.0001));  // mythtracer.cc:70-75
+            m_d = reflected;
+            coef = coef * refl;
+            path = path * 2ull;
+          } else {
+            Count<DBG>(cnt, kRefract);
+            const D3 rdir = Normalized(m_d);       // mythtracer.cc:208-212
+            m_o = Add(P, MulS(rdir, 0.00001));     // mythtracer.cc:214-218
+            m_d = rdir;
+            in_object = !in_object;
+            path = path * 2ull + 1ull;
+          }
+          continue;
+        }
+        ret = color;
+      }
+
+      // ---- an activation returned `ret`: fold it into suspended parents (mythtracer.cc:185-189,220-224) ----
+      bool finished = false;
+      for (;;) {
+        if (sp == 0) {
+          final_color = ret;
+          finished = true;
+          break;
+        }
+        ShadeFrame &f = stack[sp - 1];
+        const mtb_material *m = sc.materials + f.material;
+        if (f.stage == 0) {
+          f.color = Add(f.color, MulS(ret, m->reflectance));
+          if (f.do_refract) {
+            f.stage = 1;
+            Count<DBG>(cnt, kRefract);
+            const D3 rdir = Normalized(f.dir);
+            m_o = Add(f.point, MulS(rdir, 0.00001));
+            m_d = rdir;
+            in_object = !(f.in_object != 0);
+            coef = f.coef;
+            path = f.path * 2ull + 1ull;
+            level = sp;
+            shadow_mode = false;
+            break;  // trace the refraction child
+          }
+          ret = f.color;
+          sp--;
+        } else {
+          // (c * Tf) * Tr (mythtracer.cc:224)
+          f.color = Add(f.color, MulS(MulV(ret, Load3(m->transmission_filter)), m->transparency));
+          ret = f.color;
+          sp--;
+        }
+      }
+      if (finished) break;
+    }
+
+    unsigned char *out = rp.rgb + ((size_t)py * rp.chunk_w + px) * 3;
+    out[0] = QuantizeChannel(final_color.x);
+    out[1] = QuantizeChannel(final_color.y);
+    out[2] = QuantizeChannel(final_color.z);
+    const size_t pix = (size_t)py * rp.chunk_w + px;
+    if (rp.sig_hits != nullptr) rp.sig_hits[pix] = sig_hits;
+    if (rp.sig_shadow != nullptr) rp.sig_shadow[pix] = sig_shadow;
+    if (rp.n_rays != nullptr) rp.n_rays[pix] = n_rays;
+  }
+
+  if (DBG && rp.counters != nullptr) {
+    for (int i = 0; i < kNumCounters; i++) {
+      unsigned long long v = cnt[i];
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+      if ((threadIdx.x & 31u) == 0u && v != 0ull) atomicAdd(rp.counters + i, v);
+    }
+  } else if (rp.counters != nullptr) {
+    // the fast build still reports the ray count (the metric's numerator)
+    unsigned long long v = n_rays;
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31u) == 0u && v != 0ull) atomicAdd(rp.counters + kRays, v);
+  }
+}
+
+// Batched OctTree::IntersectRay (octtree.cc:26-40), one ray per thread.
+template <bool DBG>
+__global__ void __launch_bounds__(128) IntersectKernel(DeviceScene sc, IntersectParams ip) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long cnt_store[DBG ? kNumCounters : 1];
+  unsigned long long *cnt = cnt_store;
+  if (DBG) {
+    for (int k = 0; k < kNumCounters; k++) cnt[k] = 0;
+  }
+  if (i < ip.n) {
+    const D3 o = Load3(ip.origins + i * 3), d = Load3(ip.dirs + i * 3);
+    double t = 0.0;
+    const int slot = Trace<DBG>(sc, o, d, &t, cnt);
+    if (slot < 0) {
+      ip.tri_index[i] = -1;
+    } else {
+      ip.tri_index[i] = sc.slots[slot].tri;
+      if (ip.t != nullptr) ip.t[i] = t;
+      if (ip.point != nullptr) {
+        const D3 p = Add(o, MulS(d, t));
+        ip.point[i * 3 + 0] = p.x;
+        ip.point[i * 3 + 1] = p.y;
+        ip.point[i * 3 + 2] = p.z;
+      }
+    }
+  }
+  if (DBG && ip.counters != nullptr) {
+    for (int k = 0; k < kNumCounters; k++) {
+      unsigned long long v = cnt[k];
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+      if ((threadIdx.x & 31u) == 0u && v != 0ull) atomicAdd(ip.counters + k, v);
+    }
+  }
+}
+
+}  // namespace
+
+void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp, int n_blocks, bool debug_build,
+                      cudaStream_t stream) {
+  if (n_blocks <= 0) return;
+  if (debug_build) {
+    RenderMega<true><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);
+  } else {
+    RenderMega<false><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);
+  }
+}
+
+void LaunchIntersect(const DeviceScene &sc, const IntersectParams &ip, bool debug_build, cudaStream_t stream) {
+  if (ip.n <= 0) return;
+  const int blocks = (int)((ip.n + 127) / 128);
+  if (debug_build) {
+    IntersectKernel<true><<<blocks, 128, 0, stream>>>(sc, ip);
+  } else {
+    IntersectKernel<false><<<blocks, 128, 0, stream>>>(sc, ip);
+  }
+}
+
+}  // namespace mtb

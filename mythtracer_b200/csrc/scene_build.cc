@@ -87,6 +87,18 @@ int SplitAll(const std::vector<Box3> &tri_box, std::vector<BuildNode> *nodes, in
   return MTB_OK;
 }
 
+// double -> float, rounded towards -inf / +inf (the float box must contain the double box)
+inline float RoundDown(double x) {
+  float f = (float)x;
+  if ((double)f > x) f = std::nextafterf(f, -INFINITY);
+  return f;
+}
+inline float RoundUp(double x) {
+  float f = (float)x;
+  if ((double)f < x) f = std::nextafterf(f, INFINITY);
+  return f;
+}
+
 // Median-split BVH over `ids[b, e)`; emits records depth first and the slot order of the triangles.
 struct BvhBuilder {
   const std::vector<Box3> &tri_box;
@@ -116,12 +128,11 @@ struct BvhBuilder {
     BvhRec rec;
     memset(&rec, 0, sizeof(rec));
     for (int a = 0; a < 3; a++) {
-      rec.box[a] = u.lo[a];
-      rec.box[3 + a] = u.hi[a];
+      rec.box[a] = RoundDown(u.lo[a]);
+      rec.box[3 + a] = RoundUp(u.hi[a]);
     }
     if (e - b <= kBvhLeafSize) {
-      rec.leaf_first = slot_base + b;
-      rec.leaf_count = e - b;
+      rec.leaf = ((uint32_t)(slot_base + b) << 3) | (uint32_t)(e - b);
       rec.skip = me + 1;
       (*out)[me] = rec;
       return;
@@ -184,9 +195,11 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, FlatS
   out->root_list = (int64_t)nodes[0].list.size();
   out->biggest_list = 0;
   out->interior = 0;
+  out->max_abs_coord = 0.0;
   for (int a = 0; a < 3; a++) {
     out->aabb[a] = nodes[0].box.lo[a];
     out->aabb[3 + a] = nodes[0].box.hi[a];
+    out->max_abs_coord = std::max(out->max_abs_coord, std::max(std::fabs(nodes[0].box.lo[a]), std::fabs(nodes[0].box.hi[a])));
   }
   std::vector<int32_t> slot_of((size_t)n, -1);
   BvhBuilder bb{tri_box, &out->bvh, {}, 0};

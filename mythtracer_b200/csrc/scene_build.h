@@ -48,15 +48,15 @@ struct alignas(128) ShadeRec {
 static_assert(sizeof(ShadeRec) == 128, "ShadeRec must be one cache line");
 
 // Threaded (stackless) BVH over one long node list, records in depth-first order: on a box hit go to
-// the next record, on a miss jump to `skip`.  Boxes are unions of exact FP64 triangle AABBs.
-struct alignas(64) BvhRec {
-  double box[6];  // lo.xyz, hi.xyz
+// the next record, on a miss jump to `skip`.  A record is a CONSERVATIVE cull only: its FP32 box is the
+// union of the exact FP64 triangle AABBs below it, rounded outwards, and every triangle it lets through is
+// still decided by the exact FP64 reference tests.  32 bytes: four records per 128-byte line.
+struct alignas(32) BvhRec {
+  float box[6];    // lo.xyz rounded down, hi.xyz rounded up
   int32_t skip;
-  int32_t leaf_first;  // first slot (leaf only)
-  int32_t leaf_count;  // 0: inner record
-  int32_t pad_;
+  uint32_t leaf;   // leaf: (first_slot << 3) | count (count 1..kBvhLeafSize); inner record: 0
 };
-static_assert(sizeof(BvhRec) == 64, "BvhRec must be half a cache line");
+static_assert(sizeof(BvhRec) == 32, "BvhRec must be a quarter of a cache line");
 
 struct FlatScene {
   std::vector<NodeRec> nodes;
@@ -67,6 +67,7 @@ struct FlatScene {
   int32_t depth = 0;
   int64_t root_list = 0, biggest_list = 0, interior = 0;
   double aabb[6] = {0, 0, 0, 0, 0, 0};
+  double max_abs_coord = 0.0;  // largest |coordinate| of the scene box (bounds the FP32 cull error)
 };
 
 constexpr int kBvhLeafSize = 4;

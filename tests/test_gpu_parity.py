@@ -318,3 +318,49 @@ def test_multi_device_context(product_lib, scene_dir):
     for k in ("rgb", "line_no", "points", "n_rays", "sig_hits", "sig_shadow"):
         assert np.array_equal(got[k], ref[k], equal_nan=(k == "points")), k
     assert got["stats"]["rays"] == ref["stats"]["rays"]
+
+
+@pytest.mark.parametrize("name,scale,w,h", [("C1", 1.0, 320, 240), ("C2", 0.3, 256, 144)])
+def test_wavefront_pipeline_parity(product_lib, oracle_mod, scene_dir, name, scale, w, h):
+    """The wavefront pipeline (MTB_FLAG_WAVEFRONT) against the oracle, every tap, and against the megakernel."""
+    from mythtracer_b200 import MTB_FLAG_COUNT_WORK, MTB_FLAG_WAVEFRONT
+    files, cfg = scenes.config_scene(name, scene_dir, scale)
+    mt, orc = _load_pair(product_lib, oracle_mod, files, cfg["depth"], MTB_FLAG_WAVEFRONT | MTB_FLAG_COUNT_WORK)
+    gpu = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
+    cpu = orc.render(files.camera, w, h, depth=cfg["depth"], taps=True)
+    _assert_render_equal(gpu, cpu, name + " wavefront")
+    mt.set_flags(MTB_FLAG_WAVEFRONT)
+    fast = mt.render_chunk(files.camera, w, h, 0, 0, w, h)
+    mt.set_flags(0)
+    mega = mt.render_chunk(files.camera, w, h, 0, 0, w, h)
+    assert np.array_equal(fast["rgb"], mega["rgb"]) and np.array_equal(fast["rgb"], gpu["rgb"])
+    assert fast["stats"]["rays"] == mega["stats"]["rays"] == cpu["stats"]["rays"]
+
+
+def test_wavefront_depths_lights_lattice_and_tiles(product_lib, oracle_mod, scene_dir):
+    from mythtracer_b200 import Light, MTB_FLAG_WAVEFRONT
+    files, cfg = scenes.config_scene("C1", scene_dir)
+    mt, orc = _load_pair(product_lib, oracle_mod, files, 5, MTB_FLAG_WAVEFRONT)
+    w, h = 160, 120
+    for depth, n_lights in [(0, 1), (2, 0), (5, 4), (8, 2)]:
+        lights = scenes.LIGHT_RIG[:n_lights]
+        mt.max_depth = depth
+        mt.GetScene().lights = [Light.from_tuple(l) for l in lights]
+        orc.set_lights(lights)
+        gpu = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
+        cpu = orc.render(files.camera, w, h, depth=depth, taps=True)
+        _assert_render_equal(gpu, cpu, "wavefront depth %d lights %d" % (depth, n_lights))
+    # a clipped WorkChunk tile with odd sizes
+    mt.max_depth = 3
+    gpu = mt.render_chunk(files.camera, 333, 211, 100, 37, 77, 45, debug=True, taps=True)
+    cpu = orc.render(files.camera, 333, 211, chunk=(100, 37, 77, 45), depth=3, taps=True)
+    _assert_render_equal(gpu, cpu, "wavefront tile")
+    path, cam, lights = scenes.lattice_scene(scene_dir)
+    mt2 = _tracer(product_lib, 5, MTB_FLAG_WAVEFRONT)
+    assert mt2.LoadObj(path)
+    mt2.GetScene().lights = [Light.from_tuple(l) for l in lights]
+    orc2 = oracle_mod.Oracle.from_obj(path)
+    orc2.set_lights(lights)
+    gpu = mt2.render_chunk(cam, 65, 49, 0, 0, 65, 49, debug=True, taps=True)
+    cpu = orc2.render(cam, 65, 49, depth=5, taps=True)
+    _assert_render_equal(gpu, cpu, "wavefront lattice")

@@ -2,7 +2,7 @@
 import sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from mythtracer_b200 import MythTracer, Light, scenegen, MTB_FLAG_COUNT_WORK, MTB_FLAG_NO_LIST_BVH
+from mythtracer_b200 import MythTracer, Light, scenegen, MTB_FLAG_COUNT_WORK, MTB_FLAG_NO_LIST_BVH, MTB_FLAG_WAVEFRONT
 
 names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["C1", "C2", "C3"]
 modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["bvh"]
@@ -10,7 +10,8 @@ out = []
 for name in names:
     files, cfg = scenegen.generate_config(name, "/tmp/mtb_scenes")
     for mode in modes:
-        mt = MythTracer(max_depth=cfg["depth"], flags=MTB_FLAG_NO_LIST_BVH if mode == "nobvh" else 0)
+        base_flags = {"nobvh": MTB_FLAG_NO_LIST_BVH, "wf": MTB_FLAG_WAVEFRONT}.get(mode, 0)
+        mt = MythTracer(max_depth=cfg["depth"], flags=base_flags)
         t0 = time.time(); assert mt.LoadObj(files.obj_path); t_load = time.time() - t0
         mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]
         w, h = cfg["width"], cfg["height"]
@@ -19,7 +20,7 @@ for name in names:
             r = mt.render_chunk(files.camera, w, h, 0, 0, w, h)
             s = r["stats"]
             if best is None or s["kernel_ms"] < best["kernel_ms"]: best = s
-        mt.set_flags(MTB_FLAG_COUNT_WORK | (MTB_FLAG_NO_LIST_BVH if mode == "nobvh" else 0))
+        mt.set_flags(MTB_FLAG_COUNT_WORK | base_flags)
         c = mt.render_chunk(files.camera, w, h, 0, 0, w, h)["stats"]
         rays = best["rays"]
         rec = dict(config=name, mode=mode, tris=files.n_triangles, w=w, h=h, load_s=round(t_load, 2), kernel_ms=round(best["kernel_ms"], 3),

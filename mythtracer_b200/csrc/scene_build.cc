@@ -87,6 +87,11 @@ int SplitAll(const std::vector<Box3> &tri_box, std::vector<BuildNode> *nodes, in
   return MTB_OK;
 }
 
+inline double HalfArea(const Box3 &b) {
+  const double dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+  return dx * dy + dy * dz + dz * dx;
+}
+
 // double -> float, rounded towards -inf / +inf (the float box must contain the double box)
 inline float RoundDown(double x) {
   float f = (float)x;
@@ -137,15 +142,97 @@ struct BvhBuilder {
       (*out)[me] = rec;
       return;
     }
-    int axis = 0;
-    if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
-    if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
-    const int32_t mid = b + (e - b) / 2;
-    std::nth_element(ids.begin() + b, ids.begin() + mid, ids.begin() + e, [&](int32_t x, int32_t y) {
-      const double cx = tri_box[x].lo[axis] + tri_box[x].hi[axis];
-      const double cy = tri_box[y].lo[axis] + tri_box[y].hi[axis];
-      return cx < cy || (cx == cy && x < y);
-    });
+    // Binned surface-area heuristic over the centroids (16 bins per axis).  Every ray visits every record
+    // whose box it pierces (the cull never prunes by distance), so the expected number of box tests below a
+    // record is proportional to the summed surface areas of its descendants: exactly what SAH minimises.
+    constexpr int kBins = 16;
+    int best_axis = -1, best_bin = -1;
+    double best_cost = INFINITY;
+    for (int axis = 0; axis < 3; axis++) {
+      const double lo = clo[axis], ext = chi[axis] - clo[axis];
+      if (!(ext > 0.0)) continue;
+      Box3 bin_box[kBins];
+      int bin_n[kBins];
+      for (int k = 0; k < kBins; k++) {
+        bin_n[k] = 0;
+        for (int a = 0; a < 3; a++) {
+          bin_box[k].lo[a] = INFINITY;
+          bin_box[k].hi[a] = -INFINITY;
+        }
+      }
+      for (int32_t i = b; i < e; i++) {
+        const Box3 &tb = tri_box[ids[i]];
+        int k = (int)(((tb.lo[axis] + tb.hi[axis]) - lo) / ext * kBins);
+        k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
+        bin_n[k]++;
+        for (int a = 0; a < 3; a++) {
+          bin_box[k].lo[a] = std::min(bin_box[k].lo[a], tb.lo[a]);
+          bin_box[k].hi[a] = std::max(bin_box[k].hi[a], tb.hi[a]);
+        }
+      }
+      double right_area[kBins];
+      int right_n[kBins];
+      Box3 acc;
+      int n_acc = 0;
+      for (int a = 0; a < 3; a++) {
+        acc.lo[a] = INFINITY;
+        acc.hi[a] = -INFINITY;
+      }
+      for (int k = kBins - 1; k > 0; k--) {
+        if (bin_n[k] > 0) {
+          for (int a = 0; a < 3; a++) {
+            acc.lo[a] = std::min(acc.lo[a], bin_box[k].lo[a]);
+            acc.hi[a] = std::max(acc.hi[a], bin_box[k].hi[a]);
+          }
+          n_acc += bin_n[k];
+        }
+        right_area[k] = n_acc > 0 ? HalfArea(acc) : 0.0;
+        right_n[k] = n_acc;
+      }
+      n_acc = 0;
+      for (int a = 0; a < 3; a++) {
+        acc.lo[a] = INFINITY;
+        acc.hi[a] = -INFINITY;
+      }
+      for (int k = 0; k + 1 < kBins; k++) {
+        if (bin_n[k] > 0) {
+          for (int a = 0; a < 3; a++) {
+            acc.lo[a] = std::min(acc.lo[a], bin_box[k].lo[a]);
+            acc.hi[a] = std::max(acc.hi[a], bin_box[k].hi[a]);
+          }
+          n_acc += bin_n[k];
+        }
+        if (n_acc == 0 || right_n[k + 1] == 0) continue;
+        const double cost = HalfArea(acc) * n_acc + right_area[k + 1] * right_n[k + 1];
+        if (cost < best_cost) {
+          best_cost = cost;
+          best_axis = axis;
+          best_bin = k;
+        }
+      }
+    }
+    int32_t mid;
+    if (best_axis >= 0) {
+      const double lo = clo[best_axis], ext = chi[best_axis] - clo[best_axis];
+      auto bin_of = [&](int32_t t) {
+        int k = (int)(((tri_box[t].lo[best_axis] + tri_box[t].hi[best_axis]) - lo) / ext * kBins);
+        return k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
+      };
+      mid = (int32_t)(std::partition(ids.begin() + b, ids.begin() + e, [&](int32_t t) { return bin_of(t) <= best_bin; }) - ids.begin());
+    } else {
+      mid = b;  // all centroids coincide
+    }
+    if (mid == b || mid == e) {
+      int axis = 0;
+      if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
+      if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
+      mid = b + (e - b) / 2;
+      std::nth_element(ids.begin() + b, ids.begin() + mid, ids.begin() + e, [&](int32_t x, int32_t y) {
+        const double cx = tri_box[x].lo[axis] + tri_box[x].hi[axis];
+        const double cy = tri_box[y].lo[axis] + tri_box[y].hi[axis];
+        return cx < cy || (cx == cy && x < y);
+      });
+    }
     Build(b, mid);
     Build(mid, e);
     rec.skip = (int32_t)out->size();

@@ -115,6 +115,7 @@ typedef struct {
 #define MTB_FLAG_COUNT_WORK 1u   /* fill the n_* work counters (counting kernels) */
 #define MTB_FLAG_NO_LIST_BVH 2u  /* scan every node list linearly, like the reference (A/B measurements) */
 #define MTB_FLAG_WAVEFRONT 4u    /* wavefront pipeline instead of the per-pixel megakernel */
+#define MTB_FLAG_NO_RAY_SORT 8u  /* wavefront: keep the queues in spawn order (A/B measurements) */
 
 /* ---- life cycle -------------------------------------------------------------------------------- */
 
@@ -143,6 +144,13 @@ int mtb_set_lights(mtb_context *ctx, const mtb_light *lights, int32_t n);
 int mtb_scene_info(const mtb_context *ctx, mtb_scene_summary *out);
 /* Copies out the host-side triangle / material tables the loader produced (NULL = skip). */
 int mtb_scene_read(const mtb_context *ctx, mtb_triangle *tris, mtb_material *mtls);
+/* What the loader kept besides the tables: names (MaterialMap / TextureMap keys, material.h:50, texture.h:25)
+ * and the decoded RGBA32 texels.  Pointers stay valid until the next scene load on this context. */
+const char *mtb_scene_material_name(const mtb_context *ctx, int32_t index);
+const char *mtb_scene_texture_name(const mtb_context *ctx, int32_t index);
+int mtb_scene_texture(const mtb_context *ctx, int32_t index, mtb_texture *out);
+/* MtlFileReader::ReadMtlFile (objreader.cc:472-549): materials (+ textures) only, no geometry. */
+int mtb_load_mtl(mtb_context *ctx, const char *path);
 /* Octree membership of every triangle (insertion order): the box of the node whose list holds it
  * (6 doubles: lo.xyz, hi.xyz) and that node's depth.  Either pointer may be NULL. */
 int mtb_scene_triangle_nodes(const mtb_context *ctx, double *node_box, int32_t *node_depth);

@@ -33,6 +33,7 @@ MTB_OK = 0
 MTB_FLAG_COUNT_WORK = 1
 MTB_FLAG_NO_LIST_BVH = 2
 MTB_FLAG_WAVEFRONT = 4
+MTB_FLAG_NO_RAY_SORT = 8
 MAX_RECURSION_LEVEL = 5  # reference mythtracer.h:11 (a run-time argument here)
 
 TRI_DTYPE = np.dtype([("vertex", "f8", (9,)), ("normal", "f8", (9,)), ("uvw", "f8", (9,)),
@@ -58,7 +59,8 @@ assert TRI_DTYPE.itemsize == 224 and MTL_DTYPE.itemsize == 136 and DEBUG_DTYPE.i
 # every symbol include/mythtracer_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
     "mtb_create", "mtb_create_host", "mtb_destroy", "mtb_last_error", "mtb_device_count", "mtb_scene_upload", "mtb_load_obj",
-    "mtb_set_lights", "mtb_scene_info", "mtb_scene_read", "mtb_scene_triangle_nodes", "mtb_set_flags", "mtb_set_partition", "mtb_render_chunk",
+    "mtb_set_lights", "mtb_scene_info", "mtb_scene_read", "mtb_scene_material_name", "mtb_scene_texture_name", "mtb_scene_texture", "mtb_load_mtl",
+    "mtb_scene_triangle_nodes", "mtb_set_flags", "mtb_set_partition", "mtb_render_chunk",
     "mtb_render_chunk_device", "mtb_read_counters", "mtb_intersect_rays", "mtb_camera_sensor", "mtb_version",
 ]
 
@@ -90,6 +92,12 @@ def load_library():
     lib.mtb_create.argtypes = [ctypes.POINTER(vp), vp, i32]
     lib.mtb_create_host.argtypes = [ctypes.POINTER(vp)]
     lib.mtb_scene_triangle_nodes.argtypes = [vp, vp, vp]
+    lib.mtb_scene_material_name.argtypes = [vp, ctypes.c_int32]
+    lib.mtb_scene_material_name.restype = ctypes.c_char_p
+    lib.mtb_scene_texture_name.argtypes = [vp, ctypes.c_int32]
+    lib.mtb_scene_texture_name.restype = ctypes.c_char_p
+    lib.mtb_scene_texture.argtypes = [vp, ctypes.c_int32, vp]
+    lib.mtb_load_mtl.argtypes = [vp, ctypes.c_char_p]
     lib.mtb_destroy.argtypes = [vp]
     lib.mtb_destroy.restype = None
     lib.mtb_last_error.argtypes = [vp]

@@ -85,7 +85,8 @@ struct DeviceState {
   DeviceBuffer<uint32_t> wf_sh_flags;
   DeviceBuffer<double> wf_act_color;
   DeviceBuffer<int32_t> wf_act_refl, wf_act_refr, wf_act_mtl;
-  DeviceBuffer<uint32_t> wf_counters;
+  DeviceBuffer<uint32_t> wf_counters, wf_sort_key[2], wf_sort_hist;
+  DeviceBuffer<int32_t> wf_perm;
   uint32_t *wf_host_counters = nullptr;  // pinned
   int wf_queue_factor = 2, wf_act_factor = 6;  // capacities in units of the pixel-slot count; grown on overflow
   mtb::WfBuffers wf{};
@@ -97,7 +98,10 @@ struct DeviceState {
     for (int k = 0; k < 2; k++) {
       wf_rq_o[k].Free(); wf_rq_d[k].Free(); wf_rq_coef[k].Free(); wf_rq_path[k].Free(); wf_rq_pixel[k].Free();
       wf_rq_inobj[k].Free();
+      wf_sort_key[k].Free();
     }
+    wf_sort_hist.Free();
+    wf_perm.Free();
     wf_ctx_mtl.Free(); wf_ctx_point.Free(); wf_ctx_normal.Free(); wf_ctx_surface.Free(); wf_ctx_reflected.Free();
     wf_sh_power.Free(); wf_sh_flags.Free(); wf_act_color.Free(); wf_act_refl.Free(); wf_act_refr.Free();
     wf_act_mtl.Free(); wf_counters.Free();
@@ -118,6 +122,7 @@ struct mtb_context {
   std::vector<mtb_triangle> triangles;
   std::vector<mtb_material> materials;
   std::vector<mtb::LoadedTexture> textures;
+  std::vector<std::string> material_names, texture_names;
   std::vector<mtb_light> lights;
   int64_t device_bytes = 0;
 };
@@ -292,6 +297,8 @@ int EnsureWavefront(mtb_context *ctx, DeviceState *d, int slots, int n_lights) {
     MTB_CUDA(ctx, d->wf_rq_path[k].Reserve(qcap));
     MTB_CUDA(ctx, d->wf_rq_pixel[k].Reserve(qcap));
     MTB_CUDA(ctx, d->wf_rq_inobj[k].Reserve(qcap));
+    MTB_CUDA(ctx, d->wf_sort_key[k].Reserve(qcap));
+    d->wf.sort_key[k] = d->wf_sort_key[k].ptr;
     d->wf.rq_o[k] = d->wf_rq_o[k].ptr;
     d->wf.rq_d[k] = d->wf_rq_d[k].ptr;
     d->wf.rq_coef[k] = d->wf_rq_coef[k].ptr;
@@ -312,6 +319,15 @@ int EnsureWavefront(mtb_context *ctx, DeviceState *d, int slots, int n_lights) {
   MTB_CUDA(ctx, d->wf_act_refr.Reserve(acap));
   MTB_CUDA(ctx, d->wf_act_mtl.Reserve(acap));
   MTB_CUDA(ctx, d->wf_counters.Reserve(2));
+  MTB_CUDA(ctx, d->wf_sort_hist.Reserve((size_t)1 << mtb::kWfSortBits));
+  MTB_CUDA(ctx, d->wf_perm.Reserve(qcap));
+  d->wf.sort_hist = d->wf_sort_hist.ptr;
+  d->wf.perm = d->wf_perm.ptr;
+  for (int a = 0; a < 3; a++) {
+    const double lo = ctx->flat.aabb[a], ext = ctx->flat.aabb[3 + a] - ctx->flat.aabb[a];
+    d->wf.cell_lo[a] = (float)lo;
+    d->wf.cell_scale[a] = ext > 0.0 ? (float)(32.0 / ext) : 0.0f;
+  }
   if (d->wf_host_counters == nullptr) MTB_CUDA(ctx, cudaMallocHost(reinterpret_cast<void **>(&d->wf_host_counters), 2 * sizeof(uint32_t)));
   d->wf.ctx_mtl = d->wf_ctx_mtl.ptr;
   d->wf.ctx_point = d->wf_ctx_point.ptr;
@@ -346,9 +362,11 @@ int RunWavefront(mtb_context *ctx, DeviceState *d, const mtb::RenderParams &p, i
       last_level = level;
       level_begin[level] = act_base;
       MTB_CUDA(ctx, cudaMemsetAsync(d->wf.counters, 0, 2 * sizeof(uint32_t), s));
-      mtb::LaunchWfTraceMain(d->scene, p, d->wf, level, n, act_base, debug_build, s);
-      mtb::LaunchWfShadow(d->scene, p, d->wf, level, n, debug_build, s);
-      mtb::LaunchWfLightSpawn(d->scene, p, d->wf, level, n, act_base, debug_build, s);
+      const bool sorted = level > 0 && (ctx->flags & MTB_FLAG_NO_RAY_SORT) == 0;
+      if (sorted) mtb::LaunchWfSort(d->wf, level, n, s);
+      mtb::LaunchWfTraceMain(d->scene, p, d->wf, level, n, act_base, sorted, debug_build, s);
+      mtb::LaunchWfShadow(d->scene, p, d->wf, level, n, sorted, debug_build, s);
+      mtb::LaunchWfLightSpawn(d->scene, p, d->wf, level, n, act_base, sorted, debug_build, s);
       MTB_CUDA(ctx, cudaGetLastError());
       if (level == p.max_depth) break;  // no children beyond MAX_RECURSION_LEVEL (mythtracer.cc:181,192)
       MTB_CUDA(ctx, cudaMemcpyAsync(d->wf_host_counters, d->wf.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -613,6 +631,8 @@ int mtb_scene_upload(mtb_context *ctx, const mtb_triangle *tris, int64_t n_tris,
   ctx->triangles.assign(tris, tris + n_tris);
   ctx->materials.assign(mtls, mtls + n_mtls);
   ctx->textures.clear();
+  ctx->material_names.clear();
+  ctx->texture_names.clear();
   for (int32_t i = 0; i < n_texs; i++) {
     if (texs[i].width <= 0 || texs[i].height <= 0 || texs[i].rgba == nullptr) {
       ctx->err = "bad texture";
@@ -640,7 +660,45 @@ int mtb_load_obj(mtb_context *ctx, const char *path) {
   ctx->triangles.swap(loaded.triangles);
   ctx->materials.swap(loaded.materials);
   ctx->textures.swap(loaded.textures);
+  ctx->material_names.swap(loaded.material_names);
+  ctx->texture_names.swap(loaded.texture_names);
   return BuildAndUpload(ctx);
+}
+
+int mtb_load_mtl(mtb_context *ctx, const char *path) {
+  if (ctx == nullptr || path == nullptr) return MTB_ERR_ARG;
+  mtb::LoadedScene loaded;
+  std::string err;
+  ctx->has_scene = false;
+  if (!mtb::LoadMtlFile(path, &loaded, &err)) {
+    ctx->err = err;
+    fprintf(stderr, "error: %s\n", err.c_str());
+    return MTB_ERR_IO;
+  }
+  ctx->triangles.clear();
+  ctx->materials.swap(loaded.materials);
+  ctx->textures.swap(loaded.textures);
+  ctx->material_names.swap(loaded.material_names);
+  ctx->texture_names.swap(loaded.texture_names);
+  return BuildAndUpload(ctx);
+}
+
+const char *mtb_scene_material_name(const mtb_context *ctx, int32_t index) {
+  if (ctx == nullptr || index < 0 || (size_t)index >= ctx->material_names.size()) return nullptr;
+  return ctx->material_names[(size_t)index].c_str();
+}
+
+const char *mtb_scene_texture_name(const mtb_context *ctx, int32_t index) {
+  if (ctx == nullptr || index < 0 || (size_t)index >= ctx->texture_names.size()) return nullptr;
+  return ctx->texture_names[(size_t)index].c_str();
+}
+
+int mtb_scene_texture(const mtb_context *ctx, int32_t index, mtb_texture *out) {
+  if (ctx == nullptr || out == nullptr || index < 0 || (size_t)index >= ctx->textures.size()) return MTB_ERR_ARG;
+  out->width = ctx->textures[(size_t)index].width;
+  out->height = ctx->textures[(size_t)index].height;
+  out->rgba = ctx->textures[(size_t)index].rgba.data();
+  return MTB_OK;
 }
 
 int mtb_set_lights(mtb_context *ctx, const mtb_light *lights, int32_t n) {

@@ -259,6 +259,13 @@ __device__ int TraceRegular(const DeviceScene &sc, const Ray &r, double *t_out, 
     if (info.w < 0) {
       for (int s = info.y, e = info.y + info.z; s < e; s++) TestSlotRegular<DBG>(sc, s, r, &c_t, &c_slot, cnt);
     } else {
+      // Two phases per list ("while-while"): first walk the BVH with the cheap FP32 cull only and park
+      // the leaves it lets through, then run the exact FP64 triangle tests of the parked leaves back to
+      // back.  Lanes of a warp reach leaves at different iterations; testing triangles inside the walk
+      // would make every other lane wait for each of them.
+      constexpr int kPend = 6;
+      unsigned pend[kPend];
+      int n_pend = 0;
       int i = info.w;
       const int end = info2.y;
       while (i < end) {
@@ -268,13 +275,20 @@ __device__ int TraceRegular(const DeviceScene &sc, const Ray &r, double *t_out, 
         Count<DBG>(cnt, kBvh);
         const bool pass = r.cull32 ? CullBox32(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r)
                                    : CullBox64(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r);
-        if (pass) {
-          const unsigned leaf = __float_as_uint(q1.w);
-          for (int s = (int)(leaf >> 3), e = s + (int)(leaf & 7u); s < e; s++) TestSlotRegular<DBG>(sc, s, r, &c_t, &c_slot, cnt);
-          i = i + 1;
-        } else {
-          i = __float_as_int(q1.z);
+        i = pass ? i + 1 : __float_as_int(q1.z);
+        const unsigned leaf = __float_as_uint(q1.w);
+        if (pass && leaf != 0u) {
+          pend[n_pend++] = leaf;
+          if (n_pend == kPend) {
+            for (int j = 0; j < kPend; j++) {
+              for (int s = (int)(pend[j] >> 3), e = s + (int)(pend[j] & 7u); s < e; s++) TestSlotRegular<DBG>(sc, s, r, &c_t, &c_slot, cnt);
+            }
+            n_pend = 0;
+          }
         }
+      }
+      for (int j = 0; j < n_pend; j++) {
+        for (int s = (int)(pend[j] >> 3), e = s + (int)(pend[j] & 7u); s < e; s++) TestSlotRegular<DBG>(sc, s, r, &c_t, &c_slot, cnt);
       }
     }
     // ---- children that the ray enters, ordered by entry distance (octtree.cc:200-216) ----

@@ -78,15 +78,25 @@ struct WfBuffers {
   int32_t *act_refl, *act_refr, *act_mtl;  // child activation ids (-1: none), material of the hit
   uint32_t *counters;  // [0] rays queued for the next level, [1] overflow flag
   int32_t queue_cap, act_cap;
+  // coherence sort of a level's queue: bucket key per queued ray (direction octant + Morton cell of the
+  // origin), histogram / offsets of the counting sort, and the resulting order (sorted position -> queue
+  // position).  Only the ORDER in which rays are processed changes, never a result.
+  uint32_t *sort_key[2];
+  uint32_t *sort_hist;
+  int32_t *perm;
+  float cell_lo[3], cell_scale[3];  // origin -> 5-bit cell coordinate per axis
 };
+constexpr int kWfSortBits = 18;  // 3 direction-sign bits + 3 x 5 cell bits
 
 // wavefront.cu
+// `sorted`: the level's queue is processed in wf.perm order (levels >= 1 after LaunchWfSort)
 void LaunchWfTraceMain(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
-                       int act_base, bool debug_build, cudaStream_t stream);
+                       int act_base, bool sorted, bool debug_build, cudaStream_t stream);
 void LaunchWfShadow(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
-                    bool debug_build, cudaStream_t stream);
+                    bool sorted, bool debug_build, cudaStream_t stream);
 void LaunchWfLightSpawn(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
-                        int act_base, bool debug_build, cudaStream_t stream);
+                        int act_base, bool sorted, bool debug_build, cudaStream_t stream);
+void LaunchWfSort(const WfBuffers &wf, int level, int n, cudaStream_t stream);
 void LaunchWfFold(const DeviceScene &sc, const WfBuffers &wf, int begin, int end, cudaStream_t stream);
 void LaunchWfResolve(const RenderParams &rp, const WfBuffers &wf, int n_slots, cudaStream_t stream);
 

@@ -212,6 +212,11 @@ class MtlParser {
 
 }  // namespace
 
+bool LoadMtlFile(const char *path, LoadedScene *scene, std::string *err) {
+  MtlParser mp(scene, err);
+  return mp.Parse(path);
+}
+
 bool LoadObjFile(const char *path, LoadedScene *scene, std::string *err) {
   FileCloser fc{fopen(path, "r")};
   if (fc.f == nullptr) {

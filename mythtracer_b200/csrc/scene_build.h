@@ -93,5 +93,6 @@ struct LoadedScene {
   std::vector<std::string> texture_names;
 };
 bool LoadObjFile(const char *path, LoadedScene *scene, std::string *err);
+bool LoadMtlFile(const char *path, LoadedScene *scene, std::string *err);
 
 }  // namespace mtb

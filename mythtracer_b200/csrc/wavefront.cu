@@ -49,13 +49,64 @@ __device__ __forceinline__ void FlushCounters(unsigned long long *cnt, unsigned 
   }
 }
 
+// Coherence key of a queued ray: the direction octant and the Morton code of the origin's cell in a
+// 32^3 grid over the scene box.  Rays with equal keys start close together and head the same way, so
+// they walk the same octree nodes and list-BVH records.
+__device__ __forceinline__ unsigned Spread5(unsigned v) {  // abcde -> a00b00c00d00e
+  return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6) | ((v & 16u) << 8);
+}
+__device__ __forceinline__ unsigned RayKey(const WfBuffers &wf, const D3 &o, const D3 &d) {
+  const float fx = ((float)o.x - wf.cell_lo[0]) * wf.cell_scale[0];
+  const float fy = ((float)o.y - wf.cell_lo[1]) * wf.cell_scale[1];
+  const float fz = ((float)o.z - wf.cell_lo[2]) * wf.cell_scale[2];
+  const unsigned cx = (unsigned)fminf(fmaxf(fx, 0.0f), 31.0f);  // NaN -> 0
+  const unsigned cy = (unsigned)fminf(fmaxf(fy, 0.0f), 31.0f);
+  const unsigned cz = (unsigned)fminf(fmaxf(fz, 0.0f), 31.0f);
+  const unsigned oct = (d.x < 0.0 ? 1u : 0u) | (d.y < 0.0 ? 2u : 0u) | (d.z < 0.0 ? 4u : 0u);
+  return (oct << 15) | Spread5(cx) | (Spread5(cy) << 1) | (Spread5(cz) << 2);
+}
+
+// Counting sort of a level's queue by RayKey: histogram, exclusive scan, scatter.
+__global__ void WfSortHistogram(const uint32_t *__restrict__ keys, uint32_t *hist, int n) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i < n) atomicAdd(hist + keys[i], 1u);
+}
+__global__ void __launch_bounds__(1024) WfSortScan(uint32_t *hist) {
+  // one block: 1024 threads x 256 consecutive bins = 2^18 bins
+  __shared__ uint32_t partial[1024];
+  constexpr int kPer = (1 << kWfSortBits) / 1024;
+  uint32_t *mine = hist + (size_t)threadIdx.x * kPer;
+  uint32_t sum = 0;
+  for (int k = 0; k < kPer; k++) sum += mine[k];
+  partial[threadIdx.x] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const uint32_t v = threadIdx.x >= (unsigned)off ? partial[threadIdx.x - off] : 0u;
+    __syncthreads();
+    partial[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = partial[threadIdx.x] - sum;
+  for (int k = 0; k < kPer; k++) {
+    const uint32_t c = mine[k];
+    mine[k] = run;
+    run += c;
+  }
+}
+__global__ void WfSortScatter(const uint32_t *__restrict__ keys, uint32_t *offsets, int32_t *perm, int n) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i < n) perm[atomicAdd(offsets + keys[i], 1u)] = i;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // WfTraceMain
 // ---------------------------------------------------------------------------------------------------
 template <bool DBG>
 __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTraceMain(DeviceScene sc, RenderParams rp, WfBuffers wf, int level, int n,
-                                                        int act_base) {
-  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+                                                        int act_base, const int32_t *__restrict__ perm) {
+  // j: position in processing order (indexes the per-level scratch); i: position in the queue
+  const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int i = (perm != nullptr && j < n) ? perm[j] : j;
   unsigned long long cnt_store[DBG ? kNumCounters : 1];
   unsigned long long *cnt = cnt_store;
   if (DBG) {
@@ -63,7 +114,7 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTraceMain(Devic
   }
   unsigned traced = 0;
   const int q = level & 1;
-  if (i < n) {
+  if (j < n) {
     D3 o, d;
     int pixel;
     unsigned long long path;
@@ -152,14 +203,14 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTraceMain(Devic
           const D3 reflected = Sub(d, MulS(normal, 2 * Dot(normal, d)));
           ctx_mtl = material;
           wf.act_mtl[act] = material;
-          Store3(wf.ctx_point + (size_t)i * 3, P);
-          Store3(wf.ctx_normal + (size_t)i * 3, normal);
-          Store3(wf.ctx_surface + (size_t)i * 3, surface);
-          Store3(wf.ctx_reflected + (size_t)i * 3, reflected);
+          Store3(wf.ctx_point + (size_t)j * 3, P);
+          Store3(wf.ctx_normal + (size_t)j * 3, normal);
+          Store3(wf.ctx_surface + (size_t)j * 3, surface);
+          Store3(wf.ctx_reflected + (size_t)j * 3, reflected);
         }
       }
     }
-    wf.ctx_mtl[i] = ctx_mtl;
+    wf.ctx_mtl[j] = ctx_mtl;
     Store3(wf.act_color + (size_t)act * 3, color);
   }
   FlushCounters<DBG>(cnt, rp.counters, traced);
@@ -169,7 +220,8 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTraceMain(Devic
 // WfShadow: thread = (light, hit).  Light-major task order keeps the rays of one warp aimed at one light.
 // ---------------------------------------------------------------------------------------------------
 template <bool DBG>
-__global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfShadow(DeviceScene sc, RenderParams rp, WfBuffers wf, int level, int n) {
+__global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfShadow(DeviceScene sc, RenderParams rp, WfBuffers wf, int level, int n,
+                                                     const int32_t *__restrict__ perm) {
   const long long task = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long cnt_store[DBG ? kNumCounters : 1];
   unsigned long long *cnt = cnt_store;
@@ -217,7 +269,7 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfShadow(DeviceSc
       traced = segments;
       Store3(wf.sh_power + ((size_t)li * wf.queue_cap + i) * 3, power);
       wf.sh_flags[(size_t)li * wf.queue_cap + i] = (in_shadow ? 1u : 0u) | (segments << 1);
-      if (rp.n_rays != nullptr) atomicAdd(rp.n_rays + wf.rq_pixel[level & 1][i], segments);
+      if (rp.n_rays != nullptr) atomicAdd(rp.n_rays + wf.rq_pixel[level & 1][perm != nullptr ? perm[i] : i], segments);
     }
   }
   FlushCounters<DBG>(cnt, rp.counters, traced);
@@ -228,8 +280,9 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfShadow(DeviceSc
 // ---------------------------------------------------------------------------------------------------
 template <bool DBG>
 __global__ void __launch_bounds__(kWfBlock) WfLightSpawn(DeviceScene sc, RenderParams rp, WfBuffers wf, int level, int n,
-                                                         int act_base) {
-  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+                                                         int act_base, const int32_t *__restrict__ perm) {
+  const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int i = (perm != nullptr && j < n) ? perm[j] : j;
   unsigned long long cnt_store[DBG ? kNumCounters : 1];
   unsigned long long *cnt = cnt_store;
   if (DBG) {
@@ -241,13 +294,13 @@ __global__ void __launch_bounds__(kWfBlock) WfLightSpawn(DeviceScene sc, RenderP
   double coef = 0.0, refl = 0.0;
   bool in_object = false;
   int material = -1;
-  if (i < n) material = wf.ctx_mtl[i];
+  if (j < n) material = wf.ctx_mtl[j];
   if (material >= 0) {
     const mtb_material *m = sc.materials + material;
-    P = Load3(wf.ctx_point + (size_t)i * 3);
-    const D3 normal = Load3(wf.ctx_normal + (size_t)i * 3);
-    const D3 surface = Load3(wf.ctx_surface + (size_t)i * 3);
-    reflected = Load3(wf.ctx_reflected + (size_t)i * 3);
+    P = Load3(wf.ctx_point + (size_t)j * 3);
+    const D3 normal = Load3(wf.ctx_normal + (size_t)j * 3);
+    const D3 surface = Load3(wf.ctx_surface + (size_t)j * 3);
+    reflected = Load3(wf.ctx_reflected + (size_t)j * 3);
     m_d = Load3(wf.rq_d[q] + (size_t)i * 3);
     const unsigned long long path = wf.rq_path[q][i];
     D3 color = Mk(0.0, 0.0, 0.0);
@@ -257,8 +310,8 @@ __global__ void __launch_bounds__(kWfBlock) WfLightSpawn(DeviceScene sc, RenderP
       const D3 ldir = Normalized(Sub(Load3(lt->position), P));
       const D3 lamb = Load3(lt->ambient);
       color = Add(color, MulV(lamb, surface));
-      D3 power = Load3(wf.sh_power + ((size_t)li * wf.queue_cap + i) * 3);
-      const unsigned flags = wf.sh_flags[(size_t)li * wf.queue_cap + i];
+      D3 power = Load3(wf.sh_power + ((size_t)li * wf.queue_cap + j) * 3);
+      const unsigned flags = wf.sh_flags[(size_t)li * wf.queue_cap + j];
       const bool in_shadow = (flags & 1u) != 0u;
       sig += Mix64(path, 2ull + (unsigned long long)li, (unsigned long long)flags);
       power.x = SMax(power.x, lamb.x);
@@ -307,8 +360,10 @@ __global__ void __launch_bounds__(kWfBlock) WfLightSpawn(DeviceScene sc, RenderP
     } else {
       if (do_reflect) {
         Count<DBG>(cnt, kReflect);
-        Store3(wf.rq_o[qn] + (size_t)pos * 3, Add(P, MulS(reflected, 0.0001)));  // mythtracer.cc:70-75
+        const D3 ro = Add(P, MulS(reflected, 0.0001));  // mythtracer.cc:70-75
+        Store3(wf.rq_o[qn] + (size_t)pos * 3, ro);
         Store3(wf.rq_d[qn] + (size_t)pos * 3, reflected);
+        wf.sort_key[qn][pos] = RayKey(wf, ro, reflected);
         wf.rq_coef[qn][pos] = coef * refl;
         wf.rq_path[qn][pos] = path * 2ull;
         wf.rq_pixel[qn][pos] = pixel;
@@ -318,9 +373,11 @@ __global__ void __launch_bounds__(kWfBlock) WfLightSpawn(DeviceScene sc, RenderP
       }
       if (do_refract) {
         Count<DBG>(cnt, kRefract);
-        const D3 rdir = Normalized(m_d);                                         // mythtracer.cc:208-212
-        Store3(wf.rq_o[qn] + (size_t)pos * 3, Add(P, MulS(rdir, 0.00001)));      // mythtracer.cc:214-218
+        const D3 rdir = Normalized(m_d);                // mythtracer.cc:208-212
+        const D3 ro = Add(P, MulS(rdir, 0.00001));      // mythtracer.cc:214-218
+        Store3(wf.rq_o[qn] + (size_t)pos * 3, ro);
         Store3(wf.rq_d[qn] + (size_t)pos * 3, rdir);
+        wf.sort_key[qn][pos] = RayKey(wf, ro, rdir);
         wf.rq_coef[qn][pos] = coef;
         wf.rq_path[qn][pos] = path * 2ull + 1ull;
         wf.rq_pixel[qn][pos] = pixel;
@@ -364,37 +421,49 @@ __global__ void __launch_bounds__(256) WfResolve(RenderParams rp, WfBuffers wf, 
 
 }  // namespace
 
+void LaunchWfSort(const WfBuffers &wf, int level, int n, cudaStream_t stream) {
+  if (n <= 0) return;
+  cudaMemsetAsync(wf.sort_hist, 0, sizeof(uint32_t) << kWfSortBits, stream);
+  const uint32_t *keys = wf.sort_key[level & 1];
+  WfSortHistogram<<<(n + 255) / 256, 256, 0, stream>>>(keys, wf.sort_hist, n);
+  WfSortScan<<<1, 1024, 0, stream>>>(wf.sort_hist);
+  WfSortScatter<<<(n + 255) / 256, 256, 0, stream>>>(keys, wf.sort_hist, wf.perm, n);
+}
+
 void LaunchWfTraceMain(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
-                       int act_base, bool debug_build, cudaStream_t stream) {
+                       int act_base, bool sorted, bool debug_build, cudaStream_t stream) {
   if (n <= 0) return;
   const int blocks = (n + kWfBlock - 1) / kWfBlock;
+  const int32_t *perm = sorted ? wf.perm : nullptr;
   if (debug_build) {
-    WfTraceMain<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base);
+    WfTraceMain<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base, perm);
   } else {
-    WfTraceMain<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base);
+    WfTraceMain<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base, perm);
   }
 }
 
 void LaunchWfShadow(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
-                    bool debug_build, cudaStream_t stream) {
+                    bool sorted, bool debug_build, cudaStream_t stream) {
   const long long tasks = (long long)n * sc.n_lights;
   if (tasks <= 0) return;
   const int blocks = (int)((tasks + kWfBlock - 1) / kWfBlock);
+  const int32_t *perm = sorted ? wf.perm : nullptr;
   if (debug_build) {
-    WfShadow<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n);
+    WfShadow<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, perm);
   } else {
-    WfShadow<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n);
+    WfShadow<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, perm);
   }
 }
 
 void LaunchWfLightSpawn(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
-                        int act_base, bool debug_build, cudaStream_t stream) {
+                        int act_base, bool sorted, bool debug_build, cudaStream_t stream) {
   if (n <= 0) return;
   const int blocks = (n + kWfBlock - 1) / kWfBlock;
+  const int32_t *perm = sorted ? wf.perm : nullptr;
   if (debug_build) {
-    WfLightSpawn<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base);
+    WfLightSpawn<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base, perm);
   } else {
-    WfLightSpawn<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base);
+    WfLightSpawn<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base, perm);
   }
 }
 

@@ -212,11 +212,27 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------------
 
 def run_ours(args):
+    # NCCL / the loader may print to stdout; the contract is ONE JSON line there, so everything else goes to
+    # stderr until the final print
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def _run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_COUNT_WORK, tiles
+    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_COUNT_WORK, MTB_FLAG_WAVEFRONT, tiles
     from mythtracer_b200 import build as mtb_build
 
     rank = int(os.environ.get("RANK", "0"))
@@ -243,7 +259,8 @@ def run_ours(args):
             files, cfg = load_workload()  # reuses the files rank 0 wrote
     W, H, depth = cfg["width"], cfg["height"], cfg["depth"]
 
-    mt = MythTracer(devices=[local_rank], max_depth=depth)
+    base_flags = MTB_FLAG_WAVEFRONT if args.pipeline == "wavefront" else 0
+    mt = MythTracer(devices=[local_rank], max_depth=depth, flags=base_flags)
     t0 = time.time()
     if not mt.LoadObj(files.obj_path):
         raise SystemExit("LoadObj failed: " + mt.last_error())
@@ -284,20 +301,22 @@ def run_ours(args):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    launches0 = mt.launch_count()
     ev0.record(stream)
     for _ in range(args.steps):
         frame = step_device()
     ev1.record(stream)
     barrier()
+    launches = mt.launch_count() - launches0
     elapsed_ms = ev0.elapsed_time(ev1)
     counters = mt.read_counters()
-    t = torch.tensor([elapsed_ms, float(counters["rays"])], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, float(counters["rays"]), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        elapsed_ms, total_rays = float(tmax[0]), float(tsum[1])
+        elapsed_ms, total_rays, launches = float(tmax[0]), float(tsum[1]), int(tsum[2])
     else:
         total_rays = float(t[1])
     rays_per_frame = total_rays / args.steps
@@ -346,11 +365,11 @@ def run_ours(args):
 
     # ---- work counters of one frame (counting build, not timed) -> algorithmic bytes ----
     mt.read_counters()  # reset
-    mt.set_flags(MTB_FLAG_COUNT_WORK)
+    mt.set_flags(MTB_FLAG_COUNT_WORK | base_flags)
     mt.render_device(files.camera, W, H, d_local.data_ptr(), stream.cuda_stream)
     torch.cuda.synchronize(dev)
     work = mt.read_counters()
-    mt.set_flags(0)
+    mt.set_flags(base_flags)
     wt = torch.tensor([float(work[k]) for k in ("n_slab", "n_triaabb", "n_bvh", "n_mt", "n_shade", "n_visit", "n_hit", "rays")],
                       dtype=torch.float64, device=dev)
     if world > 1:
@@ -361,7 +380,7 @@ def run_ours(args):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return 0
+        return None
 
     peak, peak_src = measured_peak()
     achieved = my_alg / (kernel_ms_mean * 1e-3) / 1e9
@@ -376,7 +395,8 @@ def run_ours(args):
         except Exception:
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "RenderMega", "kernel_ms": kernel_ms_mean,
+                "traffic": traffic, "kernel": "RenderMega" if args.pipeline == "mega" else "wavefront pipeline (WfTraceMain+WfShadow+...)",
+                "kernel_ms": kernel_ms_mean,
                 "algorithmic_bytes_per_launch": my_alg, "peak_source": peak_src,
                 "note": "algorithmic bytes are served by L1/L2 (broadcast reads of shared nodes); frac > DRAM share is cache reuse",
                 "per_ray": {k: work_all[k] / max(work_all["rays"], 1.0) for k in ("n_slab", "n_visit", "n_triaabb", "n_bvh", "n_mt", "n_hit", "n_shade")}}
@@ -396,20 +416,19 @@ def run_ours(args):
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": config_dict(files, cfg, world, {"rays_per_frame": rays_per_frame, "scene_load_s": load_s,
+        "config": config_dict(files, cfg, world, {"pipeline": args.pipeline, "rays_per_frame": rays_per_frame, "scene_load_s": load_s,
                                                  "octree_nodes": info["n_nodes"], "tree_depth": info["tree_depth"],
                                                  "device_scene_bytes": info["device_bytes"]}),
         "roofline": roofline,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_s * 1e3 / args.steps,
                 "h2d_bytes_per_step": lights_bytes + 256, "d2h_bytes_per_step": W * H * 3},
-        "gpu_launches": args.steps * world,
+        "gpu_launches": int(launches),
         "clocks": clocks,
     }
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return line
 
 
 def main():
@@ -419,6 +438,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", default=os.environ.get("MTB_PIPELINE", "mega"), choices=["mega", "wavefront"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

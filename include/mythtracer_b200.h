@@ -115,7 +115,7 @@ typedef struct {
 #define MTB_FLAG_COUNT_WORK 1u   /* fill the n_* work counters (counting kernels) */
 #define MTB_FLAG_NO_LIST_BVH 2u  /* scan every node list linearly, like the reference (A/B measurements) */
 #define MTB_FLAG_WAVEFRONT 4u    /* wavefront pipeline instead of the per-pixel megakernel */
-#define MTB_FLAG_NO_RAY_SORT 8u  /* wavefront: keep the queues in spawn order (A/B measurements) */
+#define MTB_FLAG_RAY_SORT 8u     /* wavefront: counting-sort every queue by origin cell + direction octant (measured: no gain) */
 
 /* ---- life cycle -------------------------------------------------------------------------------- */
 
@@ -184,6 +184,9 @@ int mtb_render_chunk_device(mtb_context *ctx, const mtb_camera *cam, int image_w
 /* Work counters accumulated by mtb_render_chunk_device calls that passed stats == NULL since the last
  * read; synchronises every device of the context and resets the counters. */
 int mtb_read_counters(mtb_context *ctx, mtb_stats *stats);
+
+/* Number of kernels of this library launched on this context so far (bench.py's gpu_launches). */
+uint64_t mtb_launch_count(const mtb_context *ctx);
 
 /* Batched OctTree::IntersectRay (octtree.cc:26-40).  HOST arrays: origins/dirs n*3, tri_index n (insertion
  * index, -1 = nullptr), t n, point n*3 (nullable). */

@@ -33,7 +33,7 @@ MTB_OK = 0
 MTB_FLAG_COUNT_WORK = 1
 MTB_FLAG_NO_LIST_BVH = 2
 MTB_FLAG_WAVEFRONT = 4
-MTB_FLAG_NO_RAY_SORT = 8
+MTB_FLAG_RAY_SORT = 8
 MAX_RECURSION_LEVEL = 5  # reference mythtracer.h:11 (a run-time argument here)
 
 TRI_DTYPE = np.dtype([("vertex", "f8", (9,)), ("normal", "f8", (9,)), ("uvw", "f8", (9,)),
@@ -61,7 +61,7 @@ EXPORTED_SYMBOLS = [
     "mtb_create", "mtb_create_host", "mtb_destroy", "mtb_last_error", "mtb_device_count", "mtb_scene_upload", "mtb_load_obj",
     "mtb_set_lights", "mtb_scene_info", "mtb_scene_read", "mtb_scene_material_name", "mtb_scene_texture_name", "mtb_scene_texture", "mtb_load_mtl",
     "mtb_scene_triangle_nodes", "mtb_set_flags", "mtb_set_partition", "mtb_render_chunk",
-    "mtb_render_chunk_device", "mtb_read_counters", "mtb_intersect_rays", "mtb_camera_sensor", "mtb_version",
+    "mtb_render_chunk_device", "mtb_read_counters", "mtb_launch_count", "mtb_intersect_rays", "mtb_camera_sensor", "mtb_version",
 ]
 
 
@@ -113,6 +113,8 @@ def load_library():
     lib.mtb_render_chunk.argtypes = [vp, vp] + [i32] * 7 + [vp, vp, vp, vp]
     lib.mtb_render_chunk_device.argtypes = [vp, vp] + [i32] * 7 + [vp, vp, vp]
     lib.mtb_read_counters.argtypes = [vp, vp]
+    lib.mtb_launch_count.argtypes = [vp]
+    lib.mtb_launch_count.restype = ctypes.c_uint64
     lib.mtb_intersect_rays.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp]
     lib.mtb_camera_sensor.argtypes = [vp, i32, i32, vp]
     lib.mtb_version.restype = ctypes.c_char_p
@@ -418,6 +420,9 @@ class MythTracer:
 
     def push_lights(self):
         self._push_lights()
+
+    def launch_count(self) -> int:
+        return int(self._lib.mtb_launch_count(self._ctx))
 
     def read_counters(self) -> dict:
         stats = np.zeros((), STATS_DTYPE)

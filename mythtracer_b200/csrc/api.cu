@@ -80,11 +80,14 @@ struct DeviceState {
   DeviceBuffer<unsigned long long> wf_rq_path[2];
   DeviceBuffer<int32_t> wf_rq_pixel[2];
   DeviceBuffer<unsigned char> wf_rq_inobj[2];
-  DeviceBuffer<int32_t> wf_ctx_mtl;
-  DeviceBuffer<double> wf_ctx_point, wf_ctx_normal, wf_ctx_surface, wf_ctx_reflected, wf_sh_power;
+  DeviceBuffer<double> wf_act_point, wf_act_normal, wf_act_surface, wf_act_reflected, wf_act_dir, wf_sh_power;
   DeviceBuffer<uint32_t> wf_sh_flags;
   DeviceBuffer<double> wf_act_color;
-  DeviceBuffer<int32_t> wf_act_refl, wf_act_refr, wf_act_mtl;
+  DeviceBuffer<int32_t> wf_act_refl, wf_act_refr, wf_act_mtl, wf_act_pixel;
+  DeviceBuffer<unsigned long long> wf_act_path;
+  cudaStream_t wf_stream2 = nullptr;             // shadow / light kernels
+  cudaEvent_t wf_ev_level[MTB_MAX_RAY_DEPTH + 2] = {};  // level L traced (main stream)
+  cudaEvent_t wf_ev_lit = nullptr;               // all lights folded (second stream)
   DeviceBuffer<uint32_t> wf_counters, wf_sort_key[2], wf_sort_hist;
   DeviceBuffer<int32_t> wf_perm;
   uint32_t *wf_host_counters = nullptr;  // pinned
@@ -102,9 +105,17 @@ struct DeviceState {
     }
     wf_sort_hist.Free();
     wf_perm.Free();
-    wf_ctx_mtl.Free(); wf_ctx_point.Free(); wf_ctx_normal.Free(); wf_ctx_surface.Free(); wf_ctx_reflected.Free();
+    wf_act_point.Free(); wf_act_normal.Free(); wf_act_surface.Free(); wf_act_reflected.Free(); wf_act_dir.Free();
     wf_sh_power.Free(); wf_sh_flags.Free(); wf_act_color.Free(); wf_act_refl.Free(); wf_act_refr.Free();
-    wf_act_mtl.Free(); wf_counters.Free();
+    wf_act_mtl.Free(); wf_act_pixel.Free(); wf_act_path.Free(); wf_counters.Free();
+    if (wf_stream2 != nullptr) cudaStreamDestroy(wf_stream2);
+    wf_stream2 = nullptr;
+    for (cudaEvent_t &e : wf_ev_level) {
+      if (e != nullptr) cudaEventDestroy(e);
+      e = nullptr;
+    }
+    if (wf_ev_lit != nullptr) cudaEventDestroy(wf_ev_lit);
+    wf_ev_lit = nullptr;
     if (wf_host_counters != nullptr) cudaFreeHost(wf_host_counters);
     wf_host_counters = nullptr;
   }
@@ -125,6 +136,7 @@ struct mtb_context {
   std::vector<std::string> material_names, texture_names;
   std::vector<mtb_light> lights;
   int64_t device_bytes = 0;
+  uint64_t launches = 0;  // kernels of this library launched so far (mtb_launch_count)
 };
 
 namespace {
@@ -306,18 +318,25 @@ int EnsureWavefront(mtb_context *ctx, DeviceState *d, int slots, int n_lights) {
     d->wf.rq_pixel[k] = d->wf_rq_pixel[k].ptr;
     d->wf.rq_inobj[k] = d->wf_rq_inobj[k].ptr;
   }
-  MTB_CUDA(ctx, d->wf_ctx_mtl.Reserve(qcap));
-  MTB_CUDA(ctx, d->wf_ctx_point.Reserve(qcap * 3));
-  MTB_CUDA(ctx, d->wf_ctx_normal.Reserve(qcap * 3));
-  MTB_CUDA(ctx, d->wf_ctx_surface.Reserve(qcap * 3));
-  MTB_CUDA(ctx, d->wf_ctx_reflected.Reserve(qcap * 3));
   const size_t nl = (size_t)(n_lights > 0 ? n_lights : 1);
-  MTB_CUDA(ctx, d->wf_sh_power.Reserve(qcap * 3 * nl));
-  MTB_CUDA(ctx, d->wf_sh_flags.Reserve(qcap * nl));
+  MTB_CUDA(ctx, d->wf_act_point.Reserve(acap * 3));
+  MTB_CUDA(ctx, d->wf_act_normal.Reserve(acap * 3));
+  MTB_CUDA(ctx, d->wf_act_surface.Reserve(acap * 3));
+  MTB_CUDA(ctx, d->wf_act_reflected.Reserve(acap * 3));
+  MTB_CUDA(ctx, d->wf_act_dir.Reserve(acap * 3));
+  MTB_CUDA(ctx, d->wf_sh_power.Reserve(acap * 3 * nl));
+  MTB_CUDA(ctx, d->wf_sh_flags.Reserve(acap * nl));
   MTB_CUDA(ctx, d->wf_act_color.Reserve(acap * 3));
   MTB_CUDA(ctx, d->wf_act_refl.Reserve(acap));
   MTB_CUDA(ctx, d->wf_act_refr.Reserve(acap));
   MTB_CUDA(ctx, d->wf_act_mtl.Reserve(acap));
+  MTB_CUDA(ctx, d->wf_act_pixel.Reserve(acap));
+  MTB_CUDA(ctx, d->wf_act_path.Reserve(acap));
+  if (d->wf_stream2 == nullptr) {
+    MTB_CUDA(ctx, cudaStreamCreateWithFlags(&d->wf_stream2, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : d->wf_ev_level) MTB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    MTB_CUDA(ctx, cudaEventCreateWithFlags(&d->wf_ev_lit, cudaEventDisableTiming));
+  }
   MTB_CUDA(ctx, d->wf_counters.Reserve(2));
   MTB_CUDA(ctx, d->wf_sort_hist.Reserve((size_t)1 << mtb::kWfSortBits));
   MTB_CUDA(ctx, d->wf_perm.Reserve(qcap));
@@ -329,17 +348,19 @@ int EnsureWavefront(mtb_context *ctx, DeviceState *d, int slots, int n_lights) {
     d->wf.cell_scale[a] = ext > 0.0 ? (float)(32.0 / ext) : 0.0f;
   }
   if (d->wf_host_counters == nullptr) MTB_CUDA(ctx, cudaMallocHost(reinterpret_cast<void **>(&d->wf_host_counters), 2 * sizeof(uint32_t)));
-  d->wf.ctx_mtl = d->wf_ctx_mtl.ptr;
-  d->wf.ctx_point = d->wf_ctx_point.ptr;
-  d->wf.ctx_normal = d->wf_ctx_normal.ptr;
-  d->wf.ctx_surface = d->wf_ctx_surface.ptr;
-  d->wf.ctx_reflected = d->wf_ctx_reflected.ptr;
+  d->wf.act_point = d->wf_act_point.ptr;
+  d->wf.act_normal = d->wf_act_normal.ptr;
+  d->wf.act_surface = d->wf_act_surface.ptr;
+  d->wf.act_reflected = d->wf_act_reflected.ptr;
+  d->wf.act_dir = d->wf_act_dir.ptr;
   d->wf.sh_power = d->wf_sh_power.ptr;
   d->wf.sh_flags = d->wf_sh_flags.ptr;
   d->wf.act_color = d->wf_act_color.ptr;
   d->wf.act_refl = d->wf_act_refl.ptr;
   d->wf.act_refr = d->wf_act_refr.ptr;
   d->wf.act_mtl = d->wf_act_mtl.ptr;
+  d->wf.act_pixel = d->wf_act_pixel.ptr;
+  d->wf.act_path = d->wf_act_path.ptr;
   d->wf.counters = d->wf_counters.ptr;
   d->wf.queue_cap = (int32_t)qcap;
   d->wf.act_cap = (int32_t)acap;
@@ -358,15 +379,25 @@ int RunWavefront(mtb_context *ctx, DeviceState *d, const mtb::RenderParams &p, i
     int level_begin[MTB_MAX_RAY_DEPTH + 2];
     int n = slots, act_base = 0, last_level = 0;
     bool overflow = false;
+    cudaStream_t s2 = d->wf_stream2;
+    // the second stream must not start before earlier work on the main stream (previous frame, taps memset)
+    MTB_CUDA(ctx, cudaEventRecord(d->wf_ev_lit, s));
+    MTB_CUDA(ctx, cudaStreamWaitEvent(s2, d->wf_ev_lit, 0));
     for (int level = 0; level <= p.max_depth; level++) {
       last_level = level;
       level_begin[level] = act_base;
       MTB_CUDA(ctx, cudaMemsetAsync(d->wf.counters, 0, 2 * sizeof(uint32_t), s));
-      const bool sorted = level > 0 && (ctx->flags & MTB_FLAG_NO_RAY_SORT) == 0;
+      const bool sorted = level > 0 && (ctx->flags & MTB_FLAG_RAY_SORT) != 0;
       if (sorted) mtb::LaunchWfSort(d->wf, level, n, s);
+      // critical path (main stream): trace the level, spawn the next one
       mtb::LaunchWfTraceMain(d->scene, p, d->wf, level, n, act_base, sorted, debug_build, s);
-      mtb::LaunchWfShadow(d->scene, p, d->wf, level, n, sorted, debug_build, s);
-      mtb::LaunchWfLightSpawn(d->scene, p, d->wf, level, n, act_base, sorted, debug_build, s);
+      MTB_CUDA(ctx, cudaEventRecord(d->wf_ev_level[level], s));
+      if (level < p.max_depth) mtb::LaunchWfSpawn(d->scene, p, d->wf, level, n, act_base, debug_build, s);
+      // side branch (second stream): shadow walks and the Phong sums of this level
+      MTB_CUDA(ctx, cudaStreamWaitEvent(s2, d->wf_ev_level[level], 0));
+      mtb::LaunchWfShadow(d->scene, p, d->wf, act_base, n, debug_build, s2);
+      mtb::LaunchWfLight(d->scene, p, d->wf, act_base, n, s2);
+      ctx->launches += (sorted ? 3u : 0u) + 2u + (d->scene.n_lights > 0 ? 1u : 0u) + (level < p.max_depth ? 1u : 0u);
       MTB_CUDA(ctx, cudaGetLastError());
       if (level == p.max_depth) break;  // no children beyond MAX_RECURSION_LEVEL (mythtracer.cc:181,192)
       MTB_CUDA(ctx, cudaMemcpyAsync(d->wf_host_counters, d->wf.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -380,7 +411,12 @@ int RunWavefront(mtb_context *ctx, DeviceState *d, const mtb::RenderParams &p, i
       act_base += n;
       n = next;
     }
+    // join: the folds need every level's colours
+    MTB_CUDA(ctx, cudaEventRecord(d->wf_ev_lit, s2));
+    MTB_CUDA(ctx, cudaStreamWaitEvent(s, d->wf_ev_lit, 0));
     if (overflow) {
+      MTB_CUDA(ctx, cudaStreamSynchronize(s2));  // the side branch still reads the buffers about to be replaced
+      MTB_CUDA(ctx, cudaStreamSynchronize(s));
       d->wf_queue_factor *= 2;
       d->wf_act_factor *= 2;
       continue;  // render the frame again with larger queues
@@ -388,8 +424,10 @@ int RunWavefront(mtb_context *ctx, DeviceState *d, const mtb::RenderParams &p, i
     level_begin[last_level + 1] = act_base + n;
     for (int level = last_level - 1; level >= 0; level--) {
       mtb::LaunchWfFold(d->scene, d->wf, level_begin[level], level_begin[level + 1], s);
+      ctx->launches++;
     }
     mtb::LaunchWfResolve(p, d->wf, slots, s);
+    ctx->launches++;
     MTB_CUDA(ctx, cudaGetLastError());
     return MTB_OK;
   }
@@ -482,6 +520,7 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
       if (wrc != MTB_OK) return wrc;
     } else {
       mtb::LaunchRenderMega(d.scene, p, blocks, debug_build, s);
+      if (blocks > 0) ctx->launches++;
       MTB_CUDA(ctx, cudaGetLastError());
     }
     MTB_CUDA(ctx, cudaEventRecord(d.ev_stop, s));
@@ -800,6 +839,8 @@ int mtb_render_chunk_device(mtb_context *ctx, const mtb_camera *cam, int image_w
                     static_cast<cudaStream_t>(stream), nullptr, nullptr, stats, false);
 }
 
+uint64_t mtb_launch_count(const mtb_context *ctx) { return ctx == nullptr ? 0 : ctx->launches; }
+
 int mtb_read_counters(mtb_context *ctx, mtb_stats *stats) {
   if (ctx == nullptr || stats == nullptr) return MTB_ERR_ARG;
   unsigned long long total[mtb::kNumCounters];
@@ -856,6 +897,7 @@ int mtb_intersect_rays(mtb_context *ctx, int64_t n, const double *origins, const
   ip.counters = d.counters.ptr;
   MTB_CUDA(ctx, cudaEventRecord(d.ev_start, d.stream));
   mtb::LaunchIntersect(d.scene, ip, (ctx->flags & MTB_FLAG_COUNT_WORK) != 0, d.stream);
+  ctx->launches++;
   MTB_CUDA(ctx, cudaGetLastError());
   MTB_CUDA(ctx, cudaEventRecord(d.ev_stop, d.stream));
   MTB_CUDA(ctx, cudaMemcpyAsync(tri_index, d.q_tri.ptr, sn * 4, cudaMemcpyDeviceToHost, d.stream));

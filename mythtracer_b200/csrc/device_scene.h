@@ -68,14 +68,16 @@ struct WfBuffers {
   unsigned long long *rq_path[2];
   int32_t *rq_pixel[2];
   unsigned char *rq_inobj[2];
-  // per-level scratch, indexed by queue position
-  int32_t *ctx_mtl;  // material index of the hit; < 0: nothing to light (miss or mtl == nullptr)
-  double *ctx_point, *ctx_normal, *ctx_surface, *ctx_reflected;  // 3 doubles each
-  double *sh_power;    // [light][queue position][3]  light_power after the shadow walk
-  uint32_t *sh_flags;  // [light][queue position]     in_shadow | segments << 1
-  // activation table
+  // activation table, indexed by activation id.  Shading context written by WfTraceMain and read by the
+  // shadow / light kernels, which run on a second stream concurrently with the deeper levels' traces:
+  int32_t *act_mtl;    // material index of the hit; < 0: nothing to light (miss or mtl == nullptr)
+  double *act_point, *act_normal, *act_surface, *act_reflected, *act_dir;  // 3 doubles each
+  int32_t *act_pixel;  // chunk-local pixel (taps)
+  unsigned long long *act_path;
+  double *sh_power;    // [light][activation][3]  light_power after the shadow walk
+  uint32_t *sh_flags;  // [light][activation]     in_shadow | segments << 1
   double *act_color;   // 3 doubles: local colour, later the folded colour
-  int32_t *act_refl, *act_refr, *act_mtl;  // child activation ids (-1: none), material of the hit
+  int32_t *act_refl, *act_refr;  // child activation ids (-1: none)
   uint32_t *counters;  // [0] rays queued for the next level, [1] overflow flag
   int32_t queue_cap, act_cap;
   // coherence sort of a level's queue: bucket key per queued ray (direction octant + Morton cell of the
@@ -92,10 +94,13 @@ constexpr int kWfSortBits = 18;  // 3 direction-sign bits + 3 x 5 cell bits
 // `sorted`: the level's queue is processed in wf.perm order (levels >= 1 after LaunchWfSort)
 void LaunchWfTraceMain(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
                        int act_base, bool sorted, bool debug_build, cudaStream_t stream);
-void LaunchWfShadow(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
-                    bool sorted, bool debug_build, cudaStream_t stream);
-void LaunchWfLightSpawn(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
-                        int act_base, bool sorted, bool debug_build, cudaStream_t stream);
+void LaunchWfSpawn(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
+                   int act_base, bool debug_build, cudaStream_t stream);
+// activations [act_begin, act_begin + n) of one level
+void LaunchWfShadow(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int act_begin, int n,
+                    bool debug_build, cudaStream_t stream);
+void LaunchWfLight(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int act_begin, int n,
+                   cudaStream_t stream);
 void LaunchWfSort(const WfBuffers &wf, int level, int n, cudaStream_t stream);
 void LaunchWfFold(const DeviceScene &sc, const WfBuffers &wf, int begin, int end, cudaStream_t stream);
 void LaunchWfResolve(const RenderParams &rp, const WfBuffers &wf, int n_slots, cudaStream_t stream);

@@ -2,13 +2,18 @@
 // sequence of kernels over ray queues in HBM.
 //
 //   level L:  WfTraceMain   one thread per queued ray: OctTree::IntersectRay, hit point, interpolated normal,
-//                           surface colour, reflected direction  (mythtracer.cc:18-76)
+//                           surface colour, reflected direction  (mythtracer.cc:18-76) -> activation record
+//             WfSpawn       one thread per hit: the reflection / refraction children are appended to the queue
+//                           of level L+1 with a warp-aggregated (ballot + prefix sum) slot allocation
+//                           (mythtracer.cc:181-225).  Whether a child exists does not depend on the lights.
+//     stream 2:
 //             WfShadow      one thread per (hit, light): the whole shadow walk through transparent surfaces
 //                           (mythtracer.cc:86-156); lights are independent of each other, only the order in
-//                           which their terms are summed matters, and that order is kept by WfLightSpawn
-//             WfLightSpawn  one thread per hit: Phong sum over the lights in scene order (mythtracer.cc:78-178),
-//                           then the reflection / refraction children are appended to the queue of level L+1
-//                           with a warp-aggregated (ballot + prefix sum) slot allocation (mythtracer.cc:181-225)
+//                           which their terms are summed matters, and that order is kept by WfLight
+//             WfLight       one thread per hit: Phong sum over the lights in scene order (mythtracer.cc:78-178)
+//   The trace -> spawn -> trace chain of the levels is the critical path (each link ends with the slowest ray
+//   of its level); the shadow / light kernels of level L only need level L's activation records, so they run
+//   on a second stream and fill the machine while the chain advances.
 //   finally:  WfFold        deepest level first: parent += child * Refl, then parent += (child * Tf) * Tr --
 //                           the same two additions, in the same order, as the recursion performs on return
 //             WfResolve     V3DtoRGB (mythtracer.cc:235-241) into the chunk-local RGB24 buffer
@@ -98,14 +103,25 @@ __global__ void WfSortScatter(const uint32_t *__restrict__ keys, uint32_t *offse
   if (i < n) perm[atomicAdd(offsets + keys[i], 1u)] = i;
 }
 
+// Sub-warp packing.  A warp runs as long as its slowest ray and serialises what its lanes do differently,
+// so a level with few rays (deep levels, or a small share of the frame on one of 8 GPUs) finishes sooner
+// when its rays are spread over more, emptier warps: only the first `lanes` lanes of each warp get a ray.
+__device__ __forceinline__ long long PackedIndex64(long long n, int lanes) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = (int)(threadIdx.x & 31u);
+  return lane < lanes ? warp * lanes + lane : n;
+}
+__device__ __forceinline__ int PackedIndex(int n, int lanes) { return (int)PackedIndex64(n, lanes); }
+
 // ---------------------------------------------------------------------------------------------------
 // WfTraceMain
 // ---------------------------------------------------------------------------------------------------
 template <bool DBG>
 __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTraceMain(DeviceScene sc, RenderParams rp, WfBuffers wf, int level, int n,
-                                                        int act_base, const int32_t *__restrict__ perm) {
-  // j: position in processing order (indexes the per-level scratch); i: position in the queue
-  const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+                                                        int act_base, const int32_t *__restrict__ perm, int lanes) {
+  // j: position in processing order; i: position in the level's queue; activation id = act_base + i.
+  // Only the first `lanes` lanes of a warp carry a ray (see PackedIndex).
+  const int j = PackedIndex(n, lanes);
   const int i = (perm != nullptr && j < n) ? perm[j] : j;
   unsigned long long cnt_store[DBG ? kNumCounters : 1];
   unsigned long long *cnt = cnt_store;
@@ -131,11 +147,8 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTraceMain(Devic
       o = Load3(rp.origin);
       d = Normalized(Add(Add(start, MulS(d_scan, (double)(rp.chunk_y + py))), MulS(d_pixel, (double)(rp.chunk_x + px))));
       path = 1ull;
-      wf.rq_pixel[0][i] = pixel;
-      wf.rq_path[0][i] = path;
       wf.rq_coef[0][i] = 1.0;
       wf.rq_inobj[0][i] = 0;
-      Store3(wf.rq_d[0] + (size_t)i * 3, d);
       if (live) Count<DBG>(cnt, kPrimary);
     } else {
       o = Load3(wf.rq_o[q] + (size_t)i * 3);
@@ -146,8 +159,9 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTraceMain(Devic
     const int act = act_base + i;
     wf.act_refl[act] = -1;
     wf.act_refr[act] = -1;
-    wf.act_mtl[act] = -1;
-    int ctx_mtl = -2;
+    wf.act_pixel[act] = pixel;
+    wf.act_path[act] = path;
+    int act_mtl = -2;
     D3 color = Mk(0.0, 0.0, 0.0);
     if (live) {
       double t = 0.0;
@@ -201,28 +215,109 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTraceMain(Devic
             surface = MulV(surface, SampleTexture(sc.textures[tex], sc.texture_dim[tex], u, v));
           }
           const D3 reflected = Sub(d, MulS(normal, 2 * Dot(normal, d)));
-          ctx_mtl = material;
-          wf.act_mtl[act] = material;
-          Store3(wf.ctx_point + (size_t)j * 3, P);
-          Store3(wf.ctx_normal + (size_t)j * 3, normal);
-          Store3(wf.ctx_surface + (size_t)j * 3, surface);
-          Store3(wf.ctx_reflected + (size_t)j * 3, reflected);
+          act_mtl = material;
+          Store3(wf.act_point + (size_t)act * 3, P);
+          Store3(wf.act_normal + (size_t)act * 3, normal);
+          Store3(wf.act_surface + (size_t)act * 3, surface);
+          Store3(wf.act_reflected + (size_t)act * 3, reflected);
+          Store3(wf.act_dir + (size_t)act * 3, d);
         }
       }
     }
-    wf.ctx_mtl[j] = ctx_mtl;
+    wf.act_mtl[act] = act_mtl;
     Store3(wf.act_color + (size_t)act * 3, color);
   }
   FlushCounters<DBG>(cnt, rp.counters, traced);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// WfShadow: thread = (light, hit).  Light-major task order keeps the rays of one warp aimed at one light.
+// WfSpawn: children of the level's hits -> queue of the next level (mythtracer.cc:181-225)
 // ---------------------------------------------------------------------------------------------------
 template <bool DBG>
-__global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfShadow(DeviceScene sc, RenderParams rp, WfBuffers wf, int level, int n,
-                                                     const int32_t *__restrict__ perm) {
-  const long long task = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kWfBlock) WfSpawn(DeviceScene sc, RenderParams rp, WfBuffers wf, int level, int n, int act_base) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  unsigned long long cnt_store[DBG ? kNumCounters : 1];
+  unsigned long long *cnt = cnt_store;
+  if (DBG) {
+    for (int k = 0; k < kNumCounters; k++) cnt[k] = 0;
+  }
+  const int q = level & 1, qn = q ^ 1;
+  const int act = act_base + i;
+  bool do_reflect = false, do_refract = false;
+  double coef = 0.0, refl = 0.0;
+  bool in_object = false;
+  int material = -1;
+  if (i < n) material = wf.act_mtl[act];
+  if (material >= 0 && level < rp.max_depth) {
+    const mtb_material *m = sc.materials + material;
+    coef = wf.rq_coef[q][i];
+    in_object = wf.rq_inobj[q][i] != 0;
+    refl = m->reflectance;
+    do_reflect = refl > 0.0 && coef > 0.01 && !in_object;  // mythtracer.cc:181-184
+    do_refract = m->transparency > 0.0;                    // mythtracer.cc:192
+  }
+  // ---- queue compaction: warp ballot + prefix sum, one atomic per warp ----
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned mine = (do_reflect ? 1u : 0u) + (do_refract ? 1u : 0u);
+  unsigned incl = mine;
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= (unsigned)off) incl += v;
+  }
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned base = 0;
+  if (total > 0u) {
+    if (lane == 31u) base = atomicAdd(wf.counters + 0, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+  }
+  if (mine > 0u) {
+    unsigned pos = base + incl - mine;
+    const int next_base = act_base + n;
+    if (base + total > (unsigned)wf.queue_cap || (long long)next_base + base + total > (long long)wf.act_cap) {
+      wf.counters[1] = 1u;  // overflow: the host retries the frame with larger buffers
+    } else {
+      const D3 P = Load3(wf.act_point + (size_t)act * 3);
+      const unsigned long long path = wf.act_path[act];
+      const int pixel = wf.act_pixel[act];
+      if (do_reflect) {
+        Count<DBG>(cnt, kReflect);
+        const D3 reflected = Load3(wf.act_reflected + (size_t)act * 3);
+        const D3 ro = Add(P, MulS(reflected, 0.0001));  // mythtracer.cc:70-75
+        Store3(wf.rq_o[qn] + (size_t)pos * 3, ro);
+        Store3(wf.rq_d[qn] + (size_t)pos * 3, reflected);
+        wf.sort_key[qn][pos] = RayKey(wf, ro, reflected);
+        wf.rq_coef[qn][pos] = coef * refl;
+        wf.rq_path[qn][pos] = path * 2ull;
+        wf.rq_pixel[qn][pos] = pixel;
+        wf.rq_inobj[qn][pos] = in_object ? 1 : 0;
+        wf.act_refl[act] = next_base + (int)pos;
+        pos++;
+      }
+      if (do_refract) {
+        Count<DBG>(cnt, kRefract);
+        const D3 rdir = Normalized(Load3(wf.act_dir + (size_t)act * 3));  // mythtracer.cc:208-212
+        const D3 ro = Add(P, MulS(rdir, 0.00001));                        // mythtracer.cc:214-218
+        Store3(wf.rq_o[qn] + (size_t)pos * 3, ro);
+        Store3(wf.rq_d[qn] + (size_t)pos * 3, rdir);
+        wf.sort_key[qn][pos] = RayKey(wf, ro, rdir);
+        wf.rq_coef[qn][pos] = coef;
+        wf.rq_path[qn][pos] = path * 2ull + 1ull;
+        wf.rq_pixel[qn][pos] = pixel;
+        wf.rq_inobj[qn][pos] = in_object ? 0 : 1;
+        wf.act_refr[act] = next_base + (int)pos;
+      }
+    }
+  }
+  if (DBG) FlushCounters<true>(cnt, rp.counters, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// WfShadow: thread = (light, activation).  Light-major task order keeps the rays of a warp aimed at one light.
+// ---------------------------------------------------------------------------------------------------
+template <bool DBG>
+__global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfShadow(DeviceScene sc, RenderParams rp, WfBuffers wf, int act_begin, int n,
+                                                     int lanes) {
+  const long long task = PackedIndex64((long long)n * sc.n_lights, lanes);
   unsigned long long cnt_store[DBG ? kNumCounters : 1];
   unsigned long long *cnt = cnt_store;
   if (DBG) {
@@ -231,9 +326,9 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfShadow(DeviceSc
   unsigned traced = 0;
   if (task < (long long)n * sc.n_lights) {
     const int li = (int)(task / n);
-    const int i = (int)(task - (long long)li * n);
-    if (wf.ctx_mtl[i] >= 0) {
-      const D3 P = Load3(wf.ctx_point + (size_t)i * 3);
+    const int act = act_begin + (int)(task - (long long)li * n);
+    if (wf.act_mtl[act] >= 0) {
+      const D3 P = Load3(wf.act_point + (size_t)act * 3);
       const D3 lpos = Load3(sc.lights[li].position);
       const D3 ldir = Normalized(Sub(lpos, P));
       D3 power = Mk(1.0, 1.0, 1.0);
@@ -267,126 +362,56 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfShadow(DeviceSc
         }
       }
       traced = segments;
-      Store3(wf.sh_power + ((size_t)li * wf.queue_cap + i) * 3, power);
-      wf.sh_flags[(size_t)li * wf.queue_cap + i] = (in_shadow ? 1u : 0u) | (segments << 1);
-      if (rp.n_rays != nullptr) atomicAdd(rp.n_rays + wf.rq_pixel[level & 1][perm != nullptr ? perm[i] : i], segments);
+      Store3(wf.sh_power + ((size_t)li * wf.act_cap + act) * 3, power);
+      wf.sh_flags[(size_t)li * wf.act_cap + act] = (in_shadow ? 1u : 0u) | (segments << 1);
+      if (rp.n_rays != nullptr) atomicAdd(rp.n_rays + wf.act_pixel[act], segments);
     }
   }
   FlushCounters<DBG>(cnt, rp.counters, traced);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// WfLightSpawn
+// WfLight: Phong sum over the lights in scene order (mythtracer.cc:78-178)
 // ---------------------------------------------------------------------------------------------------
-template <bool DBG>
-__global__ void __launch_bounds__(kWfBlock) WfLightSpawn(DeviceScene sc, RenderParams rp, WfBuffers wf, int level, int n,
-                                                         int act_base, const int32_t *__restrict__ perm) {
-  const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  const int i = (perm != nullptr && j < n) ? perm[j] : j;
-  unsigned long long cnt_store[DBG ? kNumCounters : 1];
-  unsigned long long *cnt = cnt_store;
-  if (DBG) {
-    for (int k = 0; k < kNumCounters; k++) cnt[k] = 0;
-  }
-  const int q = level & 1, qn = q ^ 1;
-  bool do_reflect = false, do_refract = false;
-  D3 P = Mk(0, 0, 0), m_d = Mk(0, 0, 0), reflected = Mk(0, 0, 0);
-  double coef = 0.0, refl = 0.0;
-  bool in_object = false;
-  int material = -1;
-  if (j < n) material = wf.ctx_mtl[j];
-  if (material >= 0) {
-    const mtb_material *m = sc.materials + material;
-    P = Load3(wf.ctx_point + (size_t)j * 3);
-    const D3 normal = Load3(wf.ctx_normal + (size_t)j * 3);
-    const D3 surface = Load3(wf.ctx_surface + (size_t)j * 3);
-    reflected = Load3(wf.ctx_reflected + (size_t)j * 3);
-    m_d = Load3(wf.rq_d[q] + (size_t)i * 3);
-    const unsigned long long path = wf.rq_path[q][i];
-    D3 color = Mk(0.0, 0.0, 0.0);
-    unsigned long long sig = 0;
-    for (int li = 0; li < sc.n_lights; li++) {  // mythtracer.cc:78-178, lights in scene order
-      const mtb_light *lt = sc.lights + li;
-      const D3 ldir = Normalized(Sub(Load3(lt->position), P));
-      const D3 lamb = Load3(lt->ambient);
-      color = Add(color, MulV(lamb, surface));
-      D3 power = Load3(wf.sh_power + ((size_t)li * wf.queue_cap + j) * 3);
-      const unsigned flags = wf.sh_flags[(size_t)li * wf.queue_cap + j];
-      const bool in_shadow = (flags & 1u) != 0u;
-      sig += Mix64(path, 2ull + (unsigned long long)li, (unsigned long long)flags);
-      power.x = SMax(power.x, lamb.x);
-      power.y = SMax(power.y, lamb.y);
-      power.z = SMax(power.z, lamb.z);
-      color = Add(color, MulV(MulV(MulS(MulV(Load3(m->diffuse), surface), Dot(normal, ldir)), Load3(lt->diffuse)), power));
-      if (!in_shadow) {
-        const double refl_dot = Dot(Neg(m_d), reflected);
-        if (refl_dot > 0) {
-          color = Add(color, MulV(MulS(MulV(Load3(m->specular), surface), pow(refl_dot, m->specular_exp)), Load3(lt->specular)));
-        }
-      }
-    }
-    if (rp.sig_shadow != nullptr && sc.n_lights > 0) {
-      atomicAdd(reinterpret_cast<unsigned long long *>(rp.sig_shadow) + wf.rq_pixel[q][i], sig);
-    }
-    Store3(wf.act_color + (size_t)(act_base + i) * 3, color);
-    coef = wf.rq_coef[q][i];
-    in_object = wf.rq_inobj[q][i] != 0;
-    refl = m->reflectance;
-    do_reflect = level < rp.max_depth && refl > 0.0 && coef > 0.01 && !in_object;  // mythtracer.cc:181-184
-    do_refract = level < rp.max_depth && m->transparency > 0.0;                    // mythtracer.cc:192
-  }
-  // ---- queue compaction: warp ballot + prefix sum, one atomic per warp ----
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned mine = (do_reflect ? 1u : 0u) + (do_refract ? 1u : 0u);
-  unsigned incl = mine;
-  for (int off = 1; off < 32; off <<= 1) {
-    const unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
-    if (lane >= (unsigned)off) incl += v;
-  }
-  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-  unsigned base = 0;
-  if (total > 0u) {
-    if (lane == 31u) base = atomicAdd(wf.counters + 0, total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-  }
-  if (mine > 0u) {
-    unsigned pos = base + incl - mine;
-    const int act = act_base + i;
-    const int next_base = act_base + n;
-    const unsigned long long path = wf.rq_path[q][i];
-    const int pixel = wf.rq_pixel[q][i];
-    if (base + total > (unsigned)wf.queue_cap || (long long)next_base + base + total > (long long)wf.act_cap) {
-      wf.counters[1] = 1u;  // overflow: the host retries the frame with larger buffers
-    } else {
-      if (do_reflect) {
-        Count<DBG>(cnt, kReflect);
-        const D3 ro = Add(P, MulS(reflected, 0.0001));  // mythtracer.cc:70-75
-        Store3(wf.rq_o[qn] + (size_t)pos * 3, ro);
-        Store3(wf.rq_d[qn] + (size_t)pos * 3, reflected);
-        wf.sort_key[qn][pos] = RayKey(wf, ro, reflected);
-        wf.rq_coef[qn][pos] = coef * refl;
-        wf.rq_path[qn][pos] = path * 2ull;
-        wf.rq_pixel[qn][pos] = pixel;
-        wf.rq_inobj[qn][pos] = in_object ? 1 : 0;
-        wf.act_refl[act] = next_base + (int)pos;
-        pos++;
-      }
-      if (do_refract) {
-        Count<DBG>(cnt, kRefract);
-        const D3 rdir = Normalized(m_d);                // mythtracer.cc:208-212
-        const D3 ro = Add(P, MulS(rdir, 0.00001));      // mythtracer.cc:214-218
-        Store3(wf.rq_o[qn] + (size_t)pos * 3, ro);
-        Store3(wf.rq_d[qn] + (size_t)pos * 3, rdir);
-        wf.sort_key[qn][pos] = RayKey(wf, ro, rdir);
-        wf.rq_coef[qn][pos] = coef;
-        wf.rq_path[qn][pos] = path * 2ull + 1ull;
-        wf.rq_pixel[qn][pos] = pixel;
-        wf.rq_inobj[qn][pos] = in_object ? 0 : 1;
-        wf.act_refr[act] = next_base + (int)pos;
+__global__ void __launch_bounds__(kWfBlock) WfLight(DeviceScene sc, RenderParams rp, WfBuffers wf, int act_begin, int n) {
+  const int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (k >= n) return;
+  const int act = act_begin + k;
+  const int material = wf.act_mtl[act];
+  if (material < 0) return;
+  const mtb_material *m = sc.materials + material;
+  const D3 P = Load3(wf.act_point + (size_t)act * 3);
+  const D3 normal = Load3(wf.act_normal + (size_t)act * 3);
+  const D3 surface = Load3(wf.act_surface + (size_t)act * 3);
+  const D3 reflected = Load3(wf.act_reflected + (size_t)act * 3);
+  const D3 m_d = Load3(wf.act_dir + (size_t)act * 3);
+  const unsigned long long path = wf.act_path[act];
+  D3 color = Mk(0.0, 0.0, 0.0);
+  unsigned long long sig = 0;
+  for (int li = 0; li < sc.n_lights; li++) {
+    const mtb_light *lt = sc.lights + li;
+    const D3 ldir = Normalized(Sub(Load3(lt->position), P));
+    const D3 lamb = Load3(lt->ambient);
+    color = Add(color, MulV(lamb, surface));
+    D3 power = Load3(wf.sh_power + ((size_t)li * wf.act_cap + act) * 3);
+    const unsigned flags = wf.sh_flags[(size_t)li * wf.act_cap + act];
+    const bool in_shadow = (flags & 1u) != 0u;
+    sig += Mix64(path, 2ull + (unsigned long long)li, (unsigned long long)flags);
+    power.x = SMax(power.x, lamb.x);
+    power.y = SMax(power.y, lamb.y);
+    power.z = SMax(power.z, lamb.z);
+    color = Add(color, MulV(MulV(MulS(MulV(Load3(m->diffuse), surface), Dot(normal, ldir)), Load3(lt->diffuse)), power));
+    if (!in_shadow) {
+      const double refl_dot = Dot(Neg(m_d), reflected);
+      if (refl_dot > 0) {
+        color = Add(color, MulV(MulS(MulV(Load3(m->specular), surface), pow(refl_dot, m->specular_exp)), Load3(lt->specular)));
       }
     }
   }
-  if (DBG) FlushCounters<true>(cnt, rp.counters, 0);
+  if (rp.sig_shadow != nullptr && sc.n_lights > 0) {
+    atomicAdd(reinterpret_cast<unsigned long long *>(rp.sig_shadow) + wf.act_pixel[act], sig);
+  }
+  Store3(wf.act_color + (size_t)act * 3, color);
 }
 
 // parent += child * Refl ; parent += (child * Tf) * Tr   (mythtracer.cc:185-189, 220-224)
@@ -421,6 +446,15 @@ __global__ void __launch_bounds__(256) WfResolve(RenderParams rp, WfBuffers wf, 
 
 }  // namespace
 
+// Lanes per warp for a queue of `n` items: full warps once the queue fills the machine (148 SMs x 32
+// resident warps), otherwise the largest power of two that still spreads it over all warp slots.
+static int PackLanes(long long n) {
+  const long long slots = 148LL * 32;
+  int lanes = 32;
+  while (lanes > 4 && n < slots * lanes) lanes >>= 1;
+  return lanes;
+}
+
 void LaunchWfSort(const WfBuffers &wf, int level, int n, cudaStream_t stream) {
   if (n <= 0) return;
   cudaMemsetAsync(wf.sort_hist, 0, sizeof(uint32_t) << kWfSortBits, stream);
@@ -433,38 +467,46 @@ void LaunchWfSort(const WfBuffers &wf, int level, int n, cudaStream_t stream) {
 void LaunchWfTraceMain(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
                        int act_base, bool sorted, bool debug_build, cudaStream_t stream) {
   if (n <= 0) return;
-  const int blocks = (n + kWfBlock - 1) / kWfBlock;
+  const int lanes = level == 0 ? 32 : PackLanes(n);  // level 0 maps warps to 8x4 pixel tiles
+  const long long warps = ((long long)n + lanes - 1) / lanes;
+  const int blocks = (int)((warps * 32 + kWfBlock - 1) / kWfBlock);
   const int32_t *perm = sorted ? wf.perm : nullptr;
   if (debug_build) {
-    WfTraceMain<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base, perm);
+    WfTraceMain<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base, perm, lanes);
   } else {
-    WfTraceMain<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base, perm);
+    WfTraceMain<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base, perm, lanes);
   }
 }
 
-void LaunchWfShadow(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
-                    bool sorted, bool debug_build, cudaStream_t stream) {
-  const long long tasks = (long long)n * sc.n_lights;
-  if (tasks <= 0) return;
-  const int blocks = (int)((tasks + kWfBlock - 1) / kWfBlock);
-  const int32_t *perm = sorted ? wf.perm : nullptr;
-  if (debug_build) {
-    WfShadow<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, perm);
-  } else {
-    WfShadow<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, perm);
-  }
-}
-
-void LaunchWfLightSpawn(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
-                        int act_base, bool sorted, bool debug_build, cudaStream_t stream) {
+void LaunchWfSpawn(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
+                   int act_base, bool debug_build, cudaStream_t stream) {
   if (n <= 0) return;
   const int blocks = (n + kWfBlock - 1) / kWfBlock;
-  const int32_t *perm = sorted ? wf.perm : nullptr;
   if (debug_build) {
-    WfLightSpawn<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base, perm);
+    WfSpawn<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base);
   } else {
-    WfLightSpawn<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base, perm);
+    WfSpawn<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base);
   }
+}
+
+void LaunchWfShadow(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int act_begin, int n,
+                    bool debug_build, cudaStream_t stream) {
+  const long long tasks = (long long)n * sc.n_lights;
+  if (tasks <= 0) return;
+  const int lanes = PackLanes(tasks);
+  const long long warps = (tasks + lanes - 1) / lanes;
+  const int blocks = (int)((warps * 32 + kWfBlock - 1) / kWfBlock);
+  if (debug_build) {
+    WfShadow<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, act_begin, n, lanes);
+  } else {
+    WfShadow<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, act_begin, n, lanes);
+  }
+}
+
+void LaunchWfLight(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int act_begin, int n,
+                   cudaStream_t stream) {
+  if (n <= 0) return;
+  WfLight<<<(n + kWfBlock - 1) / kWfBlock, kWfBlock, 0, stream>>>(sc, rp, wf, act_begin, n);
 }
 
 void LaunchWfFold(const DeviceScene &sc, const WfBuffers &wf, int begin, int end, cudaStream_t stream) {

@@ -114,8 +114,15 @@ typedef struct {
 
 #define MTB_FLAG_COUNT_WORK 1u   /* fill the n_* work counters (counting kernels) */
 #define MTB_FLAG_NO_LIST_BVH 2u  /* scan every node list linearly, like the reference (A/B measurements) */
-#define MTB_FLAG_WAVEFRONT 4u    /* wavefront pipeline instead of the per-pixel megakernel */
+/* Pipeline choice.  With neither bit set the library picks per call from the measured crossover
+ * (DESIGN.md section 6): the per-pixel megakernel when a device renders >= MTB_AUTO_MEGA_PIXELS pixels,
+ * the wavefront pipeline below that (its critical path is much shorter, so it wins on small shares of
+ * a frame, e.g. 1/8 of a 1080p frame per GPU). */
+#define MTB_FLAG_WAVEFRONT 4u    /* force the wavefront pipeline */
+#define MTB_FLAG_MEGAKERNEL 16u  /* force the per-pixel megakernel */
 #define MTB_FLAG_RAY_SORT 8u     /* wavefront: counting-sort every queue by origin cell + direction octant (measured: no gain) */
+#define MTB_FLAG_NO_TILE_ORDER 32u /* megakernel: always launch tiles in scanline order (A/B of the cost-aware launch order) */
+#define MTB_AUTO_MEGA_PIXELS 700000
 
 /* ---- life cycle -------------------------------------------------------------------------------- */
 

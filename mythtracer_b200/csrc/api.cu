@@ -72,6 +72,10 @@ struct DeviceState {
   DeviceBuffer<uint64_t> sig_hits, sig_shadow;
   DeviceBuffer<uint32_t> n_rays;
   DeviceBuffer<unsigned long long> counters;
+  // cost-aware tile order of the megakernel (previous frame's per-tile ray counts)
+  DeviceBuffer<uint32_t> tile_cost;
+  DeviceBuffer<int32_t> tile_order;
+  long long tile_signature = -1;  // geometry the costs were recorded for
   // intersect scratch
   DeviceBuffer<double> q_origins, q_dirs, q_t, q_point;
   DeviceBuffer<int32_t> q_tri;
@@ -97,7 +101,7 @@ struct DeviceState {
   void FreeAll() {
     nodes.Free(); slots.Free(); shade.Free(); bvh.Free(); list_order.Free(); materials.Free(); tex_objects.Free();
     tex_dims.Free(); lights.Free(); rgb.Free(); dbg.Free(); sig_hits.Free(); sig_shadow.Free(); n_rays.Free();
-    counters.Free(); q_origins.Free(); q_dirs.Free(); q_t.Free(); q_point.Free(); q_tri.Free();
+    counters.Free(); tile_cost.Free(); tile_order.Free(); q_origins.Free(); q_dirs.Free(); q_t.Free(); q_point.Free(); q_tri.Free();
     for (int k = 0; k < 2; k++) {
       wf_rq_o[k].Free(); wf_rq_d[k].Free(); wf_rq_coef[k].Free(); wf_rq_path[k].Free(); wf_rq_pixel[k].Free();
       wf_rq_inobj[k].Free();
@@ -509,7 +513,10 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
     // a peer's scratch frame must not be overwritten while device 0 still gathers the previous one
     if (g > 0) MTB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->dev[0].ev_gathered, 0));
     MTB_CUDA(ctx, cudaEventRecord(d.ev_start, s));
-    if ((ctx->flags & MTB_FLAG_WAVEFRONT) != 0) {
+    const long long my_pixels = (long long)blocks * 64;
+    const bool wavefront = (ctx->flags & MTB_FLAG_WAVEFRONT) != 0 ||
+                           ((ctx->flags & MTB_FLAG_MEGAKERNEL) == 0 && my_pixels < MTB_AUTO_MEGA_PIXELS);
+    if (wavefront) {
       // the wavefront kernels accumulate the taps with atomics
       if (want_taps) {
         MTB_CUDA(ctx, cudaMemsetAsync(d.sig_hits.ptr, 0, npx * 8, s));
@@ -519,6 +526,22 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
       const int wrc = RunWavefront(ctx, &d, p, blocks, debug_build, s);
       if (wrc != MTB_OK) return wrc;
     } else {
+      if (blocks > 0 && (ctx->flags & MTB_FLAG_NO_TILE_ORDER) == 0) {
+        // launch order from the previous frame of the same geometry; the first frame runs in scanline order
+        const long long signature = ((long long)chunk_w << 40) ^ ((long long)chunk_h << 20) ^ ((long long)owner << 8) ^ plan.owners ^
+                                    ((long long)blocks << 4);
+        MTB_CUDA(ctx, d.tile_cost.Reserve((size_t)blocks));
+        MTB_CUDA(ctx, d.tile_order.Reserve((size_t)blocks));
+        p.tile_cost = d.tile_cost.ptr;
+        if (signature == d.tile_signature) {
+          mtb::LaunchBuildTileOrder(d.tile_cost.ptr, d.tile_order.ptr, blocks, s);
+          ctx->launches++;
+          p.tile_order = d.tile_order.ptr;
+        } else {
+          MTB_CUDA(ctx, cudaMemsetAsync(d.tile_cost.ptr, 0, (size_t)blocks * sizeof(uint32_t), s));
+          d.tile_signature = signature;
+        }
+      }
       mtb::LaunchRenderMega(d.scene, p, blocks, debug_build, s);
       if (blocks > 0) ctx->launches++;
       MTB_CUDA(ctx, cudaGetLastError());

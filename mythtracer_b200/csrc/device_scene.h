@@ -47,6 +47,10 @@ struct RenderParams {
   uint64_t *sig_shadow;
   uint32_t *n_rays;
   unsigned long long *counters;  // kNumCounters, nullable unless the counting build runs
+  // Cost-aware tile scheduling of the megakernel: block b renders tile tile_order[b] (NULL: b) and adds the
+  // rays it traced to tile_cost[tile]; the next frame launches the most expensive tiles first.
+  const int32_t *tile_order;
+  uint32_t *tile_cost;
 };
 
 struct IntersectParams {
@@ -106,6 +110,8 @@ void LaunchWfFold(const DeviceScene &sc, const WfBuffers &wf, int begin, int end
 void LaunchWfResolve(const RenderParams &rp, const WfBuffers &wf, int n_slots, cudaStream_t stream);
 
 // megakernel.cu
+// Builds tile_order (descending cost, bucketed) from tile_cost and clears tile_cost for the coming frame.
+void LaunchBuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles, cudaStream_t stream);
 void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp, int n_blocks, bool debug_build,
                       cudaStream_t stream);
 void LaunchIntersect(const DeviceScene &sc, const IntersectParams &ip, bool debug_build, cudaStream_t stream);

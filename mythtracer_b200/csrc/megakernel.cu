@@ -31,8 +31,9 @@ template <bool DBG>
 __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega(DeviceScene sc, RenderParams rp) {
   // block -> 8x8 tile of one of this launch's strips (a strip = 8 image rows; strips are interleaved
   // across devices / processes, the in-process form of the reference's master/worker tiling)
-  const int strip = rp.strip_first + ((int)blockIdx.x / rp.tiles_x) * rp.strip_stride;
-  const int px = ((int)blockIdx.x % rp.tiles_x) * kTile + (int)(threadIdx.x & 7u);
+  const int tile_id = rp.tile_order != nullptr ? rp.tile_order[blockIdx.x] : (int)blockIdx.x;
+  const int strip = rp.strip_first + (tile_id / rp.tiles_x) * rp.strip_stride;
+  const int px = (tile_id % rp.tiles_x) * kTile + (int)(threadIdx.x & 7u);
   const int py = strip * kTile + (int)(threadIdx.x >> 3);
   const bool live = px < rp.chunk_w && py < rp.chunk_h;
 
@@ -294,6 +295,11 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
     if (rp.n_rays != nullptr) rp.n_rays[pix] = n_rays;
   }
 
+  if (rp.tile_cost != nullptr) {  // what this tile cost, for the next frame's launch order
+    unsigned v = n_rays;
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31u) == 0u) atomicAdd(rp.tile_cost + tile_id, v);
+  }
   if (DBG && rp.counters != nullptr) {
     for (int i = 0; i < kNumCounters; i++) {
       unsigned long long v = cnt[i];
@@ -343,7 +349,39 @@ __global__ void __launch_bounds__(128) IntersectKernel(DeviceScene sc, Intersect
   }
 }
 
+// Counting sort of the tiles by cost bucket (log2 of the ray count, most expensive first).  One block.
+__global__ void __launch_bounds__(1024) BuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles) {
+  __shared__ unsigned hist[33];
+  __shared__ unsigned offset[33];
+  if (threadIdx.x < 33) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+    const unsigned c = tile_cost[t];
+    atomicAdd(&hist[c == 0u ? 0 : 32 - __clz((int)c)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned run = 0;
+    for (int b = 32; b >= 0; b--) {
+      offset[b] = run;
+      run += hist[b];
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+    const unsigned c = tile_cost[t];
+    const unsigned pos = atomicAdd(&offset[c == 0u ? 0 : 32 - __clz((int)c)], 1u);
+    tile_order[pos] = t;
+    tile_cost[t] = 0;
+  }
+}
+
 }  // namespace
+
+void LaunchBuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles, cudaStream_t stream) {
+  if (n_tiles <= 0) return;
+  BuildTileOrder<<<1, 1024, 0, stream>>>(tile_cost, tile_order, n_tiles);
+}
 
 void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp, int n_blocks, bool debug_build,
                       cudaStream_t stream) {

@@ -17,7 +17,10 @@ MAX_RGB_FRACTION = 1e-5
 
 
 def _tracer(product_lib, depth, flags=0, devices=None):
-    from mythtracer_b200 import MythTracer
+    """flags without a pipeline bit: force the megakernel (small test frames would auto-select the wavefront)."""
+    from mythtracer_b200 import MTB_FLAG_MEGAKERNEL, MTB_FLAG_WAVEFRONT, MythTracer
+    if not flags & (MTB_FLAG_WAVEFRONT | MTB_FLAG_MEGAKERNEL):
+        flags |= MTB_FLAG_MEGAKERNEL
     return MythTracer(devices=devices, max_depth=depth, flags=flags)
 
 
@@ -63,10 +66,14 @@ def test_c1_full_frame(product_lib, oracle_mod, scene_dir):
     _assert_render_equal(gpu, cpu, "C1")
     assert gpu["stats"]["n_shade"] == cpu["stats"]["n_shade"]
     # the fast build (no counters) must give the same bytes
-    mt.set_flags(0)
+    from mythtracer_b200 import MTB_FLAG_MEGAKERNEL
+    mt.set_flags(MTB_FLAG_MEGAKERNEL)
     fast = mt.render_chunk(files.camera, w, h, 0, 0, w, h)
     assert np.array_equal(fast["rgb"], gpu["rgb"])
     assert fast["stats"]["rays"] == cpu["stats"]["rays"]
+    mt.set_flags(0)  # automatic choice (wavefront at this size): same bytes
+    auto = mt.render_chunk(files.camera, w, h, 0, 0, w, h)
+    assert np.array_equal(auto["rgb"], gpu["rgb"]) and auto["stats"]["rays"] == cpu["stats"]["rays"]
 
 
 def test_c1_depths_and_lights(product_lib, oracle_mod, scene_dir):
@@ -176,12 +183,12 @@ def test_intersect_rays_random(product_lib, oracle_mod, scene_dir):
 
 def test_list_bvh_is_transparent(product_lib, oracle_mod, scene_dir):
     """The list-BVH only prunes work: with and without it the results are byte identical."""
-    from mythtracer_b200 import MTB_FLAG_COUNT_WORK, MTB_FLAG_NO_LIST_BVH
+    from mythtracer_b200 import MTB_FLAG_COUNT_WORK, MTB_FLAG_MEGAKERNEL, MTB_FLAG_NO_LIST_BVH
     files, cfg = scenes.config_scene("C2", scene_dir, scale=0.2)
-    mt, orc = _load_pair(product_lib, oracle_mod, files, 3, MTB_FLAG_COUNT_WORK)
+    mt, orc = _load_pair(product_lib, oracle_mod, files, 3, MTB_FLAG_COUNT_WORK | MTB_FLAG_MEGAKERNEL)
     w, h = 256, 144
     a = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
-    mt.set_flags(MTB_FLAG_COUNT_WORK | MTB_FLAG_NO_LIST_BVH)
+    mt.set_flags(MTB_FLAG_COUNT_WORK | MTB_FLAG_MEGAKERNEL | MTB_FLAG_NO_LIST_BVH)
     b = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
     for k in ("rgb", "line_no", "n_rays", "sig_hits", "sig_shadow"):
         assert np.array_equal(a[k], b[k]), k
@@ -329,9 +336,10 @@ def test_wavefront_pipeline_parity(product_lib, oracle_mod, scene_dir, name, sca
     gpu = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
     cpu = orc.render(files.camera, w, h, depth=cfg["depth"], taps=True)
     _assert_render_equal(gpu, cpu, name + " wavefront")
+    from mythtracer_b200 import MTB_FLAG_MEGAKERNEL
     mt.set_flags(MTB_FLAG_WAVEFRONT)
     fast = mt.render_chunk(files.camera, w, h, 0, 0, w, h)
-    mt.set_flags(0)
+    mt.set_flags(MTB_FLAG_MEGAKERNEL)
     mega = mt.render_chunk(files.camera, w, h, 0, 0, w, h)
     assert np.array_equal(fast["rgb"], mega["rgb"]) and np.array_equal(fast["rgb"], gpu["rgb"])
     assert fast["stats"]["rays"] == mega["stats"]["rays"] == cpu["stats"]["rays"]
@@ -364,3 +372,24 @@ def test_wavefront_depths_lights_lattice_and_tiles(product_lib, oracle_mod, scen
     gpu = mt2.render_chunk(cam, 65, 49, 0, 0, 65, 49, debug=True, taps=True)
     cpu = orc2.render(cam, 65, 49, depth=5, taps=True)
     _assert_render_equal(gpu, cpu, "wavefront lattice")
+
+
+@pytest.mark.parametrize("pipeline", ["mega", "wavefront"])
+def test_textured_light_terms_in_isolation(product_lib, oracle_mod, scene_dir, pipeline):
+    """Ambient-only, diffuse-only and specular-only lights on the textured scene, both pipelines: each Phong
+    term (mythtracer.cc:83-84,163-167,169-177) is compared on its own, so a wrong surface colour cannot hide
+    behind the other terms.  (A register-capped build of the megakernel once lost one bilinear tap here.)"""
+    from mythtracer_b200 import Light, MTB_FLAG_MEGAKERNEL, MTB_FLAG_WAVEFRONT
+    files, cfg = scenes.config_scene("C2", scene_dir, 0.1)
+    flags = MTB_FLAG_MEGAKERNEL if pipeline == "mega" else MTB_FLAG_WAVEFRONT
+    mt, orc = _load_pair(product_lib, oracle_mod, files, 2, flags)
+    w, h = 200, 112
+    pos = (200.0, 100.0, 160.0)
+    zero, one = (0.0, 0.0, 0.0), (1.0, 1.0, 1.0)
+    for amb, dif, spe in [(one, zero, zero), (zero, one, zero), (zero, zero, one), ((0.2, 0.3, 0.4), (0.9, 0.8, 0.7), (0.5, 0.6, 0.7))]:
+        rig = [pos + amb + dif + spe, (120.0, 100.0, 250.0) + zero + dif + spe]
+        mt.GetScene().lights = [Light.from_tuple(l) for l in rig]
+        orc.set_lights(rig)
+        gpu = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
+        cpu = orc.render(files.camera, w, h, depth=2, taps=True)
+        _assert_render_equal(gpu, cpu, "%s terms %s" % (pipeline, (amb, dif, spe)))

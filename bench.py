@@ -260,9 +260,6 @@ def _run_ours(args):
     W, H, depth = cfg["width"], cfg["height"], cfg["depth"]
 
     base_flags = {"wavefront": MTB_FLAG_WAVEFRONT, "mega": MTB_FLAG_MEGAKERNEL, "auto": 0}[args.pipeline]
-    # what "auto" resolves to for this share of the frame (same rule as the library, MTB_AUTO_MEGA_PIXELS)
-    share = ((tiles.n_strips(H) + world - 1) // world) * 8 * ((W + 7) // 8) * 8
-    pipeline_used = args.pipeline if args.pipeline != "auto" else ("mega" if share >= 700000 else "wavefront")
     mt = MythTracer(devices=[local_rank], max_depth=depth, flags=base_flags)
     t0 = time.time()
     if not mt.LoadObj(files.obj_path):
@@ -294,8 +291,10 @@ def _run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- warm-up, then K timed steps (device-resident) ----
-    for _ in range(max(args.warmup, 3)):
+    # ---- warm-up, then K timed steps (device-resident).  The automatic pipeline choice measures both
+    # pipelines during the first four frames of a geometry, so the warm-up covers at least five ----
+    n_warm = max(args.warmup, 5 if args.pipeline == "auto" else 3)
+    for _ in range(n_warm):
         step_device()
     barrier()
     mt.read_counters()
@@ -325,6 +324,7 @@ def _run_ours(args):
     rays_per_frame = total_rays / args.steps
     value = total_rays / (elapsed_ms * 1e-3) / 1e6
 
+    pipeline_used, tune_mega_ms, tune_wf_ms = mt.pipeline_in_use()
     # ---- kernel-only time of the dominant kernel (RenderMega), this rank, per launch ----
     kernel_ms = []
     for _ in range(min(args.steps, 5)):
@@ -416,10 +416,11 @@ def _run_ours(args):
 
     lights_bytes = 96 * len(files.lights)
     line = {
-        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": config_dict(files, cfg, world, {"pipeline": pipeline_used, "rays_per_frame": rays_per_frame, "scene_load_s": load_s,
+        "config": config_dict(files, cfg, world, {"pipeline": pipeline_used, "pipeline_choice": args.pipeline, "autotune_ms": {"mega": tune_mega_ms, "wavefront": tune_wf_ms},
+                                                 "rays_per_frame": rays_per_frame, "scene_load_s": load_s,
                                                  "octree_nodes": info["n_nodes"], "tree_depth": info["tree_depth"],
                                                  "device_scene_bytes": info["device_bytes"]}),
         "roofline": roofline,

@@ -114,15 +114,15 @@ typedef struct {
 
 #define MTB_FLAG_COUNT_WORK 1u   /* fill the n_* work counters (counting kernels) */
 #define MTB_FLAG_NO_LIST_BVH 2u  /* scan every node list linearly, like the reference (A/B measurements) */
-/* Pipeline choice.  With neither bit set the library picks per call from the measured crossover
- * (DESIGN.md section 6): the per-pixel megakernel when a device renders >= MTB_AUTO_MEGA_PIXELS pixels,
- * the wavefront pipeline below that (its critical path is much shorter, so it wins on small shares of
- * a frame, e.g. 1/8 of a 1080p frame per GPU). */
+/* Pipeline choice.  With neither bit set the library decides at run time: on the first frames of a given
+ * geometry (chunk size, partition, depth, light count) it times the per-pixel megakernel (second frame, once
+ * its cost-aware tile order is warm) and the wavefront pipeline (fourth frame, once its buffers exist) and
+ * keeps the faster one from the fifth frame on.  Both
+ * produce identical bytes, so the choice is invisible in the output. */
 #define MTB_FLAG_WAVEFRONT 4u    /* force the wavefront pipeline */
 #define MTB_FLAG_MEGAKERNEL 16u  /* force the per-pixel megakernel */
 #define MTB_FLAG_RAY_SORT 8u     /* wavefront: counting-sort every queue by origin cell + direction octant (measured: no gain) */
 #define MTB_FLAG_NO_TILE_ORDER 32u /* megakernel: always launch tiles in scanline order (A/B of the cost-aware launch order) */
-#define MTB_AUTO_MEGA_PIXELS 700000
 
 /* ---- life cycle -------------------------------------------------------------------------------- */
 
@@ -192,6 +192,9 @@ int mtb_render_chunk_device(mtb_context *ctx, const mtb_camera *cam, int image_w
  * read; synchronises every device of the context and resets the counters. */
 int mtb_read_counters(mtb_context *ctx, mtb_stats *stats);
 
+/* Automatic pipeline choice on device 0: 0 = megakernel, 1 = wavefront, -1 = still measuring; the two
+ * timed frames (ms) are returned when the pointers are non-NULL. */
+int mtb_pipeline_in_use(const mtb_context *ctx, float *mega_ms, float *wavefront_ms);
 /* Number of kernels of this library launched on this context so far (bench.py's gpu_launches). */
 uint64_t mtb_launch_count(const mtb_context *ctx);
 

@@ -62,7 +62,7 @@ EXPORTED_SYMBOLS = [
     "mtb_create", "mtb_create_host", "mtb_destroy", "mtb_last_error", "mtb_device_count", "mtb_scene_upload", "mtb_load_obj",
     "mtb_set_lights", "mtb_scene_info", "mtb_scene_read", "mtb_scene_material_name", "mtb_scene_texture_name", "mtb_scene_texture", "mtb_load_mtl",
     "mtb_scene_triangle_nodes", "mtb_set_flags", "mtb_set_partition", "mtb_render_chunk",
-    "mtb_render_chunk_device", "mtb_read_counters", "mtb_launch_count", "mtb_intersect_rays", "mtb_camera_sensor", "mtb_version",
+    "mtb_render_chunk_device", "mtb_read_counters", "mtb_launch_count", "mtb_pipeline_in_use", "mtb_intersect_rays", "mtb_camera_sensor", "mtb_version",
 ]
 
 
@@ -114,6 +114,7 @@ def load_library():
     lib.mtb_render_chunk.argtypes = [vp, vp] + [i32] * 7 + [vp, vp, vp, vp]
     lib.mtb_render_chunk_device.argtypes = [vp, vp] + [i32] * 7 + [vp, vp, vp]
     lib.mtb_read_counters.argtypes = [vp, vp]
+    lib.mtb_pipeline_in_use.argtypes = [vp, vp, vp]
     lib.mtb_launch_count.argtypes = [vp]
     lib.mtb_launch_count.restype = ctypes.c_uint64
     lib.mtb_intersect_rays.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp]
@@ -421,6 +422,13 @@ class MythTracer:
 
     def push_lights(self):
         self._push_lights()
+
+    def pipeline_in_use(self):
+        """('mega' | 'wavefront' | 'measuring', mega_ms, wavefront_ms) of the automatic choice on device 0."""
+        a, b = ctypes.c_float(0), ctypes.c_float(0)
+        rc = self._lib.mtb_pipeline_in_use(self._ctx, ctypes.cast(ctypes.byref(a), ctypes.c_void_p),
+                                           ctypes.cast(ctypes.byref(b), ctypes.c_void_p))
+        return {0: "mega", 1: "wavefront"}.get(rc, "measuring"), a.value, b.value
 
     def launch_count(self) -> int:
         return int(self._lib.mtb_launch_count(self._ctx))

@@ -76,6 +76,12 @@ struct DeviceState {
   DeviceBuffer<uint32_t> tile_cost;
   DeviceBuffer<int32_t> tile_order;
   long long tile_signature = -1;  // geometry the costs were recorded for
+  // run-time choice between the two pipelines (flags without a pipeline bit): both are timed once per
+  // geometry (megakernel with a warm tile order, then wavefront) and the faster one is kept
+  long long tune_signature = -1;
+  int tune_stage = 0;           // see RenderImpl
+  float tune_ms[2] = {0.f, 0.f};
+  bool tune_use_wavefront = false;
   // intersect scratch
   DeviceBuffer<double> q_origins, q_dirs, q_t, q_point;
   DeviceBuffer<int32_t> q_tri;
@@ -512,10 +518,28 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
     const int blocks = OwnedStrips(plan, owner) * rp.tiles_x;
     // a peer's scratch frame must not be overwritten while device 0 still gathers the previous one
     if (g > 0) MTB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->dev[0].ev_gathered, 0));
+    bool wavefront = (ctx->flags & MTB_FLAG_WAVEFRONT) != 0;
+    if ((ctx->flags & (MTB_FLAG_WAVEFRONT | MTB_FLAG_MEGAKERNEL)) == 0 && blocks > 0) {
+      // automatic: measure both pipelines on the first frames of this geometry, then keep the faster
+      const long long tsig = ((long long)chunk_w << 42) ^ ((long long)chunk_h << 24) ^ ((long long)owner << 12) ^
+                             ((long long)plan.owners << 6) ^ ((long long)max_depth << 1) ^ ((long long)d.scene.n_lights << 50);
+      if (tsig != d.tune_signature) {
+        d.tune_signature = tsig;
+        d.tune_stage = 0;
+      } else if (d.tune_stage == 2 || d.tune_stage == 4) {
+        // the previous frame was a timed one: harvest it
+        float ms = 0.f;
+        if (cudaEventSynchronize(d.ev_stop) == cudaSuccess && cudaEventElapsedTime(&ms, d.ev_start, d.ev_stop) == cudaSuccess) {
+          d.tune_ms[d.tune_stage == 2 ? 0 : 1] = ms;
+        }
+        if (d.tune_stage == 4) d.tune_use_wavefront = d.tune_ms[1] < d.tune_ms[0];
+      }
+      if (d.tune_stage < 5) d.tune_stage++;
+      // stage now: 1 = megakernel (cold tile order), 2 = megakernel (timed), 3 = wavefront (cold: buffers are
+      // allocated), 4 = wavefront (timed), 5 = decided
+      wavefront = d.tune_stage == 3 || d.tune_stage == 4 || (d.tune_stage == 5 && d.tune_use_wavefront);
+    }
     MTB_CUDA(ctx, cudaEventRecord(d.ev_start, s));
-    const long long my_pixels = (long long)blocks * 64;
-    const bool wavefront = (ctx->flags & MTB_FLAG_WAVEFRONT) != 0 ||
-                           ((ctx->flags & MTB_FLAG_MEGAKERNEL) == 0 && my_pixels < MTB_AUTO_MEGA_PIXELS);
     if (wavefront) {
       // the wavefront kernels accumulate the taps with atomics
       if (want_taps) {
@@ -863,6 +887,16 @@ int mtb_render_chunk_device(mtb_context *ctx, const mtb_camera *cam, int image_w
 }
 
 uint64_t mtb_launch_count(const mtb_context *ctx) { return ctx == nullptr ? 0 : ctx->launches; }
+
+int mtb_pipeline_in_use(const mtb_context *ctx, float *mega_ms, float *wavefront_ms) {
+  if (ctx == nullptr || ctx->dev.empty()) return -1;
+  const DeviceState &d = ctx->dev[0];
+  if (mega_ms != nullptr) *mega_ms = d.tune_ms[0];
+  if (wavefront_ms != nullptr) *wavefront_ms = d.tune_ms[1];
+  if ((ctx->flags & MTB_FLAG_WAVEFRONT) != 0) return 1;
+  if ((ctx->flags & MTB_FLAG_MEGAKERNEL) != 0) return 0;
+  return d.tune_stage >= 5 ? (d.tune_use_wavefront ? 1 : 0) : -1;
+}
 
 int mtb_read_counters(mtb_context *ctx, mtb_stats *stats) {
   if (ctx == nullptr || stats == nullptr) return MTB_ERR_ARG;

@@ -256,22 +256,23 @@ __global__ void __launch_bounds__(kWfBlock) WfSpawn(DeviceScene sc, RenderParams
     do_reflect = refl > 0.0 && coef > 0.01 && !in_object;  // mythtracer.cc:181-184
     do_refract = m->transparency > 0.0;                    // mythtracer.cc:192
   }
-  // ---- queue compaction: warp ballot + prefix sum, one atomic per warp ----
+  // ---- queue compaction: warp ballots + prefix counts, one atomic per warp.  The warp's reflection
+  // children are stored first, then its refraction children, so that neighbouring queue entries (= the
+  // lanes of a warp in the next level) are rays of the same kind from neighbouring pixels ----
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned mine = (do_reflect ? 1u : 0u) + (do_refract ? 1u : 0u);
-  unsigned incl = mine;
-  for (int off = 1; off < 32; off <<= 1) {
-    const unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
-    if (lane >= (unsigned)off) incl += v;
-  }
-  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  const unsigned refl_mask = __ballot_sync(0xffffffffu, do_reflect);
+  const unsigned refr_mask = __ballot_sync(0xffffffffu, do_refract);
+  const unsigned n_refl = (unsigned)__popc(refl_mask), n_refr = (unsigned)__popc(refr_mask);
+  const unsigned total = n_refl + n_refr;
+  const unsigned below = (1u << lane) - 1u;
   unsigned base = 0;
   if (total > 0u) {
-    if (lane == 31u) base = atomicAdd(wf.counters + 0, total);
-    base = __shfl_sync(0xffffffffu, base, 31);
+    if (lane == 0u) base = atomicAdd(wf.counters + 0, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
   }
-  if (mine > 0u) {
-    unsigned pos = base + incl - mine;
+  if (do_reflect || do_refract) {
+    const unsigned pos_refl = base + (unsigned)__popc(refl_mask & below);
+    const unsigned pos_refr = base + n_refl + (unsigned)__popc(refr_mask & below);
     const int next_base = act_base + n;
     if (base + total > (unsigned)wf.queue_cap || (long long)next_base + base + total > (long long)wf.act_cap) {
       wf.counters[1] = 1u;  // overflow: the host retries the frame with larger buffers
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(kWfBlock) WfSpawn(DeviceScene sc, RenderParams
       const unsigned long long path = wf.act_path[act];
       const int pixel = wf.act_pixel[act];
       if (do_reflect) {
+        const unsigned pos = pos_refl;
         Count<DBG>(cnt, kReflect);
         const D3 reflected = Load3(wf.act_reflected + (size_t)act * 3);
         const D3 ro = Add(P, MulS(reflected, 0.0001));  // mythtracer.cc:70-75
@@ -291,9 +293,9 @@ __global__ void __launch_bounds__(kWfBlock) WfSpawn(DeviceScene sc, RenderParams
         wf.rq_pixel[qn][pos] = pixel;
         wf.rq_inobj[qn][pos] = in_object ? 1 : 0;
         wf.act_refl[act] = next_base + (int)pos;
-        pos++;
       }
       if (do_refract) {
+        const unsigned pos = pos_refr;
         Count<DBG>(cnt, kRefract);
         const D3 rdir = Normalized(Load3(wf.act_dir + (size_t)act * 3));  // mythtracer.cc:208-212
         const D3 ro = Add(P, MulS(rdir, 0.00001));                        // mythtracer.cc:214-218

@@ -393,3 +393,30 @@ def test_textured_light_terms_in_isolation(product_lib, oracle_mod, scene_dir, p
         gpu = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
         cpu = orc.render(files.camera, w, h, depth=2, taps=True)
         _assert_render_equal(gpu, cpu, "%s terms %s" % (pipeline, (amb, dif, spe)))
+
+
+def test_automatic_pipeline_choice(product_lib, oracle_mod, scene_dir):
+    """flags = 0: the library times both pipelines on the first frames of a geometry and keeps the faster; every
+    one of those frames must carry the same bytes (the choice is invisible in the output)."""
+    from mythtracer_b200 import Light, MythTracer
+    files, cfg = scenes.config_scene("C1", scene_dir)
+    mt = MythTracer(max_depth=cfg["depth"])
+    assert mt.LoadObj(files.obj_path)
+    mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]
+    orc = oracle_mod.Oracle.from_obj(files.obj_path)
+    orc.set_lights(files.lights)
+    w, h = 320, 240
+    cpu = orc.render(files.camera, w, h, depth=cfg["depth"])
+    states = []
+    for _ in range(7):
+        out = mt.render_chunk(files.camera, w, h, 0, 0, w, h)
+        assert np.array_equal(out["rgb"], cpu["rgb"])
+        assert out["stats"]["rays"] == cpu["stats"]["rays"]
+        states.append(mt.pipeline_in_use()[0])
+    assert states[0] == "measuring" and states[-1] in ("mega", "wavefront")
+    _, mega_ms, wf_ms = mt.pipeline_in_use()
+    assert mega_ms > 0 and wf_ms > 0
+    assert states[-1] == ("wavefront" if wf_ms < mega_ms else "mega")
+    # a different geometry starts measuring again
+    mt.render_chunk(files.camera, w, h, 0, 0, w // 2, h)
+    assert mt.pipeline_in_use()[0] == "measuring"

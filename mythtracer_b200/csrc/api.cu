@@ -1,9 +1,12 @@
 // C ABI of mythtracer_b200 (see include/mythtracer_b200.h): context, scene residency in HBM, and the
 // launch / gather logic around the kernels of kernels.cu.  No CPU rendering path exists in this file.
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "device_scene.h"
@@ -12,10 +15,12 @@ namespace {
 
 std::string g_create_error;
 
+// (the devices of a context are driven by one host thread each while a frame is in flight, hence the lock)
 #define MTB_CUDA(ctx, expr)                                                                                  \
   do {                                                                                                       \
     cudaError_t e__ = (expr);                                                                                \
     if (e__ != cudaSuccess) {                                                                                \
+      std::lock_guard<std::mutex> lock__((ctx)->err_mutex);                                                  \
       (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                                      \
       return MTB_ERR_CUDA;                                                                                   \
     }                                                                                                        \
@@ -146,7 +151,8 @@ struct mtb_context {
   std::vector<std::string> material_names, texture_names;
   std::vector<mtb_light> lights;
   int64_t device_bytes = 0;
-  uint64_t launches = 0;  // kernels of this library launched so far (mtb_launch_count)
+  std::atomic<uint64_t> launches{0};  // kernels of this library launched so far (mtb_launch_count)
+  std::mutex err_mutex;
 };
 
 namespace {
@@ -487,8 +493,9 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
   rp.tiles_x = (chunk_w + 7) / 8;
   rp.strip_stride = plan.owners;
 
-  // ---- launch on every device ----
-  for (int g = 0; g < n_dev; g++) {
+  // ---- launch on every device: one host thread per device when there are several, because the wavefront
+  // pipeline reads one counter per level back to the host and must not serialise the devices ----
+  auto launch_on_device = [&](int g) -> int {
     DeviceState &d = ctx->dev[g];
     MTB_CUDA(ctx, cudaSetDevice(d.device));
     cudaStream_t s = (g == 0 && user_stream != nullptr) ? user_stream : d.stream;
@@ -571,6 +578,19 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
       MTB_CUDA(ctx, cudaGetLastError());
     }
     MTB_CUDA(ctx, cudaEventRecord(d.ev_stop, s));
+    return MTB_OK;
+  };
+  if (n_dev == 1) {
+    const int rc = launch_on_device(0);
+    if (rc != MTB_OK) return rc;
+  } else {
+    std::vector<int> rcs((size_t)n_dev, MTB_OK);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < n_dev; g++) workers.emplace_back([&, g]() { rcs[(size_t)g] = launch_on_device(g); });
+    for (std::thread &t : workers) t.join();
+    for (int rc : rcs) {
+      if (rc != MTB_OK) return rc;
+    }
   }
 
   // ---- gather on device 0 (peer copies), then device -> host ----
@@ -886,7 +906,7 @@ int mtb_render_chunk_device(mtb_context *ctx, const mtb_camera *cam, int image_w
                     static_cast<cudaStream_t>(stream), nullptr, nullptr, stats, false);
 }
 
-uint64_t mtb_launch_count(const mtb_context *ctx) { return ctx == nullptr ? 0 : ctx->launches; }
+uint64_t mtb_launch_count(const mtb_context *ctx) { return ctx == nullptr ? 0 : ctx->launches.load(); }
 
 int mtb_pipeline_in_use(const mtb_context *ctx, float *mega_ms, float *wavefront_ms) {
   if (ctx == nullptr || ctx->dev.empty()) return -1;

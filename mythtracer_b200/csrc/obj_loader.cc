@@ -47,6 +47,54 @@ void ChopLineEnd(char *line) {
   if (p != nullptr) *p = '\0';
 }
 
+// sscanf("%lf") == strtod after optional white space; these helpers avoid the format interpreter on the
+// millions of `v` / `vn` / `vt` / `f` lines of a big model while keeping sscanf's accept / reject behaviour.
+inline bool ScanDouble(const char **p, double *out) {
+  char *end = nullptr;
+  const double v = strtod(*p, &end);
+  if (end == *p) return false;
+  *out = v;
+  *p = end;
+  return true;
+}
+
+// sscanf("%i"): optional sign, 0x / 0 prefixes select base 16 / 8 (objreader.cc:117-125 reads indices so)
+inline bool ScanInt(const char **p, int *out) {
+  char *end = nullptr;
+  const long v = strtol(*p, &end, 0);
+  if (end == *p) return false;
+  *out = (int)v;
+  *p = end;
+  return true;
+}
+
+// The reference tries "%i/%i/%i", "%i//%i", "%i/%i", "%i" in turn on one face token (objreader.cc:117-125).
+// Same outcome in one pass: v is mandatory; "v/vt/vn", "v//vn", "v/vt" fill what parses; anything else keeps v.
+inline bool ScanFaceToken(const char *tok, int *v, int *vt, int *vn) {
+  *v = *vt = *vn = 0;
+  const char *p = tok;
+  if (!ScanInt(&p, v)) return false;
+  if (*p != '/') return true;
+  p++;
+  if (*p == '/') {  // v//vn
+    p++;
+    int n;
+    if (ScanInt(&p, &n)) *vn = n;
+    return true;
+  }
+  int t;
+  if (!ScanInt(&p, &t)) return true;  // "v/junk": only "%i" matches
+  *vt = t;
+  if (*p == '/') {
+    p++;
+    int n;
+    if (ScanInt(&p, &n)) *vn = n;
+  }
+  return true;
+}
+
+inline bool IsSpace(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\v' || c == '\f' || c == '\r'; }
+
 bool ReadPpmHeaderInt(FILE *f, int *out) {
   int c = fgetc(f);
   for (;;) {
@@ -234,7 +282,9 @@ bool LoadObjFile(const char *path, LoadedScene *scene, std::string *err) {
     const std::string key(key_buf);
     if (key == "v" || key == "vn") {
       double x, y, z;
-      if (sscanf(line, key == "v" ? "v %lf %lf %lf" : "vn %lf %lf %lf", &x, &y, &z) != 3) {
+      // sscanf(line, "v %lf %lf %lf"): the literal must start the line (no leading blanks), then three doubles
+      const char *p = line + key.size();
+      if (strncmp(line, key.c_str(), key.size()) != 0 || !ScanDouble(&p, &x) || !ScanDouble(&p, &y) || !ScanDouble(&p, &z)) {
         *err = std::string("unsupported ") + (key == "v" ? "vertex" : "normal") + " format \"" + line + "\"";
         return false;
       }
@@ -244,10 +294,12 @@ bool LoadObjFile(const char *path, LoadedScene *scene, std::string *err) {
       dst.push_back(z);
     } else if (key == "vt") {
       double u, v, w = 0.0;
-      if (sscanf(line, "vt %lf %lf %lf", &u, &v, &w) < 2) {
+      const char *p = line + 2;
+      if (strncmp(line, "vt", 2) != 0 || !ScanDouble(&p, &u) || !ScanDouble(&p, &v)) {
         *err = std::string("unsupported texcoord format \"") + line + "\"";
         return false;
       }
+      ScanDouble(&p, &w);  // optional third coordinate
       tex.push_back(u);
       tex.push_back(v);
       tex.push_back(w);
@@ -271,18 +323,26 @@ bool LoadObjFile(const char *path, LoadedScene *scene, std::string *err) {
       }
       if (material < 0) fprintf(stderr, "warning: material \"%s\" not found\n", name);
     } else if (key == "f") {
-      std::stringstream s(line);
-      std::string token;
-      s >> token;
+      // `s >> token; if (s.eof()) break;` keeps a token only when at least one more character follows it
+      // (objreader.cc:109-115): the first token ("f") is skipped, a token that ends the line is dropped.
       int vi[5], ti[5], ni[5];
       int count = 0;
-      while (s.good()) {
-        s >> token;
-        if (s.eof()) break;  // the quirk: a token that ends the line is dropped
+      const char *p = line;
+      while (IsSpace(*p)) p++;
+      while (*p != '\0' && !IsSpace(*p)) p++;  // the "f" itself
+      for (;;) {
+        while (IsSpace(*p)) p++;
+        if (*p == '\0') break;
+        const char *start = p;
+        while (*p != '\0' && !IsSpace(*p)) p++;
+        if (*p == '\0') break;  // the quirk: nothing follows this token
+        char tokbuf[128];
+        const size_t len = (size_t)(p - start);
+        memcpy(tokbuf, start, len);
+        tokbuf[len] = '\0';
         int v = 0, vt = 0, vn = 0;
-        if (sscanf(token.c_str(), "%i/%i/%i", &v, &vt, &vn) != 3 && sscanf(token.c_str(), "%i//%i", &v, &vn) != 2 &&
-            sscanf(token.c_str(), "%i/%i", &v, &vt) != 2 && sscanf(token.c_str(), "%i", &v) != 1) {
-          *err = "unsupported face format \"" + token + "\"";
+        if (!ScanFaceToken(tokbuf, &v, &vt, &vn)) {
+          *err = std::string("unsupported face format \"") + tokbuf + "\"";
           return false;
         }
         if (count < 4) {

@@ -420,3 +420,45 @@ def test_automatic_pipeline_choice(product_lib, oracle_mod, scene_dir):
     # a different geometry starts measuring again
     mt.render_chunk(files.camera, w, h, 0, 0, w // 2, h)
     assert mt.pipeline_in_use()[0] == "measuring"
+
+
+def _pair_from_loader(product_lib, oracle_mod, files, depth, lights):
+    """Product + oracle over the arrays the product loader parsed (a Python re-parse of 2 M faces is slow)."""
+    from mythtracer_b200 import Light
+    mt = _tracer(product_lib, depth)
+    assert mt.LoadObj(files.obj_path), mt.last_error()
+    mt.GetScene().lights = [Light.from_tuple(l) for l in lights]
+    tris, mtls = mt.scene_arrays()
+    orc = oracle_mod.Oracle(tris, mtls, [])
+    orc.set_lights(lights)
+    return mt, orc
+
+
+def test_c4_stress_scene_tiles(product_lib, oracle_mod, scene_dir):
+    """BASELINE config C4: ~2 M triangles (dense clusters of tiny triangles + long thin sticks that straddle the
+    top octree planes), 1920x1080, depth 5 -- WorkChunk tiles against the oracle, plus the octree shape."""
+    files, cfg = scenes.config_scene("C4", scene_dir)
+    mt, orc = _pair_from_loader(product_lib, oracle_mod, files, cfg["depth"], files.lights)
+    info, tree = mt.scene_info(), orc.tree_info()
+    assert info["n_triangles"] > 1900000
+    assert (info["n_nodes"], info["tree_depth"], info["biggest_list"]) == (tree["nodes"], tree["depth"], tree["biggest_list"])
+    W, H = cfg["width"], cfg["height"]
+    for (cx, cy, cw, ch) in [(300, 420, 96, 64), (1500, 200, 64, 48)]:
+        gpu = mt.render_chunk(files.camera, W, H, cx, cy, cw, ch, debug=True, taps=True)
+        cpu = orc.render(files.camera, W, H, chunk=(cx, cy, cw, ch), depth=cfg["depth"], taps=True)
+        _assert_render_equal(gpu, cpu, "C4 tile %d,%d" % (cx, cy))
+
+
+def test_c5_4k_depth8_four_lights_tiles(product_lib, oracle_mod, scene_dir):
+    """BASELINE config C5: the 500 k-triangle interior at 3840x2160, 4 lights, depth 8 -- tiles against the oracle
+    with both pipelines."""
+    from mythtracer_b200 import MTB_FLAG_MEGAKERNEL, MTB_FLAG_WAVEFRONT
+    files, cfg = scenes.config_scene("C5", scene_dir)
+    assert len(files.lights) == 4 and cfg["depth"] == 8
+    mt, orc = _pair_from_loader(product_lib, oracle_mod, files, cfg["depth"], files.lights)
+    W, H = cfg["width"], cfg["height"]
+    for flags, (cx, cy, cw, ch) in [(MTB_FLAG_MEGAKERNEL, (1800, 1100, 96, 64)), (MTB_FLAG_WAVEFRONT, (2600, 1500, 80, 48))]:
+        mt.set_flags(flags)
+        gpu = mt.render_chunk(files.camera, W, H, cx, cy, cw, ch, debug=True, taps=True)
+        cpu = orc.render(files.camera, W, H, chunk=(cx, cy, cw, ch), depth=cfg["depth"], taps=True)
+        _assert_render_equal(gpu, cpu, "C5 tile %d,%d" % (cx, cy))

@@ -70,8 +70,16 @@ struct FlatScene {
   double max_abs_coord = 0.0;  // largest |coordinate| of the scene box (bounds the FP32 cull error)
 };
 
-constexpr int kBvhLeafSize = 4;
-constexpr int kBvhMinList = 12;  // shorter lists are scanned linearly
+#ifndef MTB_BVH_LEAF
+#define MTB_BVH_LEAF 2
+#endif
+#ifndef MTB_BVH_MIN_LIST
+#define MTB_BVH_MIN_LIST 3
+#endif
+constexpr int kBvhLeafSize = MTB_BVH_LEAF;      // <= 7 (3-bit count in BvhRec::leaf)
+constexpr int kBvhMinList = MTB_BVH_MIN_LIST;  // shorter lists are scanned linearly
+// measured on B200, C3 frame (megakernel / wavefront ms): leaf 4 min 12: 39.4 / 46.5; leaf 2 min 6: 36.5 / 42.7;
+// leaf 2 min 3: 35.5 / 41.8; leaf 3 min 4: 35.6 / 42.0; leaf 1 min 2: 37.9 / 44.9; leaf 6 min 16: 43.7 / 51.4
 
 // Returns MTB_OK or an error code with text in *err.
 int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, FlatScene *out, std::string *err);

@@ -462,3 +462,43 @@ def test_c5_4k_depth8_four_lights_tiles(product_lib, oracle_mod, scene_dir):
         gpu = mt.render_chunk(files.camera, W, H, cx, cy, cw, ch, debug=True, taps=True)
         cpu = orc.render(files.camera, W, H, chunk=(cx, cy, cw, ch), depth=cfg["depth"], taps=True)
         _assert_render_equal(gpu, cpu, "C5 tile %d,%d" % (cx, cy))
+
+
+def test_edge_scenes(product_lib, oracle_mod, scene_dir):
+    """Empty scene, a single triangle, zero-area and needle triangles, all triangles in one unsplit node, a ray
+    batch of size 0 -- both pipelines."""
+    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_MEGAKERNEL, MTB_FLAG_WAVEFRONT
+    from mythtracer_b200.api import MTL_DTYPE, TRI_DTYPE
+    cam = (0.3, 0.4, -6.0, 2.0, 5.0, 1.0, 70.0)
+    lights = [(1.0, 5.0, -4.0, 0.2, 0.2, 0.2, 1.0, 1.0, 1.0, 0.8, 0.8, 0.8)]
+    mtl = np.zeros(1, MTL_DTYPE)
+    mtl["ambient"], mtl["diffuse"], mtl["specular"] = (0.4, 0.5, 0.6), (0.7, 0.6, 0.5), (0.5, 0.5, 0.5)
+    mtl["specular_exp"], mtl["reflectance"], mtl["transparency"], mtl["texture"] = 30.0, 0.4, 0.3, -1
+    mtl["transmission_filter"] = (0.9, 0.8, 0.7)
+    rng = np.random.default_rng(2)
+    cases = {"empty": np.zeros(0, TRI_DTYPE)}
+    one = np.zeros(1, TRI_DTYPE)
+    one["vertex"] = [-3, -3, 2, 4, -3, 2.5, 0, 4, 3]
+    one["normal"] = [0, 0, -1, 0.1, 0, -1, 0, 0.1, -1]
+    cases["single"] = one
+    few = np.zeros(15, TRI_DTYPE)   # below SPLIT_BOUNDARY: the root is never split; includes degenerate triangles
+    few["vertex"] = rng.uniform(-3, 3, (15, 9))
+    few["normal"] = rng.normal(size=(15, 9))
+    few["vertex"][3] = [1, 1, 1, 1, 1, 1, 1, 1, 1]                 # a point
+    few["vertex"][4] = [0, 0, 1, 1, 1, 2, 2, 2, 3]                 # collinear
+    few["vertex"][5][3:] = few["vertex"][5][:6] + 1e-9             # a needle
+    cases["few"] = few
+    for name, tris in cases.items():
+        tris["material"] = 0
+        tris["line_no"] = np.arange(len(tris))
+        orc = oracle_mod.Oracle(tris, mtl, [])
+        orc.set_lights(lights)
+        cpu = orc.render(cam, 96, 64, depth=4, taps=True)
+        for flags in (MTB_FLAG_MEGAKERNEL, MTB_FLAG_WAVEFRONT):
+            mt = MythTracer(max_depth=4, flags=flags)
+            mt.upload(tris, mtl)
+            mt.GetScene().lights = [Light.from_tuple(l) for l in lights]
+            gpu = mt.render_chunk(cam, 96, 64, 0, 0, 96, 64, debug=True, taps=True)
+            _assert_render_equal(gpu, cpu, "%s flags %d" % (name, flags))
+            r = mt.intersect_rays(np.zeros((0, 3)), np.zeros((0, 3)))
+            assert len(r["tri"]) == 0

@@ -159,3 +159,27 @@ def test_strip_partition_math():
             assert tiles.padded_height(h, world) % (8 * world) == 0 and tiles.padded_height(h, world) >= h
             for k in range(world):
                 assert all(tiles.strip_owner(s, world) == k for s in tiles.owned_strips(h, k, world))
+
+
+def test_octree_depth_limit_and_degenerate_inputs(product_lib, oracle_mod):
+    """The reference has no depth cap (octtree.cc:52-55): 16 coincident primitives recurse until its stack
+    overflows.  The builder refuses such scenes with MTB_ERR_LIMIT instead; an empty scene and scenes below the
+    split threshold are fine."""
+    from mythtracer_b200 import MythTracer, MythTracerError
+    from mythtracer_b200.api import MTL_DTYPE, TRI_DTYPE
+    mt = MythTracer(host_only=True)
+    tris = np.zeros(16, TRI_DTYPE)
+    tris["vertex"] = [1.3, 1.7, 1.1] * 3   # 16 coincident zero-size triangles: they fit into ever smaller children
+    tris["material"] = -1
+    with pytest.raises(MythTracerError, match="deeper than"):
+        mt.upload(tris, np.zeros(0, MTL_DTYPE))
+    mt.upload(tris[:15], np.zeros(0, MTL_DTYPE))                        # below SPLIT_BOUNDARY: one node
+    info = mt.scene_info()
+    assert info["n_nodes"] == 1 and info["tree_depth"] == 0 and info["root_list"] == 15
+    mt.upload(np.zeros(0, TRI_DTYPE), np.zeros(0, MTL_DTYPE))           # empty scene: root box {0,0,0}-{0,0,0}
+    info = mt.scene_info()
+    assert info["n_triangles"] == 0 and info["n_nodes"] == 1 and info["aabb_max"] == [0.0, 0.0, 0.0]
+    bad = np.zeros(1, TRI_DTYPE)
+    bad["material"] = 3
+    with pytest.raises(MythTracerError, match="material"):
+        mt.upload(bad, np.zeros(1, MTL_DTYPE))

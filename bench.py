@@ -260,7 +260,12 @@ def _run_ours(args):
     W, H, depth = cfg["width"], cfg["height"], cfg["depth"]
 
     base_flags = {"wavefront": MTB_FLAG_WAVEFRONT, "mega": MTB_FLAG_MEGAKERNEL, "auto": 0}[args.pipeline]
-    mt = MythTracer(devices=[local_rank], max_depth=depth, flags=base_flags)
+    # Launched plainly (no torchrun) with --gpus N > 1: ONE process, one context over N devices -- the
+    # in-process form (strips interleaved over the devices, peer-copy gather to device 0 over NVLink).
+    inproc = 1
+    if world == 1 and args.gpus > 1:
+        inproc = min(args.gpus, torch.cuda.device_count())
+    mt = MythTracer(devices=[local_rank] if inproc == 1 else list(range(inproc)), max_depth=depth, flags=base_flags)
     t0 = time.time()
     if not mt.LoadObj(files.obj_path):
         raise SystemExit("LoadObj failed: " + mt.last_error())
@@ -393,7 +398,7 @@ def _run_ours(args):
         try:
             with open(tpath) as f:
                 tj = json.load(f)
-            if tj.get("workload") == WORKLOAD and tj.get("n_gpus", 1) == world:
+            if tj.get("workload") == WORKLOAD and tj.get("n_gpus", 1) == world * inproc and pipeline_used == "mega":
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
@@ -416,10 +421,12 @@ def _run_ours(args):
 
     lights_bytes = 96 * len(files.lights)
     line = {
-        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world * inproc, "steps": args.steps, "warmup": n_warm,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": config_dict(files, cfg, world, {"pipeline": pipeline_used, "pipeline_choice": args.pipeline, "autotune_ms": {"mega": tune_mega_ms, "wavefront": tune_wf_ms},
+        "config": config_dict(files, cfg, world * inproc, {"launch": "one process per GPU (torchrun), NCCL gather" if world > 1 else
+                                                           ("one process, one context over %d devices, peer-copy gather" % inproc if inproc > 1 else "one process, one GPU"),
+                                                           "pipeline": pipeline_used, "pipeline_choice": args.pipeline, "autotune_ms": {"mega": tune_mega_ms, "wavefront": tune_wf_ms},
                                                  "rays_per_frame": rays_per_frame, "scene_load_s": load_s,
                                                  "octree_nodes": info["n_nodes"], "tree_depth": info["tree_depth"],
                                                  "device_scene_bytes": info["device_bytes"]}),

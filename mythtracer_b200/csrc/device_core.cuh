@@ -268,14 +268,15 @@ __device__ int TraceRegular(const DeviceScene &sc, const Ray &r, double *t_out, 
       int n_pend = 0;
       int i = info.w;
       const int end = info2.y;
+      const BvhRec *b = &node->root_rec;  // the list's first record travels in the node's own cache line
       while (i < end) {
-        const BvhRec *b = sc.bvh + i;
         const float4 q0 = __ldg(reinterpret_cast<const float4 *>(b->box));      // lo.xyz hi.x
         const float4 q1 = __ldg(reinterpret_cast<const float4 *>(b->box) + 1);  // hi.yz skip leaf
         Count<DBG>(cnt, kBvh);
         const bool pass = r.cull32 ? CullBox32(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r)
                                    : CullBox64(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r);
         i = pass ? i + 1 : __float_as_int(q1.z);
+        b = sc.bvh + i;
         const unsigned leaf = __float_as_uint(q1.w);
         if (pass && leaf != 0u) {
           pend[n_pend++] = leaf;

@@ -314,6 +314,7 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, FlatS
       nr.bvh_root = (int32_t)out->bvh.size();
       bb.Build(0, nr.list_count);
       nr.bvh_end = (int32_t)out->bvh.size();
+      nr.root_rec = out->bvh[(size_t)nr.bvh_root];
       order = &bb.ids;
     }
     for (int32_t k = 0; k < nr.list_count; k++) {

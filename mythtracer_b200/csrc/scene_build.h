@@ -13,6 +13,17 @@
 
 namespace mtb {
 
+// Threaded (stackless) BVH over one long node list, records in depth-first order: on a box hit go to
+// the next record, on a miss jump to `skip`.  A record is a CONSERVATIVE cull only: its FP32 box is the
+// union of the exact FP64 triangle AABBs below it, rounded outwards, and every triangle it lets through is
+// still decided by the exact FP64 reference tests.  32 bytes: four records per 128-byte line.
+struct alignas(32) BvhRec {
+  float box[6];    // lo.xyz rounded down, hi.xyz rounded up
+  int32_t skip;
+  uint32_t leaf;   // leaf: (first_slot << 3) | count (count 1..kBvhLeafSize); inner record: 0
+};
+static_assert(sizeof(BvhRec) == 32, "BvhRec must be a quarter of a cache line");
+
 // One octree node = one 128-byte line.  The 8 children of a node are contiguous (first_child .. +7) and
 // their boxes are exactly {lo,c} / {c,hi} per axis (octtree.cc:61-100), so a node carries the three
 // planes per axis once instead of eight child boxes.
@@ -24,7 +35,7 @@ struct alignas(128) NodeRec {
   int32_t list_first;   // first slot of this node's own primitive list
   int32_t list_count;
   int32_t bvh_root;     // first list-BVH record of this list, -1: scan the list linearly
-  int32_t pad_[8];
+  BvhRec root_rec;      // copy of bvh[bvh_root]: the first box test of a visit needs no second dependent load
 };
 static_assert(sizeof(NodeRec) == 128, "NodeRec must be one cache line");
 
@@ -46,17 +57,6 @@ struct alignas(128) ShadeRec {
   int32_t line_no;
 };
 static_assert(sizeof(ShadeRec) == 128, "ShadeRec must be one cache line");
-
-// Threaded (stackless) BVH over one long node list, records in depth-first order: on a box hit go to
-// the next record, on a miss jump to `skip`.  A record is a CONSERVATIVE cull only: its FP32 box is the
-// union of the exact FP64 triangle AABBs below it, rounded outwards, and every triangle it lets through is
-// still decided by the exact FP64 reference tests.  32 bytes: four records per 128-byte line.
-struct alignas(32) BvhRec {
-  float box[6];    // lo.xyz rounded down, hi.xyz rounded up
-  int32_t skip;
-  uint32_t leaf;   // leaf: (first_slot << 3) | count (count 1..kBvhLeafSize); inner record: 0
-};
-static_assert(sizeof(BvhRec) == 32, "BvhRec must be a quarter of a cache line");
 
 struct FlatScene {
   std::vector<NodeRec> nodes;

@@ -209,6 +209,7 @@ int UploadToDevice(mtb_context *ctx, DeviceState *d) {
   d->scene.textures = d->tex_objects.ptr;
   d->scene.texture_dim = d->tex_dims.ptr;
   d->scene.n_materials = (int32_t)ctx->materials.size();
+  d->scene.n_nodes = (int32_t)ctx->flat.nodes.size();
   // the FP32 cull's error bound assumes coordinates of ordinary magnitude (see kernels.cu, CullBox)
   const double mac = ctx->flat.max_abs_coord;
   d->scene.cull_radius = (mac >= 0x1p-10 && mac <= 0x1p20) ? (float)mac * 1.0000002f : 0.0f;

@@ -92,6 +92,24 @@ __device__ __forceinline__ void Count(unsigned long long *cnt, int which, unsign
 // 128-bit read-only loads of the 16-byte aligned records
 __device__ __forceinline__ double2 Ld2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 
+// Optional staging of the top octree levels in shared memory (levels 0-2 = 1 + 8 + 64 nodes, 9.1 KB): every ray
+// walks them, but they are L1-resident anyway; measured on B200 before being enabled.
+#ifdef MTB_SMEM_TOP
+constexpr int kTopNodes = 73;
+__device__ __forceinline__ void StageTopNodes(const DeviceScene &sc, NodeRec *top, int n_nodes) {
+  const int n = n_nodes < kTopNodes ? n_nodes : kTopNodes;
+  const uint4 *src = reinterpret_cast<const uint4 *>(sc.nodes);
+  uint4 *dst = reinterpret_cast<uint4 *>(top);
+  for (int i = (int)threadIdx.x; i < n * 8; i += (int)blockDim.x) dst[i] = __ldg(src + i);
+  __syncthreads();
+}
+#define MTB_NODE_PTR(cur) ((cur) < top_n ? top + (cur) : sc.nodes + (cur))
+#define MTB_NLD(p) (*(p))
+#else
+#define MTB_NODE_PTR(cur) (sc.nodes + (cur))
+#define MTB_NLD(p) __ldg(p)
+#endif
+
 struct Ray {
   D3 o, d, inv;
   bool sx, sy, sz;  // inv component negative (regular rays only)
@@ -222,8 +240,16 @@ __device__ __forceinline__ void TestSlotRegular(const DeviceScene &sc, int slot,
 // ---------------------------------------------------------------------------------------------------
 // Regular traversal
 // ---------------------------------------------------------------------------------------------------
+#ifdef MTB_SMEM_TOP
+#define MTB_TOP_PARAMS , const NodeRec *top, int top_n
+#define MTB_TOP_ARGS , top, top_n
+#else
+#define MTB_TOP_PARAMS
+#define MTB_TOP_ARGS
+#endif
+
 template <bool DBG>
-__device__ int TraceRegular(const DeviceScene &sc, const Ray &r, double *t_out, unsigned long long *cnt) {
+__device__ int TraceRegular(const DeviceScene &sc, const Ray &r, double *t_out, unsigned long long *cnt MTB_TOP_PARAMS) {
   int f_child[kMaxTreeStack];
   unsigned f_order[kMaxTreeStack];
   double f_t[kMaxTreeStack];
@@ -248,9 +274,9 @@ __device__ int TraceRegular(const DeviceScene &sc, const Ray &r, double *t_out, 
   int c_child = -1;
   for (;;) {
     // ---- enter node `cur`: own list first (octtree.cc:177-196) ----
-    const NodeRec *node = sc.nodes + cur;
-    const int4 info = __ldg(reinterpret_cast<const int4 *>(&node->first_child));  // first_child, list_first, list_count, bvh_root
-    const int2 info2 = __ldg(reinterpret_cast<const int2 *>(&node->child_mask));  // child_mask, bvh_end
+    const NodeRec *node = MTB_NODE_PTR(cur);
+    const int4 info = MTB_NLD(reinterpret_cast<const int4 *>(&node->first_child));  // first_child, list_first, list_count, bvh_root
+    const int2 info2 = MTB_NLD(reinterpret_cast<const int2 *>(&node->child_mask));  // child_mask, bvh_end
     Count<DBG>(cnt, kVisit);
     c_t = 0.0;
     c_slot = -1;
@@ -270,8 +296,8 @@ __device__ int TraceRegular(const DeviceScene &sc, const Ray &r, double *t_out, 
       const int end = info2.y;
       const BvhRec *b = &node->root_rec;  // the list's first record travels in the node's own cache line
       while (i < end) {
-        const float4 q0 = __ldg(reinterpret_cast<const float4 *>(b->box));      // lo.xyz hi.x
-        const float4 q1 = __ldg(reinterpret_cast<const float4 *>(b->box) + 1);  // hi.yz skip leaf
+        const float4 q0 = MTB_NLD(reinterpret_cast<const float4 *>(b->box));      // lo.xyz hi.x
+        const float4 q1 = MTB_NLD(reinterpret_cast<const float4 *>(b->box) + 1);  // hi.yz skip leaf
         Count<DBG>(cnt, kBvh);
         const bool pass = r.cull32 ? CullBox32(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r)
                                    : CullBox64(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r);
@@ -295,8 +321,9 @@ __device__ int TraceRegular(const DeviceScene &sc, const Ray &r, double *t_out, 
     // ---- children that the ray enters, ordered by entry distance (octtree.cc:200-216) ----
     const unsigned mask = (unsigned)info2.x;
     if (info.x >= 0 && mask != 0u) {
-      const double2 p0 = Ld2(node->planes + 0), p1 = Ld2(node->planes + 2), p2 = Ld2(node->planes + 4), p3 = Ld2(node->planes + 6);
-      const double hz = __ldg(&node->planes[8]);
+      const double2 p0 = MTB_NLD(reinterpret_cast<const double2 *>(node->planes + 0)), p1 = MTB_NLD(reinterpret_cast<const double2 *>(node->planes + 2)),
+                    p2 = MTB_NLD(reinterpret_cast<const double2 *>(node->planes + 4)), p3 = MTB_NLD(reinterpret_cast<const double2 *>(node->planes + 6));
+      const double hz = MTB_NLD(&node->planes[8]);
       // planes: lo = (p0.x p0.y p1.x), c = (p1.y p2.x p2.y), hi = (p3.x p3.y hz)
       const double tx0 = (p0.x - r.o.x) * r.inv.x, tx1 = (p1.y - r.o.x) * r.inv.x, tx2 = (p3.x - r.o.x) * r.inv.x;
       const double ty0 = (p0.y - r.o.y) * r.inv.y, ty1 = (p2.x - r.o.y) * r.inv.y, ty2 = (p3.y - r.o.y) * r.inv.y;
@@ -493,7 +520,7 @@ __device__ __noinline__ int TraceLiteral(const DeviceScene &sc, const Ray &r, do
 // OctTree::IntersectRay (octtree.cc:26-40): inverse direction, then one of the two traversals.
 template <bool DBG>
 __device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D3 &d, double *t_out,
-                                     unsigned long long *cnt) {
+                                     unsigned long long *cnt MTB_TOP_PARAMS) {
   Ray r;
   r.o = o;
   r.d = d;
@@ -521,7 +548,7 @@ __device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D
     r.px = pr * fabsf(r.ix);
     r.py = pr * fabsf(r.iy);
     r.pz = pr * fabsf(r.iz);
-    return TraceRegular<DBG>(sc, r, t_out, cnt);
+    return TraceRegular<DBG>(sc, r, t_out, cnt MTB_TOP_ARGS);
   }
   return TraceLiteral<DBG>(sc, r, t_out, cnt);
 }

@@ -21,6 +21,7 @@ struct DeviceScene {
   const mtb_light *lights;
   int32_t n_lights;
   int32_t n_materials;
+  int32_t n_nodes;
   // FP32 list-BVH cull: largest |coordinate| of the scene box; 0 disables the FP32 path (boxes are then
   // evaluated in FP64, still conservatively)
   float cull_radius;

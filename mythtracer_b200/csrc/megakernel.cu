@@ -29,6 +29,12 @@ struct ShadeFrame {
 #endif
 template <bool DBG>
 __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega(DeviceScene sc, RenderParams rp) {
+#ifdef MTB_SMEM_TOP
+  __shared__ NodeRec top_store[kTopNodes];
+  const NodeRec *top = top_store;
+  const int top_n = sc.n_nodes < kTopNodes ? sc.n_nodes : kTopNodes;
+  StageTopNodes(sc, top_store, sc.n_nodes);
+#endif
   // block -> 8x8 tile of one of this launch's strips (a strip = 8 image rows; strips are interleaved
   // across devices / processes, the in-process form of the reference's master/worker tiling)
   const int tile_id = rp.tile_order != nullptr ? rp.tile_order[blockIdx.x] : (int)blockIdx.x;
@@ -83,7 +89,7 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
         td = m_d;
       }
       double t = 0.0;
-      const int slot = Trace<DBG>(sc, to, td, &t, cnt);
+      const int slot = Trace<DBG>(sc, to, td, &t, cnt MTB_TOP_ARGS);
       n_rays++;
 
       bool have_ret = false;
@@ -317,6 +323,12 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
 // Batched OctTree::IntersectRay (octtree.cc:26-40), one ray per thread.
 template <bool DBG>
 __global__ void __launch_bounds__(128) IntersectKernel(DeviceScene sc, IntersectParams ip) {
+#ifdef MTB_SMEM_TOP
+  __shared__ NodeRec top_store[kTopNodes];
+  const NodeRec *top = top_store;
+  const int top_n = sc.n_nodes < kTopNodes ? sc.n_nodes : kTopNodes;
+  StageTopNodes(sc, top_store, sc.n_nodes);
+#endif
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long cnt_store[DBG ? kNumCounters : 1];
   unsigned long long *cnt = cnt_store;
@@ -326,7 +338,7 @@ __global__ void __launch_bounds__(128) IntersectKernel(DeviceScene sc, Intersect
   if (i < ip.n) {
     const D3 o = Load3(ip.origins + i * 3), d = Load3(ip.dirs + i * 3);
     double t = 0.0;
-    const int slot = Trace<DBG>(sc, o, d, &t, cnt);
+    const int slot = Trace<DBG>(sc, o, d, &t, cnt MTB_TOP_ARGS);
     if (slot < 0) {
       ip.tri_index[i] = -1;
     } else {

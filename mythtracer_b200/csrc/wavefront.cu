@@ -119,6 +119,12 @@ __device__ __forceinline__ int PackedIndex(int n, int lanes) { return (int)Packe
 template <bool DBG>
 __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTraceMain(DeviceScene sc, RenderParams rp, WfBuffers wf, int level, int n,
                                                         int act_base, const int32_t *__restrict__ perm, int lanes) {
+#ifdef MTB_SMEM_TOP
+  __shared__ NodeRec top_store[kTopNodes];
+  const NodeRec *top = top_store;
+  const int top_n = sc.n_nodes < kTopNodes ? sc.n_nodes : kTopNodes;
+  StageTopNodes(sc, top_store, sc.n_nodes);
+#endif
   // j: position in processing order; i: position in the level's queue; activation id = act_base + i.
   // Only the first `lanes` lanes of a warp carry a ray (see PackedIndex).
   const int j = PackedIndex(n, lanes);
@@ -165,7 +171,7 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTraceMain(Devic
     D3 color = Mk(0.0, 0.0, 0.0);
     if (live) {
       double t = 0.0;
-      const int slot = Trace<DBG>(sc, o, d, &t, cnt);
+      const int slot = Trace<DBG>(sc, o, d, &t, cnt MTB_TOP_ARGS);
       traced = 1;
       if (rp.n_rays != nullptr) atomicAdd(rp.n_rays + pixel, 1u);
       if (slot < 0) {
@@ -319,6 +325,12 @@ __global__ void __launch_bounds__(kWfBlock) WfSpawn(DeviceScene sc, RenderParams
 template <bool DBG>
 __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfShadow(DeviceScene sc, RenderParams rp, WfBuffers wf, int act_begin, int n,
                                                      int lanes) {
+#ifdef MTB_SMEM_TOP
+  __shared__ NodeRec top_store[kTopNodes];
+  const NodeRec *top = top_store;
+  const int top_n = sc.n_nodes < kTopNodes ? sc.n_nodes : kTopNodes;
+  StageTopNodes(sc, top_store, sc.n_nodes);
+#endif
   const long long task = PackedIndex64((long long)n * sc.n_lights, lanes);
   unsigned long long cnt_store[DBG ? kNumCounters : 1];
   unsigned long long *cnt = cnt_store;
@@ -342,7 +354,7 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfShadow(DeviceSc
         const double light_distance = Dist(seg_start, lpos);
         double t = 0.0;
         Count<DBG>(cnt, kShadow);
-        const int slot = Trace<DBG>(sc, to, ldir, &t, cnt);
+        const int slot = Trace<DBG>(sc, to, ldir, &t, cnt MTB_TOP_ARGS);
         segments++;
         if (slot < 0) break;
         if (t > light_distance) break;

@@ -55,6 +55,22 @@ def measured_peak():
     return FALLBACK_HBM_GBS, "B200_PROFILING.md fallback"
 
 
+def alg_flops(stats) -> float:
+    """24 flops per box test, 57 per Moller-Trumbore, 400 per shaded hit."""
+    return (24.0 * (stats["n_slab"] + stats["n_triaabb"] + stats.get("n_bvh", 0)) + 57.0 * stats["n_mt"] +
+            400.0 * stats["n_shade"])
+
+
+def measured_fp64_peak():
+    """FP64 separate add / mul issue rate (the code is built with --fmad=false), tools/fp_peak.cu on this pool."""
+    path = os.path.join(ROOT, "profiles", "fp_peaks.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["fp64_addmul_tflops"]), "profiles/fp_peaks.json fp64_addmul_tflops (tools/fp_peak.cu, measured)"
+    except Exception:
+        return None, "unmeasured"
+
+
 def alg_bytes(stats) -> float:
     """operands the reference arithmetic consumes; list-BVH box tests are 48-byte boxes too."""
     return (48.0 * (stats["n_slab"] + stats["n_triaabb"] + stats.get("n_bvh", 0)) + 72.0 * stats["n_mt"] +
@@ -384,6 +400,7 @@ def _run_ours(args):
         dist.all_reduce(wt, op=dist.ReduceOp.SUM)
     work_all = dict(zip(("n_slab", "n_triaabb", "n_bvh", "n_mt", "n_shade", "n_visit", "n_hit", "rays"), [float(x) for x in wt]))
     my_alg = alg_bytes(work)
+    my_flops = alg_flops(work)
 
     if rank != 0:
         if world > 1:
@@ -391,6 +408,7 @@ def _run_ours(args):
         return None
 
     peak, peak_src = measured_peak()
+    fp_peak, fp_src = measured_fp64_peak()
     achieved = my_alg / (kernel_ms_mean * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -407,6 +425,9 @@ def _run_ours(args):
                 "kernel_ms": kernel_ms_mean,
                 "algorithmic_bytes_per_launch": my_alg, "peak_source": peak_src,
                 "note": "algorithmic bytes are served by L1/L2 (broadcast reads of shared nodes); frac > DRAM share is cache reuse",
+                "fp": {"bound": "fp64 add/mul issue", "achieved": my_flops / (kernel_ms_mean * 1e-3) / 1e12, "peak": fp_peak,
+                       "unit": "Tflop/s", "frac": (my_flops / (kernel_ms_mean * 1e-3) / 1e12 / fp_peak) if fp_peak else None,
+                       "peak_source": fp_src, "algorithmic_flops_per_launch": my_flops},
                 "per_ray": {k: work_all[k] / max(work_all["rays"], 1.0) for k in ("n_slab", "n_visit", "n_triaabb", "n_bvh", "n_mt", "n_hit", "n_shade")}}
 
     cpu = None

@@ -122,6 +122,7 @@ typedef struct {
 #define MTB_FLAG_WAVEFRONT 4u    /* force the wavefront pipeline */
 #define MTB_FLAG_MEGAKERNEL 16u  /* force the per-pixel megakernel */
 #define MTB_FLAG_RAY_SORT 8u     /* wavefront: counting-sort every queue by origin cell + direction octant (measured: no gain) */
+#define MTB_FLAG_PERSISTENT 64u /* megakernel: persistent warps whose lanes draw their next pixel from a counter instead of one 8x8 tile per block (A/B; measured slower: the refilled lanes trace incoherent rays) */
 #define MTB_FLAG_NO_TILE_ORDER 32u /* megakernel: always launch tiles in scanline order (A/B of the cost-aware launch order) */
 
 /* ---- life cycle -------------------------------------------------------------------------------- */

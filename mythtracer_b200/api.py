@@ -36,6 +36,7 @@ MTB_FLAG_WAVEFRONT = 4
 MTB_FLAG_RAY_SORT = 8
 MTB_FLAG_MEGAKERNEL = 16
 MTB_FLAG_NO_TILE_ORDER = 32
+MTB_FLAG_PERSISTENT = 64
 MAX_RECURSION_LEVEL = 5  # reference mythtracer.h:11 (a run-time argument here)
 
 TRI_DTYPE = np.dtype([("vertex", "f8", (9,)), ("normal", "f8", (9,)), ("uvw", "f8", (9,)),

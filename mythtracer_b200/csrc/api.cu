@@ -80,6 +80,7 @@ struct DeviceState {
   // cost-aware tile order of the megakernel (previous frame's per-tile ray counts)
   DeviceBuffer<uint32_t> tile_cost;
   DeviceBuffer<int32_t> tile_order;
+  DeviceBuffer<uint32_t> work_counter;  // persistent megakernel: next work item
   long long tile_signature = -1;  // geometry the costs were recorded for
   // run-time choice between the two pipelines (flags without a pipeline bit): both are timed once per
   // geometry (megakernel with a warm tile order, then wavefront) and the faster one is kept
@@ -112,7 +113,7 @@ struct DeviceState {
   void FreeAll() {
     nodes.Free(); slots.Free(); shade.Free(); bvh.Free(); list_order.Free(); materials.Free(); tex_objects.Free();
     tex_dims.Free(); lights.Free(); rgb.Free(); dbg.Free(); sig_hits.Free(); sig_shadow.Free(); n_rays.Free();
-    counters.Free(); tile_cost.Free(); tile_order.Free(); q_origins.Free(); q_dirs.Free(); q_t.Free(); q_point.Free(); q_tri.Free();
+    counters.Free(); tile_cost.Free(); tile_order.Free(); work_counter.Free(); q_origins.Free(); q_dirs.Free(); q_t.Free(); q_point.Free(); q_tri.Free();
     for (int k = 0; k < 2; k++) {
       wf_rq_o[k].Free(); wf_rq_d[k].Free(); wf_rq_coef[k].Free(); wf_rq_path[k].Free(); wf_rq_pixel[k].Free();
       wf_rq_inobj[k].Free();
@@ -574,7 +575,14 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
           d.tile_signature = signature;
         }
       }
-      mtb::LaunchRenderMega(d.scene, p, blocks, debug_build, s);
+      int persistent_blocks = 0;
+      if (blocks > 0 && (ctx->flags & MTB_FLAG_PERSISTENT) != 0) {
+        MTB_CUDA(ctx, d.work_counter.Reserve(1));
+        MTB_CUDA(ctx, cudaMemsetAsync(d.work_counter.ptr, 0, sizeof(uint32_t), s));
+        p.work_counter = d.work_counter.ptr;
+        persistent_blocks = mtb::MegaResidentBlocks(d.device);
+      }
+      mtb::LaunchRenderMega(d.scene, p, blocks, persistent_blocks, debug_build, s);
       if (blocks > 0) ctx->launches++;
       MTB_CUDA(ctx, cudaGetLastError());
     }

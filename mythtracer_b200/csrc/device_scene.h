@@ -52,6 +52,10 @@ struct RenderParams {
   // rays it traced to tile_cost[tile]; the next frame launches the most expensive tiles first.
   const int32_t *tile_order;
   uint32_t *tile_cost;
+  // Persistent megakernel: lanes draw work items (item >> 6 = position in the launch order, item & 63 = pixel
+  // of that 8x8 tile) from *work_counter until n_items are handed out.
+  uint32_t *work_counter;
+  uint32_t n_items;
 };
 
 struct IntersectParams {
@@ -113,8 +117,10 @@ void LaunchWfResolve(const RenderParams &rp, const WfBuffers &wf, int n_slots, c
 // megakernel.cu
 // Builds tile_order (descending cost, bucketed) from tile_cost and clears tile_cost for the coming frame.
 void LaunchBuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles, cudaStream_t stream);
-void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp, int n_blocks, bool debug_build,
-                      cudaStream_t stream);
+// persistent_blocks > 0 selects the persistent (lane-refill) form with that grid; rp.work_counter must be zeroed
+void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp, int n_blocks, int persistent_blocks,
+                      bool debug_build, cudaStream_t stream);
+int MegaResidentBlocks(int device);  // SMs x resident RenderMega blocks per SM
 void LaunchIntersect(const DeviceScene &sc, const IntersectParams &ip, bool debug_build, cudaStream_t stream);
 
 }  // namespace mtb

@@ -27,7 +27,14 @@ struct ShadeFrame {
 #ifndef MTB_MEGA_MIN_BLOCKS
 #define MTB_MEGA_MIN_BLOCKS 16  // measured on B200 (C3): 1 -> 86 ms, 8 -> 80, 12 -> 66, 16 -> 64 (spills stay in L1)
 #endif
-template <bool DBG>
+// PERSIST: the grid is sized to the machine (SMs x resident blocks) and every LANE draws its next pixel from a
+// global counter the moment its current pixel is finished, so a warp never idles lanes behind its most
+// expensive pixel (ncu on the one-tile-per-block form: 16 of 32 lanes alive at the Trace call site).  The fetch
+// is a branch at the top of the single ray loop - not an outer loop - so freshly fetched lanes trace their
+// primary ray in the same Trace call as their neighbours' shadow / secondary rays.  Work items are numbered
+// tile by tile in launch order (item >> 6 = position in tile_order, item & 63 = pixel of the 8x8 tile), so a
+// warp's 32 consecutive items start as an 8x4 patch.
+template <bool DBG, bool PERSIST>
 __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega(DeviceScene sc, RenderParams rp) {
 #ifdef MTB_SMEM_TOP
   __shared__ NodeRec top_store[kTopNodes];
@@ -35,35 +42,31 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
   const int top_n = sc.n_nodes < kTopNodes ? sc.n_nodes : kTopNodes;
   StageTopNodes(sc, top_store, sc.n_nodes);
 #endif
-  // block -> 8x8 tile of one of this launch's strips (a strip = 8 image rows; strips are interleaved
-  // across devices / processes, the in-process form of the reference's master/worker tiling)
-  const int tile_id = rp.tile_order != nullptr ? rp.tile_order[blockIdx.x] : (int)blockIdx.x;
-  const int strip = rp.strip_first + (tile_id / rp.tiles_x) * rp.strip_stride;
-  const int px = (tile_id % rp.tiles_x) * kTile + (int)(threadIdx.x & 7u);
-  const int py = strip * kTile + (int)(threadIdx.x >> 3);
-  const bool live = px < rp.chunk_w && py < rp.chunk_h;
-
   unsigned long long cnt_store[DBG ? kNumCounters : 1];
   unsigned long long *cnt = cnt_store;
   if (DBG) {
     for (int i = 0; i < kNumCounters; i++) cnt[i] = 0;
   }
   unsigned long long sig_hits = 0, sig_shadow = 0;
-  unsigned n_rays = 0;
+  unsigned n_rays = 0;        // rays of the current pixel
+  unsigned rays_total = 0;    // rays of every pixel this lane rendered
 
-  if (live) {
+  // block -> 8x8 tile of one of this launch's strips (a strip = 8 image rows; strips are interleaved
+  // across devices / processes, the in-process form of the reference's master/worker tiling)
+  int tile_id = 0, px = 0, py = 0;
+  bool active = false;
+  bool drawn = false;  // !PERSIST: this thread's one pixel has been taken
+
+  {
     ShadeFrame stack[kMaxRayStack];
     int sp = 0;
 
-    // Sensor::GetRay (camera.cc:65-69) with full-image pixel coordinates (mythtracer.cc:298)
     const D3 start = Load3(rp.sensor), d_scan = Load3(rp.sensor + 3), d_pixel = Load3(rp.sensor + 6);
-    D3 m_o = Load3(rp.origin);
-    D3 m_d = Normalized(Add(Add(start, MulS(d_scan, (double)(rp.chunk_y + py))), MulS(d_pixel, (double)(rp.chunk_x + px))));
+    D3 m_o = Mk(0, 0, 0), m_d = Mk(0, 0, 0);
     int level = 0;
     bool in_object = false;
     double coef = 1.0;
     unsigned long long path = 1;
-    Count<DBG>(cnt, kPrimary);
 
     // shading context of the current activation (valid while its shadow rays are traced)
     D3 P = Mk(0, 0, 0), normal = Mk(0, 0, 0), surface = Mk(0, 0, 0), reflected = Mk(0, 0, 0), color = Mk(0, 0, 0);
@@ -77,6 +80,44 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
     D3 final_color = Mk(0, 0, 0);
 
     for (;;) {
+      if (!active) {
+        // ---- next pixel of this lane ----
+        unsigned item;
+        if (PERSIST) {
+          const unsigned peers = __activemask();
+          const unsigned lane = threadIdx.x & 31u;
+          const int leader = __ffs((int)peers) - 1;
+          unsigned base = 0;
+          if ((int)lane == leader) base = atomicAdd(rp.work_counter, (unsigned)__popc(peers));
+          base = __shfl_sync(peers, base, leader);
+          item = base + (unsigned)__popc(peers & ((1u << lane) - 1u));
+        } else {
+          if (drawn) break;
+          drawn = true;
+          item = blockIdx.x * (unsigned)kBlockThreads + threadIdx.x;
+        }
+        if (item >= rp.n_items) break;
+        const int pos = (int)(item >> 6);
+        tile_id = rp.tile_order != nullptr ? rp.tile_order[pos] : pos;
+        const int strip = rp.strip_first + (tile_id / rp.tiles_x) * rp.strip_stride;
+        px = (tile_id % rp.tiles_x) * kTile + (int)(item & 7u);
+        py = strip * kTile + (int)((item >> 3) & 7u);
+        if (!(px < rp.chunk_w && py < rp.chunk_h)) continue;
+        active = true;
+        // Sensor::GetRay (camera.cc:65-69) with full-image pixel coordinates (mythtracer.cc:298)
+        m_o = Load3(rp.origin);
+        m_d = Normalized(Add(Add(start, MulS(d_scan, (double)(rp.chunk_y + py))), MulS(d_pixel, (double)(rp.chunk_x + px))));
+        sp = 0;
+        level = 0;
+        in_object = false;
+        coef = 1.0;
+        path = 1;
+        shadow_mode = false;
+        sig_hits = 0;
+        sig_shadow = 0;
+        n_rays = 0;
+        Count<DBG>(cnt, kPrimary);
+      }
       D3 to, td;
       double light_distance = 0.0;
       if (shadow_mode) {
@@ -288,23 +329,28 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
           sp--;
         }
       }
-      if (finished) break;
-    }
+      if (!finished) continue;
 
-    unsigned char *out = rp.rgb + ((size_t)py * rp.chunk_w + px) * 3;
-    out[0] = QuantizeChannel(final_color.x);
-    out[1] = QuantizeChannel(final_color.y);
-    out[2] = QuantizeChannel(final_color.z);
-    const size_t pix = (size_t)py * rp.chunk_w + px;
-    if (rp.sig_hits != nullptr) rp.sig_hits[pix] = sig_hits;
-    if (rp.sig_shadow != nullptr) rp.sig_shadow[pix] = sig_shadow;
-    if (rp.n_rays != nullptr) rp.n_rays[pix] = n_rays;
+      // ---- the pixel is done (mythtracer.cc:301) ----
+      const size_t pix = (size_t)py * rp.chunk_w + px;
+      unsigned char *out = rp.rgb + pix * 3;
+      out[0] = QuantizeChannel(final_color.x);
+      out[1] = QuantizeChannel(final_color.y);
+      out[2] = QuantizeChannel(final_color.z);
+      if (rp.sig_hits != nullptr) rp.sig_hits[pix] = sig_hits;
+      if (rp.sig_shadow != nullptr) rp.sig_shadow[pix] = sig_shadow;
+      if (rp.n_rays != nullptr) rp.n_rays[pix] = n_rays;
+      rays_total += n_rays;
+      // what this tile cost, for the next frame's launch order
+      if (PERSIST && rp.tile_cost != nullptr) atomicAdd(rp.tile_cost + tile_id, n_rays);
+      active = false;
+    }
   }
 
-  if (rp.tile_cost != nullptr) {  // what this tile cost, for the next frame's launch order
-    unsigned v = n_rays;
+  if (!PERSIST && rp.tile_cost != nullptr) {
+    unsigned v = rays_total;
     for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-    if ((threadIdx.x & 31u) == 0u) atomicAdd(rp.tile_cost + tile_id, v);
+    if ((threadIdx.x & 31u) == 0u) atomicAdd(rp.tile_cost + (rp.tile_order != nullptr ? rp.tile_order[blockIdx.x] : (int)blockIdx.x), v);
   }
   if (DBG && rp.counters != nullptr) {
     for (int i = 0; i < kNumCounters; i++) {
@@ -314,7 +360,7 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
     }
   } else if (rp.counters != nullptr) {
     // the fast build still reports the ray count (the metric's numerator)
-    unsigned long long v = n_rays;
+    unsigned long long v = rays_total;
     for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
     if ((threadIdx.x & 31u) == 0u && v != 0ull) atomicAdd(rp.counters + kRays, v);
   }
@@ -395,13 +441,35 @@ void LaunchBuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles,
   BuildTileOrder<<<1, 1024, 0, stream>>>(tile_cost, tile_order, n_tiles);
 }
 
-void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp, int n_blocks, bool debug_build,
-                      cudaStream_t stream) {
+int MegaResidentBlocks(int device) {
+  static int cached[64] = {0};
+  if (device >= 0 && device < 64 && cached[device] > 0) return cached[device];
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, RenderMega<false, true>, kBlockThreads, 0) != cudaSuccess) per_sm = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) sms = 0;
+  const int n = per_sm > 0 && sms > 0 ? per_sm * sms : 148 * MTB_MEGA_MIN_BLOCKS;
+  if (device >= 0 && device < 64) cached[device] = n;
+  return n;
+}
+
+// n_blocks = number of 8x8 tiles.  persistent_blocks > 0: persistent form with that many blocks (never more than
+// there are tiles); rp.work_counter must then point at a zeroed counter.
+void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp_in, int n_blocks, int persistent_blocks,
+                      bool debug_build, cudaStream_t stream) {
   if (n_blocks <= 0) return;
-  if (debug_build) {
-    RenderMega<true><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);
+  RenderParams rp = rp_in;
+  rp.n_items = (uint32_t)n_blocks * (uint32_t)kBlockThreads;
+  if (persistent_blocks > 0) {
+    const int grid = persistent_blocks < n_blocks ? persistent_blocks : n_blocks;
+    if (debug_build) {
+      RenderMega<true, true><<<grid, kBlockThreads, 0, stream>>>(sc, rp);
+    } else {
+      RenderMega<false, true><<<grid, kBlockThreads, 0, stream>>>(sc, rp);
+    }
+  } else if (debug_build) {
+    RenderMega<true, false><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);
   } else {
-    RenderMega<false><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);
+    RenderMega<false, false><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);
   }
 }
 

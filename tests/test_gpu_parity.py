@@ -374,6 +374,36 @@ def test_wavefront_depths_lights_lattice_and_tiles(product_lib, oracle_mod, scen
     _assert_render_equal(gpu, cpu, "wavefront lattice")
 
 
+def test_persistent_and_tile_per_block_megakernel_agree(product_lib, oracle_mod, scene_dir):
+    """The megakernel's two launch forms -- one 8x8 tile per block (default) and persistent warps whose lanes draw
+    pixels from a counter (MTB_FLAG_PERSISTENT) -- against the oracle and against each other, every tap, on a
+    full frame, a clipped odd-sized tile, a partitioned render and two consecutive frames (warm tile order)."""
+    from mythtracer_b200 import MTB_FLAG_COUNT_WORK, MTB_FLAG_MEGAKERNEL, MTB_FLAG_PERSISTENT
+    files, cfg = scenes.config_scene("C2", scene_dir, 0.3)
+    mt, orc = _load_pair(product_lib, oracle_mod, files, cfg["depth"], MTB_FLAG_MEGAKERNEL)
+    w, h = 250, 141
+    cpu = orc.render(files.camera, w, h, depth=cfg["depth"], taps=True)
+    cpu_tile = orc.render(files.camera, 333, 211, chunk=(100, 37, 77, 45), depth=cfg["depth"], taps=True)
+    for flags in (MTB_FLAG_MEGAKERNEL, MTB_FLAG_MEGAKERNEL | MTB_FLAG_PERSISTENT,
+                  MTB_FLAG_MEGAKERNEL | MTB_FLAG_COUNT_WORK, MTB_FLAG_MEGAKERNEL | MTB_FLAG_PERSISTENT | MTB_FLAG_COUNT_WORK):
+        mt.set_flags(flags)
+        for frame in range(2):
+            gpu = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
+            _assert_render_equal(gpu, cpu, "flags %d frame %d" % (flags, frame))
+        full = gpu["rgb"].copy()
+        gpu = mt.render_chunk(files.camera, 333, 211, 100, 37, 77, 45, debug=True, taps=True)
+        _assert_render_equal(gpu, cpu_tile, "flags %d tile" % flags)
+        # two partitions of the frame: each fills only its own strips, together they are the frame
+        parts = []
+        for rank in range(2):
+            mt.set_partition(rank, 2)
+            parts.append(mt.render_chunk(files.camera, w, h, 0, 0, w, h)["rgb"].copy())
+        mt.set_partition(0, 1)
+        rows = np.arange(h)
+        own0 = ((rows // 8) % 2) == 0
+        assert np.array_equal(parts[0][own0], full[own0]) and np.array_equal(parts[1][~own0], full[~own0])
+
+
 @pytest.mark.parametrize("pipeline", ["mega", "wavefront"])
 def test_textured_light_terms_in_isolation(product_lib, oracle_mod, scene_dir, pipeline):
     """Ambient-only, diffuse-only and specular-only lights on the textured scene, both pipelines: each Phong

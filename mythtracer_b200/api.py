@@ -37,6 +37,7 @@ MTB_FLAG_RAY_SORT = 8
 MTB_FLAG_MEGAKERNEL = 16
 MTB_FLAG_NO_TILE_ORDER = 32
 MTB_FLAG_PERSISTENT = 64
+MTB_FLAG_EXACT_OCTREE = 128
 MAX_RECURSION_LEVEL = 5  # reference mythtracer.h:11 (a run-time argument here)
 
 TRI_DTYPE = np.dtype([("vertex", "f8", (9,)), ("normal", "f8", (9,)), ("uvw", "f8", (9,)),
@@ -51,19 +52,22 @@ CAMERA_DTYPE = np.dtype([("origin", "f8", (3,)), ("pitch", "f8"), ("yaw", "f8"),
                         align=True)
 DEBUG_DTYPE = np.dtype([("line_no", "i4"), ("pad_", "i4"), ("point", "f8", (3,))], align=True)
 STATS_DTYPE = np.dtype([(n, "u8") for n in ("rays", "primary", "shadow", "reflect", "refract", "n_slab", "n_visit",
-                                            "n_triaabb", "n_mt", "n_hit", "n_shade", "n_bvh", "n_literal")] +
+                                            "n_triaabb", "n_mt", "n_hit", "n_shade", "n_bvh", "n_literal", "n_fast",
+                                            "n_fallback")] +
                        [("kernel_ms", "f8"), ("total_ms", "f8")], align=True)
 SUMMARY_DTYPE = np.dtype([("n_triangles", "i8"), ("n_nodes", "i8"), ("n_bvh_nodes", "i8"), ("tree_depth", "i4"),
                           ("n_materials", "i4"), ("n_textures", "i4"), ("n_lights", "i4"), ("root_list", "i8"),
                           ("biggest_list", "i8"), ("interior_triangles", "i8"), ("aabb_min", "f8", (3,)),
                           ("aabb_max", "f8", (3,)), ("device_bytes", "i8")], align=True)
+BVH2_DTYPE = np.dtype([("lbox", "f4", (6,)), ("rbox", "f4", (6,)), ("left", "i4"), ("right", "i4"), ("pad_", "i4", (2,))])
+assert BVH2_DTYPE.itemsize == 64
 assert TRI_DTYPE.itemsize == 224 and MTL_DTYPE.itemsize == 136 and DEBUG_DTYPE.itemsize == 32
 
 # every symbol include/mythtracer_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
     "mtb_create", "mtb_create_host", "mtb_destroy", "mtb_last_error", "mtb_device_count", "mtb_scene_upload", "mtb_load_obj",
     "mtb_set_lights", "mtb_scene_info", "mtb_scene_read", "mtb_scene_material_name", "mtb_scene_texture_name", "mtb_scene_texture", "mtb_load_mtl",
-    "mtb_scene_triangle_nodes", "mtb_set_flags", "mtb_set_partition", "mtb_render_chunk",
+    "mtb_scene_triangle_nodes", "mtb_scene_bvh", "mtb_set_flags", "mtb_set_partition", "mtb_render_chunk",
     "mtb_render_chunk_device", "mtb_read_counters", "mtb_launch_count", "mtb_pipeline_in_use", "mtb_intersect_rays", "mtb_camera_sensor", "mtb_version",
 ]
 
@@ -95,6 +99,7 @@ def load_library():
     lib.mtb_create.argtypes = [ctypes.POINTER(vp), vp, i32]
     lib.mtb_create_host.argtypes = [ctypes.POINTER(vp)]
     lib.mtb_scene_triangle_nodes.argtypes = [vp, vp, vp]
+    lib.mtb_scene_bvh.argtypes = [vp, vp, vp, vp, vp]
     lib.mtb_scene_material_name.argtypes = [vp, ctypes.c_int32]
     lib.mtb_scene_material_name.restype = ctypes.c_char_p
     lib.mtb_scene_texture_name.argtypes = [vp, ctypes.c_int32]
@@ -376,6 +381,16 @@ class MythTracer:
         depth = np.zeros(n, np.int32)
         self._check(self._lib.mtb_scene_triangle_nodes(self._ctx, _ptr(box), _ptr(depth)), "mtb_scene_triangle_nodes")
         return box, depth
+
+    def scene_bvh(self):
+        """mtb_scene_bvh: (nodes as a structured array, depth, leaf_order = insertion index per leaf position)."""
+        n = ctypes.c_int64(0)
+        depth = ctypes.c_int32(0)
+        self._check(self._lib.mtb_scene_bvh(self._ctx, ctypes.byref(n), ctypes.byref(depth), None, None), "mtb_scene_bvh")
+        nodes = np.zeros(n.value, BVH2_DTYPE)
+        order = np.zeros(self.scene_info()["n_triangles"] if n.value else 0, np.int32)
+        self._check(self._lib.mtb_scene_bvh(self._ctx, None, None, _ptr(nodes), _ptr(order)), "mtb_scene_bvh")
+        return nodes, depth.value, order
 
     def _push_lights(self):
         arr = _lights_array(self._scene.lights)

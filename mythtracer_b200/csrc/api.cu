@@ -63,9 +63,10 @@ struct DeviceState {
   DeviceBuffer<mtb::SlotRec> slots;
   DeviceBuffer<mtb::ShadeRec> shade;
   DeviceBuffer<mtb::BvhRec> bvh;
+  DeviceBuffer<mtb::Bvh2Node> gnodes;   // scene BVH of the certified fast traversal
+  DeviceBuffer<mtb::SlotRec> gslots;
   DeviceBuffer<int32_t> list_order;
   DeviceBuffer<mtb_material> materials;
-  DeviceBuffer<cudaTextureObject_t> tex_objects;
   DeviceBuffer<int2> tex_dims;
   DeviceBuffer<mtb_light> lights;
   std::vector<cudaArray_t> tex_arrays;
@@ -111,7 +112,7 @@ struct DeviceState {
   mtb::WfBuffers wf{};
 
   void FreeAll() {
-    nodes.Free(); slots.Free(); shade.Free(); bvh.Free(); list_order.Free(); materials.Free(); tex_objects.Free();
+    nodes.Free(); slots.Free(); shade.Free(); bvh.Free(); gnodes.Free(); gslots.Free(); list_order.Free(); materials.Free();
     tex_dims.Free(); lights.Free(); rgb.Free(); dbg.Free(); sig_hits.Free(); sig_shadow.Free(); n_rays.Free();
     counters.Free(); tile_cost.Free(); tile_order.Free(); work_counter.Free(); q_origins.Free(); q_dirs.Free(); q_t.Free(); q_point.Free(); q_tri.Free();
     for (int k = 0; k < 2; k++) {
@@ -165,6 +166,14 @@ void DestroyTextures(DeviceState *d) {
   d->tex_arrays.clear();
 }
 
+// Regular rays take the certified fast traversal over the scene BVH unless the exact octree recursion is forced.
+void SelectTraversal(mtb_context *ctx, DeviceState *d) {
+  const bool fast = (ctx->flags & (MTB_FLAG_EXACT_OCTREE | MTB_FLAG_NO_LIST_BVH)) == 0 && !ctx->flat.gnodes.empty() &&
+                    d->scene.cull_radius > 0.0f;
+  d->scene.gnodes = fast ? d->gnodes.ptr : nullptr;
+  d->scene.gslots = fast ? d->gslots.ptr : nullptr;
+}
+
 int UploadToDevice(mtb_context *ctx, DeviceState *d) {
   MTB_CUDA(ctx, cudaSetDevice(d->device));
   const mtb::FlatScene &f = ctx->flat;
@@ -173,32 +182,54 @@ int UploadToDevice(mtb_context *ctx, DeviceState *d) {
   MTB_CUDA(ctx, d->shade.Upload(f.shade.data(), f.shade.size(), d->stream));
   MTB_CUDA(ctx, d->bvh.Upload(f.bvh.data(), f.bvh.size(), d->stream));
   MTB_CUDA(ctx, d->list_order.Upload(f.list_order.data(), f.list_order.size(), d->stream));
+  MTB_CUDA(ctx, d->gnodes.Upload(f.gnodes.data(), f.gnodes.size(), d->stream));
+  MTB_CUDA(ctx, d->gslots.Upload(f.gslots.data(), f.gslots.size(), d->stream));
   MTB_CUDA(ctx, d->materials.Upload(ctx->materials.data(), ctx->materials.size(), d->stream));
   DestroyTextures(d);
+  // All textures live in ONE layered CUDA array behind ONE texture object (layer = texture index, extent = the
+  // largest texture; a fetch never leaves its own texture's width x height).  The object is a kernel argument, so
+  // the handle is uniform across the warp: per-texture objects fetched from memory made the compiler emit a
+  // waterfall loop around every TEX, and that code returned wrong texels in the megakernel.
   std::vector<int2> dims;
-  for (const mtb::LoadedTexture &t : ctx->textures) {
-    cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+  d->scene.tex_atlas = 0;
+  if (!ctx->textures.empty()) {
+    size_t max_w = 1, max_h = 1;
+    for (const mtb::LoadedTexture &t : ctx->textures) {
+      max_w = std::max(max_w, (size_t)t.width);
+      max_h = std::max(max_h, (size_t)t.height);
+      dims.push_back(make_int2(t.width, t.height));
+    }
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc<unsigned int>();  // one RGBA32 texel = one 32-bit word
     cudaArray_t arr = nullptr;
-    MTB_CUDA(ctx, cudaMallocArray(&arr, &desc, (size_t)t.width, (size_t)t.height));
+    MTB_CUDA(ctx, cudaMalloc3DArray(&arr, &desc, make_cudaExtent(max_w, max_h, ctx->textures.size()), cudaArrayLayered));
     d->tex_arrays.push_back(arr);
-    MTB_CUDA(ctx, cudaMemcpy2DToArrayAsync(arr, 0, 0, t.rgba.data(), (size_t)t.width * 4, (size_t)t.width * 4,
-                                           (size_t)t.height, cudaMemcpyHostToDevice, d->stream));
+    for (size_t layer = 0; layer < ctx->textures.size(); layer++) {
+      const mtb::LoadedTexture &t = ctx->textures[layer];
+      if (t.width <= 0 || t.height <= 0) continue;
+      cudaMemcpy3DParms cp;
+      memset(&cp, 0, sizeof(cp));
+      cp.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t *>(t.rgba.data()), (size_t)t.width * 4, (size_t)t.width, (size_t)t.height);
+      cp.dstArray = arr;
+      cp.dstPos = make_cudaPos(0, 0, layer);
+      cp.extent = make_cudaExtent((size_t)t.width, (size_t)t.height, 1);
+      cp.kind = cudaMemcpyHostToDevice;
+      MTB_CUDA(ctx, cudaMemcpy3DAsync(&cp, d->stream));
+    }
     cudaResourceDesc res;
     memset(&res, 0, sizeof(res));
     res.resType = cudaResourceTypeArray;
     res.res.array.array = arr;
     cudaTextureDesc td;
     memset(&td, 0, sizeof(td));
-    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
     td.filterMode = cudaFilterModePoint;  // bilinear weights are done in FP64 by the kernel (texture.cc:47-57)
     td.readMode = cudaReadModeElementType;
     td.normalizedCoords = 0;
     cudaTextureObject_t obj = 0;
     MTB_CUDA(ctx, cudaCreateTextureObject(&obj, &res, &td, nullptr));
     d->tex_handles.push_back(obj);
-    dims.push_back(make_int2(t.width, t.height));
+    d->scene.tex_atlas = obj;
   }
-  MTB_CUDA(ctx, d->tex_objects.Upload(d->tex_handles.data(), d->tex_handles.size(), d->stream));
   MTB_CUDA(ctx, d->tex_dims.Upload(dims.data(), dims.size(), d->stream));
   MTB_CUDA(ctx, cudaStreamSynchronize(d->stream));
   d->scene.nodes = d->nodes.ptr;
@@ -207,13 +238,13 @@ int UploadToDevice(mtb_context *ctx, DeviceState *d) {
   d->scene.bvh = d->bvh.ptr;
   d->scene.list_order = d->list_order.ptr;
   d->scene.materials = d->materials.ptr;
-  d->scene.textures = d->tex_objects.ptr;
   d->scene.texture_dim = d->tex_dims.ptr;
   d->scene.n_materials = (int32_t)ctx->materials.size();
   d->scene.n_nodes = (int32_t)ctx->flat.nodes.size();
   // the FP32 cull's error bound assumes coordinates of ordinary magnitude (see kernels.cu, CullBox)
   const double mac = ctx->flat.max_abs_coord;
   d->scene.cull_radius = (mac >= 0x1p-10 && mac <= 0x1p20) ? (float)mac * 1.0000002f : 0.0f;
+  SelectTraversal(ctx, d);
   return MTB_OK;
 }
 
@@ -241,13 +272,15 @@ int BuildAndUpload(mtb_context *ctx) {
   }
   std::string err;
   const int rc = mtb::BuildFlatScene(ctx->triangles.data(), (int64_t)ctx->triangles.size(),
-                                     (ctx->flags & MTB_FLAG_NO_LIST_BVH) == 0, &ctx->flat, &err);
+                                     (ctx->flags & MTB_FLAG_NO_LIST_BVH) == 0, (ctx->flags & MTB_FLAG_NO_LIST_BVH) == 0,
+                                     &ctx->flat, &err);
   if (rc != MTB_OK) {
     ctx->err = err;
     return rc;
   }
   ctx->device_bytes = (int64_t)(ctx->flat.nodes.size() * sizeof(mtb::NodeRec) + ctx->flat.slots.size() * sizeof(mtb::SlotRec) +
                                 ctx->flat.shade.size() * sizeof(mtb::ShadeRec) + ctx->flat.bvh.size() * sizeof(mtb::BvhRec) +
+                                ctx->flat.gnodes.size() * sizeof(mtb::Bvh2Node) + ctx->flat.gslots.size() * sizeof(mtb::SlotRec) +
                                 ctx->flat.list_order.size() * 4 + ctx->materials.size() * sizeof(mtb_material));
   for (const mtb::LoadedTexture &t : ctx->textures) ctx->device_bytes += (int64_t)t.rgba.size();
   for (DeviceState &d : ctx->dev) {
@@ -272,6 +305,8 @@ void FillStats(const unsigned long long *c, mtb_stats *s) {
   s->n_shade = c[mtb::kShade];
   s->n_bvh = c[mtb::kBvh];
   s->n_literal = c[mtb::kLiteral];
+  s->n_fast = c[mtb::kFast];
+  s->n_fallback = c[mtb::kFallback];
 }
 
 struct StripPlan {
@@ -879,11 +914,25 @@ int mtb_scene_triangle_nodes(const mtb_context *ctx, double *node_box, int32_t *
   return MTB_OK;
 }
 
+int mtb_scene_bvh(const mtb_context *ctx, int64_t *n_nodes, int32_t *depth, void *nodes, int32_t *leaf_order) {
+  if (ctx == nullptr) return MTB_ERR_ARG;
+  const mtb::FlatScene &f = ctx->flat;
+  if (n_nodes != nullptr) *n_nodes = (int64_t)f.gnodes.size();
+  if (depth != nullptr) *depth = f.gbvh_depth;
+  if (nodes != nullptr && !f.gnodes.empty()) memcpy(nodes, f.gnodes.data(), f.gnodes.size() * sizeof(mtb::Bvh2Node));
+  if (leaf_order != nullptr) {
+    for (size_t i = 0; i < f.gslots.size(); i++) leaf_order[i] = f.gslots[i].tri;
+  }
+  return MTB_OK;
+}
+
 int mtb_set_flags(mtb_context *ctx, uint32_t flags) {
   if (ctx == nullptr) return MTB_ERR_ARG;
   const bool rebuild = ((ctx->flags ^ flags) & MTB_FLAG_NO_LIST_BVH) != 0 && ctx->has_scene;
   ctx->flags = flags;
-  return rebuild ? BuildAndUpload(ctx) : MTB_OK;
+  if (rebuild) return BuildAndUpload(ctx);
+  for (DeviceState &d : ctx->dev) SelectTraversal(ctx, &d);
+  return MTB_OK;
 }
 
 int mtb_set_partition(mtb_context *ctx, int part_index, int part_count) {

@@ -517,6 +517,182 @@ __device__ __noinline__ int TraceLiteral(const DeviceScene &sc, const Ray &r, do
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Certified fast traversal for regular rays.
+//
+// The octree recursion of the reference returns the closest accepted triangle; what
+// makes it expensive is the shape of the search, not the answer: every own list of every node on the ray's
+// path is examined and nothing is pruned by distance.  TraceFast searches the SAME candidate set - every
+// triangle whose exact FP64 reference test (primitive_triangle.cc:81-143) accepts the ray - through one
+// binary BVH over all triangles, nearest child first, skipping subtrees that start behind the best hit.  The
+// boxes are a conservative FP32 cull (as CullBox32); a triangle is only ever accepted, and its t only ever
+// computed, by the exact reference arithmetic, so t, the hit point and everything downstream are the
+// reference's bits.
+//
+// Where the two searches could disagree is which triangle wins when two accepted hits are closer together than
+// the rounding error of their t (the reference then decides by list / sibling order).  So every accepted hit
+// carries a forward error bound e of its t (MollerTrumboreBound), the search keeps the best hit (t*, e*) and
+// lo2 = min (t - e) over all other accepted hits, and
+//   * prunes a subtree only if its conservative entry distance exceeds t* + 2 e* + 2^-20 t*,
+//   * declares the ray AMBIGUOUS if lo2 <= t* + e* (two hits whose error intervals touch, an exact tie, or an
+//     ill-conditioned winner), in which case the caller discards the answer and runs the exact octree recursion.
+// Why an unambiguous answer is the reference's: (1) the reference evaluates the winner h* (it only stops early
+// behind a sibling that was entered EARLIER, and any accepted hit there has a true distance <= the separating
+// plane <= h*'s; with disjoint error intervals its computed t would be smaller than t*: contradiction), (2) every
+// comparison the recursion makes between two evaluated hits picks the smaller t, ties aside, (3) a pruned
+// triangle's box starts behind t* + 2 e*, so it cannot lie in an earlier sibling either.  Left over, and stated
+// in DESIGN.md section 4: an exact tie of two sibling octants' entry distances (a ray through an octree edge in
+// computed arithmetic), and a pruned, never evaluated triangle whose own computed t is off by more than the
+// pruning margin (Moller-Trumbore determinant within ~1e3 of the reference's rejection threshold 1e-8).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kFastStack = kSceneBvhMaxDepth + 8;
+constexpr int kFastExit = (int)0x80000000;
+
+// Moller-Trumbore exactly as MollerTrumbore() above (same operations, same order -> same bits) plus a forward
+// error bound of t against the exact ray-plane parameter: with u = 2^-53 and |x| meaning component-wise
+// magnitudes, det carries at most 7u * D, D = |e1| . (|d| x |e2|), the numerator at most 8u * N,
+// N = |e2| . (|tvec| x |e1|), and the final quotient 2u |t|; the bound uses 16u, 16u and 8u.
+__device__ __forceinline__ bool MollerTrumboreBound(const double *vert, const Ray &r, double *t_out, double *e_out) {
+  const double2 a = Ld2(vert + 0), b = Ld2(vert + 2), c = Ld2(vert + 4), d = Ld2(vert + 6);
+  const double v22 = __ldg(vert + 8);
+  const D3 v0 = Mk(a.x, a.y, b.x), v1 = Mk(b.y, c.x, c.y), v2 = Mk(d.x, d.y, v22);
+  const D3 e1 = Sub(v1, v0);
+  const D3 e2 = Sub(v2, v0);
+  const D3 pvec = Cross(r.d, e2);
+  const double det = Dot(e1, pvec);
+  if (det >= -0.00000001 && det < 0.00000001) return false;
+  const double inv_det = 1.0 / det;
+  const D3 tvec = Sub(r.o, v0);
+  const double u = Dot(tvec, pvec) * inv_det;
+  if (u < 0.0 || u > 1.0) return false;
+  const D3 qvec = Cross(tvec, e1);
+  const double v = Dot(r.d, qvec) * inv_det;
+  if (v < 0.0 || u + v > 1.0) return false;
+  const double t = Dot(e2, qvec) * inv_det;
+  if (t < 0.0) return false;
+  *t_out = t;
+  const D3 ad = Mk(fabs(r.d.x), fabs(r.d.y), fabs(r.d.z)), a1 = Mk(fabs(e1.x), fabs(e1.y), fabs(e1.z)),
+           a2 = Mk(fabs(e2.x), fabs(e2.y), fabs(e2.z)), at = Mk(fabs(tvec.x), fabs(tvec.y), fabs(tvec.z));
+  const double D = a1.x * (ad.y * a2.z + ad.z * a2.y) + a1.y * (ad.z * a2.x + ad.x * a2.z) + a1.z * (ad.x * a2.y + ad.y * a2.x);
+  const double N = a2.x * (at.y * a1.z + at.z * a1.y) + a2.y * (at.z * a1.x + at.x * a1.z) + a2.z * (at.x * a1.y + at.y * a1.x);
+  const double e_det = 0x1p-49 * D, e_num = 0x1p-49 * N;
+  const double den = fabs(det) - e_det;
+  *e_out = den > 0.0 ? (e_num + t * e_det) / den + 0x1p-50 * t : CUDART_INF;
+  return true;
+}
+
+struct FastBest {
+  double t, e, lo2;
+  int slot;     // canonical slot of the best hit, -1: none
+  float prune;  // subtrees whose conservative entry distance exceeds this cannot matter
+};
+
+template <bool DBG>
+__device__ __forceinline__ void TestSlotFast(const SlotRec *rec, const Ray &r, FastBest *fb, unsigned long long *cnt) {
+  const double2 b0 = Ld2(rec->box + 0), b1 = Ld2(rec->box + 2), b2 = Ld2(rec->box + 4);
+  Count<DBG>(cnt, kTriAabb);
+  double unused;
+  if (!SlabRegular(b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, r, &unused)) return;  // primitive_triangle.cc:85-108
+  Count<DBG>(cnt, kMt);
+  double t, e;
+  if (!MollerTrumboreBound(rec->vert, r, &t, &e)) return;
+  Count<DBG>(cnt, kHit);
+  if (fb->slot >= 0 && !(t < fb->t)) {
+    fb->lo2 = fmin(fb->lo2, t - e);
+    return;
+  }
+  if (fb->slot >= 0) fb->lo2 = fmin(fb->lo2, fb->t - fb->e);
+  fb->t = t;
+  fb->e = e;
+  fb->slot = __ldg(&rec->canon);
+  fb->prune = __double2float_ru(t + 2.0 * e + t * 0x1p-20);
+}
+
+// Conservative FP32 slab test of one child box; *tn = lower bound of the entry distance.  t = fma(b, i, -(o i))
+// differs from the FP64 value of (b - o) * i by at most 2^-23 |t| + 2^-20 R |i| for |o| <= 8R (o and i rounded
+// to float, the product o i, the fma); the interval is widened by 2^-21 |t| + 2^-18 R |i| (`slack`), and it is
+// enough to widen the winning axis of each min / max.
+__device__ __forceinline__ bool FastBox(float lox, float loy, float loz, float hix, float hiy, float hiz, const Ray &r,
+                                        float nox, float noy, float noz, float slack, float prune, float *tn_out) {
+  const float kRel = 4.76837158203125e-07f;  // 2^-21
+  const float tx0 = __fmaf_rn(lox, r.ix, nox), tx1 = __fmaf_rn(hix, r.ix, nox);
+  const float ty0 = __fmaf_rn(loy, r.iy, noy), ty1 = __fmaf_rn(hiy, r.iy, noy);
+  const float tz0 = __fmaf_rn(loz, r.iz, noz), tz1 = __fmaf_rn(hiz, r.iz, noz);
+  float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fminf(tz0, tz1));
+  float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
+  tn = tn - __fmaf_rn(kRel, fabsf(tn), slack);
+  tf = tf + __fmaf_rn(kRel, fabsf(tf), slack);
+  *tn_out = tn;
+  return tf >= 0.0f && tn <= tf && tn <= prune;
+}
+
+template <bool DBG>
+__device__ int TraceFast(const DeviceScene &sc, const Ray &r, double *t_out, bool *ambiguous, unsigned long long *cnt) {
+  int st_node[kFastStack];
+  float st_t[kFastStack];
+  int sp = 0;
+  const float nox = -(r.ox * r.ix), noy = -(r.oy * r.iy), noz = -(r.oz * r.iz);
+  const float slack = 4.0f * fmaxf(fmaxf(r.px, r.py), r.pz);  // 2^-18 R max|i|
+  FastBest fb;
+  fb.t = 0.0;
+  fb.e = 0.0;
+  fb.lo2 = CUDART_INF;
+  fb.slot = -1;
+  fb.prune = CUDART_INF_F;
+  int node = 0;
+  for (;;) {
+    while (node >= 0) {
+      const float4 *q = reinterpret_cast<const float4 *>(sc.gnodes + node);
+      const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+      const int2 kids = __ldg(reinterpret_cast<const int2 *>(q + 3));
+      Count<DBG>(cnt, kBvh, 2);
+      float tl, tr;
+      const bool hl = FastBox(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, nox, noy, noz, slack, fb.prune, &tl);
+      const bool hr = FastBox(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, nox, noy, noz, slack, fb.prune, &tr);
+      if (hl && hr) {
+        const bool right_first = tr < tl;
+        st_node[sp] = right_first ? kids.x : kids.y;
+        st_t[sp] = right_first ? tl : tr;
+        sp++;
+        node = right_first ? kids.y : kids.x;
+      } else if (hl) {
+        node = kids.x;
+      } else if (hr) {
+        node = kids.y;
+      } else {
+        node = kFastExit;
+        while (sp > 0) {
+          sp--;
+          if (st_t[sp] <= fb.prune) {
+            node = st_node[sp];
+            break;
+          }
+        }
+      }
+    }
+    if (node == kFastExit) break;
+    const unsigned leaf = ~(unsigned)node;
+    for (unsigned s = leaf >> 3, e = s + (leaf & 7u); s < e; s++) TestSlotFast<DBG>(sc.gslots + s, r, &fb, cnt);
+    node = kFastExit;
+    while (sp > 0) {
+      sp--;
+      if (st_t[sp] <= fb.prune) {
+        node = st_node[sp];
+        break;
+      }
+    }
+  }
+  *ambiguous = fb.slot >= 0 && fb.lo2 <= fb.t + fb.e;
+  *t_out = fb.t;
+  return fb.slot;
+}
+
+// The exact recursion as a real call: with the fast traversal in front it runs for a handful of rays per frame.
+template <bool DBG>
+__device__ __noinline__ int TraceRegularCold(const DeviceScene &sc, const Ray &r, double *t_out, unsigned long long *cnt MTB_TOP_PARAMS) {
+  return TraceRegular<DBG>(sc, r, t_out, cnt MTB_TOP_ARGS);
+}
+
 // OctTree::IntersectRay (octtree.cc:26-40): inverse direction, then one of the two traversals.
 template <bool DBG>
 __device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D3 &d, double *t_out,
@@ -548,7 +724,16 @@ __device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D
     r.px = pr * fabsf(r.ix);
     r.py = pr * fabsf(r.iy);
     r.pz = pr * fabsf(r.iz);
-    return TraceRegular<DBG>(sc, r, t_out, cnt MTB_TOP_ARGS);
+    if (sc.gnodes != nullptr && r.cull32) {
+      bool ambiguous;
+      const int slot = TraceFast<DBG>(sc, r, t_out, &ambiguous, cnt);
+      if (!ambiguous) {
+        Count<DBG>(cnt, kFast);
+        return slot;
+      }
+      Count<DBG>(cnt, kFallback);
+    }
+    return TraceRegularCold<DBG>(sc, r, t_out, cnt MTB_TOP_ARGS);
   }
   return TraceLiteral<DBG>(sc, r, t_out, cnt);
 }
@@ -583,12 +768,13 @@ __device__ __forceinline__ BaryWeights Barycentric(const D3 &v0, const D3 &v1, c
   return w;
 }
 
-// texture.cc:11-58 with point fetches of the 8-bit texels; px / 255.0 as texture.cc:100-104.
-__device__ __forceinline__ D3 Texel(cudaTextureObject_t tex, size_t x, size_t y) {
-  const uchar4 p = tex2D<uchar4>(tex, (float)x + 0.5f, (float)y + 0.5f);
-  return Mk((double)p.x / 255.0, (double)p.y / 255.0, (double)p.z / 255.0);
+// texture.cc:11-58 with point fetches of the 8-bit texels; px / 255.0 as texture.cc:100-104.  A texel is one
+// 32-bit word (R | G << 8 | B << 16 | A << 24) of layer `layer` of the scene's single layered texture object.
+__device__ __forceinline__ D3 Texel(cudaTextureObject_t atlas, int layer, size_t x, size_t y) {
+  const unsigned p = tex2DLayered<unsigned>(atlas, (float)x + 0.5f, (float)y + 0.5f, layer);
+  return Mk((double)(p & 255u) / 255.0, (double)((p >> 8) & 255u) / 255.0, (double)((p >> 16) & 255u) / 255.0);
 }
-__device__ D3 SampleTexture(cudaTextureObject_t tex, int2 dim, double u, double v) {
+__device__ __noinline__ D3 SampleTexture(cudaTextureObject_t tex, int layer, int2 dim, double u, double v) {
   u = fmod(u, 1.0);
   v = fmod(v, 1.0);
   if (u < 0.0) u += 1.0;
@@ -604,7 +790,7 @@ __device__ D3 SampleTexture(cudaTextureObject_t tex, int2 dim, double u, double 
   if (by >= height) by = height - 1;
   const size_t bx1 = (bx + 1 == width) ? bx : bx + 1;
   const size_t by1 = (by + 1 == height) ? by : by + 1;
-  const D3 c0 = Texel(tex, bx, by), c1 = Texel(tex, bx1, by), c2 = Texel(tex, bx, by1), c3 = Texel(tex, bx1, by1);
+  const D3 c0 = Texel(tex, layer, bx, by), c1 = Texel(tex, layer, bx1, by), c2 = Texel(tex, layer, bx, by1), c3 = Texel(tex, layer, bx1, by1);
   const double dx = fmod(x, 1.0);
   const double dy = fmod(y, 1.0);
   const double a0 = (1.0 - dx) * (1.0 - dy);

@@ -15,8 +15,10 @@ struct DeviceScene {
   const ShadeRec *shade;
   const BvhRec *bvh;
   const int32_t *list_order;
+  const Bvh2Node *gnodes;   // scene BVH of the certified fast traversal; NULL: exact octree recursion only
+  const SlotRec *gslots;    // the triangles in scene-BVH leaf order (SlotRec::canon = slot in slots / shade)
   const mtb_material *materials;
-  const cudaTextureObject_t *textures;  // uchar4 point-sampled texture objects
+  cudaTextureObject_t tex_atlas;  // ONE point-sampled layered texture object: layer = texture index, one RGBA32 texel per 32-bit word
   const int2 *texture_dim;
   const mtb_light *lights;
   int32_t n_lights;
@@ -29,7 +31,7 @@ struct DeviceScene {
 
 // Work counters, one slot per field of mtb_stats' integer part (same order).
 enum Counter {
-  kRays = 0, kPrimary, kShadow, kReflect, kRefract, kSlab, kVisit, kTriAabb, kMt, kHit, kShade, kBvh, kLiteral,
+  kRays = 0, kPrimary, kShadow, kReflect, kRefract, kSlab, kVisit, kTriAabb, kMt, kHit, kShade, kBvh, kLiteral, kFast, kFallback,
   kNumCounters
 };
 

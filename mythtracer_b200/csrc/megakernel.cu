@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
             if (tex >= 0) {  // mythtracer.cc:59-64
               const double u = (sh->uv[0] * w.n0 + sh->uv[2] * w.n1 + sh->uv[4] * w.n2) / w.n;
               const double v = (sh->uv[1] * w.n0 + sh->uv[3] * w.n1 + sh->uv[5] * w.n2) / w.n;
-              surface = MulV(surface, SampleTexture(sc.textures[tex], sc.texture_dim[tex], u, v));
+              surface = MulV(surface, SampleTexture(sc.tex_atlas, tex, sc.texture_dim[tex], u, v));
             }
             // ray.direction - normal * (2 * ray.direction.Dot(normal)) (mythtracer.cc:68-69)
             reflected = Sub(m_d, MulS(normal, 2 * Dot(normal, m_d)));

@@ -104,7 +104,121 @@ inline float RoundUp(double x) {
   return f;
 }
 
-// Median-split BVH over `ids[b, e)`; emits records depth first and the slot order of the triangles.
+// Bounds of ids[b, e): union box `u` and the bounds clo/chi of the doubled centroids (lo + hi).
+inline void RangeBounds(const std::vector<Box3> &tri_box, const std::vector<int32_t> &ids, int32_t b, int32_t e, Box3 *u,
+                        double clo[3], double chi[3]) {
+  for (int a = 0; a < 3; a++) {
+    u->lo[a] = clo[a] = INFINITY;
+    u->hi[a] = chi[a] = -INFINITY;
+  }
+  for (int32_t i = b; i < e; i++) {
+    const Box3 &tb = tri_box[ids[i]];
+    for (int a = 0; a < 3; a++) {
+      u->lo[a] = std::min(u->lo[a], tb.lo[a]);
+      u->hi[a] = std::max(u->hi[a], tb.hi[a]);
+      const double cc = tb.lo[a] + tb.hi[a];
+      clo[a] = std::min(clo[a], cc);
+      chi[a] = std::max(chi[a], cc);
+    }
+  }
+}
+
+// Partitions ids[b, e) in place and returns the split position (b < mid < e for e - b >= 2): binned surface-area
+// heuristic over the centroids (16 bins per axis); object median along the widest axis when SAH finds no split
+// (or `median_only`).  The summed surface area of the descendants is proportional to the expected number of box
+// tests of a ray that is not pruned by distance: what SAH minimises.
+int32_t SahPartition(const std::vector<Box3> &tri_box, std::vector<int32_t> &ids, int32_t b, int32_t e, const double clo[3],
+                     const double chi[3], bool median_only) {
+  constexpr int kBins = 16;
+  int best_axis = -1, best_bin = -1;
+  double best_cost = INFINITY;
+  for (int axis = 0; axis < 3 && !median_only; axis++) {
+    const double lo = clo[axis], ext = chi[axis] - clo[axis];
+    if (!(ext > 0.0)) continue;
+    Box3 bin_box[kBins];
+    int bin_n[kBins];
+    for (int k = 0; k < kBins; k++) {
+      bin_n[k] = 0;
+      for (int a = 0; a < 3; a++) {
+        bin_box[k].lo[a] = INFINITY;
+        bin_box[k].hi[a] = -INFINITY;
+      }
+    }
+    for (int32_t i = b; i < e; i++) {
+      const Box3 &tb = tri_box[ids[i]];
+      int k = (int)(((tb.lo[axis] + tb.hi[axis]) - lo) / ext * kBins);
+      k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
+      bin_n[k]++;
+      for (int a = 0; a < 3; a++) {
+        bin_box[k].lo[a] = std::min(bin_box[k].lo[a], tb.lo[a]);
+        bin_box[k].hi[a] = std::max(bin_box[k].hi[a], tb.hi[a]);
+      }
+    }
+    double right_area[kBins];
+    int right_n[kBins];
+    Box3 acc;
+    int n_acc = 0;
+    for (int a = 0; a < 3; a++) {
+      acc.lo[a] = INFINITY;
+      acc.hi[a] = -INFINITY;
+    }
+    for (int k = kBins - 1; k > 0; k--) {
+      if (bin_n[k] > 0) {
+        for (int a = 0; a < 3; a++) {
+          acc.lo[a] = std::min(acc.lo[a], bin_box[k].lo[a]);
+          acc.hi[a] = std::max(acc.hi[a], bin_box[k].hi[a]);
+        }
+        n_acc += bin_n[k];
+      }
+      right_area[k] = n_acc > 0 ? HalfArea(acc) : 0.0;
+      right_n[k] = n_acc;
+    }
+    n_acc = 0;
+    for (int a = 0; a < 3; a++) {
+      acc.lo[a] = INFINITY;
+      acc.hi[a] = -INFINITY;
+    }
+    for (int k = 0; k + 1 < kBins; k++) {
+      if (bin_n[k] > 0) {
+        for (int a = 0; a < 3; a++) {
+          acc.lo[a] = std::min(acc.lo[a], bin_box[k].lo[a]);
+          acc.hi[a] = std::max(acc.hi[a], bin_box[k].hi[a]);
+        }
+        n_acc += bin_n[k];
+      }
+      if (n_acc == 0 || right_n[k + 1] == 0) continue;
+      const double cost = HalfArea(acc) * n_acc + right_area[k + 1] * right_n[k + 1];
+      if (cost < best_cost) {
+        best_cost = cost;
+        best_axis = axis;
+        best_bin = k;
+      }
+    }
+  }
+  int32_t mid = b;  // all centroids coincide
+  if (best_axis >= 0) {
+    const double lo = clo[best_axis], ext = chi[best_axis] - clo[best_axis];
+    auto bin_of = [&](int32_t t) {
+      int k = (int)(((tri_box[t].lo[best_axis] + tri_box[t].hi[best_axis]) - lo) / ext * kBins);
+      return k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
+    };
+    mid = (int32_t)(std::partition(ids.begin() + b, ids.begin() + e, [&](int32_t t) { return bin_of(t) <= best_bin; }) - ids.begin());
+  }
+  if (mid == b || mid == e) {
+    int axis = 0;
+    if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
+    if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
+    mid = b + (e - b) / 2;
+    std::nth_element(ids.begin() + b, ids.begin() + mid, ids.begin() + e, [&](int32_t x, int32_t y) {
+      const double cx = tri_box[x].lo[axis] + tri_box[x].hi[axis];
+      const double cy = tri_box[y].lo[axis] + tri_box[y].hi[axis];
+      return cx < cy || (cx == cy && x < y);
+    });
+  }
+  return mid;
+}
+
+// SAH BVH over `ids[b, e)` of ONE node list; emits threaded records depth first and the slot order of the triangles.
 struct BvhBuilder {
   const std::vector<Box3> &tri_box;
   std::vector<BvhRec> *out;
@@ -116,20 +230,7 @@ struct BvhBuilder {
     out->emplace_back();
     Box3 u;
     double clo[3], chi[3];
-    for (int a = 0; a < 3; a++) {
-      u.lo[a] = clo[a] = INFINITY;
-      u.hi[a] = chi[a] = -INFINITY;
-    }
-    for (int32_t i = b; i < e; i++) {
-      const Box3 &tb = tri_box[ids[i]];
-      for (int a = 0; a < 3; a++) {
-        u.lo[a] = std::min(u.lo[a], tb.lo[a]);
-        u.hi[a] = std::max(u.hi[a], tb.hi[a]);
-        const double cc = tb.lo[a] + tb.hi[a];
-        clo[a] = std::min(clo[a], cc);
-        chi[a] = std::max(chi[a], cc);
-      }
-    }
+    RangeBounds(tri_box, ids, b, e, &u, clo, chi);
     BvhRec rec;
     memset(&rec, 0, sizeof(rec));
     for (int a = 0; a < 3; a++) {
@@ -142,97 +243,7 @@ struct BvhBuilder {
       (*out)[me] = rec;
       return;
     }
-    // Binned surface-area heuristic over the centroids (16 bins per axis).  Every ray visits every record
-    // whose box it pierces (the cull never prunes by distance), so the expected number of box tests below a
-    // record is proportional to the summed surface areas of its descendants: exactly what SAH minimises.
-    constexpr int kBins = 16;
-    int best_axis = -1, best_bin = -1;
-    double best_cost = INFINITY;
-    for (int axis = 0; axis < 3; axis++) {
-      const double lo = clo[axis], ext = chi[axis] - clo[axis];
-      if (!(ext > 0.0)) continue;
-      Box3 bin_box[kBins];
-      int bin_n[kBins];
-      for (int k = 0; k < kBins; k++) {
-        bin_n[k] = 0;
-        for (int a = 0; a < 3; a++) {
-          bin_box[k].lo[a] = INFINITY;
-          bin_box[k].hi[a] = -INFINITY;
-        }
-      }
-      for (int32_t i = b; i < e; i++) {
-        const Box3 &tb = tri_box[ids[i]];
-        int k = (int)(((tb.lo[axis] + tb.hi[axis]) - lo) / ext * kBins);
-        k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
-        bin_n[k]++;
-        for (int a = 0; a < 3; a++) {
-          bin_box[k].lo[a] = std::min(bin_box[k].lo[a], tb.lo[a]);
-          bin_box[k].hi[a] = std::max(bin_box[k].hi[a], tb.hi[a]);
-        }
-      }
-      double right_area[kBins];
-      int right_n[kBins];
-      Box3 acc;
-      int n_acc = 0;
-      for (int a = 0; a < 3; a++) {
-        acc.lo[a] = INFINITY;
-        acc.hi[a] = -INFINITY;
-      }
-      for (int k = kBins - 1; k > 0; k--) {
-        if (bin_n[k] > 0) {
-          for (int a = 0; a < 3; a++) {
-            acc.lo[a] = std::min(acc.lo[a], bin_box[k].lo[a]);
-            acc.hi[a] = std::max(acc.hi[a], bin_box[k].hi[a]);
-          }
-          n_acc += bin_n[k];
-        }
-        right_area[k] = n_acc > 0 ? HalfArea(acc) : 0.0;
-        right_n[k] = n_acc;
-      }
-      n_acc = 0;
-      for (int a = 0; a < 3; a++) {
-        acc.lo[a] = INFINITY;
-        acc.hi[a] = -INFINITY;
-      }
-      for (int k = 0; k + 1 < kBins; k++) {
-        if (bin_n[k] > 0) {
-          for (int a = 0; a < 3; a++) {
-            acc.lo[a] = std::min(acc.lo[a], bin_box[k].lo[a]);
-            acc.hi[a] = std::max(acc.hi[a], bin_box[k].hi[a]);
-          }
-          n_acc += bin_n[k];
-        }
-        if (n_acc == 0 || right_n[k + 1] == 0) continue;
-        const double cost = HalfArea(acc) * n_acc + right_area[k + 1] * right_n[k + 1];
-        if (cost < best_cost) {
-          best_cost = cost;
-          best_axis = axis;
-          best_bin = k;
-        }
-      }
-    }
-    int32_t mid;
-    if (best_axis >= 0) {
-      const double lo = clo[best_axis], ext = chi[best_axis] - clo[best_axis];
-      auto bin_of = [&](int32_t t) {
-        int k = (int)(((tri_box[t].lo[best_axis] + tri_box[t].hi[best_axis]) - lo) / ext * kBins);
-        return k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
-      };
-      mid = (int32_t)(std::partition(ids.begin() + b, ids.begin() + e, [&](int32_t t) { return bin_of(t) <= best_bin; }) - ids.begin());
-    } else {
-      mid = b;  // all centroids coincide
-    }
-    if (mid == b || mid == e) {
-      int axis = 0;
-      if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
-      if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
-      mid = b + (e - b) / 2;
-      std::nth_element(ids.begin() + b, ids.begin() + mid, ids.begin() + e, [&](int32_t x, int32_t y) {
-        const double cx = tri_box[x].lo[axis] + tri_box[x].hi[axis];
-        const double cy = tri_box[y].lo[axis] + tri_box[y].hi[axis];
-        return cx < cy || (cx == cy && x < y);
-      });
-    }
+    const int32_t mid = SahPartition(tri_box, ids, b, e, clo, chi, false);
     Build(b, mid);
     Build(mid, e);
     rec.skip = (int32_t)out->size();
@@ -240,9 +251,44 @@ struct BvhBuilder {
   }
 };
 
+// Scene BVH (Bvh2Node, scene_build.h) over ALL triangles: the acceleration structure of the certified fast
+// traversal.  ids ends up in leaf order = the order of the `gslots` copies.
+struct SceneBvhBuilder {
+  const std::vector<Box3> &tri_box;
+  std::vector<Bvh2Node> *out;
+  std::vector<int32_t> ids;
+  int32_t max_depth = 0;
+
+  // returns the child reference (>= 0 inner node, < 0 leaf) and the FP64 union box of ids[b, e)
+  int32_t Build(int32_t b, int32_t e, int32_t depth, Box3 *box) {
+    double clo[3], chi[3];
+    RangeBounds(tri_box, ids, b, e, box, clo, chi);
+    if (depth > max_depth) max_depth = depth;
+    if (e - b <= kSceneBvhLeafSize) return ~(int32_t)(((uint32_t)b << 3) | (uint32_t)(e - b));
+    const int32_t me = (int32_t)out->size();
+    out->emplace_back();
+    const int32_t mid = SahPartition(tri_box, ids, b, e, clo, chi, depth >= 40);
+    Box3 lb, rb;
+    const int32_t l = Build(b, mid, depth + 1, &lb);
+    const int32_t r = Build(mid, e, depth + 1, &rb);
+    Bvh2Node &n = (*out)[(size_t)me];
+    memset(&n, 0, sizeof(n));
+    for (int a = 0; a < 3; a++) {
+      n.lbox[a] = RoundDown(lb.lo[a]);
+      n.lbox[3 + a] = RoundUp(lb.hi[a]);
+      n.rbox[a] = RoundDown(rb.lo[a]);
+      n.rbox[3 + a] = RoundUp(rb.hi[a]);
+    }
+    n.left = l;
+    n.right = r;
+    return me;
+  }
+};
+
 }  // namespace
 
-int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, FlatScene *out, std::string *err) {
+int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool use_scene_bvh, FlatScene *out,
+                   std::string *err) {
   if (n < 0 || n > 0x3fffffff) {
     *err = "triangle count out of range";
     return MTB_ERR_ARG;
@@ -328,6 +374,7 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, FlatS
       }
       memcpy(sr.vert, tris[t].vertex, sizeof(sr.vert));
       sr.tri = t;
+      sr.canon = s;
       ShadeRec &sh = out->shade[(size_t)s];
       memcpy(sh.normal, tris[t].normal, sizeof(sh.normal));
       for (int v = 0; v < 3; v++) {
@@ -354,6 +401,40 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, FlatS
     }
     out->nodes[i].child_mask = mask;
     subtree[i] = total;
+  }
+
+  // ---- scene BVH of the certified fast traversal ----
+  out->gnodes.clear();
+  out->gslots.clear();
+  out->gbvh_depth = 0;
+  if (use_scene_bvh && n > 0) {
+    SceneBvhBuilder sb{tri_box, &out->gnodes, {}, 0};
+    sb.ids.resize((size_t)n);
+    std::iota(sb.ids.begin(), sb.ids.end(), 0);
+    Box3 whole;
+    if (n <= kSceneBvhLeafSize) {
+      // a single leaf: the root holds it as its left child and an empty leaf on the right
+      double clo[3], chi[3];
+      RangeBounds(tri_box, sb.ids, 0, (int32_t)n, &whole, clo, chi);
+      Bvh2Node root;
+      memset(&root, 0, sizeof(root));
+      for (int a = 0; a < 3; a++) {
+        root.lbox[a] = root.rbox[a] = RoundDown(whole.lo[a]);
+        root.lbox[3 + a] = root.rbox[3 + a] = RoundUp(whole.hi[a]);
+      }
+      root.left = ~(int32_t)(uint32_t)n;  // first_gslot 0, count n
+      root.right = ~0;                    // count 0
+      out->gnodes.push_back(root);
+    } else {
+      sb.Build(0, (int32_t)n, 0, &whole);
+    }
+    out->gbvh_depth = sb.max_depth;
+    if (sb.max_depth > kSceneBvhMaxDepth) {
+      out->gnodes.clear();
+    } else {
+      out->gslots.resize((size_t)n);
+      for (int64_t i = 0; i < n; i++) out->gslots[(size_t)i] = out->slots[(size_t)slot_of[(size_t)sb.ids[(size_t)i]]];
+    }
   }
   return MTB_OK;
 }

@@ -24,6 +24,18 @@ struct alignas(32) BvhRec {
 };
 static_assert(sizeof(BvhRec) == 32, "BvhRec must be a quarter of a cache line");
 
+// Scene BVH of the certified fast traversal (device_core.cuh, TraceFast): one binary BVH over ALL triangles, a
+// node holds the boxes of its two children (FP32, rounded outwards) = 64 bytes, half a line, four 128-bit loads.
+// Like BvhRec it is a CONSERVATIVE cull only: the triangles of a leaf are decided by the exact FP64 reference tests.
+struct alignas(64) Bvh2Node {
+  float lbox[6];   // left child: lo.xyz rounded down, hi.xyz rounded up
+  float rbox[6];   // right child
+  int32_t left;    // >= 0: inner node index; < 0: leaf, ~left = (first_gslot << 3) | count (count 0..7)
+  int32_t right;
+  int32_t pad_[2];
+};
+static_assert(sizeof(Bvh2Node) == 64, "Bvh2Node must be half a cache line");
+
 // One octree node = one 128-byte line.  The 8 children of a node are contiguous (first_child .. +7) and
 // their boxes are exactly {lo,c} / {c,hi} per axis (octtree.cc:61-100), so a node carries the three
 // planes per axis once instead of eight child boxes.
@@ -45,7 +57,7 @@ struct alignas(128) SlotRec {
   double box[6];   // cached_aabb: lo.xyz, hi.xyz
   double vert[9];
   int32_t tri;     // insertion index (decides ties: later in the reference's list order wins)
-  int32_t pad_;
+  int32_t canon;   // slot index in FlatScene::slots / ::shade (identity there; the gslots copies point back)
 };
 static_assert(sizeof(SlotRec) == 128, "SlotRec must be one cache line");
 
@@ -64,6 +76,9 @@ struct FlatScene {
   std::vector<ShadeRec> shade;
   std::vector<BvhRec> bvh;
   std::vector<int32_t> list_order;  // list_order[list_first + k] = slot of the k-th entry in reference order
+  std::vector<Bvh2Node> gnodes;     // scene BVH, node 0 = root (empty: no fast traversal)
+  std::vector<SlotRec> gslots;      // copies of `slots` in scene-BVH leaf order
+  int32_t gbvh_depth = 0;
   int32_t depth = 0;
   int64_t root_list = 0, biggest_list = 0, interior = 0;
   double aabb[6] = {0, 0, 0, 0, 0, 0};
@@ -76,13 +91,19 @@ struct FlatScene {
 #ifndef MTB_BVH_MIN_LIST
 #define MTB_BVH_MIN_LIST 3
 #endif
+#ifndef MTB_SCENE_BVH_LEAF
+#define MTB_SCENE_BVH_LEAF 2
+#endif
+constexpr int kSceneBvhLeafSize = MTB_SCENE_BVH_LEAF;  // <= 7
+constexpr int kSceneBvhMaxDepth = 88;                   // deeper trees (never seen) disable the fast traversal
 constexpr int kBvhLeafSize = MTB_BVH_LEAF;      // <= 7 (3-bit count in BvhRec::leaf)
 constexpr int kBvhMinList = MTB_BVH_MIN_LIST;  // shorter lists are scanned linearly
 // measured on B200, C3 frame (megakernel / wavefront ms): leaf 4 min 12: 39.4 / 46.5; leaf 2 min 6: 36.5 / 42.7;
 // leaf 2 min 3: 35.5 / 41.8; leaf 3 min 4: 35.6 / 42.0; leaf 1 min 2: 37.9 / 44.9; leaf 6 min 16: 43.7 / 51.4
 
 // Returns MTB_OK or an error code with text in *err.
-int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, FlatScene *out, std::string *err);
+int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool use_scene_bvh, FlatScene *out,
+                   std::string *err);
 
 // Camera::GetSensor / Sensor::Reset (camera.cc:17-63): out9 = start_point, delta_scanline, delta_pixel.
 void ComputeSensor(const mtb_camera &cam, int image_w, int image_h, double out9[9]);

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTraceMain(Devic
           if (tex >= 0) {
             const double u = (sh->uv[0] * w.n0 + sh->uv[2] * w.n1 + sh->uv[4] * w.n2) / w.n;
             const double v = (sh->uv[1] * w.n0 + sh->uv[3] * w.n1 + sh->uv[5] * w.n2) / w.n;
-            surface = MulV(surface, SampleTexture(sc.textures[tex], sc.texture_dim[tex], u, v));
+            surface = MulV(surface, SampleTexture(sc.tex_atlas, tex, sc.texture_dim[tex], u, v));
           }
           const D3 reflected = Sub(d, MulS(normal, 2 * Dot(normal, d)));
           act_mtl = material;

@@ -532,3 +532,76 @@ def test_edge_scenes(product_lib, oracle_mod, scene_dir):
             _assert_render_equal(gpu, cpu, "%s flags %d" % (name, flags))
             r = mt.intersect_rays(np.zeros((0, 3)), np.zeros((0, 3)))
             assert len(r["tri"]) == 0
+
+
+def test_fast_traversal_and_exact_octree_agree(product_lib, oracle_mod, scene_dir):
+    """Regular rays are answered by the certified fast traversal (scene BVH) by default and
+    by the exact octree recursion under MTB_FLAG_EXACT_OCTREE.  Both against the oracle, every tap, both pipelines,
+    on C1 (full frame), textured C2 and a C3 tile; the counters must show which traversal ran."""
+    from mythtracer_b200 import MTB_FLAG_COUNT_WORK, MTB_FLAG_EXACT_OCTREE, MTB_FLAG_MEGAKERNEL, MTB_FLAG_WAVEFRONT
+    for name, scale, (W, H), chunk in [("C1", 1.0, (320, 240), (0, 0, 320, 240)), ("C2", 0.3, (320, 180), (0, 0, 320, 180)),
+                                        ("C3", 0.2, (1920, 1080), (900, 500, 128, 64))]:
+        files, cfg = scenes.config_scene(name, scene_dir, scale)
+        mt, orc = _load_pair(product_lib, oracle_mod, files, cfg["depth"], MTB_FLAG_MEGAKERNEL)
+        cpu = orc.render(files.camera, W, H, chunk=chunk, depth=cfg["depth"], taps=True)
+        for pipe in (MTB_FLAG_MEGAKERNEL, MTB_FLAG_WAVEFRONT):
+            for exact in (0, MTB_FLAG_EXACT_OCTREE):
+                mt.set_flags(pipe | exact | MTB_FLAG_COUNT_WORK)
+                gpu = mt.render_chunk(files.camera, W, H, *chunk, debug=True, taps=True)
+                _assert_render_equal(gpu, cpu, "%s pipe %d exact %d" % (name, pipe, exact))
+                st = gpu["stats"]
+                assert st["n_fast"] + st["n_fallback"] + st["n_literal"] == st["rays"] or exact
+                if exact:
+                    assert st["n_fast"] == 0 and st["n_fallback"] == 0
+                else:
+                    assert st["n_fast"] > 0.99 * st["rays"], "the fast traversal should answer nearly every ray"
+                mt.set_flags(pipe | exact)
+                fast = mt.render_chunk(files.camera, W, H, *chunk)
+                assert np.array_equal(fast["rgb"], gpu["rgb"])
+
+
+def test_ambiguous_hits_fall_back_to_the_exact_recursion(product_lib, oracle_mod, scene_dir):
+    """Coincident triangles (exact ties in t: the reference's list order decides, octtree.cc:186-195), triangles that
+    differ by 1e-13 (hits inside each other's error bound) and a grazing, ill-conditioned triangle: the fast
+    traversal must declare these rays ambiguous and the exact recursion must give the reference's answer."""
+    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_COUNT_WORK, MTB_FLAG_MEGAKERNEL, MTB_FLAG_WAVEFRONT
+    from mythtracer_b200.api import MTL_DTYPE, TRI_DTYPE
+    cam = (0.3, 0.4, -6.0, 2.0, 5.0, 1.0, 70.0)
+    lights = [(1.0, 5.0, -4.0, 0.2, 0.2, 0.2, 1.0, 1.0, 1.0, 0.8, 0.8, 0.8)]
+    mtl = np.zeros(3, MTL_DTYPE)
+    for i, ka in enumerate([(0.9, 0.1, 0.1), (0.1, 0.9, 0.1), (0.1, 0.1, 0.9)]):
+        mtl["ambient"][i], mtl["diffuse"][i], mtl["specular"][i] = ka, (0.5, 0.5, 0.5), (0.3, 0.3, 0.3)
+        mtl["specular_exp"][i], mtl["texture"][i] = 20.0, -1
+    mtl["transparency"][2], mtl["transmission_filter"][2], mtl["reflectance"][1] = 0.5, (0.9, 0.9, 0.9), 0.5
+    rng = np.random.default_rng(7)
+    base = np.zeros(40, TRI_DTYPE)
+    base["vertex"] = rng.uniform(-4, 4, (40, 9))
+    base["vertex"][:, 2::3] += 3.0
+    base["normal"] = rng.normal(size=(40, 9))
+    tris = np.concatenate([base, base, base])           # every triangle three times: exact ties everywhere
+    tris["vertex"][80:] += 1e-13                         # the third copy is displaced by less than the error bound
+    tris["material"] = np.repeat([0, 1, 2], 40)
+    graze = np.zeros(1, TRI_DTYPE)                       # nearly edge-on from the camera: tiny determinant
+    graze["vertex"] = [0.3, 0.4, -5.0, 0.3 + 1e-7, 3.0, 6.0, 0.3 - 1e-7, -3.0, 6.0]
+    graze["normal"] = [1, 0, 0] * 3
+    tris = np.concatenate([tris, graze])
+    tris["line_no"] = np.arange(len(tris))
+    orc = oracle_mod.Oracle(tris, mtl, [])
+    orc.set_lights(lights)
+    cpu = orc.render(cam, 128, 96, depth=3, taps=True)
+    for flags in (MTB_FLAG_MEGAKERNEL, MTB_FLAG_WAVEFRONT):
+        mt = MythTracer(max_depth=3, flags=flags | MTB_FLAG_COUNT_WORK)
+        mt.upload(tris, mtl)
+        mt.GetScene().lights = [Light.from_tuple(l) for l in lights]
+        gpu = mt.render_chunk(cam, 128, 96, 0, 0, 128, 96, debug=True, taps=True)
+        _assert_render_equal(gpu, cpu, "ties flags %d" % flags)
+        assert gpu["stats"]["n_fallback"] > 0, "tied hits must be handed to the exact recursion"
+    # the same through the batched OctTree::IntersectRay
+    o = np.tile(np.array(cam[:3]), (2000, 1))
+    d = rng.normal(size=(2000, 3))
+    d[:, 2] = np.abs(d[:, 2]) + 0.5
+    got = mt.intersect_rays(o, d)
+    ref = orc.intersect(o, d)
+    assert np.array_equal(got["tri"], ref["tri"])
+    hit = got["tri"] >= 0
+    assert hit.sum() > 100 and np.array_equal(got["t"][hit], ref["t"][hit])

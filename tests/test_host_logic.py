@@ -183,3 +183,63 @@ def test_octree_depth_limit_and_degenerate_inputs(product_lib, oracle_mod):
     bad["material"] = 3
     with pytest.raises(MythTracerError, match="material"):
         mt.upload(bad, np.zeros(1, MTL_DTYPE))
+
+
+def test_scene_bvh_is_a_conservative_partition(product_lib, scene_dir):
+    """The certified fast traversal relies on two properties of the scene BVH: every triangle
+    sits in exactly one leaf, and every child box (FP32, rounded outwards) contains the exact FP64 boxes of all
+    triangles below it.  Checked on a generated scene, on scenes smaller than a leaf and on an empty scene."""
+    from mythtracer_b200 import MythTracer
+    from mythtracer_b200.api import MTL_DTYPE, TRI_DTYPE
+    from tests import scenes
+    files, cfg = scenes.config_scene("C1", scene_dir)
+    mt = MythTracer(host_only=True)
+    assert mt.LoadObj(files.obj_path)
+    tris, _ = mt.scene_arrays()
+
+    def check(mt, tris):
+        nodes, depth, order = mt.scene_bvh()
+        n = len(tris)
+        assert sorted(order.tolist()) == list(range(n)), "leaf order must be a permutation of the triangles"
+        v = tris["vertex"].reshape(n, 3, 3)
+        lo, hi = v.min(axis=1), v.max(axis=1)
+        seen = np.zeros(n, int)
+        max_depth = 0
+
+        def walk(ref, d):
+            """returns (lo, hi) of everything below `ref`"""
+            nonlocal max_depth
+            max_depth = max(max_depth, d)
+            if ref < 0:
+                x = (~ref) & 0xFFFFFFFF
+                first, count = x >> 3, x & 7
+                ids = order[first:first + count]
+                seen[ids] += 1
+                if count == 0:
+                    return np.full(3, np.inf), np.full(3, -np.inf)
+                return lo[ids].min(axis=0), hi[ids].max(axis=0)
+            nd = nodes[ref]
+            out_lo, out_hi = np.full(3, np.inf), np.full(3, -np.inf)
+            for box, child in ((nd["lbox"], int(nd["left"])), (nd["rbox"], int(nd["right"]))):
+                c_lo, c_hi = walk(child, d + 1)
+                assert np.all(box[:3].astype(np.float64) <= c_lo) and np.all(box[3:].astype(np.float64) >= c_hi), "child box must contain its triangles"
+                out_lo, out_hi = np.minimum(out_lo, c_lo), np.maximum(out_hi, c_hi)
+            return out_lo, out_hi
+
+        if n == 0:
+            assert len(nodes) == 0
+            return
+        import sys
+        sys.setrecursionlimit(10000)
+        walk(0, 0)
+        assert np.all(seen == 1), "every triangle in exactly one leaf"
+        assert max_depth <= depth + 1
+
+    check(mt, tris)
+    for n in (1, 2, 3, 5):
+        small = MythTracer(host_only=True)
+        small.upload(tris[:n], np.zeros(0, MTL_DTYPE) if False else mt.scene_arrays()[1])
+        check(small, tris[:n])
+    empty = MythTracer(host_only=True)
+    empty.upload(np.zeros(0, TRI_DTYPE), np.zeros(0, MTL_DTYPE))
+    check(empty, np.zeros(0, TRI_DTYPE))

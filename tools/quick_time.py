@@ -10,7 +10,7 @@ out = []
 for name in names:
     files, cfg = scenegen.generate_config(name, "/tmp/mtb_scenes")
     for mode in modes:
-        base_flags = {"bvh": 16, "nobvh": MTB_FLAG_NO_LIST_BVH | 16, "wf": MTB_FLAG_WAVEFRONT, "wfsort": MTB_FLAG_WAVEFRONT | 8, "auto": 0, "noorder": 16 | 32, "persist": 16 | 64}.get(mode, 0)
+        base_flags = {"bvh": 16, "nobvh": MTB_FLAG_NO_LIST_BVH | 16, "wf": MTB_FLAG_WAVEFRONT, "wfsort": MTB_FLAG_WAVEFRONT | 8, "auto": 0, "noorder": 16 | 32, "persist": 16 | 64, "exact": 16 | 128, "wfexact": 4 | 128}.get(mode, 0)
         mt = MythTracer(max_depth=cfg["depth"], flags=base_flags)
         t0 = time.time(); assert mt.LoadObj(files.obj_path); t_load = time.time() - t0
         mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]
@@ -27,7 +27,7 @@ for name in names:
                    total_ms=round(best["total_ms"], 3), rays=rays, mrays_s=round(rays / best["kernel_ms"] / 1e3, 1),
                    per_ray=dict(slab=round(c["n_slab"] / rays, 1), visit=round(c["n_visit"] / rays, 1), triaabb=round(c["n_triaabb"] / rays, 1),
                                 bvh=round(c["n_bvh"] / rays, 1), mt=round(c["n_mt"] / rays, 2), hit=round(c["n_hit"] / rays, 2), shade=round(c["n_shade"] / rays, 2)),
-                   literal=c["n_literal"], count_kernel_ms=round(c["kernel_ms"], 1))
+                   literal=c["n_literal"], fast=c["n_fast"], fallback=c["n_fallback"], count_kernel_ms=round(c["kernel_ms"], 1))
         print(json.dumps(rec), flush=True)
         out.append(rec)
         mt.close()

@@ -610,18 +610,24 @@ __device__ __forceinline__ void TestSlotFast(const SlotRec *rec, const Ray &r, F
 
 // Conservative FP32 slab test of one child box; *tn = lower bound of the entry distance.  t = fma(b, i, -(o i))
 // differs from the FP64 value of (b - o) * i by at most 2^-23 |t| + 2^-20 R |i| for |o| <= 8R (o and i rounded
-// to float, the product o i, the fma); the interval is widened by 2^-21 |t| + 2^-18 R |i| (`slack`), and it is
-// enough to widen the winning axis of each min / max.
+// to float, the product o i, the fma).  Every near plane is pushed down and every far plane up by the absolute
+// part PER AXIS (2^-18 R |i_axis|, folded into the fma's addend: FastRay::nn / nf), then the winners of the
+// max / min by the relative part 2^-21 |t|.  (The absolute part must not be shared between axes: an axis the ray
+// is almost perpendicular to has a huge |i| and would make every box of the scene pass.)
+struct FastRay {
+  float nnx, nny, nnz;  // -(o i) - slack per axis: addend of a near plane
+  float nfx, nfy, nfz;  // -(o i) + slack per axis: addend of a far plane
+};
 __device__ __forceinline__ bool FastBox(float lox, float loy, float loz, float hix, float hiy, float hiz, const Ray &r,
-                                        float nox, float noy, float noz, float slack, float prune, float *tn_out) {
+                                        const FastRay &f, float prune, float *tn_out) {
   const float kRel = 4.76837158203125e-07f;  // 2^-21
-  const float tx0 = __fmaf_rn(lox, r.ix, nox), tx1 = __fmaf_rn(hix, r.ix, nox);
-  const float ty0 = __fmaf_rn(loy, r.iy, noy), ty1 = __fmaf_rn(hiy, r.iy, noy);
-  const float tz0 = __fmaf_rn(loz, r.iz, noz), tz1 = __fmaf_rn(hiz, r.iz, noz);
-  float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fminf(tz0, tz1));
-  float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
-  tn = tn - __fmaf_rn(kRel, fabsf(tn), slack);
-  tf = tf + __fmaf_rn(kRel, fabsf(tf), slack);
+  const float nx = __fmaf_rn(r.sx ? hix : lox, r.ix, f.nnx), fx = __fmaf_rn(r.sx ? lox : hix, r.ix, f.nfx);
+  const float ny = __fmaf_rn(r.sy ? hiy : loy, r.iy, f.nny), fy = __fmaf_rn(r.sy ? loy : hiy, r.iy, f.nfy);
+  const float nz = __fmaf_rn(r.sz ? hiz : loz, r.iz, f.nnz), fz = __fmaf_rn(r.sz ? loz : hiz, r.iz, f.nfz);
+  float tn = fmaxf(fmaxf(nx, ny), nz);
+  float tf = fminf(fminf(fx, fy), fz);
+  tn = __fmaf_rn(-kRel, fabsf(tn), tn);
+  tf = __fmaf_rn(kRel, fabsf(tf), tf);
   *tn_out = tn;
   return tf >= 0.0f && tn <= tf && tn <= prune;
 }
@@ -631,8 +637,16 @@ __device__ int TraceFast(const DeviceScene &sc, const Ray &r, double *t_out, boo
   int st_node[kFastStack];
   float st_t[kFastStack];
   int sp = 0;
-  const float nox = -(r.ox * r.ix), noy = -(r.oy * r.iy), noz = -(r.oz * r.iz);
-  const float slack = 4.0f * fmaxf(fmaxf(r.px, r.py), r.pz);  // 2^-18 R max|i|
+  FastRay f;  // r.px = 2^-20 R |ix| (Trace), the slack is four times that
+  {
+    const float nox = -(r.ox * r.ix), noy = -(r.oy * r.iy), noz = -(r.oz * r.iz);
+    f.nnx = nox - 4.0f * r.px;
+    f.nfx = nox + 4.0f * r.px;
+    f.nny = noy - 4.0f * r.py;
+    f.nfy = noy + 4.0f * r.py;
+    f.nnz = noz - 4.0f * r.pz;
+    f.nfz = noz + 4.0f * r.pz;
+  }
   FastBest fb;
   fb.t = 0.0;
   fb.e = 0.0;
@@ -647,8 +661,8 @@ __device__ int TraceFast(const DeviceScene &sc, const Ray &r, double *t_out, boo
       const int2 kids = __ldg(reinterpret_cast<const int2 *>(q + 3));
       Count<DBG>(cnt, kBvh, 2);
       float tl, tr;
-      const bool hl = FastBox(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, nox, noy, noz, slack, fb.prune, &tl);
-      const bool hr = FastBox(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, nox, noy, noz, slack, fb.prune, &tr);
+      const bool hl = FastBox(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, f, fb.prune, &tl);
+      const bool hr = FastBox(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, f, fb.prune, &tr);
       if (hl && hr) {
         const bool right_first = tr < tl;
         st_node[sp] = right_first ? kids.x : kids.y;

@@ -244,6 +244,7 @@ int UploadToDevice(mtb_context *ctx, DeviceState *d) {
   // the FP32 cull's error bound assumes coordinates of ordinary magnitude (see kernels.cu, CullBox)
   const double mac = ctx->flat.max_abs_coord;
   d->scene.cull_radius = (mac >= 0x1p-10 && mac <= 0x1p20) ? (float)mac * 1.0000002f : 0.0f;
+  d->scene.max_tri_extent = std::nextafterf((float)ctx->flat.max_tri_extent, INFINITY);
   SelectTraversal(ctx, d);
   return MTB_OK;
 }

@@ -605,7 +605,7 @@ __device__ __forceinline__ void TestSlotFast(const SlotRec *rec, const Ray &r, F
   fb->t = t;
   fb->e = e;
   fb->slot = __ldg(&rec->canon);
-  fb->prune = __double2float_ru(t + 2.0 * e + t * 0x1p-20);
+  fb->prune = fminf(fb->prune, __double2float_ru(t + 2.0 * e + t * 0x1p-20));
 }
 
 // Conservative FP32 slab test of one child box; *tn = lower bound of the entry distance.  t = fma(b, i, -(o i))
@@ -632,8 +632,29 @@ __device__ __forceinline__ bool FastBox(float lox, float loy, float loz, float h
   return tf >= 0.0f && tn <= tf && tn <= prune;
 }
 
+// t_limit: the caller discards every hit with t > t_limit (a shadow segment only asks about occluders in front of
+// the light, mythtracer.cc:115-118; +inf otherwise), so subtrees that start behind t_limit + M need not be
+// searched.  M must cover the rounding error of the t the reference would compute for a triangle that is never
+// evaluated here.  Worst case over every triangle the reference could accept (|det| >= 1e-8, component extents
+// <= L = sc.max_tri_extent) whose box the ray enters at distance T: |tvec_i| <= |d_i| T + L, so
+// N <= 6 L^2 (dmax T + L), D <= 6 dmax L^2 and, as in MollerTrumboreBound (with twice its constants),
+//   e <= 2^-48 * 6 L^2 (2 dmax T + L) / (1e-8 - 2^-48 * 6 dmax L^2) + 2^-49 T =: M(T).
+// M grows by far less than 1 per unit of T, so a triangle entered behind t_limit + M(t_limit) cannot come out in
+// front of t_limit.  If the denominator is not comfortably positive (huge triangles) nothing is pruned by limit.
+__device__ __forceinline__ float LimitPrune(const DeviceScene &sc, const Ray &r, double t_limit) {
+  if (!(t_limit < CUDART_INF)) return CUDART_INF_F;
+  const double L = (double)sc.max_tri_extent;
+  const double dmax = fmax(fmax(fabs(r.d.x), fabs(r.d.y)), fabs(r.d.z));
+  const double k = 0x1p-48 * 6.0 * L * L;
+  const double den = 0.00000001 - k * dmax;
+  if (!(den > 0.000000005)) return CUDART_INF_F;
+  const double m = k * (2.0 * dmax * t_limit + L) / den + 0x1p-49 * t_limit;
+  return __double2float_ru(t_limit + 2.0 * m + t_limit * 0x1p-20);
+}
+
 template <bool DBG>
-__device__ int TraceFast(const DeviceScene &sc, const Ray &r, double *t_out, bool *ambiguous, unsigned long long *cnt) {
+__device__ int TraceFast(const DeviceScene &sc, const Ray &r, double t_limit, double *t_out, bool *ambiguous,
+                         unsigned long long *cnt) {
   int st_node[kFastStack];
   float st_t[kFastStack];
   int sp = 0;
@@ -652,7 +673,7 @@ __device__ int TraceFast(const DeviceScene &sc, const Ray &r, double *t_out, boo
   fb.e = 0.0;
   fb.lo2 = CUDART_INF;
   fb.slot = -1;
-  fb.prune = CUDART_INF_F;
+  fb.prune = LimitPrune(sc, r, t_limit);
   int node = 0;
   for (;;) {
     while (node >= 0) {
@@ -707,9 +728,11 @@ __device__ __noinline__ int TraceRegularCold(const DeviceScene &sc, const Ray &r
   return TraceRegular<DBG>(sc, r, t_out, cnt MTB_TOP_ARGS);
 }
 
-// OctTree::IntersectRay (octtree.cc:26-40): inverse direction, then one of the two traversals.
+// OctTree::IntersectRay (octtree.cc:26-40): inverse direction, then one of the traversals.
+// t_limit: results with t > t_limit are of no use to the caller (it may then get -1 or any such hit); CUDART_INF
+// for a plain closest-hit query.
 template <bool DBG>
-__device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D3 &d, double *t_out,
+__device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D3 &d, double t_limit, double *t_out,
                                      unsigned long long *cnt MTB_TOP_PARAMS) {
   Ray r;
   r.o = o;
@@ -740,7 +763,7 @@ __device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D
     r.pz = pr * fabsf(r.iz);
     if (sc.gnodes != nullptr && r.cull32) {
       bool ambiguous;
-      const int slot = TraceFast<DBG>(sc, r, t_out, &ambiguous, cnt);
+      const int slot = TraceFast<DBG>(sc, r, t_limit, t_out, &ambiguous, cnt);
       if (!ambiguous) {
         Count<DBG>(cnt, kFast);
         return slot;

@@ -27,6 +27,8 @@ struct DeviceScene {
   // FP32 list-BVH cull: largest |coordinate| of the scene box; 0 disables the FP32 path (boxes are then
   // evaluated in FP64, still conservatively)
   float cull_radius;
+  // largest extent of any triangle's box along any axis (bounds |e1|, |e2| in the error model of LimitPrune)
+  float max_tri_extent;
 };
 
 // Work counters, one slot per field of mtb_stats' integer part (same order).

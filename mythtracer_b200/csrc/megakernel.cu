@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
         td = m_d;
       }
       double t = 0.0;
-      const int slot = Trace<DBG>(sc, to, td, &t, cnt MTB_TOP_ARGS);
+      const int slot = Trace<DBG>(sc, to, td, shadow_mode ? light_distance : CUDART_INF, &t, cnt MTB_TOP_ARGS);
       n_rays++;
 
       bool have_ret = false;
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(128) IntersectKernel(DeviceScene sc, Intersect
   if (i < ip.n) {
     const D3 o = Load3(ip.origins + i * 3), d = Load3(ip.dirs + i * 3);
     double t = 0.0;
-    const int slot = Trace<DBG>(sc, o, d, &t, cnt MTB_TOP_ARGS);
+    const int slot = Trace<DBG>(sc, o, d, CUDART_INF, &t, cnt MTB_TOP_ARGS);
     if (slot < 0) {
       ip.tri_index[i] = -1;
     } else {

@@ -15,7 +15,12 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
+#include <thread>
 
 namespace mtb {
 namespace {
@@ -252,36 +257,99 @@ struct BvhBuilder {
 };
 
 // Scene BVH (Bvh2Node, scene_build.h) over ALL triangles: the acceleration structure of the certified fast
-// traversal.  ids ends up in leaf order = the order of the `gslots` copies.
+// traversal.  ids ends up in leaf order = the order of the `gslots` copies.  The top of the tree is split by the
+// calling thread; every range of at most `grain` triangles below it is an independent job for a pool of threads
+// (each job builds into its own vector, the vectors are appended and their indices rebased afterwards), so the
+// result does not depend on the number of threads.
 struct SceneBvhBuilder {
   const std::vector<Box3> &tri_box;
-  std::vector<Bvh2Node> *out;
   std::vector<int32_t> ids;
   int32_t max_depth = 0;
 
-  // returns the child reference (>= 0 inner node, < 0 leaf) and the FP64 union box of ids[b, e)
-  int32_t Build(int32_t b, int32_t e, int32_t depth, Box3 *box) {
+  struct Job {
+    int32_t b, e, depth;
+    int32_t parent, side;  // where the finished subtree hangs
+    std::vector<Bvh2Node> nodes;
+    int32_t ref = 0;       // subtree root: local node index (>= 0) or leaf (< 0)
+    Box3 box;
+    int32_t deepest = 0;
+  };
+  std::vector<Job> jobs;
+
+  static void SetChild(Bvh2Node *n, int side, int32_t ref, const Box3 &box) {
+    float *dst = side == 0 ? n->lbox : n->rbox;
+    for (int a = 0; a < 3; a++) {
+      dst[a] = RoundDown(box.lo[a]);
+      dst[3 + a] = RoundUp(box.hi[a]);
+    }
+    (side == 0 ? n->left : n->right) = ref;
+  }
+
+  // Builds ids[b, e) into *out; ranges of at most `grain` triangles become jobs when jobs_out is given.
+  // Returns the child reference (>= 0 inner node, < 0 leaf) and the FP64 union box.
+  int32_t Build(std::vector<Bvh2Node> *out, int32_t b, int32_t e, int32_t depth, Box3 *box, int32_t *deepest, int32_t grain,
+                int32_t parent, int side) {
+    if (grain > 0 && e - b <= grain && parent >= 0) {
+      Job j;
+      j.b = b;
+      j.e = e;
+      j.depth = depth;
+      j.parent = parent;
+      j.side = side;
+      jobs.push_back(std::move(j));
+      return 0;  // patched when the job is done
+    }
     double clo[3], chi[3];
     RangeBounds(tri_box, ids, b, e, box, clo, chi);
-    if (depth > max_depth) max_depth = depth;
+    if (depth > *deepest) *deepest = depth;
     if (e - b <= kSceneBvhLeafSize) return ~(int32_t)(((uint32_t)b << 3) | (uint32_t)(e - b));
     const int32_t me = (int32_t)out->size();
     out->emplace_back();
+    memset(&out->back(), 0, sizeof(Bvh2Node));
     const int32_t mid = SahPartition(tri_box, ids, b, e, clo, chi, depth >= 40);
     Box3 lb, rb;
-    const int32_t l = Build(b, mid, depth + 1, &lb);
-    const int32_t r = Build(mid, e, depth + 1, &rb);
-    Bvh2Node &n = (*out)[(size_t)me];
-    memset(&n, 0, sizeof(n));
-    for (int a = 0; a < 3; a++) {
-      n.lbox[a] = RoundDown(lb.lo[a]);
-      n.lbox[3 + a] = RoundUp(lb.hi[a]);
-      n.rbox[a] = RoundDown(rb.lo[a]);
-      n.rbox[3 + a] = RoundUp(rb.hi[a]);
-    }
-    n.left = l;
-    n.right = r;
+    const int32_t l = Build(out, b, mid, depth + 1, &lb, deepest, grain, me, 0);
+    const int32_t r = Build(out, mid, e, depth + 1, &rb, deepest, grain, me, 1);
+    // (a deferred child leaves garbage here; it is overwritten when its job is merged)
+    SetChild(&(*out)[(size_t)me], 0, l, lb);
+    SetChild(&(*out)[(size_t)me], 1, r, rb);
     return me;
+  }
+
+  void Run(std::vector<Bvh2Node> *out, int32_t n) {
+    unsigned n_threads = std::thread::hardware_concurrency();
+    if (n_threads == 0) n_threads = 1;
+    if (n_threads > 32) n_threads = 32;
+    const int32_t grain = n_threads > 1 && n >= 65536 ? std::max<int32_t>(4096, n / (int32_t)(n_threads * 8)) : 0;
+    Box3 whole;
+    for (int a = 0; a < 3; a++) whole.lo[a] = whole.hi[a] = 0.0;
+    Build(out, 0, n, 0, &whole, &max_depth, grain, -1, 0);
+    if (jobs.empty()) return;
+    std::atomic<size_t> next(0);
+    auto worker = [&]() {
+      for (;;) {
+        const size_t k = next.fetch_add(1);
+        if (k >= jobs.size()) return;
+        Job &j = jobs[k];
+        j.deepest = j.depth;
+        j.ref = Build(&j.nodes, j.b, j.e, j.depth, &j.box, &j.deepest, 0, -1, 0);
+      }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n_threads; t++) pool.emplace_back(worker);
+    worker();
+    for (std::thread &t : pool) t.join();
+    for (Job &j : jobs) {
+      const int32_t base = (int32_t)out->size();
+      for (Bvh2Node nd : j.nodes) {
+        if (nd.left >= 0) nd.left += base;
+        if (nd.right >= 0) nd.right += base;
+        out->push_back(nd);
+      }
+      SetChild(&(*out)[(size_t)j.parent], j.side, j.ref >= 0 ? j.ref + base : j.ref, j.box);
+      if (j.deepest > max_depth) max_depth = j.deepest;
+    }
+    jobs.clear();
   }
 };
 
@@ -315,9 +383,21 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
     }
     nodes[0].list[(size_t)i] = (int32_t)i;
   }
+  out->max_tri_extent = 0.0;
+  for (const Box3 &b : tri_box) {
+    for (int a = 0; a < 3; a++) out->max_tri_extent = std::max(out->max_tri_extent, b.hi[a] - b.lo[a]);
+  }
   out->depth = 0;
+  const bool timing = getenv("MTB_TIMING") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    const auto t1 = std::chrono::steady_clock::now();
+    if (timing) fprintf(stderr, "[mtb] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  };
   const int rc = SplitAll(tri_box, &nodes, &out->depth, err);
   if (rc != MTB_OK) return rc;
+  lap("octree (AttemptSplit)");
 
   // ---- flatten ----
   out->nodes.assign(nodes.size(), NodeRec{});
@@ -403,12 +483,13 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
     subtree[i] = total;
   }
 
+  lap("flatten + list BVHs");
   // ---- scene BVH of the certified fast traversal ----
   out->gnodes.clear();
   out->gslots.clear();
   out->gbvh_depth = 0;
   if (use_scene_bvh && n > 0) {
-    SceneBvhBuilder sb{tri_box, &out->gnodes, {}, 0};
+    SceneBvhBuilder sb{tri_box, {}, 0, {}};
     sb.ids.resize((size_t)n);
     std::iota(sb.ids.begin(), sb.ids.end(), 0);
     Box3 whole;
@@ -426,7 +507,7 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
       root.right = ~0;                    // count 0
       out->gnodes.push_back(root);
     } else {
-      sb.Build(0, (int32_t)n, 0, &whole);
+      sb.Run(&out->gnodes, (int32_t)n);
     }
     out->gbvh_depth = sb.max_depth;
     if (sb.max_depth > kSceneBvhMaxDepth) {
@@ -436,6 +517,7 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
       for (int64_t i = 0; i < n; i++) out->gslots[(size_t)i] = out->slots[(size_t)slot_of[(size_t)sb.ids[(size_t)i]]];
     }
   }
+  lap("scene BVH");
   return MTB_OK;
 }
 

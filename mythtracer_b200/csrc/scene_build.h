@@ -83,6 +83,7 @@ struct FlatScene {
   int64_t root_list = 0, biggest_list = 0, interior = 0;
   double aabb[6] = {0, 0, 0, 0, 0, 0};
   double max_abs_coord = 0.0;  // largest |coordinate| of the scene box (bounds the FP32 cull error)
+  double max_tri_extent = 0.0; // largest extent of a triangle box along an axis
 };
 
 #ifndef MTB_BVH_LEAF

@@ -72,8 +72,10 @@ def measured_fp64_peak():
 
 
 def alg_bytes(stats) -> float:
-    """operands the reference arithmetic consumes; list-BVH box tests are 48-byte boxes too."""
-    return (48.0 * (stats["n_slab"] + stats["n_triaabb"] + stats.get("n_bvh", 0)) + 72.0 * stats["n_mt"] +
+    """operands the arithmetic consumes: 48-byte FP64 boxes for octree slab tests and exact triangle
+    pre-tests, 24-byte FP32 boxes for the conservative BVH culls (scene BVH / list BVH), 72 bytes of vertices per
+    Moller-Trumbore evaluation, 384 bytes per shaded hit."""
+    return (48.0 * (stats["n_slab"] + stats["n_triaabb"]) + 24.0 * stats.get("n_bvh", 0) + 72.0 * stats["n_mt"] +
             384.0 * stats["n_shade"])
 
 
@@ -424,11 +426,12 @@ def _run_ours(args):
                 "traffic": traffic, "kernel": "RenderMega" if pipeline_used == "mega" else "wavefront pipeline (WfTraceMain + WfShadow dominate)",
                 "kernel_ms": kernel_ms_mean,
                 "algorithmic_bytes_per_launch": my_alg, "peak_source": peak_src,
-                "note": "algorithmic bytes are served by L1/L2 (broadcast reads of shared nodes); frac > DRAM share is cache reuse",
+                "note": "algorithmic bytes are mostly served by L1/L2 (the BVH top and neighbouring rays' nodes are shared); traffic = ncu dram bytes of the same launch",
                 "fp": {"bound": "fp64 add/mul issue", "achieved": my_flops / (kernel_ms_mean * 1e-3) / 1e12, "peak": fp_peak,
                        "unit": "Tflop/s", "frac": (my_flops / (kernel_ms_mean * 1e-3) / 1e12 / fp_peak) if fp_peak else None,
                        "peak_source": fp_src, "algorithmic_flops_per_launch": my_flops},
-                "per_ray": {k: work_all[k] / max(work_all["rays"], 1.0) for k in ("n_slab", "n_visit", "n_triaabb", "n_bvh", "n_mt", "n_hit", "n_shade")}}
+                "per_ray": {k: work_all[k] / max(work_all["rays"], 1.0) for k in ("n_slab", "n_visit", "n_triaabb", "n_bvh", "n_mt", "n_hit", "n_shade")},
+                "traversal": {"fast": work.get("n_fast", 0), "exact_fallback": work.get("n_fallback", 0), "literal": work.get("n_literal", 0)}}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -125,6 +125,7 @@ typedef struct {
 #define MTB_FLAG_MEGAKERNEL 16u  /* force the per-pixel megakernel */
 #define MTB_FLAG_RAY_SORT 8u     /* wavefront: counting-sort every queue by origin cell + direction octant (measured: no gain) */
 #define MTB_FLAG_EXACT_OCTREE 128u /* every regular ray walks the octree in the reference's recursion order (no certified fast traversal) */
+#define MTB_FLAG_NO_PACKING 256u /* megakernel: one 8x8 tile per 64-thread block, every thread traces its own rays (A/B of the block-level ray packing) */
 #define MTB_FLAG_PERSISTENT 64u /* megakernel: persistent warps whose lanes draw their next pixel from a counter instead of one 8x8 tile per block (A/B; measured slower: the refilled lanes trace incoherent rays) */
 #define MTB_FLAG_NO_TILE_ORDER 32u /* megakernel: always launch tiles in scanline order (A/B of the cost-aware launch order) */
 

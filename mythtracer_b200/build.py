@@ -25,12 +25,14 @@ def _newest_source_mtime() -> float:
     return max(os.path.getmtime(p) for p in paths)
 
 
-def build(force: bool = False, verbose: bool = False, extra=()) -> str:
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
-        return LIB
+def build(force: bool = False, verbose: bool = False, extra=(), variant: str = "") -> str:
+    """variant: development A/B builds (extra -D flags) go to build/var_<variant>/lib.so; load with MTB_LIB_PATH."""
+    lib_path = LIB if not variant else os.path.join(HERE, "build", "var_" + variant, "lib.so")
+    if not force and os.path.exists(lib_path) and os.path.getmtime(lib_path) >= _newest_source_mtime():
+        return lib_path
     nvcc = os.environ.get("NVCC", "nvcc")
     objs = []
-    build_dir = os.path.join(HERE, "build")
+    build_dir = os.path.join(HERE, "build") if not variant else os.path.join(HERE, "build", "var_" + variant)
     os.makedirs(build_dir, exist_ok=True)
     for src in SOURCES:
         obj = os.path.join(build_dir, src + ".o")
@@ -40,12 +42,16 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> str:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", lib_path] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True, extra=["-Xptxas", "-v"] if "--ptxas" in sys.argv else ()))
+    if "--variant" in sys.argv:  # python build.py --variant NAME -DFOO=1 -DBAR=2
+        i = sys.argv.index("--variant")
+        print(build(force=True, extra=[a for a in sys.argv[i + 2:]], variant=sys.argv[i + 1]))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True, extra=["-Xptxas", "-v"] if "--ptxas" in sys.argv else ()))

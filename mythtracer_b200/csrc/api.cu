@@ -595,31 +595,35 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
       const int wrc = RunWavefront(ctx, &d, p, blocks, debug_build, s);
       if (wrc != MTB_OK) return wrc;
     } else {
-      if (blocks > 0 && (ctx->flags & MTB_FLAG_NO_TILE_ORDER) == 0) {
+      // launch form: block-level ray packing (16x8 tiles) unless one of the A/B forms is asked for
+      const int mode = (ctx->flags & MTB_FLAG_PERSISTENT) != 0 ? 1 : ((ctx->flags & MTB_FLAG_NO_PACKING) != 0 ? 0 : 2);
+      p.tiles_x = (chunk_w + mtb::MegaTileWidth(mode) - 1) / mtb::MegaTileWidth(mode);
+      const int mblocks = OwnedStrips(plan, owner) * p.tiles_x;
+      if (mblocks > 0 && (ctx->flags & MTB_FLAG_NO_TILE_ORDER) == 0) {
         // launch order from the previous frame of the same geometry; the first frame runs in scanline order
         const long long signature = ((long long)chunk_w << 40) ^ ((long long)chunk_h << 20) ^ ((long long)owner << 8) ^ plan.owners ^
-                                    ((long long)blocks << 4);
-        MTB_CUDA(ctx, d.tile_cost.Reserve((size_t)blocks));
-        MTB_CUDA(ctx, d.tile_order.Reserve((size_t)blocks));
+                                    ((long long)mblocks << 4) ^ ((long long)mode << 60);
+        MTB_CUDA(ctx, d.tile_cost.Reserve((size_t)mblocks));
+        MTB_CUDA(ctx, d.tile_order.Reserve((size_t)mblocks));
         p.tile_cost = d.tile_cost.ptr;
         if (signature == d.tile_signature) {
-          mtb::LaunchBuildTileOrder(d.tile_cost.ptr, d.tile_order.ptr, blocks, s);
+          mtb::LaunchBuildTileOrder(d.tile_cost.ptr, d.tile_order.ptr, mblocks, s);
           ctx->launches++;
           p.tile_order = d.tile_order.ptr;
         } else {
-          MTB_CUDA(ctx, cudaMemsetAsync(d.tile_cost.ptr, 0, (size_t)blocks * sizeof(uint32_t), s));
+          MTB_CUDA(ctx, cudaMemsetAsync(d.tile_cost.ptr, 0, (size_t)mblocks * sizeof(uint32_t), s));
           d.tile_signature = signature;
         }
       }
       int persistent_blocks = 0;
-      if (blocks > 0 && (ctx->flags & MTB_FLAG_PERSISTENT) != 0) {
+      if (mblocks > 0 && mode == 1) {
         MTB_CUDA(ctx, d.work_counter.Reserve(1));
         MTB_CUDA(ctx, cudaMemsetAsync(d.work_counter.ptr, 0, sizeof(uint32_t), s));
         p.work_counter = d.work_counter.ptr;
         persistent_blocks = mtb::MegaResidentBlocks(d.device);
       }
-      mtb::LaunchRenderMega(d.scene, p, blocks, persistent_blocks, debug_build, s);
-      if (blocks > 0) ctx->launches++;
+      mtb::LaunchRenderMega(d.scene, p, mblocks, mode, persistent_blocks, debug_build, s);
+      if (mblocks > 0) ctx->launches++;
       MTB_CUDA(ctx, cudaGetLastError());
     }
     MTB_CUDA(ctx, cudaEventRecord(d.ev_stop, s));

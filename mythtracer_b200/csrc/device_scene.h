@@ -121,9 +121,12 @@ void LaunchWfResolve(const RenderParams &rp, const WfBuffers &wf, int n_slots, c
 // megakernel.cu
 // Builds tile_order (descending cost, bucketed) from tile_cost and clears tile_cost for the coming frame.
 void LaunchBuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles, cudaStream_t stream);
-// persistent_blocks > 0 selects the persistent (lane-refill) form with that grid; rp.work_counter must be zeroed
-void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp, int n_blocks, int persistent_blocks,
+// mode 0: one 8x8 tile per 64-thread block; 1: persistent lane refill (grid persistent_blocks, rp.work_counter
+// zeroed); 2: one 16x8 tile per 128-thread block with block-level ray packing.  rp.tiles_x must be in units of
+// MegaTileWidth(mode).
+void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp, int n_blocks, int mode, int persistent_blocks,
                       bool debug_build, cudaStream_t stream);
+int MegaTileWidth(int mode);
 int MegaResidentBlocks(int device);  // SMs x resident RenderMega blocks per SM
 void LaunchIntersect(const DeviceScene &sc, const IntersectParams &ip, bool debug_build, cudaStream_t stream);
 

@@ -34,8 +34,28 @@ struct ShadeFrame {
 // primary ray in the same Trace call as their neighbours' shadow / secondary rays.  Work items are numbered
 // tile by tile in launch order (item >> 6 = position in tile_order, item & 63 = pixel of the 8x8 tile), so a
 // warp's 32 consecutive items start as an 8x4 patch.
-template <bool DBG, bool PERSIST>
-__global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega(DeviceScene sc, RenderParams rp) {
+//
+// PACK (kPackThreads = 128 threads = a 16x8 pixel tile): the rays of one loop iteration are traced by the FIRST
+// `total` threads of the block instead of by their owners.  Every thread that needs a ray traced writes it to
+// shared memory at its rank among the needy threads (warp ballot + per-warp counts), the block synchronises,
+// thread i traces ray i, the block synchronises again and the owners pick up (slot, t).  A tile whose pixels are
+// mostly finished, or mostly cheap, then keeps one or two warps busy at close to 32 lanes instead of four warps at
+// a few lanes each (ncu on the tile-per-block form: 14 of 32 lanes per instruction).  Results cannot change: the
+// same rays are traced by the same code, only by different threads.
+constexpr int kPackThreads = 128;
+constexpr int kPackTileW = 16;
+constexpr int kModeTile = 0, kModePersist = 1, kModePack = 2;
+
+template <bool DBG, int MODE>
+__global__ void __launch_bounds__(MODE == kModePack ? kPackThreads : kBlockThreads,
+                                  MODE == kModePack ? MTB_MEGA_MIN_BLOCKS * kBlockThreads / kPackThreads : MTB_MEGA_MIN_BLOCKS)
+    RenderMega(DeviceScene sc, RenderParams rp) {
+  constexpr bool PERSIST = MODE == kModePersist;
+  constexpr bool PACK = MODE == kModePack;
+  __shared__ double s_ray[PACK ? 7 * kPackThreads : 1];   // o.xyz, d.xyz, t_limit of the rays of this iteration
+  __shared__ double s_res_t[PACK ? kPackThreads : 1];
+  __shared__ int s_res_slot[PACK ? kPackThreads : 1];
+  __shared__ int s_warp_count[PACK ? kPackThreads / 32 : 1];
 #ifdef MTB_SMEM_TOP
   __shared__ NodeRec top_store[kTopNodes];
   const NodeRec *top = top_store;
@@ -83,7 +103,19 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
       if (!active) {
         // ---- next pixel of this lane ----
         unsigned item;
-        if (PERSIST) {
+        bool fresh = !PACK;  // a new pixel was taken: set up its primary ray
+        if (PACK) {
+          if (!drawn) {
+            drawn = true;
+            const int pos = (int)blockIdx.x;
+            tile_id = rp.tile_order != nullptr ? rp.tile_order[pos] : pos;
+            const int strip = rp.strip_first + (tile_id / rp.tiles_x) * rp.strip_stride;
+            px = (tile_id % rp.tiles_x) * kPackTileW + (int)(threadIdx.x & 15u);
+            py = strip * kTile + (int)(threadIdx.x >> 4);
+            active = fresh = px < rp.chunk_w && py < rp.chunk_h;
+          }
+          item = 0;
+        } else if (PERSIST) {
           const unsigned peers = __activemask();
           const unsigned lane = threadIdx.x & 31u;
           const int leader = __ffs((int)peers) - 1;
@@ -96,14 +128,17 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
           drawn = true;
           item = blockIdx.x * (unsigned)kBlockThreads + threadIdx.x;
         }
-        if (item >= rp.n_items) break;
-        const int pos = (int)(item >> 6);
-        tile_id = rp.tile_order != nullptr ? rp.tile_order[pos] : pos;
-        const int strip = rp.strip_first + (tile_id / rp.tiles_x) * rp.strip_stride;
-        px = (tile_id % rp.tiles_x) * kTile + (int)(item & 7u);
-        py = strip * kTile + (int)((item >> 3) & 7u);
-        if (!(px < rp.chunk_w && py < rp.chunk_h)) continue;
-        active = true;
+        if (!PACK) {
+          if (item >= rp.n_items) break;
+          const int pos = (int)(item >> 6);
+          tile_id = rp.tile_order != nullptr ? rp.tile_order[pos] : pos;
+          const int strip = rp.strip_first + (tile_id / rp.tiles_x) * rp.strip_stride;
+          px = (tile_id % rp.tiles_x) * kTile + (int)(item & 7u);
+          py = strip * kTile + (int)((item >> 3) & 7u);
+          if (!(px < rp.chunk_w && py < rp.chunk_h)) continue;
+          active = true;
+        }
+        if (fresh) {  // (PACK: a thread comes by here every iteration once its pixel is finished or was never live)
         // Sensor::GetRay (camera.cc:65-69) with full-image pixel coordinates (mythtracer.cc:298)
         m_o = Load3(rp.origin);
         m_d = Normalized(Add(Add(start, MulS(d_scan, (double)(rp.chunk_y + py))), MulS(d_pixel, (double)(rp.chunk_x + px))));
@@ -117,6 +152,7 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
         sig_shadow = 0;
         n_rays = 0;
         Count<DBG>(cnt, kPrimary);
+        }
       }
       D3 to, td;
       double light_distance = 0.0;
@@ -130,7 +166,46 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
         td = m_d;
       }
       double t = 0.0;
-      const int slot = Trace<DBG>(sc, to, td, shadow_mode ? light_distance : CUDART_INF, &t, cnt MTB_TOP_ARGS);
+      int slot;
+      if (PACK) {
+        // ---- hand the ray to the block: thread i traces the i-th ray of this iteration ----
+        const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+        const unsigned needy = __ballot_sync(0xffffffffu, active);
+        if (lane == 0u) s_warp_count[warp] = __popc(needy);
+        __syncthreads();
+        int mine = __popc(needy & ((1u << lane) - 1u)), total = 0;
+#pragma unroll
+        for (int w = 0; w < kPackThreads / 32; w++) {
+          const int c = s_warp_count[w];
+          mine += (unsigned)w < warp ? c : 0;
+          total += c;
+        }
+        if (total == 0) break;  // every pixel of the tile is finished (uniform across the block)
+        if (active) {
+          s_ray[0 * kPackThreads + mine] = to.x;
+          s_ray[1 * kPackThreads + mine] = to.y;
+          s_ray[2 * kPackThreads + mine] = to.z;
+          s_ray[3 * kPackThreads + mine] = td.x;
+          s_ray[4 * kPackThreads + mine] = td.y;
+          s_ray[5 * kPackThreads + mine] = td.z;
+          s_ray[6 * kPackThreads + mine] = shadow_mode ? light_distance : CUDART_INF;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < total) {
+          const int i = (int)threadIdx.x;
+          const D3 ro = Mk(s_ray[0 * kPackThreads + i], s_ray[1 * kPackThreads + i], s_ray[2 * kPackThreads + i]);
+          const D3 rd = Mk(s_ray[3 * kPackThreads + i], s_ray[4 * kPackThreads + i], s_ray[5 * kPackThreads + i]);
+          double rt = 0.0;
+          s_res_slot[i] = Trace<DBG>(sc, ro, rd, s_ray[6 * kPackThreads + i], &rt, cnt MTB_TOP_ARGS);
+          s_res_t[i] = rt;
+        }
+        __syncthreads();
+        if (!active) continue;
+        slot = s_res_slot[mine];
+        t = s_res_t[mine];
+      } else {
+        slot = Trace<DBG>(sc, to, td, shadow_mode ? light_distance : CUDART_INF, &t, cnt MTB_TOP_ARGS);
+      }
       n_rays++;
 
       bool have_ret = false;
@@ -344,6 +419,7 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
       // what this tile cost, for the next frame's launch order
       if (PERSIST && rp.tile_cost != nullptr) atomicAdd(rp.tile_cost + tile_id, n_rays);
       active = false;
+      if (PACK) shadow_mode = false;
     }
   }
 
@@ -445,31 +521,39 @@ int MegaResidentBlocks(int device) {
   static int cached[64] = {0};
   if (device >= 0 && device < 64 && cached[device] > 0) return cached[device];
   int per_sm = 0, sms = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, RenderMega<false, true>, kBlockThreads, 0) != cudaSuccess) per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, RenderMega<false, kModePersist>, kBlockThreads, 0) != cudaSuccess) per_sm = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) sms = 0;
   const int n = per_sm > 0 && sms > 0 ? per_sm * sms : 148 * MTB_MEGA_MIN_BLOCKS;
   if (device >= 0 && device < 64) cached[device] = n;
   return n;
 }
 
-// n_blocks = number of 8x8 tiles.  persistent_blocks > 0: persistent form with that many blocks (never more than
-// there are tiles); rp.work_counter must then point at a zeroed counter.
-void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp_in, int n_blocks, int persistent_blocks,
+int MegaTileWidth(int mode) { return mode == kModePack ? kPackTileW : kTile; }
+
+// n_blocks = number of tiles (8x8 pixels; 16x8 in pack mode).  mode 1 (persistent): `persistent_blocks` blocks
+// (never more than there are tiles) and rp.work_counter must point at a zeroed counter.
+void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp_in, int n_blocks, int mode, int persistent_blocks,
                       bool debug_build, cudaStream_t stream) {
   if (n_blocks <= 0) return;
   RenderParams rp = rp_in;
   rp.n_items = (uint32_t)n_blocks * (uint32_t)kBlockThreads;
-  if (persistent_blocks > 0) {
+  if (mode == kModePack) {
+    if (debug_build) {
+      RenderMega<true, kModePack><<<n_blocks, kPackThreads, 0, stream>>>(sc, rp);
+    } else {
+      RenderMega<false, kModePack><<<n_blocks, kPackThreads, 0, stream>>>(sc, rp);
+    }
+  } else if (mode == kModePersist) {
     const int grid = persistent_blocks < n_blocks ? persistent_blocks : n_blocks;
     if (debug_build) {
-      RenderMega<true, true><<<grid, kBlockThreads, 0, stream>>>(sc, rp);
+      RenderMega<true, kModePersist><<<grid, kBlockThreads, 0, stream>>>(sc, rp);
     } else {
-      RenderMega<false, true><<<grid, kBlockThreads, 0, stream>>>(sc, rp);
+      RenderMega<false, kModePersist><<<grid, kBlockThreads, 0, stream>>>(sc, rp);
     }
   } else if (debug_build) {
-    RenderMega<true, false><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);
+    RenderMega<true, kModeTile><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);
   } else {
-    RenderMega<false, false><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);
+    RenderMega<false, kModeTile><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);
   }
 }
 

@@ -125,7 +125,7 @@ typedef struct {
 #define MTB_FLAG_MEGAKERNEL 16u  /* force the per-pixel megakernel */
 #define MTB_FLAG_RAY_SORT 8u     /* wavefront: counting-sort every queue by origin cell + direction octant (measured: no gain) */
 #define MTB_FLAG_EXACT_OCTREE 128u /* every regular ray walks the octree in the reference's recursion order (no certified fast traversal) */
-#define MTB_FLAG_NO_PACKING 256u /* megakernel: one 8x8 tile per 64-thread block, every thread traces its own rays (A/B of the block-level ray packing) */
+#define MTB_FLAG_PACKING 256u /* megakernel: 16x8 tiles per 128-thread block, the rays of an iteration are handed to the first threads of the block (A/B; measured slower: fewer tracing warps hide less latency) */
 #define MTB_FLAG_PERSISTENT 64u /* megakernel: persistent warps whose lanes draw their next pixel from a counter instead of one 8x8 tile per block (A/B; measured slower: the refilled lanes trace incoherent rays) */
 #define MTB_FLAG_NO_TILE_ORDER 32u /* megakernel: always launch tiles in scanline order (A/B of the cost-aware launch order) */
 
@@ -167,10 +167,11 @@ int mtb_load_mtl(mtb_context *ctx, const char *path);
  * (6 doubles: lo.xyz, hi.xyz) and that node's depth.  Either pointer may be NULL. */
 int mtb_scene_triangle_nodes(const mtb_context *ctx, double *node_box, int32_t *node_depth);
 /* The scene BVH of the certified fast traversal, for inspection: node count, depth, the
- * nodes themselves (64 bytes each: float lbox[6], rbox[6]; int32 left, right, pad[2]; a child >= 0 is a node
- * index, < 0 a leaf with ~child = (first << 3) | count over leaf_order) and, per leaf position, the insertion
- * index of the triangle stored there (n_triangles entries).  Any pointer may be NULL.  n_nodes == 0: the scene
- * has no fast traversal (empty scene, MTB_FLAG_NO_LIST_BVH, or a tree deeper than the traversal stack). */
+ * nodes themselves (128 bytes each: float box[4][6] = lo.xyz hi.xyz of up to four children; int32 child[4],
+ * pad[4]; a child >= 0 is a node index, < 0 a leaf with ~child = (first << 3) | count over leaf_order, unused
+ * children are empty leaves with an inverted box) and, per leaf position, the insertion index of the triangle
+ * stored there (n_triangles entries).  Any pointer may be NULL.  n_nodes == 0: the scene has no fast traversal
+ * (empty scene, MTB_FLAG_NO_LIST_BVH, or a tree deeper than the traversal stack). */
 int mtb_scene_bvh(const mtb_context *ctx, int64_t *n_nodes, int32_t *depth, void *nodes, int32_t *leaf_order);
 int mtb_set_flags(mtb_context *ctx, uint32_t flags);
 /* Tile partitioning across processes -- the in-process form of the reference's master/worker contract

@@ -63,7 +63,7 @@ struct DeviceState {
   DeviceBuffer<mtb::SlotRec> slots;
   DeviceBuffer<mtb::ShadeRec> shade;
   DeviceBuffer<mtb::BvhRec> bvh;
-  DeviceBuffer<mtb::Bvh2Node> gnodes;   // scene BVH of the certified fast traversal
+  DeviceBuffer<mtb::Bvh4Node> gnodes;   // scene BVH of the certified fast traversal
   DeviceBuffer<mtb::SlotRec> gslots;
   DeviceBuffer<int32_t> list_order;
   DeviceBuffer<mtb_material> materials;
@@ -168,7 +168,7 @@ void DestroyTextures(DeviceState *d) {
 
 // Regular rays take the certified fast traversal over the scene BVH unless the exact octree recursion is forced.
 void SelectTraversal(mtb_context *ctx, DeviceState *d) {
-  const bool fast = (ctx->flags & (MTB_FLAG_EXACT_OCTREE | MTB_FLAG_NO_LIST_BVH)) == 0 && !ctx->flat.gnodes.empty() &&
+  const bool fast = (ctx->flags & (MTB_FLAG_EXACT_OCTREE | MTB_FLAG_NO_LIST_BVH)) == 0 && !ctx->flat.gnodes4.empty() &&
                     d->scene.cull_radius > 0.0f;
   d->scene.gnodes = fast ? d->gnodes.ptr : nullptr;
   d->scene.gslots = fast ? d->gslots.ptr : nullptr;
@@ -182,7 +182,7 @@ int UploadToDevice(mtb_context *ctx, DeviceState *d) {
   MTB_CUDA(ctx, d->shade.Upload(f.shade.data(), f.shade.size(), d->stream));
   MTB_CUDA(ctx, d->bvh.Upload(f.bvh.data(), f.bvh.size(), d->stream));
   MTB_CUDA(ctx, d->list_order.Upload(f.list_order.data(), f.list_order.size(), d->stream));
-  MTB_CUDA(ctx, d->gnodes.Upload(f.gnodes.data(), f.gnodes.size(), d->stream));
+  MTB_CUDA(ctx, d->gnodes.Upload(f.gnodes4.data(), f.gnodes4.size(), d->stream));
   MTB_CUDA(ctx, d->gslots.Upload(f.gslots.data(), f.gslots.size(), d->stream));
   MTB_CUDA(ctx, d->materials.Upload(ctx->materials.data(), ctx->materials.size(), d->stream));
   DestroyTextures(d);
@@ -281,7 +281,7 @@ int BuildAndUpload(mtb_context *ctx) {
   }
   ctx->device_bytes = (int64_t)(ctx->flat.nodes.size() * sizeof(mtb::NodeRec) + ctx->flat.slots.size() * sizeof(mtb::SlotRec) +
                                 ctx->flat.shade.size() * sizeof(mtb::ShadeRec) + ctx->flat.bvh.size() * sizeof(mtb::BvhRec) +
-                                ctx->flat.gnodes.size() * sizeof(mtb::Bvh2Node) + ctx->flat.gslots.size() * sizeof(mtb::SlotRec) +
+                                ctx->flat.gnodes4.size() * sizeof(mtb::Bvh4Node) + ctx->flat.gslots.size() * sizeof(mtb::SlotRec) +
                                 ctx->flat.list_order.size() * 4 + ctx->materials.size() * sizeof(mtb_material));
   for (const mtb::LoadedTexture &t : ctx->textures) ctx->device_bytes += (int64_t)t.rgba.size();
   for (DeviceState &d : ctx->dev) {
@@ -595,8 +595,8 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
       const int wrc = RunWavefront(ctx, &d, p, blocks, debug_build, s);
       if (wrc != MTB_OK) return wrc;
     } else {
-      // launch form: block-level ray packing (16x8 tiles) unless one of the A/B forms is asked for
-      const int mode = (ctx->flags & MTB_FLAG_PERSISTENT) != 0 ? 1 : ((ctx->flags & MTB_FLAG_NO_PACKING) != 0 ? 0 : 2);
+      // launch form: one 8x8 tile per block unless one of the A/B forms is asked for
+      const int mode = (ctx->flags & MTB_FLAG_PERSISTENT) != 0 ? 1 : ((ctx->flags & MTB_FLAG_PACKING) != 0 ? 2 : 0);
       p.tiles_x = (chunk_w + mtb::MegaTileWidth(mode) - 1) / mtb::MegaTileWidth(mode);
       const int mblocks = OwnedStrips(plan, owner) * p.tiles_x;
       if (mblocks > 0 && (ctx->flags & MTB_FLAG_NO_TILE_ORDER) == 0) {
@@ -922,9 +922,9 @@ int mtb_scene_triangle_nodes(const mtb_context *ctx, double *node_box, int32_t *
 int mtb_scene_bvh(const mtb_context *ctx, int64_t *n_nodes, int32_t *depth, void *nodes, int32_t *leaf_order) {
   if (ctx == nullptr) return MTB_ERR_ARG;
   const mtb::FlatScene &f = ctx->flat;
-  if (n_nodes != nullptr) *n_nodes = (int64_t)f.gnodes.size();
-  if (depth != nullptr) *depth = f.gbvh_depth;
-  if (nodes != nullptr && !f.gnodes.empty()) memcpy(nodes, f.gnodes.data(), f.gnodes.size() * sizeof(mtb::Bvh2Node));
+  if (n_nodes != nullptr) *n_nodes = (int64_t)f.gnodes4.size();
+  if (depth != nullptr) *depth = f.gbvh4_depth;
+  if (nodes != nullptr && !f.gnodes4.empty()) memcpy(nodes, f.gnodes4.data(), f.gnodes4.size() * sizeof(mtb::Bvh4Node));
   if (leaf_order != nullptr) {
     for (size_t i = 0; i < f.gslots.size(); i++) leaf_order[i] = f.gslots[i].tri;
   }

@@ -13,6 +13,7 @@
 #include "scene_build.h"
 
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstring>
 #include <atomic>
@@ -265,6 +266,9 @@ struct SceneBvhBuilder {
   const std::vector<Box3> &tri_box;
   std::vector<int32_t> ids;
   int32_t max_depth = 0;
+  // every stored box is grown by `pad` on all sides: the absolute part of the FP32 slab test's error bound,
+  // 2^-20 R |i| in t, is a constant 2^-20 R in space (FastBox, device_core.cuh); pad = 2^-17 R
+  double pad = 0.0;
 
   struct Job {
     int32_t b, e, depth;
@@ -276,11 +280,11 @@ struct SceneBvhBuilder {
   };
   std::vector<Job> jobs;
 
-  static void SetChild(Bvh2Node *n, int side, int32_t ref, const Box3 &box) {
+  void SetChild(Bvh2Node *n, int side, int32_t ref, const Box3 &box) const {
     float *dst = side == 0 ? n->lbox : n->rbox;
     for (int a = 0; a < 3; a++) {
-      dst[a] = RoundDown(box.lo[a]);
-      dst[3 + a] = RoundUp(box.hi[a]);
+      dst[a] = RoundDown(box.lo[a] - pad);
+      dst[3 + a] = RoundUp(box.hi[a] + pad);
     }
     (side == 0 ? n->left : n->right) = ref;
   }
@@ -489,7 +493,7 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
   out->gslots.clear();
   out->gbvh_depth = 0;
   if (use_scene_bvh && n > 0) {
-    SceneBvhBuilder sb{tri_box, {}, 0, {}};
+    SceneBvhBuilder sb{tri_box, {}, 0, 0x1p-17 * out->max_abs_coord * 1.000001, {}};
     sb.ids.resize((size_t)n);
     std::iota(sb.ids.begin(), sb.ids.end(), 0);
     Box3 whole;
@@ -500,8 +504,8 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
       Bvh2Node root;
       memset(&root, 0, sizeof(root));
       for (int a = 0; a < 3; a++) {
-        root.lbox[a] = root.rbox[a] = RoundDown(whole.lo[a]);
-        root.lbox[3 + a] = root.rbox[3 + a] = RoundUp(whole.hi[a]);
+        root.lbox[a] = root.rbox[a] = RoundDown(whole.lo[a] - sb.pad);
+        root.lbox[3 + a] = root.rbox[3 + a] = RoundUp(whole.hi[a] + sb.pad);
       }
       root.left = ~(int32_t)(uint32_t)n;  // first_gslot 0, count n
       root.right = ~0;                    // count 0
@@ -518,6 +522,82 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
     }
   }
   lap("scene BVH");
+  // ---- collapse to four children per node ----
+  out->gnodes4.clear();
+  out->gbvh4_depth = 0;
+  if (!out->gnodes.empty()) {
+    struct Item {
+      int32_t ref;
+      float box[6];
+    };
+    auto area = [](const float *b) {
+      const double dx = (double)b[3] - b[0], dy = (double)b[4] - b[1], dz = (double)b[5] - b[2];
+      return dx * dy + dy * dz + dz * dx;
+    };
+    // explicit work list: (binary node, index of the 4-wide node to fill, depth)
+    struct Work {
+      int32_t n2, n4, depth;
+    };
+    std::vector<Work> todo;
+    out->gnodes4.emplace_back();
+    todo.push_back({0, 0, 0});
+    while (!todo.empty()) {
+      const Work w = todo.back();
+      todo.pop_back();
+      if (w.depth > out->gbvh4_depth) out->gbvh4_depth = w.depth;
+      Item items[4];
+      int n_items = 2;
+      const Bvh2Node &b2 = out->gnodes[(size_t)w.n2];
+      items[0].ref = b2.left;
+      memcpy(items[0].box, b2.lbox, sizeof(b2.lbox));
+      items[1].ref = b2.right;
+      memcpy(items[1].box, b2.rbox, sizeof(b2.rbox));
+      while (n_items < 4) {
+        int pick = -1;
+        double best = -1.0;
+        for (int k = 0; k < n_items; k++) {
+          if (items[k].ref >= 0 && area(items[k].box) > best) {
+            best = area(items[k].box);
+            pick = k;
+          }
+        }
+        if (pick < 0) break;
+        const Bvh2Node &c = out->gnodes[(size_t)items[pick].ref];
+        items[pick].ref = c.left;
+        memcpy(items[pick].box, c.lbox, sizeof(c.lbox));
+        items[n_items].ref = c.right;
+        memcpy(items[n_items].box, c.rbox, sizeof(c.rbox));
+        n_items++;
+      }
+      Bvh4Node n4;
+      memset(&n4, 0, sizeof(n4));
+      for (int k = 0; k < 4; k++) {
+        if (k < n_items) {
+          memcpy(n4.box[k], items[k].box, sizeof(items[k].box));
+          if (items[k].ref >= 0) {
+            n4.child[k] = (int32_t)out->gnodes4.size();
+            out->gnodes4.emplace_back();
+            todo.push_back({items[k].ref, n4.child[k], w.depth + 1});
+          } else {
+            n4.child[k] = items[k].ref;
+          }
+        } else {
+          for (int a = 0; a < 3; a++) {
+            n4.box[k][a] = FLT_MAX;
+            n4.box[k][3 + a] = -FLT_MAX;
+          }
+          n4.child[k] = ~0;  // an empty leaf
+        }
+      }
+      out->gnodes4[(size_t)w.n4] = n4;
+    }
+    if (3 * (out->gbvh4_depth + 1) + 4 > kFastStackSize) {
+      out->gnodes.clear();
+      out->gnodes4.clear();
+      out->gslots.clear();
+    }
+  }
+  lap("collapse to 4-wide");
   return MTB_OK;
 }
 

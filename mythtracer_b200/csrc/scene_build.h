@@ -36,6 +36,17 @@ struct alignas(64) Bvh2Node {
 };
 static_assert(sizeof(Bvh2Node) == 64, "Bvh2Node must be half a cache line");
 
+// The structure TraceFast actually walks: the binary scene BVH collapsed to four children per node (the child
+// with the largest box is replaced by its own two children until there are four).  The traversal is bound by the
+// chain of dependent node loads of each ray; a four-wide node halves that chain for the same boxes.  One node =
+// one 128-byte line: two pairs of child boxes laid out like Bvh2Node, then the four child references.
+struct alignas(128) Bvh4Node {
+  float box[4][6];   // child k: lo.xyz rounded down, hi.xyz rounded up; an unused child has lo = +FLT_MAX, hi = -FLT_MAX
+  int32_t child[4];  // >= 0: inner node index; < 0: leaf, ~child = (first_gslot << 3) | count; unused: ~0 (empty leaf)
+  int32_t pad_[4];
+};
+static_assert(sizeof(Bvh4Node) == 128, "Bvh4Node must be one cache line");
+
 // One octree node = one 128-byte line.  The 8 children of a node are contiguous (first_child .. +7) and
 // their boxes are exactly {lo,c} / {c,hi} per axis (octtree.cc:61-100), so a node carries the three
 // planes per axis once instead of eight child boxes.
@@ -76,7 +87,9 @@ struct FlatScene {
   std::vector<ShadeRec> shade;
   std::vector<BvhRec> bvh;
   std::vector<int32_t> list_order;  // list_order[list_first + k] = slot of the k-th entry in reference order
-  std::vector<Bvh2Node> gnodes;     // scene BVH, node 0 = root (empty: no fast traversal)
+  std::vector<Bvh2Node> gnodes;     // binary scene BVH, node 0 = root (empty: no fast traversal)
+  std::vector<Bvh4Node> gnodes4;    // the same tree collapsed to four children per node (what the device walks)
+  int32_t gbvh4_depth = 0;
   std::vector<SlotRec> gslots;      // copies of `slots` in scene-BVH leaf order
   int32_t gbvh_depth = 0;
   int32_t depth = 0;
@@ -96,7 +109,8 @@ struct FlatScene {
 #define MTB_SCENE_BVH_LEAF 2
 #endif
 constexpr int kSceneBvhLeafSize = MTB_SCENE_BVH_LEAF;  // <= 7
-constexpr int kSceneBvhMaxDepth = 88;                   // deeper trees (never seen) disable the fast traversal
+constexpr int kSceneBvhMaxDepth = 88;                   // deeper binary trees (never seen) disable the fast traversal
+constexpr int kFastStackSize = 128;                     // traversal stack of TraceFast: needs 3 * depth of the 4-wide tree
 constexpr int kBvhLeafSize = MTB_BVH_LEAF;      // <= 7 (3-bit count in BvhRec::leaf)
 constexpr int kBvhMinList = MTB_BVH_MIN_LIST;  // shorter lists are scanned linearly
 // measured on B200, C3 frame (megakernel / wavefront ms): leaf 4 min 12: 39.4 / 46.5; leaf 2 min 6: 36.5 / 42.7;

@@ -627,18 +627,21 @@ __device__ __forceinline__ void TestSlotFast(const SlotRec *rec, const Ray &rf, 
   fb->prune = fminf(fb->prune, __double2float_ru(t + 2.0 * e + t * 0x1p-20));
 }
 
-// Conservative FP32 slab test of one child box; *tn = lower bound of the entry distance.  t = fma(b, i, -(o i))
-// differs from the FP64 value of (b - o) * i by at most 2^-23 |t| + 2^-20 R |i| for |o| <= 8R (o and i rounded
-// to float, the product o i, the fma).  The absolute part is 2^-20 R in SPACE whatever the ray, so it is paid at
-// build time: every stored box is grown by 2^-17 R on all sides (SceneBvhBuilder::pad), which moves each near
-// plane down and each far plane up by 8x the bound, per axis.  The relative part widens the winners of the
-// max / min by 2^-21 |t| (4x the bound).
-__device__ __forceinline__ bool FastBox(float lox, float loy, float loz, float hix, float hiy, float hiz, const Ray &r,
-                                        float nox, float noy, float noz, float prune, float *tn_out) {
+// Conservative FP32 slab test of one child box of a quantised node; *tn_out = lower bound of the entry distance.
+// A plane is origin + q * scale (scale a power of two); its ray parameter (origin + q scale - o) * i is evaluated
+// as fma(q, ss, adj) with ss = scale * i (exact) and adj = fma(origin, i, -(o i)), both per node and axis.  Against
+// the FP64 value this is off by at most 2^-23 |t| plus 25 * 2^-24 R |i| < 2^-19 R |i| for |o| <= 8R (o and i
+// rounded to float, the product o i, the two fma).  The absolute part is a constant 2^-19 R in SPACE whatever the
+// ray, so it is paid at build time: every box is grown by 2^-17 R on all sides before it is quantised outwards
+// (SceneBvhBuilder::pad).  The relative part widens the winners of the max / min by 2^-21 |t| (4x the bound).
+__device__ __forceinline__ bool FastBoxQ(unsigned nwx, unsigned nwy, unsigned nwz, unsigned fwx, unsigned fwy, unsigned fwz,
+                                         int k, float ssx, float ssy, float ssz, float adjx, float adjy, float adjz,
+                                         float prune, float *tn_out) {
   const float kRel = 4.76837158203125e-07f;  // 2^-21
-  const float nx = __fmaf_rn(r.sx ? hix : lox, r.ix, nox), fx = __fmaf_rn(r.sx ? lox : hix, r.ix, nox);
-  const float ny = __fmaf_rn(r.sy ? hiy : loy, r.iy, noy), fy = __fmaf_rn(r.sy ? loy : hiy, r.iy, noy);
-  const float nz = __fmaf_rn(r.sz ? hiz : loz, r.iz, noz), fz = __fmaf_rn(r.sz ? loz : hiz, r.iz, noz);
+  const int sh = 8 * k;
+  const float nx = __fmaf_rn((float)((nwx >> sh) & 255u), ssx, adjx), fx = __fmaf_rn((float)((fwx >> sh) & 255u), ssx, adjx);
+  const float ny = __fmaf_rn((float)((nwy >> sh) & 255u), ssy, adjy), fy = __fmaf_rn((float)((fwy >> sh) & 255u), ssy, adjy);
+  const float nz = __fmaf_rn((float)((nwz >> sh) & 255u), ssz, adjz), fz = __fmaf_rn((float)((fwz >> sh) & 255u), ssz, adjz);
   float tn = fmaxf(fmaxf(nx, ny), nz);
   float tf = fminf(fminf(fx, fy), fz);
   tn = __fmaf_rn(-kRel, fabsf(tn), tn);
@@ -703,17 +706,27 @@ __device__ int TraceFast(const DeviceScene &sc, const Ray &rf, const double *sh,
   } while (0)
   for (;;) {
     while (node >= 0) {
-      // one 4-wide node = one 128-byte line: boxes of children 0,1 | boxes of children 2,3 | child references
-      const float4 *q = reinterpret_cast<const float4 *>(sc.gnodes + node);
-      const float4 a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2);
-      const float4 b0 = __ldg(q + 3), b1 = __ldg(q + 4), b2 = __ldg(q + 5);
-      const int4 kids = __ldg(reinterpret_cast<const int4 *>(q + 6));
+      // one quantised 4-wide node = 64 bytes: origin.xyz + exponents | near / far plane bytes | child references
+      const uint4 *q = reinterpret_cast<const uint4 *>(sc.gnodes + node);
+      const uint4 w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+      const uint4 kw = __ldg(q + 3);
+      const int4 kids = make_int4((int)kw.x, (int)kw.y, (int)kw.z, (int)kw.w);
       Count<DBG>(cnt, kBvh, 4);
+      const float ssx = __uint_as_float((w0.w & 255u) << 23) * rf.ix;
+      const float ssy = __uint_as_float(((w0.w >> 8) & 255u) << 23) * rf.iy;
+      const float ssz = __uint_as_float(((w0.w >> 16) & 255u) << 23) * rf.iz;
+      const float adjx = __fmaf_rn(__uint_as_float(w0.x), rf.ix, nox);
+      const float adjy = __fmaf_rn(__uint_as_float(w0.y), rf.iy, noy);
+      const float adjz = __fmaf_rn(__uint_as_float(w0.z), rf.iz, noz);
+      // w1 = qlo.x qlo.y qlo.z qhi.x (four children per word), w2 = qhi.y qhi.z: the planes the ray meets first
+      const unsigned nwx = rf.sx ? w1.w : w1.x, fwx = rf.sx ? w1.x : w1.w;
+      const unsigned nwy = rf.sy ? w2.x : w1.y, fwy = rf.sy ? w1.y : w2.x;
+      const unsigned nwz = rf.sz ? w2.y : w1.z, fwz = rf.sz ? w1.z : w2.y;
       float k0, k1, k2, k3;
-      const bool h0 = FastBox(a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, rf, nox, noy, noz, fb.prune, &k0);
-      const bool h1 = FastBox(a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, rf, nox, noy, noz, fb.prune, &k1);
-      const bool h2 = FastBox(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, rf, nox, noy, noz, fb.prune, &k2);
-      const bool h3 = FastBox(b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, rf, nox, noy, noz, fb.prune, &k3);
+      const bool h0 = FastBoxQ(nwx, nwy, nwz, fwx, fwy, fwz, 0, ssx, ssy, ssz, adjx, adjy, adjz, fb.prune, &k0);
+      const bool h1 = FastBoxQ(nwx, nwy, nwz, fwx, fwy, fwz, 1, ssx, ssy, ssz, adjx, adjy, adjz, fb.prune, &k1);
+      const bool h2 = FastBoxQ(nwx, nwy, nwz, fwx, fwy, fwz, 2, ssx, ssy, ssz, adjx, adjy, adjz, fb.prune, &k2);
+      const bool h3 = FastBoxQ(nwx, nwy, nwz, fwx, fwy, fwz, 3, ssx, ssy, ssz, adjx, adjy, adjz, fb.prune, &k3);
       k0 = h0 ? k0 : CUDART_INF_F;
       k1 = h1 ? k1 : CUDART_INF_F;
       k2 = h2 ? k2 : CUDART_INF_F;
@@ -791,7 +804,7 @@ __device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D
     r.px = pr * fabsf(r.ix);
     r.py = pr * fabsf(r.iy);
     r.pz = pr * fabsf(r.iz);
-    if (sc.gnodes != nullptr && r.cull32) {
+    if (sc.gnodes != nullptr && r.cull32 && ai_max <= 0x1p40 && ai_min >= 0x1p-40) {  // scale * i stays a normal float
       double *sh = s_stage + threadIdx.x;
       sh[0 * BLOCK] = r.o.x;
       sh[1 * BLOCK] = r.o.y;

@@ -598,6 +598,41 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
     }
   }
   lap("collapse to 4-wide");
+  // ---- quantise the child boxes (outwards) ----
+  out->gnodesq.assign(out->gnodes4.size(), Bvh4QNode{});
+  for (size_t i = 0; i < out->gnodes4.size(); i++) {
+    const Bvh4Node &n = out->gnodes4[i];
+    Bvh4QNode &q = out->gnodesq[i];
+    memset(&q, 0, sizeof(q));
+    for (int a = 0; a < 3; a++) {
+      double lo = INFINITY, hi = -INFINITY;
+      for (int k = 0; k < 4; k++) {
+        if (n.box[k][a] > n.box[k][3 + a]) continue;  // unused child
+        lo = std::min(lo, (double)n.box[k][a]);
+        hi = std::max(hi, (double)n.box[k][3 + a]);
+      }
+      if (!(lo <= hi)) lo = hi = 0.0;
+      q.origin[a] = (float)lo;  // exact: it is one of the float planes
+      int e = -60;
+      while (e < 100 && 255.0 * std::ldexp(1.0, e) < hi - lo) e++;
+      q.exp[a] = (uint8_t)(e + 127);
+      const double scale = std::ldexp(1.0, e);
+      for (int k = 0; k < 4; k++) {
+        if (n.box[k][a] > n.box[k][3 + a]) {
+          q.qlo[a][k] = 255;
+          q.qhi[a][k] = 0;
+          continue;
+        }
+        double ql = std::floor(((double)n.box[k][a] - lo) / scale), qh = std::ceil(((double)n.box[k][3 + a] - lo) / scale);
+        ql = ql < 0.0 ? 0.0 : (ql > 255.0 ? 255.0 : ql);
+        qh = qh < 0.0 ? 0.0 : (qh > 255.0 ? 255.0 : qh);
+        q.qlo[a][k] = (uint8_t)ql;
+        q.qhi[a][k] = (uint8_t)qh;
+      }
+    }
+    for (int k = 0; k < 4; k++) q.child[k] = n.child[k];
+  }
+  lap("quantise");
   return MTB_OK;
 }
 

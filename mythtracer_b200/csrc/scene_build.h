@@ -47,6 +47,21 @@ struct alignas(128) Bvh4Node {
 };
 static_assert(sizeof(Bvh4Node) == 128, "Bvh4Node must be one cache line");
 
+// What the device walks: Bvh4Node with the child boxes quantised to 8 bits per plane in the frame of the node
+// (origin = low corner of the union of the child boxes, one power-of-two scale per axis), rounded outwards: 64
+// bytes = four 128-bit loads per node instead of seven.  The traversal is bound by the L1 data pipe (ncu: 70 % of
+// its wavefront rate, issue slots 59 % busy), i.e. by the bytes a ray pulls through L1, and node boxes are most of them.
+struct alignas(64) Bvh4QNode {
+  float origin[3];
+  uint8_t exp[3];     // biased exponent of the per-axis scale: scale = 2^(exp - 127)
+  uint8_t pad0_;
+  uint8_t qlo[3][4];  // [axis][child]: plane = origin + q * scale;  an unused child has qlo = 255, qhi = 0
+  uint8_t qhi[3][4];
+  uint32_t pad1_[2];
+  int32_t child[4];   // as Bvh4Node::child
+};
+static_assert(sizeof(Bvh4QNode) == 64, "Bvh4QNode must be half a cache line");
+
 // One octree node = one 128-byte line.  The 8 children of a node are contiguous (first_child .. +7) and
 // their boxes are exactly {lo,c} / {c,hi} per axis (octtree.cc:61-100), so a node carries the three
 // planes per axis once instead of eight child boxes.
@@ -88,7 +103,8 @@ struct FlatScene {
   std::vector<BvhRec> bvh;
   std::vector<int32_t> list_order;  // list_order[list_first + k] = slot of the k-th entry in reference order
   std::vector<Bvh2Node> gnodes;     // binary scene BVH, node 0 = root (empty: no fast traversal)
-  std::vector<Bvh4Node> gnodes4;    // the same tree collapsed to four children per node (what the device walks)
+  std::vector<Bvh4Node> gnodes4;    // the same tree collapsed to four children per node
+  std::vector<Bvh4QNode> gnodesq;   // gnodes4 with quantised boxes (what the device walks)
   int32_t gbvh4_depth = 0;
   std::vector<SlotRec> gslots;      // copies of `slots` in scene-BVH leaf order
   int32_t gbvh_depth = 0;

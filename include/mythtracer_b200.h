@@ -167,11 +167,10 @@ int mtb_load_mtl(mtb_context *ctx, const char *path);
  * (6 doubles: lo.xyz, hi.xyz) and that node's depth.  Either pointer may be NULL. */
 int mtb_scene_triangle_nodes(const mtb_context *ctx, double *node_box, int32_t *node_depth);
 /* The scene BVH of the certified fast traversal, for inspection: node count, depth, the
- * nodes themselves (128 bytes each: float box[4][6] = lo.xyz hi.xyz of up to four children; int32 child[4],
- * pad[4]; a child >= 0 is a node index, < 0 a leaf with ~child = (first << 3) | count over leaf_order, unused
- * children are empty leaves with an inverted box) and, per leaf position, the insertion index of the triangle
- * stored there (n_triangles entries).  Any pointer may be NULL.  n_nodes == 0: the scene has no fast traversal
- * (empty scene, MTB_FLAG_NO_LIST_BVH, or a tree deeper than the traversal stack). */
+ * nodes themselves (64 bytes each: float lbox[6], rbox[6]; int32 left, right, pad[2]; a child >= 0 is a node
+ * index, < 0 a leaf with ~child = (first << 3) | count over leaf_order) and, per leaf position, the insertion
+ * index of the triangle stored there (n_triangles entries).  Any pointer may be NULL.  n_nodes == 0: the scene
+ * has no fast traversal (empty scene, MTB_FLAG_NO_LIST_BVH, or a tree deeper than the traversal stack). */
 int mtb_scene_bvh(const mtb_context *ctx, int64_t *n_nodes, int32_t *depth, void *nodes, int32_t *leaf_order);
 int mtb_set_flags(mtb_context *ctx, uint32_t flags);
 /* Tile partitioning across processes -- the in-process form of the reference's master/worker contract

@@ -64,7 +64,7 @@ struct DeviceState {
   DeviceBuffer<mtb::SlotRec> slots;
   DeviceBuffer<mtb::ShadeRec> shade;
   DeviceBuffer<mtb::BvhRec> bvh;
-  DeviceBuffer<mtb::Bvh4QNode> gnodes;   // scene BVH of the certified fast traversal
+  DeviceBuffer<mtb::Bvh2Node> gnodes;   // scene BVH of the certified fast traversal
   DeviceBuffer<mtb::SlotRec> gslots;
   DeviceBuffer<int32_t> list_order;
   DeviceBuffer<mtb_material> materials;
@@ -169,7 +169,7 @@ void DestroyTextures(DeviceState *d) {
 
 // Regular rays take the certified fast traversal over the scene BVH unless the exact octree recursion is forced.
 void SelectTraversal(mtb_context *ctx, DeviceState *d) {
-  const bool fast = (ctx->flags & (MTB_FLAG_EXACT_OCTREE | MTB_FLAG_NO_LIST_BVH)) == 0 && !ctx->flat.gnodes4.empty() &&
+  const bool fast = (ctx->flags & (MTB_FLAG_EXACT_OCTREE | MTB_FLAG_NO_LIST_BVH)) == 0 && !ctx->flat.gnodes.empty() &&
                     d->scene.cull_radius > 0.0f;
   d->scene.gnodes = fast ? d->gnodes.ptr : nullptr;
   d->scene.gslots = fast ? d->gslots.ptr : nullptr;
@@ -183,7 +183,7 @@ int UploadToDevice(mtb_context *ctx, DeviceState *d) {
   MTB_CUDA(ctx, d->shade.Upload(f.shade.data(), f.shade.size(), d->stream));
   MTB_CUDA(ctx, d->bvh.Upload(f.bvh.data(), f.bvh.size(), d->stream));
   MTB_CUDA(ctx, d->list_order.Upload(f.list_order.data(), f.list_order.size(), d->stream));
-  MTB_CUDA(ctx, d->gnodes.Upload(f.gnodesq.data(), f.gnodesq.size(), d->stream));
+  MTB_CUDA(ctx, d->gnodes.Upload(f.gnodes.data(), f.gnodes.size(), d->stream));
   MTB_CUDA(ctx, d->gslots.Upload(f.gslots.data(), f.gslots.size(), d->stream));
   MTB_CUDA(ctx, d->materials.Upload(ctx->materials.data(), ctx->materials.size(), d->stream));
   DestroyTextures(d);
@@ -282,7 +282,7 @@ int BuildAndUpload(mtb_context *ctx) {
   }
   ctx->device_bytes = (int64_t)(ctx->flat.nodes.size() * sizeof(mtb::NodeRec) + ctx->flat.slots.size() * sizeof(mtb::SlotRec) +
                                 ctx->flat.shade.size() * sizeof(mtb::ShadeRec) + ctx->flat.bvh.size() * sizeof(mtb::BvhRec) +
-                                ctx->flat.gnodesq.size() * sizeof(mtb::Bvh4QNode) + ctx->flat.gslots.size() * sizeof(mtb::SlotRec) +
+                                ctx->flat.gnodes.size() * sizeof(mtb::Bvh2Node) + ctx->flat.gslots.size() * sizeof(mtb::SlotRec) +
                                 ctx->flat.list_order.size() * 4 + ctx->materials.size() * sizeof(mtb_material));
   for (const mtb::LoadedTexture &t : ctx->textures) ctx->device_bytes += (int64_t)t.rgba.size();
   for (DeviceState &d : ctx->dev) {
@@ -923,31 +923,9 @@ int mtb_scene_triangle_nodes(const mtb_context *ctx, double *node_box, int32_t *
 int mtb_scene_bvh(const mtb_context *ctx, int64_t *n_nodes, int32_t *depth, void *nodes, int32_t *leaf_order) {
   if (ctx == nullptr) return MTB_ERR_ARG;
   const mtb::FlatScene &f = ctx->flat;
-  if (n_nodes != nullptr) *n_nodes = (int64_t)f.gnodesq.size();
-  if (depth != nullptr) *depth = f.gbvh4_depth;
-  if (nodes != nullptr) {
-    // the boxes the device tests: the quantised planes decoded exactly (origin + q * 2^e) and then rounded INWARDS
-    // to float, so that a containment check on the exported boxes is a check of what the kernels use
-    mtb::Bvh4Node *out = static_cast<mtb::Bvh4Node *>(nodes);
-    for (size_t i = 0; i < f.gnodesq.size(); i++) {
-      const mtb::Bvh4QNode &q = f.gnodesq[i];
-      mtb::Bvh4Node n;
-      memset(&n, 0, sizeof(n));
-      for (int k = 0; k < 4; k++) {
-        n.child[k] = q.child[k];
-        for (int a = 0; a < 3; a++) {
-          const double scale = std::ldexp(1.0, (int)q.exp[a] - 127);
-          const double lo = (double)q.origin[a] + (double)q.qlo[a][k] * scale, hi = (double)q.origin[a] + (double)q.qhi[a][k] * scale;
-          float flo = (float)lo, fhi = (float)hi;
-          if ((double)flo < lo) flo = std::nextafterf(flo, INFINITY);
-          if ((double)fhi > hi) fhi = std::nextafterf(fhi, -INFINITY);
-          n.box[k][a] = flo;
-          n.box[k][3 + a] = fhi;
-        }
-      }
-      out[i] = n;
-    }
-  }
+  if (n_nodes != nullptr) *n_nodes = (int64_t)f.gnodes.size();
+  if (depth != nullptr) *depth = f.gbvh_depth;
+  if (nodes != nullptr && !f.gnodes.empty()) memcpy(nodes, f.gnodes.data(), f.gnodes.size() * sizeof(mtb::Bvh2Node));
   if (leaf_order != nullptr) {
     for (size_t i = 0; i < f.gslots.size(); i++) leaf_order[i] = f.gslots[i].tri;
   }

@@ -545,6 +545,7 @@ __device__ __noinline__ int TraceLiteral(const DeviceScene &sc, const Ray &r, do
 // computed arithmetic), and a pruned, never evaluated triangle whose own computed t is off by more than the
 // pruning margin (Moller-Trumbore determinant within ~1e3 of the reference's rejection threshold 1e-8).
 // ---------------------------------------------------------------------------------------------------
+constexpr int kFastStack = kSceneBvhMaxDepth + 8;
 constexpr int kFastExit = (int)0x80000000;
 
 // Moller-Trumbore exactly as MollerTrumbore() above (same operations, same order -> same bits) plus a forward
@@ -580,68 +581,47 @@ __device__ __forceinline__ bool MollerTrumboreBound(const double *vert, const Ra
   return true;
 }
 
-// The best hit: slot and prune stay in registers; t, e and lo2 are only touched when a triangle is accepted
-// (about once per ray) and live in columns 9..11 of the staging area next to the FP64 ray.
 struct FastBest {
+  double t, e, lo2;
   int slot;     // canonical slot of the best hit, -1: none
   float prune;  // subtrees whose conservative entry distance exceeds this cannot matter
 };
 
-// The FP64 ray (origin, direction, inverse direction) is only needed at the leaves.  It is parked in shared memory
-// for the duration of a traversal (column threadIdx.x of a [9][BLOCK] array, conflict-free) so that the inner
-// node loop has the register file to itself: kept in registers, it pushed three values the box tests need every
-// iteration into local memory (ncu: 3 of the 7 memory instructions of a node visit were spill reloads, and the
-// L1 data pipe, at 77 % of its peak, is what bounds this kernel).
-template <int BLOCK>
-__device__ __forceinline__ void LoadStagedRay(const double *sh, Ray *r) {
-  r->o = Mk(sh[0 * BLOCK], sh[1 * BLOCK], sh[2 * BLOCK]);
-  r->d = Mk(sh[3 * BLOCK], sh[4 * BLOCK], sh[5 * BLOCK]);
-  r->inv = Mk(sh[6 * BLOCK], sh[7 * BLOCK], sh[8 * BLOCK]);
-}
-
-template <bool DBG, int BLOCK>
-__device__ __forceinline__ void TestSlotFast(const SlotRec *rec, const Ray &rf, const double *sh, FastBest *fb,
-                                             unsigned long long *cnt) {
+template <bool DBG>
+__device__ __forceinline__ void TestSlotFast(const SlotRec *rec, const Ray &r, FastBest *fb, unsigned long long *cnt) {
   const double2 b0 = Ld2(rec->box + 0), b1 = Ld2(rec->box + 2), b2 = Ld2(rec->box + 4);
   Count<DBG>(cnt, kTriAabb);
-  Ray r;
-  r.sx = rf.sx;
-  r.sy = rf.sy;
-  r.sz = rf.sz;
-  LoadStagedRay<BLOCK>(sh, &r);
   double unused;
   if (!SlabRegular(b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, r, &unused)) return;  // primitive_triangle.cc:85-108
   Count<DBG>(cnt, kMt);
   double t, e;
   if (!MollerTrumboreBound(rec->vert, r, &t, &e)) return;
   Count<DBG>(cnt, kHit);
-  double *best = const_cast<double *>(sh) + 9 * BLOCK;  // t, e, lo2
-  if (fb->slot >= 0 && !(t < best[0])) {
-    best[2 * BLOCK] = fmin(best[2 * BLOCK], t - e);
+  if (fb->slot >= 0 && !(t < fb->t)) {
+    fb->lo2 = fmin(fb->lo2, t - e);
     return;
   }
-  if (fb->slot >= 0) best[2 * BLOCK] = fmin(best[2 * BLOCK], best[0] - best[BLOCK]);
-  best[0] = t;
-  best[BLOCK] = e;
+  if (fb->slot >= 0) fb->lo2 = fmin(fb->lo2, fb->t - fb->e);
+  fb->t = t;
+  fb->e = e;
   fb->slot = __ldg(&rec->canon);
   fb->prune = fminf(fb->prune, __double2float_ru(t + 2.0 * e + t * 0x1p-20));
 }
 
-// Conservative FP32 slab test of one child box of a quantised node; *tn_out = lower bound of the entry distance.
-// A plane is origin + q * scale (scale a power of two); its ray parameter (origin + q scale - o) * i is evaluated
-// as fma(q, ss, adj) with ss = scale * i (exact) and adj = fma(origin, i, -(o i)), both per node and axis.  Against
-// the FP64 value this is off by at most 2^-23 |t| plus 25 * 2^-24 R |i| < 2^-19 R |i| for |o| <= 8R (o and i
-// rounded to float, the product o i, the two fma).  The absolute part is a constant 2^-19 R in SPACE whatever the
-// ray, so it is paid at build time: every box is grown by 2^-17 R on all sides before it is quantised outwards
-// (SceneBvhBuilder::pad).  The relative part widens the winners of the max / min by 2^-21 |t| (4x the bound).
-__device__ __forceinline__ bool FastBoxQ(unsigned nwx, unsigned nwy, unsigned nwz, unsigned fwx, unsigned fwy, unsigned fwz,
-                                         int k, float ssx, float ssy, float ssz, float adjx, float adjy, float adjz,
-                                         float prune, float *tn_out) {
+// Conservative FP32 slab test of one child box; *tn_out = lower bound of the entry distance.  t = fma(b, i, -(o i))
+// differs from the FP64 value of (b - o) * i by at most 2^-23 |t| + 2^-20 R |i| for |o| <= 8R (o and i rounded
+// to float, the product o i, the fma).  The absolute part is a constant 2^-20 R in SPACE whatever the ray, so it
+// is paid at build time: every stored box is grown by 2^-17 R on all sides (SceneBvhBuilder::pad, 8x the bound),
+// which moves every near plane down and every far plane up per axis.  (It must be per axis: a slack shared
+// between the axes made rays that are almost perpendicular to one axis - huge |i| - pass every box of the scene.)
+// The relative part widens the winners of the max / min by 2^-21 |t| (4x the bound); widening only the winning
+// axis is enough because the bound of the max (min) is the bound of its argmax (argmin).
+__device__ __forceinline__ bool FastBox(float lox, float loy, float loz, float hix, float hiy, float hiz, const Ray &r,
+                                        float nox, float noy, float noz, float prune, float *tn_out) {
   const float kRel = 4.76837158203125e-07f;  // 2^-21
-  const int sh = 8 * k;
-  const float nx = __fmaf_rn((float)((nwx >> sh) & 255u), ssx, adjx), fx = __fmaf_rn((float)((fwx >> sh) & 255u), ssx, adjx);
-  const float ny = __fmaf_rn((float)((nwy >> sh) & 255u), ssy, adjy), fy = __fmaf_rn((float)((fwy >> sh) & 255u), ssy, adjy);
-  const float nz = __fmaf_rn((float)((nwz >> sh) & 255u), ssz, adjz), fz = __fmaf_rn((float)((fwz >> sh) & 255u), ssz, adjz);
+  const float nx = __fmaf_rn(r.sx ? hix : lox, r.ix, nox), fx = __fmaf_rn(r.sx ? lox : hix, r.ix, nox);
+  const float ny = __fmaf_rn(r.sy ? hiy : loy, r.iy, noy), fy = __fmaf_rn(r.sy ? loy : hiy, r.iy, noy);
+  const float nz = __fmaf_rn(r.sz ? hiz : loz, r.iz, noz), fz = __fmaf_rn(r.sz ? loz : hiz, r.iz, noz);
   float tn = fmaxf(fmaxf(nx, ny), nz);
   float tf = fminf(fminf(fx, fy), fz);
   tn = __fmaf_rn(-kRel, fabsf(tn), tn);
@@ -659,9 +639,10 @@ __device__ __forceinline__ bool FastBoxQ(unsigned nwx, unsigned nwy, unsigned nw
 //   e <= 2^-48 * 6 L^2 (2 dmax T + L) / (1e-8 - 2^-48 * 6 dmax L^2) + 2^-49 T =: M(T).
 // M grows by far less than 1 per unit of T, so a triangle entered behind t_limit + M(t_limit) cannot come out in
 // front of t_limit.  If the denominator is not comfortably positive (huge triangles) nothing is pruned by limit.
-__device__ __forceinline__ float LimitPrune(const DeviceScene &sc, double dmax, double t_limit) {
+__device__ __forceinline__ float LimitPrune(const DeviceScene &sc, const Ray &r, double t_limit) {
   if (!(t_limit < CUDART_INF)) return CUDART_INF_F;
   const double L = (double)sc.max_tri_extent;
+  const double dmax = fmax(fmax(fabs(r.d.x), fabs(r.d.y)), fabs(r.d.z));
   const double k = 0x1p-48 * 6.0 * L * L;
   const double den = 0.00000001 - k * dmax;
   if (!(den > 0.000000005)) return CUDART_INF_F;
@@ -669,98 +650,61 @@ __device__ __forceinline__ float LimitPrune(const DeviceScene &sc, double dmax, 
   return __double2float_ru(t_limit + 2.0 * m + t_limit * 0x1p-20);
 }
 
-// Compare-exchange of two (entry distance, child) pairs: the nearer one ends up in (ka, ra).
-__device__ __forceinline__ void OrderPair(float &ka, int &ra, float &kb, int &rb) {
-  const bool swap = kb < ka;
-  const float k0 = swap ? kb : ka, k1 = swap ? ka : kb;
-  const int r0 = swap ? rb : ra, r1 = swap ? ra : rb;
-  ka = k0;
-  ra = r0;
-  kb = k1;
-  rb = r1;
-}
-
-// rf: the FP32 part of the ray (ox.., ix.., px.., sx..); sh: its FP64 part, staged (LoadStagedRay); prune0: LimitPrune.
-template <bool DBG, int BLOCK>
-__device__ int TraceFast(const DeviceScene &sc, const Ray &rf, const double *sh, float prune0, double *t_out, bool *ambiguous,
+template <bool DBG>
+__device__ int TraceFast(const DeviceScene &sc, const Ray &r, double t_limit, double *t_out, bool *ambiguous,
                          unsigned long long *cnt) {
-  unsigned long long stack[kFastStackSize];  // (entry distance bits << 32) | child reference
+  unsigned long long stack[kFastStack];
   int sp = 0;
-  const float nox = -(rf.ox * rf.ix), noy = -(rf.oy * rf.iy), noz = -(rf.oz * rf.iz);
+  const float nox = -(r.ox * r.ix), noy = -(r.oy * r.iy), noz = -(r.oz * r.iz);
   FastBest fb;
+  fb.t = 0.0;
+  fb.e = 0.0;
+  fb.lo2 = CUDART_INF;
   fb.slot = -1;
-  fb.prune = prune0;
-  const_cast<double *>(sh)[11 * BLOCK] = CUDART_INF;  // lo2
+  fb.prune = LimitPrune(sc, r, t_limit);
   int node = 0;
-#define MTB_FAST_PUSH(key, ref) stack[sp++] = ((unsigned long long)__float_as_uint(key) << 32) | (unsigned)(ref)
-#define MTB_FAST_POP()                                                   \
-  do {                                                                   \
-    node = kFastExit;                                                    \
-    while (sp > 0) {                                                     \
-      const unsigned long long top = stack[--sp];                        \
-      if (__uint_as_float((unsigned)(top >> 32)) <= fb.prune) {          \
-        node = (int)(unsigned)top;                                       \
-        break;                                                           \
-      }                                                                  \
-    }                                                                    \
-  } while (0)
   for (;;) {
     while (node >= 0) {
-      // one quantised 4-wide node = 64 bytes: origin.xyz + exponents | near / far plane bytes | child references
-      const uint4 *q = reinterpret_cast<const uint4 *>(sc.gnodes + node);
-      const uint4 w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
-      const uint4 kw = __ldg(q + 3);
-      const int4 kids = make_int4((int)kw.x, (int)kw.y, (int)kw.z, (int)kw.w);
-      Count<DBG>(cnt, kBvh, 4);
-      const float ssx = __uint_as_float((w0.w & 255u) << 23) * rf.ix;
-      const float ssy = __uint_as_float(((w0.w >> 8) & 255u) << 23) * rf.iy;
-      const float ssz = __uint_as_float(((w0.w >> 16) & 255u) << 23) * rf.iz;
-      const float adjx = __fmaf_rn(__uint_as_float(w0.x), rf.ix, nox);
-      const float adjy = __fmaf_rn(__uint_as_float(w0.y), rf.iy, noy);
-      const float adjz = __fmaf_rn(__uint_as_float(w0.z), rf.iz, noz);
-      // w1 = qlo.x qlo.y qlo.z qhi.x (four children per word), w2 = qhi.y qhi.z: the planes the ray meets first
-      const unsigned nwx = rf.sx ? w1.w : w1.x, fwx = rf.sx ? w1.x : w1.w;
-      const unsigned nwy = rf.sy ? w2.x : w1.y, fwy = rf.sy ? w1.y : w2.x;
-      const unsigned nwz = rf.sz ? w2.y : w1.z, fwz = rf.sz ? w1.z : w2.y;
-      float k0, k1, k2, k3;
-      const bool h0 = FastBoxQ(nwx, nwy, nwz, fwx, fwy, fwz, 0, ssx, ssy, ssz, adjx, adjy, adjz, fb.prune, &k0);
-      const bool h1 = FastBoxQ(nwx, nwy, nwz, fwx, fwy, fwz, 1, ssx, ssy, ssz, adjx, adjy, adjz, fb.prune, &k1);
-      const bool h2 = FastBoxQ(nwx, nwy, nwz, fwx, fwy, fwz, 2, ssx, ssy, ssz, adjx, adjy, adjz, fb.prune, &k2);
-      const bool h3 = FastBoxQ(nwx, nwy, nwz, fwx, fwy, fwz, 3, ssx, ssy, ssz, adjx, adjy, adjz, fb.prune, &k3);
-      k0 = h0 ? k0 : CUDART_INF_F;
-      k1 = h1 ? k1 : CUDART_INF_F;
-      k2 = h2 ? k2 : CUDART_INF_F;
-      k3 = h3 ? k3 : CUDART_INF_F;
-      int r0 = kids.x, r1 = kids.y, r2 = kids.z, r3 = kids.w;
-      // sorting network: nearest child first, children the ray misses (key +inf) last
-      OrderPair(k0, r0, k1, r1);
-      OrderPair(k2, r2, k3, r3);
-      OrderPair(k0, r0, k2, r2);
-      OrderPair(k1, r1, k3, r3);
-      OrderPair(k1, r1, k2, r2);
-      if (k0 < CUDART_INF_F) {
-        if (k3 < CUDART_INF_F) MTB_FAST_PUSH(k3, r3);
-        if (k2 < CUDART_INF_F) MTB_FAST_PUSH(k2, r2);
-        if (k1 < CUDART_INF_F) MTB_FAST_PUSH(k1, r1);
-        node = r0;
+      const float4 *q = reinterpret_cast<const float4 *>(sc.gnodes + node);
+      const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+      const int2 kids = __ldg(reinterpret_cast<const int2 *>(q + 3));
+      Count<DBG>(cnt, kBvh, 2);
+      float tl, tr;
+      const bool hl = FastBox(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, nox, noy, noz, fb.prune, &tl);
+      const bool hr = FastBox(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, nox, noy, noz, fb.prune, &tr);
+      if (hl && hr) {
+        const bool right_first = tr < tl;
+        stack[sp++] = ((unsigned long long)__float_as_uint(right_first ? tl : tr) << 32) | (unsigned)(right_first ? kids.x : kids.y);
+        node = right_first ? kids.y : kids.x;
+      } else if (hl) {
+        node = kids.x;
+      } else if (hr) {
+        node = kids.y;
       } else {
-        MTB_FAST_POP();
+        node = kFastExit;
+        while (sp > 0) {
+          const unsigned long long top = stack[--sp];
+          if (__uint_as_float((unsigned)(top >> 32)) <= fb.prune) {
+            node = (int)(unsigned)top;
+            break;
+          }
+        }
       }
     }
     if (node == kFastExit) break;
     const unsigned leaf = ~(unsigned)node;
-    for (unsigned s = leaf >> 3, e = s + (leaf & 7u); s < e; s++) TestSlotFast<DBG, BLOCK>(sc.gslots + s, rf, sh, &fb, cnt);
-    MTB_FAST_POP();
+    for (unsigned s = leaf >> 3, e = s + (leaf & 7u); s < e; s++) TestSlotFast<DBG>(sc.gslots + s, r, &fb, cnt);
+    node = kFastExit;
+    while (sp > 0) {
+      const unsigned long long top = stack[--sp];
+      if (__uint_as_float((unsigned)(top >> 32)) <= fb.prune) {
+        node = (int)(unsigned)top;
+        break;
+      }
+    }
   }
-#undef MTB_FAST_PUSH
-#undef MTB_FAST_POP
-  if (fb.slot >= 0) {
-    const double t = sh[9 * BLOCK], e = sh[10 * BLOCK], lo2 = sh[11 * BLOCK];
-    *ambiguous = lo2 <= t + e;
-    *t_out = t;
-  } else {
-    *ambiguous = false;
-  }
+  *ambiguous = fb.slot >= 0 && fb.lo2 <= fb.t + fb.e;
+  *t_out = fb.t;
   return fb.slot;
 }
 
@@ -772,11 +716,10 @@ __device__ __noinline__ int TraceRegularCold(const DeviceScene &sc, const Ray &r
 
 // OctTree::IntersectRay (octtree.cc:26-40): inverse direction, then one of the traversals.
 // t_limit: results with t > t_limit are of no use to the caller (it may then get -1 or any such hit); CUDART_INF
-// for a plain closest-hit query.  BLOCK = threads per block of the calling kernel (staging area of the FP64 ray).
-template <bool DBG, int BLOCK>
+// for a plain closest-hit query.
+template <bool DBG>
 __device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D3 &d, double t_limit, double *t_out,
                                      unsigned long long *cnt MTB_TOP_PARAMS) {
-  __shared__ double s_stage[12 * BLOCK];  // FP64 ray (9) + best hit t, e, lo2 (3), one column per thread
   Ray r;
   r.o = o;
   r.d = d;
@@ -804,42 +747,14 @@ __device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D
     r.px = pr * fabsf(r.ix);
     r.py = pr * fabsf(r.iy);
     r.pz = pr * fabsf(r.iz);
-    if (sc.gnodes != nullptr && r.cull32 && ai_max <= 0x1p40 && ai_min >= 0x1p-40) {  // scale * i stays a normal float
-      double *sh = s_stage + threadIdx.x;
-      sh[0 * BLOCK] = r.o.x;
-      sh[1 * BLOCK] = r.o.y;
-      sh[2 * BLOCK] = r.o.z;
-      sh[3 * BLOCK] = r.d.x;
-      sh[4 * BLOCK] = r.d.y;
-      sh[5 * BLOCK] = r.d.z;
-      sh[6 * BLOCK] = r.inv.x;
-      sh[7 * BLOCK] = r.inv.y;
-      sh[8 * BLOCK] = r.inv.z;
-      const float prune0 = LimitPrune(sc, fmax(fmax(fabs(d.x), fabs(d.y)), fabs(d.z)), t_limit);
-      Ray rf;  // the FP32 part only: nothing FP64 stays live across the traversal
-      rf.sx = r.sx;
-      rf.sy = r.sy;
-      rf.sz = r.sz;
-      rf.ox = r.ox;
-      rf.oy = r.oy;
-      rf.oz = r.oz;
-      rf.ix = r.ix;
-      rf.iy = r.iy;
-      rf.iz = r.iz;
-      rf.px = r.px;
-      rf.py = r.py;
-      rf.pz = r.pz;
+    if (sc.gnodes != nullptr && r.cull32) {
       bool ambiguous;
-      const int slot = TraceFast<DBG, BLOCK>(sc, rf, sh, prune0, t_out, &ambiguous, cnt);
+      const int slot = TraceFast<DBG>(sc, r, t_limit, t_out, &ambiguous, cnt);
       if (!ambiguous) {
         Count<DBG>(cnt, kFast);
         return slot;
       }
       Count<DBG>(cnt, kFallback);
-      Ray rr = rf;
-      rr.cull32 = true;
-      LoadStagedRay<BLOCK>(sh, &rr);
-      return TraceRegularCold<DBG>(sc, rr, t_out, cnt MTB_TOP_ARGS);
     }
     return TraceRegularCold<DBG>(sc, r, t_out, cnt MTB_TOP_ARGS);
   }

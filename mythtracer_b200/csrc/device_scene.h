@@ -15,7 +15,7 @@ struct DeviceScene {
   const ShadeRec *shade;
   const BvhRec *bvh;
   const int32_t *list_order;
-  const Bvh4QNode *gnodes;  // 4-wide quantised scene BVH of the certified fast traversal; NULL: exact octree recursion only
+  const Bvh2Node *gnodes;   // scene BVH of the certified fast traversal; NULL: exact octree recursion only
   const SlotRec *gslots;    // the triangles in scene-BVH leaf order (SlotRec::canon = slot in slots / shade)
   const mtb_material *materials;
   cudaTextureObject_t tex_atlas;  // ONE point-sampled layered texture object: layer = texture index, one RGBA32 texel per 32-bit word

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(MODE == kModePack ? kPackThreads : kBlockThrea
           const D3 ro = Mk(s_ray[0 * kPackThreads + i], s_ray[1 * kPackThreads + i], s_ray[2 * kPackThreads + i]);
           const D3 rd = Mk(s_ray[3 * kPackThreads + i], s_ray[4 * kPackThreads + i], s_ray[5 * kPackThreads + i]);
           double rt = 0.0;
-          s_res_slot[i] = Trace<DBG, kPackThreads>(sc, ro, rd, s_ray[6 * kPackThreads + i], &rt, cnt MTB_TOP_ARGS);
+          s_res_slot[i] = Trace<DBG>(sc, ro, rd, s_ray[6 * kPackThreads + i], &rt, cnt MTB_TOP_ARGS);
           s_res_t[i] = rt;
         }
         __syncthreads();
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(MODE == kModePack ? kPackThreads : kBlockThrea
         slot = s_res_slot[mine];
         t = s_res_t[mine];
       } else {
-        slot = Trace<DBG, kBlockThreads>(sc, to, td, shadow_mode ? light_distance : CUDART_INF, &t, cnt MTB_TOP_ARGS);
+        slot = Trace<DBG>(sc, to, td, shadow_mode ? light_distance : CUDART_INF, &t, cnt MTB_TOP_ARGS);
       }
       n_rays++;
 
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(128) IntersectKernel(DeviceScene sc, Intersect
   if (i < ip.n) {
     const D3 o = Load3(ip.origins + i * 3), d = Load3(ip.dirs + i * 3);
     double t = 0.0;
-    const int slot = Trace<DBG, 128>(sc, o, d, CUDART_INF, &t, cnt MTB_TOP_ARGS);
+    const int slot = Trace<DBG>(sc, o, d, CUDART_INF, &t, cnt MTB_TOP_ARGS);
     if (slot < 0) {
       ip.tri_index[i] = -1;
     } else {

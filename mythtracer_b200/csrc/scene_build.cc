@@ -13,7 +13,6 @@
 #include "scene_build.h"
 
 #include <algorithm>
-#include <cfloat>
 #include <cmath>
 #include <cstring>
 #include <atomic>
@@ -522,117 +521,6 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
     }
   }
   lap("scene BVH");
-  // ---- collapse to four children per node ----
-  out->gnodes4.clear();
-  out->gbvh4_depth = 0;
-  if (!out->gnodes.empty()) {
-    struct Item {
-      int32_t ref;
-      float box[6];
-    };
-    auto area = [](const float *b) {
-      const double dx = (double)b[3] - b[0], dy = (double)b[4] - b[1], dz = (double)b[5] - b[2];
-      return dx * dy + dy * dz + dz * dx;
-    };
-    // explicit work list: (binary node, index of the 4-wide node to fill, depth)
-    struct Work {
-      int32_t n2, n4, depth;
-    };
-    std::vector<Work> todo;
-    out->gnodes4.emplace_back();
-    todo.push_back({0, 0, 0});
-    while (!todo.empty()) {
-      const Work w = todo.back();
-      todo.pop_back();
-      if (w.depth > out->gbvh4_depth) out->gbvh4_depth = w.depth;
-      Item items[4];
-      int n_items = 2;
-      const Bvh2Node &b2 = out->gnodes[(size_t)w.n2];
-      items[0].ref = b2.left;
-      memcpy(items[0].box, b2.lbox, sizeof(b2.lbox));
-      items[1].ref = b2.right;
-      memcpy(items[1].box, b2.rbox, sizeof(b2.rbox));
-      while (n_items < 4) {
-        int pick = -1;
-        double best = -1.0;
-        for (int k = 0; k < n_items; k++) {
-          if (items[k].ref >= 0 && area(items[k].box) > best) {
-            best = area(items[k].box);
-            pick = k;
-          }
-        }
-        if (pick < 0) break;
-        const Bvh2Node &c = out->gnodes[(size_t)items[pick].ref];
-        items[pick].ref = c.left;
-        memcpy(items[pick].box, c.lbox, sizeof(c.lbox));
-        items[n_items].ref = c.right;
-        memcpy(items[n_items].box, c.rbox, sizeof(c.rbox));
-        n_items++;
-      }
-      Bvh4Node n4;
-      memset(&n4, 0, sizeof(n4));
-      for (int k = 0; k < 4; k++) {
-        if (k < n_items) {
-          memcpy(n4.box[k], items[k].box, sizeof(items[k].box));
-          if (items[k].ref >= 0) {
-            n4.child[k] = (int32_t)out->gnodes4.size();
-            out->gnodes4.emplace_back();
-            todo.push_back({items[k].ref, n4.child[k], w.depth + 1});
-          } else {
-            n4.child[k] = items[k].ref;
-          }
-        } else {
-          for (int a = 0; a < 3; a++) {
-            n4.box[k][a] = FLT_MAX;
-            n4.box[k][3 + a] = -FLT_MAX;
-          }
-          n4.child[k] = ~0;  // an empty leaf
-        }
-      }
-      out->gnodes4[(size_t)w.n4] = n4;
-    }
-    if (3 * (out->gbvh4_depth + 1) + 4 > kFastStackSize) {
-      out->gnodes.clear();
-      out->gnodes4.clear();
-      out->gslots.clear();
-    }
-  }
-  lap("collapse to 4-wide");
-  // ---- quantise the child boxes (outwards) ----
-  out->gnodesq.assign(out->gnodes4.size(), Bvh4QNode{});
-  for (size_t i = 0; i < out->gnodes4.size(); i++) {
-    const Bvh4Node &n = out->gnodes4[i];
-    Bvh4QNode &q = out->gnodesq[i];
-    memset(&q, 0, sizeof(q));
-    for (int a = 0; a < 3; a++) {
-      double lo = INFINITY, hi = -INFINITY;
-      for (int k = 0; k < 4; k++) {
-        if (n.box[k][a] > n.box[k][3 + a]) continue;  // unused child
-        lo = std::min(lo, (double)n.box[k][a]);
-        hi = std::max(hi, (double)n.box[k][3 + a]);
-      }
-      if (!(lo <= hi)) lo = hi = 0.0;
-      q.origin[a] = (float)lo;  // exact: it is one of the float planes
-      int e = -60;
-      while (e < 100 && 255.0 * std::ldexp(1.0, e) < hi - lo) e++;
-      q.exp[a] = (uint8_t)(e + 127);
-      const double scale = std::ldexp(1.0, e);
-      for (int k = 0; k < 4; k++) {
-        if (n.box[k][a] > n.box[k][3 + a]) {
-          q.qlo[a][k] = 255;
-          q.qhi[a][k] = 0;
-          continue;
-        }
-        double ql = std::floor(((double)n.box[k][a] - lo) / scale), qh = std::ceil(((double)n.box[k][3 + a] - lo) / scale);
-        ql = ql < 0.0 ? 0.0 : (ql > 255.0 ? 255.0 : ql);
-        qh = qh < 0.0 ? 0.0 : (qh > 255.0 ? 255.0 : qh);
-        q.qlo[a][k] = (uint8_t)ql;
-        q.qhi[a][k] = (uint8_t)qh;
-      }
-    }
-    for (int k = 0; k < 4; k++) q.child[k] = n.child[k];
-  }
-  lap("quantise");
   return MTB_OK;
 }
 

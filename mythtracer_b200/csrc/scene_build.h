@@ -25,7 +25,10 @@ struct alignas(32) BvhRec {
 static_assert(sizeof(BvhRec) == 32, "BvhRec must be a quarter of a cache line");
 
 // Scene BVH of the certified fast traversal (device_core.cuh, TraceFast): one binary BVH over ALL triangles, a
-// node holds the boxes of its two children (FP32, rounded outwards) = 64 bytes, half a line, four 128-bit loads.
+// node holds the boxes of its two children (FP32, grown by SceneBvhBuilder::pad and rounded outwards) = 64 bytes,
+// half a line, four 128-bit loads.  Measured alternatives that did not pay (same bytes): the
+// tree collapsed to four children per node (128-byte nodes, commit e83e983) and four-wide nodes with 8-bit
+// quantised boxes (64 bytes for four children, commit 5e4af88).
 // Like BvhRec it is a CONSERVATIVE cull only: the triangles of a leaf are decided by the exact FP64 reference tests.
 struct alignas(64) Bvh2Node {
   float lbox[6];   // left child: lo.xyz rounded down, hi.xyz rounded up
@@ -35,32 +38,6 @@ struct alignas(64) Bvh2Node {
   int32_t pad_[2];
 };
 static_assert(sizeof(Bvh2Node) == 64, "Bvh2Node must be half a cache line");
-
-// The structure TraceFast actually walks: the binary scene BVH collapsed to four children per node (the child
-// with the largest box is replaced by its own two children until there are four).  The traversal is bound by the
-// chain of dependent node loads of each ray; a four-wide node halves that chain for the same boxes.  One node =
-// one 128-byte line: two pairs of child boxes laid out like Bvh2Node, then the four child references.
-struct alignas(128) Bvh4Node {
-  float box[4][6];   // child k: lo.xyz rounded down, hi.xyz rounded up; an unused child has lo = +FLT_MAX, hi = -FLT_MAX
-  int32_t child[4];  // >= 0: inner node index; < 0: leaf, ~child = (first_gslot << 3) | count; unused: ~0 (empty leaf)
-  int32_t pad_[4];
-};
-static_assert(sizeof(Bvh4Node) == 128, "Bvh4Node must be one cache line");
-
-// What the device walks: Bvh4Node with the child boxes quantised to 8 bits per plane in the frame of the node
-// (origin = low corner of the union of the child boxes, one power-of-two scale per axis), rounded outwards: 64
-// bytes = four 128-bit loads per node instead of seven.  The traversal is bound by the L1 data pipe (ncu: 70 % of
-// its wavefront rate, issue slots 59 % busy), i.e. by the bytes a ray pulls through L1, and node boxes are most of them.
-struct alignas(64) Bvh4QNode {
-  float origin[3];
-  uint8_t exp[3];     // biased exponent of the per-axis scale: scale = 2^(exp - 127)
-  uint8_t pad0_;
-  uint8_t qlo[3][4];  // [axis][child]: plane = origin + q * scale;  an unused child has qlo = 255, qhi = 0
-  uint8_t qhi[3][4];
-  uint32_t pad1_[2];
-  int32_t child[4];   // as Bvh4Node::child
-};
-static_assert(sizeof(Bvh4QNode) == 64, "Bvh4QNode must be half a cache line");
 
 // One octree node = one 128-byte line.  The 8 children of a node are contiguous (first_child .. +7) and
 // their boxes are exactly {lo,c} / {c,hi} per axis (octtree.cc:61-100), so a node carries the three
@@ -102,10 +79,7 @@ struct FlatScene {
   std::vector<ShadeRec> shade;
   std::vector<BvhRec> bvh;
   std::vector<int32_t> list_order;  // list_order[list_first + k] = slot of the k-th entry in reference order
-  std::vector<Bvh2Node> gnodes;     // binary scene BVH, node 0 = root (empty: no fast traversal)
-  std::vector<Bvh4Node> gnodes4;    // the same tree collapsed to four children per node
-  std::vector<Bvh4QNode> gnodesq;   // gnodes4 with quantised boxes (what the device walks)
-  int32_t gbvh4_depth = 0;
+  std::vector<Bvh2Node> gnodes;     // scene BVH, node 0 = root (empty: no fast traversal)
   std::vector<SlotRec> gslots;      // copies of `slots` in scene-BVH leaf order
   int32_t gbvh_depth = 0;
   int32_t depth = 0;
@@ -125,8 +99,7 @@ struct FlatScene {
 #define MTB_SCENE_BVH_LEAF 2
 #endif
 constexpr int kSceneBvhLeafSize = MTB_SCENE_BVH_LEAF;  // <= 7
-constexpr int kSceneBvhMaxDepth = 88;                   // deeper binary trees (never seen) disable the fast traversal
-constexpr int kFastStackSize = 128;                     // traversal stack of TraceFast: needs 3 * depth of the 4-wide tree
+constexpr int kSceneBvhMaxDepth = 88;                   // deeper trees (never seen) disable the fast traversal
 constexpr int kBvhLeafSize = MTB_BVH_LEAF;      // <= 7 (3-bit count in BvhRec::leaf)
 constexpr int kBvhMinList = MTB_BVH_MIN_LIST;  // shorter lists are scanned linearly
 // measured on B200, C3 frame (megakernel / wavefront ms): leaf 4 min 12: 39.4 / 46.5; leaf 2 min 6: 36.5 / 42.7;

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTraceMain(Devic
     D3 color = Mk(0.0, 0.0, 0.0);
     if (live) {
       double t = 0.0;
-      const int slot = Trace<DBG, kWfBlock>(sc, o, d, CUDART_INF, &t, cnt MTB_TOP_ARGS);
+      const int slot = Trace<DBG>(sc, o, d, CUDART_INF, &t, cnt MTB_TOP_ARGS);
       traced = 1;
       if (rp.n_rays != nullptr) atomicAdd(rp.n_rays + pixel, 1u);
       if (slot < 0) {
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfShadow(DeviceSc
         const double light_distance = Dist(seg_start, lpos);
         double t = 0.0;
         Count<DBG>(cnt, kShadow);
-        const int slot = Trace<DBG, kWfBlock>(sc, to, ldir, light_distance, &t, cnt MTB_TOP_ARGS);
+        const int slot = Trace<DBG>(sc, to, ldir, light_distance, &t, cnt MTB_TOP_ARGS);
         segments++;
         if (slot < 0) break;
         if (t > light_distance) break;

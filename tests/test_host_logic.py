@@ -187,7 +187,7 @@ def test_octree_depth_limit_and_degenerate_inputs(product_lib, oracle_mod):
 
 def test_scene_bvh_is_a_conservative_partition(product_lib, scene_dir):
     """The certified fast traversal relies on two properties of the scene BVH: every triangle
-    sits in exactly one leaf, and every child box of the 4-wide tree (FP32, rounded outwards) contains the exact FP64 boxes of all
+    sits in exactly one leaf, and every child box (FP32, padded and rounded outwards) contains the exact FP64 boxes of all
     triangles below it.  Checked on a generated scene, on scenes smaller than a leaf and on an empty scene."""
     from mythtracer_b200 import MythTracer
     from mythtracer_b200.api import MTL_DTYPE, TRI_DTYPE
@@ -220,7 +220,7 @@ def test_scene_bvh_is_a_conservative_partition(product_lib, scene_dir):
                 return lo[ids].min(axis=0), hi[ids].max(axis=0)
             nd = nodes[ref]
             out_lo, out_hi = np.full(3, np.inf), np.full(3, -np.inf)
-            for box, child in zip(nd["box"], nd["child"].tolist()):
+            for box, child in ((nd["lbox"], int(nd["left"])), (nd["rbox"], int(nd["right"]))):
                 c_lo, c_hi = walk(child, d + 1)
                 assert np.all(box[:3].astype(np.float64) <= c_lo) and np.all(box[3:].astype(np.float64) >= c_hi), "child box must contain its triangles"
                 out_lo, out_hi = np.minimum(out_lo, c_lo), np.maximum(out_hi, c_hi)

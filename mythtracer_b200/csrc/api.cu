@@ -1,5 +1,5 @@
 // C ABI of mythtracer_b200 (see include/mythtracer_b200.h): context, scene residency in HBM, and the
-// launch / gather logic around the kernels of kernels.cu.  No CPU rendering path exists in this file.
+// launch / gather logic around the kernels of megakernel.cu / wavefront.cu.  No CPU rendering path exists in this file.
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -242,7 +242,7 @@ int UploadToDevice(mtb_context *ctx, DeviceState *d) {
   d->scene.texture_dim = d->tex_dims.ptr;
   d->scene.n_materials = (int32_t)ctx->materials.size();
   d->scene.n_nodes = (int32_t)ctx->flat.nodes.size();
-  // the FP32 cull's error bound assumes coordinates of ordinary magnitude (see kernels.cu, CullBox)
+  // the FP32 cull's error bound assumes coordinates of ordinary magnitude (see device_core.cuh, CullBox32 / FastBox)
   const double mac = ctx->flat.max_abs_coord;
   d->scene.cull_radius = (mac >= 0x1p-10 && mac <= 0x1p20) ? (float)mac * 1.0000002f : 0.0f;
   d->scene.max_tri_extent = std::nextafterf((float)ctx->flat.max_tri_extent, INFINITY);

@@ -7,7 +7,7 @@
 // reproduced bit for bit except for pow() (mythtracer.cc:174; CUDA's and glibc's differ by <= 2 ulp).
 //
 // Reference functions replaced here:
-//   OctTree::IntersectRay                      octtree.cc:26-40        -> TraceRegular / TraceLiteral
+//   OctTree::IntersectRay                      octtree.cc:26-40        -> Trace: TraceFast / TraceRegular / TraceLiteral
 //   Node::NodeIntersectRay                     octtree.cc:138-167      -> the slab tests inside them
 //   Node::PrimitiveIntersectRay                octtree.cc:169-257      -> the explicit frame stack
 //   Triangle::IntersectRay                     primitive_triangle.cc:81-143 -> TestSlot*
@@ -18,13 +18,17 @@
 //   MythTracer::V3DtoRGB                       mythtracer.cc:235-241   -> Quantize
 //   the OpenMP row loop                        mythtracer.cc:292-305   -> the CUDA grid (8x8 pixel tiles)
 //
-// Two traversals exist.  Rays whose direction has a zero / non-finite component ("irregular": the NaN
-// producing cases of SURVEY.md fact 9) take TraceLiteral, a literal restatement including std::min/max
-// NaN behaviour and libstdc++'s insertion sort.  All other rays take TraceRegular, which may use any
-// evaluation order that yields the same VALUES when no NaN can occur: sign-selected near/far planes
-// instead of pairwise min/max, the three shared planes of the eight children, skipping empty subtrees,
-// and a conservative threaded BVH over long node lists whose candidates are then decided by the exact
-// reference tests with the reference's tie rule (later list entry wins on equal t).
+// Three traversals exist, chosen per ray in Trace().  Rays whose direction has a zero / non-finite component
+// ("irregular": the NaN producing cases of SURVEY.md fact 9) take TraceLiteral, a literal restatement of the
+// octree recursion including std::min/max NaN behaviour and libstdc++'s insertion sort.  All other rays first
+// take TraceFast, a certified closest-hit search over one BVH of all triangles (conservative FP32 boxes, the
+// exact FP64 reference tests at the leaves, a forward error bound on every accepted hit); if it cannot certify
+// that its answer is the recursion's - two hits closer together than their error bounds - the ray is decided by
+// TraceRegular, the octree recursion itself (explicit frame stack, reference order), which may use any
+// evaluation order that yields the same VALUES when no NaN can occur: sign-selected near/far planes instead of
+// pairwise min/max, the three shared planes of the eight children, skipping empty subtrees, and a conservative
+// threaded BVH over long node lists whose candidates are decided by the exact reference tests with the
+// reference's tie rule (later list entry wins on equal t).  DESIGN.md section 4 has the argument.
 #pragma once
 #include <math_constants.h>
 

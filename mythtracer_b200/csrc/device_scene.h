@@ -1,4 +1,4 @@
-// Structures shared by the host API (api.cu) and the kernels (kernels.cu).
+// Structures shared by the host API (api.cu) and the kernels (megakernel.cu, wavefront.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -44,7 +44,7 @@ struct ShadeFrame {
 // same rays are traced by the same code, only by different threads.
 constexpr int kPackThreads = 128;
 constexpr int kPackTileW = 16;
-constexpr int kModeTile = 0, kModePersist = 1, kModePack = 2;
+constexpr int kModeTile = 0, kModePersist = 1, kModePack = 2, kModeSync = 3;
 
 template <bool DBG, int MODE>
 __global__ void __launch_bounds__(MODE == kModePack ? kPackThreads : kBlockThreads,
@@ -52,6 +52,12 @@ __global__ void __launch_bounds__(MODE == kModePack ? kPackThreads : kBlockThrea
     RenderMega(DeviceScene sc, RenderParams rp) {
   constexpr bool PERSIST = MODE == kModePersist;
   constexpr bool PACK = MODE == kModePack;
+  // SYNC: the tile-per-block form with the warp re-converged by force at the top of every iteration: a lane whose
+  // pixel is finished idles in the loop until the whole warp is, so that __syncwarp() can gather all 32 lanes in
+  // front of the Trace call.  (Per-pixel ray counts are balanced - a warp's lanes need 93 % of its maximum on C3 -
+  // yet ncu shows 14 of 32 lanes per instruction: without the barrier the lanes that come back from the shadow
+  // branch and from the secondary-ray branch walk the traversal as separate groups.)
+  constexpr bool SYNC = MODE == kModeSync;
   __shared__ double s_ray[PACK ? 7 * kPackThreads : 1];   // o.xyz, d.xyz, t_limit of the rays of this iteration
   __shared__ double s_res_t[PACK ? kPackThreads : 1];
   __shared__ int s_res_slot[PACK ? kPackThreads : 1];
@@ -100,11 +106,28 @@ __global__ void __launch_bounds__(MODE == kModePack ? kPackThreads : kBlockThrea
     D3 final_color = Mk(0, 0, 0);
 
     for (;;) {
+      if (SYNC) {
+        __syncwarp();
+        if (__all_sync(0xffffffffu, drawn && !active)) break;
+      }
       if (!active) {
         // ---- next pixel of this lane ----
         unsigned item;
         bool fresh = !PACK;  // a new pixel was taken: set up its primary ray
-        if (PACK) {
+        if (SYNC) {
+          fresh = false;
+          if (!drawn) {
+            drawn = true;
+            item = blockIdx.x * (unsigned)kBlockThreads + threadIdx.x;
+            const int pos = (int)(item >> 6);
+            tile_id = rp.tile_order != nullptr ? rp.tile_order[pos] : pos;
+            const int strip = rp.strip_first + (tile_id / rp.tiles_x) * rp.strip_stride;
+            px = (tile_id % rp.tiles_x) * kTile + (int)(item & 7u);
+            py = strip * kTile + (int)((item >> 3) & 7u);
+            active = fresh = px < rp.chunk_w && py < rp.chunk_h;
+          }
+          item = 0;
+        } else if (PACK) {
           if (!drawn) {
             drawn = true;
             const int pos = (int)blockIdx.x;
@@ -128,7 +151,7 @@ __global__ void __launch_bounds__(MODE == kModePack ? kPackThreads : kBlockThrea
           drawn = true;
           item = blockIdx.x * (unsigned)kBlockThreads + threadIdx.x;
         }
-        if (!PACK) {
+        if (!PACK && !SYNC) {
           if (item >= rp.n_items) break;
           const int pos = (int)(item >> 6);
           tile_id = rp.tile_order != nullptr ? rp.tile_order[pos] : pos;
@@ -203,6 +226,10 @@ __global__ void __launch_bounds__(MODE == kModePack ? kPackThreads : kBlockThrea
         if (!active) continue;
         slot = s_res_slot[mine];
         t = s_res_t[mine];
+      } else if (SYNC) {
+        __syncwarp();
+        if (!active) continue;
+        slot = Trace<DBG>(sc, to, td, shadow_mode ? light_distance : CUDART_INF, &t, cnt MTB_TOP_ARGS);
       } else {
         slot = Trace<DBG>(sc, to, td, shadow_mode ? light_distance : CUDART_INF, &t, cnt MTB_TOP_ARGS);
       }
@@ -419,7 +446,7 @@ __global__ void __launch_bounds__(MODE == kModePack ? kPackThreads : kBlockThrea
       // what this tile cost, for the next frame's launch order
       if (PERSIST && rp.tile_cost != nullptr) atomicAdd(rp.tile_cost + tile_id, n_rays);
       active = false;
-      if (PACK) shadow_mode = false;
+      if (PACK || SYNC) shadow_mode = false;
     }
   }
 
@@ -549,6 +576,12 @@ void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp_in, int n_bl
       RenderMega<true, kModePersist><<<grid, kBlockThreads, 0, stream>>>(sc, rp);
     } else {
       RenderMega<false, kModePersist><<<grid, kBlockThreads, 0, stream>>>(sc, rp);
+    }
+  } else if (mode == kModeSync) {
+    if (debug_build) {
+      RenderMega<true, kModeSync><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);
+    } else {
+      RenderMega<false, kModeSync><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);
     }
   } else if (debug_build) {
     RenderMega<true, kModeTile><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);

@@ -138,6 +138,30 @@ class MythTracer {
   }
 
   // ---- extensions ----
+  // Frame sequencing: enqueue a whole-frame render into `pinned_out` (w * h * 3 bytes from AllocFrame) and return
+  // without waiting; Wait() blocks until it is there.  With two frames in rotation the caller writes frame k while
+  // frame k+1 renders (apps/mythtracer_local_b200.cc).
+  bool RayTraceAsync(int image_width, int image_height, Camera *camera, uint8_t *pinned_out) {
+    if (!was_scene_finalized) {
+      puts("Finalizing tree.");
+      if (!scene.tree.Finalize(&scene.materials, &scene.textures)) return false;
+      was_scene_finalized = true;
+    }
+    mtb_context *ctx = scene.tree.context();
+    if (mtb_set_lights(ctx, reinterpret_cast<const mtb_light *>(scene.lights.data()), (int32_t)scene.lights.size()) != MTB_OK) {
+      return false;
+    }
+    const mtb_camera cam = camera->AsMtb();
+    const int rc = mtb_render_chunk_async(ctx, &cam, image_width, image_height, 0, 0, image_width, image_height,
+                                          max_recursion_level, pinned_out);
+    if (rc != MTB_OK) fprintf(stderr, "error: %s\n", mtb_last_error(ctx));
+    return rc == MTB_OK;
+  }
+  bool Wait() { return mtb_wait(scene.tree.context()) == MTB_OK; }
+  static uint8_t *AllocFrame(int image_width, int image_height) {
+    return static_cast<uint8_t *>(mtb_host_alloc((size_t)image_width * image_height * 3));
+  }
+  static void FreeFrame(uint8_t *p) { mtb_host_free(p); }
   void SetMaxRecursionLevel(int level) { max_recursion_level = level; }
   void SetDevices(const std::vector<int> &devices) { scene.tree.SetDevices(devices); }
   void SetFlags(uint32_t flags) { scene.tree.SetFlags(flags); }

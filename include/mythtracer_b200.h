@@ -193,6 +193,20 @@ int mtb_render_chunk(mtb_context *ctx, const mtb_camera *cam, int image_w, int i
                      int chunk_w, int chunk_h, int max_depth, uint8_t *rgb_out, mtb_debug *dbg_out,
                      const mtb_taps *taps, mtb_stats *stats);
 
+/* Frame sequencing (reference main_local.cc:51-149 renders, then writes, then renders ...): the same render as
+ * mtb_render_chunk, enqueued without waiting -- the call returns as soon as the kernels and the device->host copy
+ * of the frame are queued (megakernel pipeline; the wavefront pipeline still reads one counter per level).  rgb_out
+ * must stay valid until mtb_wait returns and should come from mtb_host_alloc (pinned memory) for the copy to be
+ * asynchronous.  With two such buffers a driver writes frame k to disk while frame k+1 renders
+ * (apps/mythtracer_local_b200.cc). */
+int mtb_render_chunk_async(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h, int chunk_x, int chunk_y,
+                           int chunk_w, int chunk_h, int max_depth, uint8_t *rgb_out);
+/* Waits for everything queued on the context's devices. */
+int mtb_wait(mtb_context *ctx);
+/* Pinned host memory for mtb_render_chunk_async (NULL when the allocation fails). */
+void *mtb_host_alloc(size_t bytes);
+void mtb_host_free(void *p);
+
 /* Same render, result left in DEVICE memory of device 0 (d_rgb: chunk_w*chunk_h*3 bytes); enqueued on
  * `stream` (a cudaStream_t of device 0; NULL = the context's own stream) without synchronising when the
  * context has one device.  This is the entry bench.py times for the HBM-resident figure. */

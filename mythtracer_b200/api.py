@@ -70,7 +70,7 @@ EXPORTED_SYMBOLS = [
     "mtb_create", "mtb_create_host", "mtb_destroy", "mtb_last_error", "mtb_device_count", "mtb_scene_upload", "mtb_load_obj",
     "mtb_set_lights", "mtb_scene_info", "mtb_scene_read", "mtb_scene_material_name", "mtb_scene_texture_name", "mtb_scene_texture", "mtb_load_mtl",
     "mtb_scene_triangle_nodes", "mtb_scene_bvh", "mtb_set_flags", "mtb_set_partition", "mtb_render_chunk",
-    "mtb_render_chunk_device", "mtb_read_counters", "mtb_launch_count", "mtb_pipeline_in_use", "mtb_intersect_rays", "mtb_camera_sensor", "mtb_version",
+    "mtb_render_chunk_device", "mtb_render_chunk_async", "mtb_wait", "mtb_host_alloc", "mtb_host_free", "mtb_read_counters", "mtb_launch_count", "mtb_pipeline_in_use", "mtb_intersect_rays", "mtb_camera_sensor", "mtb_version",
 ]
 
 
@@ -383,6 +383,22 @@ class MythTracer:
         depth = np.zeros(n, np.int32)
         self._check(self._lib.mtb_scene_triangle_nodes(self._ctx, _ptr(box), _ptr(depth)), "mtb_scene_triangle_nodes")
         return box, depth
+
+    def LoadMtl(self, path: str) -> bool:
+        """MtlFileReader::ReadMtlFile (objreader.cc:472-549): materials and their map_Ka textures only."""
+        return self._lib.mtb_load_mtl(self._ctx, os.fsencode(path)) == 0
+
+    def texture_name(self, index: int) -> str:
+        name = self._lib.mtb_scene_texture_name(self._ctx, index)
+        return name.decode() if name is not None else ""
+
+    def texture(self, index: int) -> np.ndarray:
+        """The decoded RGBA32 texels of texture `index` as the loader keeps them: uint8 [height, width, 4]."""
+        t = _TextureStruct()
+        self._check(self._lib.mtb_scene_texture(self._ctx, index, ctypes.byref(t)), "mtb_scene_texture")
+        n = t.width * t.height * 4
+        buf = (ctypes.c_uint8 * n).from_address(t.rgba)
+        return np.frombuffer(buf, np.uint8).reshape(t.height, t.width, 4).copy()
 
     def scene_bvh(self):
         """mtb_scene_bvh: (nodes as a structured array, depth, leaf_order = insertion index per leaf position)."""

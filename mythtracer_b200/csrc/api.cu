@@ -959,6 +959,38 @@ int mtb_render_chunk(mtb_context *ctx, const mtb_camera *cam, int image_w, int i
                     dbg_out, taps, stats, true);
 }
 
+int mtb_render_chunk_async(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h, int chunk_x, int chunk_y,
+                           int chunk_w, int chunk_h, int max_depth, uint8_t *rgb_out) {
+  if (ctx != nullptr && rgb_out == nullptr) {
+    ctx->err = "rgb_out is NULL";
+    return MTB_ERR_ARG;
+  }
+  return RenderImpl(ctx, cam, image_w, image_h, chunk_x, chunk_y, chunk_w, chunk_h, max_depth, rgb_out, nullptr, nullptr,
+                    nullptr, nullptr, nullptr, false);
+}
+
+int mtb_wait(mtb_context *ctx) {
+  if (ctx == nullptr) return MTB_ERR_ARG;
+  for (DeviceState &d : ctx->dev) {
+    MTB_CUDA(ctx, cudaSetDevice(d.device));
+    MTB_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  }
+  return MTB_OK;
+}
+
+void *mtb_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes == 0 ? 1 : bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void mtb_host_free(void *p) {
+  if (p != nullptr) cudaFreeHost(p);
+}
+
 int mtb_render_chunk_device(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h, int chunk_x,
                             int chunk_y, int chunk_w, int chunk_h, int max_depth, void *d_rgb, void *stream,
                             mtb_stats *stats) {

@@ -1,4 +1,4 @@
-// Host-side OBJ + MTL (+ PPM texture) reader with the observable behaviour of the reference loader
+// Host-side OBJ + MTL (+ texture) reader with the observable behaviour of the reference loader
 // (reference VerStarting/objreader.cc), so that the same files give the same triangles, in the same
 // order, with the same debug line numbers:
 //   * lines are consumed in 127-byte pieces (char line[128] + fgets, objreader.cc:233-235) and every piece
@@ -12,7 +12,7 @@
 //   * `usemtl` of an unknown name selects "no material" and parsing goes on (objreader.cc:85-90);
 //   * MTL keys read: newmtl Ka Kd Ks Ns Ni Tr Tf Refl map_Ka; d illum Ke map_Kd are ignored
 //     (objreader.cc:487-503); a texture that fails to load fails the whole load (objreader.cc:467-469).
-// Texture files are decoded from binary PPM (P6, maxval 255) into RGBA32: SDL2_image, which the reference
+// Texture files are decoded by image_decode.cc (PPM, PNG, BMP, TGA -> RGBA32): SDL2_image, which the reference
 // uses (texture.cc:60-109), is not available offline.
 #include <cstdio>
 #include <cstdlib>
@@ -95,47 +95,7 @@ inline bool ScanFaceToken(const char *tok, int *v, int *vt, int *vn) {
 
 inline bool IsSpace(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\v' || c == '\f' || c == '\r'; }
 
-bool ReadPpmHeaderInt(FILE *f, int *out) {
-  int c = fgetc(f);
-  for (;;) {
-    while (c == ' ' || c == '\t' || c == '\r' || c == '\n') c = fgetc(f);
-    if (c != '#') break;
-    while (c != '\n' && c != EOF) c = fgetc(f);
-  }
-  if (c < '0' || c > '9') return false;
-  long v = 0;
-  while (c >= '0' && c <= '9') {
-    v = v * 10 + (c - '0');
-    if (v > 1000000) return false;
-    c = fgetc(f);
-  }
-  *out = (int)v;
-  return true;
-}
 
-bool LoadPpm(const std::string &path, LoadedTexture *tex) {
-  FileCloser fc{fopen(path.c_str(), "rb")};
-  if (fc.f == nullptr) return false;
-  int w = 0, h = 0, maxval = 0;
-  if (fgetc(fc.f) != 'P' || fgetc(fc.f) != '6' || !ReadPpmHeaderInt(fc.f, &w) || !ReadPpmHeaderInt(fc.f, &h) ||
-      !ReadPpmHeaderInt(fc.f, &maxval) || maxval != 255) {
-    return false;
-  }
-  // the reference's sanity window (texture.cc:74-78)
-  if (w <= 0 || h <= 0 || w > 30000 || h > 30000) return false;
-  std::vector<uint8_t> rgb((size_t)w * (size_t)h * 3);
-  if (fread(rgb.data(), 1, rgb.size(), fc.f) != rgb.size()) return false;
-  tex->width = w;
-  tex->height = h;
-  tex->rgba.resize((size_t)w * (size_t)h * 4);
-  for (size_t i = 0, n = (size_t)w * (size_t)h; i < n; i++) {
-    tex->rgba[i * 4 + 0] = rgb[i * 3 + 0];
-    tex->rgba[i * 4 + 1] = rgb[i * 3 + 1];
-    tex->rgba[i * 4 + 2] = rgb[i * 3 + 2];
-    tex->rgba[i * 4 + 3] = 255;
-  }
-  return true;
-}
 
 class MtlParser {
  public:
@@ -235,7 +195,7 @@ class MtlParser {
       }
       if (tex < 0) {
         LoadedTexture t;
-        if (!LoadPpm(Join(dir_, fname), &t)) {
+        if (!DecodeImageFile(Join(dir_, fname), &t)) {
           *err_ = std::string("cannot load texture \"") + fname + "\"";
           return false;
         }

@@ -112,7 +112,7 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
 // Camera::GetSensor / Sensor::Reset (camera.cc:17-63): out9 = start_point, delta_scanline, delta_pixel.
 void ComputeSensor(const mtb_camera &cam, int image_w, int image_h, double out9[9]);
 
-// ObjFileReader::ReadObjFile + MtlFileReader::ReadMtlFile (objreader.cc:201-274,472-549) + a PPM stand-in
+// ObjFileReader::ReadObjFile + MtlFileReader::ReadMtlFile (objreader.cc:201-274,472-549) + own decoders
 // for Texture::LoadFromFile (texture.cc:60-109; SDL2_image is not available offline).
 struct LoadedTexture {
   int32_t width = 0, height = 0;
@@ -125,6 +125,9 @@ struct LoadedScene {
   std::vector<LoadedTexture> textures;
   std::vector<std::string> texture_names;
 };
+// Texture::LoadFromFile's decoding step (texture.cc:60-99) without SDL2_image: PPM, PNG, BMP, TGA -> RGBA32
+// (image_decode.cc).
+bool DecodeImageFile(const std::string &path, LoadedTexture *tex);
 bool LoadObjFile(const char *path, LoadedScene *scene, std::string *err);
 bool LoadMtlFile(const char *path, LoadedScene *scene, std::string *err);
 

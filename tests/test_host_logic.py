@@ -243,3 +243,120 @@ def test_scene_bvh_is_a_conservative_partition(product_lib, scene_dir):
     empty = MythTracer(host_only=True)
     empty.upload(np.zeros(0, TRI_DTYPE), np.zeros(0, MTL_DTYPE))
     check(empty, np.zeros(0, TRI_DTYPE))
+
+
+def _png_bytes(img, color_type, depth=8, filters=(0, 1, 2, 3, 4), palette=None, level=6, width=None, fixed=False):
+    """Minimal PNG writer (zlib from the standard library) with a chosen scanline filter per row."""
+    import struct, zlib
+    h, w = img.shape[:2]
+    rows = img.reshape(h, -1).astype(np.uint8)
+    bpp = max(1, rows.shape[1] // w) if depth >= 8 else 1
+    w = width or w
+    raw = bytearray()
+    prev = np.zeros(rows.shape[1], np.int32)
+    for y in range(h):
+        cur = rows[y].astype(np.int32)
+        f = filters[y % len(filters)]
+        a = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]])
+        c = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]])
+        if f == 0:
+            pred = np.zeros_like(cur)
+        elif f == 1:
+            pred = a
+        elif f == 2:
+            pred = prev
+        elif f == 3:
+            pred = (a + prev) // 2
+        else:
+            p = a + prev - c
+            pa, pb, pc = np.abs(p - a), np.abs(p - prev), np.abs(p - c)
+            pred = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, prev, c))
+        raw.append(f)
+        raw += ((cur - pred) & 255).astype(np.uint8).tobytes()
+        prev = cur
+
+    def chunk(tag, body):
+        return struct.pack(">I", len(body)) + tag + body + struct.pack(">I", zlib.crc32(tag + body) & 0xffffffff)
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, color_type, 0, 0, 0))
+    if palette is not None:
+        out += chunk(b"PLTE", palette.astype(np.uint8).tobytes())
+    co = zlib.compressobj(level, zlib.DEFLATED, 15, 8, zlib.Z_FIXED if fixed else zlib.Z_DEFAULT_STRATEGY)
+    comp = co.compress(bytes(raw)) + co.flush()
+    out += chunk(b"IDAT", comp[:len(comp) // 2]) + chunk(b"IDAT", comp[len(comp) // 2:]) + chunk(b"IEND", b"")
+    return out
+
+
+def test_texture_decoders_give_the_same_texels(product_lib, tmp_path):
+    """PPM, PNG (RGB / RGBA / grey / palette, every scanline filter, stored / fixed / dynamic deflate
+    blocks), BMP (24 / 32 bits, both row orders) and TGA (raw / run-length, both origins) files of one image must
+    all load to the same RGBA32 texels through MtlFileReader's map_Ka path."""
+    import struct
+    from mythtracer_b200 import MythTracer, MythTracerError
+    rng = np.random.default_rng(3)
+    h, w = 37, 53
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    img[5:20, 7:30] = (200, 10, 60)            # flat areas: long deflate matches and TGA runs
+    img[25:, :] = img[25:26, :]
+    files = {}
+    files["a.ppm"] = b"P6\n# comment\n%d %d\n255\n" % (w, h) + img.tobytes()
+    files["b.png"] = _png_bytes(img, 2)
+    rgba = np.dstack([img, rng.integers(0, 256, (h, w, 1), dtype=np.uint8)])
+    files["c.png"] = _png_bytes(rgba, 6, level=0)                       # stored blocks
+    files["d.png"] = _png_bytes(img, 2, filters=(4,), fixed=True)       # fixed-Huffman blocks, Paeth only
+    rgb16 = np.dstack([img[..., c // 2] if c % 2 == 0 else rng.integers(0, 256, (h, w), dtype=np.uint8) for c in range(6)])
+    files["e.png"] = _png_bytes(rgb16, 2, depth=16)                     # 16 bits: the high byte is the texel
+    bgr = img[..., ::-1]
+    pad = (-w * 3) % 4
+    rows_up = b"".join(bgr[y].tobytes() + b"\0" * pad for y in range(h - 1, -1, -1))
+    hdr = lambda bits, height, size: b"BM" + struct.pack("<IHHI", 54 + size, 0, 0, 54) + struct.pack("<IiiHHIIiiII", 40, w, height, 1, bits, 0, size, 2835, 2835, 0, 0)
+    files["f.bmp"] = hdr(24, h, len(rows_up)) + rows_up
+    bgra = np.dstack([bgr, np.full((h, w, 1), 255, np.uint8)])
+    files["g.bmp"] = hdr(32, -h, w * h * 4) + bgra.tobytes()            # top-down, 32 bits
+    tga_hdr = lambda typ, bits, desc: struct.pack("<BBBHHBHHHHBB", 0, 0, typ, 0, 0, 0, 0, 0, w, h, bits, desc)
+    files["h.tga"] = tga_hdr(2, 24, 0x20) + bgr.tobytes()               # raw, top-left origin
+    rle = bytearray()
+    flat = bgr[::-1].reshape(-1, 3)                                     # bottom-left origin
+    i = 0
+    while i < len(flat):
+        run = 1
+        while i + run < len(flat) and run < 128 and np.array_equal(flat[i + run], flat[i]):
+            run += 1
+        if run > 1:
+            rle.append(128 | (run - 1))
+            rle += flat[i].tobytes()
+        else:
+            lit = 1
+            while i + lit < len(flat) and lit < 128 and not np.array_equal(flat[i + lit], flat[i + lit - 1]):
+                lit += 1
+            run = lit
+            rle.append(lit - 1)
+            rle += flat[i:i + lit].tobytes()
+        i += run
+    files["i.tga"] = tga_hdr(10, 24, 0x00) + bytes(rle)
+    grey = img[..., 0]
+    files["j.png"] = _png_bytes(grey, 0)
+    pal = rng.integers(0, 256, (16, 3), dtype=np.uint8)
+    idx = rng.integers(0, 16, (h, w), dtype=np.uint8)
+    packed = np.zeros((h, (w + 1) // 2), np.uint8)
+    packed[:, :w // 2] = (idx[:, 0:w - 1:2] << 4) | idx[:, 1::2]
+    if w % 2:
+        packed[:, -1] = idx[:, -1] << 4
+    files["k.png"] = _png_bytes(packed, 3, depth=4, palette=pal, filters=(0, 2), width=w)
+    for name, data in files.items():
+        (tmp_path / name).write_bytes(data)
+    mtl = "".join("newmtl m%s\nKa 1 1 1\nmap_Ka %s\n" % (n[0], n) for n in sorted(files))
+    (tmp_path / "all.mtl").write_text(mtl)
+    mt = MythTracer(host_only=True)
+    assert mt.LoadMtl(str(tmp_path / "all.mtl")), mt.last_error()
+    tex = {mt.texture_name(i): mt.texture(i) for i in range(mt.scene_info()["n_textures"])}
+    assert sorted(tex) == sorted(files)
+    for name in "abdefghi":
+        got = tex[[n for n in files if n[0] == name][0]]
+        assert got.shape == (h, w, 4) and np.array_equal(got[..., :3], img), name
+    assert np.array_equal(tex["c.png"], rgba)
+    assert np.array_equal(tex["j.png"][..., :3], np.dstack([grey] * 3))
+    assert np.array_equal(tex["k.png"][..., :3], pal[idx])
+    # interlaced or truncated files fail the whole load, as an undecodable texture does upstream (objreader.cc:467-469)
+    (tmp_path / "bad.png").write_bytes(files["b.png"][:200])
+    (tmp_path / "bad.mtl").write_text("newmtl x\nmap_Ka bad.png\n")
+    assert not MythTracer(host_only=True).LoadMtl(str(tmp_path / "bad.mtl"))

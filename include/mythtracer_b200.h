@@ -126,6 +126,7 @@ typedef struct {
 #define MTB_FLAG_RAY_SORT 8u     /* wavefront: counting-sort every queue by origin cell + direction octant (measured: no gain) */
 #define MTB_FLAG_EXACT_OCTREE 128u /* every regular ray walks the octree in the reference's recursion order (no certified fast traversal) */
 #define MTB_FLAG_PACKING 256u /* megakernel: 16x8 tiles per 128-thread block, the rays of an iteration are handed to the first threads of the block (A/B; measured slower: fewer tracing warps hide less latency) */
+#define MTB_FLAG_RESUME 1024u /* megakernel: suspendable walks -- finished lanes shade and start their next ray while longer rays of the warp are parked */
 #define MTB_FLAG_WARP_SYNC 512u /* megakernel: finished lanes idle in the loop so that __syncwarp() re-converges the warp in front of every Trace call */
 #define MTB_FLAG_PERSISTENT 64u /* megakernel: persistent warps whose lanes draw their next pixel from a counter instead of one 8x8 tile per block (A/B; measured slower: the refilled lanes trace incoherent rays) */
 #define MTB_FLAG_NO_TILE_ORDER 32u /* megakernel: always launch tiles in scanline order (A/B of the cost-aware launch order) */

@@ -40,6 +40,7 @@ MTB_FLAG_PERSISTENT = 64
 MTB_FLAG_EXACT_OCTREE = 128
 MTB_FLAG_PACKING = 256
 MTB_FLAG_WARP_SYNC = 512
+MTB_FLAG_RESUME = 1024
 MAX_RECURSION_LEVEL = 5  # reference mythtracer.h:11 (a run-time argument here)
 
 TRI_DTYPE = np.dtype([("vertex", "f8", (9,)), ("normal", "f8", (9,)), ("uvw", "f8", (9,)),

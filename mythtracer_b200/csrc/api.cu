@@ -597,7 +597,7 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
       if (wrc != MTB_OK) return wrc;
     } else {
       // launch form: one 8x8 tile per block unless one of the A/B forms is asked for
-      const int mode = (ctx->flags & MTB_FLAG_PERSISTENT) != 0 ? 1 : ((ctx->flags & MTB_FLAG_PACKING) != 0 ? 2 : ((ctx->flags & MTB_FLAG_WARP_SYNC) != 0 ? 3 : 0));
+      const int mode = (ctx->flags & MTB_FLAG_PERSISTENT) != 0 ? 1 : ((ctx->flags & MTB_FLAG_PACKING) != 0 ? 2 : ((ctx->flags & MTB_FLAG_RESUME) != 0 ? 4 : ((ctx->flags & MTB_FLAG_WARP_SYNC) != 0 ? 3 : 0)));
       p.tiles_x = (chunk_w + mtb::MegaTileWidth(mode) - 1) / mtb::MegaTileWidth(mode);
       const int mblocks = OwnedStrips(plan, owner) * p.tiles_x;
       if (mblocks > 0 && (ctx->flags & MTB_FLAG_NO_TILE_ORDER) == 0) {

@@ -766,6 +766,163 @@ __device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Resumable form of the same traversals (megakernel, MTB_FLAG_RESUME).  ncu: 30 of 32 lanes enter Trace, 14 are
+// alive per instruction inside the node loop - a warp waits for its longest ray (mean 34 node visits).  Here the
+// walk of a ray can be SUSPENDED: all 32 lanes of a warp call TraceRun together, lanes with a ray in flight walk,
+// and the loop ends as soon as at most half of the rays that were in flight at entry are still walking.  The
+// finished lanes then consume their result (TraceEnd: the same certification and fallbacks as Trace), shade, start
+// their next ray (TraceBegin) and come back with the suspended ones.  What is computed per ray is unchanged.
+// ---------------------------------------------------------------------------------------------------
+struct FastWalk {
+  Ray r;
+  float nox, noy, noz;
+  FastBest fb;
+  int node;  // kFastExit: no walk in flight (finished, or a ray that takes one of the other traversals)
+  int sp;
+  int kind;  // 0: certified fast walk, 1: exact recursion (ray outside the FP32 model / no scene BVH), 2: literal
+};  // (the traversal stack is a separate array: a struct with a dynamically indexed member stays in local memory)
+
+template <bool DBG>
+__device__ __forceinline__ void TraceBegin(const DeviceScene &sc, const D3 &o, const D3 &d, double t_limit, FastWalk *w,
+                                           unsigned long long *cnt) {
+  Ray &r = w->r;
+  r.o = o;
+  r.d = d;
+  r.inv = Mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
+  r.sx = r.inv.x < 0.0;
+  r.sy = r.inv.y < 0.0;
+  r.sz = r.inv.z < 0.0;
+  r.cull32 = false;
+  Count<DBG>(cnt, kRays);
+  w->node = kFastExit;
+  w->sp = 0;
+  const bool regular = isfinite(r.inv.x) && isfinite(r.inv.y) && isfinite(r.inv.z) && r.inv.x != 0.0 &&
+                       r.inv.y != 0.0 && r.inv.z != 0.0 && isfinite(o.x) && isfinite(o.y) && isfinite(o.z);
+  if (!regular) {
+    w->kind = 2;
+    return;
+  }
+  const float R = sc.cull_radius;
+  const double ao = fmax(fmax(fabs(o.x), fabs(o.y)), fabs(o.z));
+  const double ai_max = fmax(fmax(fabs(r.inv.x), fabs(r.inv.y)), fabs(r.inv.z));
+  const double ai_min = fmin(fmin(fabs(r.inv.x), fabs(r.inv.y)), fabs(r.inv.z));
+  r.cull32 = R > 0.0f && ao <= 8.0 * (double)R && ai_max <= 0x1p100 && ai_min >= 0x1p-100;
+  r.ox = (float)o.x;
+  r.oy = (float)o.y;
+  r.oz = (float)o.z;
+  r.ix = (float)r.inv.x;
+  r.iy = (float)r.inv.y;
+  r.iz = (float)r.inv.z;
+  const float pr = R * 9.5367431640625e-07f;  // 2^-20 * R
+  r.px = pr * fabsf(r.ix);
+  r.py = pr * fabsf(r.iy);
+  r.pz = pr * fabsf(r.iz);
+  if (sc.gnodes == nullptr || !r.cull32) {
+    w->kind = 1;
+    return;
+  }
+  w->kind = 0;
+  w->nox = -(r.ox * r.ix);
+  w->noy = -(r.oy * r.iy);
+  w->noz = -(r.oz * r.iz);
+  w->fb.t = 0.0;
+  w->fb.e = 0.0;
+  w->fb.lo2 = CUDART_INF;
+  w->fb.slot = -1;
+  w->fb.prune = LimitPrune(sc, r, t_limit);
+  w->node = 0;
+}
+
+// Must be called by all 32 lanes of the warp (lanes without a walk in flight pass node == kFastExit).  `park` is
+// where a walk lives between calls; it must be an OPAQUE pointer (see RenderMega) so that the state is copied
+// into registers here, for the duration of the loop, and written back once - left to itself the register
+// allocator keeps the pixel state in registers and reloads the walk from local memory at every node.
+template <bool DBG>
+__device__ __noinline__ void TraceRun(const DeviceScene &sc, FastWalk *park, unsigned long long *stack, unsigned long long *cnt) {
+  int node = park->node;
+  const int stop_at = __popc(__ballot_sync(0xffffffffu, node != kFastExit)) >> 1;
+  if (__popc(__ballot_sync(0xffffffffu, node != kFastExit)) <= stop_at) return;  // nobody walks
+  // only what the node loop needs lives in registers; the FP64 ray and the best hit are read from the parked walk
+  // at the leaves
+  Ray rl;
+  rl.sx = park->r.sx;
+  rl.sy = park->r.sy;
+  rl.sz = park->r.sz;
+  rl.ix = park->r.ix;
+  rl.iy = park->r.iy;
+  rl.iz = park->r.iz;
+  const float nox = park->nox, noy = park->noy, noz = park->noz;
+  float prune = park->fb.prune;
+  int sp = park->sp;
+  for (;;) {
+    if (__popc(__ballot_sync(0xffffffffu, node != kFastExit)) <= stop_at) break;
+    if (node == kFastExit) continue;
+    while (node >= 0) {
+      const float4 *q = reinterpret_cast<const float4 *>(sc.gnodes + node);
+      const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+      const int2 kids = __ldg(reinterpret_cast<const int2 *>(q + 3));
+      Count<DBG>(cnt, kBvh, 2);
+      float tl, tr;
+      const bool hl = FastBox(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, rl, nox, noy, noz, prune, &tl);
+      const bool hr = FastBox(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, rl, nox, noy, noz, prune, &tr);
+      if (hl && hr) {
+        const bool right_first = tr < tl;
+        stack[sp++] = ((unsigned long long)__float_as_uint(right_first ? tl : tr) << 32) | (unsigned)(right_first ? kids.x : kids.y);
+        node = right_first ? kids.y : kids.x;
+      } else if (hl) {
+        node = kids.x;
+      } else if (hr) {
+        node = kids.y;
+      } else {
+        node = kFastExit;
+        while (sp > 0) {
+          const unsigned long long top = stack[--sp];
+          if (__uint_as_float((unsigned)(top >> 32)) <= prune) {
+            node = (int)(unsigned)top;
+            break;
+          }
+        }
+      }
+    }
+    if (node != kFastExit) {
+      const unsigned leaf = ~(unsigned)node;
+      Ray rr = park->r;
+      FastBest fb = park->fb;
+      for (unsigned s = leaf >> 3, e = s + (leaf & 7u); s < e; s++) TestSlotFast<DBG>(sc.gslots + s, rr, &fb, cnt);
+      park->fb = fb;
+      prune = fb.prune;
+      node = kFastExit;
+      while (sp > 0) {
+        const unsigned long long top = stack[--sp];
+        if (__uint_as_float((unsigned)(top >> 32)) <= prune) {
+          node = (int)(unsigned)top;
+          break;
+        }
+      }
+    }
+  }
+  park->node = node;
+  park->sp = sp;
+}
+
+// Result of a finished walk (w->node == kFastExit): same certification and fallbacks as Trace().
+template <bool DBG>
+__device__ __forceinline__ int TraceEnd(const DeviceScene &sc, FastWalk *w, double *t_out, unsigned long long *cnt MTB_TOP_PARAMS) {
+  if (w->kind == 0) {
+    const bool ambiguous = w->fb.slot >= 0 && w->fb.lo2 <= w->fb.t + w->fb.e;
+    if (!ambiguous) {
+      Count<DBG>(cnt, kFast);
+      *t_out = w->fb.t;
+      return w->fb.slot;
+    }
+    Count<DBG>(cnt, kFallback);
+    return TraceRegularCold<DBG>(sc, w->r, t_out, cnt MTB_TOP_ARGS);
+  }
+  if (w->kind == 1) return TraceRegularCold<DBG>(sc, w->r, t_out, cnt MTB_TOP_ARGS);
+  return TraceLiteral<DBG>(sc, w->r, t_out, cnt);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // shading helpers
 // ---------------------------------------------------------------------------------------------------
 // primitive_triangle.cc:27-40

@@ -44,7 +44,7 @@ struct ShadeFrame {
 // same rays are traced by the same code, only by different threads.
 constexpr int kPackThreads = 128;
 constexpr int kPackTileW = 16;
-constexpr int kModeTile = 0, kModePersist = 1, kModePack = 2, kModeSync = 3;
+constexpr int kModeTile = 0, kModePersist = 1, kModePack = 2, kModeSync = 3, kModeResume = 4;
 
 template <bool DBG, int MODE>
 __global__ void __launch_bounds__(MODE == kModePack ? kPackThreads : kBlockThreads,
@@ -57,7 +57,17 @@ __global__ void __launch_bounds__(MODE == kModePack ? kPackThreads : kBlockThrea
   // front of the Trace call.  (Per-pixel ray counts are balanced - a warp's lanes need 93 % of its maximum on C3 -
   // yet ncu shows 14 of 32 lanes per instruction: without the barrier the lanes that come back from the shadow
   // branch and from the secondary-ray branch walk the traversal as separate groups.)
-  constexpr bool SYNC = MODE == kModeSync;
+  // RESUME: SYNC plus suspendable walks (TraceBegin / TraceRun / TraceEnd, device_core.cuh): a lane whose ray is
+  // finished shades and starts its next ray while its neighbours' longer rays are parked, instead of waiting.
+  constexpr bool RESUME = MODE == kModeResume;
+  constexpr bool SYNC = MODE == kModeSync || RESUME;
+  FastWalk walk_store;
+  unsigned long long walk_stack[RESUME ? kFastStack : 1];
+  FastWalk *walk_ptr = &walk_store;
+  if (RESUME) asm volatile("" : "+l"(walk_ptr));  // opaque: the parked walk stays in memory between TraceRun calls
+  FastWalk &walk = *walk_ptr;
+  walk.node = kFastExit;
+  bool in_flight = false;
   __shared__ double s_ray[PACK ? 7 * kPackThreads : 1];   // o.xyz, d.xyz, t_limit of the rays of this iteration
   __shared__ double s_res_t[PACK ? kPackThreads : 1];
   __shared__ int s_res_slot[PACK ? kPackThreads : 1];
@@ -183,7 +193,7 @@ __global__ void __launch_bounds__(MODE == kModePack ? kPackThreads : kBlockThrea
         to = Add(seg_start, MulS(ldir, 0.00001));  // mythtracer.cc:95-99
         td = ldir;
         light_distance = Dist(seg_start, lpos);    // mythtracer.cc:101-102
-        Count<DBG>(cnt, kShadow);
+        if (!RESUME || !in_flight) Count<DBG>(cnt, kShadow);
       } else {
         to = m_o;
         td = m_d;
@@ -226,6 +236,16 @@ __global__ void __launch_bounds__(MODE == kModePack ? kPackThreads : kBlockThrea
         if (!active) continue;
         slot = s_res_slot[mine];
         t = s_res_t[mine];
+      } else if (RESUME) {
+        if (active && !in_flight) {
+          TraceBegin<DBG>(sc, to, td, shadow_mode ? light_distance : CUDART_INF, &walk, cnt);
+          in_flight = true;
+        }
+        __syncwarp();
+        TraceRun<DBG>(sc, &walk, walk_stack, cnt);
+        if (!active || walk.node != kFastExit) continue;  // idle, or this lane's ray is parked
+        in_flight = false;
+        slot = TraceEnd<DBG>(sc, &walk, &t, cnt MTB_TOP_ARGS);
       } else if (SYNC) {
         __syncwarp();
         if (!active) continue;
@@ -582,6 +602,12 @@ void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp_in, int n_bl
       RenderMega<true, kModeSync><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);
     } else {
       RenderMega<false, kModeSync><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);
+    }
+  } else if (mode == kModeResume) {
+    if (debug_build) {
+      RenderMega<true, kModeResume><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);
+    } else {
+      RenderMega<false, kModeResume><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);
     }
   } else if (debug_build) {
     RenderMega<true, kModeTile><<<n_blocks, kBlockThreads, 0, stream>>>(sc, rp);

@@ -378,7 +378,7 @@ def test_persistent_and_tile_per_block_megakernel_agree(product_lib, oracle_mod,
     """The megakernel's three launch forms -- one 8x8 tile per block (default), 16x8 tiles with block-level ray
     packing (MTB_FLAG_PACKING) and persistent warps whose lanes draw pixels from a counter (MTB_FLAG_PERSISTENT) -- against the oracle and against each other, every tap, on a
     full frame, a clipped odd-sized tile, a partitioned render and two consecutive frames (warm tile order)."""
-    from mythtracer_b200 import MTB_FLAG_COUNT_WORK, MTB_FLAG_MEGAKERNEL, MTB_FLAG_PACKING, MTB_FLAG_PERSISTENT, MTB_FLAG_WARP_SYNC
+    from mythtracer_b200 import MTB_FLAG_COUNT_WORK, MTB_FLAG_MEGAKERNEL, MTB_FLAG_PACKING, MTB_FLAG_PERSISTENT, MTB_FLAG_RESUME, MTB_FLAG_WARP_SYNC
     files, cfg = scenes.config_scene("C2", scene_dir, 0.3)
     mt, orc = _load_pair(product_lib, oracle_mod, files, cfg["depth"], MTB_FLAG_MEGAKERNEL)
     w, h = 250, 141
@@ -386,6 +386,7 @@ def test_persistent_and_tile_per_block_megakernel_agree(product_lib, oracle_mod,
     cpu_tile = orc.render(files.camera, 333, 211, chunk=(100, 37, 77, 45), depth=cfg["depth"], taps=True)
     for flags in (MTB_FLAG_MEGAKERNEL, MTB_FLAG_MEGAKERNEL | MTB_FLAG_PACKING, MTB_FLAG_MEGAKERNEL | MTB_FLAG_PERSISTENT,
                   MTB_FLAG_MEGAKERNEL | MTB_FLAG_WARP_SYNC, MTB_FLAG_MEGAKERNEL | MTB_FLAG_WARP_SYNC | MTB_FLAG_COUNT_WORK,
+                  MTB_FLAG_MEGAKERNEL | MTB_FLAG_RESUME, MTB_FLAG_MEGAKERNEL | MTB_FLAG_RESUME | MTB_FLAG_COUNT_WORK,
                   MTB_FLAG_MEGAKERNEL | MTB_FLAG_COUNT_WORK, MTB_FLAG_MEGAKERNEL | MTB_FLAG_PACKING | MTB_FLAG_COUNT_WORK,
                   MTB_FLAG_MEGAKERNEL | MTB_FLAG_PERSISTENT | MTB_FLAG_COUNT_WORK):
         mt.set_flags(flags)

@@ -103,7 +103,9 @@ struct DeviceState {
   DeviceBuffer<double> wf_act_color;
   DeviceBuffer<int32_t> wf_act_refl, wf_act_refr, wf_act_mtl, wf_act_pixel;
   DeviceBuffer<unsigned long long> wf_act_path;
-  cudaStream_t wf_stream2 = nullptr;             // shadow / light kernels
+  cudaStream_t wf_stream2 = nullptr;             // shadow / light kernels (side stream 0)
+  cudaStream_t wf_side[3] = {nullptr, nullptr, nullptr};  // further side streams: the shadow kernels of different levels are independent
+  cudaEvent_t wf_ev_side[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t wf_ev_level[MTB_MAX_RAY_DEPTH + 2] = {};  // level L traced (main stream)
   cudaEvent_t wf_ev_lit = nullptr;               // all lights folded (second stream)
   DeviceBuffer<uint32_t> wf_counters, wf_sort_key[2], wf_sort_hist;
@@ -128,6 +130,14 @@ struct DeviceState {
     wf_act_mtl.Free(); wf_act_pixel.Free(); wf_act_path.Free(); wf_counters.Free();
     if (wf_stream2 != nullptr) cudaStreamDestroy(wf_stream2);
     wf_stream2 = nullptr;
+    for (cudaStream_t &st : wf_side) {
+      if (st != nullptr) cudaStreamDestroy(st);
+      st = nullptr;
+    }
+    for (cudaEvent_t &e : wf_ev_side) {
+      if (e != nullptr) cudaEventDestroy(e);
+      e = nullptr;
+    }
     for (cudaEvent_t &e : wf_ev_level) {
       if (e != nullptr) cudaEventDestroy(e);
       e = nullptr;
@@ -389,6 +399,8 @@ int EnsureWavefront(mtb_context *ctx, DeviceState *d, int slots, int n_lights) {
   MTB_CUDA(ctx, d->wf_act_path.Reserve(acap));
   if (d->wf_stream2 == nullptr) {
     MTB_CUDA(ctx, cudaStreamCreateWithFlags(&d->wf_stream2, cudaStreamNonBlocking));
+    for (cudaStream_t &st : d->wf_side) MTB_CUDA(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : d->wf_ev_side) MTB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (cudaEvent_t &e : d->wf_ev_level) MTB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     MTB_CUDA(ctx, cudaEventCreateWithFlags(&d->wf_ev_lit, cudaEventDisableTiming));
   }
@@ -434,10 +446,14 @@ int RunWavefront(mtb_context *ctx, DeviceState *d, const mtb::RenderParams &p, i
     int level_begin[MTB_MAX_RAY_DEPTH + 2];
     int n = slots, act_base = 0, last_level = 0;
     bool overflow = false;
-    cudaStream_t s2 = d->wf_stream2;
-    // the second stream must not start before earlier work on the main stream (previous frame, taps memset)
+    // Side streams: the shadow walks + Phong sums of level L only depend on the trace of level L, so the levels'
+    // side kernels go round-robin over four streams and overlap each other as well as the deeper traces (on a small
+    // share of a frame - one of 8 GPUs - every one of them is latency-bound and they were the critical path when
+    // serialised on one stream).
+    cudaStream_t side[4] = {d->wf_stream2, d->wf_side[0], d->wf_side[1], d->wf_side[2]};
+    // they must not start before earlier work on the main stream (previous frame, taps memset)
     MTB_CUDA(ctx, cudaEventRecord(d->wf_ev_lit, s));
-    MTB_CUDA(ctx, cudaStreamWaitEvent(s2, d->wf_ev_lit, 0));
+    for (cudaStream_t st : side) MTB_CUDA(ctx, cudaStreamWaitEvent(st, d->wf_ev_lit, 0));
     for (int level = 0; level <= p.max_depth; level++) {
       last_level = level;
       level_begin[level] = act_base;
@@ -449,6 +465,7 @@ int RunWavefront(mtb_context *ctx, DeviceState *d, const mtb::RenderParams &p, i
       MTB_CUDA(ctx, cudaEventRecord(d->wf_ev_level[level], s));
       if (level < p.max_depth) mtb::LaunchWfSpawn(d->scene, p, d->wf, level, n, act_base, debug_build, s);
       // side branch (second stream): shadow walks and the Phong sums of this level
+      cudaStream_t s2 = side[level & 3];
       MTB_CUDA(ctx, cudaStreamWaitEvent(s2, d->wf_ev_level[level], 0));
       mtb::LaunchWfShadow(d->scene, p, d->wf, act_base, n, debug_build, s2);
       mtb::LaunchWfLight(d->scene, p, d->wf, act_base, n, s2);
@@ -467,10 +484,12 @@ int RunWavefront(mtb_context *ctx, DeviceState *d, const mtb::RenderParams &p, i
       n = next;
     }
     // join: the folds need every level's colours
-    MTB_CUDA(ctx, cudaEventRecord(d->wf_ev_lit, s2));
-    MTB_CUDA(ctx, cudaStreamWaitEvent(s, d->wf_ev_lit, 0));
+    for (int k = 0; k < 4; k++) {
+      MTB_CUDA(ctx, cudaEventRecord(d->wf_ev_side[k], side[k]));
+      MTB_CUDA(ctx, cudaStreamWaitEvent(s, d->wf_ev_side[k], 0));
+    }
     if (overflow) {
-      MTB_CUDA(ctx, cudaStreamSynchronize(s2));  // the side branch still reads the buffers about to be replaced
+      for (cudaStream_t st : side) MTB_CUDA(ctx, cudaStreamSynchronize(st));  // the side branches still read the buffers about to be replaced
       MTB_CUDA(ctx, cudaStreamSynchronize(s));
       d->wf_queue_factor *= 2;
       d->wf_act_factor *= 2;

@@ -418,57 +418,104 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
     out->max_abs_coord = std::max(out->max_abs_coord, std::max(std::fabs(nodes[0].box.lo[a]), std::fabs(nodes[0].box.hi[a])));
   }
   std::vector<int32_t> slot_of((size_t)n, -1);
-  BvhBuilder bb{tri_box, &out->bvh, {}, 0};
-  int32_t cursor = 0;
+  // Every node's list is independent (its slots, its list-BVH), so the nodes are handed out in batches to a pool of
+  // threads; each thread builds its list-BVHs into its own arena, and the arenas are stitched together in node
+  // order afterwards (record indices rebased), so the result does not depend on the number of threads.
+  std::vector<int32_t> cursor_of(nodes.size() + 1, 0);
   for (size_t i = 0; i < nodes.size(); i++) {
-    const BuildNode &bn = nodes[i];
+    cursor_of[i + 1] = cursor_of[i] + (int32_t)nodes[i].list.size();
+    out->biggest_list = std::max<int64_t>(out->biggest_list, (int64_t)nodes[i].list.size());
+    if (nodes[i].first_child >= 0) out->interior += (int64_t)nodes[i].list.size();
+  }
+  struct Piece {
+    int32_t thread = -1, offset = 0, count = 0;  // this node's list-BVH records inside the thread's arena
+  };
+  std::vector<Piece> piece(nodes.size());
+  unsigned n_threads = std::thread::hardware_concurrency();
+  if (n_threads == 0) n_threads = 1;
+  if (n_threads > 32) n_threads = 32;
+  if (n < 20000) n_threads = 1;
+  std::vector<std::vector<BvhRec>> arena(n_threads);
+  std::atomic<size_t> next_batch(0);
+  constexpr size_t kBatch = 64;
+  auto flatten_worker = [&](unsigned tid) {
+    BvhBuilder bb{tri_box, &arena[tid], {}, 0};
+    for (;;) {
+      const size_t first = next_batch.fetch_add(kBatch);
+      if (first >= nodes.size()) return;
+      const size_t last = std::min(nodes.size(), first + kBatch);
+      for (size_t i = first; i < last; i++) {
+        const BuildNode &bn = nodes[i];
+        NodeRec &nr = out->nodes[i];
+        memset(&nr, 0, sizeof(nr));
+        for (int a = 0; a < 3; a++) {
+          nr.planes[a] = bn.box.lo[a];
+          nr.planes[3 + a] = bn.c[a];
+          nr.planes[6 + a] = bn.box.hi[a];
+        }
+        const int32_t cursor = cursor_of[i];
+        nr.first_child = bn.first_child;
+        nr.list_first = cursor;
+        nr.list_count = (int32_t)bn.list.size();
+        nr.bvh_root = -1;
+        nr.bvh_end = -1;
+        const std::vector<int32_t> *order = &bn.list;
+        if (use_list_bvh && nr.list_count >= kBvhMinList) {
+          bb.ids = bn.list;
+          bb.slot_base = cursor;
+          piece[i].thread = (int32_t)tid;
+          piece[i].offset = (int32_t)arena[tid].size();
+          bb.Build(0, nr.list_count);
+          piece[i].count = (int32_t)arena[tid].size() - piece[i].offset;
+          order = &bb.ids;
+        }
+        for (int32_t k = 0; k < nr.list_count; k++) {
+          const int32_t t = (*order)[(size_t)k];
+          const int32_t sidx = cursor + k;
+          slot_of[(size_t)t] = sidx;
+          SlotRec &sr = out->slots[(size_t)sidx];
+          for (int a = 0; a < 3; a++) {
+            sr.box[a] = tri_box[(size_t)t].lo[a];
+            sr.box[3 + a] = tri_box[(size_t)t].hi[a];
+          }
+          memcpy(sr.vert, tris[t].vertex, sizeof(sr.vert));
+          sr.tri = t;
+          sr.canon = sidx;
+          ShadeRec &sh = out->shade[(size_t)sidx];
+          memcpy(sh.normal, tris[t].normal, sizeof(sh.normal));
+          for (int v = 0; v < 3; v++) {
+            sh.uv[v * 2 + 0] = tris[t].uvw[v * 3 + 0];
+            sh.uv[v * 2 + 1] = tris[t].uvw[v * 3 + 1];
+          }
+          sh.material = tris[t].material;
+          sh.line_no = tris[t].line_no;
+        }
+        for (int32_t k = 0; k < nr.list_count; k++) out->list_order[(size_t)(cursor + k)] = slot_of[(size_t)bn.list[(size_t)k]];
+      }
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n_threads; t++) pool.emplace_back(flatten_worker, t);
+    flatten_worker(0);
+    for (std::thread &t : pool) t.join();
+  }
+  size_t total_records = 0;
+  for (const std::vector<BvhRec> &a : arena) total_records += a.size();
+  out->bvh.reserve(total_records);
+  for (size_t i = 0; i < nodes.size(); i++) {
+    const Piece &pc = piece[i];
+    if (pc.thread < 0) continue;
     NodeRec &nr = out->nodes[i];
-    memset(&nr, 0, sizeof(nr));
-    for (int a = 0; a < 3; a++) {
-      nr.planes[a] = bn.box.lo[a];
-      nr.planes[3 + a] = bn.c[a];
-      nr.planes[6 + a] = bn.box.hi[a];
+    const int32_t base = (int32_t)out->bvh.size();
+    nr.bvh_root = base;
+    for (int32_t k = 0; k < pc.count; k++) {
+      BvhRec rec = arena[(size_t)pc.thread][(size_t)(pc.offset + k)];
+      rec.skip = rec.skip - pc.offset + base;
+      out->bvh.push_back(rec);
     }
-    nr.first_child = bn.first_child;
-    nr.list_first = cursor;
-    nr.list_count = (int32_t)bn.list.size();
-    nr.bvh_root = -1;
-    nr.bvh_end = -1;
-    out->biggest_list = std::max<int64_t>(out->biggest_list, nr.list_count);
-    if (bn.first_child >= 0) out->interior += nr.list_count;
-    const std::vector<int32_t> *order = &bn.list;
-    if (use_list_bvh && nr.list_count >= kBvhMinList) {
-      bb.ids = bn.list;
-      bb.slot_base = cursor;
-      nr.bvh_root = (int32_t)out->bvh.size();
-      bb.Build(0, nr.list_count);
-      nr.bvh_end = (int32_t)out->bvh.size();
-      nr.root_rec = out->bvh[(size_t)nr.bvh_root];
-      order = &bb.ids;
-    }
-    for (int32_t k = 0; k < nr.list_count; k++) {
-      const int32_t t = (*order)[(size_t)k];
-      const int32_t s = cursor + k;
-      slot_of[(size_t)t] = s;
-      SlotRec &sr = out->slots[(size_t)s];
-      for (int a = 0; a < 3; a++) {
-        sr.box[a] = tri_box[(size_t)t].lo[a];
-        sr.box[3 + a] = tri_box[(size_t)t].hi[a];
-      }
-      memcpy(sr.vert, tris[t].vertex, sizeof(sr.vert));
-      sr.tri = t;
-      sr.canon = s;
-      ShadeRec &sh = out->shade[(size_t)s];
-      memcpy(sh.normal, tris[t].normal, sizeof(sh.normal));
-      for (int v = 0; v < 3; v++) {
-        sh.uv[v * 2 + 0] = tris[t].uvw[v * 3 + 0];
-        sh.uv[v * 2 + 1] = tris[t].uvw[v * 3 + 1];
-      }
-      sh.material = tris[t].material;
-      sh.line_no = tris[t].line_no;
-    }
-    for (int32_t k = 0; k < nr.list_count; k++) out->list_order[(size_t)(cursor + k)] = slot_of[(size_t)bn.list[(size_t)k]];
-    cursor += nr.list_count;
+    nr.bvh_end = (int32_t)out->bvh.size();
+    nr.root_rec = out->bvh[(size_t)base];
   }
   // subtree occupancy, children always have larger indices than their parent
   std::vector<int64_t> subtree(nodes.size(), 0);

@@ -678,19 +678,7 @@ __device__ int TraceFast(const DeviceScene &sc, const Ray &r, double t_limit, do
       const bool hr = FastBox(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, nox, noy, noz, fb.prune, &tr);
       if (hl && hr) {
         const bool right_first = tr < tl;
-        const int far_child = right_first ? kids.x : kids.y;
-        stack[sp++] = ((unsigned long long)__float_as_uint(right_first ? tl : tr) << 32) | (unsigned)far_child;
-#if defined(MTB_PREFETCH_FAR)
-        {  // the postponed child will most likely be visited: start pulling its record in now
-          const void *pf = far_child >= 0 ? static_cast<const void *>(sc.gnodes + far_child)
-                                          : static_cast<const void *>(sc.gslots + ((~(unsigned)far_child) >> 3));
-#if MTB_PREFETCH_FAR == 1
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
-#else
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-#endif
-        }
-#endif
+        stack[sp++] = ((unsigned long long)__float_as_uint(right_first ? tl : tr) << 32) | (unsigned)(right_first ? kids.x : kids.y);
         node = right_first ? kids.y : kids.x;
       } else if (hl) {
         node = kids.x;

@@ -565,9 +565,19 @@ __device__ __forceinline__ bool MollerTrumboreBound(const double *vert, const Ra
   const D3 pvec = Cross(r.d, e2);
   const double det = Dot(e1, pvec);
   if (det >= -0.00000001 && det < 0.00000001) return false;
-  const double inv_det = 1.0 / det;
   const D3 tvec = Sub(r.o, v0);
-  const double u = Dot(tvec, pvec) * inv_det;
+  const double un = Dot(tvec, pvec);
+  {
+    // Most candidates are far misses (u far outside [0, 1]).  Their rejection by the reference's `u < 0 || u > 1`
+    // can be decided without the division: |det| >= 1e-8, so inv_det = fl(1 / det) is a normal number with det's
+    // sign and u = fl(un * inv_det) (a) is a non-zero negative number whenever un and det have opposite signs and
+    // |un| > 1e-200 (no underflow to -0, which would NOT be < 0), (b) exceeds 1 whenever un / det > 1 + 1e-10
+    // (two roundings of 2^-53 cannot bring it back to <= 1).  Anything closer goes through the division below.
+    const double us = det > 0.0 ? un : -un;
+    if (us < -1e-200 || us > fabs(det) * 1.0000000001) return false;
+  }
+  const double inv_det = 1.0 / det;
+  const double u = un * inv_det;
   if (u < 0.0 || u > 1.0) return false;
   const D3 qvec = Cross(tvec, e1);
   const double v = Dot(r.d, qvec) * inv_det;

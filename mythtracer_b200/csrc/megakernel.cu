@@ -1,4 +1,6 @@
 // RenderMega (per-pixel megakernel) and the batched intersect kernel; see device_core.cuh for the traversal.
+#include <atomic>
+
 #include "device_core.cuh"
 
 namespace mtb {
@@ -565,13 +567,13 @@ void LaunchBuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles,
 }
 
 int MegaResidentBlocks(int device) {
-  static int cached[64] = {0};
-  if (device >= 0 && device < 64 && cached[device] > 0) return cached[device];
+  static std::atomic<int> cached[64];  // devices are driven by one host thread each (api.cu)
+  if (device >= 0 && device < 64 && cached[device].load() > 0) return cached[device].load();
   int per_sm = 0, sms = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, RenderMega<false, kModePersist>, kBlockThreads, 0) != cudaSuccess) per_sm = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) sms = 0;
   const int n = per_sm > 0 && sms > 0 ? per_sm * sms : 148 * MTB_MEGA_MIN_BLOCKS;
-  if (device >= 0 && device < 64) cached[device] = n;
+  if (device >= 0 && device < 64) cached[device].store(n);
   return n;
 }
 

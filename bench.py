@@ -250,7 +250,7 @@ def _run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_COUNT_WORK, MTB_FLAG_MEGAKERNEL, MTB_FLAG_WAVEFRONT, tiles
+    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_COUNT_WORK, MTB_FLAG_HYBRID, MTB_FLAG_MEGAKERNEL, MTB_FLAG_WAVEFRONT, tiles
     from mythtracer_b200 import build as mtb_build
 
     rank = int(os.environ.get("RANK", "0"))
@@ -277,7 +277,7 @@ def _run_ours(args):
             files, cfg = load_workload()  # reuses the files rank 0 wrote
     W, H, depth = cfg["width"], cfg["height"], cfg["depth"]
 
-    base_flags = {"wavefront": MTB_FLAG_WAVEFRONT, "mega": MTB_FLAG_MEGAKERNEL, "auto": 0}[args.pipeline]
+    base_flags = {"wavefront": MTB_FLAG_WAVEFRONT, "mega": MTB_FLAG_MEGAKERNEL, "hybrid": MTB_FLAG_HYBRID, "auto": 0}[args.pipeline]
     # Launched plainly (no torchrun) with --gpus N > 1: ONE process, one context over N devices -- the
     # in-process form (strips interleaved over the devices, peer-copy gather to device 0 over NVLink).
     inproc = 1
@@ -315,8 +315,8 @@ def _run_ours(args):
         torch.cuda.synchronize(dev)
 
     # ---- warm-up, then K timed steps (device-resident).  The automatic pipeline choice measures both
-    # pipelines during the first four frames of a geometry, so the warm-up covers at least five ----
-    n_warm = max(args.warmup, 5 if args.pipeline == "auto" else 3)
+    # pipelines and the hybrid split during the first six frames of a geometry, so the warm-up covers at least seven ----
+    n_warm = max(args.warmup, 7 if args.pipeline == "auto" else 3)
     for _ in range(n_warm):
         step_device()
     barrier()
@@ -423,7 +423,7 @@ def _run_ours(args):
         except Exception:
             pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "RenderMega" if pipeline_used == "mega" else "wavefront pipeline (WfTraceMain + WfShadow dominate)",
+                "traffic": traffic, "kernel": {"mega": "RenderMega", "hybrid": "RenderMega + wavefront kernels on the most expensive tiles, concurrently"}.get(pipeline_used, "wavefront pipeline (WfTraceMain + WfShadow dominate)"),
                 "kernel_ms": kernel_ms_mean,
                 "algorithmic_bytes_per_launch": my_alg, "peak_source": peak_src,
                 "note": "algorithmic bytes are mostly served by L1/L2 (the BVH top and neighbouring rays' nodes are shared); traffic = ncu dram bytes of the same launch",
@@ -473,7 +473,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline", default=os.environ.get("MTB_PIPELINE", "auto"), choices=["auto", "mega", "wavefront"])
+    ap.add_argument("--pipeline", default=os.environ.get("MTB_PIPELINE", "auto"), choices=["auto", "mega", "wavefront", "hybrid"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

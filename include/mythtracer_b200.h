@@ -123,6 +123,7 @@ typedef struct {
  * produce identical bytes, so the choice is invisible in the output. */
 #define MTB_FLAG_WAVEFRONT 4u    /* force the wavefront pipeline */
 #define MTB_FLAG_MEGAKERNEL 16u  /* force the per-pixel megakernel */
+#define MTB_FLAG_HYBRID 2048u    /* force hybrid frames: the tiles that were most expensive in the previous frame go through the wavefront, the rest through the megakernel, concurrently */
 #define MTB_FLAG_RAY_SORT 8u     /* wavefront: counting-sort every queue by origin cell + direction octant (measured: no gain) */
 #define MTB_FLAG_EXACT_OCTREE 128u /* every regular ray walks the octree in the reference's recursion order (no certified fast traversal) */
 #define MTB_FLAG_PACKING 256u /* megakernel: 16x8 tiles per 128-thread block, the rays of an iteration are handed to the first threads of the block (A/B; measured slower: fewer tracing warps hide less latency) */
@@ -219,8 +220,8 @@ int mtb_render_chunk_device(mtb_context *ctx, const mtb_camera *cam, int image_w
  * read; synchronises every device of the context and resets the counters. */
 int mtb_read_counters(mtb_context *ctx, mtb_stats *stats);
 
-/* Automatic pipeline choice on device 0: 0 = megakernel, 1 = wavefront, -1 = still measuring; the two
- * timed frames (ms) are returned when the pointers are non-NULL. */
+/* Automatic pipeline choice on device 0: 0 = megakernel, 1 = wavefront, 2 = hybrid, -1 = still measuring; the
+ * timed megakernel / wavefront frames (ms) are returned when the pointers are non-NULL. */
 int mtb_pipeline_in_use(const mtb_context *ctx, float *mega_ms, float *wavefront_ms);
 /* Number of kernels of this library launched on this context so far (bench.py's gpu_launches). */
 uint64_t mtb_launch_count(const mtb_context *ctx);

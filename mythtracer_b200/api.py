@@ -41,6 +41,7 @@ MTB_FLAG_EXACT_OCTREE = 128
 MTB_FLAG_PACKING = 256
 MTB_FLAG_WARP_SYNC = 512
 MTB_FLAG_RESUME = 1024
+MTB_FLAG_HYBRID = 2048
 MAX_RECURSION_LEVEL = 5  # reference mythtracer.h:11 (a run-time argument here)
 
 TRI_DTYPE = np.dtype([("vertex", "f8", (9,)), ("normal", "f8", (9,)), ("uvw", "f8", (9,)),
@@ -460,11 +461,11 @@ class MythTracer:
         self._push_lights()
 
     def pipeline_in_use(self):
-        """('mega' | 'wavefront' | 'measuring', mega_ms, wavefront_ms) of the automatic choice on device 0."""
+        """('mega' | 'wavefront' | 'hybrid' | 'measuring', mega_ms, wavefront_ms) of the automatic choice on device 0."""
         a, b = ctypes.c_float(0), ctypes.c_float(0)
         rc = self._lib.mtb_pipeline_in_use(self._ctx, ctypes.cast(ctypes.byref(a), ctypes.c_void_p),
                                            ctypes.cast(ctypes.byref(b), ctypes.c_void_p))
-        return {0: "mega", 1: "wavefront"}.get(rc, "measuring"), a.value, b.value
+        return {0: "mega", 1: "wavefront", 2: "hybrid"}.get(rc, "measuring"), a.value, b.value
 
     def launch_count(self) -> int:
         return int(self._lib.mtb_launch_count(self._ctx))

@@ -1,9 +1,11 @@
 // C ABI of mythtracer_b200 (see include/mythtracer_b200.h): context, scene residency in HBM, and the
 // launch / gather logic around the kernels of megakernel.cu / wavefront.cu.  No CPU rendering path exists in this file.
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -55,6 +57,7 @@ struct DeviceBuffer {
 
 struct DeviceState {
   int device = 0;
+  int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   cudaEvent_t ev_gathered = nullptr;  // device 0 only: the last gather has read every peer buffer
@@ -88,8 +91,12 @@ struct DeviceState {
   // geometry (megakernel with a warm tile order, then wavefront) and the faster one is kept
   long long tune_signature = -1;
   int tune_stage = 0;           // see RenderImpl
-  float tune_ms[2] = {0.f, 0.f};
-  bool tune_use_wavefront = false;
+  float tune_ms[3] = {0.f, 0.f, 0.f};  // megakernel, wavefront, hybrid
+  int tune_choice = 0;                 // 0 megakernel, 1 wavefront, 2 hybrid
+  // hybrid frames: the most expensive tiles go through the wavefront while the megakernel renders the rest
+  DeviceBuffer<int32_t> heavy_k;
+  cudaStream_t hybrid_stream = nullptr;
+  cudaEvent_t ev_split = nullptr, ev_mega_done = nullptr;
   // intersect scratch
   DeviceBuffer<double> q_origins, q_dirs, q_t, q_point;
   DeviceBuffer<int32_t> q_tri;
@@ -117,7 +124,12 @@ struct DeviceState {
   void FreeAll() {
     nodes.Free(); slots.Free(); shade.Free(); bvh.Free(); gnodes.Free(); gslots.Free(); list_order.Free(); materials.Free();
     tex_dims.Free(); lights.Free(); rgb.Free(); dbg.Free(); sig_hits.Free(); sig_shadow.Free(); n_rays.Free();
-    counters.Free(); tile_cost.Free(); tile_order.Free(); work_counter.Free(); q_origins.Free(); q_dirs.Free(); q_t.Free(); q_point.Free(); q_tri.Free();
+    counters.Free(); tile_cost.Free(); tile_order.Free(); work_counter.Free(); heavy_k.Free();
+    if (hybrid_stream != nullptr) cudaStreamDestroy(hybrid_stream);
+    hybrid_stream = nullptr;
+    if (ev_split != nullptr) cudaEventDestroy(ev_split);
+    if (ev_mega_done != nullptr) cudaEventDestroy(ev_mega_done);
+    ev_split = ev_mega_done = nullptr; q_origins.Free(); q_dirs.Free(); q_t.Free(); q_point.Free(); q_tri.Free();
     for (int k = 0; k < 2; k++) {
       wf_rq_o[k].Free(); wf_rq_d[k].Free(); wf_rq_coef[k].Free(); wf_rq_path[k].Free(); wf_rq_pixel[k].Free();
       wf_rq_inobj[k].Free();
@@ -509,6 +521,19 @@ int RunWavefront(mtb_context *ctx, DeviceState *d, const mtb::RenderParams &p, i
   return MTB_ERR_LIMIT;
 }
 
+// Hybrid frames: which tiles go through the wavefront.  Measured on B200 with C3 (one device rendering 1/1, 1/2, 1/4,
+// 1/8 of the frame; megakernel 9.1 / 6.35 / 5.13 / 4.54 ms, wavefront 11.5 / 6.46 / 3.81 / 2.49 ms):
+//   tiles of >= 2x the mean cost, at most 1/8 of the tiles:  9.8 / 5.5 / 3.75 / 3.2 ms
+//   tiles of >= 1x the mean cost, at most 1/4 of the tiles: 10.8 / 6.0 / 3.55 / 2.3 ms
+// so the smaller a device's share of the frame, the more of it the wavefront gets (80 tiles per SM is the C3 frame
+// cut in two or three).
+struct HybridSplit {
+  int cap_div, factor;
+};
+HybridSplit ChooseHybridSplit(int tiles, int sm_count) {
+  return tiles >= 80 * sm_count ? HybridSplit{8, 2} : HybridSplit{4, 1};
+}
+
 // Core of both render entry points.  d_rgb_user: device-0 buffer to leave the pixels in (may be NULL when
 // rgb_host is given); user_stream: stream of device 0 to enqueue on (NULL = context stream).
 int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h, int chunk_x, int chunk_y,
@@ -584,25 +609,31 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
     // a peer's scratch frame must not be overwritten while device 0 still gathers the previous one
     if (g > 0) MTB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->dev[0].ev_gathered, 0));
     bool wavefront = (ctx->flags & MTB_FLAG_WAVEFRONT) != 0;
-    if ((ctx->flags & (MTB_FLAG_WAVEFRONT | MTB_FLAG_MEGAKERNEL)) == 0 && blocks > 0) {
+    bool hybrid = (ctx->flags & MTB_FLAG_HYBRID) != 0 && !wavefront;
+    if ((ctx->flags & (MTB_FLAG_WAVEFRONT | MTB_FLAG_MEGAKERNEL | MTB_FLAG_HYBRID)) == 0 && blocks > 0) {
       // automatic: measure both pipelines on the first frames of this geometry, then keep the faster
       const long long tsig = ((long long)chunk_w << 42) ^ ((long long)chunk_h << 24) ^ ((long long)owner << 12) ^
                              ((long long)plan.owners << 6) ^ ((long long)max_depth << 1) ^ ((long long)d.scene.n_lights << 50);
       if (tsig != d.tune_signature) {
         d.tune_signature = tsig;
         d.tune_stage = 0;
-      } else if (d.tune_stage == 2 || d.tune_stage == 4) {
+      } else if (d.tune_stage == 2 || d.tune_stage == 4 || d.tune_stage == 6) {
         // the previous frame was a timed one: harvest it
         float ms = 0.f;
         if (cudaEventSynchronize(d.ev_stop) == cudaSuccess && cudaEventElapsedTime(&ms, d.ev_start, d.ev_stop) == cudaSuccess) {
-          d.tune_ms[d.tune_stage == 2 ? 0 : 1] = ms;
+          d.tune_ms[d.tune_stage / 2 - 1] = ms;
         }
-        if (d.tune_stage == 4) d.tune_use_wavefront = d.tune_ms[1] < d.tune_ms[0];
+        if (d.tune_stage == 6) {
+          d.tune_choice = 0;
+          if (d.tune_ms[1] < d.tune_ms[d.tune_choice]) d.tune_choice = 1;
+          if (d.tune_ms[2] < d.tune_ms[d.tune_choice]) d.tune_choice = 2;
+        }
       }
-      if (d.tune_stage < 5) d.tune_stage++;
+      if (d.tune_stage < 7) d.tune_stage++;
       // stage now: 1 = megakernel (cold tile order), 2 = megakernel (timed), 3 = wavefront (cold: buffers are
-      // allocated), 4 = wavefront (timed), 5 = decided
-      wavefront = d.tune_stage == 3 || d.tune_stage == 4 || (d.tune_stage == 5 && d.tune_use_wavefront);
+      // allocated), 4 = wavefront (timed), 5 = hybrid (cold), 6 = hybrid (timed), 7 = decided
+      wavefront = d.tune_stage == 3 || d.tune_stage == 4 || (d.tune_stage == 7 && d.tune_choice == 1);
+      hybrid = d.tune_stage == 5 || d.tune_stage == 6 || (d.tune_stage == 7 && d.tune_choice == 2);
     }
     MTB_CUDA(ctx, cudaEventRecord(d.ev_start, s));
     if (wavefront) {
@@ -626,10 +657,14 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
         MTB_CUDA(ctx, d.tile_cost.Reserve((size_t)mblocks));
         MTB_CUDA(ctx, d.tile_order.Reserve((size_t)mblocks));
         p.tile_cost = d.tile_cost.ptr;
+        const bool split = hybrid && mode == 0 && mblocks >= 64;
+        const HybridSplit hs = ChooseHybridSplit(mblocks, d.sm_count);
+        if (split) MTB_CUDA(ctx, d.heavy_k.Reserve(1));
         if (signature == d.tile_signature) {
-          mtb::LaunchBuildTileOrder(d.tile_cost.ptr, d.tile_order.ptr, mblocks, s);
+          mtb::LaunchBuildTileOrder(d.tile_cost.ptr, d.tile_order.ptr, mblocks, split ? d.heavy_k.ptr : nullptr, mblocks / hs.cap_div, hs.factor, s);
           ctx->launches++;
           p.tile_order = d.tile_order.ptr;
+          if (split) p.heavy_k = d.heavy_k.ptr;
         } else {
           MTB_CUDA(ctx, cudaMemsetAsync(d.tile_cost.ptr, 0, (size_t)mblocks * sizeof(uint32_t), s));
           d.tile_signature = signature;
@@ -642,9 +677,36 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
         p.work_counter = d.work_counter.ptr;
         persistent_blocks = mtb::MegaResidentBlocks(d.device);
       }
-      mtb::LaunchRenderMega(d.scene, p, mblocks, mode, persistent_blocks, debug_build, s);
-      if (mblocks > 0) ctx->launches++;
-      MTB_CUDA(ctx, cudaGetLastError());
+      if (p.heavy_k != nullptr) {
+        // Hybrid frame.  The megakernel's critical path is its most expensive pixel (a serial chain of up to ~80
+        // rays), the wavefront's is one ray per level but it pays ~1.3x the instructions: so the tiles that were
+        // the most expensive in the previous frame (the first *heavy_k of the launch order, at most 1/8 of the tiles)
+        // go through the wavefront while the megakernel renders the rest on a second stream.  Both write their own
+        // pixels of the same buffers; the bytes do not depend on the split.
+        if (d.hybrid_stream == nullptr) {
+          MTB_CUDA(ctx, cudaStreamCreateWithFlags(&d.hybrid_stream, cudaStreamNonBlocking));
+          MTB_CUDA(ctx, cudaEventCreateWithFlags(&d.ev_split, cudaEventDisableTiming));
+          MTB_CUDA(ctx, cudaEventCreateWithFlags(&d.ev_mega_done, cudaEventDisableTiming));
+        }
+        if (want_taps) {  // the wavefront kernels accumulate the taps with atomics
+          MTB_CUDA(ctx, cudaMemsetAsync(d.sig_hits.ptr, 0, npx * 8, s));
+          MTB_CUDA(ctx, cudaMemsetAsync(d.sig_shadow.ptr, 0, npx * 8, s));
+          MTB_CUDA(ctx, cudaMemsetAsync(d.n_rays.ptr, 0, npx * 4, s));
+        }
+        MTB_CUDA(ctx, cudaEventRecord(d.ev_split, s));
+        MTB_CUDA(ctx, cudaStreamWaitEvent(d.hybrid_stream, d.ev_split, 0));
+        mtb::LaunchRenderMega(d.scene, p, mblocks, mode, 0, debug_build, d.hybrid_stream);
+        ctx->launches++;
+        MTB_CUDA(ctx, cudaGetLastError());
+        MTB_CUDA(ctx, cudaEventRecord(d.ev_mega_done, d.hybrid_stream));
+        const int wrc = RunWavefront(ctx, &d, p, mblocks / ChooseHybridSplit(mblocks, d.sm_count).cap_div, debug_build, s);
+        if (wrc != MTB_OK) return wrc;
+        MTB_CUDA(ctx, cudaStreamWaitEvent(s, d.ev_mega_done, 0));
+      } else {
+        mtb::LaunchRenderMega(d.scene, p, mblocks, mode, persistent_blocks, debug_build, s);
+        if (mblocks > 0) ctx->launches++;
+        MTB_CUDA(ctx, cudaGetLastError());
+      }
     }
     MTB_CUDA(ctx, cudaEventRecord(d.ev_stop, s));
     return MTB_OK;
@@ -754,6 +816,8 @@ int mtb_create(mtb_context **out, const int *devices, int n_devices) {
       delete ctx;
       return MTB_ERR_CUDA;
     }
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d.device) == cudaSuccess && sms > 0) d.sm_count = sms;
   }
   // NVLink peer access towards device 0, the gather target
   for (int g = 1; g < n; g++) {
@@ -1029,8 +1093,9 @@ int mtb_pipeline_in_use(const mtb_context *ctx, float *mega_ms, float *wavefront
   if (mega_ms != nullptr) *mega_ms = d.tune_ms[0];
   if (wavefront_ms != nullptr) *wavefront_ms = d.tune_ms[1];
   if ((ctx->flags & MTB_FLAG_WAVEFRONT) != 0) return 1;
+  if ((ctx->flags & MTB_FLAG_HYBRID) != 0) return 2;
   if ((ctx->flags & MTB_FLAG_MEGAKERNEL) != 0) return 0;
-  return d.tune_stage >= 5 ? (d.tune_use_wavefront ? 1 : 0) : -1;
+  return d.tune_stage >= 7 ? d.tune_choice : -1;
 }
 
 int mtb_read_counters(mtb_context *ctx, mtb_stats *stats) {

@@ -60,6 +60,9 @@ struct RenderParams {
   // of that 8x8 tile) from *work_counter until n_items are handed out.
   uint32_t *work_counter;
   uint32_t n_items;
+  // Hybrid frame: the first *heavy_k tiles of tile_order (the most expensive ones of the previous frame) are
+  // rendered by the wavefront pipeline, the rest by the megakernel, concurrently.  NULL: no split.
+  const int32_t *heavy_k;
 };
 
 struct IntersectParams {
@@ -120,7 +123,10 @@ void LaunchWfResolve(const RenderParams &rp, const WfBuffers &wf, int n_slots, c
 
 // megakernel.cu
 // Builds tile_order (descending cost, bucketed) from tile_cost and clears tile_cost for the coming frame.
-void LaunchBuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles, cudaStream_t stream);
+// heavy_k (nullable): receives the number of leading tiles of the order whose cost is at least heavy_factor x the
+// mean (whole cost buckets, at most k_max).
+void LaunchBuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles, int32_t *heavy_k, int k_max, int heavy_factor,
+                          cudaStream_t stream);
 // mode 0: one 8x8 tile per 64-thread block; 1: persistent lane refill (grid persistent_blocks, rp.work_counter
 // zeroed); 2: one 16x8 tile per 128-thread block with block-level ray packing.  rp.tiles_x must be in units of
 // MegaTileWidth(mode).

@@ -80,6 +80,8 @@ __global__ void __launch_bounds__(MODE == kModePack ? kPackThreads : kBlockThrea
   const int top_n = sc.n_nodes < kTopNodes ? sc.n_nodes : kTopNodes;
   StageTopNodes(sc, top_store, sc.n_nodes);
 #endif
+  // hybrid frame: the leading (most expensive) tiles of the order belong to the wavefront pipeline
+  if (MODE == kModeTile && rp.heavy_k != nullptr && (int)blockIdx.x < __ldg(rp.heavy_k)) return;
   unsigned long long cnt_store[DBG ? kNumCounters : 1];
   unsigned long long *cnt = cnt_store;
   if (DBG) {
@@ -533,21 +535,38 @@ __global__ void __launch_bounds__(128) IntersectKernel(DeviceScene sc, Intersect
 }
 
 // Counting sort of the tiles by cost bucket (log2 of the ray count, most expensive first).  One block.
-__global__ void __launch_bounds__(1024) BuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles) {
+__global__ void __launch_bounds__(1024) BuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles, int32_t *heavy_k, int k_max, int heavy_factor) {
   __shared__ unsigned hist[33];
   __shared__ unsigned offset[33];
+  __shared__ unsigned long long total;
   if (threadIdx.x < 33) hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) total = 0;
   __syncthreads();
+  unsigned long long mine = 0;
   for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
     const unsigned c = tile_cost[t];
+    mine += c;
     atomicAdd(&hist[c == 0u ? 0 : 32 - __clz((int)c)], 1u);
   }
+  atomicAdd(&total, mine);
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned run = 0;
     for (int b = 32; b >= 0; b--) {
       offset[b] = run;
       run += hist[b];
+    }
+    if (heavy_k != nullptr) {
+      // heavy = whole buckets [2^(b-1), 2^b) whose lower bound is at least heavy_factor x the mean cost, most
+      // expensive bucket first, as long as they fit into k_max tiles
+      const unsigned long long mean = n_tiles > 0 ? total / (unsigned long long)n_tiles : 0;
+      int k = 0;
+      for (int b = 32; b >= 2; b--) {
+        if ((1ull << (b - 1)) < (unsigned long long)heavy_factor * mean || mean == 0) break;
+        if (k + (int)hist[b] > k_max) break;
+        k += (int)hist[b];
+      }
+      *heavy_k = k;
     }
   }
   __syncthreads();
@@ -561,9 +580,10 @@ __global__ void __launch_bounds__(1024) BuildTileOrder(uint32_t *tile_cost, int3
 
 }  // namespace
 
-void LaunchBuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles, cudaStream_t stream) {
+void LaunchBuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles, int32_t *heavy_k, int k_max, int heavy_factor,
+                          cudaStream_t stream) {
   if (n_tiles <= 0) return;
-  BuildTileOrder<<<1, 1024, 0, stream>>>(tile_cost, tile_order, n_tiles);
+  BuildTileOrder<<<1, 1024, 0, stream>>>(tile_cost, tile_order, n_tiles, heavy_k, k_max, heavy_factor);
 }
 
 int MegaResidentBlocks(int device) {

@@ -116,6 +116,23 @@ __device__ __forceinline__ int PackedIndex(int n, int lanes) { return (int)Packe
 // ---------------------------------------------------------------------------------------------------
 // WfTraceMain
 // ---------------------------------------------------------------------------------------------------
+// Pixel slot -> tile of this launch.  Hybrid frames (rp.heavy_k): slot >> 6 is a position in the launch order and
+// only the first *heavy_k positions belong to the wavefront (-1 beyond them).
+__device__ __forceinline__ int WfTileOfSlot(const RenderParams &rp, int slot) {
+  const int pos = slot >> 6;
+  if (rp.heavy_k == nullptr) return pos;
+  if (pos >= __ldg(rp.heavy_k)) return -1;
+  return __ldg(rp.tile_order + pos);
+}
+
+// What a tile cost, for the next frame's launch order and split (the megakernel does the same per block).
+__device__ __forceinline__ void WfChargeTile(const RenderParams &rp, int pixel, unsigned rays) {
+  if (rp.tile_cost == nullptr || rays == 0u || pixel < 0) return;
+  const int px = pixel % rp.chunk_w, py = pixel / rp.chunk_w;
+  const int local_strip = ((py >> 3) - rp.strip_first) / rp.strip_stride;
+  atomicAdd(rp.tile_cost + local_strip * rp.tiles_x + (px >> 3), rays);
+}
+
 template <bool DBG>
 __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTraceMain(DeviceScene sc, RenderParams rp, WfBuffers wf, int level, int n,
                                                         int act_base, const int32_t *__restrict__ perm, int lanes) {
@@ -142,12 +159,13 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTraceMain(Devic
     unsigned long long path;
     bool live = true;
     if (level == 0) {
-      // 8x8 pixel tiles (a warp = 8x4 pixels) of this launch's strips, as in RenderMega
-      const int tile = i >> 6, t = i & 63;
+      // 8x8 pixel tiles (a warp = 8x4 pixels) of this launch's strips, as in RenderMega; in a hybrid frame the
+      // slots are the first *heavy_k tiles of the launch order
+      const int tile = WfTileOfSlot(rp, i), t = i & 63;
       const int strip = rp.strip_first + (tile / rp.tiles_x) * rp.strip_stride;
       const int px = (tile % rp.tiles_x) * 8 + (t & 7);
       const int py = strip * 8 + (t >> 3);
-      live = px < rp.chunk_w && py < rp.chunk_h;
+      live = tile >= 0 && px < rp.chunk_w && py < rp.chunk_h;
       pixel = live ? py * rp.chunk_w + px : -1;
       const D3 start = Load3(rp.sensor), d_scan = Load3(rp.sensor + 3), d_pixel = Load3(rp.sensor + 6);
       o = Load3(rp.origin);
@@ -232,6 +250,7 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTraceMain(Devic
     }
     wf.act_mtl[act] = act_mtl;
     Store3(wf.act_color + (size_t)act * 3, color);
+    WfChargeTile(rp, pixel, traced);
   }
   FlushCounters<DBG>(cnt, rp.counters, traced);
 }
@@ -379,6 +398,7 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfShadow(DeviceSc
       Store3(wf.sh_power + ((size_t)li * wf.act_cap + act) * 3, power);
       wf.sh_flags[(size_t)li * wf.act_cap + act] = (in_shadow ? 1u : 0u) | (segments << 1);
       if (rp.n_rays != nullptr) atomicAdd(rp.n_rays + wf.act_pixel[act], segments);
+      WfChargeTile(rp, wf.act_pixel[act], segments);
     }
   }
   FlushCounters<DBG>(cnt, rp.counters, traced);
@@ -445,7 +465,8 @@ __global__ void __launch_bounds__(256) WfResolve(RenderParams rp, WfBuffers wf, 
   const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (i >= n_slots) return;
   // same slot -> pixel mapping as level 0 of WfTraceMain (the level-0 queue itself has been reused by now)
-  const int tile = i >> 6, t = i & 63;
+  const int tile = WfTileOfSlot(rp, i), t = i & 63;
+  if (tile < 0) return;
   const int strip = rp.strip_first + (tile / rp.tiles_x) * rp.strip_stride;
   const int px = (tile % rp.tiles_x) * 8 + (t & 7);
   const int py = strip * 8 + (t >> 3);

@@ -429,8 +429,9 @@ def test_textured_light_terms_in_isolation(product_lib, oracle_mod, scene_dir, p
 
 
 def test_automatic_pipeline_choice(product_lib, oracle_mod, scene_dir):
-    """flags = 0: the library times both pipelines on the first frames of a geometry and keeps the faster; every
-    one of those frames must carry the same bytes (the choice is invisible in the output)."""
+    """flags = 0: the library times the megakernel, the wavefront and the hybrid split on the first frames of a
+    geometry and keeps the fastest; every one of those frames must carry the same bytes (the choice is invisible in
+    the output)."""
     from mythtracer_b200 import Light, MythTracer
     files, cfg = scenes.config_scene("C1", scene_dir)
     mt = MythTracer(max_depth=cfg["depth"])
@@ -441,15 +442,16 @@ def test_automatic_pipeline_choice(product_lib, oracle_mod, scene_dir):
     w, h = 320, 240
     cpu = orc.render(files.camera, w, h, depth=cfg["depth"])
     states = []
-    for _ in range(7):
+    for _ in range(9):
         out = mt.render_chunk(files.camera, w, h, 0, 0, w, h)
         assert np.array_equal(out["rgb"], cpu["rgb"])
         assert out["stats"]["rays"] == cpu["stats"]["rays"]
         states.append(mt.pipeline_in_use()[0])
-    assert states[0] == "measuring" and states[-1] in ("mega", "wavefront")
+    assert states[0] == "measuring" and states[5] == "measuring" and states[-1] in ("mega", "wavefront", "hybrid")
     _, mega_ms, wf_ms = mt.pipeline_in_use()
     assert mega_ms > 0 and wf_ms > 0
-    assert states[-1] == ("wavefront" if wf_ms < mega_ms else "mega")
+    if states[-1] != "hybrid":
+        assert states[-1] == ("wavefront" if wf_ms < mega_ms else "mega")
     # a different geometry starts measuring again
     mt.render_chunk(files.camera, w, h, 0, 0, w // 2, h)
     assert mt.pipeline_in_use()[0] == "measuring"
@@ -635,3 +637,43 @@ def test_fast_traversal_equals_exact_octree_at_full_size(product_lib, scene_dir)
             assert st["n_fast"] + st["n_fallback"] + st["n_literal"] == st["rays"]
             assert st["n_fallback"] < 1e-4 * st["rays"], "%s: %d rays fell back" % (name, st["n_fallback"])
         mt.close()
+
+
+def test_hybrid_frames(product_lib, oracle_mod, scene_dir):
+    """MTB_FLAG_HYBRID: from the second frame of a geometry on, the tiles that were most expensive in the previous
+    frame go through the wavefront pipeline while the megakernel renders the rest.  Every frame must carry the same
+    bytes and taps as the oracle's, whatever the split; also with a partition and with the counting build."""
+    from mythtracer_b200 import MTB_FLAG_COUNT_WORK, MTB_FLAG_HYBRID
+    files, cfg = scenes.config_scene("C2", scene_dir, 0.3)
+    mt, orc = _load_pair(product_lib, oracle_mod, files, cfg["depth"], MTB_FLAG_HYBRID)
+    w, h = 250, 141
+    cpu = orc.render(files.camera, w, h, depth=cfg["depth"], taps=True)
+    for flags in (MTB_FLAG_HYBRID, MTB_FLAG_HYBRID | MTB_FLAG_COUNT_WORK):
+        mt.set_flags(flags)
+        for frame in range(4):
+            gpu = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
+            _assert_render_equal(gpu, cpu, "hybrid flags %d frame %d" % (flags, frame))
+    assert mt.pipeline_in_use()[0] == "hybrid"
+    full = gpu["rgb"].copy()
+    for rank in range(2):
+        mt.set_partition(rank, 2)
+        for frame in range(3):
+            part = mt.render_chunk(files.camera, w, h, 0, 0, w, h)["rgb"]
+        rows = np.arange(h)
+        own = ((rows // 8) % 2) == rank
+        assert np.array_equal(part[own], full[own])
+    mt.set_partition(0, 1)
+    # the full-size frame: same bytes as the megakernel alone, over several frames (the split follows the costs)
+    files, cfg = scenes.config_scene("C3", scene_dir)
+    from mythtracer_b200 import Light, MTB_FLAG_MEGAKERNEL
+    mt = _tracer(product_lib, cfg["depth"], MTB_FLAG_MEGAKERNEL)
+    assert mt.LoadObj(files.obj_path)
+    mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]
+    W, H = cfg["width"], cfg["height"]
+    ref = mt.render_chunk(files.camera, W, H, 0, 0, W, H, taps=True)
+    mt.set_flags(MTB_FLAG_HYBRID)
+    for frame in range(3):
+        got = mt.render_chunk(files.camera, W, H, 0, 0, W, H, taps=True)
+        for k in ("rgb", "n_rays", "sig_hits", "sig_shadow"):
+            assert np.array_equal(got[k], ref[k]), "C3 hybrid frame %d: %s" % (frame, k)
+        assert got["stats"]["rays"] == ref["stats"]["rays"]

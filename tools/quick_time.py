@@ -10,13 +10,13 @@ out = []
 for name in names:
     files, cfg = scenegen.generate_config(name, "/tmp/mtb_scenes")
     for mode in modes:
-        base_flags = {"bvh": 16, "nobvh": MTB_FLAG_NO_LIST_BVH | 16, "wf": MTB_FLAG_WAVEFRONT, "wfsort": MTB_FLAG_WAVEFRONT | 8, "auto": 0, "noorder": 16 | 32, "persist": 16 | 64, "exact": 16 | 128, "pack": 16 | 256, "sync": 16 | 512, "resume": 16 | 1024, "wfexact": 4 | 128}.get(mode, 0)
+        base_flags = {"bvh": 16, "nobvh": MTB_FLAG_NO_LIST_BVH | 16, "wf": MTB_FLAG_WAVEFRONT, "wfsort": MTB_FLAG_WAVEFRONT | 8, "auto": 0, "noorder": 16 | 32, "persist": 16 | 64, "exact": 16 | 128, "pack": 16 | 256, "sync": 16 | 512, "resume": 16 | 1024, "hybrid": 2048, "wfexact": 4 | 128}.get(mode, 0)
         mt = MythTracer(max_depth=cfg["depth"], flags=base_flags)
         t0 = time.time(); assert mt.LoadObj(files.obj_path); t_load = time.time() - t0
         mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]
         w, h = cfg["width"], cfg["height"]
         best = None
-        for it in range(3):
+        for it in range(5):
             r = mt.render_chunk(files.camera, w, h, 0, 0, w, h)
             s = r["stats"]
             if best is None or s["kernel_ms"] < best["kernel_ms"]: best = s

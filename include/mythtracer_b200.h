@@ -116,11 +116,11 @@ typedef struct {
 
 #define MTB_FLAG_COUNT_WORK 1u   /* fill the n_* work counters (counting kernels) */
 #define MTB_FLAG_NO_LIST_BVH 2u  /* scan every node list linearly, like the reference (A/B measurements) */
-/* Pipeline choice.  With neither bit set the library decides at run time: on the first frames of a given
- * geometry (chunk size, partition, depth, light count) it times the per-pixel megakernel (second frame, once
- * its cost-aware tile order is warm) and the wavefront pipeline (fourth frame, once its buffers exist) and
- * keeps the faster one from the fifth frame on.  Both
- * produce identical bytes, so the choice is invisible in the output. */
+/* Pipeline choice.  With none of the three bits set the library decides at run time: on the first frames of a
+ * given geometry (chunk size, partition, depth, light count) it times the per-pixel megakernel (second frame, once
+ * its cost-aware tile order is warm), the wavefront pipeline (fourth frame, once its buffers exist) and the hybrid
+ * split (sixth frame) and keeps the fastest from the seventh frame on.  All three produce identical bytes, so the
+ * choice is invisible in the output. */
 #define MTB_FLAG_WAVEFRONT 4u    /* force the wavefront pipeline */
 #define MTB_FLAG_MEGAKERNEL 16u  /* force the per-pixel megakernel */
 #define MTB_FLAG_HYBRID 2048u    /* force hybrid frames: the tiles that were most expensive in the previous frame go through the wavefront, the rest through the megakernel, concurrently */

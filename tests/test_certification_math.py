@@ -1,0 +1,234 @@
+"""CPU checks of the arithmetic claims the certified fast traversal rests on (device code in
+mythtracer_b200/csrc/device_core.cuh).  Nothing here touches the GPU or the oracle: the device formulas are restated
+with Python floats (IEEE double, one rounding per operation, no contraction -- what --fmad=false gives) and numpy
+float32, and compared with exact rational arithmetic (fractions.Fraction over the same binary inputs).
+
+  * MollerTrumboreBound: |t_computed - t_exact| <= e for every accepted hit, also for sliver / grazing cases
+  * FastBox: the FP32 slab test over padded, outward-rounded boxes accepts whenever the exact FP64 pre-test
+    (primitive_triangle.cc:85-108) does, and its entry distance is a lower bound of the FP64 one
+  * LimitPrune: the worst-case bound M(T) dominates the error bound of every accepted hit whose box is entered at T
+"""
+import math
+import random
+from fractions import Fraction
+
+import numpy as np
+
+U49, U50, U48 = 2.0 ** -49, 2.0 ** -50, 2.0 ** -48
+
+
+def _sub(a, b):
+    return (a[0] - b[0], a[1] - b[1], a[2] - b[2])
+
+
+def _cross(t, a):  # math3d.h:120-126, this.Cross(a)
+    return (t[1] * a[2] - t[2] * a[1], t[2] * a[0] - t[0] * a[2], t[0] * a[1] - t[1] * a[0])
+
+
+def _dot(a, b):
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]
+
+
+def moller_trumbore_bound(v0, v1, v2, o, d):
+    """MollerTrumboreBound of device_core.cuh: (accepted, t, e)."""
+    e1, e2 = _sub(v1, v0), _sub(v2, v0)
+    pvec = _cross(d, e2)
+    det = _dot(e1, pvec)
+    if -0.00000001 <= det < 0.00000001:
+        return False, 0.0, 0.0
+    tvec = _sub(o, v0)
+    un = _dot(tvec, pvec)
+    us = un if det > 0.0 else -un
+    if us < -1e-200 or us > abs(det) * 1.0000000001:
+        early = True
+    else:
+        early = False
+    inv_det = 1.0 / det
+    u = un * inv_det
+    rejected_by_u = u < 0.0 or u > 1.0
+    assert not early or rejected_by_u, "the division-free reject must agree with the reference's u test"
+    if rejected_by_u:
+        return False, 0.0, 0.0
+    qvec = _cross(tvec, e1)
+    v = _dot(d, qvec) * inv_det
+    if v < 0.0 or u + v > 1.0:
+        return False, 0.0, 0.0
+    t = _dot(e2, qvec) * inv_det
+    if t < 0.0:
+        return False, 0.0, 0.0
+    ad, a1, a2, at = [tuple(abs(x) for x in w) for w in (d, e1, e2, tvec)]
+    D = a1[0] * (ad[1] * a2[2] + ad[2] * a2[1]) + a1[1] * (ad[2] * a2[0] + ad[0] * a2[2]) + a1[2] * (ad[0] * a2[1] + ad[1] * a2[0])
+    N = a2[0] * (at[1] * a1[2] + at[2] * a1[1]) + a2[1] * (at[2] * a1[0] + at[0] * a1[2]) + a2[2] * (at[0] * a1[1] + at[1] * a1[0])
+    e_det, e_num = U49 * D, U49 * N
+    den = abs(det) - e_det
+    e = (e_num + t * e_det) / den + U50 * t if den > 0.0 else math.inf
+    return True, t, e
+
+
+def exact_t(v0, v1, v2, o, d):
+    F = lambda w: tuple(Fraction(x) for x in w)
+    v0, v1, v2, o, d = F(v0), F(v1), F(v2), F(o), F(d)
+    e1, e2 = _sub(v1, v0), _sub(v2, v0)
+    det = _dot(e1, _cross(d, e2))
+    if det == 0:
+        return None
+    return _dot(e2, _cross(_sub(o, v0), e1)) / det
+
+
+def _random_case(rng, kind):
+    R = 400.0
+    scale = 10.0 ** rng.uniform(-3, 2)
+    c = [rng.uniform(-R, R) for _ in range(3)]
+    v = [[c[a] + rng.uniform(-scale, scale) for a in range(3)] for _ in range(3)]
+    # aim at a point inside the triangle so that most cases are accepted
+    w = [rng.random() for _ in range(3)]
+    s = sum(w)
+    target = [sum(w[k] / s * v[k][a] for k in range(3)) for a in range(3)]
+    if kind == "grazing":  # origin almost in the triangle's plane
+        e1 = [v[1][a] - v[0][a] for a in range(3)]
+        back = 10.0 ** rng.uniform(0, 2.5)
+        n1 = math.sqrt(sum(x * x for x in e1)) or 1.0
+        o = [target[a] - e1[a] / n1 * back + rng.uniform(-1, 1) * 10.0 ** rng.uniform(-9, -3) for a in range(3)]
+    else:
+        o = [rng.uniform(-R, R) for _ in range(3)]
+    d = [target[a] - o[a] for a in range(3)]
+    n = math.sqrt(sum(x * x for x in d)) or 1.0
+    stretch = 1.0 if kind != "unnormalised" else 10.0 ** rng.uniform(-1, 1)  # reflected rays are not unit length
+    d = [x / n * stretch for x in d]
+    return tuple(v[0]), tuple(v[1]), tuple(v[2]), tuple(o), tuple(d)
+
+
+def test_moller_trumbore_error_bound_holds():
+    rng = random.Random(11)
+    accepted = finite = 0
+    worst = 0.0
+    for i in range(9000):
+        kind = ("plain", "grazing", "unnormalised")[i % 3]
+        v0, v1, v2, o, d = _random_case(rng, kind)
+        ok, t, e = moller_trumbore_bound(v0, v1, v2, o, d)
+        if not ok:
+            continue
+        accepted += 1
+        if not math.isfinite(e):
+            continue  # an infinite bound makes the ray ambiguous: the exact recursion decides
+        finite += 1
+        tx = exact_t(v0, v1, v2, o, d)
+        err = abs(Fraction(t) - tx)
+        assert err <= Fraction(e), (kind, t, float(tx), e, float(err))
+        if e > 0:
+            worst = max(worst, float(err) / e)
+    assert accepted > 4000 and finite > 3500
+    assert worst < 0.6, "the bound is supposed to have at least ~2x slack (%.3f)" % worst
+
+
+def test_division_free_reject_agrees_with_the_u_test():
+    """Far misses: `us < -1e-200 || us > |det| * (1 + 1e-10)` must imply the reference's `u < 0 || u > 1` (asserted
+    inside moller_trumbore_bound), and must fire for most of them; includes denormal-sized numerators."""
+    rng = random.Random(3)
+    misses = 0
+    for i in range(20000):
+        v0, v1, v2, o, d = _random_case(rng, "plain")
+        # move the ray sideways so that it misses the triangle by up to a few triangle sizes, or scale everything
+        # down towards the denormal range every 10th case
+        shift = [rng.uniform(-1, 1) * 10.0 ** rng.uniform(-3, 2) for _ in range(3)]
+        o = tuple(o[a] + shift[a] for a in range(3))
+        if i % 10 == 0:
+            s = 10.0 ** rng.uniform(-160, -100)
+            v0, v1, v2, o = [tuple(x * s for x in w) for w in (v0, v1, v2, o)]
+        ok, t, e = moller_trumbore_bound(v0, v1, v2, o, d)
+        misses += 0 if ok else 1
+    assert misses > 5000
+
+
+def _round_out(lo, hi):
+    flo, fhi = np.float32(lo), np.float32(hi)
+    if float(flo) > lo:
+        flo = np.nextafter(flo, np.float32(-np.inf))
+    if float(fhi) < hi:
+        fhi = np.nextafter(fhi, np.float32(np.inf))
+    return flo, fhi
+
+
+def _fma32(a, b, c):
+    # a * b is exact in double (24 + 24 bits); one more rounding to float: within half an ulp32 of the true fma
+    return np.float32(float(a) * float(b) + float(c))
+
+
+def test_fast_box_is_conservative():
+    rng = random.Random(5)
+    R = 400.0
+    pad = 2.0 ** -17 * R * 1.000001
+    k_rel = np.float32(2.0 ** -21)
+    checked = passed64 = 0
+    for i in range(20000):
+        size = 10.0 ** rng.uniform(-3, 2)
+        c = [rng.uniform(-R, R - size) for _ in range(3)]
+        lo = [c[a] for a in range(3)]
+        hi = [min(R, c[a] + rng.uniform(0, size)) for a in range(3)]
+        o = [rng.uniform(-8 * R, 8 * R) if i % 4 == 0 else rng.uniform(-R, R) for _ in range(3)]
+        # aim through the box (or near it), with one component made tiny every other case
+        tgt = [rng.uniform(lo[a] - 0.01 * size, hi[a] + 0.01 * size) for a in range(3)]
+        d = [tgt[a] - o[a] for a in range(3)]
+        n = math.sqrt(sum(x * x for x in d)) or 1.0
+        d = [x / n for x in d]
+        if i % 2 == 0:
+            d[rng.randrange(3)] = rng.choice([-1, 1]) * 10.0 ** rng.uniform(-12, -3)
+        if any(x == 0.0 for x in d):
+            continue
+        inv = [1.0 / x for x in d]
+        # the exact FP64 pre-test (SlabRegular == primitive_triangle.cc:85-108 for regular rays)
+        near = [((hi[a] if inv[a] < 0 else lo[a]) - o[a]) * inv[a] for a in range(3)]
+        far = [((lo[a] if inv[a] < 0 else hi[a]) - o[a]) * inv[a] for a in range(3)]
+        tmax, tmin = min(far), max(near)
+        pass64 = not (tmax < 0.0) and not (tmin > tmax)
+        # FastBox on the padded, outward-rounded float box
+        of = [np.float32(x) for x in o]
+        fi = [np.float32(x) for x in inv]
+        no = [-(of[a] * fi[a]) for a in range(3)]
+        box = [_round_out(lo[a] - pad, hi[a] + pad) for a in range(3)]
+        n32 = [_fma32(box[a][1] if inv[a] < 0 else box[a][0], fi[a], no[a]) for a in range(3)]
+        f32 = [_fma32(box[a][0] if inv[a] < 0 else box[a][1], fi[a], no[a]) for a in range(3)]
+        tn, tf = max(n32), min(f32)
+        tn = _fma32(-k_rel, abs(tn), tn)
+        tf = _fma32(k_rel, abs(tf), tf)
+        pass32 = bool(tf >= 0.0 and tn <= tf)
+        checked += 1
+        if pass64:
+            passed64 += 1
+            assert pass32, (lo, hi, o, d, tmin, tmax, float(tn), float(tf))
+            assert float(tn) <= tmin, (float(tn), tmin)
+    assert checked > 15000 and passed64 > 5000
+
+
+def limit_margin(L, dmax, T):
+    """M(T) of LimitPrune (the code prunes at t_limit + 2 M)."""
+    k = U48 * 6.0 * L * L
+    den = 0.00000001 - k * dmax
+    if not den > 0.000000005:
+        return math.inf
+    return k * (2.0 * dmax * T + L) / den + (2.0 ** -49) * T
+
+
+def test_limit_margin_dominates_the_error_bound():
+    rng = random.Random(23)
+    n = 0
+    worst = 0.0
+    for i in range(9000):
+        v0, v1, v2, o, d = _random_case(rng, ("plain", "grazing", "unnormalised")[i % 3])
+        ok, t, e = moller_trumbore_bound(v0, v1, v2, o, d)
+        if not ok or not math.isfinite(e):
+            continue
+        L = max(max(v0[a], v1[a], v2[a]) - min(v0[a], v1[a], v2[a]) for a in range(3))
+        dmax = max(abs(x) for x in d)
+        # entry distance of the triangle's box: T <= t (the hit lies inside the box)
+        inv = [1.0 / x for x in d]
+        lo = [min(v0[a], v1[a], v2[a]) for a in range(3)]
+        hi = [max(v0[a], v1[a], v2[a]) for a in range(3)]
+        T = max(max(((hi[a] if inv[a] < 0 else lo[a]) - o[a]) * inv[a] for a in range(3)), 0.0)
+        M = limit_margin(L, dmax, T)
+        if not math.isfinite(M):
+            continue
+        n += 1
+        assert e <= M, (e, M, L, dmax, T, t)
+        worst = max(worst, e / M if M > 0 else 0.0)
+    assert n > 3000

@@ -232,3 +232,64 @@ def test_limit_margin_dominates_the_error_bound():
         assert e <= M, (e, M, L, dmax, T, t)
         worst = max(worst, e / M if M > 0 else 0.0)
     assert n > 3000
+
+
+def test_unambiguous_winner_is_the_recursions_winner(oracle_mod):
+    """The certification rule itself, on the CPU: over ALL triangles whose exact reference test accepts a ray, take
+    the smallest t; if no other accepted hit's error interval touches the winner's (lo2 > t* + e*), the octree
+    recursion of the reference (oracle restatement, pinned bit for bit to the unmodified reference) must return that
+    very triangle with that very t.  The scene is built to provoke near-ties: every triangle also exists as a copy
+    displaced by 1e-13 .. 1e-9 and as an exact duplicate; those rays must come out ambiguous, not wrong."""
+    from mythtracer_b200.api import MTL_DTYPE, TRI_DTYPE
+    rng = random.Random(17)
+    nrng = np.random.default_rng(17)
+    base = np.zeros(60, TRI_DTYPE)
+    base["vertex"] = nrng.uniform(-6, 6, (60, 9))
+    base["vertex"][:, 2::3] += 10.0
+    near = base.copy()
+    near["vertex"] += nrng.uniform(-1, 1, (60, 9)) * (10.0 ** nrng.uniform(-13, -9, (60, 1)))
+    tris = np.concatenate([base, near, base[:20]])
+    tris["material"] = -1
+    tris["line_no"] = np.arange(len(tris))
+    orc = oracle_mod.Oracle(tris, np.zeros(0, MTL_DTYPE), [])
+    n_rays = 1500
+    o = nrng.uniform(-3, 3, (n_rays, 3))
+    d = nrng.normal(size=(n_rays, 3))
+    d[:, 2] = np.abs(d[:, 2]) + 1.5
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    ref = orc.intersect(o, d)
+    verts = [tuple(map(tuple, t.reshape(3, 3))) for t in tris["vertex"]]
+    boxes = [(tuple(min(v[k][a] for k in range(3)) for a in range(3)), tuple(max(v[k][a] for k in range(3)) for a in range(3))) for v in verts]
+    unambiguous = ambiguous = misses = 0
+    for r in range(n_rays):
+        ro, rd = tuple(o[r]), tuple(d[r])
+        inv = [1.0 / x for x in rd]
+        best = None
+        lo2 = math.inf
+        for k, (v0, v1, v2) in enumerate(verts):
+            lo, hi = boxes[k]
+            # the reference's AABB pre-test (primitive_triangle.cc:85-108), regular rays
+            near_t = max(((hi[a] if inv[a] < 0 else lo[a]) - ro[a]) * inv[a] for a in range(3))
+            far_t = min(((lo[a] if inv[a] < 0 else hi[a]) - ro[a]) * inv[a] for a in range(3))
+            if far_t < 0.0 or near_t > far_t:
+                continue
+            ok, t, e = moller_trumbore_bound(v0, v1, v2, ro, rd)
+            if not ok:
+                continue
+            if best is not None and not (t < best[0]):
+                lo2 = min(lo2, t - e)
+                continue
+            if best is not None:
+                lo2 = min(lo2, best[0] - best[1])
+            best = (t, e, k)
+        if best is None:
+            misses += 1
+            assert ref["tri"][r] == -1
+            continue
+        if lo2 <= best[0] + best[1]:
+            ambiguous += 1  # handed to the exact recursion on the device
+            continue
+        unambiguous += 1
+        assert ref["tri"][r] == best[2], (r, int(ref["tri"][r]), best)
+        assert ref["t"][r] == best[0]
+    assert ambiguous > 30 and unambiguous > 200, (unambiguous, ambiguous, misses)

@@ -293,3 +293,46 @@ def test_unambiguous_winner_is_the_recursions_winner(oracle_mod):
         assert ref["tri"][r] == best[2], (r, int(ref["tri"][r]), best)
         assert ref["t"][r] == best[0]
     assert ambiguous > 30 and unambiguous > 200, (unambiguous, ambiguous, misses)
+
+
+def test_stated_edge_case_sibling_entry_tie_is_a_property_of_the_reference(oracle_mod, tmp_path):
+    """DESIGN.md section 4, stated edge case (a), made concrete.  A regular ray that passes exactly through an edge of
+    the octree grid (computed entry distances of three sibling octants are EQUAL): the reference's recursion visits the
+    tied siblings in index order, accepts the hit it finds in the first one (t = 4.90) and stops, although a later
+    sibling holds a triangle that is hit at t = 3.0.  The unmodified reference and the oracle restatement agree on the
+    farther triangle; brute force over all triangles gives the nearer one -- which is also what a closest-hit search
+    (the device's default traversal for regular rays) returns.  MTB_FLAG_EXACT_OCTREE walks the recursion itself."""
+    from mythtracer_b200.api import MTL_DTYPE, TRI_DTYPE
+    tris = []
+
+    def tri(a, b, c):
+        tris.append([*a, *b, *c])
+    tri((1, 3, 1.0), (3, 1, 1.0), (2.2, 2.2, 3.9))        # octant 0 (x < 4, y < 4): hit at t = 4.90
+    tri((4, 4, 2.0), (4, 4, 3.25), (6, 2, 2.5))           # octant 1 (x >= 4, y <= 4): its edge lies ON the grid edge x = y = 4
+    tri((0, 0, 0), (0.3, 0, 0), (0, 0.3, 0))              # the root box is [0, 8]^3, centre (4, 4, 4)
+    tri((8, 8, 8), (7.7, 8, 8), (8, 7.7, 8))
+    rng = np.random.default_rng(1)
+    for _ in range(14):                                   # >= 16 primitives: the root splits (octtree.h:43)
+        c = np.array([6.5, 1.0, 6.5]) + rng.uniform(-0.4, 0.4, 3)
+        tri(c, c + [0.2, 0, 0], c + [0, 0.2, 0])
+    arr = np.zeros(len(tris), TRI_DTYPE)
+    arr["vertex"] = np.array(tris, float)
+    arr["material"] = -1
+    arr["line_no"] = np.arange(len(tris))
+    orc = oracle_mod.Oracle(arr, np.zeros(0, MTL_DTYPE), [])
+    o = np.array([[7.0, 7.0, 3.0]])
+    d = np.array([[-1.0, -1.0, -0.125]])                  # crosses x = 4 and y = 4 at t = 3 exactly
+    rec = orc.intersect(o, d)
+    brute = orc.intersect(o, d, brute=True)
+    assert rec["tri"][0] == 0 and abs(rec["t"][0] - 4.904347826086957) < 1e-12
+    assert brute["tri"][0] == 1 and brute["t"][0] == 3.0
+    if oracle_mod.Reference.available():
+        path = tmp_path / "edge.obj"
+        with open(path, "w") as f:
+            for t in tris:
+                for k in range(3):
+                    f.write("v %r %r %r\n" % (float(t[3 * k]), float(t[3 * k + 1]), float(t[3 * k + 2])))
+            for i in range(len(tris)):
+                f.write("f %d %d %d \n" % (3 * i + 1, 3 * i + 2, 3 * i + 3))
+        ref = oracle_mod.Reference(str(path)).intersect(o, d)
+        assert ref["line_no"][0] == 3 * len(tris) and abs(ref["t"][0] - rec["t"][0]) == 0.0

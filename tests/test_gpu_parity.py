@@ -677,3 +677,40 @@ def test_hybrid_frames(product_lib, oracle_mod, scene_dir):
         for k in ("rgb", "n_rays", "sig_hits", "sig_shadow"):
             assert np.array_equal(got[k], ref[k]), "C3 hybrid frame %d: %s" % (frame, k)
         assert got["stats"]["rays"] == ref["stats"]["rays"]
+
+
+def test_stated_edge_case_sibling_entry_tie_on_the_device(product_lib, oracle_mod):
+    """DESIGN.md section 4, stated edge case (a), on the device: for the constructed ray through an octree grid edge
+    (tests/test_certification_math.py has the construction and the reference's side of it) MTB_FLAG_EXACT_OCTREE must
+    return what the reference returns -- the FARTHER triangle, bit-identical t -- while the default closest-hit
+    traversal returns the nearer one.  This is the one place where the default is allowed to differ, and does."""
+    from mythtracer_b200 import MythTracer, MTB_FLAG_EXACT_OCTREE
+    from mythtracer_b200.api import MTL_DTYPE, TRI_DTYPE
+    tris = []
+
+    def tri(a, b, c):
+        tris.append([*a, *b, *c])
+    tri((1, 3, 1.0), (3, 1, 1.0), (2.2, 2.2, 3.9))
+    tri((4, 4, 2.0), (4, 4, 3.25), (6, 2, 2.5))
+    tri((0, 0, 0), (0.3, 0, 0), (0, 0.3, 0))
+    tri((8, 8, 8), (7.7, 8, 8), (8, 7.7, 8))
+    rng = np.random.default_rng(1)
+    for _ in range(14):
+        c = np.array([6.5, 1.0, 6.5]) + rng.uniform(-0.4, 0.4, 3)
+        tri(c, c + [0.2, 0, 0], c + [0, 0.2, 0])
+    arr = np.zeros(len(tris), TRI_DTYPE)
+    arr["vertex"] = np.array(tris, float)
+    arr["material"] = -1
+    arr["line_no"] = np.arange(len(tris))
+    o = np.array([[7.0, 7.0, 3.0]])
+    d = np.array([[-1.0, -1.0, -0.125]])
+    ref = oracle_mod.Oracle(arr, np.zeros(0, MTL_DTYPE), []).intersect(o, d)
+    assert ref["tri"][0] == 0
+    exact = MythTracer(flags=MTB_FLAG_EXACT_OCTREE)
+    exact.upload(arr, np.zeros(0, MTL_DTYPE))
+    got = exact.intersect_rays(o, d)
+    assert got["tri"][0] == 0 and got["t"][0] == ref["t"][0]
+    fast = MythTracer()
+    fast.upload(arr, np.zeros(0, MTL_DTYPE))
+    got = fast.intersect_rays(o, d)
+    assert got["tri"][0] == 1 and got["t"][0] == 3.0

@@ -124,12 +124,14 @@ typedef struct {
 #define MTB_FLAG_WAVEFRONT 4u    /* force the wavefront pipeline */
 #define MTB_FLAG_MEGAKERNEL 16u  /* force the per-pixel megakernel */
 #define MTB_FLAG_HYBRID 2048u    /* force hybrid frames: the tiles that were most expensive in the previous frame go through the wavefront, the rest through the megakernel, concurrently */
-#define MTB_FLAG_RAY_SORT 8u     /* wavefront: counting-sort every queue by origin cell + direction octant (measured: no gain) */
 #define MTB_FLAG_EXACT_OCTREE 128u /* every regular ray walks the octree in the reference's recursion order (no certified fast traversal) */
-#define MTB_FLAG_PACKING 256u /* megakernel: 16x8 tiles per 128-thread block, the rays of an iteration are handed to the first threads of the block (A/B; measured slower: fewer tracing warps hide less latency) */
-#define MTB_FLAG_RESUME 1024u /* megakernel: suspendable walks -- finished lanes shade and start their next ray while longer rays of the warp are parked */
-#define MTB_FLAG_WARP_SYNC 512u /* megakernel: finished lanes idle in the loop so that __syncwarp() re-converges the warp in front of every Trace call */
-#define MTB_FLAG_PERSISTENT 64u /* megakernel: persistent warps whose lanes draw their next pixel from a counter instead of one 8x8 tile per block (A/B; measured slower: the refilled lanes trace incoherent rays) */
+/* Retired A/B forms of round 1 (all bit-identical, all measured slower on B200; DESIGN.md section 5 keeps the
+ * numbers).  The bits are still accepted and ignored, so callers that set them keep working. */
+#define MTB_FLAG_RAY_SORT 8u      /* was: wavefront, counting-sort every queue by origin cell + direction octant */
+#define MTB_FLAG_PACKING 256u     /* was: megakernel, block-level ray packing on 16x8 tiles */
+#define MTB_FLAG_RESUME 1024u     /* was: megakernel, suspendable walks */
+#define MTB_FLAG_WARP_SYNC 512u   /* was: megakernel, forced warp re-convergence in front of every traversal */
+#define MTB_FLAG_PERSISTENT 64u   /* was: megakernel, persistent warps drawing pixels from a counter */
 #define MTB_FLAG_NO_TILE_ORDER 32u /* megakernel: always launch tiles in scanline order (A/B of the cost-aware launch order) */
 
 /* ---- life cycle -------------------------------------------------------------------------------- */
@@ -197,7 +199,7 @@ int mtb_render_chunk(mtb_context *ctx, const mtb_camera *cam, int image_w, int i
 
 /* Frame sequencing (reference main_local.cc:51-149 renders, then writes, then renders ...): the same render as
  * mtb_render_chunk, enqueued without waiting -- the call returns as soon as the kernels and the device->host copy
- * of the frame are queued (megakernel pipeline; the wavefront pipeline still reads one counter per level).  rgb_out
+ * of the frame are queued (no pipeline reads anything back while a frame is in flight).  rgb_out
  * must stay valid until mtb_wait returns and should come from mtb_host_alloc (pinned memory) for the copy to be
  * asynchronous.  With two such buffers a driver writes frame k to disk while frame k+1 renders
  * (apps/mythtracer_local_b200.cc). */
@@ -216,6 +218,20 @@ int mtb_render_chunk_device(mtb_context *ctx, const mtb_camera *cam, int image_w
                             int chunk_y, int chunk_w, int chunk_h, int max_depth, void *d_rgb, void *stream,
                             mtb_stats *stats);
 
+/* Frames shared between processes - the in-box form of the master's frame that workers blit into
+ * (main_net_master.cc:223-236) when every GPU is driven by its own process.  The gathering process creates the frame
+ * on its device and passes the 64-byte handle to the others by any means (bench.py: torch.distributed broadcast);
+ * they open it and hand the mapped pointer to mtb_render_chunk_device as d_rgb: with mtb_set_partition in effect
+ * their kernels then store the tiles they own straight into the gatherer's HBM over NVLink (cudaIpc* peer mapping),
+ * and the frame is complete when every process has finished its call - no gather copy, no collective on the data
+ * path.  mtb_frame_release frees (creator) or unmaps (opener) the frame; mtb_destroy releases what is left. */
+#define MTB_FRAME_HANDLE_BYTES 64
+int mtb_frame_create(mtb_context *ctx, size_t bytes, void **d_ptr, unsigned char handle[MTB_FRAME_HANDLE_BYTES]);
+int mtb_frame_open(mtb_context *ctx, const unsigned char handle[MTB_FRAME_HANDLE_BYTES], void **d_ptr);
+int mtb_frame_release(mtb_context *ctx, void *d_ptr);
+/* Waits for the context's devices, then copies `bytes` bytes at `offset` of a frame to host memory. */
+int mtb_frame_read(mtb_context *ctx, const void *d_ptr, size_t offset, size_t bytes, void *host_out);
+
 /* Work counters accumulated by mtb_render_chunk_device calls that passed stats == NULL since the last
  * read; synchronises every device of the context and resets the counters. */
 int mtb_read_counters(mtb_context *ctx, mtb_stats *stats);
@@ -227,7 +243,10 @@ int mtb_pipeline_in_use(const mtb_context *ctx, float *mega_ms, float *wavefront
 uint64_t mtb_launch_count(const mtb_context *ctx);
 
 /* Batched OctTree::IntersectRay (octtree.cc:26-40).  HOST arrays: origins/dirs n*3, tri_index n (insertion
- * index, -1 = nullptr), t n, point n*3 (nullable). */
+ * index, -1 = nullptr), t n, point n*3 (nullable).  Miss contract: tri_index[i] = -1, t[i] = NaN, point[i] = NaN
+ * (the reference leaves its out-parameters untouched on a miss, octtree.cc:36-39; a batched call writes whole
+ * arrays, so the untouched state is spelled NaN).  The C++ shim's single-ray IntersectRay leaves *point and
+ * *distance untouched on a miss like the reference. */
 int mtb_intersect_rays(mtb_context *ctx, int64_t n, const double *origins, const double *dirs, int32_t *tri_index,
                        double *t, double *point, mtb_stats *stats);
 

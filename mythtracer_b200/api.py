@@ -43,6 +43,7 @@ MTB_FLAG_WARP_SYNC = 512
 MTB_FLAG_RESUME = 1024
 MTB_FLAG_HYBRID = 2048
 MAX_RECURSION_LEVEL = 5  # reference mythtracer.h:11 (a run-time argument here)
+FRAME_HANDLE_BYTES = 64
 
 TRI_DTYPE = np.dtype([("vertex", "f8", (9,)), ("normal", "f8", (9,)), ("uvw", "f8", (9,)),
                       ("material", "i4"), ("line_no", "i4")], align=True)
@@ -73,6 +74,7 @@ EXPORTED_SYMBOLS = [
     "mtb_set_lights", "mtb_scene_info", "mtb_scene_read", "mtb_scene_material_name", "mtb_scene_texture_name", "mtb_scene_texture", "mtb_load_mtl",
     "mtb_scene_triangle_nodes", "mtb_scene_bvh", "mtb_set_flags", "mtb_set_partition", "mtb_render_chunk",
     "mtb_render_chunk_device", "mtb_render_chunk_async", "mtb_wait", "mtb_host_alloc", "mtb_host_free", "mtb_read_counters", "mtb_launch_count", "mtb_pipeline_in_use", "mtb_intersect_rays", "mtb_camera_sensor", "mtb_version",
+    "mtb_frame_create", "mtb_frame_open", "mtb_frame_release", "mtb_frame_read",
 ]
 
 
@@ -130,6 +132,11 @@ def load_library():
     lib.mtb_launch_count.restype = ctypes.c_uint64
     lib.mtb_intersect_rays.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp]
     lib.mtb_camera_sensor.argtypes = [vp, i32, i32, vp]
+    lib.mtb_wait.argtypes = [vp]
+    lib.mtb_frame_create.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp), vp]
+    lib.mtb_frame_open.argtypes = [vp, vp, ctypes.POINTER(vp)]
+    lib.mtb_frame_release.argtypes = [vp, vp]
+    lib.mtb_frame_read.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_size_t, vp]
     lib.mtb_version.restype = ctypes.c_char_p
     _lib = lib
     return lib
@@ -459,6 +466,35 @@ class MythTracer:
 
     def push_lights(self):
         self._push_lights()
+
+    def wait(self):
+        """mtb_wait: everything queued on the context's devices has finished."""
+        self._check(self._lib.mtb_wait(self._ctx), "mtb_wait")
+
+    # -- frames shared between processes (one process per GPU; include/mythtracer_b200.h) --
+    def frame_create(self, n_bytes: int):
+        """-> (device pointer, 64-byte handle other processes pass to frame_open)."""
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * FRAME_HANDLE_BYTES)()
+        self._check(self._lib.mtb_frame_create(self._ctx, n_bytes, ctypes.byref(ptr), handle), "mtb_frame_create")
+        return int(ptr.value), bytes(handle)
+
+    def frame_open(self, handle: bytes) -> int:
+        ptr = ctypes.c_void_p()
+        buf = (ctypes.c_ubyte * FRAME_HANDLE_BYTES).from_buffer_copy(bytes(handle))
+        self._check(self._lib.mtb_frame_open(self._ctx, buf, ctypes.byref(ptr)), "mtb_frame_open")
+        return int(ptr.value)
+
+    def frame_release(self, ptr: int):
+        self._check(self._lib.mtb_frame_release(self._ctx, ctypes.c_void_p(ptr)), "mtb_frame_release")
+
+    def frame_read(self, ptr: int, n_bytes: int, offset: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Copies n_bytes of a frame to the host (waits for the context's queued work first)."""
+        if out is None:
+            out = np.zeros(n_bytes, np.uint8)
+        assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size >= n_bytes
+        self._check(self._lib.mtb_frame_read(self._ctx, ctypes.c_void_p(ptr), offset, n_bytes, _ptr(out)), "mtb_frame_read")
+        return out
 
     def pipeline_in_use(self):
         """('mega' | 'wavefront' | 'hybrid' | 'measuring', mega_ms, wavefront_ms) of the automatic choice on device 0."""

@@ -61,7 +61,8 @@ struct DeviceState {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   cudaEvent_t ev_gathered = nullptr;  // device 0 only: the last gather has read every peer buffer
-  bool peer_to_dev0 = false;
+  bool peer_to_dev0 = false;     // device 0 can read this device's memory (peer-copy gather)
+  bool peer_store_dev0 = false;  // this device's kernels can store into device 0's memory (direct tile stores)
   // scene
   DeviceBuffer<mtb::NodeRec> nodes;
   DeviceBuffer<mtb::SlotRec> slots;
@@ -70,6 +71,7 @@ struct DeviceState {
   DeviceBuffer<mtb::Bvh2Node> gnodes;   // scene BVH of the certified fast traversal
   DeviceBuffer<mtb::SlotRec> gslots;
   DeviceBuffer<int32_t> list_order;
+  DeviceBuffer<int32_t> slot_node;
   DeviceBuffer<mtb_material> materials;
   DeviceBuffer<int2> tex_dims;
   DeviceBuffer<mtb_light> lights;
@@ -85,7 +87,6 @@ struct DeviceState {
   // cost-aware tile order of the megakernel (previous frame's per-tile ray counts)
   DeviceBuffer<uint32_t> tile_cost;
   DeviceBuffer<int32_t> tile_order;
-  DeviceBuffer<uint32_t> work_counter;  // persistent megakernel: next work item
   long long tile_signature = -1;  // geometry the costs were recorded for
   // run-time choice between the two pipelines (flags without a pipeline bit): both are timed once per
   // geometry (megakernel with a warm tile order, then wavefront) and the faster one is kept
@@ -115,16 +116,20 @@ struct DeviceState {
   cudaEvent_t wf_ev_side[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t wf_ev_level[MTB_MAX_RAY_DEPTH + 2] = {};  // level L traced (main stream)
   cudaEvent_t wf_ev_lit = nullptr;               // all lights folded (second stream)
-  DeviceBuffer<uint32_t> wf_counters, wf_sort_key[2], wf_sort_hist;
-  DeviceBuffer<int32_t> wf_perm;
-  uint32_t *wf_host_counters = nullptr;  // pinned
-  int wf_queue_factor = 2, wf_act_factor = 6;  // capacities in units of the pixel-slot count; grown on overflow
+  DeviceBuffer<uint32_t> wf_level_n, wf_ctrl;
+  DeviceBuffer<unsigned long long> wf_work;
+  // pinned; written by WfCommit at the end of every frame (level counts, overflow flag, frame sequence number) and read
+  // by the host at the START of the next frame only: grid sizes and queue capacities follow the scene with one frame
+  // of delay and without a single host read-back while a frame is in flight
+  uint32_t *wf_host = nullptr;
+  uint32_t wf_seen_sequence = 0;
+  int wf_queue_factor = 2, wf_act_factor = 6;  // capacities in units of the pixel-slot count; doubled after an overflow
   mtb::WfBuffers wf{};
 
   void FreeAll() {
-    nodes.Free(); slots.Free(); shade.Free(); bvh.Free(); gnodes.Free(); gslots.Free(); list_order.Free(); materials.Free();
+    nodes.Free(); slots.Free(); shade.Free(); bvh.Free(); gnodes.Free(); gslots.Free(); list_order.Free(); slot_node.Free(); materials.Free();
     tex_dims.Free(); lights.Free(); rgb.Free(); dbg.Free(); sig_hits.Free(); sig_shadow.Free(); n_rays.Free();
-    counters.Free(); tile_cost.Free(); tile_order.Free(); work_counter.Free(); heavy_k.Free();
+    counters.Free(); tile_cost.Free(); tile_order.Free(); heavy_k.Free();
     if (hybrid_stream != nullptr) cudaStreamDestroy(hybrid_stream);
     hybrid_stream = nullptr;
     if (ev_split != nullptr) cudaEventDestroy(ev_split);
@@ -133,13 +138,10 @@ struct DeviceState {
     for (int k = 0; k < 2; k++) {
       wf_rq_o[k].Free(); wf_rq_d[k].Free(); wf_rq_coef[k].Free(); wf_rq_path[k].Free(); wf_rq_pixel[k].Free();
       wf_rq_inobj[k].Free();
-      wf_sort_key[k].Free();
     }
-    wf_sort_hist.Free();
-    wf_perm.Free();
     wf_act_point.Free(); wf_act_normal.Free(); wf_act_surface.Free(); wf_act_reflected.Free(); wf_act_dir.Free();
     wf_sh_power.Free(); wf_sh_flags.Free(); wf_act_color.Free(); wf_act_refl.Free(); wf_act_refr.Free();
-    wf_act_mtl.Free(); wf_act_pixel.Free(); wf_act_path.Free(); wf_counters.Free();
+    wf_act_mtl.Free(); wf_act_pixel.Free(); wf_act_path.Free(); wf_level_n.Free(); wf_ctrl.Free(); wf_work.Free();
     if (wf_stream2 != nullptr) cudaStreamDestroy(wf_stream2);
     wf_stream2 = nullptr;
     for (cudaStream_t &st : wf_side) {
@@ -156,8 +158,8 @@ struct DeviceState {
     }
     if (wf_ev_lit != nullptr) cudaEventDestroy(wf_ev_lit);
     wf_ev_lit = nullptr;
-    if (wf_host_counters != nullptr) cudaFreeHost(wf_host_counters);
-    wf_host_counters = nullptr;
+    if (wf_host != nullptr) cudaFreeHost(wf_host);
+    wf_host = nullptr;
   }
 };
 
@@ -177,6 +179,8 @@ struct mtb_context {
   std::vector<mtb_light> lights;
   int64_t device_bytes = 0;
   std::atomic<uint64_t> launches{0};  // kernels of this library launched so far (mtb_launch_count)
+  bool no_peer_store = false;         // MTB_NO_PEER_STORE=1: gather with peer copies instead of direct tile stores (A/B)
+  std::vector<void *> owned_frames, opened_frames;  // mtb_frame_create / mtb_frame_open
   std::mutex err_mutex;
 };
 
@@ -205,6 +209,7 @@ int UploadToDevice(mtb_context *ctx, DeviceState *d) {
   MTB_CUDA(ctx, d->shade.Upload(f.shade.data(), f.shade.size(), d->stream));
   MTB_CUDA(ctx, d->bvh.Upload(f.bvh.data(), f.bvh.size(), d->stream));
   MTB_CUDA(ctx, d->list_order.Upload(f.list_order.data(), f.list_order.size(), d->stream));
+  MTB_CUDA(ctx, d->slot_node.Upload(f.slot_node.data(), f.slot_node.size(), d->stream));
   MTB_CUDA(ctx, d->gnodes.Upload(f.gnodes.data(), f.gnodes.size(), d->stream));
   MTB_CUDA(ctx, d->gslots.Upload(f.gslots.data(), f.gslots.size(), d->stream));
   MTB_CUDA(ctx, d->materials.Upload(ctx->materials.data(), ctx->materials.size(), d->stream));
@@ -260,6 +265,7 @@ int UploadToDevice(mtb_context *ctx, DeviceState *d) {
   d->scene.shade = d->shade.ptr;
   d->scene.bvh = d->bvh.ptr;
   d->scene.list_order = d->list_order.ptr;
+  d->scene.slot_node = d->slot_node.ptr;
   d->scene.materials = d->materials.ptr;
   d->scene.texture_dim = d->tex_dims.ptr;
   d->scene.n_materials = (int32_t)ctx->materials.size();
@@ -305,7 +311,7 @@ int BuildAndUpload(mtb_context *ctx) {
   ctx->device_bytes = (int64_t)(ctx->flat.nodes.size() * sizeof(mtb::NodeRec) + ctx->flat.slots.size() * sizeof(mtb::SlotRec) +
                                 ctx->flat.shade.size() * sizeof(mtb::ShadeRec) + ctx->flat.bvh.size() * sizeof(mtb::BvhRec) +
                                 ctx->flat.gnodes.size() * sizeof(mtb::Bvh2Node) + ctx->flat.gslots.size() * sizeof(mtb::SlotRec) +
-                                ctx->flat.list_order.size() * 4 + ctx->materials.size() * sizeof(mtb_material));
+                                ctx->flat.list_order.size() * 4 + ctx->flat.slot_node.size() * 4 + ctx->materials.size() * sizeof(mtb_material));
   for (const mtb::LoadedTexture &t : ctx->textures) ctx->device_bytes += (int64_t)t.rgba.size();
   for (DeviceState &d : ctx->dev) {
     const int urc = UploadToDevice(ctx, &d);
@@ -386,8 +392,6 @@ int EnsureWavefront(mtb_context *ctx, DeviceState *d, int slots, int n_lights) {
     MTB_CUDA(ctx, d->wf_rq_path[k].Reserve(qcap));
     MTB_CUDA(ctx, d->wf_rq_pixel[k].Reserve(qcap));
     MTB_CUDA(ctx, d->wf_rq_inobj[k].Reserve(qcap));
-    MTB_CUDA(ctx, d->wf_sort_key[k].Reserve(qcap));
-    d->wf.sort_key[k] = d->wf_sort_key[k].ptr;
     d->wf.rq_o[k] = d->wf_rq_o[k].ptr;
     d->wf.rq_d[k] = d->wf_rq_d[k].ptr;
     d->wf.rq_coef[k] = d->wf_rq_coef[k].ptr;
@@ -416,17 +420,13 @@ int EnsureWavefront(mtb_context *ctx, DeviceState *d, int slots, int n_lights) {
     for (cudaEvent_t &e : d->wf_ev_level) MTB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     MTB_CUDA(ctx, cudaEventCreateWithFlags(&d->wf_ev_lit, cudaEventDisableTiming));
   }
-  MTB_CUDA(ctx, d->wf_counters.Reserve(2));
-  MTB_CUDA(ctx, d->wf_sort_hist.Reserve((size_t)1 << mtb::kWfSortBits));
-  MTB_CUDA(ctx, d->wf_perm.Reserve(qcap));
-  d->wf.sort_hist = d->wf_sort_hist.ptr;
-  d->wf.perm = d->wf_perm.ptr;
-  for (int a = 0; a < 3; a++) {
-    const double lo = ctx->flat.aabb[a], ext = ctx->flat.aabb[3 + a] - ctx->flat.aabb[a];
-    d->wf.cell_lo[a] = (float)lo;
-    d->wf.cell_scale[a] = ext > 0.0 ? (float)(32.0 / ext) : 0.0f;
+  MTB_CUDA(ctx, d->wf_level_n.Reserve(MTB_MAX_RAY_DEPTH + 2));
+  MTB_CUDA(ctx, d->wf_ctrl.Reserve(2));
+  MTB_CUDA(ctx, d->wf_work.Reserve(mtb::kNumCounters));
+  if (d->wf_host == nullptr) {
+    MTB_CUDA(ctx, cudaMallocHost(reinterpret_cast<void **>(&d->wf_host), mtb::kWfHostWords * sizeof(uint32_t)));
+    memset(d->wf_host, 0, mtb::kWfHostWords * sizeof(uint32_t));
   }
-  if (d->wf_host_counters == nullptr) MTB_CUDA(ctx, cudaMallocHost(reinterpret_cast<void **>(&d->wf_host_counters), 2 * sizeof(uint32_t)));
   d->wf.act_point = d->wf_act_point.ptr;
   d->wf.act_normal = d->wf_act_normal.ptr;
   d->wf.act_surface = d->wf_act_surface.ptr;
@@ -440,85 +440,89 @@ int EnsureWavefront(mtb_context *ctx, DeviceState *d, int slots, int n_lights) {
   d->wf.act_mtl = d->wf_act_mtl.ptr;
   d->wf.act_pixel = d->wf_act_pixel.ptr;
   d->wf.act_path = d->wf_act_path.ptr;
-  d->wf.counters = d->wf_counters.ptr;
+  d->wf.level_n = d->wf_level_n.ptr;
+  d->wf.ctrl = d->wf_ctrl.ptr;
+  d->wf.work = d->wf_work.ptr;
   d->wf.queue_cap = (int32_t)qcap;
   d->wf.act_cap = (int32_t)acap;
   return MTB_OK;
 }
 
-// One frame (this device's strips) through the wavefront pipeline.  The host only reads one counter per
-// level (how many rays the next level holds); everything else stays on the device.
+// One frame (this device's strips / its share of a hybrid frame) through the wavefront pipeline: every kernel of
+// every level is enqueued at once, nothing is read back.  How many rays a level holds is only known on the device;
+// the grids are sized from the counts of the last completed frame of the same size (+25 %), else from the capacity
+// bound, and the kernels loop grid-strided over the real count.  If a queue overflows, the kernels of the remaining
+// levels exit at once and the RenderMega launch queued at the end renders the same tiles instead (same bytes); the
+// host sees the overflow flag at the start of the next frame and doubles the queues.
 int RunWavefront(mtb_context *ctx, DeviceState *d, const mtb::RenderParams &p, int n_blocks, bool debug_build,
                  cudaStream_t s) {
   const int slots = n_blocks * 64;
   if (slots <= 0) return MTB_OK;
-  for (int attempt = 0; attempt < 6; attempt++) {
-    const int rc = EnsureWavefront(ctx, d, slots, d->scene.n_lights);
-    if (rc != MTB_OK) return rc;
-    int level_begin[MTB_MAX_RAY_DEPTH + 2];
-    int n = slots, act_base = 0, last_level = 0;
-    bool overflow = false;
-    // Side streams: the shadow walks + Phong sums of level L only depend on the trace of level L, so the levels'
-    // side kernels go round-robin over four streams and overlap each other as well as the deeper traces (on a small
-    // share of a frame - one of 8 GPUs - every one of them is latency-bound and they were the critical path when
-    // serialised on one stream).
-    cudaStream_t side[4] = {d->wf_stream2, d->wf_side[0], d->wf_side[1], d->wf_side[2]};
-    // they must not start before earlier work on the main stream (previous frame, taps memset)
-    MTB_CUDA(ctx, cudaEventRecord(d->wf_ev_lit, s));
-    for (cudaStream_t st : side) MTB_CUDA(ctx, cudaStreamWaitEvent(st, d->wf_ev_lit, 0));
-    for (int level = 0; level <= p.max_depth; level++) {
-      last_level = level;
-      level_begin[level] = act_base;
-      MTB_CUDA(ctx, cudaMemsetAsync(d->wf.counters, 0, 2 * sizeof(uint32_t), s));
-      const bool sorted = level > 0 && (ctx->flags & MTB_FLAG_RAY_SORT) != 0;
-      if (sorted) mtb::LaunchWfSort(d->wf, level, n, s);
-      // critical path (main stream): trace the level, spawn the next one
-      mtb::LaunchWfTraceMain(d->scene, p, d->wf, level, n, act_base, sorted, debug_build, s);
-      MTB_CUDA(ctx, cudaEventRecord(d->wf_ev_level[level], s));
-      if (level < p.max_depth) mtb::LaunchWfSpawn(d->scene, p, d->wf, level, n, act_base, debug_build, s);
-      // side branch (second stream): shadow walks and the Phong sums of this level
-      cudaStream_t s2 = side[level & 3];
-      MTB_CUDA(ctx, cudaStreamWaitEvent(s2, d->wf_ev_level[level], 0));
-      mtb::LaunchWfShadow(d->scene, p, d->wf, act_base, n, debug_build, s2);
-      mtb::LaunchWfLight(d->scene, p, d->wf, act_base, n, s2);
-      ctx->launches += (sorted ? 3u : 0u) + 2u + (d->scene.n_lights > 0 ? 1u : 0u) + (level < p.max_depth ? 1u : 0u);
-      MTB_CUDA(ctx, cudaGetLastError());
-      if (level == p.max_depth) break;  // no children beyond MAX_RECURSION_LEVEL (mythtracer.cc:181,192)
-      MTB_CUDA(ctx, cudaMemcpyAsync(d->wf_host_counters, d->wf.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-      MTB_CUDA(ctx, cudaStreamSynchronize(s));
-      if (d->wf_host_counters[1] != 0u) {
-        overflow = true;
-        break;
+  // feedback of the frames completed so far (pinned memory written by WfCommit; a frame still in flight simply is not
+  // in it yet)
+  long long hint[MTB_MAX_RAY_DEPTH + 2];
+  bool have_hint = false;
+  if (d->wf_host != nullptr) {
+    const uint32_t seq = d->wf_host[mtb::kWfHostSequence];
+    if (seq != d->wf_seen_sequence) {
+      d->wf_seen_sequence = seq;
+      if (d->wf_host[mtb::kWfHostOverflow] != 0u) {
+        d->wf_queue_factor *= 2;
+        d->wf_act_factor *= 2;
       }
-      const int next = (int)d->wf_host_counters[0];
-      if (next == 0) break;
-      act_base += n;
-      n = next;
     }
-    // join: the folds need every level's colours
-    for (int k = 0; k < 4; k++) {
-      MTB_CUDA(ctx, cudaEventRecord(d->wf_ev_side[k], side[k]));
-      MTB_CUDA(ctx, cudaStreamWaitEvent(s, d->wf_ev_side[k], 0));
+    if (seq != 0u && d->wf_host[mtb::kWfHostOverflow] == 0u && d->wf_host[0] == (uint32_t)slots) {
+      have_hint = true;
+      for (int l = 0; l <= MTB_MAX_RAY_DEPTH + 1; l++) hint[l] = (long long)d->wf_host[l];
     }
-    if (overflow) {
-      for (cudaStream_t st : side) MTB_CUDA(ctx, cudaStreamSynchronize(st));  // the side branches still read the buffers about to be replaced
-      MTB_CUDA(ctx, cudaStreamSynchronize(s));
-      d->wf_queue_factor *= 2;
-      d->wf_act_factor *= 2;
-      continue;  // render the frame again with larger queues
-    }
-    level_begin[last_level + 1] = act_base + n;
-    for (int level = last_level - 1; level >= 0; level--) {
-      mtb::LaunchWfFold(d->scene, d->wf, level_begin[level], level_begin[level + 1], s);
-      ctx->launches++;
-    }
-    mtb::LaunchWfResolve(p, d->wf, slots, s);
-    ctx->launches++;
-    MTB_CUDA(ctx, cudaGetLastError());
-    return MTB_OK;
   }
-  ctx->err = "wavefront queues kept overflowing";
-  return MTB_ERR_LIMIT;
+  const int rc = EnsureWavefront(ctx, d, slots, d->scene.n_lights);
+  if (rc != MTB_OK) return rc;
+  long long expect[MTB_MAX_RAY_DEPTH + 2];
+  for (int level = 0; level <= p.max_depth; level++) {
+    long long bound = level >= 24 ? (long long)d->wf.queue_cap : std::min<long long>((long long)d->wf.queue_cap, (long long)slots << level);
+    expect[level] = have_hint ? std::min(bound, hint[level] + hint[level] / 4 + 2048) : bound;
+  }
+  expect[0] = slots;
+  // Side streams: the shadow walks + Phong sums of level L only depend on the trace of level L, so the levels'
+  // side kernels go round-robin over four streams and overlap each other as well as the deeper traces (on a small
+  // share of a frame - one of 8 GPUs - every one of them is latency-bound and they were the critical path when
+  // serialised on one stream).
+  cudaStream_t side[4] = {d->wf_stream2, d->wf_side[0], d->wf_side[1], d->wf_side[2]};
+  mtb::LaunchWfBegin(d->wf, slots, s);
+  // they must not start before earlier work on the main stream (previous frame, taps memset, WfBegin)
+  MTB_CUDA(ctx, cudaEventRecord(d->wf_ev_lit, s));
+  for (cudaStream_t st : side) MTB_CUDA(ctx, cudaStreamWaitEvent(st, d->wf_ev_lit, 0));
+  for (int level = 0; level <= p.max_depth; level++) {
+    // critical path (main stream): trace the level and queue its children
+    mtb::LaunchWfTrace(d->scene, p, d->wf, level, expect[level], debug_build, s);
+    MTB_CUDA(ctx, cudaEventRecord(d->wf_ev_level[level], s));
+    // side branch: shadow walks and the Phong sums of this level
+    cudaStream_t s2 = side[level & 3];
+    MTB_CUDA(ctx, cudaStreamWaitEvent(s2, d->wf_ev_level[level], 0));
+    mtb::LaunchWfShadow(d->scene, p, d->wf, level, expect[level], debug_build, s2);
+    mtb::LaunchWfLight(d->scene, p, d->wf, level, expect[level], s2);
+    ctx->launches += 2u + (d->scene.n_lights > 0 ? 1u : 0u);
+  }
+  // join: the folds need every level's colours
+  for (int k = 0; k < 4; k++) {
+    MTB_CUDA(ctx, cudaEventRecord(d->wf_ev_side[k], side[k]));
+    MTB_CUDA(ctx, cudaStreamWaitEvent(s, d->wf_ev_side[k], 0));
+  }
+  for (int level = p.max_depth - 1; level >= 0; level--) {
+    mtb::LaunchWfFold(d->scene, d->wf, level, expect[level], s);
+    ctx->launches++;
+  }
+  mtb::LaunchWfResolve(p, d->wf, slots, s);
+  mtb::LaunchWfCommit(d->wf, p.counters, d->wf_host, s);
+  // the repair launch: a no-op (its blocks read one word and exit) unless a queue overflowed
+  mtb::RenderParams repair = p;
+  repair.run_if = d->wf.ctrl;
+  repair.mega_part = 1;
+  mtb::LaunchRenderMega(d->scene, repair, n_blocks, debug_build, s);
+  ctx->launches += 4u;  // WfBegin, WfResolve, WfCommit, repair
+  MTB_CUDA(ctx, cudaGetLastError());
+  return MTB_OK;
 }
 
 // Hybrid frames: which tiles go through the wavefront.  Measured on B200 with C3 (one device rendering 1/1, 1/2, 1/4,
@@ -576,8 +580,18 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
   rp.tiles_x = (chunk_w + 7) / 8;
   rp.strip_stride = plan.owners;
 
-  // ---- launch on every device: one host thread per device when there are several, because the wavefront
-  // pipeline reads one counter per level back to the host and must not serialise the devices ----
+  // the frame on device 0 that receives every device's tiles
+  DeviceState &dev0 = ctx->dev[0];
+  MTB_CUDA(ctx, cudaSetDevice(dev0.device));
+  if (d_rgb_user == nullptr) MTB_CUDA(ctx, dev0.rgb.Reserve(npx * 3));
+  uint8_t *const rgb_target = d_rgb_user != nullptr ? static_cast<uint8_t *>(d_rgb_user) : dev0.rgb.ptr;
+  // direct peer stores need a mapping of the target in the storing device's address space: the context's own frame
+  // (cudaMalloc) has one wherever peer access is on; a caller's buffer may come from an allocator without one
+  std::vector<char> peer_store((size_t)n_dev, 0);
+  for (int g = 1; g < n_dev; g++) peer_store[(size_t)g] = ctx->dev[(size_t)g].peer_store_dev0 && d_rgb_user == nullptr && !ctx->no_peer_store;
+
+  // ---- launch on every device: one host thread per device when there are several (launching a frame is a few
+  // dozen driver calls per device; in parallel the devices start together) ----
   auto launch_on_device = [&](int g) -> int {
     DeviceState &d = ctx->dev[g];
     MTB_CUDA(ctx, cudaSetDevice(d.device));
@@ -585,9 +599,18 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
     const int owner = ctx->part_index * n_dev + g;
     mtb::RenderParams p = rp;
     p.strip_first = owner;
-    const bool direct = (g == 0 && d_rgb_user != nullptr);
-    if (!direct) MTB_CUDA(ctx, d.rgb.Reserve(npx * 3));
-    p.rgb = direct ? static_cast<uint8_t *>(d_rgb_user) : d.rgb.ptr;
+    // Where the pixels go.  Device 0: the caller's device buffer, or the context's frame.  Other devices: straight
+    // into device 0's frame through its peer mapping when there is one (RenderMega leaves whole tile rows as aligned
+    // 8-byte stores, WfResolve likewise) - the in-box BlitWorkChunk (main_net_master.cc:223-236) costs no copy then -
+    // else into an own frame that device 0 gathers with one pitched peer copy.
+    if (g == 0) {
+      p.rgb = rgb_target;
+    } else if (peer_store[(size_t)g]) {
+      p.rgb = rgb_target;
+    } else {
+      MTB_CUDA(ctx, d.rgb.Reserve(npx * 3));
+      p.rgb = d.rgb.ptr;
+    }
     if (dbg_host != nullptr) {
       MTB_CUDA(ctx, d.dbg.Reserve(npx));
       p.dbg = d.dbg.ptr;
@@ -646,18 +669,15 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
       const int wrc = RunWavefront(ctx, &d, p, blocks, debug_build, s);
       if (wrc != MTB_OK) return wrc;
     } else {
-      // launch form: one 8x8 tile per block unless one of the A/B forms is asked for
-      const int mode = (ctx->flags & MTB_FLAG_PERSISTENT) != 0 ? 1 : ((ctx->flags & MTB_FLAG_PACKING) != 0 ? 2 : ((ctx->flags & MTB_FLAG_RESUME) != 0 ? 4 : ((ctx->flags & MTB_FLAG_WARP_SYNC) != 0 ? 3 : 0)));
-      p.tiles_x = (chunk_w + mtb::MegaTileWidth(mode) - 1) / mtb::MegaTileWidth(mode);
-      const int mblocks = OwnedStrips(plan, owner) * p.tiles_x;
+      const int mblocks = blocks;
       if (mblocks > 0 && (ctx->flags & MTB_FLAG_NO_TILE_ORDER) == 0) {
         // launch order from the previous frame of the same geometry; the first frame runs in scanline order
         const long long signature = ((long long)chunk_w << 40) ^ ((long long)chunk_h << 20) ^ ((long long)owner << 8) ^ plan.owners ^
-                                    ((long long)mblocks << 4) ^ ((long long)mode << 60);
+                                    ((long long)mblocks << 4);
         MTB_CUDA(ctx, d.tile_cost.Reserve((size_t)mblocks));
         MTB_CUDA(ctx, d.tile_order.Reserve((size_t)mblocks));
         p.tile_cost = d.tile_cost.ptr;
-        const bool split = hybrid && mode == 0 && mblocks >= 64;
+        const bool split = hybrid && mblocks >= 64;
         const HybridSplit hs = ChooseHybridSplit(mblocks, d.sm_count);
         if (split) MTB_CUDA(ctx, d.heavy_k.Reserve(1));
         if (signature == d.tile_signature) {
@@ -669,13 +689,6 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
           MTB_CUDA(ctx, cudaMemsetAsync(d.tile_cost.ptr, 0, (size_t)mblocks * sizeof(uint32_t), s));
           d.tile_signature = signature;
         }
-      }
-      int persistent_blocks = 0;
-      if (mblocks > 0 && mode == 1) {
-        MTB_CUDA(ctx, d.work_counter.Reserve(1));
-        MTB_CUDA(ctx, cudaMemsetAsync(d.work_counter.ptr, 0, sizeof(uint32_t), s));
-        p.work_counter = d.work_counter.ptr;
-        persistent_blocks = mtb::MegaResidentBlocks(d.device);
       }
       if (p.heavy_k != nullptr) {
         // Hybrid frame.  The megakernel's critical path is its most expensive pixel (a serial chain of up to ~80
@@ -695,7 +708,7 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
         }
         MTB_CUDA(ctx, cudaEventRecord(d.ev_split, s));
         MTB_CUDA(ctx, cudaStreamWaitEvent(d.hybrid_stream, d.ev_split, 0));
-        mtb::LaunchRenderMega(d.scene, p, mblocks, mode, 0, debug_build, d.hybrid_stream);
+        mtb::LaunchRenderMega(d.scene, p, mblocks, debug_build, d.hybrid_stream);
         ctx->launches++;
         MTB_CUDA(ctx, cudaGetLastError());
         MTB_CUDA(ctx, cudaEventRecord(d.ev_mega_done, d.hybrid_stream));
@@ -703,7 +716,7 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
         if (wrc != MTB_OK) return wrc;
         MTB_CUDA(ctx, cudaStreamWaitEvent(s, d.ev_mega_done, 0));
       } else {
-        mtb::LaunchRenderMega(d.scene, p, mblocks, mode, persistent_blocks, debug_build, s);
+        mtb::LaunchRenderMega(d.scene, p, mblocks, debug_build, s);
         if (mblocks > 0) ctx->launches++;
         MTB_CUDA(ctx, cudaGetLastError());
       }
@@ -728,12 +741,12 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
   DeviceState &d0 = ctx->dev[0];
   MTB_CUDA(ctx, cudaSetDevice(d0.device));
   cudaStream_t s0 = user_stream != nullptr ? user_stream : d0.stream;
-  uint8_t *rgb0 = d_rgb_user != nullptr ? static_cast<uint8_t *>(d_rgb_user) : d0.rgb.ptr;
+  uint8_t *rgb0 = rgb_target;
   for (int g = 1; g < n_dev; g++) {
     DeviceState &d = ctx->dev[g];
     const int owner = ctx->part_index * n_dev + g;
     MTB_CUDA(ctx, cudaStreamWaitEvent(s0, d.ev_stop, 0));
-    int rc = GatherStrips(ctx, plan, owner, chunk_w, chunk_h, 3, rgb0, d.rgb.ptr, s0);
+    int rc = peer_store[(size_t)g] ? MTB_OK : GatherStrips(ctx, plan, owner, chunk_w, chunk_h, 3, rgb0, d.rgb.ptr, s0);
     if (rc != MTB_OK) return rc;
     if (dbg_host != nullptr) {
       rc = GatherStrips(ctx, plan, owner, chunk_w, chunk_h, sizeof(mtb_debug), d0.dbg.ptr, d.dbg.ptr, s0);
@@ -746,7 +759,6 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
       if (rc != MTB_OK) return rc;
     }
   }
-  if (n_dev > 1) MTB_CUDA(ctx, cudaEventRecord(d0.ev_gathered, s0));
   if (rgb_host != nullptr) MTB_CUDA(ctx, cudaMemcpyAsync(rgb_host, rgb0, npx * 3, cudaMemcpyDeviceToHost, s0));
   if (dbg_host != nullptr) {
     MTB_CUDA(ctx, cudaMemcpyAsync(dbg_host, d0.dbg.ptr, npx * sizeof(mtb_debug), cudaMemcpyDeviceToHost, s0));
@@ -756,6 +768,8 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
     if (taps->sig_shadow) MTB_CUDA(ctx, cudaMemcpyAsync(taps->sig_shadow, d0.sig_shadow.ptr, npx * 8, cudaMemcpyDeviceToHost, s0));
     if (taps->n_rays) MTB_CUDA(ctx, cudaMemcpyAsync(taps->n_rays, d0.n_rays.ptr, npx * 4, cudaMemcpyDeviceToHost, s0));
   }
+  // the peers may overwrite their scratch frames, and device 0's frame, once this frame has left device 0
+  if (n_dev > 1) MTB_CUDA(ctx, cudaEventRecord(d0.ev_gathered, s0));
   if (!synchronous && stats == nullptr) return MTB_OK;
 
   MTB_CUDA(ctx, cudaStreamSynchronize(s0));
@@ -819,7 +833,8 @@ int mtb_create(mtb_context **out, const int *devices, int n_devices) {
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d.device) == cudaSuccess && sms > 0) d.sm_count = sms;
   }
-  // NVLink peer access towards device 0, the gather target
+  // NVLink peer access between device 0, the gather target, and every other device: device 0 -> g for the peer-copy
+  // gather of taps / debug planes, g -> device 0 so that g's kernels can store their tiles straight into the frame
   for (int g = 1; g < n; g++) {
     int can = 0;
     cudaDeviceCanAccessPeer(&can, ctx->dev[0].device, ctx->dev[(size_t)g].device);
@@ -828,6 +843,23 @@ int mtb_create(mtb_context **out, const int *devices, int n_devices) {
       e = cudaDeviceEnablePeerAccess(ctx->dev[(size_t)g].device, 0);
       if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) ctx->dev[(size_t)g].peer_to_dev0 = true;
       cudaGetLastError();
+    }
+    can = 0;
+    cudaDeviceCanAccessPeer(&can, ctx->dev[(size_t)g].device, ctx->dev[0].device);
+    if (can) {
+      cudaSetDevice(ctx->dev[(size_t)g].device);
+      e = cudaDeviceEnablePeerAccess(ctx->dev[0].device, 0);
+      if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) ctx->dev[(size_t)g].peer_store_dev0 = true;
+      cudaGetLastError();
+    }
+  }
+  {  // development knobs (A/B measurements, tests that force a queue overflow)
+    const char *v = getenv("MTB_NO_PEER_STORE");
+    ctx->no_peer_store = v != nullptr && v[0] == '1';
+    const char *qf = getenv("MTB_WF_QUEUE_FACTOR"), *af = getenv("MTB_WF_ACT_FACTOR");
+    for (DeviceState &d : ctx->dev) {
+      if (qf != nullptr && atoi(qf) >= 1) d.wf_queue_factor = atoi(qf);
+      if (af != nullptr && atoi(af) >= 1) d.wf_act_factor = atoi(af);
     }
   }
   *out = ctx;
@@ -842,6 +874,12 @@ int mtb_create_host(mtb_context **out) {
 
 void mtb_destroy(mtb_context *ctx) {
   if (ctx == nullptr) return;
+  if (!ctx->dev.empty()) {
+    cudaSetDevice(ctx->dev[0].device);
+    cudaDeviceSynchronize();
+    for (void *p : ctx->opened_frames) cudaIpcCloseMemHandle(p);
+    for (void *p : ctx->owned_frames) cudaFree(p);
+  }
   for (DeviceState &d : ctx->dev) {
     cudaSetDevice(d.device);
     if (d.stream != nullptr) cudaStreamSynchronize(d.stream);
@@ -1171,6 +1209,71 @@ int mtb_intersect_rays(mtb_context *ctx, int64_t n, const double *origins, const
     stats->kernel_ms = ms;
     stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   }
+  return MTB_OK;
+}
+
+// ---- frames shared between processes (one process per GPU) ----
+int mtb_frame_create(mtb_context *ctx, size_t bytes, void **d_ptr, unsigned char handle[MTB_FRAME_HANDLE_BYTES]) {
+  if (ctx == nullptr || d_ptr == nullptr || handle == nullptr || ctx->dev.empty()) return MTB_ERR_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) <= MTB_FRAME_HANDLE_BYTES, "handle size");
+  *d_ptr = nullptr;
+  MTB_CUDA(ctx, cudaSetDevice(ctx->dev[0].device));
+  void *p = nullptr;
+  MTB_CUDA(ctx, cudaMalloc(&p, bytes == 0 ? 1 : bytes));
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    ctx->err = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e);
+    return MTB_ERR_CUDA;
+  }
+  MTB_CUDA(ctx, cudaMemset(p, 0, bytes == 0 ? 1 : bytes));
+  memset(handle, 0, MTB_FRAME_HANDLE_BYTES);
+  memcpy(handle, &h, sizeof(h));
+  ctx->owned_frames.push_back(p);
+  *d_ptr = p;
+  return MTB_OK;
+}
+
+int mtb_frame_open(mtb_context *ctx, const unsigned char handle[MTB_FRAME_HANDLE_BYTES], void **d_ptr) {
+  if (ctx == nullptr || d_ptr == nullptr || handle == nullptr || ctx->dev.empty()) return MTB_ERR_ARG;
+  *d_ptr = nullptr;
+  MTB_CUDA(ctx, cudaSetDevice(ctx->dev[0].device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void *p = nullptr;
+  MTB_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  ctx->opened_frames.push_back(p);
+  *d_ptr = p;
+  return MTB_OK;
+}
+
+int mtb_frame_release(mtb_context *ctx, void *d_ptr) {
+  if (ctx == nullptr || d_ptr == nullptr || ctx->dev.empty()) return MTB_ERR_ARG;
+  MTB_CUDA(ctx, cudaSetDevice(ctx->dev[0].device));
+  for (size_t i = 0; i < ctx->owned_frames.size(); i++) {
+    if (ctx->owned_frames[i] == d_ptr) {
+      ctx->owned_frames.erase(ctx->owned_frames.begin() + (long)i);
+      MTB_CUDA(ctx, cudaFree(d_ptr));
+      return MTB_OK;
+    }
+  }
+  for (size_t i = 0; i < ctx->opened_frames.size(); i++) {
+    if (ctx->opened_frames[i] == d_ptr) {
+      ctx->opened_frames.erase(ctx->opened_frames.begin() + (long)i);
+      MTB_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
+      return MTB_OK;
+    }
+  }
+  ctx->err = "not a frame of this context";
+  return MTB_ERR_ARG;
+}
+
+int mtb_frame_read(mtb_context *ctx, const void *d_ptr, size_t offset, size_t bytes, void *host_out) {
+  if (ctx == nullptr || d_ptr == nullptr || host_out == nullptr || ctx->dev.empty()) return MTB_ERR_ARG;
+  MTB_CUDA(ctx, cudaSetDevice(ctx->dev[0].device));
+  MTB_CUDA(ctx, cudaDeviceSynchronize());
+  MTB_CUDA(ctx, cudaMemcpy(host_out, static_cast<const char *>(d_ptr) + offset, bytes, cudaMemcpyDeviceToHost));
   return MTB_OK;
 }
 

@@ -96,24 +96,6 @@ __device__ __forceinline__ void Count(unsigned long long *cnt, int which, unsign
 // 128-bit read-only loads of the 16-byte aligned records
 __device__ __forceinline__ double2 Ld2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 
-// Optional staging of the top octree levels in shared memory (levels 0-2 = 1 + 8 + 64 nodes, 9.1 KB): every ray
-// walks them, but they are L1-resident anyway; measured on B200 before being enabled.
-#ifdef MTB_SMEM_TOP
-constexpr int kTopNodes = 73;
-__device__ __forceinline__ void StageTopNodes(const DeviceScene &sc, NodeRec *top, int n_nodes) {
-  const int n = n_nodes < kTopNodes ? n_nodes : kTopNodes;
-  const uint4 *src = reinterpret_cast<const uint4 *>(sc.nodes);
-  uint4 *dst = reinterpret_cast<uint4 *>(top);
-  for (int i = (int)threadIdx.x; i < n * 8; i += (int)blockDim.x) dst[i] = __ldg(src + i);
-  __syncthreads();
-}
-#define MTB_NODE_PTR(cur) ((cur) < top_n ? top + (cur) : sc.nodes + (cur))
-#define MTB_NLD(p) (*(p))
-#else
-#define MTB_NODE_PTR(cur) (sc.nodes + (cur))
-#define MTB_NLD(p) __ldg(p)
-#endif
-
 struct Ray {
   D3 o, d, inv;
   bool sx, sy, sz;  // inv component negative (regular rays only)
@@ -244,16 +226,8 @@ __device__ __forceinline__ void TestSlotRegular(const DeviceScene &sc, int slot,
 // ---------------------------------------------------------------------------------------------------
 // Regular traversal
 // ---------------------------------------------------------------------------------------------------
-#ifdef MTB_SMEM_TOP
-#define MTB_TOP_PARAMS , const NodeRec *top, int top_n
-#define MTB_TOP_ARGS , top, top_n
-#else
-#define MTB_TOP_PARAMS
-#define MTB_TOP_ARGS
-#endif
-
 template <bool DBG>
-__device__ int TraceRegular(const DeviceScene &sc, const Ray &r, double *t_out, unsigned long long *cnt MTB_TOP_PARAMS) {
+__device__ int TraceRegular(const DeviceScene &sc, const Ray &r, double *t_out, unsigned long long *cnt) {
   int f_child[kMaxTreeStack];
   unsigned f_order[kMaxTreeStack];
   double f_t[kMaxTreeStack];
@@ -278,9 +252,9 @@ __device__ int TraceRegular(const DeviceScene &sc, const Ray &r, double *t_out, 
   int c_child = -1;
   for (;;) {
     // ---- enter node `cur`: own list first (octtree.cc:177-196) ----
-    const NodeRec *node = MTB_NODE_PTR(cur);
-    const int4 info = MTB_NLD(reinterpret_cast<const int4 *>(&node->first_child));  // first_child, list_first, list_count, bvh_root
-    const int2 info2 = MTB_NLD(reinterpret_cast<const int2 *>(&node->child_mask));  // child_mask, bvh_end
+    const NodeRec *node = (sc.nodes + cur);
+    const int4 info = __ldg(reinterpret_cast<const int4 *>(&node->first_child));  // first_child, list_first, list_count, bvh_root
+    const int2 info2 = __ldg(reinterpret_cast<const int2 *>(&node->child_mask));  // child_mask, bvh_end
     Count<DBG>(cnt, kVisit);
     c_t = 0.0;
     c_slot = -1;
@@ -300,8 +274,8 @@ __device__ int TraceRegular(const DeviceScene &sc, const Ray &r, double *t_out, 
       const int end = info2.y;
       const BvhRec *b = &node->root_rec;  // the list's first record travels in the node's own cache line
       while (i < end) {
-        const float4 q0 = MTB_NLD(reinterpret_cast<const float4 *>(b->box));      // lo.xyz hi.x
-        const float4 q1 = MTB_NLD(reinterpret_cast<const float4 *>(b->box) + 1);  // hi.yz skip leaf
+        const float4 q0 = __ldg(reinterpret_cast<const float4 *>(b->box));      // lo.xyz hi.x
+        const float4 q1 = __ldg(reinterpret_cast<const float4 *>(b->box) + 1);  // hi.yz skip leaf
         Count<DBG>(cnt, kBvh);
         const bool pass = r.cull32 ? CullBox32(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r)
                                    : CullBox64(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r);
@@ -325,9 +299,9 @@ __device__ int TraceRegular(const DeviceScene &sc, const Ray &r, double *t_out, 
     // ---- children that the ray enters, ordered by entry distance (octtree.cc:200-216) ----
     const unsigned mask = (unsigned)info2.x;
     if (info.x >= 0 && mask != 0u) {
-      const double2 p0 = MTB_NLD(reinterpret_cast<const double2 *>(node->planes + 0)), p1 = MTB_NLD(reinterpret_cast<const double2 *>(node->planes + 2)),
-                    p2 = MTB_NLD(reinterpret_cast<const double2 *>(node->planes + 4)), p3 = MTB_NLD(reinterpret_cast<const double2 *>(node->planes + 6));
-      const double hz = MTB_NLD(&node->planes[8]);
+      const double2 p0 = __ldg(reinterpret_cast<const double2 *>(node->planes + 0)), p1 = __ldg(reinterpret_cast<const double2 *>(node->planes + 2)),
+                    p2 = __ldg(reinterpret_cast<const double2 *>(node->planes + 4)), p3 = __ldg(reinterpret_cast<const double2 *>(node->planes + 6));
+      const double hz = __ldg(&node->planes[8]);
       // planes: lo = (p0.x p0.y p1.x), c = (p1.y p2.x p2.y), hi = (p3.x p3.y hz)
       const double tx0 = (p0.x - r.o.x) * r.inv.x, tx1 = (p1.y - r.o.x) * r.inv.x, tx2 = (p3.x - r.o.x) * r.inv.x;
       const double ty0 = (p0.y - r.o.y) * r.inv.y, ty1 = (p2.x - r.o.y) * r.inv.y, ty2 = (p3.y - r.o.y) * r.inv.y;
@@ -595,51 +569,76 @@ __device__ __forceinline__ bool MollerTrumboreBound(const double *vert, const Ra
   return true;
 }
 
-struct FastBest {
-  double t, e, lo2;
-  int slot;     // canonical slot of the best hit, -1: none
-  float prune;  // subtrees whose conservative entry distance exceeds this cannot matter
+// What the LEAVES need of a ray and of the search so far, in the thread's local memory: the FP64 ray (the exact
+// tests run in the reference's FP64 arithmetic) and the best hit with its error bound.  The node loop runs on FP32
+// values only (FastRay); keeping the 18 registers of the FP64 ray and the 6 of the best hit alive across it made
+// the register allocator spill and rematerialise inside the loop (3 local loads + 3 F2F + 3 DSETP per node visit
+// under the 64-register cap).  MTB_FAST_BARRIER makes the address escape, so nothing of it stays in registers
+// between two leaf visits.
+struct alignas(16) FastMem {
+  double o[3], d[3], inv[3];
+  double t, e, lo2;  // best hit: distance, forward error bound; lo2 = min (t - e) over all other accepted hits
+};
+#define MTB_FAST_BARRIER(m) asm volatile("" : : "l"(m) : "memory")
+
+struct FastRay {
+  float ix, iy, iz, nox, noy, noz;  // FP32 inverse direction and -(origin * inverse direction)
 };
 
+// One triangle of a scene-BVH leaf: the reference's exact FP64 pre-test and Moller-Trumbore.  *slot / *prune are the
+// canonical slot of the best hit so far (-1: none) and the FP32 pruning distance (registers of the caller).
 template <bool DBG>
-__device__ __forceinline__ void TestSlotFast(const SlotRec *rec, const Ray &r, FastBest *fb, unsigned long long *cnt) {
+__device__ __forceinline__ void TestSlotFast(const SlotRec *rec, FastMem *m, int *slot, float *prune, unsigned long long *cnt) {
+  Ray r;
+  r.o = Mk(m->o[0], m->o[1], m->o[2]);
+  r.inv = Mk(m->inv[0], m->inv[1], m->inv[2]);
+  r.sx = r.inv.x < 0.0;
+  r.sy = r.inv.y < 0.0;
+  r.sz = r.inv.z < 0.0;
   const double2 b0 = Ld2(rec->box + 0), b1 = Ld2(rec->box + 2), b2 = Ld2(rec->box + 4);
   Count<DBG>(cnt, kTriAabb);
   double unused;
   if (!SlabRegular(b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, r, &unused)) return;  // primitive_triangle.cc:85-108
   Count<DBG>(cnt, kMt);
+  r.d = Mk(m->d[0], m->d[1], m->d[2]);
   double t, e;
   if (!MollerTrumboreBound(rec->vert, r, &t, &e)) return;
   Count<DBG>(cnt, kHit);
-  if (fb->slot >= 0 && !(t < fb->t)) {
-    fb->lo2 = fmin(fb->lo2, t - e);
-    return;
+  const int canon = __ldg(&rec->canon);
+  if (canon == *slot) return;  // the best hit itself, met again through another of its references (spatial splits)
+  if (*slot >= 0) {
+    const double bt = m->t;
+    if (!(t < bt)) {
+      m->lo2 = fmin(m->lo2, t - e);
+      return;
+    }
+    m->lo2 = fmin(m->lo2, bt - m->e);
   }
-  if (fb->slot >= 0) fb->lo2 = fmin(fb->lo2, fb->t - fb->e);
-  fb->t = t;
-  fb->e = e;
-  fb->slot = __ldg(&rec->canon);
-  fb->prune = fminf(fb->prune, __double2float_ru(t + 2.0 * e + t * 0x1p-20));
+  m->t = t;
+  m->e = e;
+  *slot = canon;
+  *prune = fminf(*prune, __double2float_ru(t + 2.0 * e + t * 0x1p-20));
 }
 
-// Conservative FP32 slab test of one child box; *tn_out = lower bound of the entry distance.  t = fma(b, i, -(o i))
-// differs from the FP64 value of (b - o) * i by at most 2^-23 |t| + 2^-20 R |i| for |o| <= 8R (o and i rounded
-// to float, the product o i, the fma).  The absolute part is a constant 2^-20 R in SPACE whatever the ray, so it
-// is paid at build time: every stored box is grown by 2^-17 R on all sides (SceneBvhBuilder::pad, 8x the bound),
-// which moves every near plane down and every far plane up per axis.  (It must be per axis: a slack shared
-// between the axes made rays that are almost perpendicular to one axis - huge |i| - pass every box of the scene.)
-// The relative part widens the winners of the max / min by 2^-21 |t| (4x the bound); widening only the winning
-// axis is enough because the bound of the max (min) is the bound of its argmax (argmin).
-__device__ __forceinline__ bool FastBox(float lox, float loy, float loz, float hix, float hiy, float hiz, const Ray &r,
-                                        float nox, float noy, float noz, float prune, float *tn_out) {
-  const float kRel = 4.76837158203125e-07f;  // 2^-21
-  const float nx = __fmaf_rn(r.sx ? hix : lox, r.ix, nox), fx = __fmaf_rn(r.sx ? lox : hix, r.ix, nox);
-  const float ny = __fmaf_rn(r.sy ? hiy : loy, r.iy, noy), fy = __fmaf_rn(r.sy ? loy : hiy, r.iy, noy);
-  const float nz = __fmaf_rn(r.sz ? hiz : loz, r.iz, noz), fz = __fmaf_rn(r.sz ? loz : hiz, r.iz, noz);
-  float tn = fmaxf(fmaxf(nx, ny), nz);
-  float tf = fminf(fminf(fx, fy), fz);
-  tn = __fmaf_rn(-kRel, fabsf(tn), tn);
-  tf = __fmaf_rn(kRel, fabsf(tf), tf);
+// Conservative FP32 slab test of one child box; *tn_out = lower bound of the entry distance.  With u = 2^-24,
+// of = fl(o), if = fl(1/d), nox = -fl(of if) and t32 = fma(b, if, nox):
+//   t32 = [ (b - o) i (1 + a2) - o i (1 + a2) ((1 + a1)(1 + a3) - 1) ] (1 + a4),  |a_k| <= u,
+// so |t32 - (b - o) i| <= (2u |b - o| + 2u |o|) |i| (1 + 3u): IN SPACE (divide by |i|) the error is at most
+// 2^-23 (|b - o| + |o|) <= 2^-23 * 17 R = 2^-18.9 R for |o| <= 8R, |b| <= R, whatever the ray.  It is therefore paid
+// once, at build time: every stored box is grown by 2^-16 R on all sides (SceneBvhBuilder::pad, 7.5x the bound), which
+// moves every near plane down and every far plane up PER AXIS.  (Per axis matters: a slack shared between the axes
+// made rays almost perpendicular to one axis - huge |i| - pass every box of the scene.  Round 1 paid the |b - o| part
+// with two extra FMAs per box in the node loop; folding it into the padding removes them, at 0.006 units of padding
+// in the 400-unit C3 room.)  The min / max of per-plane lower / upper bounds are bounds of the true min / max.
+__device__ __forceinline__ bool FastBox(float lox, float loy, float loz, float hix, float hiy, float hiz, const FastRay &r,
+                                        float prune, float *tn_out) {
+  // near / far plane per axis = min / max of the two plane distances (the same two values a sign select picks:
+  // the inverse direction is finite and non-zero here, so no NaN can arise) - no predicate per axis to keep alive
+  const float ax = __fmaf_rn(lox, r.ix, r.nox), bx = __fmaf_rn(hix, r.ix, r.nox);
+  const float ay = __fmaf_rn(loy, r.iy, r.noy), by = __fmaf_rn(hiy, r.iy, r.noy);
+  const float az = __fmaf_rn(loz, r.iz, r.noz), bz = __fmaf_rn(hiz, r.iz, r.noz);
+  const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+  const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
   *tn_out = tn;
   return tf >= 0.0f && tn <= tf && tn <= prune;
 }
@@ -653,10 +652,10 @@ __device__ __forceinline__ bool FastBox(float lox, float loy, float loz, float h
 //   e <= 2^-48 * 6 L^2 (2 dmax T + L) / (1e-8 - 2^-48 * 6 dmax L^2) + 2^-49 T =: M(T).
 // M grows by far less than 1 per unit of T, so a triangle entered behind t_limit + M(t_limit) cannot come out in
 // front of t_limit.  If the denominator is not comfortably positive (huge triangles) nothing is pruned by limit.
-__device__ __forceinline__ float LimitPrune(const DeviceScene &sc, const Ray &r, double t_limit) {
+__device__ __forceinline__ float LimitPrune(const DeviceScene &sc, const D3 &d, double t_limit) {
   if (!(t_limit < CUDART_INF)) return CUDART_INF_F;
   const double L = (double)sc.max_tri_extent;
-  const double dmax = fmax(fmax(fabs(r.d.x), fabs(r.d.y)), fabs(r.d.z));
+  const double dmax = fmax(fmax(fabs(d.x), fabs(d.y)), fabs(d.z));
   const double k = 0x1p-48 * 6.0 * L * L;
   const double den = 0.00000001 - k * dmax;
   if (!(den > 0.000000005)) return CUDART_INF_F;
@@ -664,18 +663,95 @@ __device__ __forceinline__ float LimitPrune(const DeviceScene &sc, const Ray &r,
   return __double2float_ru(t_limit + 2.0 * m + t_limit * 0x1p-20);
 }
 
+// Traversal stack of TraceFast.  An entry is 64 bits: conservative entry distance (FP32 bits) << 32 | child
+// reference.  Short-stack form (north star item 3): the first MTB_SMEM_STACK entries of every thread live in shared
+// memory, laid out [entry][thread] (conflict-free 64-bit accesses, no local-memory traffic, no L1 lines taken from the
+// BVH nodes); only deeper entries - a few per cent of the pushes - go to the thread's local array.  MTB_SMEM_STACK = 0
+// keeps the whole stack in local memory (measured A/B in DESIGN.md section 5).
+#ifndef MTB_SMEM_STACK
+#define MTB_SMEM_STACK 8
+#endif
+struct FastStack {
+  unsigned sbase;  // shared-space address of this thread's column (entry k at sbase + k * stride_bytes)
+  int stride_bytes;
+};
+#if MTB_SMEM_STACK > 0
+// (the address goes through an empty asm: left to itself the compiler recomputes it from SR_TID at every push / pop)
+#define MTB_DECLARE_FAST_STACK(threads)                                                    \
+  __shared__ unsigned long long s_fast_stack[MTB_SMEM_STACK * (threads)];                   \
+  unsigned fast_stack_base__ = (unsigned)__cvta_generic_to_shared(s_fast_stack + threadIdx.x); \
+  asm volatile("" : "+r"(fast_stack_base__));                                              \
+  const FastStack fstack{fast_stack_base__, (threads) * 8}
+#else
+#define MTB_DECLARE_FAST_STACK(threads) const FastStack fstack{0u, 0}
+#endif
+constexpr int kFastLocalStack = kFastStack - MTB_SMEM_STACK;
+
+__device__ __forceinline__ void FastPush(const FastStack &fs, unsigned long long *local, int sp, unsigned long long v) {
+#if MTB_SMEM_STACK > 0
+  if (sp < MTB_SMEM_STACK) {
+    asm volatile("st.shared.u64 [%0], %1;" : : "r"(fs.sbase + (unsigned)(sp * fs.stride_bytes)), "l"(v));
+  } else {
+    local[sp - MTB_SMEM_STACK] = v;
+  }
+#else
+  local[sp] = v;
+#endif
+}
+__device__ __forceinline__ unsigned long long FastPop(const FastStack &fs, const unsigned long long *local, int sp) {
+#if MTB_SMEM_STACK > 0
+  if (sp < MTB_SMEM_STACK) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(fs.sbase + (unsigned)(sp * fs.stride_bytes)));
+    return v;
+  }
+  return local[sp - MTB_SMEM_STACK];
+#else
+  return local[sp];
+#endif
+}
+
+// Closing stated edge case (a) of round 1.  The recursion stops at the first child, in
+// entry-distance order, that returns a hit (octtree.cc:244-246).  Octants have disjoint interiors, so along a regular
+// ray an octant B that is entered AFTER a sibling A is entered only when A has been left: a hit in A cannot be
+// farther than a hit in B, and stopping behind A loses nothing - unless the computed entry keys of A and B tie or
+// flip although B really comes first.  Then in(B) <= out(B) <= in(A) <= in(B) + (rounding of the two keys): the
+// ray's passage through B, and through every octree node inside B, is degenerate - it touches B in an edge or a
+// corner.  (If instead A really comes first, a hit in A is at most as far as the winner, and the error-interval rule
+// above already calls that ray ambiguous.)  So for the final hit the passage of the ray through the octree node H
+// that HOLDS the winning triangle is measured with the reference's own FP64 slab arithmetic, and a passage shorter
+// than 2^-40 relative (keys carry ~2^-52) hands the ray to the exact recursion.  The test ray of round 1
+// (o = (7,7,3), d = (-1,-1,-1/8) through the edge x = y = 4 of a [0,8]^3 root) is such a ray.
+__device__ __forceinline__ bool DegeneratePassage(const DeviceScene &sc, int slot, const FastMem *m) {
+  Ray r;
+  r.o = Mk(m->o[0], m->o[1], m->o[2]);
+  r.inv = Mk(m->inv[0], m->inv[1], m->inv[2]);
+  r.sx = r.inv.x < 0.0;
+  r.sy = r.inv.y < 0.0;
+  r.sz = r.inv.z < 0.0;
+  const NodeRec *h = sc.nodes + __ldg(sc.slot_node + slot);
+  const double2 p0 = Ld2(h->planes + 0), p1 = Ld2(h->planes + 2), p3 = Ld2(h->planes + 6);
+  const double hz = __ldg(&h->planes[8]);
+  // planes: lo = (p0.x p0.y p1.x), hi = (p3.x p3.y hz)
+  const double nx = ((r.sx ? p3.x : p0.x) - r.o.x) * r.inv.x, fx = ((r.sx ? p0.x : p3.x) - r.o.x) * r.inv.x;
+  const double ny = ((r.sy ? p3.y : p0.y) - r.o.y) * r.inv.y, fy = ((r.sy ? p0.y : p3.y) - r.o.y) * r.inv.y;
+  const double nz = ((r.sz ? hz : p1.x) - r.o.z) * r.inv.z, fz = ((r.sz ? p1.x : hz) - r.o.z) * r.inv.z;
+  const double tmin = SMax3(nx, ny, nz), tmax = SMin3(fx, fy, fz);
+  return !(tmax - tmin > 0x1p-40 * (fabs(tmin) + fabs(tmax)));
+}
+
+// `m` holds the FP64 ray (filled by the caller); `prune0` = LimitPrune.  Returns the canonical slot of the closest
+// accepted hit (-1: none) with its distance in *t_out.
 template <bool DBG>
-__device__ int TraceFast(const DeviceScene &sc, const Ray &r, double t_limit, double *t_out, bool *ambiguous,
-                         unsigned long long *cnt) {
-  unsigned long long stack[kFastStack];
+__device__ __forceinline__ int TraceFast(const DeviceScene &sc, FastMem *m, const FastRay &r, float prune0, double *t_out, bool *ambiguous,
+                                         unsigned long long *cnt, const FastStack &fs) {
+  unsigned long long stack[kFastLocalStack];
   int sp = 0;
-  const float nox = -(r.ox * r.ix), noy = -(r.oy * r.iy), noz = -(r.oz * r.iz);
-  FastBest fb;
-  fb.t = 0.0;
-  fb.e = 0.0;
-  fb.lo2 = CUDART_INF;
-  fb.slot = -1;
-  fb.prune = LimitPrune(sc, r, t_limit);
+  int slot = -1;
+  float prune = prune0;
+  m->lo2 = CUDART_INF;
+  m->t = 0.0;
+  m->e = 0.0;
   int node = 0;
   for (;;) {
     while (node >= 0) {
@@ -684,11 +760,11 @@ __device__ int TraceFast(const DeviceScene &sc, const Ray &r, double t_limit, do
       const int2 kids = __ldg(reinterpret_cast<const int2 *>(q + 3));
       Count<DBG>(cnt, kBvh, 2);
       float tl, tr;
-      const bool hl = FastBox(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, nox, noy, noz, fb.prune, &tl);
-      const bool hr = FastBox(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, nox, noy, noz, fb.prune, &tr);
+      const bool hl = FastBox(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, prune, &tl);
+      const bool hr = FastBox(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, prune, &tr);
       if (hl && hr) {
         const bool right_first = tr < tl;
-        stack[sp++] = ((unsigned long long)__float_as_uint(right_first ? tl : tr) << 32) | (unsigned)(right_first ? kids.x : kids.y);
+        FastPush(fs, stack, sp++, ((unsigned long long)__float_as_uint(right_first ? tl : tr) << 32) | (unsigned)(right_first ? kids.x : kids.y));
         node = right_first ? kids.y : kids.x;
       } else if (hl) {
         node = kids.x;
@@ -697,8 +773,8 @@ __device__ int TraceFast(const DeviceScene &sc, const Ray &r, double t_limit, do
       } else {
         node = kFastExit;
         while (sp > 0) {
-          const unsigned long long top = stack[--sp];
-          if (__uint_as_float((unsigned)(top >> 32)) <= fb.prune) {
+          const unsigned long long top = FastPop(fs, stack, --sp);
+          if (__uint_as_float((unsigned)(top >> 32)) <= prune) {
             node = (int)(unsigned)top;
             break;
           }
@@ -707,116 +783,45 @@ __device__ int TraceFast(const DeviceScene &sc, const Ray &r, double t_limit, do
     }
     if (node == kFastExit) break;
     const unsigned leaf = ~(unsigned)node;
-    for (unsigned s = leaf >> 3, e = s + (leaf & 7u); s < e; s++) TestSlotFast<DBG>(sc.gslots + s, r, &fb, cnt);
+    MTB_FAST_BARRIER(m);
+    for (unsigned s = leaf >> 3, e = s + (leaf & 7u); s < e; s++) TestSlotFast<DBG>(sc.gslots + s, m, &slot, &prune, cnt);
+    MTB_FAST_BARRIER(m);
     node = kFastExit;
     while (sp > 0) {
-      const unsigned long long top = stack[--sp];
-      if (__uint_as_float((unsigned)(top >> 32)) <= fb.prune) {
+      const unsigned long long top = FastPop(fs, stack, --sp);
+      if (__uint_as_float((unsigned)(top >> 32)) <= prune) {
         node = (int)(unsigned)top;
         break;
       }
     }
   }
-  *ambiguous = fb.slot >= 0 && fb.lo2 <= fb.t + fb.e;
-  *t_out = fb.t;
-  return fb.slot;
+  bool amb = false;
+  if (slot >= 0) {
+    const double t = m->t;
+    amb = m->lo2 <= t + m->e || DegeneratePassage(sc, slot, m);
+    *t_out = t;
+  }
+  *ambiguous = amb;
+  return slot;
 }
 
-// The exact recursion as a real call: with the fast traversal in front it runs for a handful of rays per frame.
-template <bool DBG>
-__device__ __noinline__ int TraceRegularCold(const DeviceScene &sc, const Ray &r, double *t_out, unsigned long long *cnt MTB_TOP_PARAMS) {
-  return TraceRegular<DBG>(sc, r, t_out, cnt MTB_TOP_ARGS);
-}
-
-// OctTree::IntersectRay (octtree.cc:26-40): inverse direction, then one of the traversals.
-// t_limit: results with t > t_limit are of no use to the caller (it may then get -1 or any such hit); CUDART_INF
-// for a plain closest-hit query.
-template <bool DBG>
-__device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D3 &d, double t_limit, double *t_out,
-                                     unsigned long long *cnt MTB_TOP_PARAMS) {
-  Ray r;
+// The ray record of the exact traversals (TraceRegular / TraceLiteral): inverse direction, signs, FP32 cull values.
+__device__ __forceinline__ void MakeRay(const DeviceScene &sc, const D3 &o, const D3 &d, Ray *out, bool *regular) {
+  Ray &r = *out;
   r.o = o;
   r.d = d;
   r.inv = Mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
   r.sx = r.inv.x < 0.0;
   r.sy = r.inv.y < 0.0;
   r.sz = r.inv.z < 0.0;
-  Count<DBG>(cnt, kRays);
-  const bool regular = isfinite(r.inv.x) && isfinite(r.inv.y) && isfinite(r.inv.z) && r.inv.x != 0.0 &&
-                       r.inv.y != 0.0 && r.inv.z != 0.0 && isfinite(o.x) && isfinite(o.y) && isfinite(o.z);
-  if (regular) {
-    // FP32 cull preconditions (see CullBox32): origin within 8R, |inv| within [2^-100, 2^100]
-    const float R = sc.cull_radius;
-    const double ao = fmax(fmax(fabs(o.x), fabs(o.y)), fabs(o.z));
-    const double ai_max = fmax(fmax(fabs(r.inv.x), fabs(r.inv.y)), fabs(r.inv.z));
-    const double ai_min = fmin(fmin(fabs(r.inv.x), fabs(r.inv.y)), fabs(r.inv.z));
-    r.cull32 = R > 0.0f && ao <= 8.0 * (double)R && ai_max <= 0x1p100 && ai_min >= 0x1p-100;
-    r.ox = (float)o.x;
-    r.oy = (float)o.y;
-    r.oz = (float)o.z;
-    r.ix = (float)r.inv.x;
-    r.iy = (float)r.inv.y;
-    r.iz = (float)r.inv.z;
-    const float pr = R * 9.5367431640625e-07f;  // 2^-20 * R
-    r.px = pr * fabsf(r.ix);
-    r.py = pr * fabsf(r.iy);
-    r.pz = pr * fabsf(r.iz);
-    if (sc.gnodes != nullptr && r.cull32) {
-      bool ambiguous;
-      const int slot = TraceFast<DBG>(sc, r, t_limit, t_out, &ambiguous, cnt);
-      if (!ambiguous) {
-        Count<DBG>(cnt, kFast);
-        return slot;
-      }
-      Count<DBG>(cnt, kFallback);
-    }
-    return TraceRegularCold<DBG>(sc, r, t_out, cnt MTB_TOP_ARGS);
-  }
-  return TraceLiteral<DBG>(sc, r, t_out, cnt);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Resumable form of the same traversals (megakernel, MTB_FLAG_RESUME).  ncu: 30 of 32 lanes enter Trace, 14 are
-// alive per instruction inside the node loop - a warp waits for its longest ray (mean 34 node visits).  Here the
-// walk of a ray can be SUSPENDED: all 32 lanes of a warp call TraceRun together, lanes with a ray in flight walk,
-// and the loop ends as soon as at most half of the rays that were in flight at entry are still walking.  The
-// finished lanes then consume their result (TraceEnd: the same certification and fallbacks as Trace), shade, start
-// their next ray (TraceBegin) and come back with the suspended ones.  What is computed per ray is unchanged.
-// ---------------------------------------------------------------------------------------------------
-struct FastWalk {
-  Ray r;
-  float nox, noy, noz;
-  FastBest fb;
-  int node;  // kFastExit: no walk in flight (finished, or a ray that takes one of the other traversals)
-  int sp;
-  int kind;  // 0: certified fast walk, 1: exact recursion (ray outside the FP32 model / no scene BVH), 2: literal
-};  // (the traversal stack is a separate array: a struct with a dynamically indexed member stays in local memory)
-
-template <bool DBG>
-__device__ __forceinline__ void TraceBegin(const DeviceScene &sc, const D3 &o, const D3 &d, double t_limit, FastWalk *w,
-                                           unsigned long long *cnt) {
-  Ray &r = w->r;
-  r.o = o;
-  r.d = d;
-  r.inv = Mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
-  r.sx = r.inv.x < 0.0;
-  r.sy = r.inv.y < 0.0;
-  r.sz = r.inv.z < 0.0;
-  r.cull32 = false;
-  Count<DBG>(cnt, kRays);
-  w->node = kFastExit;
-  w->sp = 0;
-  const bool regular = isfinite(r.inv.x) && isfinite(r.inv.y) && isfinite(r.inv.z) && r.inv.x != 0.0 &&
-                       r.inv.y != 0.0 && r.inv.z != 0.0 && isfinite(o.x) && isfinite(o.y) && isfinite(o.z);
-  if (!regular) {
-    w->kind = 2;
-    return;
-  }
+  *regular = isfinite(r.inv.x) && isfinite(r.inv.y) && isfinite(r.inv.z) && r.inv.x != 0.0 && r.inv.y != 0.0 &&
+             r.inv.z != 0.0 && isfinite(o.x) && isfinite(o.y) && isfinite(o.z);
+  // FP32 cull preconditions (see CullBox32 / FastBox): origin within 8R, |inv| within [2^-100, 2^100]
   const float R = sc.cull_radius;
   const double ao = fmax(fmax(fabs(o.x), fabs(o.y)), fabs(o.z));
   const double ai_max = fmax(fmax(fabs(r.inv.x), fabs(r.inv.y)), fabs(r.inv.z));
   const double ai_min = fmin(fmin(fabs(r.inv.x), fabs(r.inv.y)), fabs(r.inv.z));
-  r.cull32 = R > 0.0f && ao <= 8.0 * (double)R && ai_max <= 0x1p100 && ai_min >= 0x1p-100;
+  r.cull32 = *regular && R > 0.0f && ao <= 8.0 * (double)R && ai_max <= 0x1p100 && ai_min >= 0x1p-100;
   r.ox = (float)o.x;
   r.oy = (float)o.y;
   r.oz = (float)o.z;
@@ -827,109 +832,62 @@ __device__ __forceinline__ void TraceBegin(const DeviceScene &sc, const D3 &o, c
   r.px = pr * fabsf(r.ix);
   r.py = pr * fabsf(r.iy);
   r.pz = pr * fabsf(r.iz);
-  if (sc.gnodes == nullptr || !r.cull32) {
-    w->kind = 1;
-    return;
-  }
-  w->kind = 0;
-  w->nox = -(r.ox * r.ix);
-  w->noy = -(r.oy * r.iy);
-  w->noz = -(r.oz * r.iz);
-  w->fb.t = 0.0;
-  w->fb.e = 0.0;
-  w->fb.lo2 = CUDART_INF;
-  w->fb.slot = -1;
-  w->fb.prune = LimitPrune(sc, r, t_limit);
-  w->node = 0;
 }
 
-// Must be called by all 32 lanes of the warp (lanes without a walk in flight pass node == kFastExit).  `park` is
-// where a walk lives between calls; it must be an OPAQUE pointer (see RenderMega) so that the state is copied
-// into registers here, for the duration of the loop, and written back once - left to itself the register
-// allocator keeps the pixel state in registers and reloads the walk from local memory at every node.
+// Rays the fast traversal does not answer: irregular rays (literal recursion), rays outside the FP32 error model or
+// scenes without a scene BVH, and rays whose fast answer could not be certified (exact recursion).
 template <bool DBG>
-__device__ __noinline__ void TraceRun(const DeviceScene &sc, FastWalk *park, unsigned long long *stack, unsigned long long *cnt) {
-  int node = park->node;
-  const int stop_at = __popc(__ballot_sync(0xffffffffu, node != kFastExit)) >> 1;
-  if (__popc(__ballot_sync(0xffffffffu, node != kFastExit)) <= stop_at) return;  // nobody walks
-  // only what the node loop needs lives in registers; the FP64 ray and the best hit are read from the parked walk
-  // at the leaves
-  Ray rl;
-  rl.sx = park->r.sx;
-  rl.sy = park->r.sy;
-  rl.sz = park->r.sz;
-  rl.ix = park->r.ix;
-  rl.iy = park->r.iy;
-  rl.iz = park->r.iz;
-  const float nox = park->nox, noy = park->noy, noz = park->noz;
-  float prune = park->fb.prune;
-  int sp = park->sp;
-  for (;;) {
-    if (__popc(__ballot_sync(0xffffffffu, node != kFastExit)) <= stop_at) break;
-    if (node == kFastExit) continue;
-    while (node >= 0) {
-      const float4 *q = reinterpret_cast<const float4 *>(sc.gnodes + node);
-      const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-      const int2 kids = __ldg(reinterpret_cast<const int2 *>(q + 3));
-      Count<DBG>(cnt, kBvh, 2);
-      float tl, tr;
-      const bool hl = FastBox(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, rl, nox, noy, noz, prune, &tl);
-      const bool hr = FastBox(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, rl, nox, noy, noz, prune, &tr);
-      if (hl && hr) {
-        const bool right_first = tr < tl;
-        stack[sp++] = ((unsigned long long)__float_as_uint(right_first ? tl : tr) << 32) | (unsigned)(right_first ? kids.x : kids.y);
-        node = right_first ? kids.y : kids.x;
-      } else if (hl) {
-        node = kids.x;
-      } else if (hr) {
-        node = kids.y;
-      } else {
-        node = kFastExit;
-        while (sp > 0) {
-          const unsigned long long top = stack[--sp];
-          if (__uint_as_float((unsigned)(top >> 32)) <= prune) {
-            node = (int)(unsigned)top;
-            break;
-          }
-        }
-      }
-    }
-    if (node != kFastExit) {
-      const unsigned leaf = ~(unsigned)node;
-      Ray rr = park->r;
-      FastBest fb = park->fb;
-      for (unsigned s = leaf >> 3, e = s + (leaf & 7u); s < e; s++) TestSlotFast<DBG>(sc.gslots + s, rr, &fb, cnt);
-      park->fb = fb;
-      prune = fb.prune;
-      node = kFastExit;
-      while (sp > 0) {
-        const unsigned long long top = stack[--sp];
-        if (__uint_as_float((unsigned)(top >> 32)) <= prune) {
-          node = (int)(unsigned)top;
-          break;
-        }
-      }
-    }
-  }
-  park->node = node;
-  park->sp = sp;
+__device__ __noinline__ int TraceExactCold(const DeviceScene &sc, const D3 &o, const D3 &d, double *t_out, unsigned long long *cnt) {
+  Ray r;
+  bool regular;
+  MakeRay(sc, o, d, &r, &regular);
+  if (regular) return TraceRegular<DBG>(sc, r, t_out, cnt);
+  return TraceLiteral<DBG>(sc, r, t_out, cnt);
 }
 
-// Result of a finished walk (w->node == kFastExit): same certification and fallbacks as Trace().
+// OctTree::IntersectRay (octtree.cc:26-40): inverse direction, then one of the traversals.
+// t_limit: results with t > t_limit are of no use to the caller (it may then get -1 or any such hit); CUDART_INF
+// for a plain closest-hit query.
 template <bool DBG>
-__device__ __forceinline__ int TraceEnd(const DeviceScene &sc, FastWalk *w, double *t_out, unsigned long long *cnt MTB_TOP_PARAMS) {
-  if (w->kind == 0) {
-    const bool ambiguous = w->fb.slot >= 0 && w->fb.lo2 <= w->fb.t + w->fb.e;
+__device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D3 &d, double t_limit, double *t_out,
+                                     unsigned long long *cnt, const FastStack &fs) {
+  Count<DBG>(cnt, kRays);
+  FastMem mem;
+  bool fast;
+  FastRay fr;
+  float prune0;
+  {
+    const D3 inv = Mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
+    const bool regular = isfinite(inv.x) && isfinite(inv.y) && isfinite(inv.z) && inv.x != 0.0 && inv.y != 0.0 &&
+                         inv.z != 0.0 && isfinite(o.x) && isfinite(o.y) && isfinite(o.z);
+    const float R = sc.cull_radius;
+    const double ao = fmax(fmax(fabs(o.x), fabs(o.y)), fabs(o.z));
+    const double ai_max = fmax(fmax(fabs(inv.x), fabs(inv.y)), fabs(inv.z));
+    const double ai_min = fmin(fmin(fabs(inv.x), fabs(inv.y)), fabs(inv.z));
+    fast = regular && sc.gnodes != nullptr && R > 0.0f && ao <= 8.0 * (double)R && ai_max <= 0x1p100 && ai_min >= 0x1p-100;
+    mem.o[0] = o.x, mem.o[1] = o.y, mem.o[2] = o.z;
+    mem.d[0] = d.x, mem.d[1] = d.y, mem.d[2] = d.z;
+    mem.inv[0] = inv.x, mem.inv[1] = inv.y, mem.inv[2] = inv.z;
+    fr.ix = (float)inv.x;
+    fr.iy = (float)inv.y;
+    fr.iz = (float)inv.z;
+    fr.nox = -((float)o.x * fr.ix);
+    fr.noy = -((float)o.y * fr.iy);
+    fr.noz = -((float)o.z * fr.iz);
+    prune0 = LimitPrune(sc, d, t_limit);
+  }
+  if (fast) {
+    MTB_FAST_BARRIER(&mem);
+    bool ambiguous;
+    const int slot = TraceFast<DBG>(sc, &mem, fr, prune0, t_out, &ambiguous, cnt, fs);
     if (!ambiguous) {
       Count<DBG>(cnt, kFast);
-      *t_out = w->fb.t;
-      return w->fb.slot;
+      return slot;
     }
     Count<DBG>(cnt, kFallback);
-    return TraceRegularCold<DBG>(sc, w->r, t_out, cnt MTB_TOP_ARGS);
   }
-  if (w->kind == 1) return TraceRegularCold<DBG>(sc, w->r, t_out, cnt MTB_TOP_ARGS);
-  return TraceLiteral<DBG>(sc, w->r, t_out, cnt);
+  MTB_FAST_BARRIER(&mem);
+  return TraceExactCold<DBG>(sc, Mk(mem.o[0], mem.o[1], mem.o[2]), Mk(mem.d[0], mem.d[1], mem.d[2]), t_out, cnt);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@ struct DeviceScene {
   const ShadeRec *shade;
   const BvhRec *bvh;
   const int32_t *list_order;
+  const int32_t *slot_node;  // canonical slot -> octree node holding it
   const Bvh2Node *gnodes;   // scene BVH of the certified fast traversal; NULL: exact octree recursion only
   const SlotRec *gslots;    // the triangles in scene-BVH leaf order (SlotRec::canon = slot in slots / shade)
   const mtb_material *materials;
@@ -56,13 +57,16 @@ struct RenderParams {
   // rays it traced to tile_cost[tile]; the next frame launches the most expensive tiles first.
   const int32_t *tile_order;
   uint32_t *tile_cost;
-  // Persistent megakernel: lanes draw work items (item >> 6 = position in the launch order, item & 63 = pixel
-  // of that 8x8 tile) from *work_counter until n_items are handed out.
-  uint32_t *work_counter;
-  uint32_t n_items;
   // Hybrid frame: the first *heavy_k tiles of tile_order (the most expensive ones of the previous frame) are
   // rendered by the wavefront pipeline, the rest by the megakernel, concurrently.  NULL: no split.
   const int32_t *heavy_k;
+  // Which side of the split a RenderMega launch renders: 0 = positions >= *heavy_k (the megakernel half of a hybrid
+  // frame; everything when heavy_k is NULL), 1 = positions < *heavy_k (the wavefront's tiles: the repair launch below).
+  int32_t mega_part;
+  // Repair launch: the wavefront pipeline runs without reading anything back to the host; if one of its queues
+  // overflowed, *run_if != 0 and a RenderMega launch queued behind it renders the wavefront's tiles again (both
+  // pipelines produce the same bytes).  NULL: unconditional launch.  Blocks of a launch with *run_if == 0 exit at once.
+  const uint32_t *run_if;
 };
 
 struct IntersectParams {
@@ -94,32 +98,28 @@ struct WfBuffers {
   uint32_t *sh_flags;  // [light][activation]     in_shadow | segments << 1
   double *act_color;   // 3 doubles: local colour, later the folded colour
   int32_t *act_refl, *act_refr;  // child activation ids (-1: none)
-  uint32_t *counters;  // [0] rays queued for the next level, [1] overflow flag
+  // Device-side frame control (nothing of it is read by the host while a frame is in flight):
+  uint32_t *level_n;   // [MTB_MAX_RAY_DEPTH + 2] rays queued per level; [0] = pixel slots
+  uint32_t *ctrl;      // [0] overflow flag (a queue was too small: the frame is rendered by the repair launch)
+  unsigned long long *work;  // [kNumCounters] work counters of this frame, committed by WfCommit unless it overflowed
   int32_t queue_cap, act_cap;
-  // coherence sort of a level's queue: bucket key per queued ray (direction octant + Morton cell of the
-  // origin), histogram / offsets of the counting sort, and the resulting order (sorted position -> queue
-  // position).  Only the ORDER in which rays are processed changes, never a result.
-  uint32_t *sort_key[2];
-  uint32_t *sort_hist;
-  int32_t *perm;
-  float cell_lo[3], cell_scale[3];  // origin -> 5-bit cell coordinate per axis
 };
-constexpr int kWfSortBits = 18;  // 3 direction-sign bits + 3 x 5 cell bits
+// layout of the pinned host copy WfCommit writes: level_n[0 .. MTB_MAX_RAY_DEPTH + 1], overflow flag, frame sequence
+constexpr int kWfHostOverflow = MTB_MAX_RAY_DEPTH + 2;
+constexpr int kWfHostSequence = MTB_MAX_RAY_DEPTH + 3;
+constexpr int kWfHostWords = MTB_MAX_RAY_DEPTH + 4;
 
-// wavefront.cu
-// `sorted`: the level's queue is processed in wf.perm order (levels >= 1 after LaunchWfSort)
-void LaunchWfTraceMain(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
-                       int act_base, bool sorted, bool debug_build, cudaStream_t stream);
-void LaunchWfSpawn(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
-                   int act_base, bool debug_build, cudaStream_t stream);
-// activations [act_begin, act_begin + n) of one level
-void LaunchWfShadow(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int act_begin, int n,
-                    bool debug_build, cudaStream_t stream);
-void LaunchWfLight(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int act_begin, int n,
+// wavefront.cu.  `expect` = rays the level is expected to hold (sizes the grid only; the kernels read the real count
+// on the device and loop grid-strided).
+void LaunchWfBegin(const WfBuffers &wf, int slots, cudaStream_t stream);
+void LaunchWfTrace(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, long long expect, bool debug_build,
                    cudaStream_t stream);
-void LaunchWfSort(const WfBuffers &wf, int level, int n, cudaStream_t stream);
-void LaunchWfFold(const DeviceScene &sc, const WfBuffers &wf, int begin, int end, cudaStream_t stream);
+void LaunchWfShadow(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, long long expect, bool debug_build,
+                    cudaStream_t stream);
+void LaunchWfLight(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, long long expect, cudaStream_t stream);
+void LaunchWfFold(const DeviceScene &sc, const WfBuffers &wf, int level, long long expect, cudaStream_t stream);
 void LaunchWfResolve(const RenderParams &rp, const WfBuffers &wf, int n_slots, cudaStream_t stream);
+void LaunchWfCommit(const WfBuffers &wf, unsigned long long *global, uint32_t *host_copy, cudaStream_t stream);
 
 // megakernel.cu
 // Builds tile_order (descending cost, bucketed) from tile_cost and clears tile_cost for the coming frame.
@@ -127,13 +127,8 @@ void LaunchWfResolve(const RenderParams &rp, const WfBuffers &wf, int n_slots, c
 // mean (whole cost buckets, at most k_max).
 void LaunchBuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles, int32_t *heavy_k, int k_max, int heavy_factor,
                           cudaStream_t stream);
-// mode 0: one 8x8 tile per 64-thread block; 1: persistent lane refill (grid persistent_blocks, rp.work_counter
-// zeroed); 2: one 16x8 tile per 128-thread block with block-level ray packing.  rp.tiles_x must be in units of
-// MegaTileWidth(mode).
-void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp, int n_blocks, int mode, int persistent_blocks,
-                      bool debug_build, cudaStream_t stream);
-int MegaTileWidth(int mode);
-int MegaResidentBlocks(int device);  // SMs x resident RenderMega blocks per SM
+// One 8x8 tile per 64-thread block; n_blocks = tiles of the launch (rp.tiles_x in units of 8 pixels).
+void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp, int n_blocks, bool debug_build, cudaStream_t stream);
 void LaunchIntersect(const DeviceScene &sc, const IntersectParams &ip, bool debug_build, cudaStream_t stream);
 
 }  // namespace mtb

@@ -265,8 +265,8 @@ struct SceneBvhBuilder {
   const std::vector<Box3> &tri_box;
   std::vector<int32_t> ids;
   int32_t max_depth = 0;
-  // every stored box is grown by `pad` on all sides: the absolute part of the FP32 slab test's error bound,
-  // 2^-20 R |i| in t, is a constant 2^-20 R in space (FastBox, device_core.cuh); pad = 2^-17 R
+  // every stored box is grown by `pad` on all sides: the FP32 slab test's whole error bound is a constant
+  // 2^-18.9 R in space, whatever the ray (FastBox, device_core.cuh); pad = 2^-16 R
   double pad = 0.0;
 
   struct Job {
@@ -407,6 +407,7 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
   out->slots.assign((size_t)n, SlotRec{});
   out->shade.assign((size_t)n, ShadeRec{});
   out->list_order.assign((size_t)n, 0);
+  out->slot_node.assign((size_t)n, 0);
   out->bvh.clear();
   out->root_list = (int64_t)nodes[0].list.size();
   out->biggest_list = 0;
@@ -473,6 +474,7 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
           const int32_t t = (*order)[(size_t)k];
           const int32_t sidx = cursor + k;
           slot_of[(size_t)t] = sidx;
+          out->slot_node[(size_t)sidx] = (int32_t)i;
           SlotRec &sr = out->slots[(size_t)sidx];
           for (int a = 0; a < 3; a++) {
             sr.box[a] = tri_box[(size_t)t].lo[a];
@@ -539,7 +541,7 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
   out->gslots.clear();
   out->gbvh_depth = 0;
   if (use_scene_bvh && n > 0) {
-    SceneBvhBuilder sb{tri_box, {}, 0, 0x1p-17 * out->max_abs_coord * 1.000001, {}};
+    SceneBvhBuilder sb{tri_box, {}, 0, 0x1p-16 * out->max_abs_coord * 1.000001, {}};
     sb.ids.resize((size_t)n);
     std::iota(sb.ids.begin(), sb.ids.end(), 0);
     Box3 whole;

@@ -25,7 +25,7 @@ struct alignas(32) BvhRec {
 static_assert(sizeof(BvhRec) == 32, "BvhRec must be a quarter of a cache line");
 
 // Scene BVH of the certified fast traversal (device_core.cuh, TraceFast): one binary BVH over ALL triangles, a
-// node holds the boxes of its two children (FP32, grown by SceneBvhBuilder::pad and rounded outwards) = 64 bytes,
+// node holds the boxes of its two children (FP32, grown by SceneBvhBuilder::pad = 2^-16 R and rounded outwards) = 64 bytes,
 // half a line, four 128-bit loads.  Measured alternatives that did not pay (same bytes): the
 // tree collapsed to four children per node (128-byte nodes, commit e83e983) and four-wide nodes with 8-bit
 // quantised boxes (64 bytes for four children, commit 5e4af88).
@@ -79,6 +79,7 @@ struct FlatScene {
   std::vector<ShadeRec> shade;
   std::vector<BvhRec> bvh;
   std::vector<int32_t> list_order;  // list_order[list_first + k] = slot of the k-th entry in reference order
+  std::vector<int32_t> slot_node;   // octree node whose own list holds the slot (TraceFast's degenerate-passage check)
   std::vector<Bvh2Node> gnodes;     // scene BVH, node 0 = root (empty: no fast traversal)
   std::vector<SlotRec> gslots;      // copies of `slots` in scene-BVH leaf order
   int32_t gbvh_depth = 0;

@@ -1,27 +1,33 @@
 // Wavefront pipeline: the recursive TraceRayWorker (mythtracer.cc:13-228) as an iterative, level-by-level
 // sequence of kernels over ray queues in HBM.
 //
-//   level L:  WfTraceMain   one thread per queued ray: OctTree::IntersectRay, hit point, interpolated normal,
-//                           surface colour, reflected direction  (mythtracer.cc:18-76) -> activation record
-//             WfSpawn       one thread per hit: the reflection / refraction children are appended to the queue
-//                           of level L+1 with a warp-aggregated (ballot + prefix sum) slot allocation
+//   level L:  WfTrace       one thread per queued ray: OctTree::IntersectRay, hit point, interpolated normal,
+//                           surface colour, reflected direction (mythtracer.cc:18-76) -> activation record; then, in
+//                           the same kernel, the reflection / refraction children of the hit are appended to the queue
+//                           of level L+1 with a warp-aggregated (ballot + prefix count) slot allocation
 //                           (mythtracer.cc:181-225).  Whether a child exists does not depend on the lights.
-//     stream 2:
+//     side streams:
 //             WfShadow      one thread per (hit, light): the whole shadow walk through transparent surfaces
 //                           (mythtracer.cc:86-156); lights are independent of each other, only the order in
 //                           which their terms are summed matters, and that order is kept by WfLight
 //             WfLight       one thread per hit: Phong sum over the lights in scene order (mythtracer.cc:78-178)
-//   The trace -> spawn -> trace chain of the levels is the critical path (each link ends with the slowest ray
-//   of its level); the shadow / light kernels of level L only need level L's activation records, so they run
-//   on a second stream and fill the machine while the chain advances.
+//   The trace chain of the levels is the critical path (each link ends with the slowest ray of its level); the
+//   shadow / light kernels of level L only need level L's activation records, so they run on side streams and fill
+//   the machine while the chain advances.
 //   finally:  WfFold        deepest level first: parent += child * Refl, then parent += (child * Tf) * Tr --
 //                           the same two additions, in the same order, as the recursion performs on return
 //             WfResolve     V3DtoRGB (mythtracer.cc:235-241) into the chunk-local RGB24 buffer
+//             WfCommit      work counters of the frame -> the context's counters
+//
+// Nothing is read back to the host while a frame is in flight (round 1 read one counter per level): how many rays
+// a level holds is a device-side number (WfBuffers::level_n), every kernel sizes its own loop from it, and the host
+// only chooses grid sizes - from the previous frame's counts when it has them, else from the capacity bound.  A
+// queue that overflows sets WfBuffers::ctrl[0]; every later kernel of the frame then exits at once and a RenderMega
+// launch that is always queued behind the frame (RenderParams::run_if) renders the same pixels instead - both
+// pipelines produce the same bytes - while the host enlarges the queues for the next frame.
 //
 // Because every activation keeps its own colour and the fold replays the reference's additions in the
 // reference's order, the result is bit-identical to the megakernel (and to the reference, up to pow()).
-// Compared with the megakernel the traversal kernels need ~half the registers (the shading state lives in
-// HBM between kernels), rays of one kind run together, and finished pixels do not idle lanes.
 #include "device_core.cuh"
 
 namespace mtb {
@@ -54,67 +60,37 @@ __device__ __forceinline__ void FlushCounters(unsigned long long *cnt, unsigned 
   }
 }
 
-// Coherence key of a queued ray: the direction octant and the Morton code of the origin's cell in a
-// 32^3 grid over the scene box.  Rays with equal keys start close together and head the same way, so
-// they walk the same octree nodes and list-BVH records.
-__device__ __forceinline__ unsigned Spread5(unsigned v) {  // abcde -> a00b00c00d00e
-  return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6) | ((v & 16u) << 8);
-}
-__device__ __forceinline__ unsigned RayKey(const WfBuffers &wf, const D3 &o, const D3 &d) {
-  const float fx = ((float)o.x - wf.cell_lo[0]) * wf.cell_scale[0];
-  const float fy = ((float)o.y - wf.cell_lo[1]) * wf.cell_scale[1];
-  const float fz = ((float)o.z - wf.cell_lo[2]) * wf.cell_scale[2];
-  const unsigned cx = (unsigned)fminf(fmaxf(fx, 0.0f), 31.0f);  // NaN -> 0
-  const unsigned cy = (unsigned)fminf(fmaxf(fy, 0.0f), 31.0f);
-  const unsigned cz = (unsigned)fminf(fmaxf(fz, 0.0f), 31.0f);
-  const unsigned oct = (d.x < 0.0 ? 1u : 0u) | (d.y < 0.0 ? 2u : 0u) | (d.z < 0.0 ? 4u : 0u);
-  return (oct << 15) | Spread5(cx) | (Spread5(cy) << 1) | (Spread5(cz) << 2);
-}
-
-// Counting sort of a level's queue by RayKey: histogram, exclusive scan, scatter.
-__global__ void WfSortHistogram(const uint32_t *__restrict__ keys, uint32_t *hist, int n) {
-  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  if (i < n) atomicAdd(hist + keys[i], 1u);
-}
-__global__ void __launch_bounds__(1024) WfSortScan(uint32_t *hist) {
-  // one block: 1024 threads x 256 consecutive bins = 2^18 bins
-  __shared__ uint32_t partial[1024];
-  constexpr int kPer = (1 << kWfSortBits) / 1024;
-  uint32_t *mine = hist + (size_t)threadIdx.x * kPer;
-  uint32_t sum = 0;
-  for (int k = 0; k < kPer; k++) sum += mine[k];
-  partial[threadIdx.x] = sum;
-  __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    const uint32_t v = threadIdx.x >= (unsigned)off ? partial[threadIdx.x - off] : 0u;
-    __syncthreads();
-    partial[threadIdx.x] += v;
-    __syncthreads();
-  }
-  uint32_t run = partial[threadIdx.x] - sum;
-  for (int k = 0; k < kPer; k++) {
-    const uint32_t c = mine[k];
-    mine[k] = run;
-    run += c;
-  }
-}
-__global__ void WfSortScatter(const uint32_t *__restrict__ keys, uint32_t *offsets, int32_t *perm, int n) {
-  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  if (i < n) perm[atomicAdd(offsets + keys[i], 1u)] = i;
+// Rays queued for `level` and the activation id of its first ray (activations are numbered level by level).
+struct LevelRange {
+  int n, base;
+};
+__device__ __forceinline__ LevelRange WfLevel(const WfBuffers &wf, int level) {
+  LevelRange r;
+  r.base = 0;
+  for (int k = 0; k < level; k++) r.base += (int)wf.level_n[k];
+  r.n = (int)wf.level_n[level];
+  return r;
 }
 
 // Sub-warp packing.  A warp runs as long as its slowest ray and serialises what its lanes do differently,
 // so a level with few rays (deep levels, or a small share of the frame on one of 8 GPUs) finishes sooner
 // when its rays are spread over more, emptier warps: only the first `lanes` lanes of each warp get a ray.
-__device__ __forceinline__ long long PackedIndex64(long long n, int lanes) {
+// The loops below are warp-uniform: a warp handles items [first, first + lanes), then advances by the grid.
+struct WarpSpan {
+  long long first, step;
+  int lane;
+};
+__device__ __forceinline__ WarpSpan WfSpan(int lanes) {
+  WarpSpan s;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = (int)(threadIdx.x & 31u);
-  return lane < lanes ? warp * lanes + lane : n;
+  s.lane = (int)(threadIdx.x & 31u);
+  s.first = warp * lanes;
+  s.step = (((long long)gridDim.x * blockDim.x) >> 5) * lanes;
+  return s;
 }
-__device__ __forceinline__ int PackedIndex(int n, int lanes) { return (int)PackedIndex64(n, lanes); }
 
 // ---------------------------------------------------------------------------------------------------
-// WfTraceMain
+// WfTrace
 // ---------------------------------------------------------------------------------------------------
 // Pixel slot -> tile of this launch.  Hybrid frames (rp.heavy_k): slot >> 6 is a position in the launch order and
 // only the first *heavy_k positions belong to the wavefront (-1 beyond them).
@@ -133,350 +109,361 @@ __device__ __forceinline__ void WfChargeTile(const RenderParams &rp, int pixel, 
   atomicAdd(rp.tile_cost + local_strip * rp.tiles_x + (px >> 3), rays);
 }
 
+// First kernel of a frame: level 0 holds one ray per pixel slot, nothing else is queued, no overflow, no work yet.
+__global__ void WfBegin(WfBuffers wf, int slots) {
+  const int i = (int)threadIdx.x;
+  if (i <= MTB_MAX_RAY_DEPTH + 1) wf.level_n[i] = i == 0 ? (uint32_t)slots : 0u;
+  if (i < 2) wf.ctrl[i] = 0u;
+  if (i < kNumCounters) wf.work[i] = 0ull;
+}
+
 template <bool DBG>
-__global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTraceMain(DeviceScene sc, RenderParams rp, WfBuffers wf, int level, int n,
-                                                        int act_base, const int32_t *__restrict__ perm, int lanes) {
-#ifdef MTB_SMEM_TOP
-  __shared__ NodeRec top_store[kTopNodes];
-  const NodeRec *top = top_store;
-  const int top_n = sc.n_nodes < kTopNodes ? sc.n_nodes : kTopNodes;
-  StageTopNodes(sc, top_store, sc.n_nodes);
-#endif
-  // j: position in processing order; i: position in the level's queue; activation id = act_base + i.
-  // Only the first `lanes` lanes of a warp carry a ray (see PackedIndex).
-  const int j = PackedIndex(n, lanes);
-  const int i = (perm != nullptr && j < n) ? perm[j] : j;
+__global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTrace(DeviceScene sc, RenderParams rp, WfBuffers wf, int level, int lanes) {
+  MTB_DECLARE_FAST_STACK(kWfBlock);
+  if (wf.ctrl[0] != 0u) return;  // an earlier level overflowed: the frame is rendered by the repair launch
+  const LevelRange lr = WfLevel(wf, level);
+  const int n = lr.n < wf.queue_cap ? lr.n : wf.queue_cap, act_base = lr.base;
   unsigned long long cnt_store[DBG ? kNumCounters : 1];
   unsigned long long *cnt = cnt_store;
   if (DBG) {
     for (int k = 0; k < kNumCounters; k++) cnt[k] = 0;
   }
   unsigned traced = 0;
-  const int q = level & 1;
-  if (j < n) {
-    D3 o, d;
-    int pixel;
-    unsigned long long path;
-    bool live = true;
-    if (level == 0) {
-      // 8x8 pixel tiles (a warp = 8x4 pixels) of this launch's strips, as in RenderMega; in a hybrid frame the
-      // slots are the first *heavy_k tiles of the launch order
-      const int tile = WfTileOfSlot(rp, i), t = i & 63;
-      const int strip = rp.strip_first + (tile / rp.tiles_x) * rp.strip_stride;
-      const int px = (tile % rp.tiles_x) * 8 + (t & 7);
-      const int py = strip * 8 + (t >> 3);
-      live = tile >= 0 && px < rp.chunk_w && py < rp.chunk_h;
-      pixel = live ? py * rp.chunk_w + px : -1;
-      const D3 start = Load3(rp.sensor), d_scan = Load3(rp.sensor + 3), d_pixel = Load3(rp.sensor + 6);
-      o = Load3(rp.origin);
-      d = Normalized(Add(Add(start, MulS(d_scan, (double)(rp.chunk_y + py))), MulS(d_pixel, (double)(rp.chunk_x + px))));
-      path = 1ull;
-      wf.rq_coef[0][i] = 1.0;
-      wf.rq_inobj[0][i] = 0;
-      if (live) Count<DBG>(cnt, kPrimary);
-    } else {
-      o = Load3(wf.rq_o[q] + (size_t)i * 3);
-      d = Load3(wf.rq_d[q] + (size_t)i * 3);
-      pixel = wf.rq_pixel[q][i];
-      path = wf.rq_path[q][i];
-    }
-    const int act = act_base + i;
-    wf.act_refl[act] = -1;
-    wf.act_refr[act] = -1;
-    wf.act_pixel[act] = pixel;
-    wf.act_path[act] = path;
-    int act_mtl = -2;
-    D3 color = Mk(0.0, 0.0, 0.0);
-    if (live) {
-      double t = 0.0;
-      const int slot = Trace<DBG>(sc, o, d, CUDART_INF, &t, cnt MTB_TOP_ARGS);
-      traced = 1;
-      if (rp.n_rays != nullptr) atomicAdd(rp.n_rays + pixel, 1u);
-      if (slot < 0) {
-        if (level == 0 && rp.dbg != nullptr) {
-          mtb_debug *dbg = rp.dbg + pixel;
-          dbg->line_no = -1;
-          dbg->pad_ = 0;
-          dbg->point[0] = dbg->point[1] = dbg->point[2] = CUDART_NAN;
-        }
-      } else {
-        const ShadeRec *sh = sc.shade + slot;
-        const SlotRec *sr = sc.slots + slot;
-        const D3 P = Add(o, MulS(d, t));
-        const int line_no = __ldg(&sh->line_no);
-        if (level == 0 && rp.dbg != nullptr) {
-          mtb_debug *dbg = rp.dbg + pixel;
-          dbg->line_no = line_no;
-          dbg->pad_ = 0;
-          dbg->point[0] = P.x;
-          dbg->point[1] = P.y;
-          dbg->point[2] = P.z;
-        }
-        if (rp.sig_hits != nullptr) {
-          atomicAdd(reinterpret_cast<unsigned long long *>(rp.sig_hits) + pixel, Mix64(path, 1ull, (unsigned long long)(long long)line_no));
-        }
-        Count<DBG>(cnt, kShade);
-        const D3 v0 = Load3(sr->vert), v1 = Load3(sr->vert + 3), v2 = Load3(sr->vert + 6);
-        const BaryWeights w = Barycentric(v0, v1, v2, P);
-        D3 normal = DivS(Add(Add(MulS(Load3(sh->normal), w.n0), MulS(Load3(sh->normal + 3), w.n1)), MulS(Load3(sh->normal + 6), w.n2)), w.n);
-        const D3 towards_camera = Neg(d);
-        double normal_ray_dot = Dot(towards_camera, normal);
-        if (normal_ray_dot < 0.0) {
-          normal = Neg(normal);
-          normal_ray_dot = Dot(towards_camera, normal);
-        }
-        const int material = __ldg(&sh->material);
-        if (material < 0) {  // mythtracer.cc:49-52
-          normal_ray_dot = (normal_ray_dot + 1.0) * 0.5;
-          color = Mk(normal_ray_dot, normal_ray_dot, normal_ray_dot);
-        } else {
-          const mtb_material *m = sc.materials + material;
-          D3 surface = Load3(m->ambient);
-          const int tex = m->texture;
-          if (tex >= 0) {
-            const double u = (sh->uv[0] * w.n0 + sh->uv[2] * w.n1 + sh->uv[4] * w.n2) / w.n;
-            const double v = (sh->uv[1] * w.n0 + sh->uv[3] * w.n1 + sh->uv[5] * w.n2) / w.n;
-            surface = MulV(surface, SampleTexture(sc.tex_atlas, tex, sc.texture_dim[tex], u, v));
-          }
-          const D3 reflected = Sub(d, MulS(normal, 2 * Dot(normal, d)));
-          act_mtl = material;
-          Store3(wf.act_point + (size_t)act * 3, P);
-          Store3(wf.act_normal + (size_t)act * 3, normal);
-          Store3(wf.act_surface + (size_t)act * 3, surface);
-          Store3(wf.act_reflected + (size_t)act * 3, reflected);
-          Store3(wf.act_dir + (size_t)act * 3, d);
-        }
-      }
-    }
-    wf.act_mtl[act] = act_mtl;
-    Store3(wf.act_color + (size_t)act * 3, color);
-    WfChargeTile(rp, pixel, traced);
-  }
-  FlushCounters<DBG>(cnt, rp.counters, traced);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// WfSpawn: children of the level's hits -> queue of the next level (mythtracer.cc:181-225)
-// ---------------------------------------------------------------------------------------------------
-template <bool DBG>
-__global__ void __launch_bounds__(kWfBlock) WfSpawn(DeviceScene sc, RenderParams rp, WfBuffers wf, int level, int n, int act_base) {
-  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  unsigned long long cnt_store[DBG ? kNumCounters : 1];
-  unsigned long long *cnt = cnt_store;
-  if (DBG) {
-    for (int k = 0; k < kNumCounters; k++) cnt[k] = 0;
-  }
   const int q = level & 1, qn = q ^ 1;
-  const int act = act_base + i;
-  bool do_reflect = false, do_refract = false;
-  double coef = 0.0, refl = 0.0;
-  bool in_object = false;
-  int material = -1;
-  if (i < n) material = wf.act_mtl[act];
-  if (material >= 0 && level < rp.max_depth) {
-    const mtb_material *m = sc.materials + material;
-    coef = wf.rq_coef[q][i];
-    in_object = wf.rq_inobj[q][i] != 0;
-    refl = m->reflectance;
-    do_reflect = refl > 0.0 && coef > 0.01 && !in_object;  // mythtracer.cc:181-184
-    do_refract = m->transparency > 0.0;                    // mythtracer.cc:192
-  }
-  // ---- queue compaction: warp ballots + prefix counts, one atomic per warp.  The warp's reflection
-  // children are stored first, then its refraction children, so that neighbouring queue entries (= the
-  // lanes of a warp in the next level) are rays of the same kind from neighbouring pixels ----
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned refl_mask = __ballot_sync(0xffffffffu, do_reflect);
-  const unsigned refr_mask = __ballot_sync(0xffffffffu, do_refract);
-  const unsigned n_refl = (unsigned)__popc(refl_mask), n_refr = (unsigned)__popc(refr_mask);
-  const unsigned total = n_refl + n_refr;
-  const unsigned below = (1u << lane) - 1u;
-  unsigned base = 0;
-  if (total > 0u) {
-    if (lane == 0u) base = atomicAdd(wf.counters + 0, total);
-    base = __shfl_sync(0xffffffffu, base, 0);
-  }
-  if (do_reflect || do_refract) {
-    const unsigned pos_refl = base + (unsigned)__popc(refl_mask & below);
-    const unsigned pos_refr = base + n_refl + (unsigned)__popc(refr_mask & below);
-    const int next_base = act_base + n;
-    if (base + total > (unsigned)wf.queue_cap || (long long)next_base + base + total > (long long)wf.act_cap) {
-      wf.counters[1] = 1u;  // overflow: the host retries the frame with larger buffers
-    } else {
-      const D3 P = Load3(wf.act_point + (size_t)act * 3);
-      const unsigned long long path = wf.act_path[act];
-      const int pixel = wf.act_pixel[act];
-      if (do_reflect) {
-        const unsigned pos = pos_refl;
-        Count<DBG>(cnt, kReflect);
-        const D3 reflected = Load3(wf.act_reflected + (size_t)act * 3);
-        const D3 ro = Add(P, MulS(reflected, 0.0001));  // mythtracer.cc:70-75
-        Store3(wf.rq_o[qn] + (size_t)pos * 3, ro);
-        Store3(wf.rq_d[qn] + (size_t)pos * 3, reflected);
-        wf.sort_key[qn][pos] = RayKey(wf, ro, reflected);
-        wf.rq_coef[qn][pos] = coef * refl;
-        wf.rq_path[qn][pos] = path * 2ull;
-        wf.rq_pixel[qn][pos] = pixel;
-        wf.rq_inobj[qn][pos] = in_object ? 1 : 0;
-        wf.act_refl[act] = next_base + (int)pos;
+  const WarpSpan span = WfSpan(lanes);
+  for (long long first = span.first; first < n; first += span.step) {
+    // i: position in the level's queue; activation id = act_base + i
+    const int i = (int)first + span.lane;
+    const bool mine = span.lane < lanes && i < n;
+    bool do_reflect = false, do_refract = false, in_object = false;
+    double coef = 1.0, refl = 0.0;
+    D3 P = Mk(0.0, 0.0, 0.0), child_refl = Mk(0.0, 0.0, 0.0), d = Mk(0.0, 0.0, 0.0);
+    int pixel = -1;
+    unsigned long long path = 1ull;
+    const int act = act_base + i;
+    if (mine) {
+      D3 o;
+      bool live = true;
+      if (level == 0) {
+        // 8x8 pixel tiles (a warp = 8x4 pixels) of this launch's strips, as in RenderMega; in a hybrid frame the
+        // slots are the first *heavy_k tiles of the launch order
+        const int tile = WfTileOfSlot(rp, i), t = i & 63;
+        const int strip = rp.strip_first + (tile / rp.tiles_x) * rp.strip_stride;
+        const int px = (tile % rp.tiles_x) * 8 + (t & 7);
+        const int py = strip * 8 + (t >> 3);
+        live = tile >= 0 && px < rp.chunk_w && py < rp.chunk_h;
+        pixel = live ? py * rp.chunk_w + px : -1;
+        const D3 start = Load3(rp.sensor), d_scan = Load3(rp.sensor + 3), d_pixel = Load3(rp.sensor + 6);
+        o = Load3(rp.origin);
+        d = Normalized(Add(Add(start, MulS(d_scan, (double)(rp.chunk_y + py))), MulS(d_pixel, (double)(rp.chunk_x + px))));
+        if (live) Count<DBG>(cnt, kPrimary);
+      } else {
+        o = Load3(wf.rq_o[q] + (size_t)i * 3);
+        d = Load3(wf.rq_d[q] + (size_t)i * 3);
+        pixel = wf.rq_pixel[q][i];
+        path = wf.rq_path[q][i];
+        coef = wf.rq_coef[q][i];
+        in_object = wf.rq_inobj[q][i] != 0;
       }
-      if (do_refract) {
-        const unsigned pos = pos_refr;
-        Count<DBG>(cnt, kRefract);
-        const D3 rdir = Normalized(Load3(wf.act_dir + (size_t)act * 3));  // mythtracer.cc:208-212
-        const D3 ro = Add(P, MulS(rdir, 0.00001));                        // mythtracer.cc:214-218
-        Store3(wf.rq_o[qn] + (size_t)pos * 3, ro);
-        Store3(wf.rq_d[qn] + (size_t)pos * 3, rdir);
-        wf.sort_key[qn][pos] = RayKey(wf, ro, rdir);
-        wf.rq_coef[qn][pos] = coef;
-        wf.rq_path[qn][pos] = path * 2ull + 1ull;
-        wf.rq_pixel[qn][pos] = pixel;
-        wf.rq_inobj[qn][pos] = in_object ? 0 : 1;
-        wf.act_refr[act] = next_base + (int)pos;
+      wf.act_refl[act] = -1;
+      wf.act_refr[act] = -1;
+      wf.act_pixel[act] = pixel;
+      wf.act_path[act] = path;
+      int act_mtl = -2;
+      D3 color = Mk(0.0, 0.0, 0.0);
+      if (live) {
+        double t = 0.0;
+        const int slot = Trace<DBG>(sc, o, d, CUDART_INF, &t, cnt, fstack);
+        traced++;
+        if (rp.n_rays != nullptr) atomicAdd(rp.n_rays + pixel, 1u);
+        WfChargeTile(rp, pixel, 1u);
+        if (slot < 0) {
+          if (level == 0 && rp.dbg != nullptr) {
+            mtb_debug *dbg = rp.dbg + pixel;
+            dbg->line_no = -1;
+            dbg->pad_ = 0;
+            dbg->point[0] = dbg->point[1] = dbg->point[2] = CUDART_NAN;
+          }
+        } else {
+          const ShadeRec *sh = sc.shade + slot;
+          const SlotRec *sr = sc.slots + slot;
+          P = Add(o, MulS(d, t));
+          const int line_no = __ldg(&sh->line_no);
+          if (level == 0 && rp.dbg != nullptr) {
+            mtb_debug *dbg = rp.dbg + pixel;
+            dbg->line_no = line_no;
+            dbg->pad_ = 0;
+            dbg->point[0] = P.x;
+            dbg->point[1] = P.y;
+            dbg->point[2] = P.z;
+          }
+          if (rp.sig_hits != nullptr) {
+            atomicAdd(reinterpret_cast<unsigned long long *>(rp.sig_hits) + pixel, Mix64(path, 1ull, (unsigned long long)(long long)line_no));
+          }
+          Count<DBG>(cnt, kShade);
+          const D3 v0 = Load3(sr->vert), v1 = Load3(sr->vert + 3), v2 = Load3(sr->vert + 6);
+          const BaryWeights w = Barycentric(v0, v1, v2, P);
+          D3 normal = DivS(Add(Add(MulS(Load3(sh->normal), w.n0), MulS(Load3(sh->normal + 3), w.n1)), MulS(Load3(sh->normal + 6), w.n2)), w.n);
+          const D3 towards_camera = Neg(d);
+          double normal_ray_dot = Dot(towards_camera, normal);
+          if (normal_ray_dot < 0.0) {
+            normal = Neg(normal);
+            normal_ray_dot = Dot(towards_camera, normal);
+          }
+          const int material = __ldg(&sh->material);
+          if (material < 0) {  // mythtracer.cc:49-52
+            normal_ray_dot = (normal_ray_dot + 1.0) * 0.5;
+            color = Mk(normal_ray_dot, normal_ray_dot, normal_ray_dot);
+          } else {
+            const mtb_material *m = sc.materials + material;
+            D3 surface = Load3(m->ambient);
+            const int tex = m->texture;
+            if (tex >= 0) {
+              const double u = (sh->uv[0] * w.n0 + sh->uv[2] * w.n1 + sh->uv[4] * w.n2) / w.n;
+              const double v = (sh->uv[1] * w.n0 + sh->uv[3] * w.n1 + sh->uv[5] * w.n2) / w.n;
+              surface = MulV(surface, SampleTexture(sc.tex_atlas, tex, sc.texture_dim[tex], u, v));
+            }
+            child_refl = Sub(d, MulS(normal, 2 * Dot(normal, d)));
+            act_mtl = material;
+            Store3(wf.act_point + (size_t)act * 3, P);
+            Store3(wf.act_normal + (size_t)act * 3, normal);
+            Store3(wf.act_surface + (size_t)act * 3, surface);
+            Store3(wf.act_reflected + (size_t)act * 3, child_refl);
+            Store3(wf.act_dir + (size_t)act * 3, d);
+            if (level < rp.max_depth) {
+              refl = m->reflectance;
+              do_reflect = refl > 0.0 && coef > 0.01 && !in_object;  // mythtracer.cc:181-184
+              do_refract = m->transparency > 0.0;                    // mythtracer.cc:192
+            }
+          }
+        }
+      }
+      wf.act_mtl[act] = act_mtl;
+      Store3(wf.act_color + (size_t)act * 3, color);
+    }
+    // ---- children of the warp's hits -> queue of the next level: warp ballots + prefix counts, one atomic per
+    // warp.  The warp's reflection children are stored first, then its refraction children, so that neighbouring
+    // queue entries (= the lanes of a warp in the next level) are rays of the same kind from neighbouring pixels ----
+    __syncwarp();
+    const unsigned refl_mask = __ballot_sync(0xffffffffu, do_reflect);
+    const unsigned refr_mask = __ballot_sync(0xffffffffu, do_refract);
+    const unsigned n_refl = (unsigned)__popc(refl_mask), n_refr = (unsigned)__popc(refr_mask);
+    const unsigned total = n_refl + n_refr;
+    if (total == 0u) continue;
+    const unsigned below = (1u << span.lane) - 1u;
+    unsigned base = 0;
+    if (span.lane == 0) base = atomicAdd(wf.level_n + level + 1, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (do_reflect || do_refract) {
+      const int next_base = act_base + lr.n;
+      if (base + total > (unsigned)wf.queue_cap || (long long)next_base + base + total > (long long)wf.act_cap) {
+        wf.ctrl[0] = 1u;  // overflow: this frame is rendered by the repair launch, the next one gets larger queues
+      } else {
+        if (do_reflect) {
+          const unsigned pos = base + (unsigned)__popc(refl_mask & below);
+          Count<DBG>(cnt, kReflect);
+          Store3(wf.rq_o[qn] + (size_t)pos * 3, Add(P, MulS(child_refl, 0.0001)));  // mythtracer.cc:70-75
+          Store3(wf.rq_d[qn] + (size_t)pos * 3, child_refl);
+          wf.rq_coef[qn][pos] = coef * refl;
+          wf.rq_path[qn][pos] = path * 2ull;
+          wf.rq_pixel[qn][pos] = pixel;
+          wf.rq_inobj[qn][pos] = in_object ? 1 : 0;
+          wf.act_refl[act] = next_base + (int)pos;
+        }
+        if (do_refract) {
+          const unsigned pos = base + n_refl + (unsigned)__popc(refr_mask & below);
+          Count<DBG>(cnt, kRefract);
+          const D3 rdir = Normalized(d);                                       // mythtracer.cc:208-212
+          Store3(wf.rq_o[qn] + (size_t)pos * 3, Add(P, MulS(rdir, 0.00001)));  // mythtracer.cc:214-218
+          Store3(wf.rq_d[qn] + (size_t)pos * 3, rdir);
+          wf.rq_coef[qn][pos] = coef;
+          wf.rq_path[qn][pos] = path * 2ull + 1ull;
+          wf.rq_pixel[qn][pos] = pixel;
+          wf.rq_inobj[qn][pos] = in_object ? 0 : 1;
+          wf.act_refr[act] = next_base + (int)pos;
+        }
       }
     }
   }
-  if (DBG) FlushCounters<true>(cnt, rp.counters, 0);
+  FlushCounters<DBG>(cnt, wf.work, traced);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // WfShadow: thread = (light, activation).  Light-major task order keeps the rays of a warp aimed at one light.
 // ---------------------------------------------------------------------------------------------------
 template <bool DBG>
-__global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfShadow(DeviceScene sc, RenderParams rp, WfBuffers wf, int act_begin, int n,
-                                                     int lanes) {
-#ifdef MTB_SMEM_TOP
-  __shared__ NodeRec top_store[kTopNodes];
-  const NodeRec *top = top_store;
-  const int top_n = sc.n_nodes < kTopNodes ? sc.n_nodes : kTopNodes;
-  StageTopNodes(sc, top_store, sc.n_nodes);
-#endif
-  const long long task = PackedIndex64((long long)n * sc.n_lights, lanes);
+__global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfShadow(DeviceScene sc, RenderParams rp, WfBuffers wf, int level, int lanes) {
+  MTB_DECLARE_FAST_STACK(kWfBlock);
+  if (wf.ctrl[0] != 0u) return;
+  const LevelRange lr = WfLevel(wf, level);
+  const int n = lr.n < wf.queue_cap ? lr.n : wf.queue_cap;
+  const long long tasks = (long long)n * sc.n_lights;
   unsigned long long cnt_store[DBG ? kNumCounters : 1];
   unsigned long long *cnt = cnt_store;
   if (DBG) {
     for (int k = 0; k < kNumCounters; k++) cnt[k] = 0;
   }
   unsigned traced = 0;
-  if (task < (long long)n * sc.n_lights) {
+  const WarpSpan span = WfSpan(lanes);
+  for (long long first = span.first; first < tasks; first += span.step) {
+    const long long task = first + span.lane;
+    if (span.lane >= lanes || task >= tasks) continue;
     const int li = (int)(task / n);
-    const int act = act_begin + (int)(task - (long long)li * n);
-    if (wf.act_mtl[act] >= 0) {
-      const D3 P = Load3(wf.act_point + (size_t)act * 3);
-      const D3 lpos = Load3(sc.lights[li].position);
-      const D3 ldir = Normalized(Sub(lpos, P));
-      D3 power = Mk(1.0, 1.0, 1.0);
-      bool in_shadow = false, through = false;
-      unsigned segments = 0;
-      D3 seg_start = P;
-      for (;;) {  // mythtracer.cc:94-156
-        const D3 to = Add(seg_start, MulS(ldir, 0.00001));
-        const double light_distance = Dist(seg_start, lpos);
-        double t = 0.0;
-        Count<DBG>(cnt, kShadow);
-        const int slot = Trace<DBG>(sc, to, ldir, light_distance, &t, cnt MTB_TOP_ARGS);
-        segments++;
-        if (slot < 0) break;
-        if (t > light_distance) break;
-        const int smtl = __ldg(&sc.shade[slot].material);
-        const double str = smtl >= 0 ? __ldg(&sc.materials[smtl].transparency) : 0.0;
-        if (str == 0.0) {
-          power = Mk(0.0, 0.0, 0.0);
-          in_shadow = true;
-          break;
-        }
-        if (!through) power = MulV(power, MulS(Load3(sc.materials[smtl].transmission_filter), str));
-        through = !through;
-        seg_start = Add(Add(to, MulS(ldir, t)), MulS(ldir, 0.0000001));
-        if (SqrDist(P, seg_start) > SqrDist(P, lpos)) break;
-        if (power.x <= 0.001 && power.y <= 0.001 && power.z <= 0.001) {
-          power = Mk(0.0, 0.0, 0.0);
-          in_shadow = true;
-          break;
-        }
+    const int act = lr.base + (int)(task - (long long)li * n);
+    if (wf.act_mtl[act] < 0) continue;
+    const D3 P = Load3(wf.act_point + (size_t)act * 3);
+    const D3 lpos = Load3(sc.lights[li].position);
+    const D3 ldir = Normalized(Sub(lpos, P));
+    D3 power = Mk(1.0, 1.0, 1.0);
+    bool in_shadow = false, through = false;
+    unsigned segments = 0;
+    D3 seg_start = P;
+    for (;;) {  // mythtracer.cc:94-156
+      const D3 to = Add(seg_start, MulS(ldir, 0.00001));
+      const double light_distance = Dist(seg_start, lpos);
+      double t = 0.0;
+      Count<DBG>(cnt, kShadow);
+      const int slot = Trace<DBG>(sc, to, ldir, light_distance, &t, cnt, fstack);
+      segments++;
+      if (slot < 0) break;
+      if (t > light_distance) break;
+      const int smtl = __ldg(&sc.shade[slot].material);
+      const double str = smtl >= 0 ? __ldg(&sc.materials[smtl].transparency) : 0.0;
+      if (str == 0.0) {
+        power = Mk(0.0, 0.0, 0.0);
+        in_shadow = true;
+        break;
       }
-      traced = segments;
-      Store3(wf.sh_power + ((size_t)li * wf.act_cap + act) * 3, power);
-      wf.sh_flags[(size_t)li * wf.act_cap + act] = (in_shadow ? 1u : 0u) | (segments << 1);
-      if (rp.n_rays != nullptr) atomicAdd(rp.n_rays + wf.act_pixel[act], segments);
-      WfChargeTile(rp, wf.act_pixel[act], segments);
+      if (!through) power = MulV(power, MulS(Load3(sc.materials[smtl].transmission_filter), str));
+      through = !through;
+      seg_start = Add(Add(to, MulS(ldir, t)), MulS(ldir, 0.0000001));
+      if (SqrDist(P, seg_start) > SqrDist(P, lpos)) break;
+      if (power.x <= 0.001 && power.y <= 0.001 && power.z <= 0.001) {
+        power = Mk(0.0, 0.0, 0.0);
+        in_shadow = true;
+        break;
+      }
     }
+    traced += segments;
+    Store3(wf.sh_power + ((size_t)li * wf.act_cap + act) * 3, power);
+    wf.sh_flags[(size_t)li * wf.act_cap + act] = (in_shadow ? 1u : 0u) | (segments << 1);
+    if (rp.n_rays != nullptr) atomicAdd(rp.n_rays + wf.act_pixel[act], segments);
+    WfChargeTile(rp, wf.act_pixel[act], segments);
   }
-  FlushCounters<DBG>(cnt, rp.counters, traced);
+  FlushCounters<DBG>(cnt, wf.work, traced);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // WfLight: Phong sum over the lights in scene order (mythtracer.cc:78-178)
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWfBlock) WfLight(DeviceScene sc, RenderParams rp, WfBuffers wf, int act_begin, int n) {
-  const int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  if (k >= n) return;
-  const int act = act_begin + k;
-  const int material = wf.act_mtl[act];
-  if (material < 0) return;
-  const mtb_material *m = sc.materials + material;
-  const D3 P = Load3(wf.act_point + (size_t)act * 3);
-  const D3 normal = Load3(wf.act_normal + (size_t)act * 3);
-  const D3 surface = Load3(wf.act_surface + (size_t)act * 3);
-  const D3 reflected = Load3(wf.act_reflected + (size_t)act * 3);
-  const D3 m_d = Load3(wf.act_dir + (size_t)act * 3);
-  const unsigned long long path = wf.act_path[act];
-  D3 color = Mk(0.0, 0.0, 0.0);
-  unsigned long long sig = 0;
-  for (int li = 0; li < sc.n_lights; li++) {
-    const mtb_light *lt = sc.lights + li;
-    const D3 ldir = Normalized(Sub(Load3(lt->position), P));
-    const D3 lamb = Load3(lt->ambient);
-    color = Add(color, MulV(lamb, surface));
-    D3 power = Load3(wf.sh_power + ((size_t)li * wf.act_cap + act) * 3);
-    const unsigned flags = wf.sh_flags[(size_t)li * wf.act_cap + act];
-    const bool in_shadow = (flags & 1u) != 0u;
-    sig += Mix64(path, 2ull + (unsigned long long)li, (unsigned long long)flags);
-    power.x = SMax(power.x, lamb.x);
-    power.y = SMax(power.y, lamb.y);
-    power.z = SMax(power.z, lamb.z);
-    color = Add(color, MulV(MulV(MulS(MulV(Load3(m->diffuse), surface), Dot(normal, ldir)), Load3(lt->diffuse)), power));
-    if (!in_shadow) {
-      const double refl_dot = Dot(Neg(m_d), reflected);
-      if (refl_dot > 0) {
-        color = Add(color, MulV(MulS(MulV(Load3(m->specular), surface), pow(refl_dot, m->specular_exp)), Load3(lt->specular)));
+__global__ void __launch_bounds__(kWfBlock) WfLight(DeviceScene sc, RenderParams rp, WfBuffers wf, int level) {
+  if (wf.ctrl[0] != 0u) return;
+  const LevelRange lr = WfLevel(wf, level);
+  const int n = lr.n < wf.queue_cap ? lr.n : wf.queue_cap;
+  for (int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < n; k += (int)(gridDim.x * blockDim.x)) {
+    const int act = lr.base + k;
+    const int material = wf.act_mtl[act];
+    if (material < 0) continue;
+    const mtb_material *m = sc.materials + material;
+    const D3 P = Load3(wf.act_point + (size_t)act * 3);
+    const D3 normal = Load3(wf.act_normal + (size_t)act * 3);
+    const D3 surface = Load3(wf.act_surface + (size_t)act * 3);
+    const D3 reflected = Load3(wf.act_reflected + (size_t)act * 3);
+    const D3 m_d = Load3(wf.act_dir + (size_t)act * 3);
+    const unsigned long long path = wf.act_path[act];
+    D3 color = Mk(0.0, 0.0, 0.0);
+    unsigned long long sig = 0;
+    for (int li = 0; li < sc.n_lights; li++) {
+      const mtb_light *lt = sc.lights + li;
+      const D3 ldir = Normalized(Sub(Load3(lt->position), P));
+      const D3 lamb = Load3(lt->ambient);
+      color = Add(color, MulV(lamb, surface));
+      D3 power = Load3(wf.sh_power + ((size_t)li * wf.act_cap + act) * 3);
+      const unsigned flags = wf.sh_flags[(size_t)li * wf.act_cap + act];
+      const bool in_shadow = (flags & 1u) != 0u;
+      sig += Mix64(path, 2ull + (unsigned long long)li, (unsigned long long)flags);
+      power.x = SMax(power.x, lamb.x);
+      power.y = SMax(power.y, lamb.y);
+      power.z = SMax(power.z, lamb.z);
+      color = Add(color, MulV(MulV(MulS(MulV(Load3(m->diffuse), surface), Dot(normal, ldir)), Load3(lt->diffuse)), power));
+      if (!in_shadow) {
+        const double refl_dot = Dot(Neg(m_d), reflected);
+        if (refl_dot > 0) {
+          color = Add(color, MulV(MulS(MulV(Load3(m->specular), surface), pow(refl_dot, m->specular_exp)), Load3(lt->specular)));
+        }
       }
     }
+    if (rp.sig_shadow != nullptr && sc.n_lights > 0) {
+      atomicAdd(reinterpret_cast<unsigned long long *>(rp.sig_shadow) + wf.act_pixel[act], sig);
+    }
+    Store3(wf.act_color + (size_t)act * 3, color);
   }
-  if (rp.sig_shadow != nullptr && sc.n_lights > 0) {
-    atomicAdd(reinterpret_cast<unsigned long long *>(rp.sig_shadow) + wf.act_pixel[act], sig);
-  }
-  Store3(wf.act_color + (size_t)act * 3, color);
 }
 
 // parent += child * Refl ; parent += (child * Tf) * Tr   (mythtracer.cc:185-189, 220-224)
-__global__ void __launch_bounds__(256) WfFold(DeviceScene sc, WfBuffers wf, int begin, int end) {
-  const int a = begin + (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  if (a >= end) return;
-  const int rc = wf.act_refl[a], tc = wf.act_refr[a];
-  if (rc < 0 && tc < 0) return;
-  const mtb_material *m = sc.materials + wf.act_mtl[a];
-  D3 color = Load3(wf.act_color + (size_t)a * 3);
-  if (rc >= 0) color = Add(color, MulS(Load3(wf.act_color + (size_t)rc * 3), m->reflectance));
-  if (tc >= 0) color = Add(color, MulS(MulV(Load3(wf.act_color + (size_t)tc * 3), Load3(m->transmission_filter)), m->transparency));
-  Store3(wf.act_color + (size_t)a * 3, color);
+__global__ void __launch_bounds__(256) WfFold(DeviceScene sc, WfBuffers wf, int level) {
+  if (wf.ctrl[0] != 0u) return;
+  const LevelRange lr = WfLevel(wf, level);
+  const int n = lr.n < wf.queue_cap ? lr.n : wf.queue_cap;
+  for (int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < n; k += (int)(gridDim.x * blockDim.x)) {
+    const int a = lr.base + k;
+    const int rc = wf.act_refl[a], tc = wf.act_refr[a];
+    if (rc < 0 && tc < 0) continue;
+    const mtb_material *m = sc.materials + wf.act_mtl[a];
+    D3 color = Load3(wf.act_color + (size_t)a * 3);
+    if (rc >= 0) color = Add(color, MulS(Load3(wf.act_color + (size_t)rc * 3), m->reflectance));
+    if (tc >= 0) color = Add(color, MulS(MulV(Load3(wf.act_color + (size_t)tc * 3), Load3(m->transmission_filter)), m->transparency));
+    Store3(wf.act_color + (size_t)a * 3, color);
+  }
 }
 
+// One thread = 8 bytes of a tile row (a row of 8 pixels = 24 bytes = the 24 consecutive doubles of act_color that
+// belong to slots tile * 64 + row * 8 + 0..7): the frame may be the peer-mapped frame of another GPU, where one
+// aligned 8-byte store per thread is what the link likes (RenderMega writes its tiles the same way).
 __global__ void __launch_bounds__(256) WfResolve(RenderParams rp, WfBuffers wf, int n_slots) {
-  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  if (i >= n_slots) return;
-  // same slot -> pixel mapping as level 0 of WfTraceMain (the level-0 queue itself has been reused by now)
-  const int tile = WfTileOfSlot(rp, i), t = i & 63;
+  if (wf.ctrl[0] != 0u) return;
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);  // (tile position, row, segment)
+  const int pos = i / 24, row = (i % 24) / 3, seg = i % 3;
+  if (pos * 64 >= n_slots) return;
+  // same slot -> pixel mapping as level 0 of WfTrace (the level-0 queue itself has been reused by now)
+  const int tile = WfTileOfSlot(rp, pos * 64);
   if (tile < 0) return;
   const int strip = rp.strip_first + (tile / rp.tiles_x) * rp.strip_stride;
-  const int px = (tile % rp.tiles_x) * 8 + (t & 7);
-  const int py = strip * 8 + (t >> 3);
-  if (px >= rp.chunk_w || py >= rp.chunk_h) return;
-  const int pixel = py * rp.chunk_w + px;
-  const D3 c = Load3(wf.act_color + (size_t)i * 3);
-  unsigned char *out = rp.rgb + (size_t)pixel * 3;
-  out[0] = QuantizeChannel(c.x);
-  out[1] = QuantizeChannel(c.y);
-  out[2] = QuantizeChannel(c.z);
+  const int px0 = (tile % rp.tiles_x) * 8, py = strip * 8 + row;
+  if (py >= rp.chunk_h) return;
+  const double *c = wf.act_color + ((size_t)pos * 64 + (size_t)row * 8) * 3 + seg * 8;
+  unsigned char b[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) b[k] = QuantizeChannel(c[k]);
+  unsigned char *out = rp.rgb + ((size_t)py * rp.chunk_w + px0) * 3 + seg * 8;
+  if (px0 + 8 <= rp.chunk_w && (rp.chunk_w & 7) == 0 && (reinterpret_cast<uintptr_t>(rp.rgb) & 7u) == 0u) {
+    uint2 v;
+    v.x = (unsigned)b[0] | ((unsigned)b[1] << 8) | ((unsigned)b[2] << 16) | ((unsigned)b[3] << 24);
+    v.y = (unsigned)b[4] | ((unsigned)b[5] << 8) | ((unsigned)b[6] << 16) | ((unsigned)b[7] << 24);
+    *reinterpret_cast<uint2 *>(out) = v;
+  } else {
+    const int valid = (rp.chunk_w - px0) * 3 - seg * 8;  // bytes of this segment that lie inside the chunk
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (k < valid) out[k] = b[k];
+    }
+  }
+}
+
+// Last kernel of a frame.  The work counters of a frame that overflowed are dropped (the repair launch counts its
+// own rays); host_copy (pinned, nullable) receives level_n[] and the overflow flag for the next frame's grid sizes
+// and queue capacities - written by the device, never waited for by the host.
+__global__ void WfCommit(WfBuffers wf, unsigned long long *global, uint32_t *host_copy) {
+  const int i = (int)threadIdx.x;
+  const bool overflow = wf.ctrl[0] != 0u;
+  if (!overflow && global != nullptr && i < kNumCounters && wf.work[i] != 0ull) atomicAdd(global + i, wf.work[i]);
+  if (host_copy != nullptr) {
+    if (i <= MTB_MAX_RAY_DEPTH + 1) host_copy[i] = wf.level_n[i];
+    if (i == 0) host_copy[kWfHostOverflow] = overflow ? 1u : 0u;
+    __syncwarp();
+    __threadfence_system();
+    if (i == 0) host_copy[kWfHostSequence] += 1u;  // frames completed so far
+  }
 }
 
 }  // namespace
@@ -490,68 +477,60 @@ static int PackLanes(long long n) {
   return lanes;
 }
 
-void LaunchWfSort(const WfBuffers &wf, int level, int n, cudaStream_t stream) {
-  if (n <= 0) return;
-  cudaMemsetAsync(wf.sort_hist, 0, sizeof(uint32_t) << kWfSortBits, stream);
-  const uint32_t *keys = wf.sort_key[level & 1];
-  WfSortHistogram<<<(n + 255) / 256, 256, 0, stream>>>(keys, wf.sort_hist, n);
-  WfSortScan<<<1, 1024, 0, stream>>>(wf.sort_hist);
-  WfSortScatter<<<(n + 255) / 256, 256, 0, stream>>>(keys, wf.sort_hist, wf.perm, n);
+// Blocks for `items` loop items at `lanes` items per warp, at most what `bound` items need; never zero (the real
+// item count is read on the device, the loops are grid-strided).
+static int BlocksFor(long long items, long long bound, int lanes, int block) {
+  if (items > bound) items = bound;
+  if (items < 1) items = 1;
+  const long long warps = (items + lanes - 1) / lanes;
+  long long blocks = (warps * 32 + block - 1) / block;
+  if (blocks > 0x3fffffff) blocks = 0x3fffffff;
+  return (int)blocks;
 }
 
-void LaunchWfTraceMain(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
-                       int act_base, bool sorted, bool debug_build, cudaStream_t stream) {
-  if (n <= 0) return;
-  const int lanes = level == 0 ? 32 : PackLanes(n);  // level 0 maps warps to 8x4 pixel tiles
-  const long long warps = ((long long)n + lanes - 1) / lanes;
-  const int blocks = (int)((warps * 32 + kWfBlock - 1) / kWfBlock);
-  const int32_t *perm = sorted ? wf.perm : nullptr;
-  if (debug_build) {
-    WfTraceMain<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base, perm, lanes);
-  } else {
-    WfTraceMain<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base, perm, lanes);
-  }
-}
+void LaunchWfBegin(const WfBuffers &wf, int slots, cudaStream_t stream) { WfBegin<<<1, 32, 0, stream>>>(wf, slots); }
 
-void LaunchWfSpawn(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, int n,
-                   int act_base, bool debug_build, cudaStream_t stream) {
-  if (n <= 0) return;
-  const int blocks = (n + kWfBlock - 1) / kWfBlock;
-  if (debug_build) {
-    WfSpawn<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base);
-  } else {
-    WfSpawn<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, n, act_base);
-  }
-}
-
-void LaunchWfShadow(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int act_begin, int n,
-                    bool debug_build, cudaStream_t stream) {
-  const long long tasks = (long long)n * sc.n_lights;
-  if (tasks <= 0) return;
-  const int lanes = PackLanes(tasks);
-  const long long warps = (tasks + lanes - 1) / lanes;
-  const int blocks = (int)((warps * 32 + kWfBlock - 1) / kWfBlock);
-  if (debug_build) {
-    WfShadow<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, act_begin, n, lanes);
-  } else {
-    WfShadow<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, act_begin, n, lanes);
-  }
-}
-
-void LaunchWfLight(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int act_begin, int n,
+// `expect`: how many rays the level is expected to hold (previous frame, with headroom; or the capacity bound)
+void LaunchWfTrace(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, long long expect, bool debug_build,
                    cudaStream_t stream) {
-  if (n <= 0) return;
-  WfLight<<<(n + kWfBlock - 1) / kWfBlock, kWfBlock, 0, stream>>>(sc, rp, wf, act_begin, n);
+  const int lanes = level == 0 ? 32 : PackLanes(expect);  // level 0 maps warps to 8x4 pixel tiles
+  const int blocks = BlocksFor(expect, wf.queue_cap, lanes, kWfBlock);
+  if (debug_build) {
+    WfTrace<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, lanes);
+  } else {
+    WfTrace<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, lanes);
+  }
 }
 
-void LaunchWfFold(const DeviceScene &sc, const WfBuffers &wf, int begin, int end, cudaStream_t stream) {
-  if (end <= begin) return;
-  WfFold<<<(end - begin + 255) / 256, 256, 0, stream>>>(sc, wf, begin, end);
+void LaunchWfShadow(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, long long expect, bool debug_build,
+                    cudaStream_t stream) {
+  if (sc.n_lights <= 0) return;
+  const long long tasks = expect * sc.n_lights;
+  const int lanes = PackLanes(tasks);
+  const int blocks = BlocksFor(tasks, (long long)wf.queue_cap * sc.n_lights, lanes, kWfBlock);
+  if (debug_build) {
+    WfShadow<true><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, lanes);
+  } else {
+    WfShadow<false><<<blocks, kWfBlock, 0, stream>>>(sc, rp, wf, level, lanes);
+  }
+}
+
+void LaunchWfLight(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int level, long long expect, cudaStream_t stream) {
+  WfLight<<<BlocksFor(expect, wf.queue_cap, 32, kWfBlock), kWfBlock, 0, stream>>>(sc, rp, wf, level);
+}
+
+void LaunchWfFold(const DeviceScene &sc, const WfBuffers &wf, int level, long long expect, cudaStream_t stream) {
+  WfFold<<<BlocksFor(expect, wf.queue_cap, 32, 256), 256, 0, stream>>>(sc, wf, level);
 }
 
 void LaunchWfResolve(const RenderParams &rp, const WfBuffers &wf, int n_slots, cudaStream_t stream) {
   if (n_slots <= 0) return;
-  WfResolve<<<(n_slots + 255) / 256, 256, 0, stream>>>(rp, wf, n_slots);
+  const int threads = (n_slots / 64) * 24;
+  WfResolve<<<(threads + 255) / 256, 256, 0, stream>>>(rp, wf, n_slots);
+}
+
+void LaunchWfCommit(const WfBuffers &wf, unsigned long long *global, uint32_t *host_copy, cudaStream_t stream) {
+  WfCommit<<<1, 32, 0, stream>>>(wf, global, host_copy);
 }
 
 }  // namespace mtb

@@ -444,6 +444,13 @@ class Reference:
     def threads(self):
         return self.lib().ref_num_threads()
 
+    def set_threads(self, n: int):
+        """Team size of the reference's OpenMP loop (a launcher may have exported OMP_NUM_THREADS=1)."""
+        lib = self.lib()
+        if hasattr(lib, "ref_set_threads"):
+            lib.ref_set_threads.argtypes = [ctypes.c_int]
+            lib.ref_set_threads(int(n))
+
     def aabb(self):
         out = np.zeros(6)
         self.lib().ref_scene_aabb(_ptr(out))

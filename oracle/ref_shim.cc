@@ -87,6 +87,13 @@ extern "C" {
 
 int ref_num_threads() { return omp_get_max_threads(); }
 
+// The reference's `#pragma omp parallel for` (mythtracer.cc:292-295) takes the runtime's default team size.  A launcher
+// that exports OMP_NUM_THREADS=1 (torch.distributed.run does) would silently time it on one core: the bench's
+// reference arm states the team size instead.
+void ref_set_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+}
+
 void ref_set_depth(int depth) { raytracer::MAX_RECURSION_LEVEL = depth; }
 
 int ref_get_depth() { return raytracer::MAX_RECURSION_LEVEL; }

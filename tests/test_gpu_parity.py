@@ -374,21 +374,21 @@ def test_wavefront_depths_lights_lattice_and_tiles(product_lib, oracle_mod, scen
     _assert_render_equal(gpu, cpu, "wavefront lattice")
 
 
-def test_persistent_and_tile_per_block_megakernel_agree(product_lib, oracle_mod, scene_dir):
-    """The megakernel's three launch forms -- one 8x8 tile per block (default), 16x8 tiles with block-level ray
-    packing (MTB_FLAG_PACKING) and persistent warps whose lanes draw pixels from a counter (MTB_FLAG_PERSISTENT) -- against the oracle and against each other, every tap, on a
-    full frame, a clipped odd-sized tile, a partitioned render and two consecutive frames (warm tile order)."""
-    from mythtracer_b200 import MTB_FLAG_COUNT_WORK, MTB_FLAG_MEGAKERNEL, MTB_FLAG_PACKING, MTB_FLAG_PERSISTENT, MTB_FLAG_RESUME, MTB_FLAG_WARP_SYNC
+def test_megakernel_launch_forms(product_lib, oracle_mod, scene_dir):
+    """The megakernel against the oracle, every tap: the plain and the counting build, with and without the
+    cost-aware tile order, with the retired round-1 flag bits set (accepted and ignored) -- on a full frame, a
+    clipped odd-sized tile (rows that cannot leave the block as aligned 8-byte stores), a partitioned render and
+    two consecutive frames (warm tile order)."""
+    from mythtracer_b200 import (MTB_FLAG_COUNT_WORK, MTB_FLAG_MEGAKERNEL, MTB_FLAG_NO_TILE_ORDER, MTB_FLAG_PACKING,
+                                 MTB_FLAG_PERSISTENT, MTB_FLAG_RESUME, MTB_FLAG_WARP_SYNC)
     files, cfg = scenes.config_scene("C2", scene_dir, 0.3)
     mt, orc = _load_pair(product_lib, oracle_mod, files, cfg["depth"], MTB_FLAG_MEGAKERNEL)
     w, h = 250, 141
     cpu = orc.render(files.camera, w, h, depth=cfg["depth"], taps=True)
     cpu_tile = orc.render(files.camera, 333, 211, chunk=(100, 37, 77, 45), depth=cfg["depth"], taps=True)
-    for flags in (MTB_FLAG_MEGAKERNEL, MTB_FLAG_MEGAKERNEL | MTB_FLAG_PACKING, MTB_FLAG_MEGAKERNEL | MTB_FLAG_PERSISTENT,
-                  MTB_FLAG_MEGAKERNEL | MTB_FLAG_WARP_SYNC, MTB_FLAG_MEGAKERNEL | MTB_FLAG_WARP_SYNC | MTB_FLAG_COUNT_WORK,
-                  MTB_FLAG_MEGAKERNEL | MTB_FLAG_RESUME, MTB_FLAG_MEGAKERNEL | MTB_FLAG_RESUME | MTB_FLAG_COUNT_WORK,
-                  MTB_FLAG_MEGAKERNEL | MTB_FLAG_COUNT_WORK, MTB_FLAG_MEGAKERNEL | MTB_FLAG_PACKING | MTB_FLAG_COUNT_WORK,
-                  MTB_FLAG_MEGAKERNEL | MTB_FLAG_PERSISTENT | MTB_FLAG_COUNT_WORK):
+    cpu_w8 = orc.render(files.camera, 256, 100, chunk=(0, 0, 256, 100), depth=cfg["depth"], taps=True)
+    for flags in (MTB_FLAG_MEGAKERNEL, MTB_FLAG_MEGAKERNEL | MTB_FLAG_COUNT_WORK, MTB_FLAG_MEGAKERNEL | MTB_FLAG_NO_TILE_ORDER,
+                  MTB_FLAG_MEGAKERNEL | MTB_FLAG_PACKING | MTB_FLAG_PERSISTENT | MTB_FLAG_RESUME | MTB_FLAG_WARP_SYNC):
         mt.set_flags(flags)
         for frame in range(2):
             gpu = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
@@ -396,6 +396,10 @@ def test_persistent_and_tile_per_block_megakernel_agree(product_lib, oracle_mod,
         full = gpu["rgb"].copy()
         gpu = mt.render_chunk(files.camera, 333, 211, 100, 37, 77, 45, debug=True, taps=True)
         _assert_render_equal(gpu, cpu_tile, "flags %d tile" % flags)
+        # a width that is a multiple of 8 (whole tile rows leave the block as aligned 8-byte stores) with a clipped
+        # last strip (100 = 12 * 8 + 4 rows)
+        gpu = mt.render_chunk(files.camera, 256, 100, 0, 0, 256, 100, debug=True, taps=True)
+        _assert_render_equal(gpu, cpu_w8, "flags %d 256x100" % flags)
         # two partitions of the frame: each fills only its own strips, together they are the frame
         parts = []
         for rank in range(2):
@@ -679,12 +683,13 @@ def test_hybrid_frames(product_lib, oracle_mod, scene_dir):
         assert got["stats"]["rays"] == ref["stats"]["rays"]
 
 
-def test_stated_edge_case_sibling_entry_tie_on_the_device(product_lib, oracle_mod):
-    """DESIGN.md section 4, stated edge case (a), on the device: for the constructed ray through an octree grid edge
-    (tests/test_certification_math.py has the construction and the reference's side of it) MTB_FLAG_EXACT_OCTREE must
-    return what the reference returns -- the FARTHER triangle, bit-identical t -- while the default closest-hit
-    traversal returns the nearer one.  This is the one place where the default is allowed to differ, and does."""
-    from mythtracer_b200 import MythTracer, MTB_FLAG_EXACT_OCTREE
+def test_sibling_entry_tie_on_the_device(product_lib, oracle_mod):
+    """Round 1's stated edge case (a), closed: for the constructed ray through an octree grid edge
+    (tests/test_certification_math.py has the construction and the reference's side of it) the reference returns the
+    FARTHER triangle (octtree.cc:244-246 stops behind a sibling whose entry distance ties).  The default traversal
+    must return exactly that -- the winner of its closest-hit search lies in an octree node the ray only touches
+    (DegeneratePassage, device_core.cuh), so the ray is handed to the exact recursion -- as must MTB_FLAG_EXACT_OCTREE."""
+    from mythtracer_b200 import MythTracer, MTB_FLAG_COUNT_WORK, MTB_FLAG_EXACT_OCTREE
     from mythtracer_b200.api import MTL_DTYPE, TRI_DTYPE
     tris = []
 
@@ -702,15 +707,18 @@ def test_stated_edge_case_sibling_entry_tie_on_the_device(product_lib, oracle_mo
     arr["vertex"] = np.array(tris, float)
     arr["material"] = -1
     arr["line_no"] = np.arange(len(tris))
-    o = np.array([[7.0, 7.0, 3.0]])
-    d = np.array([[-1.0, -1.0, -0.125]])
+    # the tie ray, and two neighbours of it that pass the grid edge at a distance (no tie: the nearer triangle wins)
+    o = np.array([[7.0, 7.0, 3.0], [7.0, 7.0, 3.0], [7.0, 7.0, 3.0]])
+    d = np.array([[-1.0, -1.0, -0.125], [-1.0, -0.99, -0.125], [-0.99, -1.0, -0.125]])
     ref = oracle_mod.Oracle(arr, np.zeros(0, MTL_DTYPE), []).intersect(o, d)
     assert ref["tri"][0] == 0
-    exact = MythTracer(flags=MTB_FLAG_EXACT_OCTREE)
-    exact.upload(arr, np.zeros(0, MTL_DTYPE))
-    got = exact.intersect_rays(o, d)
-    assert got["tri"][0] == 0 and got["t"][0] == ref["t"][0]
-    fast = MythTracer()
-    fast.upload(arr, np.zeros(0, MTL_DTYPE))
-    got = fast.intersect_rays(o, d)
-    assert got["tri"][0] == 1 and got["t"][0] == 3.0
+    for flags in (MTB_FLAG_EXACT_OCTREE, 0, MTB_FLAG_COUNT_WORK):
+        mt = MythTracer(flags=flags)
+        mt.upload(arr, np.zeros(0, MTL_DTYPE))
+        got = mt.intersect_rays(o, d, want_stats=True)
+        assert np.array_equal(got["tri"], ref["tri"]), (flags, got["tri"], ref["tri"])
+        hit = ref["tri"] >= 0
+        assert np.array_equal(got["t"][hit], ref["t"][hit])
+        if flags == MTB_FLAG_COUNT_WORK:
+            assert got["stats"]["n_fallback"] >= 1 and got["stats"]["n_fast"] >= 1
+        mt.close()

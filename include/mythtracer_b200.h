@@ -102,6 +102,8 @@ typedef struct {
   uint64_t n_literal; /* rays that took the literal (NaN-exact) traversal */
   uint64_t n_fast;     /* rays answered by the certified fast traversal (scene BVH) */
   uint64_t n_fallback; /* rays the fast traversal could not certify and handed to the exact octree recursion */
+  uint64_t n_long128_rays, n_long128_visits; /* fast traversals of more than 128 scene-BVH node visits, and their visits */
+  uint64_t n_long512_rays, n_long512_visits; /* ... of more than 512 node visits (the tail that bounds small partitions) */
   double kernel_ms;   /* device time of the kernels of this call (CUDA events) */
   double total_ms;    /* host wall time of the call, copies included */
 } mtb_stats;

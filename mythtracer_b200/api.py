@@ -58,7 +58,7 @@ CAMERA_DTYPE = np.dtype([("origin", "f8", (3,)), ("pitch", "f8"), ("yaw", "f8"),
 DEBUG_DTYPE = np.dtype([("line_no", "i4"), ("pad_", "i4"), ("point", "f8", (3,))], align=True)
 STATS_DTYPE = np.dtype([(n, "u8") for n in ("rays", "primary", "shadow", "reflect", "refract", "n_slab", "n_visit",
                                             "n_triaabb", "n_mt", "n_hit", "n_shade", "n_bvh", "n_literal", "n_fast",
-                                            "n_fallback")] +
+                                            "n_fallback", "n_long128_rays", "n_long128_visits", "n_long512_rays", "n_long512_visits")] +
                        [("kernel_ms", "f8"), ("total_ms", "f8")], align=True)
 SUMMARY_DTYPE = np.dtype([("n_triangles", "i8"), ("n_nodes", "i8"), ("n_bvh_nodes", "i8"), ("tree_depth", "i4"),
                           ("n_materials", "i4"), ("n_textures", "i4"), ("n_lights", "i4"), ("root_list", "i8"),

@@ -61,6 +61,7 @@ struct DeviceState {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   cudaEvent_t ev_gathered = nullptr;  // device 0 only: the last gather has read every peer buffer
+  cudaStream_t l2_window_stream = nullptr;  // stream that carries the L2 access-policy window (MTB_L2_PERSIST_MB)
   bool peer_to_dev0 = false;     // device 0 can read this device's memory (peer-copy gather)
   bool peer_store_dev0 = false;  // this device's kernels can store into device 0's memory (direct tile stores)
   // scene
@@ -180,6 +181,7 @@ struct mtb_context {
   int64_t device_bytes = 0;
   std::atomic<uint64_t> launches{0};  // kernels of this library launched so far (mtb_launch_count)
   bool no_peer_store = false;         // MTB_NO_PEER_STORE=1: gather with peer copies instead of direct tile stores (A/B)
+  int l2_persist_mb = 0;              // MTB_L2_PERSIST_MB=n: pin the scene BVH's nodes in n MB of persisting L2 (A/B)
   std::vector<void *> owned_frames, opened_frames;  // mtb_frame_create / mtb_frame_open
   std::mutex err_mutex;
 };
@@ -278,6 +280,28 @@ int UploadToDevice(mtb_context *ctx, DeviceState *d) {
   return MTB_OK;
 }
 
+// A/B knob: an access-policy window over the scene BVH's node array on `s` (hit = persisting, miss = streaming), so
+// that the thread-local memory traffic of the kernels cannot evict the nodes every ray walks.
+void ApplyL2Window(mtb_context *ctx, DeviceState *d, cudaStream_t s) {
+  if (ctx->l2_persist_mb <= 0 || d->gnodes.ptr == nullptr || ctx->flat.gnodes.empty()) return;
+  int max_persist = 0, max_window = 0;
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, d->device);
+  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, d->device);
+  size_t carve = std::min<size_t>((size_t)ctx->l2_persist_mb << 20, (size_t)std::max(max_persist, 0));
+  if (carve == 0 || max_window <= 0) return;
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+  const size_t bytes = std::min<size_t>(ctx->flat.gnodes.size() * sizeof(mtb::Bvh2Node), (size_t)max_window);
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof(attr));
+  attr.accessPolicyWindow.base_ptr = d->gnodes.ptr;
+  attr.accessPolicyWindow.num_bytes = bytes;
+  attr.accessPolicyWindow.hitRatio = bytes <= carve ? 1.0f : (float)((double)carve / (double)bytes);
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+  cudaGetLastError();
+}
+
 int UploadLights(mtb_context *ctx, DeviceState *d) {
   MTB_CUDA(ctx, cudaSetDevice(d->device));
   MTB_CUDA(ctx, d->lights.Upload(ctx->lights.data(), ctx->lights.size(), d->stream));
@@ -337,6 +361,10 @@ void FillStats(const unsigned long long *c, mtb_stats *s) {
   s->n_literal = c[mtb::kLiteral];
   s->n_fast = c[mtb::kFast];
   s->n_fallback = c[mtb::kFallback];
+  s->n_long128_rays = c[mtb::kLongRays128];
+  s->n_long128_visits = c[mtb::kLongVisits128];
+  s->n_long512_rays = c[mtb::kLongRays512];
+  s->n_long512_visits = c[mtb::kLongVisits512];
 }
 
 struct StripPlan {
@@ -658,6 +686,10 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
       wavefront = d.tune_stage == 3 || d.tune_stage == 4 || (d.tune_stage == 7 && d.tune_choice == 1);
       hybrid = d.tune_stage == 5 || d.tune_stage == 6 || (d.tune_stage == 7 && d.tune_choice == 2);
     }
+    if (ctx->l2_persist_mb > 0 && d.l2_window_stream != s) {
+      ApplyL2Window(ctx, &d, s);
+      d.l2_window_stream = s;
+    }
     MTB_CUDA(ctx, cudaEventRecord(d.ev_start, s));
     if (wavefront) {
       // the wavefront kernels accumulate the taps with atomics
@@ -856,6 +888,8 @@ int mtb_create(mtb_context **out, const int *devices, int n_devices) {
   {  // development knobs (A/B measurements, tests that force a queue overflow)
     const char *v = getenv("MTB_NO_PEER_STORE");
     ctx->no_peer_store = v != nullptr && v[0] == '1';
+    const char *l2 = getenv("MTB_L2_PERSIST_MB");
+    ctx->l2_persist_mb = l2 != nullptr ? atoi(l2) : 0;
     const char *qf = getenv("MTB_WF_QUEUE_FACTOR"), *af = getenv("MTB_WF_ACT_FACTOR");
     for (DeviceState &d : ctx->dev) {
       if (qf != nullptr && atoi(qf) >= 1) d.wf_queue_factor = atoi(qf);

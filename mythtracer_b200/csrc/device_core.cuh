@@ -530,10 +530,18 @@ constexpr int kFastExit = (int)0x80000000;
 // error bound of t against the exact ray-plane parameter: with u = 2^-53 and |x| meaning component-wise
 // magnitudes, det carries at most 7u * D, D = |e1| . (|d| x |e2|), the numerator at most 8u * N,
 // N = |e2| . (|tvec| x |e1|), and the final quotient 2u |t|; the bound uses 16u, 16u and 8u.
-__device__ __forceinline__ bool MollerTrumboreBound(const double *vert, const Ray &r, double *t_out, double *e_out) {
-  const double2 a = Ld2(vert + 0), b = Ld2(vert + 2), c = Ld2(vert + 4), d = Ld2(vert + 6);
-  const double v22 = __ldg(vert + 8);
-  const D3 v0 = Mk(a.x, a.y, b.x), v1 = Mk(b.y, c.x, c.y), v2 = Mk(d.x, d.y, v22);
+struct TriVerts {
+  double2 a, b, c, d;
+  double v22;
+};
+__device__ __forceinline__ TriVerts LoadVerts(const double *vert) {
+  TriVerts v;
+  v.a = Ld2(vert + 0), v.b = Ld2(vert + 2), v.c = Ld2(vert + 4), v.d = Ld2(vert + 6);
+  v.v22 = __ldg(vert + 8);
+  return v;
+}
+__device__ __forceinline__ bool MollerTrumboreBound(const TriVerts &tv, const Ray &r, double *t_out, double *e_out) {
+  const D3 v0 = Mk(tv.a.x, tv.a.y, tv.b.x), v1 = Mk(tv.b.y, tv.c.x, tv.c.y), v2 = Mk(tv.d.x, tv.d.y, tv.v22);
   const D3 e1 = Sub(v1, v0);
   const D3 e2 = Sub(v2, v0);
   const D3 pvec = Cross(r.d, e2);
@@ -569,53 +577,112 @@ __device__ __forceinline__ bool MollerTrumboreBound(const double *vert, const Ra
   return true;
 }
 
-// What the LEAVES need of a ray and of the search so far, in the thread's local memory: the FP64 ray (the exact
-// tests run in the reference's FP64 arithmetic) and the best hit with its error bound.  The node loop runs on FP32
-// values only (FastRay); keeping the 18 registers of the FP64 ray and the 6 of the best hit alive across it made
-// the register allocator spill and rematerialise inside the loop (3 local loads + 3 F2F + 3 DSETP per node visit
-// under the 64-register cap).  MTB_FAST_BARRIER makes the address escape, so nothing of it stays in registers
-// between two leaf visits.
+// What the LEAVES need of a ray and of the search so far: the FP64 ray (the exact tests run in the reference's FP64
+// arithmetic) and the best hit with its error bound - twelve doubles per thread that are written once per ray and
+// read at every leaf visit.  The node loop runs on FP32 values only (FastRay); keeping the 18 registers of the FP64
+// ray and the 6 of the best hit alive across it made the register allocator spill and rematerialise inside the loop
+// (3 local loads + 3 F2F + 3 DSETP per node visit under the 64-register cap).
+//
+// Where the twelve doubles live is a build option (measured A/B in DESIGN.md section 5):
+//   MTB_SMEM_RAY = 1  shared memory, laid out [field][thread] (conflict-free 64-bit accesses).  ncu on the
+//                     local-memory form: the leaf reloads were 44 % of the kernel's local-memory bytes, half of them
+//                     missed L1 (the per-SM working set of 1024 threads' local memory is larger than L1) and went to
+//                     L2 next to the BVH nodes.
+//   MTB_SMEM_RAY = 0  a local struct whose address escapes through MTB_FAST_BARRIER, so nothing of it stays in
+//                     registers between two leaf visits.
+#ifndef MTB_SMEM_RAY
+#define MTB_SMEM_RAY 1
+#endif
+#ifndef MTB_LEAF_PRELOAD
+#define MTB_LEAF_PRELOAD 1
+#endif
+// Traversal stack of TraceFast.  An entry is 64 bits: conservative entry distance (FP32 bits) << 32 | child
+// reference.  Short-stack form (north star item 3): the first MTB_SMEM_STACK entries of every thread live in shared
+// memory, laid out [entry][thread]; only deeper entries go to the thread's local array.  MTB_SMEM_STACK = 0 keeps
+// the whole stack in local memory (measured: 8.93 vs 9.06 ms on C3 for 8 shared entries - the carve-out costs L1).
+#ifndef MTB_SMEM_STACK
+#define MTB_SMEM_STACK 0
+#endif
+enum FastField { kFmO = 0, kFmD = 3, kFmInv = 6, kFmT = 9, kFmE = 10, kFmLo2 = 11, kFmWords = 12 };
 struct alignas(16) FastMem {
-  double o[3], d[3], inv[3];
-  double t, e, lo2;  // best hit: distance, forward error bound; lo2 = min (t - e) over all other accepted hits
+  double w[kFmWords];  // o.xyz, d.xyz, inv.xyz, best t, its error bound e, lo2 = min (t - e) over all other accepted hits
 };
 #define MTB_FAST_BARRIER(m) asm volatile("" : : "l"(m) : "memory")
+
+// Per-thread handles of the fast traversal's scratch memory.
+struct FastCtx {
+  unsigned stack_base;  // shared-space address of this thread's stack column (entry k at + k * stride_bytes)
+  unsigned ray_base;    // shared-space address of this thread's FastMem column (field f at + f * stride_bytes)
+  int stride_bytes;     // threads per block * 8
+};
+#if MTB_SMEM_STACK > 0 || MTB_SMEM_RAY
+#define MTB_DECLARE_FAST_CTX(threads)                                                                         \
+  __shared__ unsigned long long s_fast_scratch[(MTB_SMEM_STACK + (MTB_SMEM_RAY ? kFmWords : 0)) * (threads)]; \
+  const unsigned fast_base__ = (unsigned)__cvta_generic_to_shared(s_fast_scratch + threadIdx.x);              \
+  const FastCtx fctx{fast_base__, fast_base__ + (unsigned)(MTB_SMEM_STACK * (threads) * 8), (threads) * 8}
+#else
+#define MTB_DECLARE_FAST_CTX(threads) const FastCtx fctx{0u, 0u, 0}
+#endif
+
+__device__ __forceinline__ double FmLoad(const FastCtx &fc, const FastMem *m, int field) {
+#if MTB_SMEM_RAY
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(fc.ray_base + (unsigned)(field * fc.stride_bytes)));
+  return v;
+#else
+  return m->w[field];
+#endif
+}
+__device__ __forceinline__ void FmStore(const FastCtx &fc, FastMem *m, int field, double v) {
+#if MTB_SMEM_RAY
+  asm volatile("st.shared.f64 [%0], %1;" : : "r"(fc.ray_base + (unsigned)(field * fc.stride_bytes)), "d"(v));
+#else
+  m->w[field] = v;
+#endif
+}
+__device__ __forceinline__ D3 FmLoad3(const FastCtx &fc, const FastMem *m, int field) {
+  return Mk(FmLoad(fc, m, field), FmLoad(fc, m, field + 1), FmLoad(fc, m, field + 2));
+}
 
 struct FastRay {
   float ix, iy, iz, nox, noy, noz;  // FP32 inverse direction and -(origin * inverse direction)
 };
 
-// One triangle of a scene-BVH leaf: the reference's exact FP64 pre-test and Moller-Trumbore.  *slot / *prune are the
-// canonical slot of the best hit so far (-1: none) and the FP32 pruning distance (registers of the caller).
+// One triangle of a scene-BVH leaf: the reference's exact FP64 pre-test and Moller-Trumbore.  `r` carries the FP64
+// origin and inverse direction (loaded once per leaf visit); the direction is fetched when the pre-test passes.
+// *slot / *prune are the canonical slot of the best hit so far (-1: none) and the FP32 pruning distance.
 template <bool DBG>
-__device__ __forceinline__ void TestSlotFast(const SlotRec *rec, FastMem *m, int *slot, float *prune, unsigned long long *cnt) {
-  Ray r;
-  r.o = Mk(m->o[0], m->o[1], m->o[2]);
-  r.inv = Mk(m->inv[0], m->inv[1], m->inv[2]);
-  r.sx = r.inv.x < 0.0;
-  r.sy = r.inv.y < 0.0;
-  r.sz = r.inv.z < 0.0;
+__device__ __forceinline__ void TestSlotFast(const SlotRec *rec, Ray &r, const FastCtx &fc, FastMem *m, int *slot, float *prune,
+                                             unsigned long long *cnt) {
   const double2 b0 = Ld2(rec->box + 0), b1 = Ld2(rec->box + 2), b2 = Ld2(rec->box + 4);
+#if MTB_LEAF_PRELOAD
+  // the vertices travel with the box (same 128-byte record): one memory round trip per candidate instead of two
+  // for the 58 % of the candidates that pass the pre-test
+  const TriVerts tv = LoadVerts(rec->vert);
+#endif
   Count<DBG>(cnt, kTriAabb);
   double unused;
   if (!SlabRegular(b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, r, &unused)) return;  // primitive_triangle.cc:85-108
   Count<DBG>(cnt, kMt);
-  r.d = Mk(m->d[0], m->d[1], m->d[2]);
+  r.d = FmLoad3(fc, m, kFmD);
+#if !MTB_LEAF_PRELOAD
+  const TriVerts tv = LoadVerts(rec->vert);
+#endif
   double t, e;
-  if (!MollerTrumboreBound(rec->vert, r, &t, &e)) return;
+  if (!MollerTrumboreBound(tv, r, &t, &e)) return;
   Count<DBG>(cnt, kHit);
   const int canon = __ldg(&rec->canon);
   if (canon == *slot) return;  // the best hit itself, met again through another of its references (spatial splits)
   if (*slot >= 0) {
-    const double bt = m->t;
+    const double bt = FmLoad(fc, m, kFmT), lo2 = FmLoad(fc, m, kFmLo2);
     if (!(t < bt)) {
-      m->lo2 = fmin(m->lo2, t - e);
+      FmStore(fc, m, kFmLo2, fmin(lo2, t - e));
       return;
     }
-    m->lo2 = fmin(m->lo2, bt - m->e);
+    FmStore(fc, m, kFmLo2, fmin(lo2, bt - FmLoad(fc, m, kFmE)));
   }
-  m->t = t;
-  m->e = e;
+  FmStore(fc, m, kFmT, t);
+  FmStore(fc, m, kFmE, e);
   *slot = canon;
   *prune = fminf(*prune, __double2float_ru(t + 2.0 * e + t * 0x1p-20));
 }
@@ -663,34 +730,12 @@ __device__ __forceinline__ float LimitPrune(const DeviceScene &sc, const D3 &d, 
   return __double2float_ru(t_limit + 2.0 * m + t_limit * 0x1p-20);
 }
 
-// Traversal stack of TraceFast.  An entry is 64 bits: conservative entry distance (FP32 bits) << 32 | child
-// reference.  Short-stack form (north star item 3): the first MTB_SMEM_STACK entries of every thread live in shared
-// memory, laid out [entry][thread] (conflict-free 64-bit accesses, no local-memory traffic, no L1 lines taken from the
-// BVH nodes); only deeper entries - a few per cent of the pushes - go to the thread's local array.  MTB_SMEM_STACK = 0
-// keeps the whole stack in local memory (measured A/B in DESIGN.md section 5).
-#ifndef MTB_SMEM_STACK
-#define MTB_SMEM_STACK 8
-#endif
-struct FastStack {
-  unsigned sbase;  // shared-space address of this thread's column (entry k at sbase + k * stride_bytes)
-  int stride_bytes;
-};
-#if MTB_SMEM_STACK > 0
-// (the address goes through an empty asm: left to itself the compiler recomputes it from SR_TID at every push / pop)
-#define MTB_DECLARE_FAST_STACK(threads)                                                    \
-  __shared__ unsigned long long s_fast_stack[MTB_SMEM_STACK * (threads)];                   \
-  unsigned fast_stack_base__ = (unsigned)__cvta_generic_to_shared(s_fast_stack + threadIdx.x); \
-  asm volatile("" : "+r"(fast_stack_base__));                                              \
-  const FastStack fstack{fast_stack_base__, (threads) * 8}
-#else
-#define MTB_DECLARE_FAST_STACK(threads) const FastStack fstack{0u, 0}
-#endif
 constexpr int kFastLocalStack = kFastStack - MTB_SMEM_STACK;
 
-__device__ __forceinline__ void FastPush(const FastStack &fs, unsigned long long *local, int sp, unsigned long long v) {
+__device__ __forceinline__ void FastPush(const FastCtx &fc, unsigned long long *local, int sp, unsigned long long v) {
 #if MTB_SMEM_STACK > 0
   if (sp < MTB_SMEM_STACK) {
-    asm volatile("st.shared.u64 [%0], %1;" : : "r"(fs.sbase + (unsigned)(sp * fs.stride_bytes)), "l"(v));
+    asm volatile("st.shared.u64 [%0], %1;" : : "r"(fc.stack_base + (unsigned)(sp * fc.stride_bytes)), "l"(v));
   } else {
     local[sp - MTB_SMEM_STACK] = v;
   }
@@ -698,11 +743,11 @@ __device__ __forceinline__ void FastPush(const FastStack &fs, unsigned long long
   local[sp] = v;
 #endif
 }
-__device__ __forceinline__ unsigned long long FastPop(const FastStack &fs, const unsigned long long *local, int sp) {
+__device__ __forceinline__ unsigned long long FastPop(const FastCtx &fc, const unsigned long long *local, int sp) {
 #if MTB_SMEM_STACK > 0
   if (sp < MTB_SMEM_STACK) {
     unsigned long long v;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(fs.sbase + (unsigned)(sp * fs.stride_bytes)));
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(fc.stack_base + (unsigned)(sp * fc.stride_bytes)));
     return v;
   }
   return local[sp - MTB_SMEM_STACK];
@@ -722,10 +767,10 @@ __device__ __forceinline__ unsigned long long FastPop(const FastStack &fs, const
 // that HOLDS the winning triangle is measured with the reference's own FP64 slab arithmetic, and a passage shorter
 // than 2^-40 relative (keys carry ~2^-52) hands the ray to the exact recursion.  The test ray of round 1
 // (o = (7,7,3), d = (-1,-1,-1/8) through the edge x = y = 4 of a [0,8]^3 root) is such a ray.
-__device__ __forceinline__ bool DegeneratePassage(const DeviceScene &sc, int slot, const FastMem *m) {
+__device__ __forceinline__ bool DegeneratePassage(const DeviceScene &sc, int slot, const FastCtx &fc, const FastMem *m) {
   Ray r;
-  r.o = Mk(m->o[0], m->o[1], m->o[2]);
-  r.inv = Mk(m->inv[0], m->inv[1], m->inv[2]);
+  r.o = FmLoad3(fc, m, kFmO);
+  r.inv = FmLoad3(fc, m, kFmInv);
   r.sx = r.inv.x < 0.0;
   r.sy = r.inv.y < 0.0;
   r.sz = r.inv.z < 0.0;
@@ -740,31 +785,39 @@ __device__ __forceinline__ bool DegeneratePassage(const DeviceScene &sc, int slo
   return !(tmax - tmin > 0x1p-40 * (fabs(tmin) + fabs(tmax)));
 }
 
-// `m` holds the FP64 ray (filled by the caller); `prune0` = LimitPrune.  Returns the canonical slot of the closest
-// accepted hit (-1: none) with its distance in *t_out.
+// The FP64 ray has been stored by the caller (fields kFmO .. kFmInv); `prune0` = LimitPrune.  Returns the canonical
+// slot of the closest accepted hit (-1: none) with its distance in *t_out.
+#ifndef MTB_PREFETCH_KIDS
+#define MTB_PREFETCH_KIDS 0
+#endif
 template <bool DBG>
 __device__ __forceinline__ int TraceFast(const DeviceScene &sc, FastMem *m, const FastRay &r, float prune0, double *t_out, bool *ambiguous,
-                                         unsigned long long *cnt, const FastStack &fs) {
+                                         unsigned long long *cnt, const FastCtx &fc) {
   unsigned long long stack[kFastLocalStack];
   int sp = 0;
   int slot = -1;
   float prune = prune0;
-  m->lo2 = CUDART_INF;
-  m->t = 0.0;
-  m->e = 0.0;
+  FmStore(fc, m, kFmLo2, CUDART_INF);
   int node = 0;
+  unsigned visits = 0;  // (counting build only)
   for (;;) {
     while (node >= 0) {
+      if (DBG) visits++;
       const float4 *q = reinterpret_cast<const float4 *>(sc.gnodes + node);
-      const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
       const int2 kids = __ldg(reinterpret_cast<const int2 *>(q + 3));
+      const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+#if MTB_PREFETCH_KIDS
+      // the next node of the walk is one of the two children: start both fetches now, the box tests take ~100 cycles
+      if (kids.x >= 0) asm volatile("prefetch.global.L1 [%0];" : : "l"(sc.gnodes + kids.x));
+      if (kids.y >= 0) asm volatile("prefetch.global.L1 [%0];" : : "l"(sc.gnodes + kids.y));
+#endif
       Count<DBG>(cnt, kBvh, 2);
       float tl, tr;
       const bool hl = FastBox(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, prune, &tl);
       const bool hr = FastBox(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, prune, &tr);
       if (hl && hr) {
         const bool right_first = tr < tl;
-        FastPush(fs, stack, sp++, ((unsigned long long)__float_as_uint(right_first ? tl : tr) << 32) | (unsigned)(right_first ? kids.x : kids.y));
+        FastPush(fc, stack, sp++, ((unsigned long long)__float_as_uint(right_first ? tl : tr) << 32) | (unsigned)(right_first ? kids.x : kids.y));
         node = right_first ? kids.y : kids.x;
       } else if (hl) {
         node = kids.x;
@@ -773,7 +826,7 @@ __device__ __forceinline__ int TraceFast(const DeviceScene &sc, FastMem *m, cons
       } else {
         node = kFastExit;
         while (sp > 0) {
-          const unsigned long long top = FastPop(fs, stack, --sp);
+          const unsigned long long top = FastPop(fc, stack, --sp);
           if (__uint_as_float((unsigned)(top >> 32)) <= prune) {
             node = (int)(unsigned)top;
             break;
@@ -783,22 +836,35 @@ __device__ __forceinline__ int TraceFast(const DeviceScene &sc, FastMem *m, cons
     }
     if (node == kFastExit) break;
     const unsigned leaf = ~(unsigned)node;
-    MTB_FAST_BARRIER(m);
-    for (unsigned s = leaf >> 3, e = s + (leaf & 7u); s < e; s++) TestSlotFast<DBG>(sc.gslots + s, m, &slot, &prune, cnt);
-    MTB_FAST_BARRIER(m);
+    {
+      MTB_FAST_BARRIER(m);
+      Ray rr;  // FP64 origin and inverse direction: once per leaf visit
+      rr.o = FmLoad3(fc, m, kFmO);
+      rr.inv = FmLoad3(fc, m, kFmInv);
+      rr.sx = rr.inv.x < 0.0;
+      rr.sy = rr.inv.y < 0.0;
+      rr.sz = rr.inv.z < 0.0;
+      for (unsigned s = leaf >> 3, e = s + (leaf & 7u); s < e; s++) TestSlotFast<DBG>(sc.gslots + s, rr, fc, m, &slot, &prune, cnt);
+      MTB_FAST_BARRIER(m);
+    }
     node = kFastExit;
     while (sp > 0) {
-      const unsigned long long top = FastPop(fs, stack, --sp);
+      const unsigned long long top = FastPop(fc, stack, --sp);
       if (__uint_as_float((unsigned)(top >> 32)) <= prune) {
         node = (int)(unsigned)top;
         break;
       }
     }
   }
+  if (DBG) {
+    if (visits > 128u) Count<DBG>(cnt, kLongRays128), Count<DBG>(cnt, kLongVisits128, visits);
+    if (visits > 512u) Count<DBG>(cnt, kLongRays512), Count<DBG>(cnt, kLongVisits512, visits);
+  }
   bool amb = false;
   if (slot >= 0) {
-    const double t = m->t;
-    amb = m->lo2 <= t + m->e || DegeneratePassage(sc, slot, m);
+    MTB_FAST_BARRIER(m);
+    const double t = FmLoad(fc, m, kFmT);
+    amb = FmLoad(fc, m, kFmLo2) <= t + FmLoad(fc, m, kFmE) || DegeneratePassage(sc, slot, fc, m);
     *t_out = t;
   }
   *ambiguous = amb;
@@ -850,7 +916,7 @@ __device__ __noinline__ int TraceExactCold(const DeviceScene &sc, const D3 &o, c
 // for a plain closest-hit query.
 template <bool DBG>
 __device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D3 &d, double t_limit, double *t_out,
-                                     unsigned long long *cnt, const FastStack &fs) {
+                                     unsigned long long *cnt, const FastCtx &fc) {
   Count<DBG>(cnt, kRays);
   FastMem mem;
   bool fast;
@@ -865,9 +931,9 @@ __device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D
     const double ai_max = fmax(fmax(fabs(inv.x), fabs(inv.y)), fabs(inv.z));
     const double ai_min = fmin(fmin(fabs(inv.x), fabs(inv.y)), fabs(inv.z));
     fast = regular && sc.gnodes != nullptr && R > 0.0f && ao <= 8.0 * (double)R && ai_max <= 0x1p100 && ai_min >= 0x1p-100;
-    mem.o[0] = o.x, mem.o[1] = o.y, mem.o[2] = o.z;
-    mem.d[0] = d.x, mem.d[1] = d.y, mem.d[2] = d.z;
-    mem.inv[0] = inv.x, mem.inv[1] = inv.y, mem.inv[2] = inv.z;
+    FmStore(fc, &mem, kFmO + 0, o.x), FmStore(fc, &mem, kFmO + 1, o.y), FmStore(fc, &mem, kFmO + 2, o.z);
+    FmStore(fc, &mem, kFmD + 0, d.x), FmStore(fc, &mem, kFmD + 1, d.y), FmStore(fc, &mem, kFmD + 2, d.z);
+    FmStore(fc, &mem, kFmInv + 0, inv.x), FmStore(fc, &mem, kFmInv + 1, inv.y), FmStore(fc, &mem, kFmInv + 2, inv.z);
     fr.ix = (float)inv.x;
     fr.iy = (float)inv.y;
     fr.iz = (float)inv.z;
@@ -879,7 +945,7 @@ __device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D
   if (fast) {
     MTB_FAST_BARRIER(&mem);
     bool ambiguous;
-    const int slot = TraceFast<DBG>(sc, &mem, fr, prune0, t_out, &ambiguous, cnt, fs);
+    const int slot = TraceFast<DBG>(sc, &mem, fr, prune0, t_out, &ambiguous, cnt, fc);
     if (!ambiguous) {
       Count<DBG>(cnt, kFast);
       return slot;
@@ -887,7 +953,7 @@ __device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D
     Count<DBG>(cnt, kFallback);
   }
   MTB_FAST_BARRIER(&mem);
-  return TraceExactCold<DBG>(sc, Mk(mem.o[0], mem.o[1], mem.o[2]), Mk(mem.d[0], mem.d[1], mem.d[2]), t_out, cnt);
+  return TraceExactCold<DBG>(sc, FmLoad3(fc, &mem, kFmO), FmLoad3(fc, &mem, kFmD), t_out, cnt);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -35,6 +35,7 @@ struct DeviceScene {
 // Work counters, one slot per field of mtb_stats' integer part (same order).
 enum Counter {
   kRays = 0, kPrimary, kShadow, kReflect, kRefract, kSlab, kVisit, kTriAabb, kMt, kHit, kShade, kBvh, kLiteral, kFast, kFallback,
+  kLongRays128, kLongVisits128, kLongRays512, kLongVisits512,
   kNumCounters
 };
 

@@ -48,21 +48,24 @@ __device__ __forceinline__ void St3(double *p, const D3 &v) {
 // post-order so that colour sums associate identically.  Every loop iteration issues exactly one
 // OctTree::IntersectRay-equivalent query (a primary / reflection / refraction ray or one shadow segment),
 // so the lanes of a warp reconverge at the single Trace call site.  One block = one 8x8 pixel tile (a warp =
-// 8x4 pixels); the finished tile leaves the block as 24 aligned 8-byte stores (the frame buffer may be the
-// peer-mapped frame of another GPU, api.cu).
+// 8x4 pixels); a finished warp writes its 4 rows as 12 aligned 8-byte stores (the frame buffer may be the
+// peer-mapped frame of another GPU, api.cu) and exits without waiting for the other warp.
 //
 // Retired launch forms of round 1, all bit-identical and all measured slower on B200:
 // persistent lane refill, block-level ray packing, forced warp re-convergence, suspendable walks.
 // ---------------------------------------------------------------------------------------------------
+#ifndef MTB_BLOCK_EPILOGUE
+#define MTB_BLOCK_EPILOGUE 0
+#endif
 #ifndef MTB_MEGA_MIN_BLOCKS
-#define MTB_MEGA_MIN_BLOCKS 16  // measured on B200 (C3, round 1): 12 -> 9.9 ms, 16 -> 9.3, 20 -> 10.5
+#define MTB_MEGA_MIN_BLOCKS 14  // blocks per SM (72 registers); measured on one B200, C3, round 2: 14 -> 9.13 ms, 16 -> 9.38, 20 -> 10.3
 #endif
 
 constexpr unsigned kShadowMode = 1u, kInObject = 2u, kInShadow = 4u, kThrough = 8u;
 
 template <bool DBG>
 __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega(DeviceScene sc, RenderParams rp) {
-  MTB_DECLARE_FAST_STACK(kBlockThreads);
+  MTB_DECLARE_FAST_CTX(kBlockThreads);
   __shared__ __align__(8) unsigned char s_rgb[kTile * kTile * 3];
   // repair launch of a wavefront frame whose queues did not overflow: nothing to do
   if (rp.run_if != nullptr && __ldg(rp.run_if) == 0u) return;
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
           td = Ld3(st.m_d);
         }
         MTB_STATE_BARRIER();
-        slot = Trace<DBG>(sc, to, td, limit, &t, cnt, fstack);
+        slot = Trace<DBG>(sc, to, td, limit, &t, cnt, fctx);
         MTB_STATE_BARRIER();
       }
       n_rays++;
@@ -354,16 +357,25 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
     }
   }
 
-  // ---- the tile leaves the block: rows of 24 bytes as aligned 8-byte stores when the layout allows it ----
-  __syncthreads();
+  // ---- the warp's half of the tile (4 rows of 24 bytes) leaves as aligned 8-byte stores when the layout allows it.
+  // Warp-level on purpose: with a block-wide barrier here the warp that finishes first kept its slot on the SM until
+  // the other one was done (ncu: 9 % of all warp samples sat in that barrier); now it exits and a warp of the next
+  // tile takes its registers. ----
+#if MTB_BLOCK_EPILOGUE
+  __syncthreads();  // (A/B of the warp-level epilogue)
+#else
+  __syncwarp();
+#endif
   {
-    const int px0 = (tile_id % rp.tiles_x) * kTile, py0 = strip * kTile;
+    const int px0 = (tile_id % rp.tiles_x) * kTile, py0 = strip * kTile + (int)(threadIdx.x >> 5) * 4;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned char *half = s_rgb + (threadIdx.x >> 5) * (4 * kTile * 3);
     const bool whole_rows = px0 + kTile <= rp.chunk_w && (rp.chunk_w & 7) == 0 && (reinterpret_cast<uintptr_t>(rp.rgb) & 7u) == 0u;
     if (whole_rows) {
-      if (threadIdx.x < 24u) {
-        const int row = (int)threadIdx.x / 3, seg = (int)threadIdx.x % 3;
+      if (lane < 12u) {
+        const int row = (int)lane / 3, seg = (int)lane % 3;
         if (py0 + row < rp.chunk_h) {
-          const uint2 v = *reinterpret_cast<const uint2 *>(s_rgb + row * 24 + seg * 8);
+          const uint2 v = *reinterpret_cast<const uint2 *>(half + row * 24 + seg * 8);
           *reinterpret_cast<uint2 *>(rp.rgb + ((size_t)(py0 + row) * rp.chunk_w + px0) * 3 + seg * 8) = v;
         }
       }
@@ -399,7 +411,7 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
 // Batched OctTree::IntersectRay (octtree.cc:26-40), one ray per thread.
 template <bool DBG>
 __global__ void __launch_bounds__(128) IntersectKernel(DeviceScene sc, IntersectParams ip) {
-  MTB_DECLARE_FAST_STACK(128);
+  MTB_DECLARE_FAST_CTX(128);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long cnt_store[DBG ? kNumCounters : 1];
   unsigned long long *cnt = cnt_store;
@@ -409,7 +421,7 @@ __global__ void __launch_bounds__(128) IntersectKernel(DeviceScene sc, Intersect
   if (i < ip.n) {
     const D3 o = Load3(ip.origins + i * 3), d = Load3(ip.dirs + i * 3);
     double t = 0.0;
-    const int slot = Trace<DBG>(sc, o, d, CUDART_INF, &t, cnt, fstack);
+    const int slot = Trace<DBG>(sc, o, d, CUDART_INF, &t, cnt, fctx);
     if (slot < 0) {
       // miss contract (include/mythtracer_b200.h): tri_index -1, t and point NaN - the scratch buffers are reused
       // between queries, so a miss must not leave an earlier query's values behind

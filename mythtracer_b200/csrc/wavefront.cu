@@ -119,7 +119,7 @@ __global__ void WfBegin(WfBuffers wf, int slots) {
 
 template <bool DBG>
 __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTrace(DeviceScene sc, RenderParams rp, WfBuffers wf, int level, int lanes) {
-  MTB_DECLARE_FAST_STACK(kWfBlock);
+  MTB_DECLARE_FAST_CTX(kWfBlock);
   if (wf.ctrl[0] != 0u) return;  // an earlier level overflowed: the frame is rendered by the repair launch
   const LevelRange lr = WfLevel(wf, level);
   const int n = lr.n < wf.queue_cap ? lr.n : wf.queue_cap, act_base = lr.base;
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTrace(DeviceSce
       D3 color = Mk(0.0, 0.0, 0.0);
       if (live) {
         double t = 0.0;
-        const int slot = Trace<DBG>(sc, o, d, CUDART_INF, &t, cnt, fstack);
+        const int slot = Trace<DBG>(sc, o, d, CUDART_INF, &t, cnt, fctx);
         traced++;
         if (rp.n_rays != nullptr) atomicAdd(rp.n_rays + pixel, 1u);
         WfChargeTile(rp, pixel, 1u);
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfTrace(DeviceSce
 // ---------------------------------------------------------------------------------------------------
 template <bool DBG>
 __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfShadow(DeviceScene sc, RenderParams rp, WfBuffers wf, int level, int lanes) {
-  MTB_DECLARE_FAST_STACK(kWfBlock);
+  MTB_DECLARE_FAST_CTX(kWfBlock);
   if (wf.ctrl[0] != 0u) return;
   const LevelRange lr = WfLevel(wf, level);
   const int n = lr.n < wf.queue_cap ? lr.n : wf.queue_cap;
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kWfBlock, MTB_WF_MIN_BLOCKS) WfShadow(DeviceSc
       const double light_distance = Dist(seg_start, lpos);
       double t = 0.0;
       Count<DBG>(cnt, kShadow);
-      const int slot = Trace<DBG>(sc, to, ldir, light_distance, &t, cnt, fstack);
+      const int slot = Trace<DBG>(sc, to, ldir, light_distance, &t, cnt, fctx);
       segments++;
       if (slot < 0) break;
       if (t > light_distance) break;

@@ -114,6 +114,7 @@ typedef struct {
   int64_t root_list, biggest_list, interior_triangles;
   double aabb_min[3], aabb_max[3]; /* OctTree::GetAABB (octtree.cc:42-44) */
   int64_t device_bytes;
+  int64_t n_scene_refs; /* leaf positions of the scene BVH: >= n_triangles (large triangles are referenced from several leaves) */
 } mtb_scene_summary;
 
 #define MTB_FLAG_COUNT_WORK 1u   /* fill the n_* work counters (counting kernels) */

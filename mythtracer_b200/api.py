@@ -63,7 +63,7 @@ STATS_DTYPE = np.dtype([(n, "u8") for n in ("rays", "primary", "shadow", "reflec
 SUMMARY_DTYPE = np.dtype([("n_triangles", "i8"), ("n_nodes", "i8"), ("n_bvh_nodes", "i8"), ("tree_depth", "i4"),
                           ("n_materials", "i4"), ("n_textures", "i4"), ("n_lights", "i4"), ("root_list", "i8"),
                           ("biggest_list", "i8"), ("interior_triangles", "i8"), ("aabb_min", "f8", (3,)),
-                          ("aabb_max", "f8", (3,)), ("device_bytes", "i8")], align=True)
+                          ("aabb_max", "f8", (3,)), ("device_bytes", "i8"), ("n_scene_refs", "i8")], align=True)
 BVH2_DTYPE = np.dtype([("lbox", "f4", (6,)), ("rbox", "f4", (6,)), ("left", "i4"), ("right", "i4"), ("pad_", "i4", (2,))])
 assert BVH2_DTYPE.itemsize == 64
 assert TRI_DTYPE.itemsize == 224 and MTL_DTYPE.itemsize == 136 and DEBUG_DTYPE.itemsize == 32
@@ -415,7 +415,7 @@ class MythTracer:
         depth = ctypes.c_int32(0)
         self._check(self._lib.mtb_scene_bvh(self._ctx, ctypes.byref(n), ctypes.byref(depth), None, None), "mtb_scene_bvh")
         nodes = np.zeros(n.value, BVH2_DTYPE)
-        order = np.zeros(self.scene_info()["n_triangles"] if n.value else 0, np.int32)
+        order = np.zeros(self.scene_info()["n_scene_refs"] if n.value else 0, np.int32)
         self._check(self._lib.mtb_scene_bvh(self._ctx, None, None, _ptr(nodes), _ptr(order)), "mtb_scene_bvh")
         return nodes, depth.value, order
 

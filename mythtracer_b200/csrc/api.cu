@@ -1042,6 +1042,7 @@ int mtb_scene_info(const mtb_context *ctx, mtb_scene_summary *out) {
     out->aabb_max[a] = ctx->flat.aabb[3 + a];
   }
   out->device_bytes = ctx->device_bytes;
+  out->n_scene_refs = (int64_t)ctx->flat.gslots.size();
   return MTB_OK;
 }
 

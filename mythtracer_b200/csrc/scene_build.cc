@@ -256,6 +256,100 @@ struct BvhBuilder {
   }
 };
 
+// Spatial pre-splitting of large triangles for the scene BVH ("early split clipping").  A long thin triangle that
+// crosses the room diagonally has an AABB the size of the room: every ray passes its box, the reference's exact
+// pre-test passes too, and the triangle has to be given its exact Moller-Trumbore evaluation by almost every ray
+// (round 1, C4: 2835 evaluations per ray).  Here such a triangle enters the scene BVH as several REFERENCES, each with
+// the bounds of the piece of the triangle inside one cell of a recursive midpoint split of its box; a ray then reaches
+// the triangle only through the pieces it actually passes.  What is evaluated at a leaf is unchanged - the whole
+// triangle, by the reference's exact pre-test and Moller-Trumbore - so the set of accepted hits can only shrink by
+// hits whose computed position lies outside every padded piece box, i.e. off the triangle by more than the padding:
+// that needs a ray parallel to the triangle's plane to within rounding (|det| a few ulps above the reference's 1e-8
+// threshold), the extension of stated edge case (b) of DESIGN.md section 4 to split triangles.
+struct Poly {
+  int n = 0;
+  double v[10][3];
+};
+
+// Sutherland-Hodgman against the half space x[axis] <= p (keep_low) or >= p; points on the plane get x[axis] = p.
+inline void ClipPoly(const Poly &in, int axis, double p, bool keep_low, Poly *out) {
+  out->n = 0;
+  for (int i = 0; i < in.n; i++) {
+    const double *a = in.v[i], *b = in.v[(i + 1) % in.n];
+    const bool ina = keep_low ? a[axis] <= p : a[axis] >= p;
+    const bool inb = keep_low ? b[axis] <= p : b[axis] >= p;
+    if (ina && out->n < 10) {
+      for (int k = 0; k < 3; k++) out->v[out->n][k] = a[k];
+      out->n++;
+    }
+    if (ina != inb && out->n < 10) {
+      const double t = (p - a[axis]) / (b[axis] - a[axis]);
+      for (int k = 0; k < 3; k++) out->v[out->n][k] = a[k] + t * (b[k] - a[k]);
+      out->v[out->n][axis] = p;
+      out->n++;
+    }
+  }
+}
+
+// References of triangle `tri` (box `tb`) with pieces no longer than `max_extent` along any axis, appended to the
+// lists.  Every piece box is grown by `guard` (the clipping arithmetic rounds) and clipped to the triangle's box.
+inline void SplitTriangle(const double vert[9], const Box3 &tb, int32_t tri, double max_extent, double guard,
+                          std::vector<Box3> *ref_box, std::vector<int32_t> *ref_tri) {
+  struct Item {
+    Poly poly;
+    Box3 cell;
+    int depth;
+  };
+  std::vector<Item> stack(1);
+  stack[0].poly.n = 3;
+  for (int i = 0; i < 3; i++) {
+    for (int k = 0; k < 3; k++) stack[0].poly.v[i][k] = vert[i * 3 + k];
+  }
+  stack[0].cell = tb;
+  stack[0].depth = 0;
+  while (!stack.empty()) {
+    Item it = stack.back();
+    stack.pop_back();
+    // bounds of the piece, inside its cell
+    Box3 pb;
+    for (int a = 0; a < 3; a++) {
+      pb.lo[a] = INFINITY;
+      pb.hi[a] = -INFINITY;
+      for (int i = 0; i < it.poly.n; i++) {
+        pb.lo[a] = std::min(pb.lo[a], it.poly.v[i][a]);
+        pb.hi[a] = std::max(pb.hi[a], it.poly.v[i][a]);
+      }
+      pb.lo[a] = std::max(pb.lo[a], it.cell.lo[a]);
+      pb.hi[a] = std::min(pb.hi[a], it.cell.hi[a]);
+    }
+    int axis = 0;
+    for (int a = 1; a < 3; a++) {
+      if (pb.hi[a] - pb.lo[a] > pb.hi[axis] - pb.lo[axis]) axis = a;
+    }
+    const double ext = pb.hi[axis] - pb.lo[axis];
+    if (!(ext > max_extent) || it.depth >= 24) {
+      Box3 out;
+      for (int a = 0; a < 3; a++) {
+        out.lo[a] = std::max(pb.lo[a] - guard, tb.lo[a]);
+        out.hi[a] = std::min(pb.hi[a] + guard, tb.hi[a]);
+      }
+      ref_box->push_back(out);
+      ref_tri->push_back(tri);
+      continue;
+    }
+    const double mid = pb.lo[axis] + 0.5 * ext;
+    for (int side = 0; side < 2; side++) {
+      Item child;
+      ClipPoly(it.poly, axis, mid, side == 0, &child.poly);
+      if (child.poly.n < 3) continue;
+      child.cell = pb;
+      (side == 0 ? child.cell.hi[axis] : child.cell.lo[axis]) = mid;
+      child.depth = it.depth + 1;
+      stack.push_back(child);
+    }
+  }
+}
+
 // Scene BVH (Bvh2Node, scene_build.h) over ALL triangles: the acceleration structure of the certified fast
 // traversal.  ids ends up in leaf order = the order of the `gslots` copies.  The top of the tree is split by the
 // calling thread; every range of at most `grain` triangles below it is an independent job for a pool of threads
@@ -541,32 +635,76 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
   out->gslots.clear();
   out->gbvh_depth = 0;
   if (use_scene_bvh && n > 0) {
-    SceneBvhBuilder sb{tri_box, {}, 0, 0x1p-16 * out->max_abs_coord * 1.000001, {}};
-    sb.ids.resize((size_t)n);
+    // references: one per triangle, several for triangles much larger than the scene's grain (see SplitTriangle)
+    std::vector<Box3> ref_box;
+    std::vector<int32_t> ref_tri;
+    {
+      double scene_ext = 0.0;
+      for (int a = 0; a < 3; a++) scene_ext = std::max(scene_ext, out->aabb[3 + a] - out->aabb[a]);
+      const char *env = getenv("MTB_SPLIT_DIV");  // development knob: pieces of at most scene extent / div (0: no splitting)
+      const double div = env != nullptr ? atof(env) : 64.0;  // measured on C4 (B200): 16 -> 20.8 ms, 32 -> 12.1, 64 -> 7.6 (no splitting: 438)
+      double max_extent = div > 0.0 ? scene_ext / div : INFINITY;
+      const double guard = 1e-9 * std::max(out->max_abs_coord, 1e-30);
+      for (int attempt = 0; attempt < 8; attempt++) {
+        ref_box.clear();
+        ref_tri.clear();
+        ref_box.reserve((size_t)n + (size_t)n / 4);
+        ref_tri.reserve((size_t)n + (size_t)n / 4);
+        for (int64_t i = 0; i < n; i++) {
+          const Box3 &tb = tri_box[(size_t)i];
+          const double dx = tb.hi[0] - tb.lo[0], dy = tb.hi[1] - tb.lo[1], dz = tb.hi[2] - tb.lo[2];
+          const double ext = std::max(std::max(dx, dy), dz);
+          // Only boxes that are mostly empty are worth several references: a long triangle that runs diagonally
+          // through its box (area far below the box's cross sections).  A big axis-aligned wall triangle fills half
+          // of its flat box; splitting those only deepens the tree (measured on C3: +4 % node visits, no gain).
+          bool wasteful = false;
+          if (ext > max_extent) {
+            const double *v = tris[i].vertex;
+            const double e1[3] = {v[3] - v[0], v[4] - v[1], v[5] - v[2]}, e2[3] = {v[6] - v[0], v[7] - v[1], v[8] - v[2]};
+            const double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+            const double tri_area = 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
+            wasteful = tri_area < 0.125 * (dx * dy + dy * dz + dz * dx);
+          }
+          if (!wasteful) {
+            ref_box.push_back(tb);
+            ref_tri.push_back((int32_t)i);
+          } else {
+            SplitTriangle(tris[i].vertex, tb, (int32_t)i, max_extent, guard, &ref_box, &ref_tri);
+          }
+        }
+        // budget: at most half as many extra references as there are triangles (+ 4096 for small scenes with big walls)
+        if (ref_box.size() <= (size_t)n + (size_t)n / 2 + 4096 && ref_box.size() < 0x0fffffffu) break;
+        max_extent *= 2.0;
+      }
+    }
+    const int64_t n_refs = (int64_t)ref_box.size();
+    out->n_split_refs = n_refs - n;
+    SceneBvhBuilder sb{ref_box, {}, 0, 0x1p-16 * out->max_abs_coord * 1.000001, {}};
+    sb.ids.resize((size_t)n_refs);
     std::iota(sb.ids.begin(), sb.ids.end(), 0);
     Box3 whole;
-    if (n <= kSceneBvhLeafSize) {
+    if (n_refs <= kSceneBvhLeafSize) {
       // a single leaf: the root holds it as its left child and an empty leaf on the right
       double clo[3], chi[3];
-      RangeBounds(tri_box, sb.ids, 0, (int32_t)n, &whole, clo, chi);
+      RangeBounds(ref_box, sb.ids, 0, (int32_t)n_refs, &whole, clo, chi);
       Bvh2Node root;
       memset(&root, 0, sizeof(root));
       for (int a = 0; a < 3; a++) {
         root.lbox[a] = root.rbox[a] = RoundDown(whole.lo[a] - sb.pad);
         root.lbox[3 + a] = root.rbox[3 + a] = RoundUp(whole.hi[a] + sb.pad);
       }
-      root.left = ~(int32_t)(uint32_t)n;  // first_gslot 0, count n
+      root.left = ~(int32_t)(uint32_t)n_refs;  // first_gslot 0, count n_refs
       root.right = ~0;                    // count 0
       out->gnodes.push_back(root);
     } else {
-      sb.Run(&out->gnodes, (int32_t)n);
+      sb.Run(&out->gnodes, (int32_t)n_refs);
     }
     out->gbvh_depth = sb.max_depth;
     if (sb.max_depth > kSceneBvhMaxDepth) {
       out->gnodes.clear();
     } else {
-      out->gslots.resize((size_t)n);
-      for (int64_t i = 0; i < n; i++) out->gslots[(size_t)i] = out->slots[(size_t)slot_of[(size_t)sb.ids[(size_t)i]]];
+      out->gslots.resize((size_t)n_refs);
+      for (int64_t i = 0; i < n_refs; i++) out->gslots[(size_t)i] = out->slots[(size_t)slot_of[(size_t)ref_tri[(size_t)sb.ids[(size_t)i]]]];
     }
   }
   if (timing && !out->gnodes.empty()) {

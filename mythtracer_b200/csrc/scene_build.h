@@ -81,7 +81,9 @@ struct FlatScene {
   std::vector<int32_t> list_order;  // list_order[list_first + k] = slot of the k-th entry in reference order
   std::vector<int32_t> slot_node;   // octree node whose own list holds the slot (TraceFast's degenerate-passage check)
   std::vector<Bvh2Node> gnodes;     // scene BVH, node 0 = root (empty: no fast traversal)
-  std::vector<SlotRec> gslots;      // copies of `slots` in scene-BVH leaf order
+  std::vector<SlotRec> gslots;      // copies of `slots` in scene-BVH leaf order: one per REFERENCE (a triangle much larger
+                                    // than the scene's grain is referenced from several leaves, see SplitTriangle)
+  int64_t n_split_refs = 0;         // gslots.size() - slots.size()
   int32_t gbvh_depth = 0;
   int32_t depth = 0;
   int64_t root_list = 0, biggest_list = 0, interior = 0;

@@ -186,63 +186,86 @@ def test_octree_depth_limit_and_degenerate_inputs(product_lib, oracle_mod):
 
 
 def test_scene_bvh_is_a_conservative_partition(product_lib, scene_dir):
-    """The certified fast traversal relies on two properties of the scene BVH: every triangle
-    sits in exactly one leaf, and every child box (FP32, padded and rounded outwards) contains the exact FP64 boxes of all
-    triangles below it.  Checked on a generated scene, on scenes smaller than a leaf and on an empty scene."""
+    """The certified fast traversal relies on these properties of the scene BVH: every triangle
+    is referenced from at least one leaf; the stored box of a child (FP32, padded and rounded outwards) contains
+    everything below it - for a triangle with ONE reference its exact FP64 box, for a triangle that was split into
+    several references (SplitTriangle, scene_build.cc) the boxes of its references together cover the triangle.
+    Checked on generated scenes (C1: big wall triangles are split; the C4 stress scene: room-spanning sticks), on
+    scenes smaller than a leaf and on an empty scene."""
     from mythtracer_b200 import MythTracer
     from mythtracer_b200.api import MTL_DTYPE, TRI_DTYPE
     from tests import scenes
-    files, cfg = scenes.config_scene("C1", scene_dir)
-    mt = MythTracer(host_only=True)
-    assert mt.LoadObj(files.obj_path)
-    tris, _ = mt.scene_arrays()
+    import sys
+    sys.setrecursionlimit(10000)
 
-    def check(mt, tris):
+    def check(mt, tris, expect_splits=None):
         nodes, depth, order = mt.scene_bvh()
         n = len(tris)
-        assert sorted(order.tolist()) == list(range(n)), "leaf order must be a permutation of the triangles"
-        v = tris["vertex"].reshape(n, 3, 3)
-        lo, hi = v.min(axis=1), v.max(axis=1)
-        seen = np.zeros(n, int)
-        max_depth = 0
-
-        def walk(ref, d):
-            """returns (lo, hi) of everything below `ref`"""
-            nonlocal max_depth
-            max_depth = max(max_depth, d)
-            if ref < 0:
-                x = (~ref) & 0xFFFFFFFF
-                first, count = x >> 3, x & 7
-                ids = order[first:first + count]
-                seen[ids] += 1
-                if count == 0:
-                    return np.full(3, np.inf), np.full(3, -np.inf)
-                return lo[ids].min(axis=0), hi[ids].max(axis=0)
-            nd = nodes[ref]
-            out_lo, out_hi = np.full(3, np.inf), np.full(3, -np.inf)
-            for box, child in ((nd["lbox"], int(nd["left"])), (nd["rbox"], int(nd["right"]))):
-                c_lo, c_hi = walk(child, d + 1)
-                assert np.all(box[:3].astype(np.float64) <= c_lo) and np.all(box[3:].astype(np.float64) >= c_hi), "child box must contain its triangles"
-                out_lo, out_hi = np.minimum(out_lo, c_lo), np.maximum(out_hi, c_hi)
-            return out_lo, out_hi
-
         if n == 0:
             assert len(nodes) == 0
             return
-        import sys
-        sys.setrecursionlimit(10000)
-        walk(0, 0)
-        assert np.all(seen == 1), "every triangle in exactly one leaf"
-        assert max_depth <= depth + 1
+        refs = np.bincount(order, minlength=n)
+        assert len(refs) == n and np.all(refs >= 1), "every triangle must be referenced from a leaf"
+        assert mt.scene_info()["n_scene_refs"] == len(order)
+        if expect_splits is not None:
+            assert (refs.max() > 1) == expect_splits
+        v = tris["vertex"].reshape(n, 3, 3)
+        lo, hi = v.min(axis=1), v.max(axis=1)
+        leaf_boxes = {}  # triangle -> list of the (lo, hi) boxes of the leaves that reference it
+        max_depth = 0
 
-    check(mt, tris)
+        def walk(ref, box, d):
+            """`box` = the box the parent stores for this child; returns nothing, asserts containment"""
+            nonlocal max_depth
+            max_depth = max(max_depth, d)
+            b_lo, b_hi = box[:3].astype(np.float64), box[3:].astype(np.float64)
+            if ref < 0:
+                x = (~ref) & 0xFFFFFFFF
+                first, count = x >> 3, x & 7
+                for t in order[first:first + count]:
+                    if refs[t] == 1:
+                        assert np.all(b_lo <= lo[t]) and np.all(b_hi >= hi[t]), "leaf box must contain its triangle"
+                    else:
+                        assert np.all(b_lo <= hi[t]) and np.all(b_hi >= lo[t]), "a reference's box must touch its triangle"
+                        leaf_boxes.setdefault(int(t), []).append((b_lo, b_hi))
+                return
+            nd = nodes[ref]
+            for cbox, child in ((nd["lbox"], int(nd["left"])), (nd["rbox"], int(nd["right"]))):
+                if child >= 0 or ((~child) & 7) > 0:
+                    assert np.all(box[:3] <= cbox[:3]) and np.all(box[3:] >= cbox[3:]), "a child box must lie inside its parent's"
+                walk(child, cbox, d + 1)
+
+        root = nodes[0]
+        whole = np.concatenate([np.minimum(root["lbox"][:3], root["rbox"][:3]), np.maximum(root["lbox"][3:], root["rbox"][3:])])
+        walk(0, whole, 0)
+        assert max_depth <= depth + 1
+        # split triangles: points all over the triangle must lie in one of its references' boxes
+        rng = np.random.default_rng(3)
+        w = rng.dirichlet(np.ones(3), 64)
+        w = np.concatenate([w, np.eye(3), [[0.5, 0.5, 0.0], [0.0, 0.5, 0.5], [0.5, 0.0, 0.5]]])
+        for t, boxes in list(leaf_boxes.items())[:400]:
+            pts = w @ v[t]
+            b_lo = np.array([b[0] for b in boxes])
+            b_hi = np.array([b[1] for b in boxes])
+            inside = np.all((pts[:, None, :] >= b_lo[None]) & (pts[:, None, :] <= b_hi[None]), axis=2).any(axis=1)
+            assert inside.all(), "the references of a split triangle must cover it"
+
+    files, cfg = scenes.config_scene("C1", scene_dir)
+    mt = MythTracer(host_only=True)
+    assert mt.LoadObj(files.obj_path)
+    tris, mtls = mt.scene_arrays()
+    check(mt, tris, expect_splits=True)
     for n in (1, 2, 3, 5):
         small = MythTracer(host_only=True)
-        small.upload(tris[:n], np.zeros(0, MTL_DTYPE) if False else mt.scene_arrays()[1])
+        small.upload(tris[:n], mtls)
         check(small, tris[:n])
     empty = MythTracer(host_only=True)
     empty.upload(np.zeros(0, TRI_DTYPE), np.zeros(0, MTL_DTYPE))
     check(empty, np.zeros(0, TRI_DTYPE))
+    files4, _ = scenes.config_scene("C4", scene_dir, 0.02)
+    mt4 = MythTracer(host_only=True)
+    assert mt4.LoadObj(files4.obj_path)
+    check(mt4, mt4.scene_arrays()[0], expect_splits=True)
 
 
 def _png_bytes(img, color_type, depth=8, filters=(0, 1, 2, 3, 4), palette=None, level=6, width=None, fixed=False):

@@ -326,6 +326,7 @@ def time_other_workloads(names, steps):
             out[name] = {"triangles": files.n_triangles, "width": W, "height": H, "lights": cfg["n_lights"], "max_depth": cfg["depth"],
                          "ms_per_frame": ms, "mrays_s": rays / ms / 1e3, "rays_per_frame": rays, "pipeline": mt.pipeline_in_use()[0],
                          "steps": steps, "scene_generate_s": gen_s, "scene_load_s": load_s, "first_frame_s": first_frame_s,
+                         "time_to_first_frame_s": load_s + first_frame_s, "load_stages_ms": mt.load_timing(),
                          "frame_sha256": hashlib.sha256(d_frame.cpu().numpy().tobytes()).hexdigest()}
             mt.close()
             del d_frame
@@ -379,6 +380,7 @@ def _run_ours(args):
     if not mt.LoadObj(files.obj_path):
         raise SystemExit("LoadObj failed: " + mt.last_error())
     load_s = time.time() - t0
+    load_stages = mt.load_timing()
     mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]
     mt.push_lights()
     mt.set_partition(rank, world)
@@ -625,7 +627,7 @@ def _run_ours(args):
         "dtype": "f64", "data": "synthetic",
         "config": config_dict(files, cfg, world * inproc, {"launch": launch, "gather": gather,
                                                            "pipeline": pipeline_used, "pipeline_choice": args.pipeline, "autotune_ms": {"mega": tune_mega_ms, "wavefront": tune_wf_ms},
-                                                           "rays_per_frame": rays_per_frame, "scene_load_s": load_s,
+                                                           "rays_per_frame": rays_per_frame, "scene_load_s": load_s, "load_stages_ms": load_stages,
                                                            "octree_nodes": info["n_nodes"], "tree_depth": info["tree_depth"],
                                                            "device_scene_bytes": info["device_bytes"], "commit": git_head(),
                                                            "other_workloads": others}),

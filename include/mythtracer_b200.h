@@ -135,6 +135,12 @@ typedef struct {
 #define MTB_FLAG_RESUME 1024u     /* was: megakernel, suspendable walks */
 #define MTB_FLAG_WARP_SYNC 512u   /* was: megakernel, forced warp re-convergence in front of every traversal */
 #define MTB_FLAG_PERSISTENT 64u   /* was: megakernel, persistent warps drawing pixels from a counter */
+/* Scene BVH built ON THE DEVICE (PLOC over the reference boxes, csrc/device_build.cu) instead of
+ * on the host threads (binned SAH).  Measured on B200, C3: the device build takes ~20-50 ms against 165 ms on 24 host
+ * cores (time to first frame 0.31 s vs 0.39 s), but its trees cost 12 % more box tests per ray (frame 10.2 vs 9.17 ms):
+ * the right choice for a scene that is rendered a few times, the wrong one for an animation - hence opt-in.  The
+ * rendered bytes are the same either way. */
+#define MTB_FLAG_DEVICE_BVH 4096u
 #define MTB_FLAG_NO_TILE_ORDER 32u /* megakernel: always launch tiles in scanline order (A/B of the cost-aware launch order) */
 
 /* ---- life cycle -------------------------------------------------------------------------------- */
@@ -177,9 +183,15 @@ int mtb_scene_triangle_nodes(const mtb_context *ctx, double *node_box, int32_t *
 /* The scene BVH of the certified fast traversal, for inspection: node count, depth, the
  * nodes themselves (64 bytes each: float lbox[6], rbox[6]; int32 left, right, pad[2]; a child >= 0 is a node
  * index, < 0 a leaf with ~child = (first << 3) | count over leaf_order) and, per leaf position, the insertion
- * index of the triangle stored there (n_triangles entries).  Any pointer may be NULL.  n_nodes == 0: the scene
+ * index of the triangle stored there (mtb_scene_summary::n_scene_refs entries).  Any pointer may be NULL.  n_nodes == 0: the scene
  * has no fast traversal (empty scene, MTB_FLAG_NO_LIST_BVH, or a tree deeper than the traversal stack). */
 int mtb_scene_bvh(const mtb_context *ctx, int64_t *n_nodes, int32_t *depth, void *nodes, int32_t *leaf_order);
+/* Stages of the last scene load, milliseconds (time to the first frame): out_ms[0] OBJ + MTL
+ * parse, [1] octree (AttemptSplit), [2] flatten + list BVHs, [3] scene BVH on the host (or just its references when
+ * it is built on the device), [4] scene BVH on the device incl. the leaf-record gather, [5] upload, [6] 1.0 when
+ * the scene BVH was built on the device, [7] the host tree build itself (it runs on its own thread while [1] and [2]
+ * proceed; [3] is only what was left to wait for, plus the leaf-record gather). */
+int mtb_load_timing(const mtb_context *ctx, double out_ms[8]);
 int mtb_set_flags(mtb_context *ctx, uint32_t flags);
 /* Tile partitioning across processes -- the in-process form of the reference's master/worker contract
  * (main_net_master.cc:195-221: the frame is cut into tiles, every worker holds the whole scene and renders

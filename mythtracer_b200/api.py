@@ -42,6 +42,7 @@ MTB_FLAG_PACKING = 256
 MTB_FLAG_WARP_SYNC = 512
 MTB_FLAG_RESUME = 1024
 MTB_FLAG_HYBRID = 2048
+MTB_FLAG_DEVICE_BVH = 4096
 MAX_RECURSION_LEVEL = 5  # reference mythtracer.h:11 (a run-time argument here)
 FRAME_HANDLE_BYTES = 64
 
@@ -74,7 +75,7 @@ EXPORTED_SYMBOLS = [
     "mtb_set_lights", "mtb_scene_info", "mtb_scene_read", "mtb_scene_material_name", "mtb_scene_texture_name", "mtb_scene_texture", "mtb_load_mtl",
     "mtb_scene_triangle_nodes", "mtb_scene_bvh", "mtb_set_flags", "mtb_set_partition", "mtb_render_chunk",
     "mtb_render_chunk_device", "mtb_render_chunk_async", "mtb_wait", "mtb_host_alloc", "mtb_host_free", "mtb_read_counters", "mtb_launch_count", "mtb_pipeline_in_use", "mtb_intersect_rays", "mtb_camera_sensor", "mtb_version",
-    "mtb_frame_create", "mtb_frame_open", "mtb_frame_release", "mtb_frame_read",
+    "mtb_frame_create", "mtb_frame_open", "mtb_frame_release", "mtb_frame_read", "mtb_load_timing",
 ]
 
 
@@ -133,6 +134,7 @@ def load_library():
     lib.mtb_intersect_rays.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp]
     lib.mtb_camera_sensor.argtypes = [vp, i32, i32, vp]
     lib.mtb_wait.argtypes = [vp]
+    lib.mtb_load_timing.argtypes = [vp, vp]
     lib.mtb_frame_create.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp), vp]
     lib.mtb_frame_open.argtypes = [vp, vp, ctypes.POINTER(vp)]
     lib.mtb_frame_release.argtypes = [vp, vp]
@@ -466,6 +468,14 @@ class MythTracer:
 
     def push_lights(self):
         self._push_lights()
+
+    def load_timing(self) -> dict:
+        """Stages of the last scene load in milliseconds (mtb_load_timing)."""
+        out = np.zeros(8)
+        self._check(self._lib.mtb_load_timing(self._ctx, _ptr(out)), "mtb_load_timing")
+        return {"parse_ms": out[0], "octree_ms": out[1], "flatten_ms": out[2], "scene_bvh_host_ms": out[3],
+                "scene_bvh_device_ms": out[4], "upload_ms": out[5], "scene_bvh_on_device": bool(out[6]),
+                "scene_bvh_host_thread_ms": out[7]}
 
     def wait(self):
         """mtb_wait: everything queued on the context's devices has finished."""

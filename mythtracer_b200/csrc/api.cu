@@ -14,6 +14,14 @@
 
 #include "device_scene.h"
 
+namespace mtb {
+// device_build.cu
+cudaError_t BuildSceneBvhOnDevice(const double *h_ref_box, int64_t n_refs, const double scene_box[6], double pad, cudaStream_t stream,
+                                  Bvh2Node **d_nodes_out, int32_t *n_nodes_out, int32_t **d_leaf_ref_out, int32_t *depth_out);
+void LaunchGatherLeafSlots(const SlotRec *slots, const int32_t *ref_slot, const int32_t *leaf_ref, int64_t n_positions, SlotRec *gslots,
+                           cudaStream_t stream);
+}  // namespace mtb
+
 namespace {
 
 std::string g_create_error;
@@ -73,6 +81,8 @@ struct DeviceState {
   DeviceBuffer<mtb::SlotRec> gslots;
   DeviceBuffer<int32_t> list_order;
   DeviceBuffer<int32_t> slot_node;
+  DeviceBuffer<int32_t> leaf_ref, ref_slot;  // device-built scene BVH: leaf position -> reference -> canonical slot
+  int32_t device_bvh_depth = 0;
   DeviceBuffer<mtb_material> materials;
   DeviceBuffer<int2> tex_dims;
   DeviceBuffer<mtb_light> lights;
@@ -128,7 +138,7 @@ struct DeviceState {
   mtb::WfBuffers wf{};
 
   void FreeAll() {
-    nodes.Free(); slots.Free(); shade.Free(); bvh.Free(); gnodes.Free(); gslots.Free(); list_order.Free(); slot_node.Free(); materials.Free();
+    nodes.Free(); slots.Free(); shade.Free(); bvh.Free(); gnodes.Free(); gslots.Free(); list_order.Free(); slot_node.Free(); leaf_ref.Free(); ref_slot.Free(); materials.Free();
     tex_dims.Free(); lights.Free(); rgb.Free(); dbg.Free(); sig_hits.Free(); sig_shadow.Free(); n_rays.Free();
     counters.Free(); tile_cost.Free(); tile_order.Free(); heavy_k.Free();
     if (hybrid_stream != nullptr) cudaStreamDestroy(hybrid_stream);
@@ -182,6 +192,8 @@ struct mtb_context {
   std::atomic<uint64_t> launches{0};  // kernels of this library launched so far (mtb_launch_count)
   bool no_peer_store = false;         // MTB_NO_PEER_STORE=1: gather with peer copies instead of direct tile stores (A/B)
   int l2_persist_mb = 0;              // MTB_L2_PERSIST_MB=n: pin the scene BVH's nodes in n MB of persisting L2 (A/B)
+  bool device_bvh = false;            // the scene BVH of the current scene was built on the devices (device_build.cu)
+  double ms_parse = 0.0, ms_upload = 0.0, ms_device_bvh = 0.0;  // stages of the last load (mtb_load_timing)
   std::vector<void *> owned_frames, opened_frames;  // mtb_frame_create / mtb_frame_open
   std::mutex err_mutex;
 };
@@ -197,8 +209,8 @@ void DestroyTextures(DeviceState *d) {
 
 // Regular rays take the certified fast traversal over the scene BVH unless the exact octree recursion is forced.
 void SelectTraversal(mtb_context *ctx, DeviceState *d) {
-  const bool fast = (ctx->flags & (MTB_FLAG_EXACT_OCTREE | MTB_FLAG_NO_LIST_BVH)) == 0 && !ctx->flat.gnodes.empty() &&
-                    d->scene.cull_radius > 0.0f;
+  const bool fast = (ctx->flags & (MTB_FLAG_EXACT_OCTREE | MTB_FLAG_NO_LIST_BVH)) == 0 && d->gnodes.ptr != nullptr && d->gnodes.count > 0 &&
+                    d->gslots.ptr != nullptr && d->scene.cull_radius > 0.0f;
   d->scene.gnodes = fast ? d->gnodes.ptr : nullptr;
   d->scene.gslots = fast ? d->gslots.ptr : nullptr;
 }
@@ -212,8 +224,53 @@ int UploadToDevice(mtb_context *ctx, DeviceState *d) {
   MTB_CUDA(ctx, d->bvh.Upload(f.bvh.data(), f.bvh.size(), d->stream));
   MTB_CUDA(ctx, d->list_order.Upload(f.list_order.data(), f.list_order.size(), d->stream));
   MTB_CUDA(ctx, d->slot_node.Upload(f.slot_node.data(), f.slot_node.size(), d->stream));
-  MTB_CUDA(ctx, d->gnodes.Upload(f.gnodes.data(), f.gnodes.size(), d->stream));
-  MTB_CUDA(ctx, d->gslots.Upload(f.gslots.data(), f.gslots.size(), d->stream));
+  d->gnodes.Free();
+  d->gslots.Free();
+  d->leaf_ref.Free();
+  d->ref_slot.Free();
+  d->device_bvh_depth = 0;
+  if (ctx->device_bvh) {
+    // the scene BVH is built on the device from the reference boxes (PLOC, device_build.cu) and
+    // the leaf-ordered triangle records are gathered on the device from the records uploaded above - the host neither
+    // builds nor uploads them.
+    const auto t0 = std::chrono::steady_clock::now();
+    mtb::Bvh2Node *d_nodes = nullptr;
+    int32_t *d_leaf_ref = nullptr;
+    int32_t n_nodes = 0, depth = 0;
+    const int64_t n_refs = (int64_t)f.ref_slot.size();
+    const cudaError_t e = mtb::BuildSceneBvhOnDevice(f.ref_box.data(), n_refs, f.aabb, f.bvh_pad, d->stream, &d_nodes, &n_nodes, &d_leaf_ref, &depth);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      ctx->err = std::string("device BVH build: ") + cudaGetErrorString(e);
+      return MTB_ERR_CUDA;
+    }
+    d->gnodes.ptr = d_nodes;
+    d->gnodes.count = (size_t)n_nodes;
+    d->leaf_ref.ptr = d_leaf_ref;
+    d->leaf_ref.count = (size_t)n_refs;
+    d->device_bvh_depth = depth;
+    if (depth > mtb::kSceneBvhMaxDepth) {  // deeper than the traversal stack (never seen): no fast traversal
+      d->gnodes.Free();
+      d->leaf_ref.Free();
+    } else {
+      MTB_CUDA(ctx, d->ref_slot.Upload(f.ref_slot.data(), f.ref_slot.size(), d->stream));
+      MTB_CUDA(ctx, d->gslots.Reserve((size_t)n_refs));
+      mtb::LaunchGatherLeafSlots(d->slots.ptr, d->ref_slot.ptr, d->leaf_ref.ptr, n_refs, d->gslots.ptr, d->stream);
+      MTB_CUDA(ctx, cudaGetLastError());
+    }
+    MTB_CUDA(ctx, cudaStreamSynchronize(d->stream));
+    ctx->ms_device_bvh = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (getenv("MTB_TIMING") != nullptr) {
+      fprintf(stderr, "[mtb] %-28s %8.1f ms (%d nodes, depth %d)\n", "scene BVH on the device", ctx->ms_device_bvh, n_nodes, depth);
+    }
+  } else {
+    MTB_CUDA(ctx, d->gnodes.Upload(f.gnodes.data(), f.gnodes.size(), d->stream));
+    MTB_CUDA(ctx, d->gslots.Upload(f.gslots.data(), f.gslots.size(), d->stream));
+    if (f.gnodes.empty()) {
+      d->gnodes.Free();
+      d->gslots.Free();
+    }
+  }
   MTB_CUDA(ctx, d->materials.Upload(ctx->materials.data(), ctx->materials.size(), d->stream));
   DestroyTextures(d);
   // All textures live in ONE layered CUDA array behind ONE texture object (layer = texture index, extent = the
@@ -325,9 +382,17 @@ int BuildAndUpload(mtb_context *ctx) {
     }
   }
   std::string err;
+  // Where the scene BVH is built: on the host threads (binned SAH; the default: its trees render C3 12 % faster),
+  // on the devices (MTB_FLAG_DEVICE_BVH: PLOC, csrc/device_build.cu; contexts with a device, scenes of at least 64
+  // triangles), or not at all (MTB_FLAG_NO_LIST_BVH).
+  mtb::SceneBvhMode mode = mtb::kSceneBvhNone;
+  if ((ctx->flags & MTB_FLAG_NO_LIST_BVH) == 0) {
+    const bool device = !ctx->dev.empty() && (ctx->flags & MTB_FLAG_DEVICE_BVH) != 0 && ctx->triangles.size() >= 64;
+    mode = device ? mtb::kSceneBvhRefs : mtb::kSceneBvhHost;
+  }
+  ctx->device_bvh = mode == mtb::kSceneBvhRefs;
   const int rc = mtb::BuildFlatScene(ctx->triangles.data(), (int64_t)ctx->triangles.size(),
-                                     (ctx->flags & MTB_FLAG_NO_LIST_BVH) == 0, (ctx->flags & MTB_FLAG_NO_LIST_BVH) == 0,
-                                     &ctx->flat, &err);
+                                     (ctx->flags & MTB_FLAG_NO_LIST_BVH) == 0, mode, &ctx->flat, &err);
   if (rc != MTB_OK) {
     ctx->err = err;
     return rc;
@@ -335,12 +400,18 @@ int BuildAndUpload(mtb_context *ctx) {
   ctx->device_bytes = (int64_t)(ctx->flat.nodes.size() * sizeof(mtb::NodeRec) + ctx->flat.slots.size() * sizeof(mtb::SlotRec) +
                                 ctx->flat.shade.size() * sizeof(mtb::ShadeRec) + ctx->flat.bvh.size() * sizeof(mtb::BvhRec) +
                                 ctx->flat.gnodes.size() * sizeof(mtb::Bvh2Node) + ctx->flat.gslots.size() * sizeof(mtb::SlotRec) +
+                                ctx->flat.ref_slot.size() * (sizeof(mtb::SlotRec) + 8) +
                                 ctx->flat.list_order.size() * 4 + ctx->flat.slot_node.size() * 4 + ctx->materials.size() * sizeof(mtb_material));
   for (const mtb::LoadedTexture &t : ctx->textures) ctx->device_bytes += (int64_t)t.rgba.size();
+  const auto t_up = std::chrono::steady_clock::now();
+  ctx->ms_device_bvh = 0.0;
   for (DeviceState &d : ctx->dev) {
     const int urc = UploadToDevice(ctx, &d);
     if (urc != MTB_OK) return urc;
   }
+  ctx->ms_upload = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_up).count() - ctx->ms_device_bvh;
+  if (ctx->device_bvh && !ctx->dev.empty()) ctx->device_bytes += (int64_t)(ctx->dev[0].gnodes.count * sizeof(mtb::Bvh2Node));
+  if (getenv("MTB_TIMING") != nullptr) fprintf(stderr, "[mtb] %-28s %8.1f ms\n", "upload", ctx->ms_upload);
   ctx->has_scene = true;
   return MTB_OK;
 }
@@ -963,7 +1034,11 @@ int mtb_load_obj(mtb_context *ctx, const char *path) {
   mtb::LoadedScene loaded;
   std::string err;
   ctx->has_scene = false;
-  if (!mtb::LoadObjFile(path, &loaded, &err)) {
+  const auto t_parse = std::chrono::steady_clock::now();
+  const bool parsed = mtb::LoadObjFile(path, &loaded, &err);
+  ctx->ms_parse = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_parse).count();
+  if (getenv("MTB_TIMING") != nullptr) fprintf(stderr, "[mtb] %-28s %8.1f ms\n", "OBJ + MTL parse", ctx->ms_parse);
+  if (!parsed) {
     ctx->err = err;
     fprintf(stderr, "error: %s\n", err.c_str());
     return MTB_ERR_IO;
@@ -1042,7 +1117,7 @@ int mtb_scene_info(const mtb_context *ctx, mtb_scene_summary *out) {
     out->aabb_max[a] = ctx->flat.aabb[3 + a];
   }
   out->device_bytes = ctx->device_bytes;
-  out->n_scene_refs = (int64_t)ctx->flat.gslots.size();
+  out->n_scene_refs = ctx->device_bvh ? (int64_t)ctx->flat.ref_slot.size() : (int64_t)ctx->flat.gslots.size();
   return MTB_OK;
 }
 
@@ -1079,6 +1154,21 @@ int mtb_scene_triangle_nodes(const mtb_context *ctx, double *node_box, int32_t *
 int mtb_scene_bvh(const mtb_context *ctx, int64_t *n_nodes, int32_t *depth, void *nodes, int32_t *leaf_order) {
   if (ctx == nullptr) return MTB_ERR_ARG;
   const mtb::FlatScene &f = ctx->flat;
+  if (ctx->device_bvh && !ctx->dev.empty()) {
+    // built on the device: read it back from device 0 for inspection
+    const DeviceState &d = ctx->dev[0];
+    if (n_nodes != nullptr) *n_nodes = (int64_t)d.gnodes.count;
+    if (depth != nullptr) *depth = d.device_bvh_depth;
+    if (cudaSetDevice(d.device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return MTB_ERR_CUDA;
+    if (nodes != nullptr && d.gnodes.count > 0 &&
+        cudaMemcpy(nodes, d.gnodes.ptr, d.gnodes.count * sizeof(mtb::Bvh2Node), cudaMemcpyDeviceToHost) != cudaSuccess) return MTB_ERR_CUDA;
+    if (leaf_order != nullptr && d.leaf_ref.count > 0) {
+      std::vector<int32_t> refs(d.leaf_ref.count);
+      if (cudaMemcpy(refs.data(), d.leaf_ref.ptr, refs.size() * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return MTB_ERR_CUDA;
+      for (size_t i = 0; i < refs.size(); i++) leaf_order[i] = f.slots[(size_t)f.ref_slot[(size_t)refs[i]]].tri;
+    }
+    return MTB_OK;
+  }
   if (n_nodes != nullptr) *n_nodes = (int64_t)f.gnodes.size();
   if (depth != nullptr) *depth = f.gbvh_depth;
   if (nodes != nullptr && !f.gnodes.empty()) memcpy(nodes, f.gnodes.data(), f.gnodes.size() * sizeof(mtb::Bvh2Node));
@@ -1088,9 +1178,22 @@ int mtb_scene_bvh(const mtb_context *ctx, int64_t *n_nodes, int32_t *depth, void
   return MTB_OK;
 }
 
+int mtb_load_timing(const mtb_context *ctx, double out_ms[8]) {
+  if (ctx == nullptr || out_ms == nullptr) return MTB_ERR_ARG;
+  out_ms[0] = ctx->ms_parse;
+  out_ms[1] = ctx->flat.ms_octree;
+  out_ms[2] = ctx->flat.ms_flatten;
+  out_ms[3] = ctx->flat.ms_scene_bvh;
+  out_ms[4] = ctx->ms_device_bvh;
+  out_ms[5] = ctx->ms_upload;
+  out_ms[6] = ctx->device_bvh ? 1.0 : 0.0;
+  out_ms[7] = ctx->flat.ms_scene_bvh_thread;
+  return MTB_OK;
+}
+
 int mtb_set_flags(mtb_context *ctx, uint32_t flags) {
   if (ctx == nullptr) return MTB_ERR_ARG;
-  const bool rebuild = ((ctx->flags ^ flags) & MTB_FLAG_NO_LIST_BVH) != 0 && ctx->has_scene;
+  const bool rebuild = ((ctx->flags ^ flags) & (MTB_FLAG_NO_LIST_BVH | MTB_FLAG_DEVICE_BVH)) != 0 && ctx->has_scene;
   ctx->flags = flags;
   if (rebuild) return BuildAndUpload(ctx);
   for (DeviceState &d : ctx->dev) SelectTraversal(ctx, &d);

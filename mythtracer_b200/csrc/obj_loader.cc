@@ -14,12 +14,16 @@
 //     (objreader.cc:487-503); a texture that fails to load fails the whole load (objreader.cc:467-469).
 // Texture files are decoded by image_decode.cc (PPM, PNG, BMP, TGA -> RGBA32): SDL2_image, which the reference
 // uses (texture.cc:60-109), is not available offline.
+#include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <sstream>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "scene_build.h"
 
@@ -225,152 +229,364 @@ bool LoadMtlFile(const char *path, LoadedScene *scene, std::string *err) {
   return mp.Parse(path);
 }
 
-bool LoadObjFile(const char *path, LoadedScene *scene, std::string *err) {
-  FileCloser fc{fopen(path, "r")};
-  if (fc.f == nullptr) {
-    *err = std::string("file \"") + path + "\" not found";
+// ---------------------------------------------------------------------------------------------------
+// OBJ reader.  The reference reads line by line (objreader.cc:201-274); what it observably does is kept (see the
+// list at the top of this file), but the work is organised for a many-core host - the parse was 0.35 s of the 0.61 s
+// a 500 k-triangle scene needed to reach its first frame in round 1:
+//   phase 1 (parallel): the file is cut at newline boundaries into chunks; every chunk is consumed in the same
+//            127-byte pieces fgets would deliver (a piece ends at a newline, so every chunk start is a piece start),
+//            and parsed into chunk-local vertex / normal / texcoord arrays, face records and an ordered list of
+//            events (usemtl, mtllib, warnings, the first error);
+//   phase 2 (sequential, tiny): chunks in file order - running piece counts give the 0-based line numbers
+//            (objreader.cc:210,233), events resolve materials with the names known AT THAT POINT of the file, the
+//            first error in file order ends the load;
+//   phase 3 (parallel): triangles are assembled into their final positions; an index is valid only against the
+//            vertices defined BEFORE its face, as in a sequential read.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct FaceRec {
+  int32_t vi[5], ti[5], ni[5];
+  int32_t count;               // 3, or 5 for a quad (0,1,2),(2,3,0)
+  int32_t piece;               // piece index inside the chunk
+  int32_t n_pos, n_nrm, n_tex; // chunk-local element counts in front of this face
+  int32_t material;            // filled in phase 2
+};
+
+enum EventKind { kEvUseMtl, kEvMtlLib, kEvWarnFeature, kEvError };
+struct ObjEvent {
+  EventKind kind;
+  std::string text;
+  int32_t face_index;  // faces of the chunk in front of this event
+  int32_t piece;
+};
+
+struct ChunkOut {
+  std::vector<double> pos, nrm, tex;  // xyz triples
+  std::vector<FaceRec> faces;
+  std::vector<ObjEvent> events;
+  int32_t n_pieces = 0;
+  int32_t n_tris = 0;
+  // phase 3
+  int32_t bad_face = -1;
+  std::string bad_text;
+};
+
+// One piece (what fgets(line, 128) would have delivered, NUL-terminated, line end chopped).  Returns false on an
+// error (an error event has been recorded).
+bool ParsePiece(char *line, int32_t piece, ChunkOut *out) {
+  char key_buf[16] = {0};
+  {
+    const char *q = line;
+    while (IsSpace(*q)) q++;
+    int n = 0;
+    while (*q != '\0' && !IsSpace(*q) && n < 15) key_buf[n++] = *q++;
+    if (n == 0 || key_buf[0] == '#') return true;
+  }
+  auto fail = [&](const std::string &text) {
+    out->events.push_back(ObjEvent{kEvError, text, (int32_t)out->faces.size(), piece});
     return false;
+  };
+  const std::string key(key_buf);
+  if (key == "v" || key == "vn") {
+    double x, y, z;
+    // sscanf(line, "v %lf %lf %lf"): the literal must start the line (no leading blanks), then three doubles
+    const char *p = line + key.size();
+    if (strncmp(line, key.c_str(), key.size()) != 0 || !ScanDouble(&p, &x) || !ScanDouble(&p, &y) || !ScanDouble(&p, &z)) {
+      return fail(std::string("unsupported ") + (key == "v" ? "vertex" : "normal") + " format \"" + line + "\"");
+    }
+    std::vector<double> &dst = key == "v" ? out->pos : out->nrm;
+    dst.push_back(x);
+    dst.push_back(y);
+    dst.push_back(z);
+  } else if (key == "vt") {
+    double u, v, w = 0.0;
+    const char *p = line + 2;
+    if (strncmp(line, "vt", 2) != 0 || !ScanDouble(&p, &u) || !ScanDouble(&p, &v)) {
+      return fail(std::string("unsupported texcoord format \"") + line + "\"");
+    }
+    ScanDouble(&p, &w);  // optional third coordinate
+    out->tex.push_back(u);
+    out->tex.push_back(v);
+    out->tex.push_back(w);
+  } else if (key == "mtllib") {
+    char fname[256];
+    if (sscanf(line, "mtllib %255[^\n]", fname) != 1) return fail(std::string("unsupported mtllib format \"") + line + "\"");
+    out->events.push_back(ObjEvent{kEvMtlLib, fname, (int32_t)out->faces.size(), piece});
+  } else if (key == "usemtl") {
+    char name[128];
+    if (sscanf(line, "usemtl %127s", name) != 1) return fail("unsupported usemtl format");
+    out->events.push_back(ObjEvent{kEvUseMtl, name, (int32_t)out->faces.size(), piece});
+  } else if (key == "f") {
+    // `s >> token; if (s.eof()) break;` keeps a token only when at least one more character follows it
+    // (objreader.cc:109-115): the first token ("f") is skipped, a token that ends the line is dropped.
+    FaceRec fr;
+    int count = 0;
+    const char *p = line;
+    while (IsSpace(*p)) p++;
+    while (*p != '\0' && !IsSpace(*p)) p++;  // the "f" itself
+    for (;;) {
+      while (IsSpace(*p)) p++;
+      if (*p == '\0') break;
+      const char *start = p;
+      while (*p != '\0' && !IsSpace(*p)) p++;
+      if (*p == '\0') break;  // the quirk: nothing follows this token
+      char tokbuf[128];
+      const size_t len = (size_t)(p - start);
+      memcpy(tokbuf, start, len);
+      tokbuf[len] = '\0';
+      int v = 0, vt = 0, vn = 0;
+      if (!ScanFaceToken(tokbuf, &v, &vt, &vn)) return fail(std::string("unsupported face format \"") + tokbuf + "\"");
+      if (count < 4) {
+        fr.vi[count] = v - 1;
+        fr.ti[count] = vt - 1;
+        fr.ni[count] = vn - 1;
+      }
+      count++;
+    }
+    if (count != 3 && count != 4) return fail("unsupported face count (" + std::to_string(count) + ")\n  " + line);
+    if (count == 4) {
+      fr.vi[4] = fr.vi[0];
+      fr.ti[4] = fr.ti[0];
+      fr.ni[4] = fr.ni[0];
+      count = 5;
+    }
+    fr.count = count;
+    fr.piece = piece;
+    fr.n_pos = (int32_t)(out->pos.size() / 3);
+    fr.n_nrm = (int32_t)(out->nrm.size() / 3);
+    fr.n_tex = (int32_t)(out->tex.size() / 3);
+    fr.material = -1;
+    out->faces.push_back(fr);
+    out->n_tris += count == 5 ? 2 : 1;
+  } else if (key == "s" || key == "g" || key == "o") {
+    return true;
+  } else {
+    out->events.push_back(ObjEvent{kEvWarnFeature, key_buf, (int32_t)out->faces.size(), piece});
+  }
+  return true;
+}
+
+// Consumes data[begin, end) the way `while (fgets(line, 128, f))` does: pieces of at most 127 bytes, a piece ends
+// behind a newline; the C string a piece holds ends at its first NUL byte.
+void ParseChunk(const char *data, size_t begin, size_t end, ChunkOut *out) {
+  size_t p = begin;
+  char line[128];
+  while (p < end) {
+    size_t len = end - p < 127 ? end - p : 127;
+    const void *nl = memchr(data + p, '\n', len);
+    if (nl != nullptr) len = (size_t)(static_cast<const char *>(nl) - (data + p)) + 1;
+    memcpy(line, data + p, len);
+    line[len] = '\0';
+    p += len;
+    const int32_t piece = out->n_pieces++;
+    ChopLineEnd(line);
+    if (!ParsePiece(line, piece, out)) return;  // the sequential reader stops at its first error
+  }
+}
+
+}  // namespace
+
+bool LoadObjFile(const char *path, LoadedScene *scene, std::string *err) {
+  std::vector<char> data;
+  {
+    FileCloser fc{fopen(path, "rb")};
+    if (fc.f == nullptr) {
+      *err = std::string("file \"") + path + "\" not found";
+      return false;
+    }
+    char buf[1 << 16];
+    size_t got;
+    if (fseek(fc.f, 0, SEEK_END) == 0) {
+      const long size = ftell(fc.f);
+      if (size > 0) data.reserve((size_t)size);
+      fseek(fc.f, 0, SEEK_SET);
+    }
+    while ((got = fread(buf, 1, sizeof(buf), fc.f)) > 0) data.insert(data.end(), buf, buf + got);
   }
   const std::string dir = DirOf(path);
-  std::vector<double> pos, nrm, tex;  // xyz triples
-  int material = -1;
-  char line[128];
-  for (int line_no = 0; fgets(line, sizeof(line), fc.f) != nullptr; line_no++) {
-    ChopLineEnd(line);
-    // sscanf(line, "%15s", key): skip white space, then up to 15 non-space characters (done by hand: the format
-    // interpreter was a quarter of the load time of a 500 k-triangle model)
-    char key_buf[16] = {0};
-    {
-      const char *q = line;
-      while (IsSpace(*q)) q++;
-      int n = 0;
-      while (*q != '\0' && !IsSpace(*q) && n < 15) key_buf[n++] = *q++;
-      if (n == 0 || key_buf[0] == '#') continue;
-    }
-    const std::string key(key_buf);
-    if (key == "v" || key == "vn") {
-      double x, y, z;
-      // sscanf(line, "v %lf %lf %lf"): the literal must start the line (no leading blanks), then three doubles
-      const char *p = line + key.size();
-      if (strncmp(line, key.c_str(), key.size()) != 0 || !ScanDouble(&p, &x) || !ScanDouble(&p, &y) || !ScanDouble(&p, &z)) {
-        *err = std::string("unsupported ") + (key == "v" ? "vertex" : "normal") + " format \"" + line + "\"";
-        return false;
-      }
-      std::vector<double> &dst = key == "v" ? pos : nrm;
-      dst.push_back(x);
-      dst.push_back(y);
-      dst.push_back(z);
-    } else if (key == "vt") {
-      double u, v, w = 0.0;
-      const char *p = line + 2;
-      if (strncmp(line, "vt", 2) != 0 || !ScanDouble(&p, &u) || !ScanDouble(&p, &v)) {
-        *err = std::string("unsupported texcoord format \"") + line + "\"";
-        return false;
-      }
-      ScanDouble(&p, &w);  // optional third coordinate
-      tex.push_back(u);
-      tex.push_back(v);
-      tex.push_back(w);
-    } else if (key == "mtllib") {
-      char fname[256];
-      if (sscanf(line, "mtllib %255[^\n]", fname) != 1) {
-        *err = std::string("unsupported mtllib format \"") + line + "\"";
-        return false;
-      }
-      MtlParser mp(scene, err);
-      if (!mp.Parse(Join(dir, fname))) return false;
-    } else if (key == "usemtl") {
-      char name[128];
-      if (sscanf(line, "usemtl %127s", name) != 1) {
-        *err = "unsupported usemtl format";
-        return false;
-      }
-      material = -1;
-      for (size_t i = 0; i < scene->material_names.size(); i++) {
-        if (scene->material_names[i] == name) material = (int)i;
-      }
-      if (material < 0) fprintf(stderr, "warning: material \"%s\" not found\n", name);
-    } else if (key == "f") {
-      // `s >> token; if (s.eof()) break;` keeps a token only when at least one more character follows it
-      // (objreader.cc:109-115): the first token ("f") is skipped, a token that ends the line is dropped.
-      int vi[5], ti[5], ni[5];
-      int count = 0;
-      const char *p = line;
-      while (IsSpace(*p)) p++;
-      while (*p != '\0' && !IsSpace(*p)) p++;  // the "f" itself
+  const size_t size = data.size();
+
+  // ---- phase 1: chunks that start right behind a newline ----
+  unsigned n_threads = std::thread::hardware_concurrency();
+  if (n_threads == 0) n_threads = 1;
+  if (n_threads > 32) n_threads = 32;
+  if (size < (1u << 20)) n_threads = 1;
+  if (const char *env = getenv("MTB_LOADER_THREADS")) {  // tests: the result must not depend on the chunking
+    if (atoi(env) >= 1) n_threads = (unsigned)std::min(atoi(env), 64);
+  }
+  const size_t n_chunks = n_threads == 1 ? 1 : (size_t)n_threads * 4;
+  std::vector<size_t> cut(n_chunks + 1, size);
+  cut[0] = 0;
+  for (size_t c = 1; c < n_chunks; c++) {
+    size_t p = size / n_chunks * c;
+    if (p < cut[c - 1]) p = cut[c - 1];
+    const void *nl = p < size ? memchr(data.data() + p, '\n', size - p) : nullptr;
+    cut[c] = nl != nullptr ? (size_t)(static_cast<const char *>(nl) - data.data()) + 1 : size;
+  }
+  std::vector<ChunkOut> chunks(n_chunks);
+  {
+    std::atomic<size_t> next(0);
+    auto worker = [&]() {
       for (;;) {
-        while (IsSpace(*p)) p++;
-        if (*p == '\0') break;
-        const char *start = p;
-        while (*p != '\0' && !IsSpace(*p)) p++;
-        if (*p == '\0') break;  // the quirk: nothing follows this token
-        char tokbuf[128];
-        const size_t len = (size_t)(p - start);
-        memcpy(tokbuf, start, len);
-        tokbuf[len] = '\0';
-        int v = 0, vt = 0, vn = 0;
-        if (!ScanFaceToken(tokbuf, &v, &vt, &vn)) {
-          *err = std::string("unsupported face format \"") + tokbuf + "\"";
-          return false;
-        }
-        if (count < 4) {
-          vi[count] = v - 1;
-          ti[count] = vt - 1;
-          ni[count] = vn - 1;
-        }
-        count++;
+        const size_t c = next.fetch_add(1);
+        if (c >= n_chunks) return;
+        ParseChunk(data.data(), cut[c], cut[c + 1], &chunks[c]);
       }
-      if (count != 3 && count != 4) {
-        *err = "unsupported face count (" + std::to_string(count) + ")\n  " + line;
-        return false;
-      }
-      if (count == 4) {
-        vi[4] = vi[0];
-        ti[4] = ti[0];
-        ni[4] = ni[0];
-        count = 5;
-      }
-      for (int base = 0; base + 3 <= count; base += 2) {
-        mtb_triangle tr;
-        memset(&tr, 0, sizeof(tr));
-        for (int j = 0; j < 3; j++) {
-          const int idx = vi[base + j];
-          // The reference indexes its vectors unchecked (objreader.cc:155); out-of-range is refused here.
-          if (idx < 0 || (size_t)idx * 3 + 2 >= pos.size()) {
-            *err = std::string("vertex index out of range in \"") + line + "\"";
-            return false;
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n_threads; t++) pool.emplace_back(worker);
+    worker();
+    for (std::thread &t : pool) t.join();
+  }
+
+  // ---- phase 2: file order ----
+  std::vector<int64_t> pos_base(n_chunks + 1, 0), nrm_base(n_chunks + 1, 0), tex_base(n_chunks + 1, 0), line_base(n_chunks + 1, 0),
+      tri_base(n_chunks + 1, 0);
+  int material = -1;
+  size_t used_chunks = n_chunks;
+  bool failed = false;
+  std::string fail_text;
+  for (size_t c = 0; c < n_chunks && !failed; c++) {
+    ChunkOut &ch = chunks[c];
+    size_t next_event = 0;
+    for (size_t f = 0; f <= ch.faces.size(); f++) {
+      while (next_event < ch.events.size() && (size_t)ch.events[next_event].face_index == f) {
+        const ObjEvent &ev = ch.events[next_event++];
+        if (ev.kind == kEvUseMtl) {
+          material = -1;
+          for (size_t i = 0; i < scene->material_names.size(); i++) {
+            if (scene->material_names[i] == ev.text) material = (int)i;
           }
-          memcpy(tr.vertex + j * 3, &pos[(size_t)idx * 3], 3 * sizeof(double));
-        }
-        if (ni[base] != -1 && ni[base + 1] != -1 && ni[base + 2] != -1) {
-          for (int j = 0; j < 3; j++) {
-            const int idx = ni[base + j];
-            if (idx < 0 || (size_t)idx * 3 + 2 >= nrm.size()) {
-              *err = std::string("normal index out of range in \"") + line + "\"";
-              return false;
-            }
-            memcpy(tr.normal + j * 3, &nrm[(size_t)idx * 3], 3 * sizeof(double));
+          if (material < 0) fprintf(stderr, "warning: material \"%s\" not found\n", ev.text.c_str());
+        } else if (ev.kind == kEvMtlLib) {
+          MtlParser mp(scene, err);
+          if (!mp.Parse(Join(dir, ev.text.c_str()))) {
+            failed = true;
+            fail_text = *err;
           }
+        } else if (ev.kind == kEvWarnFeature) {
+          fprintf(stderr, "warning: unknown OBJ feature \"%s\"\n", ev.text.c_str());
+        } else {
+          failed = true;
+          fail_text = ev.text;
         }
-        if (ti[base] != -1 && ti[base + 1] != -1 && ti[base + 2] != -1) {
-          for (int j = 0; j < 3; j++) {
-            const int idx = ti[base + j];
-            if (idx < 0 || (size_t)idx * 3 + 2 >= tex.size()) {
-              *err = std::string("texcoord index out of range in \"") + line + "\"";
-              return false;
-            }
-            memcpy(tr.uvw + j * 3, &tex[(size_t)idx * 3], 3 * sizeof(double));
-          }
-        }
-        tr.material = material;
-        tr.line_no = line_no;
-        scene->triangles.push_back(tr);
+        if (failed) break;
       }
-    } else if (key == "s" || key == "g" || key == "o") {
-      continue;
-    } else {
-      fprintf(stderr, "warning: unknown OBJ feature \"%s\"\n", key_buf);
+      if (failed) {
+        // everything in front of the failing piece still counts (an out-of-range index there is the earlier error)
+        ch.faces.resize(f);
+        ch.n_tris = 0;
+        for (const FaceRec &fr : ch.faces) ch.n_tris += fr.count == 5 ? 2 : 1;
+        break;
+      }
+      if (f < ch.faces.size()) ch.faces[f].material = material;
     }
+    pos_base[c + 1] = pos_base[c] + (int64_t)ch.pos.size();
+    nrm_base[c + 1] = nrm_base[c] + (int64_t)ch.nrm.size();
+    tex_base[c + 1] = tex_base[c] + (int64_t)ch.tex.size();
+    line_base[c + 1] = line_base[c] + ch.n_pieces;
+    tri_base[c + 1] = tri_base[c] + ch.n_tris;
+    if (failed) used_chunks = c + 1;
+  }
+
+  // ---- phase 3: global attribute arrays, then the triangles in their final places ----
+  std::vector<double> pos((size_t)pos_base[used_chunks]), nrm((size_t)nrm_base[used_chunks]), tex((size_t)tex_base[used_chunks]);
+  const size_t tri0 = scene->triangles.size();
+  scene->triangles.resize(tri0 + (size_t)tri_base[used_chunks]);
+  {
+    std::atomic<size_t> next(0);
+    auto gather = [&]() {
+      for (;;) {
+        const size_t c = next.fetch_add(1);
+        if (c >= used_chunks) return;
+        const ChunkOut &ch = chunks[c];
+        if (!ch.pos.empty()) memcpy(&pos[(size_t)pos_base[c]], ch.pos.data(), ch.pos.size() * sizeof(double));
+        if (!ch.nrm.empty()) memcpy(&nrm[(size_t)nrm_base[c]], ch.nrm.data(), ch.nrm.size() * sizeof(double));
+        if (!ch.tex.empty()) memcpy(&tex[(size_t)tex_base[c]], ch.tex.data(), ch.tex.size() * sizeof(double));
+      }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n_threads; t++) pool.emplace_back(gather);
+    gather();
+    for (std::thread &t : pool) t.join();
+  }
+  {
+    std::atomic<size_t> next(0);
+    auto assemble = [&]() {
+      for (;;) {
+        const size_t c = next.fetch_add(1);
+        if (c >= used_chunks) return;
+        ChunkOut &ch = chunks[c];
+        mtb_triangle *dst = scene->triangles.data() + tri0 + (size_t)tri_base[c];
+        for (size_t f = 0; f < ch.faces.size(); f++) {
+          const FaceRec &fr = ch.faces[f];
+          // what a sequential reader had seen when it reached this face
+          const size_t have_pos = (size_t)(pos_base[c] / 3 + fr.n_pos), have_nrm = (size_t)(nrm_base[c] / 3 + fr.n_nrm),
+                       have_tex = (size_t)(tex_base[c] / 3 + fr.n_tex);
+          for (int base = 0; base + 3 <= fr.count; base += 2) {
+            mtb_triangle tr;
+            memset(&tr, 0, sizeof(tr));
+            const char *bad = nullptr;
+            for (int j = 0; j < 3; j++) {
+              const int idx = fr.vi[base + j];
+              // The reference indexes its vectors unchecked (objreader.cc:155); out-of-range is refused here.
+              if (idx < 0 || (size_t)idx >= have_pos) {
+                bad = "vertex";
+                break;
+              }
+              memcpy(tr.vertex + j * 3, &pos[(size_t)idx * 3], 3 * sizeof(double));
+            }
+            if (bad == nullptr && fr.ni[base] != -1 && fr.ni[base + 1] != -1 && fr.ni[base + 2] != -1) {
+              for (int j = 0; j < 3; j++) {
+                const int idx = fr.ni[base + j];
+                if (idx < 0 || (size_t)idx >= have_nrm) {
+                  bad = "normal";
+                  break;
+                }
+                memcpy(tr.normal + j * 3, &nrm[(size_t)idx * 3], 3 * sizeof(double));
+              }
+            }
+            if (bad == nullptr && fr.ti[base] != -1 && fr.ti[base + 1] != -1 && fr.ti[base + 2] != -1) {
+              for (int j = 0; j < 3; j++) {
+                const int idx = fr.ti[base + j];
+                if (idx < 0 || (size_t)idx >= have_tex) {
+                  bad = "texcoord";
+                  break;
+                }
+                memcpy(tr.uvw + j * 3, &tex[(size_t)idx * 3], 3 * sizeof(double));
+              }
+            }
+            if (bad != nullptr) {
+              if (ch.bad_face < 0) {
+                ch.bad_face = (int32_t)f;
+                ch.bad_text = std::string(bad) + " index out of range in line " + std::to_string(line_base[c] + fr.piece);
+              }
+              break;
+            }
+            tr.material = fr.material;
+            tr.line_no = (int32_t)(line_base[c] + fr.piece);
+            *dst++ = tr;
+          }
+          if (ch.bad_face >= 0) break;
+        }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n_threads; t++) pool.emplace_back(assemble);
+    assemble();
+    for (std::thread &t : pool) t.join();
+  }
+  for (size_t c = 0; c < used_chunks; c++) {
+    if (chunks[c].bad_face >= 0) {  // the earliest error in file order
+      *err = chunks[c].bad_text;
+      scene->triangles.resize(tri0);
+      return false;
+    }
+  }
+  if (failed) {
+    *err = fail_text;
+    return false;
   }
   return true;
 }

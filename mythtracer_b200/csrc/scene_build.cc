@@ -350,6 +350,182 @@ inline void SplitTriangle(const double vert[9], const Box3 &tb, int32_t tri, dou
   }
 }
 
+// The top levels of the scene BVH are ranges of hundreds of thousands of references handled by ONE node at a time;
+// in round 1 the calling thread binned and partitioned them alone (0.10 of the 0.15 s of the C3 build on 24 cores).
+// These helpers spread one such pass over the host threads.  Results do not depend on the number of threads: the
+// bounds and bins are min / max / counts (order-free), the partition is STABLE (a unique result).
+constexpr int32_t kParallelRange = 1 << 15;
+
+template <typename F>
+void ParallelSlices(int32_t b, int32_t e, unsigned n_threads, F fn) {  // fn(slice index, slice begin, slice end)
+  const int32_t n = e - b;
+  const unsigned slices = n_threads < 1 ? 1 : n_threads;
+  if (slices == 1) {
+    fn(0u, b, e);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (unsigned k = 1; k < slices; k++) {
+    pool.emplace_back([=]() { fn(k, b + (int32_t)((int64_t)n * k / slices), b + (int32_t)((int64_t)n * (k + 1) / slices)); });
+  }
+  fn(0u, b, b + (int32_t)((int64_t)n / slices));
+  for (std::thread &t : pool) t.join();
+}
+
+inline void ParallelRangeBounds(const std::vector<Box3> &tri_box, const std::vector<int32_t> &ids, int32_t b, int32_t e, unsigned n_threads,
+                                Box3 *u, double clo[3], double chi[3]) {
+  struct Part {
+    Box3 u;
+    double clo[3], chi[3];
+  };
+  std::vector<Part> part(n_threads < 1 ? 1 : n_threads);
+  ParallelSlices(b, e, n_threads, [&](unsigned k, int32_t sb, int32_t se) { RangeBounds(tri_box, ids, sb, se, &part[k].u, part[k].clo, part[k].chi); });
+  for (int a = 0; a < 3; a++) {
+    u->lo[a] = clo[a] = INFINITY;
+    u->hi[a] = chi[a] = -INFINITY;
+  }
+  for (const Part &p : part) {
+    for (int a = 0; a < 3; a++) {
+      u->lo[a] = std::min(u->lo[a], p.u.lo[a]);
+      u->hi[a] = std::max(u->hi[a], p.u.hi[a]);
+      clo[a] = std::min(clo[a], p.clo[a]);
+      chi[a] = std::max(chi[a], p.chi[a]);
+    }
+  }
+}
+
+// SahPartition for a big range: the same 16 bins per axis and the same cost, every pass spread over the threads.
+int32_t ParallelSahPartition(const std::vector<Box3> &tri_box, std::vector<int32_t> &ids, std::vector<int32_t> &scratch, int32_t b, int32_t e,
+                             const double clo[3], const double chi[3], unsigned n_threads) {
+  constexpr int kBins = 16;
+  struct Bins {
+    Box3 box[3][kBins];
+    int n[3][kBins];
+  };
+  const unsigned T = n_threads < 1 ? 1 : n_threads;
+  std::vector<Bins> part(T);
+  ParallelSlices(b, e, T, [&](unsigned k, int32_t sb, int32_t se) {
+    Bins &bn = part[k];
+    for (int axis = 0; axis < 3; axis++) {
+      for (int q = 0; q < kBins; q++) {
+        bn.n[axis][q] = 0;
+        for (int a = 0; a < 3; a++) {
+          bn.box[axis][q].lo[a] = INFINITY;
+          bn.box[axis][q].hi[a] = -INFINITY;
+        }
+      }
+    }
+    for (int32_t i = sb; i < se; i++) {
+      const Box3 &tb = tri_box[ids[i]];
+      for (int axis = 0; axis < 3; axis++) {
+        const double ext = chi[axis] - clo[axis];
+        if (!(ext > 0.0)) continue;
+        int q = (int)(((tb.lo[axis] + tb.hi[axis]) - clo[axis]) / ext * kBins);
+        q = q < 0 ? 0 : (q >= kBins ? kBins - 1 : q);
+        bn.n[axis][q]++;
+        for (int a = 0; a < 3; a++) {
+          bn.box[axis][q].lo[a] = std::min(bn.box[axis][q].lo[a], tb.lo[a]);
+          bn.box[axis][q].hi[a] = std::max(bn.box[axis][q].hi[a], tb.hi[a]);
+        }
+      }
+    }
+  });
+  int best_axis = -1, best_bin = -1;
+  double best_cost = INFINITY;
+  for (int axis = 0; axis < 3; axis++) {
+    if (!(chi[axis] - clo[axis] > 0.0)) continue;
+    Box3 bin_box[kBins];
+    int bin_n[kBins];
+    for (int q = 0; q < kBins; q++) {
+      bin_n[q] = 0;
+      for (int a = 0; a < 3; a++) {
+        bin_box[q].lo[a] = INFINITY;
+        bin_box[q].hi[a] = -INFINITY;
+      }
+      for (const Bins &bn : part) {
+        bin_n[q] += bn.n[axis][q];
+        for (int a = 0; a < 3; a++) {
+          bin_box[q].lo[a] = std::min(bin_box[q].lo[a], bn.box[axis][q].lo[a]);
+          bin_box[q].hi[a] = std::max(bin_box[q].hi[a], bn.box[axis][q].hi[a]);
+        }
+      }
+    }
+    double right_area[kBins];
+    int right_n[kBins];
+    Box3 acc;
+    int n_acc = 0;
+    for (int a = 0; a < 3; a++) {
+      acc.lo[a] = INFINITY;
+      acc.hi[a] = -INFINITY;
+    }
+    for (int q = kBins - 1; q > 0; q--) {
+      if (bin_n[q] > 0) {
+        for (int a = 0; a < 3; a++) {
+          acc.lo[a] = std::min(acc.lo[a], bin_box[q].lo[a]);
+          acc.hi[a] = std::max(acc.hi[a], bin_box[q].hi[a]);
+        }
+        n_acc += bin_n[q];
+      }
+      right_area[q] = n_acc > 0 ? HalfArea(acc) : 0.0;
+      right_n[q] = n_acc;
+    }
+    n_acc = 0;
+    for (int a = 0; a < 3; a++) {
+      acc.lo[a] = INFINITY;
+      acc.hi[a] = -INFINITY;
+    }
+    for (int q = 0; q + 1 < kBins; q++) {
+      if (bin_n[q] > 0) {
+        for (int a = 0; a < 3; a++) {
+          acc.lo[a] = std::min(acc.lo[a], bin_box[q].lo[a]);
+          acc.hi[a] = std::max(acc.hi[a], bin_box[q].hi[a]);
+        }
+        n_acc += bin_n[q];
+      }
+      if (n_acc == 0 || right_n[q + 1] == 0) continue;
+      const double cost = HalfArea(acc) * n_acc + right_area[q + 1] * right_n[q + 1];
+      if (cost < best_cost) {
+        best_cost = cost;
+        best_axis = axis;
+        best_bin = q;
+      }
+    }
+  }
+  if (best_axis < 0) return SahPartition(tri_box, ids, b, e, clo, chi, true);  // all centroids coincide: median
+  // stable partition through the scratch array: lefts of all slices first, then the rights, each in input order
+  const double lo = clo[best_axis], ext = chi[best_axis] - clo[best_axis];
+  auto is_left = [&](int32_t t) {
+    int q = (int)(((tri_box[t].lo[best_axis] + tri_box[t].hi[best_axis]) - lo) / ext * kBins);
+    q = q < 0 ? 0 : (q >= kBins ? kBins - 1 : q);
+    return q <= best_bin;
+  };
+  std::vector<int32_t> n_left(T + 1, 0), s_begin(T, b), s_end(T, b);
+  ParallelSlices(b, e, T, [&](unsigned k, int32_t sb, int32_t se) {
+    int32_t c = 0;
+    for (int32_t i = sb; i < se; i++) c += is_left(ids[i]) ? 1 : 0;
+    n_left[k + 1] = c;
+    s_begin[k] = sb;
+    s_end[k] = se;
+  });
+  for (unsigned k = 0; k < T; k++) n_left[k + 1] += n_left[k];
+  const int32_t mid = b + n_left[T];
+  if (mid == b || mid == e) return SahPartition(tri_box, ids, b, e, clo, chi, true);
+  if (scratch.size() < ids.size()) scratch.resize(ids.size());
+  ParallelSlices(b, e, T, [&](unsigned k, int32_t sb, int32_t se) {
+    int32_t l = b + n_left[k], r = mid + (sb - b) - n_left[k];
+    for (int32_t i = sb; i < se; i++) {
+      const int32_t t = ids[i];
+      if (is_left(t)) {
+        scratch[(size_t)l++] = t;
+      } else {
+        scratch[(size_t)r++] = t;
+      }
+    }
+  });
+  ParallelSlices(b, e, T, [&](unsigned, int32_t sb, int32_t se) { memcpy(&ids[(size_t)sb], &scratch[(size_t)sb], (size_t)(se - sb) * sizeof(int32_t)); });
+  return mid;
+}
+
 // Scene BVH (Bvh2Node, scene_build.h) over ALL triangles: the acceleration structure of the certified fast
 // traversal.  ids ends up in leaf order = the order of the `gslots` copies.  The top of the tree is split by the
 // calling thread; every range of at most `grain` triangles below it is an independent job for a pool of threads
@@ -362,6 +538,9 @@ struct SceneBvhBuilder {
   // every stored box is grown by `pad` on all sides: the FP32 slab test's whole error bound is a constant
   // 2^-18.9 R in space, whatever the ray (FastBox, device_core.cuh); pad = 2^-16 R
   double pad = 0.0;
+
+  unsigned par_threads = 1;
+  std::vector<int32_t> scratch;  // ParallelSahPartition
 
   struct Job {
     int32_t b, e, depth;
@@ -397,13 +576,19 @@ struct SceneBvhBuilder {
       return 0;  // patched when the job is done
     }
     double clo[3], chi[3];
-    RangeBounds(tri_box, ids, b, e, box, clo, chi);
+    const bool wide = grain > 0 && e - b >= kParallelRange;  // (only the calling thread's top of the tree has grain > 0)
+    if (wide) {
+      ParallelRangeBounds(tri_box, ids, b, e, par_threads, box, clo, chi);
+    } else {
+      RangeBounds(tri_box, ids, b, e, box, clo, chi);
+    }
     if (depth > *deepest) *deepest = depth;
     if (e - b <= kSceneBvhLeafSize) return ~(int32_t)(((uint32_t)b << 3) | (uint32_t)(e - b));
     const int32_t me = (int32_t)out->size();
     out->emplace_back();
     memset(&out->back(), 0, sizeof(Bvh2Node));
-    const int32_t mid = SahPartition(tri_box, ids, b, e, clo, chi, depth >= 40);
+    const int32_t mid = wide && depth < 40 ? ParallelSahPartition(tri_box, ids, scratch, b, e, clo, chi, par_threads)
+                                           : SahPartition(tri_box, ids, b, e, clo, chi, depth >= 40);
     Box3 lb, rb;
     const int32_t l = Build(out, b, mid, depth + 1, &lb, deepest, grain, me, 0);
     const int32_t r = Build(out, mid, e, depth + 1, &rb, deepest, grain, me, 1);
@@ -417,7 +602,9 @@ struct SceneBvhBuilder {
     unsigned n_threads = std::thread::hardware_concurrency();
     if (n_threads == 0) n_threads = 1;
     if (n_threads > 32) n_threads = 32;
-    const int32_t grain = n_threads > 1 && n >= 65536 ? std::max<int32_t>(4096, n / (int32_t)(n_threads * 8)) : 0;
+    // (the grain does not depend on the thread count: the tree must not either)
+    const int32_t grain = n >= 65536 ? std::max<int32_t>(4096, n / 256) : 0;
+    par_threads = n_threads;
     Box3 whole;
     for (int a = 0; a < 3; a++) whole.lo[a] = whole.hi[a] = 0.0;
     Build(out, 0, n, 0, &whole, &max_depth, grain, -1, 0);
@@ -452,8 +639,9 @@ struct SceneBvhBuilder {
 
 }  // namespace
 
-int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool use_scene_bvh, FlatScene *out,
+int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, SceneBvhMode scene_bvh, FlatScene *out,
                    std::string *err) {
+  const bool use_scene_bvh = scene_bvh != kSceneBvhNone;
   if (n < 0 || n > 0x3fffffff) {
     *err = "triangle count out of range";
     return MTB_ERR_ARG;
@@ -487,14 +675,116 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
   out->depth = 0;
   const bool timing = getenv("MTB_TIMING") != nullptr;
   auto t0 = std::chrono::steady_clock::now();
-  auto lap = [&](const char *what) {
+  auto lap = [&](const char *what, double *record) {
     const auto t1 = std::chrono::steady_clock::now();
-    if (timing) fprintf(stderr, "[mtb] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (timing) fprintf(stderr, "[mtb] %-28s %8.1f ms\n", what, ms);
+    if (record != nullptr) *record = ms;
     t0 = t1;
   };
+  const auto t_build0 = std::chrono::steady_clock::now();
+  out->max_abs_coord = 0.0;
+  for (int a = 0; a < 3; a++) {
+    out->aabb[a] = nodes[0].box.lo[a];
+    out->aabb[3 + a] = nodes[0].box.hi[a];
+    out->max_abs_coord = std::max(out->max_abs_coord, std::max(std::fabs(nodes[0].box.lo[a]), std::fabs(nodes[0].box.hi[a])));
+  }
+
+  // ---- scene BVH of the certified fast traversal, part 1: references and (host build) the tree.  It needs nothing
+  // of the octree, so on big scenes it runs on its own thread while the octree is split and flattened below. ----
+  out->gnodes.clear();
+  out->gslots.clear();
+  out->gbvh_depth = 0;
+  out->ref_box.clear();
+  out->ref_slot.clear();
+  out->n_split_refs = 0;
+  out->bvh_pad = 0x1p-16 * out->max_abs_coord * 1.000001;
+  std::vector<Box3> ref_box;
+  std::vector<int32_t> ref_tri;
+  SceneBvhBuilder sb{ref_box, {}, 0, out->bvh_pad, {}};
+  double ms_tree = 0.0;
+  auto build_tree = [&]() {
+    const auto tt0 = std::chrono::steady_clock::now();
+    // references: one per triangle, several for triangles much larger than the scene's grain (see SplitTriangle)
+    {
+      double scene_ext = 0.0;
+      for (int a = 0; a < 3; a++) scene_ext = std::max(scene_ext, out->aabb[3 + a] - out->aabb[a]);
+      const char *env = getenv("MTB_SPLIT_DIV");  // development knob: pieces of at most scene extent / div (0: no splitting)
+      const double div = env != nullptr ? atof(env) : 64.0;  // measured on C4 (B200): 16 -> 20.8 ms, 32 -> 12.1, 64 -> 7.6 (no splitting: 438)
+      double max_extent = div > 0.0 ? scene_ext / div : INFINITY;
+      const double guard = 1e-9 * std::max(out->max_abs_coord, 1e-30);
+      for (int attempt = 0; attempt < 8; attempt++) {
+        ref_box.clear();
+        ref_tri.clear();
+        ref_box.reserve((size_t)n + (size_t)n / 4);
+        ref_tri.reserve((size_t)n + (size_t)n / 4);
+        for (int64_t i = 0; i < n; i++) {
+          const Box3 &tb = tri_box[(size_t)i];
+          const double dx = tb.hi[0] - tb.lo[0], dy = tb.hi[1] - tb.lo[1], dz = tb.hi[2] - tb.lo[2];
+          const double ext = std::max(std::max(dx, dy), dz);
+          // Only boxes that are mostly empty are worth several references: a long triangle that runs diagonally
+          // through its box (area far below the box's cross sections).  A big axis-aligned wall triangle fills half
+          // of its flat box; splitting those only deepens the tree (measured on C3: +4 % node visits, no gain).
+          bool wasteful = false;
+          if (ext > max_extent) {
+            const double *v = tris[i].vertex;
+            const double e1[3] = {v[3] - v[0], v[4] - v[1], v[5] - v[2]}, e2[3] = {v[6] - v[0], v[7] - v[1], v[8] - v[2]};
+            const double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+            const double tri_area = 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
+            wasteful = tri_area < 0.125 * (dx * dy + dy * dz + dz * dx);
+          }
+          if (!wasteful) {
+            ref_box.push_back(tb);
+            ref_tri.push_back((int32_t)i);
+          } else {
+            SplitTriangle(tris[i].vertex, tb, (int32_t)i, max_extent, guard, &ref_box, &ref_tri);
+          }
+        }
+        // budget: at most half as many extra references as there are triangles (+ 4096 for small scenes with big walls)
+        if (ref_box.size() <= (size_t)n + (size_t)n / 2 + 4096 && ref_box.size() < 0x0fffffffu) break;
+        max_extent *= 2.0;
+      }
+    }
+    const int64_t n_refs = (int64_t)ref_box.size();
+    out->n_split_refs = n_refs - n;
+    if (scene_bvh == kSceneBvhHost) {
+      sb.ids.resize((size_t)n_refs);
+      std::iota(sb.ids.begin(), sb.ids.end(), 0);
+      Box3 whole;
+      if (n_refs <= kSceneBvhLeafSize) {
+        // a single leaf: the root holds it as its left child and an empty leaf on the right
+        double clo[3], chi[3];
+        RangeBounds(ref_box, sb.ids, 0, (int32_t)n_refs, &whole, clo, chi);
+        Bvh2Node root;
+        memset(&root, 0, sizeof(root));
+        for (int a = 0; a < 3; a++) {
+          root.lbox[a] = root.rbox[a] = RoundDown(whole.lo[a] - sb.pad);
+          root.lbox[3 + a] = root.rbox[3 + a] = RoundUp(whole.hi[a] + sb.pad);
+        }
+        root.left = ~(int32_t)(uint32_t)n_refs;  // first_gslot 0, count n_refs
+        root.right = ~0;                         // count 0
+        out->gnodes.push_back(root);
+      } else {
+        sb.Run(&out->gnodes, (int32_t)n_refs);
+      }
+      out->gbvh_depth = sb.max_depth;
+      if (sb.max_depth > kSceneBvhMaxDepth) out->gnodes.clear();
+    }
+    ms_tree = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tt0).count();
+  };
+  std::thread tree_thread;
+  const bool tree_wanted = use_scene_bvh && n > 0;
+  if (tree_wanted && n >= 65536 && std::thread::hardware_concurrency() > 2) tree_thread = std::thread(build_tree);
+  struct Joiner {  // (an error return below must not leave the thread running)
+    std::thread *t;
+    ~Joiner() {
+      if (t->joinable()) t->join();
+    }
+  } joiner{&tree_thread};
+
   const int rc = SplitAll(tri_box, &nodes, &out->depth, err);
   if (rc != MTB_OK) return rc;
-  lap("octree (AttemptSplit)");
+  lap("octree (AttemptSplit)", &out->ms_octree);
 
   // ---- flatten ----
   out->nodes.assign(nodes.size(), NodeRec{});
@@ -506,12 +796,6 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
   out->root_list = (int64_t)nodes[0].list.size();
   out->biggest_list = 0;
   out->interior = 0;
-  out->max_abs_coord = 0.0;
-  for (int a = 0; a < 3; a++) {
-    out->aabb[a] = nodes[0].box.lo[a];
-    out->aabb[3 + a] = nodes[0].box.hi[a];
-    out->max_abs_coord = std::max(out->max_abs_coord, std::max(std::fabs(nodes[0].box.lo[a]), std::fabs(nodes[0].box.hi[a])));
-  }
   std::vector<int32_t> slot_of((size_t)n, -1);
   // Every node's list is independent (its slots, its list-BVH), so the nodes are handed out in batches to a pool of
   // threads; each thread builds its list-BVHs into its own arena, and the arenas are stitched together in node
@@ -629,82 +913,30 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
     subtree[i] = total;
   }
 
-  lap("flatten + list BVHs");
-  // ---- scene BVH of the certified fast traversal ----
-  out->gnodes.clear();
-  out->gslots.clear();
-  out->gbvh_depth = 0;
-  if (use_scene_bvh && n > 0) {
-    // references: one per triangle, several for triangles much larger than the scene's grain (see SplitTriangle)
-    std::vector<Box3> ref_box;
-    std::vector<int32_t> ref_tri;
-    {
-      double scene_ext = 0.0;
-      for (int a = 0; a < 3; a++) scene_ext = std::max(scene_ext, out->aabb[3 + a] - out->aabb[a]);
-      const char *env = getenv("MTB_SPLIT_DIV");  // development knob: pieces of at most scene extent / div (0: no splitting)
-      const double div = env != nullptr ? atof(env) : 64.0;  // measured on C4 (B200): 16 -> 20.8 ms, 32 -> 12.1, 64 -> 7.6 (no splitting: 438)
-      double max_extent = div > 0.0 ? scene_ext / div : INFINITY;
-      const double guard = 1e-9 * std::max(out->max_abs_coord, 1e-30);
-      for (int attempt = 0; attempt < 8; attempt++) {
-        ref_box.clear();
-        ref_tri.clear();
-        ref_box.reserve((size_t)n + (size_t)n / 4);
-        ref_tri.reserve((size_t)n + (size_t)n / 4);
-        for (int64_t i = 0; i < n; i++) {
-          const Box3 &tb = tri_box[(size_t)i];
-          const double dx = tb.hi[0] - tb.lo[0], dy = tb.hi[1] - tb.lo[1], dz = tb.hi[2] - tb.lo[2];
-          const double ext = std::max(std::max(dx, dy), dz);
-          // Only boxes that are mostly empty are worth several references: a long triangle that runs diagonally
-          // through its box (area far below the box's cross sections).  A big axis-aligned wall triangle fills half
-          // of its flat box; splitting those only deepens the tree (measured on C3: +4 % node visits, no gain).
-          bool wasteful = false;
-          if (ext > max_extent) {
-            const double *v = tris[i].vertex;
-            const double e1[3] = {v[3] - v[0], v[4] - v[1], v[5] - v[2]}, e2[3] = {v[6] - v[0], v[7] - v[1], v[8] - v[2]};
-            const double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
-            const double tri_area = 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
-            wasteful = tri_area < 0.125 * (dx * dy + dy * dz + dz * dx);
-          }
-          if (!wasteful) {
-            ref_box.push_back(tb);
-            ref_tri.push_back((int32_t)i);
-          } else {
-            SplitTriangle(tris[i].vertex, tb, (int32_t)i, max_extent, guard, &ref_box, &ref_tri);
-          }
-        }
-        // budget: at most half as many extra references as there are triangles (+ 4096 for small scenes with big walls)
-        if (ref_box.size() <= (size_t)n + (size_t)n / 2 + 4096 && ref_box.size() < 0x0fffffffu) break;
-        max_extent *= 2.0;
-      }
+  lap("flatten + list BVHs", &out->ms_flatten);
+  // ---- scene BVH, part 2: what needs both the tree and the slot order of the octree lists ----
+  if (tree_wanted) {
+    if (tree_thread.joinable()) {
+      tree_thread.join();
+    } else {
+      build_tree();
     }
     const int64_t n_refs = (int64_t)ref_box.size();
-    out->n_split_refs = n_refs - n;
-    SceneBvhBuilder sb{ref_box, {}, 0, 0x1p-16 * out->max_abs_coord * 1.000001, {}};
-    sb.ids.resize((size_t)n_refs);
-    std::iota(sb.ids.begin(), sb.ids.end(), 0);
-    Box3 whole;
-    if (n_refs <= kSceneBvhLeafSize) {
-      // a single leaf: the root holds it as its left child and an empty leaf on the right
-      double clo[3], chi[3];
-      RangeBounds(ref_box, sb.ids, 0, (int32_t)n_refs, &whole, clo, chi);
-      Bvh2Node root;
-      memset(&root, 0, sizeof(root));
-      for (int a = 0; a < 3; a++) {
-        root.lbox[a] = root.rbox[a] = RoundDown(whole.lo[a] - sb.pad);
-        root.lbox[3 + a] = root.rbox[3 + a] = RoundUp(whole.hi[a] + sb.pad);
+    if (scene_bvh == kSceneBvhRefs) {
+      out->ref_box.resize((size_t)n_refs * 6);
+      out->ref_slot.resize((size_t)n_refs);
+      for (int64_t r = 0; r < n_refs; r++) {
+        for (int a = 0; a < 3; a++) {
+          out->ref_box[(size_t)r * 6 + a] = ref_box[(size_t)r].lo[a];
+          out->ref_box[(size_t)r * 6 + 3 + a] = ref_box[(size_t)r].hi[a];
+        }
+        out->ref_slot[(size_t)r] = slot_of[(size_t)ref_tri[(size_t)r]];
       }
-      root.left = ~(int32_t)(uint32_t)n_refs;  // first_gslot 0, count n_refs
-      root.right = ~0;                    // count 0
-      out->gnodes.push_back(root);
-    } else {
-      sb.Run(&out->gnodes, (int32_t)n_refs);
-    }
-    out->gbvh_depth = sb.max_depth;
-    if (sb.max_depth > kSceneBvhMaxDepth) {
-      out->gnodes.clear();
-    } else {
+    } else if (!out->gnodes.empty()) {
       out->gslots.resize((size_t)n_refs);
-      for (int64_t i = 0; i < n_refs; i++) out->gslots[(size_t)i] = out->slots[(size_t)slot_of[(size_t)ref_tri[(size_t)sb.ids[(size_t)i]]]];
+      ParallelSlices(0, (int32_t)n_refs, n_refs >= 65536 ? sb.par_threads : 1u, [&](unsigned, int32_t sb_, int32_t se_) {
+        for (int32_t i = sb_; i < se_; i++) out->gslots[(size_t)i] = out->slots[(size_t)slot_of[(size_t)ref_tri[(size_t)sb.ids[(size_t)i]]]];
+      });
     }
   }
   if (timing && !out->gnodes.empty()) {
@@ -735,7 +967,10 @@ int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool 
     fprintf(stderr, "[mtb] scene BVH SAH: expected node visits %.2f, expected triangle tests %.2f per random ray\n",
             1.0 + inner / root, leaf / root);
   }
-  lap("scene BVH");
+  lap(scene_bvh == kSceneBvhRefs ? "scene BVH references (join)" : "scene BVH (join + leaf records)", &out->ms_scene_bvh);
+  out->ms_scene_bvh_thread = ms_tree;
+  out->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build0).count();
+  if (timing) fprintf(stderr, "[mtb] %-28s %8.1f ms (on its own thread, overlapping the octree stages)\n", "  scene BVH tree build", ms_tree);
   return MTB_OK;
 }
 

@@ -83,7 +83,17 @@ struct FlatScene {
   std::vector<Bvh2Node> gnodes;     // scene BVH, node 0 = root (empty: no fast traversal)
   std::vector<SlotRec> gslots;      // copies of `slots` in scene-BVH leaf order: one per REFERENCE (a triangle much larger
                                     // than the scene's grain is referenced from several leaves, see SplitTriangle)
-  int64_t n_split_refs = 0;         // gslots.size() - slots.size()
+  int64_t n_split_refs = 0;         // references - triangles
+  // What a DEVICE-side build of the scene BVH needs (device_build.cu): the exact FP64 box of every reference
+  // (6 doubles each), the canonical slot of the triangle behind it, and the padding of the stored boxes.
+  std::vector<double> ref_box;
+  std::vector<int32_t> ref_slot;
+  double bvh_pad = 0.0;
+  // host stages of the last build, milliseconds (time to first frame)
+  // (the scene BVH's tree is built on its own thread WHILE the octree is split and flattened: ms_scene_bvh is what was
+  // left to wait for afterwards plus the leaf-record gather, ms_scene_bvh_thread the build itself, ms_total the wall
+  // time of the whole host build)
+  double ms_octree = 0.0, ms_flatten = 0.0, ms_scene_bvh = 0.0, ms_scene_bvh_thread = 0.0, ms_total = 0.0;
   int32_t gbvh_depth = 0;
   int32_t depth = 0;
   int64_t root_list = 0, biggest_list = 0, interior = 0;
@@ -109,7 +119,10 @@ constexpr int kBvhMinList = MTB_BVH_MIN_LIST;  // shorter lists are scanned line
 // leaf 2 min 3: 35.5 / 41.8; leaf 3 min 4: 35.6 / 42.0; leaf 1 min 2: 37.9 / 44.9; leaf 6 min 16: 43.7 / 51.4
 
 // Returns MTB_OK or an error code with text in *err.
-int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, bool use_scene_bvh, FlatScene *out,
+// scene_bvh: kSceneBvhNone, kSceneBvhHost (binned SAH on the host threads: gnodes / gslots are filled) or kSceneBvhRefs
+// (only the references are prepared; the tree is built on the device).
+enum SceneBvhMode { kSceneBvhNone = 0, kSceneBvhHost = 1, kSceneBvhRefs = 2 };
+int BuildFlatScene(const mtb_triangle *tris, int64_t n, bool use_list_bvh, SceneBvhMode scene_bvh, FlatScene *out,
                    std::string *err);
 
 // Camera::GetSensor / Sensor::Reset (camera.cc:17-63): out9 = start_point, delta_scanline, delta_pixel.

@@ -28,6 +28,8 @@
 //
 // Because every activation keeps its own colour and the fold replays the reference's additions in the
 // reference's order, the result is bit-identical to the megakernel (and to the reference, up to pow()).
+#include <cstdlib>
+
 #include "device_core.cuh"
 
 namespace mtb {
@@ -471,9 +473,14 @@ __global__ void WfCommit(WfBuffers wf, unsigned long long *global, uint32_t *hos
 // Lanes per warp for a queue of `n` items: full warps once the queue fills the machine (148 SMs x 32
 // resident warps), otherwise the largest power of two that still spreads it over all warp slots.
 static int PackLanes(long long n) {
+  static const int min_lanes = []() {
+    const char *env = getenv("MTB_WF_MIN_LANES");  // development knob (A/B of the packing)
+    const int v = env != nullptr ? atoi(env) : 4;
+    return v >= 1 && v <= 32 ? v : 4;
+  }();
   const long long slots = 148LL * 32;
   int lanes = 32;
-  while (lanes > 4 && n < slots * lanes) lanes >>= 1;
+  while (lanes > min_lanes && n < slots * lanes) lanes >>= 1;
   return lanes;
 }
 

@@ -175,3 +175,51 @@ def test_tiles_stored_into_another_process_frame(product_lib, scene_dir):
     assert np.array_equal(got, ref)
     mt.frame_release(ptr)
     mt.close()
+
+
+def test_device_built_scene_bvh(product_lib, oracle_mod, scene_dir):
+    """with MTB_FLAG_DEVICE_BVH the scene BVH is built ON the device (PLOC,
+    csrc/device_build.cu).  The tree read back from the device must have the properties the certified traversal
+    relies on (every triangle referenced, child boxes contain what is below them, split references cover their
+    triangle); a render over it must be the oracle's, and the same bytes as over the host-built tree - which tree is
+    walked can only change the speed.  (The full-size C3 frame over the device-built tree is compared with the
+    reference's render in test_c3_device_built_tree_equals_the_reference.)"""
+    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_DEVICE_BVH, MTB_FLAG_MEGAKERNEL
+    from tests.bvh_check import check_scene_bvh
+    for name, scale in (("C1", 1.0), ("C4", 0.02)):
+        files, cfg = scenes.config_scene(name, scene_dir, scale)
+        mt = MythTracer(max_depth=cfg["depth"], flags=MTB_FLAG_MEGAKERNEL | MTB_FLAG_DEVICE_BVH)
+        assert mt.LoadObj(files.obj_path), mt.last_error()
+        timing = mt.load_timing()
+        assert timing["scene_bvh_on_device"] and timing["scene_bvh_device_ms"] > 0.0
+        check_scene_bvh(mt, mt.scene_arrays()[0], expect_splits=True)
+        mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]
+        w, h = 160, 120
+        dev = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
+        orc = oracle_mod.Oracle.from_obj(files.obj_path)
+        orc.set_lights(files.lights)
+        cpu = orc.render(files.camera, w, h, depth=cfg["depth"], taps=True)
+        for k in ("line_no", "n_rays", "sig_hits", "sig_shadow"):
+            assert np.array_equal(dev[k], cpu[k]), (name, k)
+        assert np.abs(dev["rgb"].astype(int) - cpu["rgb"].astype(int)).max() <= MAX_RGB_DIFF
+        mt.set_flags(MTB_FLAG_MEGAKERNEL)
+        assert not mt.load_timing()["scene_bvh_on_device"]
+        host = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
+        for k in ("rgb", "line_no", "n_rays", "sig_hits", "sig_shadow"):
+            assert np.array_equal(dev[k], host[k]), (name, k)
+        mt.close()
+
+
+def test_c3_device_built_tree_equals_the_reference(product_lib, scene_dir):
+    """The whole C3 frame rendered over the DEVICE-built scene BVH against the reference's own render."""
+    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_DEVICE_BVH, MTB_FLAG_MEGAKERNEL
+    z, files, cfg = _golden("C3", scene_dir)
+    W, H = cfg["width"], cfg["height"]
+    mt = MythTracer(max_depth=cfg["depth"], flags=MTB_FLAG_MEGAKERNEL | MTB_FLAG_DEVICE_BVH)
+    assert mt.LoadObj(files.obj_path), mt.last_error()
+    assert mt.load_timing()["scene_bvh_on_device"]
+    mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]
+    got = mt.render_chunk(files.camera, W, H, 0, 0, W, H, debug=True)
+    _compare(got["rgb"], got["line_no"], z, "C3 over the device-built tree")
+    assert _sha(got["points"]) == str(z["points_sha256"])
+    mt.close()

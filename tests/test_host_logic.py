@@ -96,6 +96,41 @@ def test_loader_quirks(product_lib, oracle_mod, scene_dir):
     assert not ok and "out of range" in mt.last_error()
 
 
+def test_loader_result_does_not_depend_on_the_chunking(product_lib, scene_dir, tmp_path, monkeypatch):
+    """The OBJ reader parses the file in chunks on several threads (obj_loader.cc); triangles, their order, materials
+    and 0-based line numbers (pieces of 127 bytes count as lines, objreader.cc:233-235) must be those of a sequential
+    read, whatever the chunking - including over-long lines, a usemtl in front of its mtllib, CR LF line ends, and the
+    error a sequential reader would meet first."""
+    from mythtracer_b200 import MythTracer
+    from tests import scenes
+    files, cfg = scenes.config_scene("C2", scene_dir, 0.1)
+    quirky = tmp_path / "quirky.obj"
+    body = ["usemtl matte", "mtllib quirky.mtl", "# " + "x" * 300, "v 0 0 0", "v 1 0 0\r", "v 0 1 0", "vn 0 0 1", "usemtl matte",
+            "f 1//1 2//1 3//1 ", "o thing", "v 0 0 1" + " " * 200, "usemtl nowhere", "f 1 2 4 ", "usemtl mirror", "f 1 2 3 4 "]
+    body += ["v %d 0.5 0.25" % i for i in range(400)] + ["f 5 6 7 ", "f 2 3 400 "]
+    quirky.write_text("\n".join(body) + "\n")
+    (tmp_path / "quirky.mtl").write_text(scenes.BASIC_MTL)
+    broken = tmp_path / "broken.obj"
+    broken.write_text("\n".join(["v 0 0 0", "v 1 0 0", "v 0 1 0", "f 1 2 3 "] * 50 + ["f 1 2 900 "] + ["v 1 1 1"] * 900 + ["v oops"]) + "\n")
+    results = {}
+    for threads in ("1", "3", "16"):
+        monkeypatch.setenv("MTB_LOADER_THREADS", threads)
+        for path in (files.obj_path, str(quirky)):
+            mt = MythTracer(host_only=True)
+            assert mt.LoadObj(path), mt.last_error()
+            tris, mtls = mt.scene_arrays()
+            key = os.path.basename(path)
+            if key in results:
+                assert np.array_equal(results[key][0], tris) and np.array_equal(results[key][1], mtls), (key, threads)
+            results[key] = (tris, mtls)
+        mt = MythTracer(host_only=True)
+        assert not mt.LoadObj(str(broken))
+        assert "index out of range" in mt.last_error(), mt.last_error()  # the earlier of the two errors
+    q = results["quirky.obj"][0]
+    assert len(q) == 6 and q["material"].tolist()[:2] == [0, -1]  # first usemtl precedes its mtllib: unknown at that point -> none
+    assert q["line_no"][0] > 8  # the 300-character comment counts as three lines
+
+
 @pytest.mark.parametrize("name,scale", [("C1", 1.0), ("C2", 0.2), ("C4", 0.02)])
 def test_octree_builder_matches_oracle(product_lib, oracle_mod, scene_dir, name, scale):
     """Same boxes, same list membership, same depth as the reference rules (octtree.cc:46-135)."""
@@ -198,57 +233,7 @@ def test_scene_bvh_is_a_conservative_partition(product_lib, scene_dir):
     import sys
     sys.setrecursionlimit(10000)
 
-    def check(mt, tris, expect_splits=None):
-        nodes, depth, order = mt.scene_bvh()
-        n = len(tris)
-        if n == 0:
-            assert len(nodes) == 0
-            return
-        refs = np.bincount(order, minlength=n)
-        assert len(refs) == n and np.all(refs >= 1), "every triangle must be referenced from a leaf"
-        assert mt.scene_info()["n_scene_refs"] == len(order)
-        if expect_splits is not None:
-            assert (refs.max() > 1) == expect_splits
-        v = tris["vertex"].reshape(n, 3, 3)
-        lo, hi = v.min(axis=1), v.max(axis=1)
-        leaf_boxes = {}  # triangle -> list of the (lo, hi) boxes of the leaves that reference it
-        max_depth = 0
-
-        def walk(ref, box, d):
-            """`box` = the box the parent stores for this child; returns nothing, asserts containment"""
-            nonlocal max_depth
-            max_depth = max(max_depth, d)
-            b_lo, b_hi = box[:3].astype(np.float64), box[3:].astype(np.float64)
-            if ref < 0:
-                x = (~ref) & 0xFFFFFFFF
-                first, count = x >> 3, x & 7
-                for t in order[first:first + count]:
-                    if refs[t] == 1:
-                        assert np.all(b_lo <= lo[t]) and np.all(b_hi >= hi[t]), "leaf box must contain its triangle"
-                    else:
-                        assert np.all(b_lo <= hi[t]) and np.all(b_hi >= lo[t]), "a reference's box must touch its triangle"
-                        leaf_boxes.setdefault(int(t), []).append((b_lo, b_hi))
-                return
-            nd = nodes[ref]
-            for cbox, child in ((nd["lbox"], int(nd["left"])), (nd["rbox"], int(nd["right"]))):
-                if child >= 0 or ((~child) & 7) > 0:
-                    assert np.all(box[:3] <= cbox[:3]) and np.all(box[3:] >= cbox[3:]), "a child box must lie inside its parent's"
-                walk(child, cbox, d + 1)
-
-        root = nodes[0]
-        whole = np.concatenate([np.minimum(root["lbox"][:3], root["rbox"][:3]), np.maximum(root["lbox"][3:], root["rbox"][3:])])
-        walk(0, whole, 0)
-        assert max_depth <= depth + 1
-        # split triangles: points all over the triangle must lie in one of its references' boxes
-        rng = np.random.default_rng(3)
-        w = rng.dirichlet(np.ones(3), 64)
-        w = np.concatenate([w, np.eye(3), [[0.5, 0.5, 0.0], [0.0, 0.5, 0.5], [0.5, 0.0, 0.5]]])
-        for t, boxes in list(leaf_boxes.items())[:400]:
-            pts = w @ v[t]
-            b_lo = np.array([b[0] for b in boxes])
-            b_hi = np.array([b[1] for b in boxes])
-            inside = np.all((pts[:, None, :] >= b_lo[None]) & (pts[:, None, :] <= b_hi[None]), axis=2).any(axis=1)
-            assert inside.all(), "the references of a split triangle must cover it"
+    from tests.bvh_check import check_scene_bvh as check
 
     files, cfg = scenes.config_scene("C1", scene_dir)
     mt = MythTracer(host_only=True)

@@ -10,7 +10,7 @@ out = []
 for name in names:
     files, cfg = scenegen.generate_config(name, "/tmp/mtb_scenes")
     for mode in modes:
-        base_flags = {"bvh": 16, "nobvh": MTB_FLAG_NO_LIST_BVH | 16, "wf": MTB_FLAG_WAVEFRONT, "wfsort": MTB_FLAG_WAVEFRONT | 8, "auto": 0, "noorder": 16 | 32, "persist": 16 | 64, "exact": 16 | 128, "pack": 16 | 256, "sync": 16 | 512, "resume": 16 | 1024, "hybrid": 2048, "wfexact": 4 | 128}.get(mode, 0)
+        base_flags = {"bvh": 16, "nobvh": MTB_FLAG_NO_LIST_BVH | 16, "wf": MTB_FLAG_WAVEFRONT, "wfsort": MTB_FLAG_WAVEFRONT | 8, "auto": 0, "noorder": 16 | 32, "persist": 16 | 64, "exact": 16 | 128, "pack": 16 | 256, "sync": 16 | 512, "resume": 16 | 1024, "hybrid": 2048, "wfexact": 4 | 128, "devbvh": 16 | 4096}.get(mode, 0)
         mt = MythTracer(max_depth=cfg["depth"], flags=base_flags)
         t0 = time.time(); assert mt.LoadObj(files.obj_path); t_load = time.time() - t0
         mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]
@@ -31,7 +31,7 @@ for name in names:
                                 bvh=round(c["n_bvh"] / rays, 1), mt=round(c["n_mt"] / rays, 2), hit=round(c["n_hit"] / rays, 2), shade=round(c["n_shade"] / rays, 2)),
                    literal=c["n_literal"], fast=c["n_fast"], fallback=c["n_fallback"], count_kernel_ms=round(c["kernel_ms"], 1), all_ms=all_ms,
                    long128=dict(rays=c["n_long128_rays"], visits=c["n_long128_visits"]), long512=dict(rays=c["n_long512_rays"], visits=c["n_long512_visits"]),
-                   total_visits=c["n_bvh"] // 2)
+                   total_visits=c["n_bvh"] // 2, load=mt.load_timing())
         print(json.dumps(rec), flush=True)
         out.append(rec)
         mt.close()

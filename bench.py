@@ -308,7 +308,7 @@ def time_other_workloads(names, steps):
             mt.render_device(files.camera, W, H, d_frame.data_ptr(), stream.cuda_stream)
             torch.cuda.synchronize(dev)
             first_frame_s = time.time() - t0
-            for _ in range(7):  # automatic pipeline choice: six measuring frames
+            for _ in range(14):  # automatic pipeline choice: twelve measuring frames
                 mt.render_device(files.camera, W, H, d_frame.data_ptr(), stream.cuda_stream)
             torch.cuda.synchronize(dev)
             mt.read_counters()
@@ -456,7 +456,7 @@ def _run_ours(args):
 
     # ---- warm-up, then K timed steps (device-resident).  The automatic pipeline choice measures both
     # pipelines and the hybrid split during the first six frames of a geometry, so the warm-up covers at least seven ----
-    n_warm = max(args.warmup, 7 if args.pipeline == "auto" else 3)
+    n_warm = max(args.warmup, 14 if args.pipeline == "auto" else (10 if args.pipeline == "hybrid" else 3))
     for _ in range(n_warm):
         step_device()
     barrier()
@@ -626,7 +626,7 @@ def _run_ours(args):
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": config_dict(files, cfg, world * inproc, {"launch": launch, "gather": gather,
-                                                           "pipeline": pipeline_used, "pipeline_choice": args.pipeline, "autotune_ms": {"mega": tune_mega_ms, "wavefront": tune_wf_ms},
+                                                           "pipeline": pipeline_used, "pipeline_choice": args.pipeline, "hybrid_share": mt.hybrid_share(), "autotune_ms": {"mega": tune_mega_ms, "wavefront": tune_wf_ms},
                                                            "rays_per_frame": rays_per_frame, "scene_load_s": load_s, "load_stages_ms": load_stages,
                                                            "octree_nodes": info["n_nodes"], "tree_depth": info["tree_depth"],
                                                            "device_scene_bytes": info["device_bytes"], "commit": git_head(),

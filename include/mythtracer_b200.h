@@ -122,7 +122,7 @@ typedef struct {
 /* Pipeline choice.  With none of the three bits set the library decides at run time: on the first frames of a
  * given geometry (chunk size, partition, depth, light count) it times the per-pixel megakernel (second frame, once
  * its cost-aware tile order is warm), the wavefront pipeline (fourth frame, once its buffers exist) and the hybrid
- * split (sixth frame) and keeps the fastest from the seventh frame on.  All three produce identical bytes, so the
+ * split (frames 5 to 12, while the split settles; the last one is timed) and keeps the fastest from frame 13 on.  All three produce identical bytes, so the
  * choice is invisible in the output. */
 #define MTB_FLAG_WAVEFRONT 4u    /* force the wavefront pipeline */
 #define MTB_FLAG_MEGAKERNEL 16u  /* force the per-pixel megakernel */
@@ -254,6 +254,9 @@ int mtb_read_counters(mtb_context *ctx, mtb_stats *stats);
 /* Automatic pipeline choice on device 0: 0 = megakernel, 1 = wavefront, 2 = hybrid, -1 = still measuring; the
  * timed megakernel / wavefront frames (ms) are returned when the pointers are non-NULL. */
 int mtb_pipeline_in_use(const mtb_context *ctx, float *mega_ms, float *wavefront_ms);
+/* Hybrid frames: the share of the frame's rays that currently goes through the wavefront on device 0 (steered frame by
+ * frame from the measured times of the two halves). */
+float mtb_hybrid_share(const mtb_context *ctx);
 /* Number of kernels of this library launched on this context so far (bench.py's gpu_launches). */
 uint64_t mtb_launch_count(const mtb_context *ctx);
 

@@ -75,7 +75,7 @@ EXPORTED_SYMBOLS = [
     "mtb_set_lights", "mtb_scene_info", "mtb_scene_read", "mtb_scene_material_name", "mtb_scene_texture_name", "mtb_scene_texture", "mtb_load_mtl",
     "mtb_scene_triangle_nodes", "mtb_scene_bvh", "mtb_set_flags", "mtb_set_partition", "mtb_render_chunk",
     "mtb_render_chunk_device", "mtb_render_chunk_async", "mtb_wait", "mtb_host_alloc", "mtb_host_free", "mtb_read_counters", "mtb_launch_count", "mtb_pipeline_in_use", "mtb_intersect_rays", "mtb_camera_sensor", "mtb_version",
-    "mtb_frame_create", "mtb_frame_open", "mtb_frame_release", "mtb_frame_read", "mtb_load_timing",
+    "mtb_frame_create", "mtb_frame_open", "mtb_frame_release", "mtb_frame_read", "mtb_load_timing", "mtb_hybrid_share",
 ]
 
 
@@ -134,6 +134,8 @@ def load_library():
     lib.mtb_intersect_rays.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp]
     lib.mtb_camera_sensor.argtypes = [vp, i32, i32, vp]
     lib.mtb_wait.argtypes = [vp]
+    lib.mtb_hybrid_share.argtypes = [vp]
+    lib.mtb_hybrid_share.restype = ctypes.c_float
     lib.mtb_load_timing.argtypes = [vp, vp]
     lib.mtb_frame_create.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp), vp]
     lib.mtb_frame_open.argtypes = [vp, vp, ctypes.POINTER(vp)]
@@ -512,6 +514,9 @@ class MythTracer:
         rc = self._lib.mtb_pipeline_in_use(self._ctx, ctypes.cast(ctypes.byref(a), ctypes.c_void_p),
                                            ctypes.cast(ctypes.byref(b), ctypes.c_void_p))
         return {0: "mega", 1: "wavefront", 2: "hybrid"}.get(rc, "measuring"), a.value, b.value
+
+    def hybrid_share(self) -> float:
+        return float(self._lib.mtb_hybrid_share(self._ctx))
 
     def launch_count(self) -> int:
         return int(self._lib.mtb_launch_count(self._ctx))

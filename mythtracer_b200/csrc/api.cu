@@ -108,7 +108,9 @@ struct DeviceState {
   // hybrid frames: the most expensive tiles go through the wavefront while the megakernel renders the rest
   DeviceBuffer<int32_t> heavy_k;
   cudaStream_t hybrid_stream = nullptr;
-  cudaEvent_t ev_split = nullptr, ev_mega_done = nullptr;
+  cudaEvent_t ev_split = nullptr, ev_mega_done = nullptr, ev_wf_done = nullptr;  // (timed: they steer the split)
+  float hybrid_share = 0.30f;     // share of the frame's rays that goes through the wavefront; steered frame by frame
+  bool hybrid_timed = false;      // the three events above were recorded by the previous hybrid frame
   // intersect scratch
   DeviceBuffer<double> q_origins, q_dirs, q_t, q_point;
   DeviceBuffer<int32_t> q_tri;
@@ -145,7 +147,8 @@ struct DeviceState {
     hybrid_stream = nullptr;
     if (ev_split != nullptr) cudaEventDestroy(ev_split);
     if (ev_mega_done != nullptr) cudaEventDestroy(ev_mega_done);
-    ev_split = ev_mega_done = nullptr; q_origins.Free(); q_dirs.Free(); q_t.Free(); q_point.Free(); q_tri.Free();
+    if (ev_wf_done != nullptr) cudaEventDestroy(ev_wf_done);
+    ev_split = ev_mega_done = ev_wf_done = nullptr; q_origins.Free(); q_dirs.Free(); q_t.Free(); q_point.Free(); q_tri.Free();
     for (int k = 0; k < 2; k++) {
       wf_rq_o[k].Free(); wf_rq_d[k].Free(); wf_rq_coef[k].Free(); wf_rq_path[k].Free(); wf_rq_pixel[k].Free();
       wf_rq_inobj[k].Free();
@@ -193,6 +196,7 @@ struct mtb_context {
   bool no_peer_store = false;         // MTB_NO_PEER_STORE=1: gather with peer copies instead of direct tile stores (A/B)
   int l2_persist_mb = 0;              // MTB_L2_PERSIST_MB=n: pin the scene BVH's nodes in n MB of persisting L2 (A/B)
   bool device_bvh = false;            // the scene BVH of the current scene was built on the devices (device_build.cu)
+  int64_t atlas_bytes = 0;            // layered texture array as allocated on a device
   double ms_parse = 0.0, ms_upload = 0.0, ms_device_bvh = 0.0;  // stages of the last load (mtb_load_timing)
   std::vector<void *> owned_frames, opened_frames;  // mtb_frame_create / mtb_frame_open
   std::mutex err_mutex;
@@ -288,6 +292,17 @@ int UploadToDevice(mtb_context *ctx, DeviceState *d) {
     }
     cudaChannelFormatDesc desc = cudaCreateChannelDesc<unsigned int>();  // one RGBA32 texel = one 32-bit word
     cudaArray_t arr = nullptr;
+    // every layer has the extent of the largest texture: what is really allocated is max_w * max_h * layers texels
+    // (mtb_scene_info reports that, not the sum of the images), and a scene that mixes one huge texture with many
+    // small ones is refused with a clear message instead of a bare CUDA allocation error
+    const size_t atlas_bytes = max_w * max_h * ctx->textures.size() * 4;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && atlas_bytes > free_b) {
+      ctx->err = "texture atlas of " + std::to_string(ctx->textures.size()) + " layers of " + std::to_string(max_w) + " x " +
+                 std::to_string(max_h) + " texels (" + std::to_string(atlas_bytes >> 20) + " MiB: every layer has the extent of the largest texture) does not fit the device";
+      return MTB_ERR_LIMIT;
+    }
+    ctx->atlas_bytes = (int64_t)atlas_bytes;
     MTB_CUDA(ctx, cudaMalloc3DArray(&arr, &desc, make_cudaExtent(max_w, max_h, ctx->textures.size()), cudaArrayLayered));
     d->tex_arrays.push_back(arr);
     for (size_t layer = 0; layer < ctx->textures.size(); layer++) {
@@ -402,7 +417,7 @@ int BuildAndUpload(mtb_context *ctx) {
                                 ctx->flat.gnodes.size() * sizeof(mtb::Bvh2Node) + ctx->flat.gslots.size() * sizeof(mtb::SlotRec) +
                                 ctx->flat.ref_slot.size() * (sizeof(mtb::SlotRec) + 8) +
                                 ctx->flat.list_order.size() * 4 + ctx->flat.slot_node.size() * 4 + ctx->materials.size() * sizeof(mtb_material));
-  for (const mtb::LoadedTexture &t : ctx->textures) ctx->device_bytes += (int64_t)t.rgba.size();
+  ctx->atlas_bytes = 0;
   const auto t_up = std::chrono::steady_clock::now();
   ctx->ms_device_bvh = 0.0;
   for (DeviceState &d : ctx->dev) {
@@ -411,6 +426,7 @@ int BuildAndUpload(mtb_context *ctx) {
   }
   ctx->ms_upload = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_up).count() - ctx->ms_device_bvh;
   if (ctx->device_bvh && !ctx->dev.empty()) ctx->device_bytes += (int64_t)(ctx->dev[0].gnodes.count * sizeof(mtb::Bvh2Node));
+  ctx->device_bytes += ctx->atlas_bytes;  // the layered texture array as allocated
   if (getenv("MTB_TIMING") != nullptr) fprintf(stderr, "[mtb] %-28s %8.1f ms\n", "upload", ctx->ms_upload);
   ctx->has_scene = true;
   return MTB_OK;
@@ -624,18 +640,16 @@ int RunWavefront(mtb_context *ctx, DeviceState *d, const mtb::RenderParams &p, i
   return MTB_OK;
 }
 
-// Hybrid frames: which tiles go through the wavefront.  Measured on B200 with C3 (one device rendering 1/1, 1/2, 1/4,
-// 1/8 of the frame; megakernel 9.1 / 6.35 / 5.13 / 4.54 ms, wavefront 11.5 / 6.46 / 3.81 / 2.49 ms):
-//   tiles of >= 2x the mean cost, at most 1/8 of the tiles:  9.8 / 5.5 / 3.75 / 3.2 ms
-//   tiles of >= 1x the mean cost, at most 1/4 of the tiles: 10.8 / 6.0 / 3.55 / 2.3 ms
-// so the smaller a device's share of the frame, the more of it the wavefront gets (80 tiles per SM is the C3 frame
-// cut in two or three).
-struct HybridSplit {
-  int cap_div, factor;
-};
-HybridSplit ChooseHybridSplit(int tiles, int sm_count) {
-  return tiles >= 80 * sm_count ? HybridSplit{8, 2} : HybridSplit{4, 1};
-}
+// Hybrid frames: which tiles go through the wavefront.  The megakernel's critical path is its most expensive pixel
+// (a serial chain of up to ~80 rays), the wavefront's is one ray per level but it pays ~1.3x the instructions, so the
+// most expensive tiles of the previous frame go to the wavefront and the rest to the megakernel, concurrently.  How
+// much is not a constant: round 1 used two fixed rules picked from a table measured on C3; now the share of the
+// frame's rays that the wavefront gets is STEERED - both halves are timed with events, and the share moves a step
+// towards whichever half finished first (no host wait: the events of the previous frame are only read if they have
+// completed).  At most half of the tiles can go to the wavefront (its queues are sized for that).
+constexpr int kTuneDecided = 13;  // frames 5..12 of a new geometry are hybrid frames
+constexpr float kHybridShareMin = 0.02f, kHybridShareMax = 0.90f, kHybridShareStep = 0.04f;
+int HybridMaxTiles(int tiles) { return tiles / 2; }
 
 // Core of both render entry points.  d_rgb_user: device-0 buffer to leave the pixels in (may be NULL when
 // rgb_host is given); user_stream: stream of device 0 to enqueue on (NULL = context stream).
@@ -739,23 +753,24 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
       if (tsig != d.tune_signature) {
         d.tune_signature = tsig;
         d.tune_stage = 0;
-      } else if (d.tune_stage == 2 || d.tune_stage == 4 || d.tune_stage == 6) {
+      } else if (d.tune_stage == 2 || d.tune_stage == 4 || d.tune_stage == kTuneDecided - 1) {
         // the previous frame was a timed one: harvest it
         float ms = 0.f;
         if (cudaEventSynchronize(d.ev_stop) == cudaSuccess && cudaEventElapsedTime(&ms, d.ev_start, d.ev_stop) == cudaSuccess) {
-          d.tune_ms[d.tune_stage / 2 - 1] = ms;
+          d.tune_ms[d.tune_stage == 2 ? 0 : (d.tune_stage == 4 ? 1 : 2)] = ms;
         }
-        if (d.tune_stage == 6) {
+        if (d.tune_stage == kTuneDecided - 1) {
           d.tune_choice = 0;
           if (d.tune_ms[1] < d.tune_ms[d.tune_choice]) d.tune_choice = 1;
           if (d.tune_ms[2] < d.tune_ms[d.tune_choice]) d.tune_choice = 2;
         }
       }
-      if (d.tune_stage < 7) d.tune_stage++;
+      if (d.tune_stage < kTuneDecided) d.tune_stage++;
       // stage now: 1 = megakernel (cold tile order), 2 = megakernel (timed), 3 = wavefront (cold: buffers are
-      // allocated), 4 = wavefront (timed), 5 = hybrid (cold), 6 = hybrid (timed), 7 = decided
-      wavefront = d.tune_stage == 3 || d.tune_stage == 4 || (d.tune_stage == 7 && d.tune_choice == 1);
-      hybrid = d.tune_stage == 5 || d.tune_stage == 6 || (d.tune_stage == 7 && d.tune_choice == 2);
+      // allocated), 4 = wavefront (timed), 5 .. kTuneDecided - 1 = hybrid (the split settles; the last one is timed),
+      // kTuneDecided = decided
+      wavefront = d.tune_stage == 3 || d.tune_stage == 4 || (d.tune_stage == kTuneDecided && d.tune_choice == 1);
+      hybrid = (d.tune_stage >= 5 && d.tune_stage < kTuneDecided) || (d.tune_stage == kTuneDecided && d.tune_choice == 2);
     }
     if (ctx->l2_persist_mb > 0 && d.l2_window_stream != s) {
       ApplyL2Window(ctx, &d, s);
@@ -781,16 +796,29 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
         MTB_CUDA(ctx, d.tile_order.Reserve((size_t)mblocks));
         p.tile_cost = d.tile_cost.ptr;
         const bool split = hybrid && mblocks >= 64;
-        const HybridSplit hs = ChooseHybridSplit(mblocks, d.sm_count);
         if (split) MTB_CUDA(ctx, d.heavy_k.Reserve(1));
+        if (split && d.hybrid_timed && d.ev_wf_done != nullptr && cudaEventQuery(d.ev_wf_done) == cudaSuccess &&
+            cudaEventQuery(d.ev_mega_done) == cudaSuccess) {
+          // steer the split with the previous hybrid frame: the half that took longer gives up work
+          float t_mega = 0.f, t_wf = 0.f;
+          if (cudaEventElapsedTime(&t_mega, d.ev_split, d.ev_mega_done) == cudaSuccess &&
+              cudaEventElapsedTime(&t_wf, d.ev_split, d.ev_wf_done) == cudaSuccess) {
+            if (t_wf > t_mega * 1.04f) d.hybrid_share -= kHybridShareStep;
+            if (t_mega > t_wf * 1.04f) d.hybrid_share += kHybridShareStep;
+            d.hybrid_share = std::min(kHybridShareMax, std::max(kHybridShareMin, d.hybrid_share));
+          }
+          cudaGetLastError();
+        }
         if (signature == d.tile_signature) {
-          mtb::LaunchBuildTileOrder(d.tile_cost.ptr, d.tile_order.ptr, mblocks, split ? d.heavy_k.ptr : nullptr, mblocks / hs.cap_div, hs.factor, s);
+          mtb::LaunchBuildTileOrder(d.tile_cost.ptr, d.tile_order.ptr, mblocks, split ? d.heavy_k.ptr : nullptr, HybridMaxTiles(mblocks),
+                                    (unsigned)(d.hybrid_share * 65536.0f), s);
           ctx->launches++;
           p.tile_order = d.tile_order.ptr;
           if (split) p.heavy_k = d.heavy_k.ptr;
         } else {
           MTB_CUDA(ctx, cudaMemsetAsync(d.tile_cost.ptr, 0, (size_t)mblocks * sizeof(uint32_t), s));
           d.tile_signature = signature;
+          d.hybrid_timed = false;
         }
       }
       if (p.heavy_k != nullptr) {
@@ -801,8 +829,9 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
         // pixels of the same buffers; the bytes do not depend on the split.
         if (d.hybrid_stream == nullptr) {
           MTB_CUDA(ctx, cudaStreamCreateWithFlags(&d.hybrid_stream, cudaStreamNonBlocking));
-          MTB_CUDA(ctx, cudaEventCreateWithFlags(&d.ev_split, cudaEventDisableTiming));
-          MTB_CUDA(ctx, cudaEventCreateWithFlags(&d.ev_mega_done, cudaEventDisableTiming));
+          MTB_CUDA(ctx, cudaEventCreate(&d.ev_split));
+          MTB_CUDA(ctx, cudaEventCreate(&d.ev_mega_done));
+          MTB_CUDA(ctx, cudaEventCreate(&d.ev_wf_done));
         }
         if (want_taps) {  // the wavefront kernels accumulate the taps with atomics
           MTB_CUDA(ctx, cudaMemsetAsync(d.sig_hits.ptr, 0, npx * 8, s));
@@ -815,8 +844,10 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
         ctx->launches++;
         MTB_CUDA(ctx, cudaGetLastError());
         MTB_CUDA(ctx, cudaEventRecord(d.ev_mega_done, d.hybrid_stream));
-        const int wrc = RunWavefront(ctx, &d, p, mblocks / ChooseHybridSplit(mblocks, d.sm_count).cap_div, debug_build, s);
+        const int wrc = RunWavefront(ctx, &d, p, HybridMaxTiles(mblocks), debug_build, s);
         if (wrc != MTB_OK) return wrc;
+        MTB_CUDA(ctx, cudaEventRecord(d.ev_wf_done, s));
+        d.hybrid_timed = true;
         MTB_CUDA(ctx, cudaStreamWaitEvent(s, d.ev_mega_done, 0));
       } else {
         mtb::LaunchRenderMega(d.scene, p, mblocks, debug_build, s);
@@ -1271,8 +1302,10 @@ int mtb_pipeline_in_use(const mtb_context *ctx, float *mega_ms, float *wavefront
   if ((ctx->flags & MTB_FLAG_WAVEFRONT) != 0) return 1;
   if ((ctx->flags & MTB_FLAG_HYBRID) != 0) return 2;
   if ((ctx->flags & MTB_FLAG_MEGAKERNEL) != 0) return 0;
-  return d.tune_stage >= 7 ? d.tune_choice : -1;
+  return d.tune_stage >= kTuneDecided ? d.tune_choice : -1;
 }
+
+float mtb_hybrid_share(const mtb_context *ctx) { return ctx == nullptr || ctx->dev.empty() ? 0.0f : ctx->dev[0].hybrid_share; }
 
 int mtb_read_counters(mtb_context *ctx, mtb_stats *stats) {
   if (ctx == nullptr || stats == nullptr) return MTB_ERR_ARG;

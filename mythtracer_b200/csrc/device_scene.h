@@ -124,9 +124,9 @@ void LaunchWfCommit(const WfBuffers &wf, unsigned long long *global, uint32_t *h
 
 // megakernel.cu
 // Builds tile_order (descending cost, bucketed) from tile_cost and clears tile_cost for the coming frame.
-// heavy_k (nullable): receives the number of leading tiles of the order whose cost is at least heavy_factor x the
-// mean (whole cost buckets, at most k_max).
-void LaunchBuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles, int32_t *heavy_k, int k_max, int heavy_factor,
+// heavy_k (nullable): receives the number of leading tiles of the order that carry heavy_share_q16 / 65536 of the
+// frame's rays (at most k_max tiles).
+void LaunchBuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles, int32_t *heavy_k, int k_max, unsigned heavy_share_q16,
                           cudaStream_t stream);
 // One 8x8 tile per 64-thread block; n_blocks = tiles of the launch (rp.tiles_x in units of 8 pixels).
 void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp, int n_blocks, bool debug_build, cudaStream_t stream);

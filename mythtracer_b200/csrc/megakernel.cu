@@ -449,18 +449,28 @@ __global__ void __launch_bounds__(128) IntersectKernel(DeviceScene sc, Intersect
 }
 
 // Counting sort of the tiles by cost bucket (log2 of the ray count, most expensive first).  One block.
-__global__ void __launch_bounds__(1024) BuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles, int32_t *heavy_k, int k_max, int heavy_factor) {
+// heavy_k (nullable): receives how many leading tiles of the order - the most expensive ones - together carry
+// `heavy_share_q16` / 65536 of the frame's rays (whole buckets, then part of the next one), at most k_max tiles: the
+// wavefront's side of a hybrid frame.
+__global__ void __launch_bounds__(1024) BuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles, int32_t *heavy_k, int k_max,
+                                                       unsigned heavy_share_q16) {
   __shared__ unsigned hist[33];
   __shared__ unsigned offset[33];
+  __shared__ unsigned long long bucket_cost[33];
   __shared__ unsigned long long total;
-  if (threadIdx.x < 33) hist[threadIdx.x] = 0;
+  if (threadIdx.x < 33) {
+    hist[threadIdx.x] = 0;
+    bucket_cost[threadIdx.x] = 0;
+  }
   if (threadIdx.x == 0) total = 0;
   __syncthreads();
   unsigned long long mine = 0;
   for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
     const unsigned c = tile_cost[t];
     mine += c;
-    atomicAdd(&hist[c == 0u ? 0 : 32 - __clz((int)c)], 1u);
+    const int b = c == 0u ? 0 : 32 - __clz((int)c);
+    atomicAdd(&hist[b], 1u);
+    atomicAdd(&bucket_cost[b], (unsigned long long)c);
   }
   atomicAdd(&total, mine);
   __syncthreads();
@@ -471,16 +481,21 @@ __global__ void __launch_bounds__(1024) BuildTileOrder(uint32_t *tile_cost, int3
       run += hist[b];
     }
     if (heavy_k != nullptr) {
-      // heavy = whole buckets [2^(b-1), 2^b) whose lower bound is at least heavy_factor x the mean cost, most
-      // expensive bucket first, as long as they fit into k_max tiles
-      const unsigned long long mean = n_tiles > 0 ? total / (unsigned long long)n_tiles : 0;
+      const unsigned long long want = (total >> 16) * heavy_share_q16 + (((total & 0xffffull) * heavy_share_q16) >> 16);
+      unsigned long long got = 0;
       int k = 0;
-      for (int b = 32; b >= 2; b--) {
-        if ((1ull << (b - 1)) < (unsigned long long)heavy_factor * mean || mean == 0) break;
-        if (k + (int)hist[b] > k_max) break;
-        k += (int)hist[b];
+      for (int b = 32; b >= 1 && got < want; b--) {
+        if (hist[b] == 0u) continue;
+        if (got + bucket_cost[b] <= want) {
+          got += bucket_cost[b];
+          k += (int)hist[b];
+        } else {  // part of this bucket (its tiles cost within a factor of two of each other)
+          const unsigned long long per_tile = bucket_cost[b] / hist[b] + 1ull;
+          k += (int)((want - got) / per_tile);
+          got = want;
+        }
       }
-      *heavy_k = k;
+      *heavy_k = k < k_max ? k : k_max;
     }
   }
   __syncthreads();
@@ -494,10 +509,10 @@ __global__ void __launch_bounds__(1024) BuildTileOrder(uint32_t *tile_cost, int3
 
 }  // namespace
 
-void LaunchBuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles, int32_t *heavy_k, int k_max, int heavy_factor,
+void LaunchBuildTileOrder(uint32_t *tile_cost, int32_t *tile_order, int n_tiles, int32_t *heavy_k, int k_max, unsigned heavy_share_q16,
                           cudaStream_t stream) {
   if (n_tiles <= 0) return;
-  BuildTileOrder<<<1, 1024, 0, stream>>>(tile_cost, tile_order, n_tiles, heavy_k, k_max, heavy_factor);
+  BuildTileOrder<<<1, 1024, 0, stream>>>(tile_cost, tile_order, n_tiles, heavy_k, k_max, heavy_share_q16);
 }
 
 // n_blocks = number of 8x8 tiles of the launch.

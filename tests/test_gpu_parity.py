@@ -446,12 +446,13 @@ def test_automatic_pipeline_choice(product_lib, oracle_mod, scene_dir):
     w, h = 320, 240
     cpu = orc.render(files.camera, w, h, depth=cfg["depth"])
     states = []
-    for _ in range(9):
+    for _ in range(15):
         out = mt.render_chunk(files.camera, w, h, 0, 0, w, h)
         assert np.array_equal(out["rgb"], cpu["rgb"])
         assert out["stats"]["rays"] == cpu["stats"]["rays"]
         states.append(mt.pipeline_in_use()[0])
-    assert states[0] == "measuring" and states[5] == "measuring" and states[-1] in ("mega", "wavefront", "hybrid")
+    assert states[0] == "measuring" and states[10] == "measuring" and states[-1] in ("mega", "wavefront", "hybrid")
+    assert 0.0 < mt.hybrid_share() < 1.0
     _, mega_ms, wf_ms = mt.pipeline_in_use()
     assert mega_ms > 0 and wf_ms > 0
     if states[-1] != "hybrid":
@@ -676,11 +677,14 @@ def test_hybrid_frames(product_lib, oracle_mod, scene_dir):
     W, H = cfg["width"], cfg["height"]
     ref = mt.render_chunk(files.camera, W, H, 0, 0, W, H, taps=True)
     mt.set_flags(MTB_FLAG_HYBRID)
-    for frame in range(3):
+    shares = []
+    for frame in range(6):  # (the share of the frame that goes to the wavefront is steered from frame to frame)
         got = mt.render_chunk(files.camera, W, H, 0, 0, W, H, taps=True)
+        shares.append(mt.hybrid_share())
         for k in ("rgb", "n_rays", "sig_hits", "sig_shadow"):
             assert np.array_equal(got[k], ref[k]), "C3 hybrid frame %d: %s" % (frame, k)
         assert got["stats"]["rays"] == ref["stats"]["rays"]
+    assert len(set(shares)) > 1, "the split must move"
 
 
 def test_sibling_entry_tie_on_the_device(product_lib, oracle_mod):

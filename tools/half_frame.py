@@ -14,10 +14,10 @@ buf = torch.zeros((tiles.padded_height(H, world), W, 3), dtype=torch.uint8, devi
 for rank in range(min(world, 2)):
     mt.set_partition(rank, world)
     ts = []
-    for it in range(6):
+    for it in range(16):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); e0.record(s)
         mt.render_device(files.camera, W, H, buf.data_ptr(), s.cuda_stream)
         e1.record(s); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     c = mt.read_counters()
-    print(json.dumps(dict(mode=mode, world=world, rank=rank, ms=round(min(ts), 2), rays_per_frame=c["rays"] // 4)))
+    print(json.dumps(dict(mode=mode, world=world, rank=rank, ms=round(min(ts[8:]), 2), first=round(ts[1], 2), share=round(mt.hybrid_share(), 2), rays_per_frame=c["rays"] // 16)))

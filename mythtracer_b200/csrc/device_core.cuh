@@ -596,6 +596,9 @@ __device__ __forceinline__ bool MollerTrumboreBound(const TriVerts &tv, const Ra
 #ifndef MTB_LEAF_PRELOAD
 #define MTB_LEAF_PRELOAD 1
 #endif
+#ifndef MTB_LD256
+#define MTB_LD256 1
+#endif
 // Traversal stack of TraceFast.  An entry is 64 bits: conservative entry distance (FP32 bits) << 32 | child
 // reference.  Short-stack form (north star item 3): the first MTB_SMEM_STACK entries of every thread live in shared
 // memory, laid out [entry][thread]; only deeper entries go to the thread's local array.  MTB_SMEM_STACK = 0 keeps
@@ -654,11 +657,24 @@ struct FastRay {
 template <bool DBG>
 __device__ __forceinline__ void TestSlotFast(const SlotRec *rec, Ray &r, const FastCtx &fc, FastMem *m, int *slot, float *prune,
                                              unsigned long long *cnt) {
+#if MTB_LD256 && MTB_LEAF_PRELOAD
+  // the whole 128-byte record (box, vertices, ids) in four 256-bit loads: one memory round trip per candidate
+  double2 b0, b1, b2;
+  TriVerts tv;
+  double ids_word;
+  {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(b0.x), "=d"(b0.y), "=d"(b1.x), "=d"(b1.y) : "l"(rec));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(b2.x), "=d"(b2.y), "=d"(tv.a.x), "=d"(tv.a.y) : "l"(reinterpret_cast<const char *>(rec) + 32));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(tv.b.x), "=d"(tv.b.y), "=d"(tv.c.x), "=d"(tv.c.y) : "l"(reinterpret_cast<const char *>(rec) + 64));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(tv.d.x), "=d"(tv.d.y), "=d"(tv.v22), "=d"(ids_word) : "l"(reinterpret_cast<const char *>(rec) + 96));
+  }
+#else
   const double2 b0 = Ld2(rec->box + 0), b1 = Ld2(rec->box + 2), b2 = Ld2(rec->box + 4);
 #if MTB_LEAF_PRELOAD
   // the vertices travel with the box (same 128-byte record): one memory round trip per candidate instead of two
   // for the 58 % of the candidates that pass the pre-test
   const TriVerts tv = LoadVerts(rec->vert);
+#endif
 #endif
   Count<DBG>(cnt, kTriAabb);
   double unused;
@@ -671,7 +687,11 @@ __device__ __forceinline__ void TestSlotFast(const SlotRec *rec, Ray &r, const F
   double t, e;
   if (!MollerTrumboreBound(tv, r, &t, &e)) return;
   Count<DBG>(cnt, kHit);
+#if MTB_LD256 && MTB_LEAF_PRELOAD
+  const int canon = __double2hiint(ids_word);  // SlotRec: tri (low word), canon (high word) behind the vertices
+#else
   const int canon = __ldg(&rec->canon);
+#endif
   if (canon == *slot) return;  // the best hit itself, met again through another of its references (spatial splits)
   if (*slot >= 0) {
     const double bt = FmLoad(fc, m, kFmT), lo2 = FmLoad(fc, m, kFmLo2);
@@ -803,9 +823,28 @@ __device__ __forceinline__ int TraceFast(const DeviceScene &sc, FastMem *m, cons
   for (;;) {
     while (node >= 0) {
       if (DBG) visits++;
+#if MTB_LD256
+      // one 64-byte node = two 256-bit loads (LDG.E.256, new with sm_100): half the L1 requests / wavefronts of four
+      // 128-bit loads when the lanes of a warp are at different nodes
+      float4 q0, q1, q2;
+      int2 kids;
+      {
+        const Bvh2Node *np_ = sc.gnodes + node;
+        float w8, w9, w10, w11;
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w), "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w)
+                     : "l"(np_));
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w), "=f"(w8), "=f"(w9), "=f"(w10), "=f"(w11)
+                     : "l"(reinterpret_cast<const char *>(np_) + 32));
+        kids.x = __float_as_int(w8);
+        kids.y = __float_as_int(w9);
+      }
+#else
       const float4 *q = reinterpret_cast<const float4 *>(sc.gnodes + node);
       const int2 kids = __ldg(reinterpret_cast<const int2 *>(q + 3));
       const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+#endif
 #if MTB_PREFETCH_KIDS
       // the next node of the walk is one of the two children: start both fetches now, the box tests take ~100 cycles
       if (kids.x >= 0) asm volatile("prefetch.global.L1 [%0];" : : "l"(sc.gnodes + kids.x));

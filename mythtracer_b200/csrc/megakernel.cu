@@ -456,23 +456,45 @@ __global__ void __launch_bounds__(1024) BuildTileOrder(uint32_t *tile_cost, int3
                                                        unsigned heavy_share_q16) {
   __shared__ unsigned hist[33];
   __shared__ unsigned offset[33];
-  __shared__ unsigned long long bucket_cost[33];
+  // (32-bit sums: 64-bit shared-memory atomics are CAS loops - with all tiles in two or three buckets they made this
+  // one-block kernel take 570 us per frame, 6 % of a C3 frame; a device's share of a frame stays far below 2^32 rays)
+  // Every warp counts into its own copy (atomics on one address are serialised; 1024 threads on two or three hot
+  // buckets took 33 us in round 1).
+  __shared__ unsigned bucket_cost[33];
   __shared__ unsigned long long total;
-  if (threadIdx.x < 33) {
-    hist[threadIdx.x] = 0;
-    bucket_cost[threadIdx.x] = 0;
+  __shared__ unsigned w_hist[32][33], w_cost[32][33];
+  for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) {
+    (&w_hist[0][0])[i] = 0;
+    (&w_cost[0][0])[i] = 0;
   }
-  if (threadIdx.x == 0) total = 0;
   __syncthreads();
-  unsigned long long mine = 0;
-  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+  // warp w owns the contiguous tiles [w * chunk, (w + 1) * chunk): inside a bucket the launch order then stays in
+  // tile order, i.e. blocks that run at the same time render neighbouring tiles
+  const unsigned warp = threadIdx.x >> 5;
+  const int chunk = (n_tiles + 31) / 32;
+  const int t_begin = (int)warp * chunk + (int)(threadIdx.x & 31u), t_end = min(n_tiles, ((int)warp + 1) * chunk);
+  for (int t = t_begin; t < t_end; t += 32) {
     const unsigned c = tile_cost[t];
-    mine += c;
     const int b = c == 0u ? 0 : 32 - __clz((int)c);
-    atomicAdd(&hist[b], 1u);
-    atomicAdd(&bucket_cost[b], (unsigned long long)c);
+    atomicAdd(&w_hist[warp][b], 1u);
+    atomicAdd(&w_cost[warp][b], c);
   }
-  atomicAdd(&total, mine);
+  __syncthreads();
+  if (threadIdx.x < 33) {
+    unsigned h = 0, c = 0;
+    for (int w = 0; w < 32; w++) {
+      h += w_hist[w][threadIdx.x];
+      c += w_cost[w][threadIdx.x];
+    }
+    hist[threadIdx.x] = h;
+    bucket_cost[threadIdx.x] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long sum = 0;
+    for (int b = 0; b <= 32; b++) sum += bucket_cost[b];
+    total = sum;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned run = 0;
@@ -486,11 +508,11 @@ __global__ void __launch_bounds__(1024) BuildTileOrder(uint32_t *tile_cost, int3
       int k = 0;
       for (int b = 32; b >= 1 && got < want; b--) {
         if (hist[b] == 0u) continue;
-        if (got + bucket_cost[b] <= want) {
-          got += bucket_cost[b];
+        if (got + (unsigned long long)bucket_cost[b] <= want) {
+          got += (unsigned long long)bucket_cost[b];
           k += (int)hist[b];
         } else {  // part of this bucket (its tiles cost within a factor of two of each other)
-          const unsigned long long per_tile = bucket_cost[b] / hist[b] + 1ull;
+          const unsigned long long per_tile = (unsigned long long)bucket_cost[b] / hist[b] + 1ull;
           k += (int)((want - got) / per_tile);
           got = want;
         }
@@ -499,9 +521,19 @@ __global__ void __launch_bounds__(1024) BuildTileOrder(uint32_t *tile_cost, int3
     }
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+  // positions: a bucket's range is cut into one piece per warp (what that warp counted), filled with warp-local atomics
+  if (threadIdx.x < 33) {
+    unsigned run = offset[threadIdx.x];
+    for (int w = 0; w < 32; w++) {
+      const unsigned h = w_hist[w][threadIdx.x];
+      w_hist[w][threadIdx.x] = run;
+      run += h;
+    }
+  }
+  __syncthreads();
+  for (int t = t_begin; t < t_end; t += 32) {
     const unsigned c = tile_cost[t];
-    const unsigned pos = atomicAdd(&offset[c == 0u ? 0 : 32 - __clz((int)c)], 1u);
+    const unsigned pos = atomicAdd(&w_hist[warp][c == 0u ? 0 : 32 - __clz((int)c)], 1u);
     tile_order[pos] = t;
     tile_cost[t] = 0;
   }

@@ -126,6 +126,7 @@ typedef struct {
  * choice is invisible in the output. */
 #define MTB_FLAG_WAVEFRONT 4u    /* force the wavefront pipeline */
 #define MTB_FLAG_MEGAKERNEL 16u  /* force the per-pixel megakernel */
+#define MTB_FLAG_QUEUE 8192u     /* force the queue pipeline: the wavefront as ONE persistent kernel over a single device-side ray queue (all levels) */
 #define MTB_FLAG_HYBRID 2048u    /* force hybrid frames: the tiles that were most expensive in the previous frame go through the wavefront, the rest through the megakernel, concurrently */
 #define MTB_FLAG_EXACT_OCTREE 128u /* every regular ray walks the octree in the reference's recursion order (no certified fast traversal) */
 /* Retired A/B forms of round 1 (all bit-identical, all measured slower on B200; DESIGN.md section 5 keeps the

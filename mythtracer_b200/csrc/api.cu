@@ -130,6 +130,10 @@ struct DeviceState {
   cudaEvent_t wf_ev_level[MTB_MAX_RAY_DEPTH + 2] = {};  // level L traced (main stream)
   cudaEvent_t wf_ev_lit = nullptr;               // all lights folded (second stream)
   DeviceBuffer<uint32_t> wf_level_n, wf_ctrl;
+  DeviceBuffer<double> wf_act_coef;       // queue pipeline (WfQueue)
+  DeviceBuffer<int32_t> wf_act_info;
+  DeviceBuffer<uint32_t> wf_act_ready, wf_qctl;
+  uint32_t wf_epoch = 0;                  // frame number of the queue pipeline: act_ready[id] == epoch marks a complete entry
   DeviceBuffer<unsigned long long> wf_work;
   // pinned; written by WfCommit at the end of every frame (level counts, overflow flag, frame sequence number) and read
   // by the host at the START of the next frame only: grid sizes and queue capacities follow the scene with one frame
@@ -155,7 +159,7 @@ struct DeviceState {
     }
     wf_act_point.Free(); wf_act_normal.Free(); wf_act_surface.Free(); wf_act_reflected.Free(); wf_act_dir.Free();
     wf_sh_power.Free(); wf_sh_flags.Free(); wf_act_color.Free(); wf_act_refl.Free(); wf_act_refr.Free();
-    wf_act_mtl.Free(); wf_act_pixel.Free(); wf_act_path.Free(); wf_level_n.Free(); wf_ctrl.Free(); wf_work.Free();
+    wf_act_mtl.Free(); wf_act_pixel.Free(); wf_act_path.Free(); wf_level_n.Free(); wf_ctrl.Free(); wf_work.Free(); wf_act_coef.Free(); wf_act_info.Free(); wf_act_ready.Free(); wf_qctl.Free();
     if (wf_stream2 != nullptr) cudaStreamDestroy(wf_stream2);
     wf_stream2 = nullptr;
     for (cudaStream_t &st : wf_side) {
@@ -640,6 +644,52 @@ int RunWavefront(mtb_context *ctx, DeviceState *d, const mtb::RenderParams &p, i
   return MTB_OK;
 }
 
+// One frame through the queue pipeline: one persistent kernel takes every activation of every level from a single
+// device-side ray queue (wavefront.cu, WfQueue), then the per-pixel fold.  Four launches, nothing read back; overflow
+// of the activation table is handled like in RunWavefront (repair launch, larger tables next frame).
+int RunWavefrontQueue(mtb_context *ctx, DeviceState *d, const mtb::RenderParams &p, int n_blocks, bool debug_build, cudaStream_t s) {
+  const int slots = n_blocks * 64;
+  if (slots <= 0) return MTB_OK;
+  if (d->wf_host != nullptr) {
+    const uint32_t seq = d->wf_host[mtb::kWfHostSequence];
+    if (seq != d->wf_seen_sequence) {
+      d->wf_seen_sequence = seq;
+      if (d->wf_host[mtb::kWfHostOverflow] != 0u) {
+        d->wf_queue_factor *= 2;
+        d->wf_act_factor *= 2;
+      }
+    }
+  }
+  const int rc = EnsureWavefront(ctx, d, slots, d->scene.n_lights);
+  if (rc != MTB_OK) return rc;
+  const size_t acap = (size_t)d->wf.act_cap;
+  const uint32_t *ready_before = d->wf_act_ready.ptr;
+  MTB_CUDA(ctx, d->wf_act_coef.Reserve(acap));
+  MTB_CUDA(ctx, d->wf_act_info.Reserve(acap));
+  MTB_CUDA(ctx, d->wf_act_ready.Reserve(acap));
+  MTB_CUDA(ctx, d->wf_qctl.Reserve(mtb::kQWords));
+  if (d->wf_act_ready.ptr != ready_before || d->wf_epoch == 0xffffffffu) {
+    MTB_CUDA(ctx, cudaMemsetAsync(d->wf_act_ready.ptr, 0, d->wf_act_ready.count * sizeof(uint32_t), s));
+    d->wf_epoch = 0;
+  }
+  d->wf_epoch++;
+  d->wf.act_coef = d->wf_act_coef.ptr;
+  d->wf.act_info = d->wf_act_info.ptr;
+  d->wf.act_ready = d->wf_act_ready.ptr;
+  d->wf.qctl = d->wf_qctl.ptr;
+  mtb::LaunchWfQueueBegin(d->wf, slots, s);
+  mtb::LaunchWfQueue(d->scene, p, d->wf, slots, d->wf_epoch, d->sm_count, debug_build, s);
+  mtb::LaunchWfResolveTree(d->scene, p, d->wf, slots, s);
+  mtb::LaunchWfCommit(d->wf, p.counters, d->wf_host, s);
+  mtb::RenderParams repair = p;
+  repair.run_if = d->wf.ctrl;
+  repair.mega_part = 1;
+  mtb::LaunchRenderMega(d->scene, repair, n_blocks, debug_build, s);
+  ctx->launches += 5u;
+  MTB_CUDA(ctx, cudaGetLastError());
+  return MTB_OK;
+}
+
 // Hybrid frames: which tiles go through the wavefront.  The megakernel's critical path is its most expensive pixel
 // (a serial chain of up to ~80 rays), the wavefront's is one ray per level but it pays ~1.3x the instructions, so the
 // most expensive tiles of the previous frame go to the wavefront and the rest to the megakernel, concurrently.  How
@@ -744,9 +794,9 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
     const int blocks = OwnedStrips(plan, owner) * rp.tiles_x;
     // a peer's scratch frame must not be overwritten while device 0 still gathers the previous one
     if (g > 0) MTB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->dev[0].ev_gathered, 0));
-    bool wavefront = (ctx->flags & MTB_FLAG_WAVEFRONT) != 0;
+    bool wavefront = (ctx->flags & (MTB_FLAG_WAVEFRONT | MTB_FLAG_QUEUE)) != 0;
     bool hybrid = (ctx->flags & MTB_FLAG_HYBRID) != 0 && !wavefront;
-    if ((ctx->flags & (MTB_FLAG_WAVEFRONT | MTB_FLAG_MEGAKERNEL | MTB_FLAG_HYBRID)) == 0 && blocks > 0) {
+    if ((ctx->flags & (MTB_FLAG_WAVEFRONT | MTB_FLAG_QUEUE | MTB_FLAG_MEGAKERNEL | MTB_FLAG_HYBRID)) == 0 && blocks > 0) {
       // automatic: measure both pipelines on the first frames of this geometry, then keep the faster
       const long long tsig = ((long long)chunk_w << 42) ^ ((long long)chunk_h << 24) ^ ((long long)owner << 12) ^
                              ((long long)plan.owners << 6) ^ ((long long)max_depth << 1) ^ ((long long)d.scene.n_lights << 50);
@@ -784,7 +834,8 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
         MTB_CUDA(ctx, cudaMemsetAsync(d.sig_shadow.ptr, 0, npx * 8, s));
         MTB_CUDA(ctx, cudaMemsetAsync(d.n_rays.ptr, 0, npx * 4, s));
       }
-      const int wrc = RunWavefront(ctx, &d, p, blocks, debug_build, s);
+      const int wrc = (ctx->flags & MTB_FLAG_QUEUE) != 0 ? RunWavefrontQueue(ctx, &d, p, blocks, debug_build, s)
+                                                         : RunWavefront(ctx, &d, p, blocks, debug_build, s);
       if (wrc != MTB_OK) return wrc;
     } else {
       const int mblocks = blocks;

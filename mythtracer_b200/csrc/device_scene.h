@@ -104,7 +104,15 @@ struct WfBuffers {
   uint32_t *ctrl;      // [0] overflow flag (a queue was too small: the frame is rendered by the repair launch)
   unsigned long long *work;  // [kNumCounters] work counters of this frame, committed by WfCommit unless it overflowed
   int32_t queue_cap, act_cap;
+  // Queue pipeline (WfQueue): ONE ray queue for all levels, entry id = activation id.  A queued ray lives in
+  // act_point (origin) / act_dir (direction) / act_coef / act_path / act_pixel / act_info (level | in_object << 8)
+  // of its activation until a warp takes it; act_ready[id] == epoch of the frame once the entry is complete.
+  double *act_coef;
+  int32_t *act_info;
+  uint32_t *act_ready;
+  uint32_t *qctl;  // [kQHead] next entry to hand out, [kQTail] entries reserved, [kQPending] activations not finished yet
 };
+enum QueueCtl { kQHead = 0, kQTail = 1, kQPending = 2, kQWords = 4 };
 // layout of the pinned host copy WfCommit writes: level_n[0 .. MTB_MAX_RAY_DEPTH + 1], overflow flag, frame sequence
 constexpr int kWfHostOverflow = MTB_MAX_RAY_DEPTH + 2;
 constexpr int kWfHostSequence = MTB_MAX_RAY_DEPTH + 3;
@@ -121,6 +129,11 @@ void LaunchWfLight(const DeviceScene &sc, const RenderParams &rp, const WfBuffer
 void LaunchWfFold(const DeviceScene &sc, const WfBuffers &wf, int level, long long expect, cudaStream_t stream);
 void LaunchWfResolve(const RenderParams &rp, const WfBuffers &wf, int n_slots, cudaStream_t stream);
 void LaunchWfCommit(const WfBuffers &wf, unsigned long long *global, uint32_t *host_copy, cudaStream_t stream);
+// Queue pipeline: one persistent kernel for all levels (WfQueue), then the per-pixel fold + V3DtoRGB (WfResolveTree).
+void LaunchWfQueueBegin(const WfBuffers &wf, int slots, cudaStream_t stream);
+void LaunchWfQueue(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int slots, unsigned epoch, int sm_count, bool debug_build,
+                   cudaStream_t stream);
+void LaunchWfResolveTree(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int slots, cudaStream_t stream);
 
 // megakernel.cu
 // Builds tile_order (descending cost, bucketed) from tile_cost and clears tile_cost for the coming frame.

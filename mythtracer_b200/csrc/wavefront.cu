@@ -452,6 +452,431 @@ __global__ void __launch_bounds__(256) WfResolve(RenderParams rp, WfBuffers wf, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Queue pipeline: ONE persistent kernel for all levels
+// ---------------------------------------------------------------------------------------------------
+// The level-by-level pipeline above pays, per level, one kernel boundary on its critical path (a level's trace kernel
+// ends with its slowest ray before the first ray of the next level starts) and writes the whole shading context of
+// every activation to HBM for the shadow / light kernels.  Here a task is ONE ACTIVATION from beginning to end:
+// a warp takes up to 32 consecutive entries of a single ray queue (entry id = activation id; ids below `slots` are
+// the primary rays), traces them, shades the hits, appends their reflection / refraction children to the queue
+// (warp ballots + prefix counts, one atomic per warp) and publishes them BEFORE it walks its own shadow segments -
+// so the chain primary -> child -> grandchild runs ahead on other warps while the shadow walks fill the machine -
+// and then does the shadow walks and the Phong sum of its hits in registers (nothing but colour, material and the two
+// child links of an activation is ever stored).  The lanes of a warp are in phase by construction: all trace, then
+// all walk towards light 0, then light 1, ... (the megakernel's lanes drift apart because every pixel follows its own
+// tree).  The fold happens afterwards, per pixel, in the reference's order (WfResolveTree).
+//
+// Queue protocol.  qctl[kQTail] is advanced by producers (reservation), then the entries are written, then - after a
+// __threadfence() - act_ready[id] = epoch marks each one complete.  A consumer takes [head, head + n) with one
+// compare-and-swap on qctl[kQHead] (never beyond the reserved tail), and a lane whose entry is not complete yet spins
+// on its flag; the producer never waits for anything in between, so the wait is short.  Queue fields are read with
+// ld.global.cg: they were written by another SM during this kernel and L1 is not coherent.  qctl[kQPending] counts
+// activations that are not finished; a warp that finds the queue empty leaves when it is zero.  Overflow of the
+// activation table, or a wait that lasts absurdly long, sets ctrl[0]: every warp leaves and the repair launch
+// (RenderMega, same bytes) renders the frame.
+#ifndef MTB_QUEUE_MIN_BLOCKS
+#define MTB_QUEUE_MIN_BLOCKS 14  // 64-thread blocks at 72 registers, the megakernel's shape
+#endif
+constexpr unsigned kQueueSpinLimit = 1u << 22;
+
+__device__ __forceinline__ unsigned LdVolatile(const uint32_t *p) {
+  unsigned v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ D3 LdCg3(const double *p) { return Mk(__ldcg(p), __ldcg(p + 1), __ldcg(p + 2)); }
+
+__global__ void WfQueueBegin(WfBuffers wf, int slots) {
+  const int i = (int)threadIdx.x;
+  if (i <= MTB_MAX_RAY_DEPTH + 1) wf.level_n[i] = i == 0 ? (uint32_t)slots : 0u;
+  if (i < 2) wf.ctrl[i] = 0u;
+  if (i < kNumCounters) wf.work[i] = 0ull;
+  if (i < kQWords) wf.qctl[i] = (i == kQTail || i == kQPending) ? (uint32_t)slots : 0u;
+}
+
+template <bool DBG>
+__global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(DeviceScene sc, RenderParams rp, WfBuffers wf, int slots, unsigned epoch) {
+  MTB_DECLARE_FAST_CTX(kBlockThreads);
+  unsigned long long cnt_store[DBG ? kNumCounters : 1];
+  unsigned long long *cnt = cnt_store;
+  if (DBG) {
+    for (int k = 0; k < kNumCounters; k++) cnt[k] = 0;
+  }
+  const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+  unsigned traced = 0;
+  // The warp's ticket: it owns activations [ticket, ticket + 32) and has handed `done` of them to its lanes so far.
+  unsigned ticket = 0, done = 32;
+  for (;;) {
+    if (done >= 32u) {
+      if (lane == 0u) ticket = atomicAdd(wf.qctl + kQHead, 32u);  // fetch-and-add: never fails, never retried
+      ticket = __shfl_sync(0xffffffffu, ticket, 0);
+      done = 0;
+    }
+    if (ticket >= (unsigned)wf.act_cap) break;  // beyond the table: such entries are never produced (overflow is flagged)
+    // ---- how many of the ticket's entries exist by now?  Primary rays always do; queued ones once the tail has
+    // passed them.  A partly filled ticket is not waited for for long: what is there goes out to the first lanes
+    // (late in a frame that spreads the few remaining rays over many warps by itself) ----
+    unsigned n = 32u - done;
+    bool over = false;
+    if (ticket >= (unsigned)slots) {
+      unsigned waited = 0;
+      for (;;) {
+        unsigned tail = 0, pending = 1, stop = 0;
+        if (lane == 0u) {
+          tail = LdVolatile(wf.qctl + kQTail);
+          pending = LdVolatile(wf.qctl + kQPending);
+          stop = LdVolatile(wf.ctrl);
+          if (pending == 0u) tail = LdVolatile(wf.qctl + kQTail);  // nothing is in flight any more: this tail is final
+        }
+        tail = __shfl_sync(0xffffffffu, tail, 0);
+        pending = __shfl_sync(0xffffffffu, pending, 0);
+        stop = __shfl_sync(0xffffffffu, stop, 0);
+        const unsigned first = ticket + done;
+        const unsigned avail = tail > first ? (tail - first < 32u - done ? tail - first : 32u - done) : 0u;
+        if (stop != 0u || (avail == 0u && pending == 0u)) {
+          over = true;
+          break;
+        }
+        if (avail == 32u - done || (avail > 0u && waited >= 2u)) {
+          n = avail;
+          break;
+        }
+        __nanosleep(waited < 16u ? 250u : 2000u);
+        if (++waited > kQueueSpinLimit) {
+          if (lane == 0u) wf.ctrl[0] = 1u;
+          over = true;
+          break;
+        }
+      }
+    }
+    if (over) break;
+
+    // ---- the batch: lane k < n owns activation ticket + done + k ----
+    const bool mine = lane < n;
+    const int act = (int)(ticket + done + lane);
+    done += n;
+    bool live = mine, failed = false, in_object = false;
+    int level = 0, pixel = -1;
+    double coef = 1.0;
+    unsigned long long path = 1ull;
+    D3 o = Mk(0.0, 0.0, 0.0), d = Mk(0.0, 0.0, 0.0);
+    if (mine) {
+      if (act < slots) {
+        // 8x8 pixel tiles (a warp = 8x4 pixels) of this launch's strips, as in RenderMega / WfTrace level 0
+        const int tile = WfTileOfSlot(rp, act), t = act & 63;
+        const int strip = rp.strip_first + (tile / rp.tiles_x) * rp.strip_stride;
+        const int px = (tile % rp.tiles_x) * 8 + (t & 7);
+        const int py = strip * 8 + (t >> 3);
+        live = tile >= 0 && px < rp.chunk_w && py < rp.chunk_h;
+        pixel = live ? py * rp.chunk_w + px : -1;
+        const D3 start = Load3(rp.sensor), d_scan = Load3(rp.sensor + 3), d_pixel = Load3(rp.sensor + 6);
+        o = Load3(rp.origin);
+        d = Normalized(Add(Add(start, MulS(d_scan, (double)(rp.chunk_y + py))), MulS(d_pixel, (double)(rp.chunk_x + px))));
+        if (live) Count<DBG>(cnt, kPrimary);
+      } else {
+        // reserved, and being written by the warp that spawned it: a short wait
+        unsigned spins = 0;
+        while (LdVolatile(wf.act_ready + act) != epoch) {
+          if (++spins > kQueueSpinLimit || ((spins & 255u) == 0u && LdVolatile(wf.ctrl) != 0u)) {
+            failed = true;
+            break;
+          }
+          __nanosleep(40u);
+        }
+        __threadfence();
+        if (!failed) {
+          o = LdCg3(wf.act_point + (size_t)act * 3);
+          d = LdCg3(wf.act_dir + (size_t)act * 3);
+          coef = __ldcg(wf.act_coef + act);
+          path = __ldcg(wf.act_path + act);
+          pixel = __ldcg(wf.act_pixel + act);
+          const int info = __ldcg(wf.act_info + act);
+          level = info & 0xff;
+          in_object = (info >> 8) != 0;
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, failed)) {
+      if (lane == 0u) wf.ctrl[0] = 1u;
+      break;
+    }
+
+    // ---- trace (mythtracer.cc:13-76) ----
+    double t = 0.0;
+    int slot = -1;
+    if (live) {
+      slot = Trace<DBG>(sc, o, d, CUDART_INF, &t, cnt, fctx);
+      traced++;
+    }
+    bool do_reflect = false, do_refract = false, lit = false;
+    double refl = 0.0;
+    int material = -2;
+    D3 P = Mk(0.0, 0.0, 0.0), normal = P, surface = P, reflected = P, color = P;
+    if (live) {
+      if (slot < 0) {
+        if (level == 0 && rp.dbg != nullptr) {
+          mtb_debug *dbg = rp.dbg + pixel;
+          dbg->line_no = -1;
+          dbg->pad_ = 0;
+          dbg->point[0] = dbg->point[1] = dbg->point[2] = CUDART_NAN;
+        }
+      } else {
+        const ShadeRec *sh = sc.shade + slot;
+        const SlotRec *sr = sc.slots + slot;
+        P = Add(o, MulS(d, t));
+        const int line_no = __ldg(&sh->line_no);
+        if (level == 0 && rp.dbg != nullptr) {
+          mtb_debug *dbg = rp.dbg + pixel;
+          dbg->line_no = line_no;
+          dbg->pad_ = 0;
+          dbg->point[0] = P.x;
+          dbg->point[1] = P.y;
+          dbg->point[2] = P.z;
+        }
+        if (rp.sig_hits != nullptr) {
+          atomicAdd(reinterpret_cast<unsigned long long *>(rp.sig_hits) + pixel, Mix64(path, 1ull, (unsigned long long)(long long)line_no));
+        }
+        Count<DBG>(cnt, kShade);
+        const D3 v0 = Load3(sr->vert), v1 = Load3(sr->vert + 3), v2 = Load3(sr->vert + 6);
+        const BaryWeights w = Barycentric(v0, v1, v2, P);
+        normal = DivS(Add(Add(MulS(Load3(sh->normal), w.n0), MulS(Load3(sh->normal + 3), w.n1)), MulS(Load3(sh->normal + 6), w.n2)), w.n);
+        const D3 towards_camera = Neg(d);
+        double normal_ray_dot = Dot(towards_camera, normal);
+        if (normal_ray_dot < 0.0) {
+          normal = Neg(normal);
+          normal_ray_dot = Dot(towards_camera, normal);
+        }
+        const int mtl = __ldg(&sh->material);
+        if (mtl < 0) {  // mythtracer.cc:49-52
+          normal_ray_dot = (normal_ray_dot + 1.0) * 0.5;
+          color = Mk(normal_ray_dot, normal_ray_dot, normal_ray_dot);
+        } else {
+          const mtb_material *m = sc.materials + mtl;
+          surface = Load3(m->ambient);
+          const int tex = m->texture;
+          if (tex >= 0) {
+            const double u = (sh->uv[0] * w.n0 + sh->uv[2] * w.n1 + sh->uv[4] * w.n2) / w.n;
+            const double v = (sh->uv[1] * w.n0 + sh->uv[3] * w.n1 + sh->uv[5] * w.n2) / w.n;
+            surface = MulV(surface, SampleTexture(sc.tex_atlas, tex, sc.texture_dim[tex], u, v));
+          }
+          reflected = Sub(d, MulS(normal, 2 * Dot(normal, d)));
+          material = mtl;
+          lit = true;
+          if (level < rp.max_depth) {
+            refl = m->reflectance;
+            do_reflect = refl > 0.0 && coef > 0.01 && !in_object;  // mythtracer.cc:181-184
+            do_refract = m->transparency > 0.0;                    // mythtracer.cc:192
+          }
+        }
+      }
+    }
+
+    // ---- children -> queue, published before this warp walks its shadow segments.  The warp's reflection children
+    // are stored first, then its refraction children: neighbouring entries (= the lanes of some warp later) are rays
+    // of the same kind from neighbouring pixels ----
+    const unsigned refl_mask = __ballot_sync(0xffffffffu, do_reflect);
+    const unsigned refr_mask = __ballot_sync(0xffffffffu, do_refract);
+    const unsigned n_refl = (unsigned)__popc(refl_mask), total = n_refl + (unsigned)__popc(refr_mask);
+    int child_refl = -1, child_refr = -1;
+    bool overflow = false;
+    if (total != 0u) {
+      unsigned base = 0;
+      if (lane == 0u) {
+        atomicAdd(wf.qctl + kQPending, total);  // counted before they can be seen: the count never runs low
+        base = atomicAdd(wf.qctl + kQTail, total);
+      }
+      base = __shfl_sync(0xffffffffu, base, 0);
+      overflow = (unsigned long long)base + total > (unsigned long long)wf.act_cap;
+      if (!overflow) {
+        if (do_reflect) {
+          const int c = (int)(base + (unsigned)__popc(refl_mask & below));
+          Count<DBG>(cnt, kReflect);
+          Store3(wf.act_point + (size_t)c * 3, Add(P, MulS(reflected, 0.0001)));  // mythtracer.cc:70-75
+          Store3(wf.act_dir + (size_t)c * 3, reflected);
+          wf.act_coef[c] = coef * refl;
+          wf.act_path[c] = path * 2ull;
+          wf.act_pixel[c] = pixel;
+          wf.act_info[c] = (level + 1) | (in_object ? 256 : 0);
+          child_refl = c;
+        }
+        if (do_refract) {
+          const int c = (int)(base + n_refl + (unsigned)__popc(refr_mask & below));
+          Count<DBG>(cnt, kRefract);
+          const D3 rdir = Normalized(d);                                        // mythtracer.cc:208-212
+          Store3(wf.act_point + (size_t)c * 3, Add(P, MulS(rdir, 0.00001)));    // mythtracer.cc:214-218
+          Store3(wf.act_dir + (size_t)c * 3, rdir);
+          wf.act_coef[c] = coef;
+          wf.act_path[c] = path * 2ull + 1ull;
+          wf.act_pixel[c] = pixel;
+          wf.act_info[c] = (level + 1) | (in_object ? 0 : 256);
+          child_refr = c;
+        }
+        __threadfence();
+        if (child_refl >= 0) asm volatile("st.volatile.global.u32 [%0], %1;" : : "l"(wf.act_ready + child_refl), "r"(epoch) : "memory");
+        if (child_refr >= 0) asm volatile("st.volatile.global.u32 [%0], %1;" : : "l"(wf.act_ready + child_refr), "r"(epoch) : "memory");
+      }
+    }
+    if (overflow) {
+      if (lane == 0u) wf.ctrl[0] = 1u;
+      break;
+    }
+    // this batch's activations spawn nothing else: they leave the count (their children are in it already)
+    if (lane == 0u) atomicAdd(wf.qctl + kQPending, 0u - n);
+
+    // ---- shadow walks and the Phong sum of the hits, light by light (mythtracer.cc:78-178) ----
+    unsigned rays = live ? 1u : 0u;
+    if (lit) {
+      const mtb_material *m = sc.materials + material;
+      unsigned long long sig = 0ull;
+      for (int li = 0; li < sc.n_lights; li++) {
+        const mtb_light *lt = sc.lights + li;
+        const D3 lpos = Load3(lt->position);
+        const D3 ldir = Normalized(Sub(lpos, P));
+        const D3 lamb = Load3(lt->ambient);
+        color = Add(color, MulV(lamb, surface));  // mythtracer.cc:83-84
+        D3 power = Mk(1.0, 1.0, 1.0);
+        bool in_shadow = false, through = false;
+        unsigned segments = 0;
+        D3 seg_start = P;
+        for (;;) {  // mythtracer.cc:94-156
+          const D3 to = Add(seg_start, MulS(ldir, 0.00001));
+          const double light_distance = Dist(seg_start, lpos);
+          double ts = 0.0;
+          Count<DBG>(cnt, kShadow);
+          const int sslot = Trace<DBG>(sc, to, ldir, light_distance, &ts, cnt, fctx);
+          segments++;
+          if (sslot < 0) break;
+          if (ts > light_distance) break;
+          const int smtl = __ldg(&sc.shade[sslot].material);
+          const double str = smtl >= 0 ? __ldg(&sc.materials[smtl].transparency) : 0.0;
+          if (str == 0.0) {
+            power = Mk(0.0, 0.0, 0.0);
+            in_shadow = true;
+            break;
+          }
+          if (!through) power = MulV(power, MulS(Load3(sc.materials[smtl].transmission_filter), str));
+          through = !through;
+          seg_start = Add(Add(to, MulS(ldir, ts)), MulS(ldir, 0.0000001));
+          if (SqrDist(P, seg_start) > SqrDist(P, lpos)) break;
+          if (power.x <= 0.001 && power.y <= 0.001 && power.z <= 0.001) {
+            power = Mk(0.0, 0.0, 0.0);
+            in_shadow = true;
+            break;
+          }
+        }
+        rays += segments;
+        sig += Mix64(path, 2ull + (unsigned long long)li, (in_shadow ? 1ull : 0ull) | ((unsigned long long)segments << 1));
+        power.x = SMax(power.x, lamb.x);
+        power.y = SMax(power.y, lamb.y);
+        power.z = SMax(power.z, lamb.z);
+        color = Add(color, MulV(MulV(MulS(MulV(Load3(m->diffuse), surface), Dot(normal, ldir)), Load3(lt->diffuse)), power));
+        if (!in_shadow) {
+          const double refl_dot = Dot(Neg(d), reflected);
+          if (refl_dot > 0) {
+            color = Add(color, MulV(MulS(MulV(Load3(m->specular), surface), pow(refl_dot, m->specular_exp)), Load3(lt->specular)));
+          }
+        }
+      }
+      if (rp.sig_shadow != nullptr && sc.n_lights > 0) atomicAdd(reinterpret_cast<unsigned long long *>(rp.sig_shadow) + pixel, sig);
+    }
+    if (mine) {
+      wf.act_mtl[act] = material;
+      wf.act_refl[act] = child_refl;
+      wf.act_refr[act] = child_refr;
+      Store3(wf.act_color + (size_t)act * 3, color);
+      if (live) {
+        traced += rays - 1u;
+        if (rp.n_rays != nullptr) atomicAdd(rp.n_rays + pixel, rays);
+        WfChargeTile(rp, pixel, rays);
+      }
+    }
+  }
+  FlushCounters<DBG>(cnt, wf.work, traced);
+}
+
+// Per-pixel fold of the activation tree in the reference's order - parent += child * Refl, then
+// parent += (child * Tf) * Tr (mythtracer.cc:185-189, 220-224), children before parents - followed by V3DtoRGB
+// (mythtracer.cc:235-241).  One block = one 8x8 tile (slots pos * 64 ..), written like RenderMega writes its tiles.
+__global__ void __launch_bounds__(kBlockThreads) WfResolveTree(DeviceScene sc, RenderParams rp, WfBuffers wf, int slots) {
+  __shared__ __align__(8) unsigned char s_rgb[kTile * kTile * 3];
+  if (wf.ctrl[0] != 0u) return;
+  const int pos = (int)blockIdx.x, root = pos * 64 + (int)threadIdx.x;
+  const int tile = WfTileOfSlot(rp, pos * 64);
+  if (tile < 0 || root >= slots) return;
+  const int strip = rp.strip_first + (tile / rp.tiles_x) * rp.strip_stride;
+  const int tx = (int)(threadIdx.x & 7u), ty = (int)(threadIdx.x >> 3);
+  const int px = (tile % rp.tiles_x) * kTile + tx, py = strip * kTile + ty;
+  const bool live = px < rp.chunk_w && py < rp.chunk_h;
+  {
+    int f_act[MTB_MAX_RAY_DEPTH + 2];
+    unsigned char f_stage[MTB_MAX_RAY_DEPTH + 2];  // 0: nothing folded yet, 1: reflection child in progress / done, 2: refraction child
+    D3 f_color[MTB_MAX_RAY_DEPTH + 2];
+    int sp = 0;
+    D3 ret = Mk(0.0, 0.0, 0.0);
+    if (live) {
+      f_act[0] = root;
+      f_stage[0] = 0;
+      f_color[0] = Load3(wf.act_color + (size_t)root * 3);
+      sp = 1;
+    }
+    while (sp > 0) {
+      const int a = f_act[sp - 1];
+      int child = -1;
+      if (f_stage[sp - 1] == 0) {
+        f_stage[sp - 1] = 1;
+        child = wf.act_refl[a];
+      }
+      if (child < 0 && f_stage[sp - 1] == 1) {
+        f_stage[sp - 1] = 2;
+        child = wf.act_refr[a];
+      }
+      if (child >= 0 && sp < MTB_MAX_RAY_DEPTH + 2) {
+        f_act[sp] = child;
+        f_stage[sp] = 0;
+        f_color[sp] = Load3(wf.act_color + (size_t)child * 3);
+        sp++;
+        continue;
+      }
+      ret = f_color[sp - 1];
+      sp--;
+      if (sp == 0) break;
+      const mtb_material *m = sc.materials + wf.act_mtl[f_act[sp - 1]];
+      if (f_stage[sp - 1] == 1) {
+        f_color[sp - 1] = Add(f_color[sp - 1], MulS(ret, m->reflectance));
+      } else {
+        f_color[sp - 1] = Add(f_color[sp - 1], MulS(MulV(ret, Load3(m->transmission_filter)), m->transparency));
+      }
+    }
+    unsigned char *out = s_rgb + ((ty * kTile) + tx) * 3;
+    out[0] = QuantizeChannel(ret.x);
+    out[1] = QuantizeChannel(ret.y);
+    out[2] = QuantizeChannel(ret.z);
+  }
+  __syncwarp();
+  {
+    const int px0 = (tile % rp.tiles_x) * kTile, py0 = strip * kTile + (int)(threadIdx.x >> 5) * 4;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned char *half = s_rgb + (threadIdx.x >> 5) * (4 * kTile * 3);
+    const bool whole_rows = px0 + kTile <= rp.chunk_w && (rp.chunk_w & 7) == 0 && (reinterpret_cast<uintptr_t>(rp.rgb) & 7u) == 0u;
+    if (whole_rows) {
+      if (lane < 12u) {
+        const int row = (int)lane / 3, seg = (int)lane % 3;
+        if (py0 + row < rp.chunk_h) {
+          const uint2 v = *reinterpret_cast<const uint2 *>(half + row * 24 + seg * 8);
+          *reinterpret_cast<uint2 *>(rp.rgb + ((size_t)(py0 + row) * rp.chunk_w + px0) * 3 + seg * 8) = v;
+        }
+      }
+    } else if (live) {
+      unsigned char *dst = rp.rgb + ((size_t)py * rp.chunk_w + px) * 3;
+      const unsigned char *src = s_rgb + ((ty * kTile) + tx) * 3;
+      dst[0] = src[0];
+      dst[1] = src[1];
+      dst[2] = src[2];
+    }
+  }
+}
+
 // Last kernel of a frame.  The work counters of a frame that overflowed are dropped (the repair launch counts its
 // own rays); host_copy (pinned, nullable) receives level_n[] and the overflow flag for the next frame's grid sizes
 // and queue capacities - written by the device, never waited for by the host.
@@ -534,6 +959,26 @@ void LaunchWfResolve(const RenderParams &rp, const WfBuffers &wf, int n_slots, c
   if (n_slots <= 0) return;
   const int threads = (n_slots / 64) * 24;
   WfResolve<<<(threads + 255) / 256, 256, 0, stream>>>(rp, wf, n_slots);
+}
+
+void LaunchWfQueueBegin(const WfBuffers &wf, int slots, cudaStream_t stream) { WfQueueBegin<<<1, 32, 0, stream>>>(wf, slots); }
+
+void LaunchWfQueue(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int slots, unsigned epoch, int sm_count, bool debug_build,
+                   cudaStream_t stream) {
+  // persistent: what the device can hold, but not more warps than the frame has groups of 32 primary rays
+  long long blocks = (long long)sm_count * MTB_QUEUE_MIN_BLOCKS;
+  const long long need = ((long long)slots / 32 + 1) / 2;
+  if (blocks > need) blocks = need < 1 ? 1 : need;
+  if (debug_build) {
+    WfQueue<true><<<(int)blocks, kBlockThreads, 0, stream>>>(sc, rp, wf, slots, epoch);
+  } else {
+    WfQueue<false><<<(int)blocks, kBlockThreads, 0, stream>>>(sc, rp, wf, slots, epoch);
+  }
+}
+
+void LaunchWfResolveTree(const DeviceScene &sc, const RenderParams &rp, const WfBuffers &wf, int slots, cudaStream_t stream) {
+  if (slots <= 0) return;
+  WfResolveTree<<<slots / 64, kBlockThreads, 0, stream>>>(sc, rp, wf, slots);
 }
 
 void LaunchWfCommit(const WfBuffers &wf, unsigned long long *global, uint32_t *host_copy, cudaStream_t stream) {

@@ -19,7 +19,8 @@ MAX_RGB_FRACTION = 1e-5
 def _tracer(product_lib, depth, flags=0, devices=None):
     """flags without a pipeline bit: force the megakernel (small test frames would auto-select the wavefront)."""
     from mythtracer_b200 import MTB_FLAG_MEGAKERNEL, MTB_FLAG_WAVEFRONT, MythTracer
-    if not flags & (MTB_FLAG_WAVEFRONT | MTB_FLAG_MEGAKERNEL):
+    from mythtracer_b200 import MTB_FLAG_QUEUE
+    if not flags & (MTB_FLAG_WAVEFRONT | MTB_FLAG_MEGAKERNEL | MTB_FLAG_QUEUE):
         flags |= MTB_FLAG_MEGAKERNEL
     return MythTracer(devices=devices, max_depth=depth, flags=flags)
 
@@ -372,6 +373,54 @@ def test_wavefront_depths_lights_lattice_and_tiles(product_lib, oracle_mod, scen
     gpu = mt2.render_chunk(cam, 65, 49, 0, 0, 65, 49, debug=True, taps=True)
     cpu = orc2.render(cam, 65, 49, depth=5, taps=True)
     _assert_render_equal(gpu, cpu, "wavefront lattice")
+
+
+@pytest.mark.parametrize("name,scale,w,h", [("C1", 1.0, 320, 240), ("C2", 0.3, 256, 144)])
+def test_queue_pipeline_parity(product_lib, oracle_mod, scene_dir, name, scale, w, h):
+    """The queue pipeline (MTB_FLAG_QUEUE: one persistent kernel over a single ray queue) against the oracle, every
+    tap, in the plain and the counting build, and against the megakernel's bytes."""
+    from mythtracer_b200 import MTB_FLAG_COUNT_WORK, MTB_FLAG_MEGAKERNEL, MTB_FLAG_QUEUE
+    files, cfg = scenes.config_scene(name, scene_dir, scale)
+    mt, orc = _load_pair(product_lib, oracle_mod, files, cfg["depth"], MTB_FLAG_QUEUE | MTB_FLAG_COUNT_WORK)
+    gpu = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
+    cpu = orc.render(files.camera, w, h, depth=cfg["depth"], taps=True)
+    _assert_render_equal(gpu, cpu, name + " queue (counting build)")
+    mt.set_flags(MTB_FLAG_QUEUE)
+    for it in range(3):  # the epoch of the ready flags moves on from frame to frame
+        fast = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
+        _assert_render_equal(fast, cpu, name + " queue frame %d" % it)
+    mt.set_flags(MTB_FLAG_MEGAKERNEL)
+    mega = mt.render_chunk(files.camera, w, h, 0, 0, w, h)
+    assert np.array_equal(fast["rgb"], mega["rgb"]) and np.array_equal(fast["rgb"], gpu["rgb"])
+    assert fast["stats"]["rays"] == mega["stats"]["rays"] == cpu["stats"]["rays"]
+
+
+def test_queue_pipeline_depths_lights_lattice_and_tiles(product_lib, oracle_mod, scene_dir):
+    from mythtracer_b200 import Light, MTB_FLAG_QUEUE
+    files, cfg = scenes.config_scene("C1", scene_dir)
+    mt, orc = _load_pair(product_lib, oracle_mod, files, 5, MTB_FLAG_QUEUE)
+    w, h = 160, 120
+    for depth, n_lights in [(0, 1), (2, 0), (5, 4), (8, 2)]:
+        lights = scenes.LIGHT_RIG[:n_lights]
+        mt.max_depth = depth
+        mt.GetScene().lights = [Light.from_tuple(l) for l in lights]
+        orc.set_lights(lights)
+        gpu = mt.render_chunk(files.camera, w, h, 0, 0, w, h, debug=True, taps=True)
+        cpu = orc.render(files.camera, w, h, depth=depth, taps=True)
+        _assert_render_equal(gpu, cpu, "queue depth %d lights %d" % (depth, n_lights))
+    mt.max_depth = 3
+    gpu = mt.render_chunk(files.camera, 333, 211, 100, 37, 77, 45, debug=True, taps=True)
+    cpu = orc.render(files.camera, 333, 211, chunk=(100, 37, 77, 45), depth=3, taps=True)
+    _assert_render_equal(gpu, cpu, "queue tile")
+    path, cam, lights = scenes.lattice_scene(scene_dir)
+    mt2 = _tracer(product_lib, 5, MTB_FLAG_QUEUE)
+    assert mt2.LoadObj(path)
+    mt2.GetScene().lights = [Light.from_tuple(l) for l in lights]
+    orc2 = oracle_mod.Oracle.from_obj(path)
+    orc2.set_lights(lights)
+    gpu = mt2.render_chunk(cam, 65, 49, 0, 0, 65, 49, debug=True, taps=True)
+    cpu = orc2.render(cam, 65, 49, depth=5, taps=True)
+    _assert_render_equal(gpu, cpu, "queue lattice")
 
 
 def test_megakernel_launch_forms(product_lib, oracle_mod, scene_dir):

@@ -5,7 +5,7 @@ import torch
 from mythtracer_b200 import MythTracer, Light, scenegen, MTB_FLAG_WAVEFRONT, tiles
 world = int(sys.argv[1]); mode = sys.argv[2]
 files, cfg = scenegen.generate_config("C3", "/tmp/mtb_scenes")
-mt = MythTracer(max_depth=cfg["depth"], flags=MTB_FLAG_WAVEFRONT if mode == "wf" else (16 if mode == "mega" else (2048 if mode == "hybrid" else 0)))
+mt = MythTracer(max_depth=cfg["depth"], flags=MTB_FLAG_WAVEFRONT if mode == "wf" else (16 if mode == "mega" else (2048 if mode == "hybrid" else (8192 if mode == "queue" else 0))))
 assert mt.LoadObj(files.obj_path)
 mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]; mt.push_lights()
 W, H = cfg["width"], cfg["height"]

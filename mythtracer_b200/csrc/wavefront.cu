@@ -487,6 +487,20 @@ __device__ __forceinline__ unsigned LdVolatile(const uint32_t *p) {
 }
 __device__ __forceinline__ D3 LdCg3(const double *p) { return Mk(__ldcg(p), __ldcg(p + 1), __ldcg(p + 2)); }
 
+// What an activation keeps across a traversal (local memory, explicit; cf. PixelState in megakernel.cu).
+struct alignas(16) QueueState {
+  double m_o[3], m_d[3];                                       // its ray
+  double P[3], normal[3], surface[3], reflected[3], color[3];  // shading context (mythtracer.cc:38-76)
+  double ldir[3], seg_start[3], power[3];                      // shadow walk of the current light (mythtracer.cc:86-156)
+};
+#define MTB_QSTATE_BARRIER() asm volatile("" : : "l"(&st) : "memory")
+__device__ __forceinline__ D3 Ld3q(const double *p) { return Mk(p[0], p[1], p[2]); }
+__device__ __forceinline__ void St3q(double *p, const D3 &v) {
+  p[0] = v.x;
+  p[1] = v.y;
+  p[2] = v.z;
+}
+
 __global__ void WfQueueBegin(WfBuffers wf, int slots) {
   const int i = (int)threadIdx.x;
   if (i <= MTB_MAX_RAY_DEPTH + 1) wf.level_n[i] = i == 0 ? (uint32_t)slots : 0u;
@@ -602,191 +616,253 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
       break;
     }
 
-    // ---- trace (mythtracer.cc:13-76) ----
-    double t = 0.0;
-    int slot = -1;
-    if (live) {
-      slot = Trace<DBG>(sc, o, d, CUDART_INF, &t, cnt, fctx);
-      traced++;
-    }
-    bool do_reflect = false, do_refract = false, lit = false;
-    double refl = 0.0;
-    int material = -2;
-    D3 P = Mk(0.0, 0.0, 0.0), normal = P, surface = P, reflected = P, color = P;
-    if (live) {
-      if (slot < 0) {
-        if (level == 0 && rp.dbg != nullptr) {
-          mtb_debug *dbg = rp.dbg + pixel;
-          dbg->line_no = -1;
-          dbg->pad_ = 0;
-          dbg->point[0] = dbg->point[1] = dbg->point[2] = CUDART_NAN;
-        }
-      } else {
-        const ShadeRec *sh = sc.shade + slot;
-        const SlotRec *sr = sc.slots + slot;
-        P = Add(o, MulS(d, t));
-        const int line_no = __ldg(&sh->line_no);
-        if (level == 0 && rp.dbg != nullptr) {
-          mtb_debug *dbg = rp.dbg + pixel;
-          dbg->line_no = line_no;
-          dbg->pad_ = 0;
-          dbg->point[0] = P.x;
-          dbg->point[1] = P.y;
-          dbg->point[2] = P.z;
-        }
-        if (rp.sig_hits != nullptr) {
-          atomicAdd(reinterpret_cast<unsigned long long *>(rp.sig_hits) + pixel, Mix64(path, 1ull, (unsigned long long)(long long)line_no));
-        }
-        Count<DBG>(cnt, kShade);
-        const D3 v0 = Load3(sr->vert), v1 = Load3(sr->vert + 3), v2 = Load3(sr->vert + 6);
-        const BaryWeights w = Barycentric(v0, v1, v2, P);
-        normal = DivS(Add(Add(MulS(Load3(sh->normal), w.n0), MulS(Load3(sh->normal + 3), w.n1)), MulS(Load3(sh->normal + 6), w.n2)), w.n);
-        const D3 towards_camera = Neg(d);
-        double normal_ray_dot = Dot(towards_camera, normal);
-        if (normal_ray_dot < 0.0) {
-          normal = Neg(normal);
-          normal_ray_dot = Dot(towards_camera, normal);
-        }
-        const int mtl = __ldg(&sh->material);
-        if (mtl < 0) {  // mythtracer.cc:49-52
-          normal_ray_dot = (normal_ray_dot + 1.0) * 0.5;
-          color = Mk(normal_ray_dot, normal_ray_dot, normal_ray_dot);
+    // ---- one traversal per loop iteration, as in RenderMega: iteration 0 traces the activations' own rays, then the
+    // hits are shaded and their children queued (warp-wide), then every further iteration is one shadow segment of
+    // the lanes that still walk.  What has to survive a traversal lives in `st` (local memory, explicit - see
+    // PixelState in megakernel.cu for why); a handful of scalars stay in registers ----
+    QueueState st;
+    St3q(st.m_o, o);
+    St3q(st.m_d, d);
+    St3q(st.color, Mk(0.0, 0.0, 0.0));
+    bool walking = live, main_phase = true, lit = false, in_shadow = false, through = false;
+    int material = -2, li = 0, child_refl = -1, child_refr = -1;
+    unsigned segments = 0, rays = 0;
+    unsigned long long sig = 0ull;
+    double light_distance = 0.0;
+    bool stop_all = false;
+    for (;;) {
+      int slot = -1;
+      double t = 0.0;
+      if (walking) {
+        D3 to, td;
+        double limit = CUDART_INF;
+        if (main_phase) {
+          to = Ld3q(st.m_o);
+          td = Ld3q(st.m_d);
         } else {
-          const mtb_material *m = sc.materials + mtl;
-          surface = Load3(m->ambient);
-          const int tex = m->texture;
-          if (tex >= 0) {
-            const double u = (sh->uv[0] * w.n0 + sh->uv[2] * w.n1 + sh->uv[4] * w.n2) / w.n;
-            const double v = (sh->uv[1] * w.n0 + sh->uv[3] * w.n1 + sh->uv[5] * w.n2) / w.n;
-            surface = MulV(surface, SampleTexture(sc.tex_atlas, tex, sc.texture_dim[tex], u, v));
-          }
-          reflected = Sub(d, MulS(normal, 2 * Dot(normal, d)));
-          material = mtl;
-          lit = true;
-          if (level < rp.max_depth) {
-            refl = m->reflectance;
-            do_reflect = refl > 0.0 && coef > 0.01 && !in_object;  // mythtracer.cc:181-184
-            do_refract = m->transparency > 0.0;                    // mythtracer.cc:192
+          const D3 seg = Ld3q(st.seg_start);
+          td = Ld3q(st.ldir);
+          to = Add(seg, MulS(td, 0.00001));                                     // mythtracer.cc:95-99
+          limit = light_distance = Dist(seg, Load3(sc.lights[li].position));   // mythtracer.cc:101-102
+          Count<DBG>(cnt, kShadow);
+        }
+        MTB_QSTATE_BARRIER();
+        slot = Trace<DBG>(sc, to, td, limit, &t, cnt, fctx);
+        MTB_QSTATE_BARRIER();
+        rays++;
+      }
+      if (main_phase) {
+        // ---- results of the activations' own rays (mythtracer.cc:13-76); every lane of the warp is here ----
+        main_phase = false;
+        bool do_reflect = false, do_refract = false;
+        double refl = 0.0;
+        if (walking) {
+          walking = false;
+          if (slot < 0) {
+            if (level == 0 && rp.dbg != nullptr) {
+              mtb_debug *dbg = rp.dbg + pixel;
+              dbg->line_no = -1;
+              dbg->pad_ = 0;
+              dbg->point[0] = dbg->point[1] = dbg->point[2] = CUDART_NAN;
+            }
+          } else {
+            const ShadeRec *sh = sc.shade + slot;
+            const SlotRec *sr = sc.slots + slot;
+            const D3 m_d = Ld3q(st.m_d);
+            const D3 P = Add(Ld3q(st.m_o), MulS(m_d, t));
+            const int line_no = __ldg(&sh->line_no);
+            if (level == 0 && rp.dbg != nullptr) {
+              mtb_debug *dbg = rp.dbg + pixel;
+              dbg->line_no = line_no;
+              dbg->pad_ = 0;
+              dbg->point[0] = P.x;
+              dbg->point[1] = P.y;
+              dbg->point[2] = P.z;
+            }
+            if (rp.sig_hits != nullptr) {
+              atomicAdd(reinterpret_cast<unsigned long long *>(rp.sig_hits) + pixel, Mix64(path, 1ull, (unsigned long long)(long long)line_no));
+            }
+            Count<DBG>(cnt, kShade);
+            const D3 v0 = Load3(sr->vert), v1 = Load3(sr->vert + 3), v2 = Load3(sr->vert + 6);
+            const BaryWeights w = Barycentric(v0, v1, v2, P);
+            D3 normal = DivS(Add(Add(MulS(Load3(sh->normal), w.n0), MulS(Load3(sh->normal + 3), w.n1)), MulS(Load3(sh->normal + 6), w.n2)), w.n);
+            const D3 towards_camera = Neg(m_d);
+            double normal_ray_dot = Dot(towards_camera, normal);
+            if (normal_ray_dot < 0.0) {
+              normal = Neg(normal);
+              normal_ray_dot = Dot(towards_camera, normal);
+            }
+            const int mtl = __ldg(&sh->material);
+            if (mtl < 0) {  // mythtracer.cc:49-52
+              normal_ray_dot = (normal_ray_dot + 1.0) * 0.5;
+              St3q(st.color, Mk(normal_ray_dot, normal_ray_dot, normal_ray_dot));
+            } else {
+              const mtb_material *m = sc.materials + mtl;
+              D3 surface = Load3(m->ambient);
+              const int tex = m->texture;
+              if (tex >= 0) {
+                const double u = (sh->uv[0] * w.n0 + sh->uv[2] * w.n1 + sh->uv[4] * w.n2) / w.n;
+                const double v = (sh->uv[1] * w.n0 + sh->uv[3] * w.n1 + sh->uv[5] * w.n2) / w.n;
+                surface = MulV(surface, SampleTexture(sc.tex_atlas, tex, sc.texture_dim[tex], u, v));
+              }
+              const D3 reflected = Sub(m_d, MulS(normal, 2 * Dot(normal, m_d)));
+              St3q(st.P, P);
+              St3q(st.normal, normal);
+              St3q(st.surface, surface);
+              St3q(st.reflected, reflected);
+              material = mtl;
+              lit = true;
+              if (level < rp.max_depth) {
+                refl = m->reflectance;
+                do_reflect = refl > 0.0 && coef > 0.01 && !in_object;  // mythtracer.cc:181-184
+                do_refract = m->transparency > 0.0;                    // mythtracer.cc:192
+              }
+            }
           }
         }
+        // ---- children -> queue, published before this warp walks its shadow segments.  The warp's reflection
+        // children are stored first, then its refraction children: neighbouring entries (= the lanes of some warp
+        // later) are rays of the same kind from neighbouring pixels ----
+        const unsigned refl_mask = __ballot_sync(0xffffffffu, do_reflect);
+        const unsigned refr_mask = __ballot_sync(0xffffffffu, do_refract);
+        const unsigned n_refl = (unsigned)__popc(refl_mask), total = n_refl + (unsigned)__popc(refr_mask);
+        if (total != 0u) {
+          unsigned base = 0;
+          if (lane == 0u) {
+            atomicAdd(wf.qctl + kQPending, total);  // counted before they can be seen: the count never runs low
+            base = atomicAdd(wf.qctl + kQTail, total);
+          }
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if ((unsigned long long)base + total > (unsigned long long)wf.act_cap) {
+            stop_all = true;
+          } else {
+            if (do_reflect || do_refract) {
+              const D3 P = Ld3q(st.P), m_d = Ld3q(st.m_d);
+              if (do_reflect) {
+                const int c = (int)(base + (unsigned)__popc(refl_mask & below));
+                const D3 reflected = Ld3q(st.reflected);
+                Count<DBG>(cnt, kReflect);
+                Store3(wf.act_point + (size_t)c * 3, Add(P, MulS(reflected, 0.0001)));  // mythtracer.cc:70-75
+                Store3(wf.act_dir + (size_t)c * 3, reflected);
+                wf.act_coef[c] = coef * refl;
+                wf.act_path[c] = path * 2ull;
+                wf.act_pixel[c] = pixel;
+                wf.act_info[c] = (level + 1) | (in_object ? 256 : 0);
+                child_refl = c;
+              }
+              if (do_refract) {
+                const int c = (int)(base + n_refl + (unsigned)__popc(refr_mask & below));
+                Count<DBG>(cnt, kRefract);
+                const D3 rdir = Normalized(m_d);                                      // mythtracer.cc:208-212
+                Store3(wf.act_point + (size_t)c * 3, Add(P, MulS(rdir, 0.00001)));    // mythtracer.cc:214-218
+                Store3(wf.act_dir + (size_t)c * 3, rdir);
+                wf.act_coef[c] = coef;
+                wf.act_path[c] = path * 2ull + 1ull;
+                wf.act_pixel[c] = pixel;
+                wf.act_info[c] = (level + 1) | (in_object ? 0 : 256);
+                child_refr = c;
+              }
+              __threadfence();
+              if (child_refl >= 0) asm volatile("st.volatile.global.u32 [%0], %1;" : : "l"(wf.act_ready + child_refl), "r"(epoch) : "memory");
+              if (child_refr >= 0) asm volatile("st.volatile.global.u32 [%0], %1;" : : "l"(wf.act_ready + child_refr), "r"(epoch) : "memory");
+            }
+          }
+        }
+        if (stop_all) break;
+        // this batch's activations spawn nothing else: they leave the count (their children are in it already)
+        if (lane == 0u) atomicAdd(wf.qctl + kQPending, 0u - n);
+        // the links and the material are final now
+        if (mine) {
+          wf.act_mtl[act] = material;
+          wf.act_refl[act] = child_refl;
+          wf.act_refr[act] = child_refr;
+        }
+        walking = lit && sc.n_lights > 0;
+      } else if (walking) {
+        // ---- one shadow segment came back (mythtracer.cc:104-156) ----
+        bool light_done = false;
+        segments++;
+        if (slot < 0) {
+          light_done = true;
+        } else if (t > light_distance) {
+          light_done = true;
+        } else {
+          const int smtl = __ldg(&sc.shade[slot].material);
+          const double str = smtl >= 0 ? __ldg(&sc.materials[smtl].transparency) : 0.0;
+          if (str == 0.0) {
+            St3q(st.power, Mk(0.0, 0.0, 0.0));
+            in_shadow = true;
+            light_done = true;
+          } else {
+            D3 power = Ld3q(st.power);
+            if (!through) {
+              power = MulV(power, MulS(Load3(sc.materials[smtl].transmission_filter), str));
+              St3q(st.power, power);
+            }
+            through = !through;
+            const D3 ldir = Ld3q(st.ldir);
+            const D3 to = Add(Ld3q(st.seg_start), MulS(ldir, 0.00001));
+            const D3 seg_start = Add(Add(to, MulS(ldir, t)), MulS(ldir, 0.0000001));  // mythtracer.cc:137
+            St3q(st.seg_start, seg_start);
+            const D3 P = Ld3q(st.P);
+            if (SqrDist(P, seg_start) > SqrDist(P, Load3(sc.lights[li].position))) {  // mythtracer.cc:141-145
+              light_done = true;
+            } else if (power.x <= 0.001 && power.y <= 0.001 && power.z <= 0.001) {
+              St3q(st.power, Mk(0.0, 0.0, 0.0));
+              in_shadow = true;
+              light_done = true;
+            }
+          }
+        }
+        if (light_done) {
+          // ---- this light is settled: Phong terms (mythtracer.cc:159-177) ----
+          const mtb_light *lt = sc.lights + li;
+          const mtb_material *m = sc.materials + material;
+          sig += Mix64(path, 2ull + (unsigned long long)li, (in_shadow ? 1ull : 0ull) | ((unsigned long long)segments << 1));
+          const D3 lamb = Load3(lt->ambient);
+          D3 power = Ld3q(st.power);
+          power.x = SMax(power.x, lamb.x);
+          power.y = SMax(power.y, lamb.y);
+          power.z = SMax(power.z, lamb.z);
+          const D3 surface = Ld3q(st.surface);
+          D3 color = Ld3q(st.color);
+          color = Add(color, MulV(MulV(MulS(MulV(Load3(m->diffuse), surface), Dot(Ld3q(st.normal), Ld3q(st.ldir))), Load3(lt->diffuse)), power));
+          if (!in_shadow) {
+            const double refl_dot = Dot(Neg(Ld3q(st.m_d)), Ld3q(st.reflected));
+            if (refl_dot > 0) {
+              color = Add(color, MulV(MulS(MulV(Load3(m->specular), surface), pow(refl_dot, m->specular_exp)), Load3(lt->specular)));
+            }
+          }
+          St3q(st.color, color);
+          li++;
+          walking = li < sc.n_lights;
+        } else {
+          continue;  // next segment of the same light
+        }
+      }
+      if (!walking) break;
+      // ---- start the shadow walk of light li (mythtracer.cc:79-94) ----
+      {
+        const mtb_light *lt = sc.lights + li;
+        const D3 P = Ld3q(st.P);
+        St3q(st.ldir, Normalized(Sub(Load3(lt->position), P)));
+        St3q(st.color, Add(Ld3q(st.color), MulV(Load3(lt->ambient), Ld3q(st.surface))));  // mythtracer.cc:83-84
+        St3q(st.power, Mk(1.0, 1.0, 1.0));
+        St3q(st.seg_start, P);
+        in_shadow = false;
+        through = false;
+        segments = 0;
       }
     }
-
-    // ---- children -> queue, published before this warp walks its shadow segments.  The warp's reflection children
-    // are stored first, then its refraction children: neighbouring entries (= the lanes of some warp later) are rays
-    // of the same kind from neighbouring pixels ----
-    const unsigned refl_mask = __ballot_sync(0xffffffffu, do_reflect);
-    const unsigned refr_mask = __ballot_sync(0xffffffffu, do_refract);
-    const unsigned n_refl = (unsigned)__popc(refl_mask), total = n_refl + (unsigned)__popc(refr_mask);
-    int child_refl = -1, child_refr = -1;
-    bool overflow = false;
-    if (total != 0u) {
-      unsigned base = 0;
-      if (lane == 0u) {
-        atomicAdd(wf.qctl + kQPending, total);  // counted before they can be seen: the count never runs low
-        base = atomicAdd(wf.qctl + kQTail, total);
-      }
-      base = __shfl_sync(0xffffffffu, base, 0);
-      overflow = (unsigned long long)base + total > (unsigned long long)wf.act_cap;
-      if (!overflow) {
-        if (do_reflect) {
-          const int c = (int)(base + (unsigned)__popc(refl_mask & below));
-          Count<DBG>(cnt, kReflect);
-          Store3(wf.act_point + (size_t)c * 3, Add(P, MulS(reflected, 0.0001)));  // mythtracer.cc:70-75
-          Store3(wf.act_dir + (size_t)c * 3, reflected);
-          wf.act_coef[c] = coef * refl;
-          wf.act_path[c] = path * 2ull;
-          wf.act_pixel[c] = pixel;
-          wf.act_info[c] = (level + 1) | (in_object ? 256 : 0);
-          child_refl = c;
-        }
-        if (do_refract) {
-          const int c = (int)(base + n_refl + (unsigned)__popc(refr_mask & below));
-          Count<DBG>(cnt, kRefract);
-          const D3 rdir = Normalized(d);                                        // mythtracer.cc:208-212
-          Store3(wf.act_point + (size_t)c * 3, Add(P, MulS(rdir, 0.00001)));    // mythtracer.cc:214-218
-          Store3(wf.act_dir + (size_t)c * 3, rdir);
-          wf.act_coef[c] = coef;
-          wf.act_path[c] = path * 2ull + 1ull;
-          wf.act_pixel[c] = pixel;
-          wf.act_info[c] = (level + 1) | (in_object ? 0 : 256);
-          child_refr = c;
-        }
-        __threadfence();
-        if (child_refl >= 0) asm volatile("st.volatile.global.u32 [%0], %1;" : : "l"(wf.act_ready + child_refl), "r"(epoch) : "memory");
-        if (child_refr >= 0) asm volatile("st.volatile.global.u32 [%0], %1;" : : "l"(wf.act_ready + child_refr), "r"(epoch) : "memory");
-      }
-    }
-    if (overflow) {
+    if (__any_sync(0xffffffffu, stop_all)) {
       if (lane == 0u) wf.ctrl[0] = 1u;
       break;
     }
-    // this batch's activations spawn nothing else: they leave the count (their children are in it already)
-    if (lane == 0u) atomicAdd(wf.qctl + kQPending, 0u - n);
-
-    // ---- shadow walks and the Phong sum of the hits, light by light (mythtracer.cc:78-178) ----
-    unsigned rays = live ? 1u : 0u;
-    if (lit) {
-      const mtb_material *m = sc.materials + material;
-      unsigned long long sig = 0ull;
-      for (int li = 0; li < sc.n_lights; li++) {
-        const mtb_light *lt = sc.lights + li;
-        const D3 lpos = Load3(lt->position);
-        const D3 ldir = Normalized(Sub(lpos, P));
-        const D3 lamb = Load3(lt->ambient);
-        color = Add(color, MulV(lamb, surface));  // mythtracer.cc:83-84
-        D3 power = Mk(1.0, 1.0, 1.0);
-        bool in_shadow = false, through = false;
-        unsigned segments = 0;
-        D3 seg_start = P;
-        for (;;) {  // mythtracer.cc:94-156
-          const D3 to = Add(seg_start, MulS(ldir, 0.00001));
-          const double light_distance = Dist(seg_start, lpos);
-          double ts = 0.0;
-          Count<DBG>(cnt, kShadow);
-          const int sslot = Trace<DBG>(sc, to, ldir, light_distance, &ts, cnt, fctx);
-          segments++;
-          if (sslot < 0) break;
-          if (ts > light_distance) break;
-          const int smtl = __ldg(&sc.shade[sslot].material);
-          const double str = smtl >= 0 ? __ldg(&sc.materials[smtl].transparency) : 0.0;
-          if (str == 0.0) {
-            power = Mk(0.0, 0.0, 0.0);
-            in_shadow = true;
-            break;
-          }
-          if (!through) power = MulV(power, MulS(Load3(sc.materials[smtl].transmission_filter), str));
-          through = !through;
-          seg_start = Add(Add(to, MulS(ldir, ts)), MulS(ldir, 0.0000001));
-          if (SqrDist(P, seg_start) > SqrDist(P, lpos)) break;
-          if (power.x <= 0.001 && power.y <= 0.001 && power.z <= 0.001) {
-            power = Mk(0.0, 0.0, 0.0);
-            in_shadow = true;
-            break;
-          }
-        }
-        rays += segments;
-        sig += Mix64(path, 2ull + (unsigned long long)li, (in_shadow ? 1ull : 0ull) | ((unsigned long long)segments << 1));
-        power.x = SMax(power.x, lamb.x);
-        power.y = SMax(power.y, lamb.y);
-        power.z = SMax(power.z, lamb.z);
-        color = Add(color, MulV(MulV(MulS(MulV(Load3(m->diffuse), surface), Dot(normal, ldir)), Load3(lt->diffuse)), power));
-        if (!in_shadow) {
-          const double refl_dot = Dot(Neg(d), reflected);
-          if (refl_dot > 0) {
-            color = Add(color, MulV(MulS(MulV(Load3(m->specular), surface), pow(refl_dot, m->specular_exp)), Load3(lt->specular)));
-          }
-        }
-      }
-      if (rp.sig_shadow != nullptr && sc.n_lights > 0) atomicAdd(reinterpret_cast<unsigned long long *>(rp.sig_shadow) + pixel, sig);
-    }
     if (mine) {
-      wf.act_mtl[act] = material;
-      wf.act_refl[act] = child_refl;
-      wf.act_refr[act] = child_refr;
-      Store3(wf.act_color + (size_t)act * 3, color);
+      Store3(wf.act_color + (size_t)act * 3, Ld3q(st.color));
       if (live) {
-        traced += rays - 1u;
+        traced += rays;
+        if (lit && rp.sig_shadow != nullptr && sc.n_lights > 0) atomicAdd(reinterpret_cast<unsigned long long *>(rp.sig_shadow) + pixel, sig);
         if (rp.n_rays != nullptr) atomicAdd(rp.n_rays + pixel, rays);
         WfChargeTile(rp, pixel, rays);
       }

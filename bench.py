@@ -342,7 +342,7 @@ def _run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_COUNT_WORK, MTB_FLAG_HYBRID, MTB_FLAG_MEGAKERNEL, MTB_FLAG_WAVEFRONT, tiles
+    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_COUNT_WORK, MTB_FLAG_HYBRID, MTB_FLAG_MEGAKERNEL, MTB_FLAG_QUEUE, MTB_FLAG_WAVEFRONT, tiles
     from mythtracer_b200 import build as mtb_build
 
     rank = int(os.environ.get("RANK", "0"))
@@ -369,7 +369,7 @@ def _run_ours(args):
             files, cfg = load_workload()  # reuses the files rank 0 wrote
     W, H, depth = cfg["width"], cfg["height"], cfg["depth"]
 
-    base_flags = {"wavefront": MTB_FLAG_WAVEFRONT, "mega": MTB_FLAG_MEGAKERNEL, "hybrid": MTB_FLAG_HYBRID, "auto": 0}[args.pipeline]
+    base_flags = {"wavefront": MTB_FLAG_WAVEFRONT, "mega": MTB_FLAG_MEGAKERNEL, "hybrid": MTB_FLAG_HYBRID, "queue": MTB_FLAG_QUEUE, "auto": 0}[args.pipeline]
     # Launched plainly (no torchrun) with --gpus N > 1: ONE process, one context over N devices -- the
     # in-process form (strips interleaved over the devices, tiles stored straight into device 0's frame over NVLink).
     inproc = 1
@@ -626,7 +626,7 @@ def _run_ours(args):
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": config_dict(files, cfg, world * inproc, {"launch": launch, "gather": gather,
-                                                           "pipeline": pipeline_used, "pipeline_choice": args.pipeline, "hybrid_share": mt.hybrid_share(), "autotune_ms": {"mega": tune_mega_ms, "wavefront": tune_wf_ms},
+                                                           "pipeline": pipeline_used, "pipeline_choice": args.pipeline, "hybrid_share": mt.hybrid_share(), "autotune_ms": {"mega": tune_mega_ms, "queue": tune_wf_ms},
                                                            "rays_per_frame": rays_per_frame, "scene_load_s": load_s, "load_stages_ms": load_stages,
                                                            "octree_nodes": info["n_nodes"], "tree_depth": info["tree_depth"],
                                                            "device_scene_bytes": info["device_bytes"], "commit": git_head(),
@@ -655,7 +655,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-workloads", action="store_true", default=os.environ.get("MTB_BENCH_OTHERS", "1") == "0")
-    ap.add_argument("--pipeline", default=os.environ.get("MTB_PIPELINE", "auto"), choices=["auto", "mega", "wavefront", "hybrid"])
+    ap.add_argument("--pipeline", default=os.environ.get("MTB_PIPELINE", "auto"), choices=["auto", "mega", "wavefront", "hybrid", "queue"])
     ap.add_argument("--gather", default=os.environ.get("MTB_GATHER", "peer"), choices=["peer", "nccl"],
                     help="N > 1 under torchrun: direct peer stores into rank 0's frame (default) or an NCCL gather (A/B)")
     args = ap.parse_args()

@@ -252,8 +252,9 @@ int mtb_frame_read(mtb_context *ctx, const void *d_ptr, size_t offset, size_t by
  * read; synchronises every device of the context and resets the counters. */
 int mtb_read_counters(mtb_context *ctx, mtb_stats *stats);
 
-/* Automatic pipeline choice on device 0: 0 = megakernel, 1 = wavefront, 2 = hybrid, -1 = still measuring; the
- * timed megakernel / wavefront frames (ms) are returned when the pointers are non-NULL. */
+/* Pipeline in use on device 0: 0 = megakernel, 1 = wavefront (level by level; only when forced), 2 = hybrid,
+ * 3 = queue pipeline (the wavefront candidate of the automatic choice), -1 = still measuring; the timed megakernel /
+ * queue-pipeline frames (ms) of the automatic choice are returned when the pointers are non-NULL. */
 int mtb_pipeline_in_use(const mtb_context *ctx, float *mega_ms, float *wavefront_ms);
 /* Hybrid frames: the share of the frame's rays that currently goes through the wavefront on device 0 (steered frame by
  * frame from the measured times of the two halves). */

@@ -510,11 +510,11 @@ class MythTracer:
         return out
 
     def pipeline_in_use(self):
-        """('mega' | 'wavefront' | 'hybrid' | 'measuring', mega_ms, wavefront_ms) of the automatic choice on device 0."""
+        """('mega' | 'wavefront' | 'hybrid' | 'queue' | 'measuring', mega_ms, queue_ms) on device 0."""
         a, b = ctypes.c_float(0), ctypes.c_float(0)
         rc = self._lib.mtb_pipeline_in_use(self._ctx, ctypes.cast(ctypes.byref(a), ctypes.c_void_p),
                                            ctypes.cast(ctypes.byref(b), ctypes.c_void_p))
-        return {0: "mega", 1: "wavefront", 2: "hybrid"}.get(rc, "measuring"), a.value, b.value
+        return {0: "mega", 1: "wavefront", 2: "hybrid", 3: "queue"}.get(rc, "measuring"), a.value, b.value
 
     def hybrid_share(self) -> float:
         return float(self._lib.mtb_hybrid_share(self._ctx))

@@ -795,6 +795,7 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
     // a peer's scratch frame must not be overwritten while device 0 still gathers the previous one
     if (g > 0) MTB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->dev[0].ev_gathered, 0));
     bool wavefront = (ctx->flags & (MTB_FLAG_WAVEFRONT | MTB_FLAG_QUEUE)) != 0;
+    bool queue = (ctx->flags & MTB_FLAG_QUEUE) != 0;  // the wavefront as one persistent kernel over a ray queue
     bool hybrid = (ctx->flags & MTB_FLAG_HYBRID) != 0 && !wavefront;
     if ((ctx->flags & (MTB_FLAG_WAVEFRONT | MTB_FLAG_QUEUE | MTB_FLAG_MEGAKERNEL | MTB_FLAG_HYBRID)) == 0 && blocks > 0) {
       // automatic: measure both pipelines on the first frames of this geometry, then keep the faster
@@ -816,10 +817,12 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
         }
       }
       if (d.tune_stage < kTuneDecided) d.tune_stage++;
-      // stage now: 1 = megakernel (cold tile order), 2 = megakernel (timed), 3 = wavefront (cold: buffers are
-      // allocated), 4 = wavefront (timed), 5 .. kTuneDecided - 1 = hybrid (the split settles; the last one is timed),
-      // kTuneDecided = decided
+      // stage now: 1 = megakernel (cold tile order), 2 = megakernel (timed), 3 = queue pipeline (cold: buffers are
+      // allocated), 4 = queue pipeline (timed), 5 .. kTuneDecided - 1 = hybrid (the split settles; the last one is
+      // timed), kTuneDecided = decided.  (The wavefront candidate is its queue form: measured faster than the
+      // level-by-level form at every share of the C3 frame)
       wavefront = d.tune_stage == 3 || d.tune_stage == 4 || (d.tune_stage == kTuneDecided && d.tune_choice == 1);
+      queue = wavefront;
       hybrid = (d.tune_stage >= 5 && d.tune_stage < kTuneDecided) || (d.tune_stage == kTuneDecided && d.tune_choice == 2);
     }
     if (ctx->l2_persist_mb > 0 && d.l2_window_stream != s) {
@@ -834,8 +837,7 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
         MTB_CUDA(ctx, cudaMemsetAsync(d.sig_shadow.ptr, 0, npx * 8, s));
         MTB_CUDA(ctx, cudaMemsetAsync(d.n_rays.ptr, 0, npx * 4, s));
       }
-      const int wrc = (ctx->flags & MTB_FLAG_QUEUE) != 0 ? RunWavefrontQueue(ctx, &d, p, blocks, debug_build, s)
-                                                         : RunWavefront(ctx, &d, p, blocks, debug_build, s);
+      const int wrc = queue ? RunWavefrontQueue(ctx, &d, p, blocks, debug_build, s) : RunWavefront(ctx, &d, p, blocks, debug_build, s);
       if (wrc != MTB_OK) return wrc;
     } else {
       const int mblocks = blocks;
@@ -1350,10 +1352,12 @@ int mtb_pipeline_in_use(const mtb_context *ctx, float *mega_ms, float *wavefront
   const DeviceState &d = ctx->dev[0];
   if (mega_ms != nullptr) *mega_ms = d.tune_ms[0];
   if (wavefront_ms != nullptr) *wavefront_ms = d.tune_ms[1];
+  if ((ctx->flags & MTB_FLAG_QUEUE) != 0) return 3;
   if ((ctx->flags & MTB_FLAG_WAVEFRONT) != 0) return 1;
   if ((ctx->flags & MTB_FLAG_HYBRID) != 0) return 2;
   if ((ctx->flags & MTB_FLAG_MEGAKERNEL) != 0) return 0;
-  return d.tune_stage >= kTuneDecided ? d.tune_choice : -1;
+  if (d.tune_stage < kTuneDecided) return -1;
+  return d.tune_choice == 1 ? 3 : d.tune_choice;
 }
 
 float mtb_hybrid_share(const mtb_context *ctx) { return ctx == nullptr || ctx->dev.empty() ? 0.0f : ctx->dev[0].hybrid_share; }

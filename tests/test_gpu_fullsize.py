@@ -60,8 +60,9 @@ def _compare(got_rgb, got_line_no, z, what):
 
 
 def test_c3_full_frame_equals_the_reference(product_lib, scene_dir):
-    """Every pixel of the 1920x1080 C3 frame against the reference's own render, megakernel / wavefront / hybrid."""
-    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_HYBRID, MTB_FLAG_MEGAKERNEL, MTB_FLAG_WAVEFRONT
+    """Every pixel of the 1920x1080 C3 frame against the reference's own render: megakernel, wavefront (level by level),
+    queue pipeline, hybrid."""
+    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_HYBRID, MTB_FLAG_MEGAKERNEL, MTB_FLAG_QUEUE, MTB_FLAG_WAVEFRONT
     z, files, cfg = _golden("C3", scene_dir)
     W, H = cfg["width"], cfg["height"]
     assert len(z["rows"]) == H
@@ -69,7 +70,7 @@ def test_c3_full_frame_equals_the_reference(product_lib, scene_dir):
     assert mt.LoadObj(files.obj_path), mt.last_error()
     mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]
     shas = set()
-    for name, flags, frames in (("megakernel", MTB_FLAG_MEGAKERNEL, 2), ("wavefront", MTB_FLAG_WAVEFRONT, 2), ("hybrid", MTB_FLAG_HYBRID, 3)):
+    for name, flags, frames in (("megakernel", MTB_FLAG_MEGAKERNEL, 2), ("wavefront", MTB_FLAG_WAVEFRONT, 2), ("queue", MTB_FLAG_QUEUE, 2), ("hybrid", MTB_FLAG_HYBRID, 3)):
         mt.set_flags(flags)
         for frame in range(frames):  # (later frames: warm tile order / hybrid split / grids sized from the last frame)
             got = mt.render_chunk(files.camera, W, H, 0, 0, W, H, debug=True)
@@ -103,7 +104,7 @@ def test_wavefront_queue_overflow_is_repaired_on_the_device(product_lib, oracle_
     """Queues sized for one ray per pixel overflow at the first bounce of a reflective + transparent scene: the frame
     must still be exact in every tap and counter (the repair launch renders it), and the queues must have grown by
     the time a later frame goes through the wavefront kernels themselves."""
-    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_COUNT_WORK, MTB_FLAG_WAVEFRONT
+    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_COUNT_WORK, MTB_FLAG_QUEUE, MTB_FLAG_WAVEFRONT
     monkeypatch.setenv("MTB_WF_QUEUE_FACTOR", "1")
     monkeypatch.setenv("MTB_WF_ACT_FACTOR", "1")
     files, cfg = scenes.config_scene("C1", scene_dir)
@@ -112,7 +113,7 @@ def test_wavefront_queue_overflow_is_repaired_on_the_device(product_lib, oracle_
     orc.set_lights(files.lights)
     cpu = orc.render(files.camera, w, h, depth=4, taps=True)
     assert cpu["stats"]["reflect"] + cpu["stats"]["refract"] > 0
-    for flags in (MTB_FLAG_WAVEFRONT, MTB_FLAG_WAVEFRONT | MTB_FLAG_COUNT_WORK):
+    for flags in (MTB_FLAG_WAVEFRONT, MTB_FLAG_WAVEFRONT | MTB_FLAG_COUNT_WORK, MTB_FLAG_QUEUE, MTB_FLAG_QUEUE | MTB_FLAG_COUNT_WORK):
         mt = MythTracer(max_depth=4, flags=flags)
         assert mt.LoadObj(files.obj_path), mt.last_error()
         mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]

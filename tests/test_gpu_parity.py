@@ -500,12 +500,12 @@ def test_automatic_pipeline_choice(product_lib, oracle_mod, scene_dir):
         assert np.array_equal(out["rgb"], cpu["rgb"])
         assert out["stats"]["rays"] == cpu["stats"]["rays"]
         states.append(mt.pipeline_in_use()[0])
-    assert states[0] == "measuring" and states[10] == "measuring" and states[-1] in ("mega", "wavefront", "hybrid")
+    assert states[0] == "measuring" and states[10] == "measuring" and states[-1] in ("mega", "queue", "hybrid")
     assert 0.0 < mt.hybrid_share() < 1.0
     _, mega_ms, wf_ms = mt.pipeline_in_use()
     assert mega_ms > 0 and wf_ms > 0
     if states[-1] != "hybrid":
-        assert states[-1] == ("wavefront" if wf_ms < mega_ms else "mega")
+        assert states[-1] == ("queue" if wf_ms < mega_ms else "mega")
     # a different geometry starts measuring again
     mt.render_chunk(files.camera, w, h, 0, 0, w // 2, h)
     assert mt.pipeline_in_use()[0] == "measuring"

@@ -454,8 +454,9 @@ def _run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- warm-up, then K timed steps (device-resident).  The automatic pipeline choice measures both
-    # pipelines and the hybrid split during the first six frames of a geometry, so the warm-up covers at least seven ----
+    # ---- warm-up, then K timed steps (device-resident).  The automatic pipeline choice measures the megakernel, the
+    # queue pipeline and the hybrid split during the first 12 frames of a geometry and decides at the 13th, so the
+    # warm-up covers at least 14 (reported as "warmup" in the JSON line) ----
     n_warm = max(args.warmup, 14 if args.pipeline == "auto" else (10 if args.pipeline == "hybrid" else 3))
     for _ in range(n_warm):
         step_device()
@@ -501,7 +502,11 @@ def _run_ours(args):
     frame_sha = hashlib.sha256(read_frame(last_ptr).tobytes()).hexdigest() if rank == 0 else None
     t = torch.tensor([elapsed_ms, float(counters["rays"]), float(launches), kernel_ms_mean], dtype=torch.float64, device=dev)
     kernel_ms_max = kernel_ms_mean
+    kernel_ms_ranks = [kernel_ms_mean]
     if world > 1:
+        per_rank = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(per_rank, t[3:4].clone())
+        kernel_ms_ranks = [round(float(x[0]), 4) for x in per_rank]
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
@@ -592,8 +597,9 @@ def _run_ours(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
                 "dram_frac": (traffic / (kernel_ms_mean * 1e-3) / 1e9 / peak) if traffic else None,
-                "kernel": {"mega": "RenderMega", "hybrid": "RenderMega + wavefront kernels on the most expensive tiles, concurrently"}.get(pipeline_used, "wavefront pipeline (WfTrace + WfShadow dominate)"),
-                "kernel_ms": kernel_ms_mean, "kernel_ms_max_over_ranks": kernel_ms_max,
+                "kernel": {"mega": "RenderMega", "hybrid": "RenderMega + wavefront kernels on the most expensive tiles, concurrently",
+                           "queue": "WfQueue (one persistent kernel over the device-side ray queue; + WfResolveTree)"}.get(pipeline_used, "wavefront pipeline (WfTrace + WfShadow dominate)"),
+                "kernel_ms": kernel_ms_mean, "kernel_ms_max_over_ranks": kernel_ms_max, "kernel_ms_per_rank": kernel_ms_ranks,
                 "kernel_ms_how": "mean over the K timed steps of CUDA events recorded around this rank's render call inside the timed loop (after the L2 flush)",
                 "algorithmic_bytes_per_launch": my_alg, "peak_source": peak_src,
                 "note": "frac counts ALGORITHMIC operand bytes (SURVEY 8d), most of which are served by L1/L2 (the BVH top and neighbouring rays' nodes are shared); dram_frac = ncu DRAM bytes of the same launch / time / peak is the HBM utilisation proper",

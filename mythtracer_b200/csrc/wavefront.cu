@@ -479,6 +479,12 @@ __global__ void __launch_bounds__(256) WfResolve(RenderParams rp, WfBuffers wf, 
 #define MTB_QUEUE_MIN_BLOCKS 14  // 64-thread blocks at 72 registers, the megakernel's shape
 #endif
 constexpr unsigned kQueueSpinLimit = 1u << 22;
+#ifndef MTB_QUEUE_MIN_TICKET
+#define MTB_QUEUE_MIN_TICKET 4
+#endif
+#ifndef MTB_QUEUE_DRAIN
+#define MTB_QUEUE_DRAIN 1  // 0: tickets are always 32 wide
+#endif
 
 __device__ __forceinline__ unsigned LdVolatile(const uint32_t *p) {
   unsigned v;
@@ -519,19 +525,37 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
   }
   const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
   unsigned traced = 0;
-  // The warp's ticket: it owns activations [ticket, ticket + 32) and has handed `done` of them to its lanes so far.
-  unsigned ticket = 0, done = 32;
+  // The warp's ticket: it owns activations [ticket, ticket + tsize) and has handed `done` of them to its lanes so far.
+  // Tickets are 32 wide (primary rays: whole groups of 8x4 pixels) until the queue runs dry at the very end of the
+  // frame: when fewer rays are queued than MTB_QUEUE_DRAIN per warp of the grid, a warp takes 16, 8 or 4, so that the
+  // last rays spread over more, emptier warps - a warp runs as long as its slowest ray, and the kernel as long as its
+  // last warp.  (Smaller tickets any earlier cost more than they gain: measured with thresholds 6x higher, C3 share
+  // 1/8: 1.86 ms instead of 1.67.)
+  const unsigned n_warps = gridDim.x * (kBlockThreads / 32);
+  unsigned ticket = 0, tsize = 32, done = 32;
   for (;;) {
-    if (done >= 32u) {
-      if (lane == 0u) ticket = atomicAdd(wf.qctl + kQHead, 32u);  // fetch-and-add: never fails, never retried
+    if (done >= tsize) {
+      if (lane == 0u) {
+        const unsigned head = LdVolatile(wf.qctl + kQHead);
+        tsize = 32u;
+        if (head >= (unsigned)slots) {  // (the head only grows: a ticket taken now lies behind the primary rays too)
+          const unsigned tail = LdVolatile(wf.qctl + kQTail);
+          const unsigned backlog = tail > head ? tail - head : 0u;
+          const unsigned unit = n_warps * MTB_QUEUE_DRAIN;
+          tsize = backlog >= 4u * unit ? 32u : (backlog >= 2u * unit ? 16u : (backlog >= unit ? 8u : 4u));
+          if (MTB_QUEUE_MIN_TICKET < 4 && backlog < unit / 2u) tsize = backlog >= unit / 4u ? 2u : (unsigned)MTB_QUEUE_MIN_TICKET;
+        }
+        ticket = atomicAdd(wf.qctl + kQHead, tsize);  // fetch-and-add: never fails, never retried
+      }
       ticket = __shfl_sync(0xffffffffu, ticket, 0);
+      tsize = __shfl_sync(0xffffffffu, tsize, 0);
       done = 0;
     }
     if (ticket >= (unsigned)wf.act_cap) break;  // beyond the table: such entries are never produced (overflow is flagged)
     // ---- how many of the ticket's entries exist by now?  Primary rays always do; queued ones once the tail has
     // passed them.  A partly filled ticket is not waited for for long: what is there goes out to the first lanes
     // (late in a frame that spreads the few remaining rays over many warps by itself) ----
-    unsigned n = 32u - done;
+    unsigned n = tsize - done;
     bool over = false;
     if (ticket >= (unsigned)slots) {
       unsigned waited = 0;
@@ -547,12 +571,12 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
         pending = __shfl_sync(0xffffffffu, pending, 0);
         stop = __shfl_sync(0xffffffffu, stop, 0);
         const unsigned first = ticket + done;
-        const unsigned avail = tail > first ? (tail - first < 32u - done ? tail - first : 32u - done) : 0u;
+        const unsigned avail = tail > first ? (tail - first < tsize - done ? tail - first : tsize - done) : 0u;
         if (stop != 0u || (avail == 0u && pending == 0u)) {
           over = true;
           break;
         }
-        if (avail == 32u - done || (avail > 0u && waited >= 2u)) {
+        if (avail == tsize - done || (avail > 0u && waited >= 2u)) {
           n = avail;
           break;
         }

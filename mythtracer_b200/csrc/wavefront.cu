@@ -529,8 +529,8 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
   // Tickets are 32 wide (primary rays: whole groups of 8x4 pixels) until the queue runs dry at the very end of the
   // frame: when fewer rays are queued than MTB_QUEUE_DRAIN per warp of the grid, a warp takes 16, 8 or 4, so that the
   // last rays spread over more, emptier warps - a warp runs as long as its slowest ray, and the kernel as long as its
-  // last warp.  (Smaller tickets any earlier cost more than they gain: measured with thresholds 6x higher, C3 share
-  // 1/8: 1.86 ms instead of 1.67.)
+  // last warp.  Measured on C3, share 1/8 of the frame: always 32 wide 1.67 ms; this rule 1.50; thresholds 4x higher
+  // 1.67, 6x higher 1.86 (small tickets any earlier cost more than they gain); tickets down to 2 or 1: 1.49.
   const unsigned n_warps = gridDim.x * (kBlockThreads / 32);
   unsigned ticket = 0, tsize = 32, done = 32;
   for (;;) {

@@ -1,0 +1,19 @@
+#!/bin/bash
+# round 2, 8-GPU run with the queue pipeline: torchrun bench at N = 8 / 4 / 2 (direct peer stores), in-process form
+mkdir -p gpurun_out
+run() { # name nproc steps
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $2 --steps $3 --warmup 5 > gpurun_out/r2x_$1.json 2> gpurun_out/r2x_$1.err; echo "$1 rc=$?"
+}
+run n8 8 20
+run n8_long 8 200
+run n4 4 20
+run n2 2 20
+timeout 900 python bench.py --gpus 8 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2x_inproc8.json 2> gpurun_out/r2x_inproc8.err; echo "inproc8 rc=$?"
+for f in gpurun_out/r2x_n8.json gpurun_out/r2x_n8_long.json gpurun_out/r2x_n4.json gpurun_out/r2x_n2.json gpurun_out/r2x_inproc8.json; do python - "$f" <<'PY'
+import json,sys
+try:
+    j=json.load(open(sys.argv[1]))
+    print(sys.argv[1].split('/')[-1], "value %.1f ms %.3f e2e %.1f (%.3f ms) kernel_ms %.3f max %.3f ranks %s ref_eq %s pipeline %s launches %d" % (j["value"], j["ms_per_step"], j["e2e"]["value"], j["e2e"]["ms_per_step"], j["roofline"]["kernel_ms"], j["roofline"]["kernel_ms_max_over_ranks"], j["roofline"].get("kernel_ms_per_rank"), j["frame_equals_reference"], j["config"]["pipeline"], j["gpu_launches"]))
+except Exception as e: print(sys.argv[1], "unreadable", e)
+PY
+done

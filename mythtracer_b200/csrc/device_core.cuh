@@ -810,6 +810,9 @@ __device__ __forceinline__ bool DegeneratePassage(const DeviceScene &sc, int slo
 #ifndef MTB_PREFETCH_KIDS
 #define MTB_PREFETCH_KIDS 0
 #endif
+#ifndef MTB_SPEC_LEAF
+#define MTB_SPEC_LEAF 0
+#endif
 template <bool DBG>
 __device__ __forceinline__ int TraceFast(const DeviceScene &sc, FastMem *m, const FastRay &r, float prune0, double *t_out, bool *ambiguous,
                                          unsigned long long *cnt, const FastCtx &fc) {
@@ -820,6 +823,21 @@ __device__ __forceinline__ int TraceFast(const DeviceScene &sc, FastMem *m, cons
   FmStore(fc, m, kFmLo2, CUDART_INF);
   int node = 0;
   unsigned visits = 0;  // (counting build only)
+  // next subtree from the stack that still starts in front of the pruning distance; kFastExit when there is none
+#define MTB_FAST_POP()                                                   \
+  do {                                                                   \
+    node = kFastExit;                                                    \
+    while (sp > 0) {                                                     \
+      const unsigned long long top__ = FastPop(fc, stack, --sp);         \
+      if (__uint_as_float((unsigned)(top__ >> 32)) <= prune) {           \
+        node = (int)(unsigned)top__;                                     \
+        break;                                                           \
+      }                                                                  \
+    }                                                                    \
+  } while (0)
+#if MTB_SPEC_LEAF
+  int pend = kFastExit;  // a leaf that was reached but not tested yet (kFastExit: none)
+#endif
   for (;;) {
     while (node >= 0) {
       if (DBG) visits++;
@@ -863,18 +881,25 @@ __device__ __forceinline__ int TraceFast(const DeviceScene &sc, FastMem *m, cons
       } else if (hr) {
         node = kids.y;
       } else {
-        node = kFastExit;
-        while (sp > 0) {
-          const unsigned long long top = FastPop(fc, stack, --sp);
-          if (__uint_as_float((unsigned)(top >> 32)) <= prune) {
-            node = (int)(unsigned)top;
-            break;
-          }
-        }
+        MTB_FAST_POP();
       }
+#if MTB_SPEC_LEAF
+      // Speculative walk (Aila & Laine): the first leaf a lane reaches is parked and the lane keeps walking - the other
+      // lanes of the warp are still in this loop anyway - until it reaches a second leaf or runs out of nodes.  The
+      // parked leaf has not lowered the pruning distance yet, so the lane may visit nodes it would have skipped; which
+      // candidates are EVALUATED before the search ends can change, which triangle wins cannot (section 4: every
+      // accepted hit is exact, a pruned subtree starts behind t* + 2 e*).
+      if (node < 0 && node != kFastExit && pend == kFastExit) {
+        pend = node;
+        MTB_FAST_POP();
+      }
+#endif
     }
+#if MTB_SPEC_LEAF
+    if (node == kFastExit && pend == kFastExit) break;
+#else
     if (node == kFastExit) break;
-    const unsigned leaf = ~(unsigned)node;
+#endif
     {
       MTB_FAST_BARRIER(m);
       Ray rr;  // FP64 origin and inverse direction: once per leaf visit
@@ -883,18 +908,25 @@ __device__ __forceinline__ int TraceFast(const DeviceScene &sc, FastMem *m, cons
       rr.sx = rr.inv.x < 0.0;
       rr.sy = rr.inv.y < 0.0;
       rr.sz = rr.inv.z < 0.0;
+#if MTB_SPEC_LEAF
+      // the parked leaf first (it was reached first), then the one the walk stopped at
+#pragma unroll 1
+      for (int k = 0; k < 2; k++) {
+        const int lf = k == 0 ? pend : node;
+        if (lf == kFastExit) continue;
+        const unsigned leaf = ~(unsigned)lf;
+        for (unsigned s = leaf >> 3, e = s + (leaf & 7u); s < e; s++) TestSlotFast<DBG>(sc.gslots + s, rr, fc, m, &slot, &prune, cnt);
+      }
+      pend = kFastExit;
+#else
+      const unsigned leaf = ~(unsigned)node;
       for (unsigned s = leaf >> 3, e = s + (leaf & 7u); s < e; s++) TestSlotFast<DBG>(sc.gslots + s, rr, fc, m, &slot, &prune, cnt);
+#endif
       MTB_FAST_BARRIER(m);
     }
-    node = kFastExit;
-    while (sp > 0) {
-      const unsigned long long top = FastPop(fc, stack, --sp);
-      if (__uint_as_float((unsigned)(top >> 32)) <= prune) {
-        node = (int)(unsigned)top;
-        break;
-      }
-    }
+    MTB_FAST_POP();
   }
+#undef MTB_FAST_POP
   if (DBG) {
     if (visits > 128u) Count<DBG>(cnt, kLongRays128), Count<DBG>(cnt, kLongVisits128, visits);
     if (visits > 512u) Count<DBG>(cnt, kLongRays512), Count<DBG>(cnt, kLongVisits512, visits);

@@ -273,8 +273,15 @@ def golden_frame_sha():
 
 
 def git_head():
+    """Commit of the tree: from git where there is one, else the stamp mythtracer_b200/build.py left next to the
+    built library (the GPU box gets a snapshot without .git)."""
     try:
         return subprocess.check_output(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], stderr=subprocess.DEVNULL, text=True).strip()
+    except Exception:
+        pass
+    try:
+        with open(os.path.join(ROOT, "mythtracer_b200", "build", "commit.txt")) as f:
+            return f.read().strip() or None
     except Exception:
         return None
 
@@ -581,6 +588,9 @@ def _run_ours(args):
 
     peak, peak_src = measured_peak()
     fp_peak, fp_src = measured_fp64_peak()
+    # (one context over several devices counts the work of all of them, the kernel time is one device's: its share)
+    my_alg /= inproc
+    my_flops /= inproc
     achieved = my_alg / (kernel_ms_mean * 1e-3) / 1e9
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")

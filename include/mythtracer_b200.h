@@ -142,6 +142,11 @@ typedef struct {
  * the right choice for a scene that is rendered a few times, the wrong one for an animation - hence opt-in.  The
  * rendered bytes are the same either way. */
 #define MTB_FLAG_DEVICE_BVH 4096u
+/* Two rays per lane (measurement aid): mtb_intersect_rays walks rays 2i and 2i+1 in ONE thread - two independent
+ * node-load chains in flight per lane (csrc/device_core.cuh, Trace2).  Results are identical to the one-ray-per-lane
+ * form; measured on B200 with the shadow rays of the C3 frame it is 6 % SLOWER, so the
+ * renderers do not use it. */
+#define MTB_FLAG_PAIR_RAYS 16384u
 #define MTB_FLAG_NO_TILE_ORDER 32u /* megakernel: always launch tiles in scanline order (A/B of the cost-aware launch order) */
 
 /* ---- life cycle -------------------------------------------------------------------------------- */

@@ -25,8 +25,27 @@ def _newest_source_mtime() -> float:
     return max(os.path.getmtime(p) for p in paths)
 
 
+COMMIT_STAMP = os.path.join(HERE, "build", "commit.txt")
+
+
+def stamp_commit() -> None:
+    """Records the git commit of the tree the library was built from (there is no .git on the GPU box: the stamp
+    travels with the built library and bench.py reports it as config.commit)."""
+    try:
+        head = subprocess.check_output(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], stderr=subprocess.DEVNULL, text=True).strip()
+        dirty = subprocess.check_output(["git", "-C", ROOT, "status", "--porcelain", "--", "mythtracer_b200", "include", "bench.py"],
+                                        stderr=subprocess.DEVNULL, text=True).strip()
+    except Exception:
+        return
+    os.makedirs(os.path.dirname(COMMIT_STAMP), exist_ok=True)
+    with open(COMMIT_STAMP, "w") as f:
+        f.write(head + ("+" if dirty else "") + "\n")
+
+
 def build(force: bool = False, verbose: bool = False, extra=(), variant: str = "") -> str:
     """variant: development A/B builds (extra -D flags) go to build/var_<variant>/lib.so; load with MTB_LIB_PATH."""
+    if not variant:
+        stamp_commit()
     lib_path = LIB if not variant else os.path.join(HERE, "build", "var_" + variant, "lib.so")
     if not force and os.path.exists(lib_path) and os.path.getmtime(lib_path) >= _newest_source_mtime():
         return lib_path

@@ -1028,6 +1028,187 @@ __device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Two rays per lane.  The fast traversal is latency-bound (a walk is a chain of dependent node
+// loads, half of them served by L2, with ~24 warps per SM to hide them), so a lane that walks TWO independent rays in
+// one loop - both node loads are issued before either is consumed - doubles the loads in flight per warp for ~20
+// registers.  The two rays are independent queries (the shadow segments of one hit towards two lights; two rays of a
+// batch): each keeps its own stack (local memory), its own FP64 scratch column (shared memory) and its own best hit,
+// and is answered exactly as Trace() would answer it alone - same candidates, same exact tests, same certification,
+// same fallback to the exact recursion.
+// ---------------------------------------------------------------------------------------------------
+#define MTB_DECLARE_FAST_CTX2(threads)                                                             \
+  __shared__ unsigned long long s_fast_scratch[2 * kFmWords * (threads)];                          \
+  const unsigned fast_base__ = (unsigned)__cvta_generic_to_shared(s_fast_scratch + threadIdx.x);   \
+  const FastCtx fctx{0u, fast_base__, (threads) * 8};                                              \
+  const FastCtx fctx_b{0u, fast_base__ + (unsigned)(kFmWords * (threads) * 8), (threads) * 8}
+
+struct PairQuery {
+  bool active;     // in: there is a ray
+  bool fast;       // (internal) the ray is inside the fast traversal's model
+  double t_limit;  // in: as Trace()
+  int slot;        // out: canonical slot of the hit, -1: none
+  double t;        // out
+};
+
+// Ray set-up of Trace(): stores the FP64 ray into the scratch column `fc`, returns the FP32 ray and the pruning limit.
+__device__ __forceinline__ bool FastSetup(const DeviceScene &sc, const D3 &o, const D3 &d, double t_limit, const FastCtx &fc, FastRay *fr,
+                                          float *prune0) {
+  const D3 inv = Mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
+  const bool regular = isfinite(inv.x) && isfinite(inv.y) && isfinite(inv.z) && inv.x != 0.0 && inv.y != 0.0 && inv.z != 0.0 &&
+                       isfinite(o.x) && isfinite(o.y) && isfinite(o.z);
+  const float R = sc.cull_radius;
+  const double ao = fmax(fmax(fabs(o.x), fabs(o.y)), fabs(o.z));
+  const double ai_max = fmax(fmax(fabs(inv.x), fabs(inv.y)), fabs(inv.z));
+  const double ai_min = fmin(fmin(fabs(inv.x), fabs(inv.y)), fabs(inv.z));
+  const bool fast = regular && sc.gnodes != nullptr && R > 0.0f && ao <= 8.0 * (double)R && ai_max <= 0x1p100 && ai_min >= 0x1p-100;
+  FmStore(fc, nullptr, kFmO + 0, o.x), FmStore(fc, nullptr, kFmO + 1, o.y), FmStore(fc, nullptr, kFmO + 2, o.z);
+  FmStore(fc, nullptr, kFmD + 0, d.x), FmStore(fc, nullptr, kFmD + 1, d.y), FmStore(fc, nullptr, kFmD + 2, d.z);
+  FmStore(fc, nullptr, kFmInv + 0, inv.x), FmStore(fc, nullptr, kFmInv + 1, inv.y), FmStore(fc, nullptr, kFmInv + 2, inv.z);
+  FmStore(fc, nullptr, kFmLo2, CUDART_INF);
+  fr->ix = (float)inv.x;
+  fr->iy = (float)inv.y;
+  fr->iz = (float)inv.z;
+  fr->nox = -((float)o.x * fr->ix);
+  fr->noy = -((float)o.y * fr->iy);
+  fr->noz = -((float)o.z * fr->iz);
+  *prune0 = LimitPrune(sc, d, t_limit);
+  return fast;
+}
+
+#if MTB_SMEM_RAY && MTB_LD256 && MTB_SMEM_STACK == 0
+template <bool DBG>
+__device__ __forceinline__ void Trace2(const DeviceScene &sc, const D3 &oa, const D3 &da, const D3 &ob, const D3 &db, PairQuery *qa,
+                                       PairQuery *qb, unsigned long long *cnt, const FastCtx &fca, const FastCtx &fcb) {
+  FastRay ra, rb;
+  float prune_a = 0.f, prune_b = 0.f;
+  qa->slot = qb->slot = -1;
+  qa->fast = qa->active && FastSetup(sc, oa, da, qa->t_limit, fca, &ra, &prune_a);
+  qb->fast = qb->active && FastSetup(sc, ob, db, qb->t_limit, fcb, &rb, &prune_b);
+  if (qa->active) Count<DBG>(cnt, kRays);
+  if (qb->active) Count<DBG>(cnt, kRays);
+  unsigned long long stack_a[kFastLocalStack], stack_b[kFastLocalStack];
+  int sp_a = 0, sp_b = 0, slot_a = -1, slot_b = -1;
+  int node_a = qa->fast ? 0 : kFastExit, node_b = qb->fast ? 0 : kFastExit;
+  asm volatile("" ::: "memory");
+  // one step of one walk: the two child boxes of the loaded node against the ray, nearer child first
+#define MTB_PAIR_STEP(node, q0, q1, q2, kx, ky, r, prune, stack, sp)                                                          \
+  do {                                                                                                                        \
+    Count<DBG>(cnt, kBvh, 2);                                                                                                 \
+    float tl__, tr__;                                                                                                         \
+    const bool hl__ = FastBox(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, prune, &tl__);                                           \
+    const bool hr__ = FastBox(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, prune, &tr__);                                           \
+    if (hl__ && hr__) {                                                                                                       \
+      const bool rf__ = tr__ < tl__;                                                                                          \
+      stack[sp++] = ((unsigned long long)__float_as_uint(rf__ ? tl__ : tr__) << 32) | (unsigned)(rf__ ? kx : ky);             \
+      node = rf__ ? ky : kx;                                                                                                  \
+    } else if (hl__) {                                                                                                        \
+      node = kx;                                                                                                              \
+    } else if (hr__) {                                                                                                        \
+      node = ky;                                                                                                              \
+    } else {                                                                                                                  \
+      node = kFastExit;                                                                                                       \
+      while (sp > 0) {                                                                                                        \
+        const unsigned long long top__ = stack[--sp];                                                                         \
+        if (__uint_as_float((unsigned)(top__ >> 32)) <= prune) {                                                              \
+          node = (int)(unsigned)top__;                                                                                        \
+          break;                                                                                                              \
+        }                                                                                                                     \
+      }                                                                                                                       \
+    }                                                                                                                         \
+  } while (0)
+#define MTB_PAIR_LOAD(node, q0, q1, q2, kx, ky)                                                                               \
+  float4 q0, q1, q2;                                                                                                          \
+  int kx, ky;                                                                                                                 \
+  {                                                                                                                           \
+    const Bvh2Node *np__ = sc.gnodes + (node >= 0 ? node : 0);                                                                \
+    float w8__, w9__, w10__, w11__;                                                                                           \
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                                       \
+                 : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w), "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w)             \
+                 : "l"(np__));                                                                                                \
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                                       \
+                 : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w), "=f"(w8__), "=f"(w9__), "=f"(w10__), "=f"(w11__)           \
+                 : "l"(reinterpret_cast<const char *>(np__) + 32));                                                           \
+    kx = __float_as_int(w8__);                                                                                                \
+    ky = __float_as_int(w9__);                                                                                                \
+  }
+  for (;;) {
+    while (node_a >= 0 || node_b >= 0) {
+      // both loads leave before either result is needed
+      MTB_PAIR_LOAD(node_a, a0, a1, a2, akx, aky);
+      MTB_PAIR_LOAD(node_b, b0, b1, b2, bkx, bky);
+      if (node_a >= 0) MTB_PAIR_STEP(node_a, a0, a1, a2, akx, aky, ra, prune_a, stack_a, sp_a);
+      if (node_b >= 0) MTB_PAIR_STEP(node_b, b0, b1, b2, bkx, bky, rb, prune_b, stack_b, sp_b);
+    }
+    if (node_a == kFastExit && node_b == kFastExit) break;
+    // leaves: one instance of the exact tests serves both walks (k selects the scratch column and the state)
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) {
+      const int lf = k == 0 ? node_a : node_b;
+      if (lf == kFastExit) continue;
+      FastCtx fck = fca;
+      if (k) fck.ray_base = fcb.ray_base;
+      int slot = k == 0 ? slot_a : slot_b;
+      float prune = k == 0 ? prune_a : prune_b;
+      Ray rr;
+      rr.o = FmLoad3(fck, nullptr, kFmO);
+      rr.inv = FmLoad3(fck, nullptr, kFmInv);
+      rr.sx = rr.inv.x < 0.0;
+      rr.sy = rr.inv.y < 0.0;
+      rr.sz = rr.inv.z < 0.0;
+      const unsigned leaf = ~(unsigned)lf;
+      for (unsigned s = leaf >> 3, e = s + (leaf & 7u); s < e; s++) TestSlotFast<DBG>(sc.gslots + s, rr, fck, nullptr, &slot, &prune, cnt);
+      int node = kFastExit;
+      if (k == 0) {
+        slot_a = slot, prune_a = prune;
+        while (sp_a > 0) {
+          const unsigned long long top = stack_a[--sp_a];
+          if (__uint_as_float((unsigned)(top >> 32)) <= prune) {
+            node = (int)(unsigned)top;
+            break;
+          }
+        }
+        node_a = node;
+      } else {
+        slot_b = slot, prune_b = prune;
+        while (sp_b > 0) {
+          const unsigned long long top = stack_b[--sp_b];
+          if (__uint_as_float((unsigned)(top >> 32)) <= prune) {
+            node = (int)(unsigned)top;
+            break;
+          }
+        }
+        node_b = node;
+      }
+    }
+  }
+#undef MTB_PAIR_STEP
+#undef MTB_PAIR_LOAD
+  asm volatile("" ::: "memory");
+  // certification and fallback, per ray, as in TraceFast / Trace
+#pragma unroll 1
+  for (int k = 0; k < 2; k++) {
+    PairQuery *q = k == 0 ? qa : qb;
+    if (!q->active) continue;
+    const FastCtx &fck = k == 0 ? fca : fcb;
+    const int slot = k == 0 ? slot_a : slot_b;
+    bool exact = !q->fast;
+    if (q->fast && slot >= 0) {
+      const double t = FmLoad(fck, nullptr, kFmT);
+      exact = FmLoad(fck, nullptr, kFmLo2) <= t + FmLoad(fck, nullptr, kFmE) || DegeneratePassage(sc, slot, fck, nullptr);
+      q->t = t;
+    }
+    if (!exact) {
+      Count<DBG>(cnt, kFast);
+      q->slot = slot;
+    } else {
+      if (q->fast) Count<DBG>(cnt, kFallback);
+      q->slot = TraceExactCold<DBG>(sc, FmLoad3(fck, nullptr, kFmO), FmLoad3(fck, nullptr, kFmD), &q->t, cnt);
+    }
+  }
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------------
 // shading helpers
 // ---------------------------------------------------------------------------------------------------
 // primitive_triangle.cc:27-40

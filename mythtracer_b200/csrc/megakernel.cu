@@ -448,6 +448,53 @@ __global__ void __launch_bounds__(128) IntersectKernel(DeviceScene sc, Intersect
   }
 }
 
+// The same query, two rays per thread (rays 2i and 2i + 1): Trace2, device_core.cuh.
+template <bool DBG>
+__global__ void __launch_bounds__(64) IntersectPairKernel(DeviceScene sc, IntersectParams ip) {
+  MTB_DECLARE_FAST_CTX2(64);
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  unsigned long long cnt_store[DBG ? kNumCounters : 1];
+  unsigned long long *cnt = cnt_store;
+  if (DBG) {
+    for (int k = 0; k < kNumCounters; k++) cnt[k] = 0;
+  }
+  if (i < ip.n) {
+    PairQuery qa, qb;
+    qa.active = true;
+    qb.active = i + 1 < ip.n;
+    qa.t_limit = qb.t_limit = CUDART_INF;
+    const int64_t j = qb.active ? i + 1 : i;
+    Trace2<DBG>(sc, Load3(ip.origins + i * 3), Load3(ip.dirs + i * 3), Load3(ip.origins + j * 3), Load3(ip.dirs + j * 3), &qa, &qb, cnt, fctx, fctx_b);
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) {
+      const PairQuery &q = k == 0 ? qa : qb;
+      if (!q.active) continue;
+      const int64_t r = i + k;
+      if (q.slot < 0) {
+        ip.tri_index[r] = -1;
+        if (ip.t != nullptr) ip.t[r] = CUDART_NAN;
+        if (ip.point != nullptr) ip.point[r * 3 + 0] = ip.point[r * 3 + 1] = ip.point[r * 3 + 2] = CUDART_NAN;
+      } else {
+        ip.tri_index[r] = sc.slots[q.slot].tri;
+        if (ip.t != nullptr) ip.t[r] = q.t;
+        if (ip.point != nullptr) {
+          const D3 p = Add(Load3(ip.origins + r * 3), MulS(Load3(ip.dirs + r * 3), q.t));
+          ip.point[r * 3 + 0] = p.x;
+          ip.point[r * 3 + 1] = p.y;
+          ip.point[r * 3 + 2] = p.z;
+        }
+      }
+    }
+  }
+  if (DBG && ip.counters != nullptr) {
+    for (int k = 0; k < kNumCounters; k++) {
+      unsigned long long v = cnt[k];
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+      if ((threadIdx.x & 31u) == 0u && v != 0ull) atomicAdd(ip.counters + k, v);
+    }
+  }
+}
+
 // Counting sort of the tiles by cost bucket (log2 of the ray count, most expensive first).  One block.
 // heavy_k (nullable): receives how many leading tiles of the order - the most expensive ones - together carry
 // `heavy_share_q16` / 65536 of the frame's rays (whole buckets, then part of the next one), at most k_max tiles: the
@@ -557,8 +604,17 @@ void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp, int n_block
   }
 }
 
-void LaunchIntersect(const DeviceScene &sc, const IntersectParams &ip, bool debug_build, cudaStream_t stream) {
+void LaunchIntersect(const DeviceScene &sc, const IntersectParams &ip, bool debug_build, bool pairs, cudaStream_t stream) {
   if (ip.n <= 0) return;
+  if (pairs) {
+    const int blocks = (int)(((ip.n + 1) / 2 + 63) / 64);
+    if (debug_build) {
+      IntersectPairKernel<true><<<blocks, 64, 0, stream>>>(sc, ip);
+    } else {
+      IntersectPairKernel<false><<<blocks, 64, 0, stream>>>(sc, ip);
+    }
+    return;
+  }
   const int blocks = (int)((ip.n + 127) / 128);
   if (debug_build) {
     IntersectKernel<true><<<blocks, 128, 0, stream>>>(sc, ip);

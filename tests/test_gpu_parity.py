@@ -775,3 +775,27 @@ def test_sibling_entry_tie_on_the_device(product_lib, oracle_mod):
         if flags == MTB_FLAG_COUNT_WORK:
             assert got["stats"]["n_fallback"] >= 1 and got["stats"]["n_fast"] >= 1
         mt.close()
+
+
+def test_two_rays_per_lane_gives_the_same_answers(product_lib, oracle_mod, scene_dir):
+    """MTB_FLAG_PAIR_RAYS (Trace2: one thread walks rays 2i and 2i+1 in one loop) against the oracle: random rays,
+    axis-parallel ones (literal path), rays from outside, and an odd count (the last thread has one ray)."""
+    from mythtracer_b200 import MTB_FLAG_COUNT_WORK, MTB_FLAG_PAIR_RAYS
+    files, cfg = scenes.config_scene("C2", scene_dir, scale=0.2)
+    mt, orc = _load_pair(product_lib, oracle_mod, files, 3)
+    rng = np.random.default_rng(12)
+    o, d = scenes.random_rays(rng, orc.aabb(), 20001)
+    d[:1000] = np.eye(3)[rng.integers(0, 3, 1000)] * rng.choice([-1.0, 1.0], (1000, 1))
+    o[1000:2000] += 1000.0
+    cpu = orc.intersect(o, d)
+    hit = cpu["tri"] >= 0
+    assert hit.sum() > 5000
+    for flags in (MTB_FLAG_PAIR_RAYS, MTB_FLAG_PAIR_RAYS | MTB_FLAG_COUNT_WORK):
+        mt.set_flags(flags)
+        gpu = mt.intersect_rays(o, d, want_stats=True)
+        assert np.array_equal(gpu["tri"], cpu["tri"]), flags
+        assert np.array_equal(gpu["t"][hit], cpu["t"][hit]), flags
+        assert np.array_equal(gpu["point"][hit], cpu["point"][hit]), flags
+        assert np.isnan(gpu["t"][~hit]).all()
+        if flags & MTB_FLAG_COUNT_WORK:
+            assert gpu["stats"]["rays"] == len(o) and gpu["stats"]["n_literal"] >= 1000

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmythtracer_b200.so")
-SOURCES = ["api.cu", "megakernel.cu", "wavefront.cu", "device_build.cu", "scene_build.cc", "obj_loader.cc", "image_decode.cc"]
+SOURCES = ["api.cu", "megakernel.cu", "wavefront.cu", "device_build.cu", "scene_build.cc", "obj_loader.cc", "image_decode.cc", "jpeg_decode.cc"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-O2,-Wall", "-D_USE_MATH_DEFINES",

@@ -3,10 +3,11 @@
 // ever read afterwards (px / 255.0, texture.cc:100-104).  SDL2_image is not available offline, so the formats
 // OBJ/MTL assets usually reference are decoded here, to the same RGBA32 bytes:
 //   * PPM  P6, maxval 255
-//   * PNG  non-interlaced; greyscale, greyscale+alpha, RGB, RGBA, palette; 1/2/4/8 bits (16 bits keep the high byte,
+//   * PNG  non-interlaced or Adam7; greyscale, greyscale+alpha, RGB, RGBA, palette; 1/2/4/8 bits (16 bits keep the high byte,
 //          as libpng's strip_16); no gamma / colour management (libpng's default as well)
 //   * BMP  uncompressed 24 / 32 bits and 8-bit palette, bottom-up or top-down
 //   * TGA  true-colour (type 2), greyscale (3) and run-length true-colour (10), 24 / 32 bits, either origin
+//   * JPEG baseline / extended sequential / progressive, 8 bits, grey or three components (jpeg_decode.cc)
 // Anything else fails the load, as an undecodable file does upstream (objreader.cc:467-469).
 #include <cstdint>
 #include <cstdio>
@@ -17,6 +18,8 @@
 #include "scene_build.h"
 
 namespace mtb {
+bool DecodeJpeg(const std::vector<uint8_t> &d, LoadedTexture *tex);  // jpeg_decode.cc
+
 namespace {
 
 bool ReadWholeFile(const std::string &path, std::vector<uint8_t> *out) {
@@ -273,7 +276,7 @@ bool DecodePng(const std::vector<uint8_t> &d, LoadedTexture *tex) {
     }
     pos += 12 + (size_t)len;
   }
-  if (!have_ihdr || !SizeOk(w, h) || interlace != 0 || idat.size() < 6) return false;
+  if (!have_ihdr || !SizeOk(w, h) || idat.size() < 6) return false;
   int channels;
   switch (color) {
     case 0: channels = 1; break;
@@ -286,65 +289,90 @@ bool DecodePng(const std::vector<uint8_t> &d, LoadedTexture *tex) {
   if (!(depth == 8 || depth == 16 || ((color == 0 || color == 3) && (depth == 1 || depth == 2 || depth == 4)))) return false;
   if (color == 3 && (depth == 16 || palette.size() < 3)) return false;
   const size_t bpp_bits = (size_t)channels * depth;
-  const size_t stride = ((size_t)w * bpp_bits + 7) / 8;
   const size_t bpp = (bpp_bits + 7) / 8;  // filter unit, at least one byte
+  // The image arrives as one pass (non-interlaced) or as the seven Adam7 passes, each a complete filtered sub-image
+  // of the pixels (x0 + i dx, y0 + j dy); a pass without pixels has no bytes at all.
+  struct Pass {
+    uint32_t x0, y0, dx, dy;
+  };
+  static const Pass kAdam7[7] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+  static const Pass kWhole[1] = {{0, 0, 1, 1}};
+  if (interlace > 1) return false;
+  const Pass *passes = interlace ? kAdam7 : kWhole;
+  const int n_passes = interlace ? 7 : 1;
+  size_t expect = 0;
+  for (int k = 0; k < n_passes; k++) {
+    const Pass &ps = passes[k];
+    if (w <= ps.x0 || h <= ps.y0) continue;
+    const size_t pw = (w - ps.x0 + ps.dx - 1) / ps.dx, ph = (h - ps.y0 + ps.dy - 1) / ps.dy;
+    expect += ((pw * bpp_bits + 7) / 8 + 1) * ph;
+  }
   std::vector<uint8_t> raw;
   // zlib header (2 bytes) + deflate stream + adler32 (4 bytes, not checked)
   if ((idat[0] & 0x0f) != 8 || (idat[1] & 0x20) != 0) return false;
-  if (!Inflate(idat.data() + 2, idat.size() - 2, &raw, (stride + 1) * h)) return false;
-  if (raw.size() < (stride + 1) * h) return false;
-  // undo the scanline filters in place
-  std::vector<uint8_t> prev(stride, 0);
+  if (!Inflate(idat.data() + 2, idat.size() - 2, &raw, expect)) return false;
+  if (raw.size() < expect) return false;
   SetSize(tex, (int)w, (int)h);
-  for (uint32_t y = 0; y < h; y++) {
-    uint8_t *row = &raw[(size_t)y * (stride + 1) + 1];
-    const uint8_t filter = row[-1];
-    for (size_t i = 0; i < stride; i++) {
-      const int a = i >= bpp ? row[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
-      int pred;
-      switch (filter) {
-        case 0: pred = 0; break;
-        case 1: pred = a; break;
-        case 2: pred = b; break;
-        case 3: pred = (a + b) >> 1; break;
-        case 4: {
-          const int p = a + b - c, pa = p > a ? p - a : a - p, pb = p > b ? p - b : b - p, pc = p > c ? p - c : c - p;
-          pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
-          break;
+  size_t at = 0;
+  for (int k = 0; k < n_passes; k++) {
+    const Pass &ps = passes[k];
+    if (w <= ps.x0 || h <= ps.y0) continue;
+    const size_t pw = (w - ps.x0 + ps.dx - 1) / ps.dx, ph = (h - ps.y0 + ps.dy - 1) / ps.dy;
+    const size_t stride = (pw * bpp_bits + 7) / 8;
+    // undo the scanline filters in place (the row above the first row of a pass is all zero)
+    std::vector<uint8_t> prev(stride, 0);
+    for (size_t py = 0; py < ph; py++) {
+      uint8_t *row = &raw[at + py * (stride + 1) + 1];
+      const uint8_t filter = row[-1];
+      for (size_t i = 0; i < stride; i++) {
+        const int a = i >= bpp ? row[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+        int pred;
+        switch (filter) {
+          case 0: pred = 0; break;
+          case 1: pred = a; break;
+          case 2: pred = b; break;
+          case 3: pred = (a + b) >> 1; break;
+          case 4: {
+            const int p = a + b - c, pa = p > a ? p - a : a - p, pb = p > b ? p - b : b - p, pc = p > c ? p - c : c - p;
+            pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+            break;
+          }
+          default: return false;
         }
-        default: return false;
+        row[i] = (uint8_t)(row[i] + pred);
       }
-      row[i] = (uint8_t)(row[i] + pred);
+      memcpy(prev.data(), row, stride);
+      const size_t y = ps.y0 + py * ps.dy;
+      for (size_t px_i = 0; px_i < pw; px_i++) {
+        uint8_t *dst = &tex->rgba[(y * w + ps.x0 + px_i * ps.dx) * 4];
+        uint8_t v[4] = {0, 0, 0, 255};
+        if (depth >= 8) {
+          const size_t step = depth / 8;  // 16 bits: the high (first) byte, like png_set_strip_16
+          const uint8_t *px = row + px_i * channels * step;
+          for (int ch = 0; ch < channels; ch++) v[ch] = px[ch * step];
+        } else {
+          const size_t bit = px_i * depth;
+          const int sample = (row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
+          v[0] = (uint8_t)(color == 3 ? sample : sample * 255 / ((1 << depth) - 1));
+        }
+        if (color == 3) {
+          const size_t idx = (size_t)v[0] * 3;
+          if (idx + 3 > palette.size()) return false;
+          dst[0] = palette[idx];
+          dst[1] = palette[idx + 1];
+          dst[2] = palette[idx + 2];
+        } else if (color == 0 || color == 4) {
+          dst[0] = dst[1] = dst[2] = v[0];
+          if (color == 4) dst[3] = v[1];
+        } else {
+          dst[0] = v[0];
+          dst[1] = v[1];
+          dst[2] = v[2];
+          if (color == 6) dst[3] = v[3];
+        }
+      }
     }
-    memcpy(prev.data(), row, stride);
-    uint8_t *dst = &tex->rgba[(size_t)y * w * 4];
-    for (uint32_t x = 0; x < w; x++) {
-      uint8_t v[4] = {0, 0, 0, 255};
-      if (depth >= 8) {
-        const size_t step = depth / 8;  // 16 bits: the high (first) byte, like png_set_strip_16
-        const uint8_t *px = row + (size_t)x * channels * step;
-        for (int ch = 0; ch < channels; ch++) v[ch] = px[ch * step];
-      } else {
-        const size_t bit = (size_t)x * depth;
-        const int sample = (row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
-        v[0] = (uint8_t)(color == 3 ? sample : sample * 255 / ((1 << depth) - 1));
-      }
-      if (color == 3) {
-        const size_t idx = (size_t)v[0] * 3;
-        if (idx + 3 > palette.size()) return false;
-        dst[x * 4 + 0] = palette[idx];
-        dst[x * 4 + 1] = palette[idx + 1];
-        dst[x * 4 + 2] = palette[idx + 2];
-      } else if (color == 0 || color == 4) {
-        dst[x * 4 + 0] = dst[x * 4 + 1] = dst[x * 4 + 2] = v[0];
-        if (color == 4) dst[x * 4 + 3] = v[1];
-      } else {
-        dst[x * 4 + 0] = v[0];
-        dst[x * 4 + 1] = v[1];
-        dst[x * 4 + 2] = v[2];
-        if (color == 6) dst[x * 4 + 3] = v[3];
-      }
-    }
+    at += (stride + 1) * ph;
   }
   return true;
 }
@@ -468,6 +496,7 @@ bool DecodeImageFile(const std::string &path, LoadedTexture *tex) {
   if (!ReadWholeFile(path, &d) || d.size() < 4) return false;
   static const uint8_t kPngMagic[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
   if (d.size() >= 8 && memcmp(d.data(), kPngMagic, 8) == 0) return DecodePng(d, tex);
+  if (d[0] == 0xff && d[1] == 0xd8 && d[2] == 0xff) return DecodeJpeg(d, tex);
   if (d[0] == 'P' && d[1] == '6') return DecodePpm(d, tex);
   if (d[0] == 'B' && d[1] == 'M') return DecodeBmp(d, tex);
   if (EndsWithNoCase(path, ".tga")) return DecodeTga(d, tex);  // TGA has no magic number

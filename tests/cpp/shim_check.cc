@@ -50,6 +50,26 @@ int main(int argc, char **argv) {
   if (!(std::fabs(r.direction.Length() - 1.0) < 1e-12)) return Fail("Sensor::GetRay");
   V3D a{1, 2, 3}, b{5, 4, 3};  // math3d_test.cc:68-89
   if (a.Dot(b) != 22.0 || a.Cross(b).v[1] != 12.0 || std::fabs(a.Length() - 3.7416573867739413) > 1e-12) return Fail("math3d");
+  {  // the Primitive virtuals (primitive.h:20-30), called the way reference code would: through Primitive*
+    Triangle tri;
+    tri.vertex[0] = {0, 0, 0}, tri.vertex[1] = {1, 0, 0}, tri.vertex[2] = {0, 1, 0};
+    tri.normal[0] = {1, 0, 0}, tri.normal[1] = {0, 1, 0}, tri.normal[2] = {0, 0, 1};
+    tri.uvw[0] = {0, 0, 0}, tri.uvw[1] = {1, 0, 0}, tri.uvw[2] = {0, 1, 0};
+    tri.CacheAABB();
+    const Primitive *prim = &tri;
+    V3D hit{};
+    double dist = -1.0;
+    if (!prim->IntersectRay(Ray({0.25, 0.25, 1.0}, {0, 0, -1}), &hit, &dist) || dist != 1.0 || hit.v[0] != 0.25 || hit.v[1] != 0.25 ||
+        hit.v[2] != 0.0)
+      return Fail("Triangle::IntersectRay hit");
+    if (prim->IntersectRay(Ray({0.75, 0.75, 1.0}, {0, 0, -1}), &hit, &dist)) return Fail("Triangle::IntersectRay outside (u + v > 1)");
+    if (prim->IntersectRay(Ray({0.25, 0.25, 1.0}, {0, 0, 1}), &hit, &dist)) return Fail("Triangle::IntersectRay behind the origin");
+    if (prim->IntersectRay(Ray({0.25, 0.25, 1.0}, {1, 0, 0}), &hit, &dist)) return Fail("Triangle::IntersectRay parallel");
+    const V3D uvw = prim->GetUVW({0.25, 0.5, 0.0}), nrm = prim->GetNormal({0.25, 0.5, 0.0});
+    if (std::fabs(uvw.v[0] - 0.25) > 1e-12 || std::fabs(uvw.v[1] - 0.5) > 1e-12 || std::fabs(nrm.v[0] - 0.25) > 1e-12 ||
+        std::fabs(nrm.v[1] - 0.25) > 1e-12 || std::fabs(nrm.v[2] - 0.5) > 1e-12)
+      return Fail("Triangle::GetUVW / GetNormal");
+  }
   if (strcmp(argv[1], "host") == 0) {
     puts("host ok");
     return 0;

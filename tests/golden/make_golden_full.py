@@ -28,7 +28,7 @@ from oracle import oracle_py  # noqa: E402
 SCENE_DIR = os.environ.get("MTB_SCENE_DIR", "/tmp/mtb_scenes")
 BAND_ROWS = 8
 # (number of bands of 8 rows) per config; None = the whole frame
-BANDS = {"C3": None, "C4": 7, "C5": 14}
+BANDS = {"C2": None, "C3": None, "C4": 7, "C5": 14}
 
 
 def sha(a) -> str:

@@ -330,11 +330,24 @@ def time_other_workloads(names, steps):
             torch.cuda.synchronize(dev)
             ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
             rays = mt.read_counters()["rays"] / steps
-            out[name] = {"triangles": files.n_triangles, "width": W, "height": H, "lights": cfg["n_lights"], "max_depth": cfg["depth"],
+            # the same frame as the unmodified reference rendered it (tests/golden/full_<cfg>.npz: whole frame or bands)
+            equals_ref, ref_rows = None, 0
+            gpath = os.path.join(ROOT, "tests", "golden", "full_%s.npz" % name)
+            frame_np = d_frame.cpu().numpy()
+            if os.path.exists(gpath):
+                try:
+                    import numpy as np
+                    with np.load(gpath) as z:
+                        rows = z["rows"]
+                        ref_rows = int(len(rows))
+                        equals_ref = bool(int(z["width"]) == W and int(z["height"]) == H and np.array_equal(frame_np[rows], z["rgb"]))
+                except Exception:
+                    equals_ref = None
+            out[name] = {"equals_reference": equals_ref, "reference_rows_compared": ref_rows, "triangles": files.n_triangles, "width": W, "height": H, "lights": cfg["n_lights"], "max_depth": cfg["depth"],
                          "ms_per_frame": ms, "mrays_s": rays / ms / 1e3, "rays_per_frame": rays, "pipeline": mt.pipeline_in_use()[0],
                          "steps": steps, "scene_generate_s": gen_s, "scene_load_s": load_s, "first_frame_s": first_frame_s,
                          "time_to_first_frame_s": load_s + first_frame_s, "load_stages_ms": mt.load_timing(),
-                         "frame_sha256": hashlib.sha256(d_frame.cpu().numpy().tobytes()).hexdigest()}
+                         "frame_sha256": hashlib.sha256(frame_np.tobytes()).hexdigest()}
             mt.close()
             del d_frame
         except Exception as e:  # reported, never required

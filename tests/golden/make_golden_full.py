@@ -1,9 +1,10 @@
 """Full-size golden fixtures, made by the UNMODIFIED reference (oracle/_ref) in the build container.
 
-    python tests/golden/make_golden_full.py [C3] [C4] [C5]
+    python tests/golden/make_golden_full.py [C2] [C3] [C4[:full]] [C5[:full]]
 
-* C3 (BASELINE.json configs[2]): the WHOLE 1920x1080 frame, depth 5, 2 lights.
-* C4 / C5: full-width bands of 8 rows spread over the frame height, together >= 5 % of the frame.
+* C2 (textured, 1280x720) and C3 (BASELINE.json configs[2], 1920x1080, depth 5, 2 lights): the WHOLE frame.
+* C4 / C5: full-width bands of 8 rows spread over the frame height, together >= 5 % of the frame (`:full` = the whole
+  frame; C4 takes ~45 minutes of 8 cores, C5 ~2.5 hours).
 
 Per config it writes tests/golden/full_<cfg>.npz with what the reference returned through its public API
 (RayTrace(WorkChunk*) with output_debug, mythtracer.cc:280-312,24-36): the RGB24 bytes, the per-pixel
@@ -89,5 +90,8 @@ def make(name):
 
 if __name__ == "__main__":
     assert os.path.isdir("/root/reference/VerStarting"), "golden vectors are made where the reference is mounted"
-    for n in (sys.argv[1:] or ["C3", "C5", "C4"]):
+    for n in (sys.argv[1:] or ["C2", "C3", "C5", "C4"]):
+        if n.endswith(":full"):  # e.g. C4:full - the whole frame instead of bands
+            n = n[:-5]
+            BANDS[n] = None
         make(n)

@@ -3,7 +3,9 @@ tests/golden/make_golden_full.py in the build container with oracle/_ref):
 
 * C3 (the configuration the headline metric is quoted on): the WHOLE 1920x1080 frame -- every primary hit id and
   every RGB byte (RGB within the stated pow() tolerance, in practice 0 differing bytes), for every pipeline;
-* C4 (2 M triangles, stress) and C5 (4K, depth 8, 4 lights): full-width bands of 8 rows, >= 5 % of the frame.
+* C2 (textured, 720p): the whole frame;
+* C4 (2 M triangles, stress) and C5 (4K, depth 8, 4 lights): full-width bands of 8 rows, >= 5 % of the frame (or
+  whatever the fixture holds - make_golden_full.py C4:full makes the whole frame).
 
 Plus the paths that only matter at scale: a wavefront frame whose queues overflow (repaired on the device, taps and
 counters exact), and frames shared between processes (tiles stored straight into another process's frame).
@@ -81,6 +83,28 @@ def test_c3_full_frame_equals_the_reference(product_lib, scene_dir):
             assert _sha(got["rgb"]) == str(z["rgb_sha256"])
         shas.add(_sha(got["rgb"]))
     assert len(shas) == 1, "the pipelines disagree with each other"
+    mt.close()
+
+
+def test_c2_textured_full_frame_equals_the_reference(product_lib, scene_dir):
+    """Every pixel of the textured 1280x720 C2 frame (depth 3, bilinear texture fetches in every shaded hit) against the
+    reference's own render, megakernel and queue pipeline."""
+    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_MEGAKERNEL, MTB_FLAG_QUEUE
+    z, files, cfg = _golden("C2", scene_dir)
+    W, H = cfg["width"], cfg["height"]
+    assert len(z["rows"]) == H
+    mt = MythTracer(max_depth=cfg["depth"], flags=MTB_FLAG_MEGAKERNEL)
+    assert mt.LoadObj(files.obj_path), mt.last_error()
+    assert mt.scene_info()["n_textures"] > 0
+    mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]
+    for name, flags in (("megakernel", MTB_FLAG_MEGAKERNEL), ("queue", MTB_FLAG_QUEUE)):
+        mt.set_flags(flags)
+        for frame in range(2):
+            got = mt.render_chunk(files.camera, W, H, 0, 0, W, H, debug=True)
+        differing = _compare(got["rgb"], got["line_no"], z, "C2 " + name)
+        assert _sha(got["points"]) == str(z["points_sha256"]), "C2 %s: hit points differ from the reference's" % name
+        if differing == 0:
+            assert _sha(got["rgb"]) == str(z["rgb_sha256"])
     mt.close()
 
 

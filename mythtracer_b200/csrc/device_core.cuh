@@ -813,8 +813,11 @@ __device__ __forceinline__ bool DegeneratePassage(const DeviceScene &sc, int slo
 #ifndef MTB_SPEC_LEAF
 #define MTB_SPEC_LEAF 0
 #endif
+#ifndef MTB_RAY_RELOAD
+#define MTB_RAY_RELOAD 1
+#endif
 template <bool DBG>
-__device__ __forceinline__ int TraceFast(const DeviceScene &sc, FastMem *m, const FastRay &r, float prune0, double *t_out, bool *ambiguous,
+__device__ __forceinline__ int TraceFast(const DeviceScene &sc, FastMem *m, const FastRay &r_in, float prune0, double *t_out, bool *ambiguous,
                                          unsigned long long *cnt, const FastCtx &fc) {
   unsigned long long stack[kFastLocalStack];
   int sp = 0;
@@ -838,7 +841,21 @@ __device__ __forceinline__ int TraceFast(const DeviceScene &sc, FastMem *m, cons
 #if MTB_SPEC_LEAF
   int pend = kFastExit;  // a leaf that was reached but not tested yet (kFastExit: none)
 #endif
+#if MTB_RAY_RELOAD
+  // The FP32 ray is only needed in the node loop, the leaf tests in between are where the register pressure peaks
+  // (FP64 Moller-Trumbore).  Left to itself ptxas keeps the six floats "live" across the leaf phase by spilling them and
+  // puts the reloads INSIDE the node loop (three LDL per node visit at 64 registers).  So the live range is split by
+  // hand: the ray stays in memory behind a laundered pointer and is loaded once per entry into the node loop - the
+  // barrier of the leaf phase (memory clobber) forces exactly that.
+  const FastRay *r_mem = &r_in;
+  asm volatile("" : "+l"(r_mem) : : "memory");
+#else
+  const FastRay &r = r_in;
+#endif
   for (;;) {
+#if MTB_RAY_RELOAD
+    const FastRay r = *r_mem;
+#endif
     while (node >= 0) {
       if (DBG) visits++;
 #if MTB_LD256

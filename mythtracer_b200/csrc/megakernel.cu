@@ -32,7 +32,12 @@ struct alignas(16) PixelState {
   double P[3], normal[3], surface[3], reflected[3], color[3];    // its shading context (mythtracer.cc:38-76)
   double ldir[3], seg_start[3], power[3];                        // shadow walk of the current light (mythtracer.cc:86-156)
   double coef;                                                   // current_reflection_coef
+  double light_distance;                                         // of the shadow segment in flight (mythtracer.cc:101-102)
   unsigned long long path, sig_hits, sig_shadow;
+  // small integers that are only touched between two traversals (a register each across the node loop would push
+  // the FP32 ray of TraceFast into spill slots at 64 registers)
+  int level, li, material;
+  unsigned segments, n_rays;
 };
 #define MTB_STATE_BARRIER() asm volatile("" : : "l"(&st) : "memory")
 
@@ -92,9 +97,13 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
     PixelState st;
     ShadeFrame frames[kMaxRayStack];
     // what stays in registers across a traversal
-    int sp = 0, level = 0, li = 0, material = -1;
-    unsigned flags = 0, segments = 0;
-    double light_distance = 0.0;
+    int sp = 0;
+    unsigned flags = 0;
+    st.level = 0;
+    st.li = 0;
+    st.material = -1;
+    st.segments = 0;
+    st.n_rays = 0;
 
     {  // Sensor::GetRay (camera.cc:65-69) with full-image pixel coordinates (mythtracer.cc:298)
       const D3 start = Load3(rp.sensor), d_scan = Load3(rp.sensor + 3), d_pixel = Load3(rp.sensor + 6);
@@ -117,7 +126,8 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
           const D3 seg = Ld3(st.seg_start);
           td = Ld3(st.ldir);
           to = Add(seg, MulS(td, 0.00001));                                    // mythtracer.cc:95-99
-          limit = light_distance = Dist(seg, Load3(sc.lights[li].position));  // mythtracer.cc:101-102
+          limit = Dist(seg, Load3(sc.lights[st.li].position));  // mythtracer.cc:101-102
+          st.light_distance = limit;
           Count<DBG>(cnt, kShadow);
         } else {
           to = Ld3(st.m_o);
@@ -127,16 +137,16 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
         slot = Trace<DBG>(sc, to, td, limit, &t, cnt, fctx);
         MTB_STATE_BARRIER();
       }
-      n_rays++;
+      st.n_rays++;
 
       bool have_ret = false;
       D3 ret = Mk(0.0, 0.0, 0.0);
       if (flags & kShadowMode) {
         bool light_done = false;
-        segments++;
+        st.segments++;
         if (slot < 0) {
           light_done = true;  // mythtracer.cc:109-112
-        } else if (t > light_distance) {
+        } else if (t > st.light_distance) {
           light_done = true;  // mythtracer.cc:115-118
         } else {
           const int smtl = __ldg(&sc.shade[slot].material);
@@ -160,7 +170,7 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
             const D3 seg_start = Add(hit_point, MulS(ldir, 0.0000001));  // mythtracer.cc:137
             St3(st.seg_start, seg_start);
             const D3 P = Ld3(st.P);
-            if (SqrDist(P, seg_start) > SqrDist(P, Load3(sc.lights[li].position))) {  // mythtracer.cc:141-145
+            if (SqrDist(P, seg_start) > SqrDist(P, Load3(sc.lights[st.li].position))) {  // mythtracer.cc:141-145
               light_done = true;
             } else if (power.x <= 0.001 && power.y <= 0.001 && power.z <= 0.001) {
               St3(st.power, Mk(0.0, 0.0, 0.0));
@@ -172,11 +182,11 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
         if (!light_done) continue;  // next segment of the same light
 
         // ---- this light is settled: Phong terms (mythtracer.cc:159-177) ----
-        const mtb_light *lt = sc.lights + li;
-        const mtb_material *m = sc.materials + material;
+        const mtb_light *lt = sc.lights + st.li;
+        const mtb_material *m = sc.materials + st.material;
         const bool in_shadow = (flags & kInShadow) != 0u;
         if (want_sig) {
-          st.sig_shadow += Mix64(st.path, 2ull + (unsigned long long)li, (in_shadow ? 1ull : 0ull) | ((unsigned long long)segments << 1));
+          st.sig_shadow += Mix64(st.path, 2ull + (unsigned long long)st.li, (in_shadow ? 1ull : 0ull) | ((unsigned long long)st.segments << 1));
         }
         const D3 lamb = Load3(lt->ambient);
         D3 power = Ld3(st.power);
@@ -193,11 +203,11 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
           }
         }
         St3(st.color, color);
-        li++;
+        st.li++;
       } else {
         // ---- result of a primary / reflection / refraction ray (mythtracer.cc:13-76) ----
         if (slot < 0) {
-          if (level == 0 && rp.dbg != nullptr) {
+          if (st.level == 0 && rp.dbg != nullptr) {
             mtb_debug *dbg = rp.dbg + (size_t)py * rp.chunk_w + px;
             dbg->line_no = -1;
             dbg->pad_ = 0;
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
           const D3 m_d = Ld3(st.m_d);
           const D3 P = Add(Ld3(st.m_o), MulS(m_d, t));
           const int line_no = __ldg(&sh->line_no);
-          if (level == 0 && rp.dbg != nullptr) {
+          if (st.level == 0 && rp.dbg != nullptr) {
             mtb_debug *dbg = rp.dbg + (size_t)py * rp.chunk_w + px;
             dbg->line_no = line_no;
             dbg->pad_ = 0;
@@ -230,13 +240,13 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
             normal = Neg(normal);
             normal_ray_dot = Dot(towards_camera, normal);
           }
-          material = __ldg(&sh->material);
-          if (material < 0) {  // mythtracer.cc:49-52
+          st.material = __ldg(&sh->material);
+          if (st.material < 0) {  // mythtracer.cc:49-52
             normal_ray_dot = (normal_ray_dot + 1.0) * 0.5;
             ret = Mk(normal_ray_dot, normal_ray_dot, normal_ray_dot);
             have_ret = true;
           } else {
-            const mtb_material *m = sc.materials + material;
+            const mtb_material *m = sc.materials + st.material;
             D3 surface = Load3(m->ambient);
             const int tex = m->texture;
             if (tex >= 0) {  // mythtracer.cc:59-64
@@ -250,32 +260,32 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
             // ray.direction - normal * (2 * ray.direction.Dot(normal)) (mythtracer.cc:68-69)
             St3(st.reflected, Sub(m_d, MulS(normal, 2 * Dot(normal, m_d))));
             St3(st.color, Mk(0.0, 0.0, 0.0));
-            li = 0;
+            st.li = 0;
           }
         }
       }
 
       if (!have_ret) {
-        if (li < sc.n_lights) {
+        if (st.li < sc.n_lights) {
           // ---- start the shadow walk of light li (mythtracer.cc:79-94) ----
-          const mtb_light *lt = sc.lights + li;
+          const mtb_light *lt = sc.lights + st.li;
           const D3 P = Ld3(st.P);
           St3(st.ldir, Normalized(Sub(Load3(lt->position), P)));
           St3(st.color, Add(Ld3(st.color), MulV(Load3(lt->ambient), Ld3(st.surface))));  // mythtracer.cc:83-84
           St3(st.power, Mk(1.0, 1.0, 1.0));
           St3(st.seg_start, P);
           flags = (flags & kInObject) | kShadowMode;  // in_shadow = through = false
-          segments = 0;
+          st.segments = 0;
           continue;
         }
         // ---- all lights done: secondary rays (mythtracer.cc:181-225) ----
         flags &= kInObject;
-        const mtb_material *m = sc.materials + material;
+        const mtb_material *m = sc.materials + st.material;
         const double refl = m->reflectance, tr = m->transparency;
         const double coef = st.coef;
         const bool in_object = (flags & kInObject) != 0u;
-        const bool do_reflect = level < rp.max_depth && refl > 0.0 && coef > 0.01 && !in_object;
-        const bool do_refract = level < rp.max_depth && tr > 0.0;
+        const bool do_reflect = st.level < rp.max_depth && refl > 0.0 && coef > 0.01 && !in_object;
+        const bool do_refract = st.level < rp.max_depth && tr > 0.0;
         if (do_reflect || do_refract) {
           const D3 P = Ld3(st.P), m_d = Ld3(st.m_d);
           ShadeFrame &f = frames[sp];
@@ -284,12 +294,12 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
           St3(f.dir, m_d);
           f.coef = coef;
           f.path = st.path;
-          f.material = material;
+          f.material = st.material;
           f.stage = do_reflect ? 0 : 1;
           f.do_refract = do_refract ? 1 : 0;
           f.in_object = in_object ? 1 : 0;
           sp++;
-          level++;
+          st.level++;
           if (do_reflect) {
             Count<DBG>(cnt, kReflect);
             const D3 reflected = Ld3(st.reflected);
@@ -331,7 +341,7 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
             flags = f.in_object != 0 ? 0u : kInObject;  // in_object toggled; not in a shadow walk
             st.coef = f.coef;
             st.path = f.path * 2ull + 1ull;
-            level = sp;
+            st.level = sp;
             break;  // trace the refraction child
           }
           ret = c;
@@ -352,6 +362,7 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_MEGA_MIN_BLOCKS) RenderMega
       const size_t pix = (size_t)py * rp.chunk_w + px;
       if (rp.sig_hits != nullptr) rp.sig_hits[pix] = st.sig_hits;
       if (rp.sig_shadow != nullptr) rp.sig_shadow[pix] = st.sig_shadow;
+      n_rays = st.n_rays;
       if (rp.n_rays != nullptr) rp.n_rays[pix] = n_rays;
       break;
     }

@@ -3,9 +3,9 @@ tests/golden/make_golden_full.py in the build container with oracle/_ref):
 
 * C3 (the configuration the headline metric is quoted on): the WHOLE 1920x1080 frame -- every primary hit id and
   every RGB byte (RGB within the stated pow() tolerance, in practice 0 differing bytes), for every pipeline;
-* C2 (textured, 720p): the whole frame;
-* C4 (2 M triangles, stress) and C5 (4K, depth 8, 4 lights): full-width bands of 8 rows, >= 5 % of the frame (or
-  whatever the fixture holds - make_golden_full.py C4:full makes the whole frame).
+* C2 (textured, 720p) and C4 (2 M triangles incl. the room-spanning sticks that the scene BVH references through
+  several pre-split pieces): the whole frame;
+* C5 (4K, depth 8, 4 lights): full-width bands of 8 rows, >= 5 % of the frame.
 
 Plus the paths that only matter at scale: a wavefront frame whose queues overflow (repaired on the device, taps and
 counters exact), and frames shared between processes (tiles stored straight into another process's frame).
@@ -110,17 +110,22 @@ def test_c2_textured_full_frame_equals_the_reference(product_lib, scene_dir):
 
 @pytest.mark.parametrize("name", ["C4", "C5"])
 def test_bands_equal_the_reference(product_lib, scene_dir, name):
-    """>= 5 % of the C4 / C5 frame (bands of 8 rows over the frame height) against the reference's render."""
-    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_MEGAKERNEL
+    """The whole C4 frame and >= 5 % of the C5 frame (bands of 8 rows over the frame height) against the reference's
+    render, megakernel and queue pipeline."""
+    from mythtracer_b200 import Light, MythTracer, MTB_FLAG_MEGAKERNEL, MTB_FLAG_QUEUE
     z, files, cfg = _golden(name, scene_dir)
     W, H = cfg["width"], cfg["height"]
     assert len(z["rows"]) >= 0.05 * H
+    if name == "C4":
+        assert len(z["rows"]) == H
     mt = MythTracer(max_depth=cfg["depth"], flags=MTB_FLAG_MEGAKERNEL)
     assert mt.LoadObj(files.obj_path), mt.last_error()
     mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]
-    got = mt.render_chunk(files.camera, W, H, 0, 0, W, H, debug=True)
-    _compare(got["rgb"], got["line_no"], z, name)
-    assert _sha(got["points"][z["rows"]]) == str(z["points_sha256"])
+    for pipeline, flags in (("megakernel", MTB_FLAG_MEGAKERNEL), ("queue", MTB_FLAG_QUEUE)):
+        mt.set_flags(flags)
+        got = mt.render_chunk(files.camera, W, H, 0, 0, W, H, debug=True)
+        _compare(got["rgb"], got["line_no"], z, "%s %s" % (name, pipeline))
+        assert _sha(got["points"][z["rows"]]) == str(z["points_sha256"]), "%s %s: hit points" % (name, pipeline)
     mt.close()
 
 

@@ -620,28 +620,41 @@ struct FastCtx {
 };
 #if MTB_SMEM_STACK > 0 || MTB_SMEM_RAY
 #define MTB_DECLARE_FAST_CTX(threads)                                                                         \
-  __shared__ unsigned long long s_fast_scratch[(MTB_SMEM_STACK + (MTB_SMEM_RAY ? kFmWords : 0)) * (threads)]; \
+  __shared__ unsigned long long s_fast_scratch[(MTB_SMEM_STACK + (MTB_SMEM_RAY ? kFmSharedWords : 0)) * (threads)]; \
   const unsigned fast_base__ = (unsigned)__cvta_generic_to_shared(s_fast_scratch + threadIdx.x);              \
   const FastCtx fctx{fast_base__, fast_base__ + (unsigned)(MTB_SMEM_STACK * (threads) * 8), (threads) * 8}
 #else
 #define MTB_DECLARE_FAST_CTX(threads) const FastCtx fctx{0u, 0u, 0}
 #endif
 
+// kFmO .. kFmInv are read at every leaf visit and live in shared memory (MTB_SMEM_RAY).  The best hit (kFmT, kFmE,
+// kFmLo2) is touched by 0.5 accepted hits per ray; MTB_SMEM_HIT = 0 keeps it in the thread's local FastMem instead, so
+// that nine shared words per thread let sixteen 64-thread blocks fit the 100 KB shared-memory configuration instead of
+// the 132 KB one (32 KB more L1).  Measured on B200 at 16 blocks per SM: C3 8.92 vs 8.86 ms, C5 49.6 vs 49.3 with all
+// twelve words shared - L1 capacity is not what the walk waits for - so the default stays 1.  `field` is a constant at
+// every call site.
+#ifndef MTB_SMEM_HIT
+#define MTB_SMEM_HIT 1
+#endif
+constexpr int kFmSharedWords = MTB_SMEM_HIT ? (int)kFmWords : (int)kFmT;
 __device__ __forceinline__ double FmLoad(const FastCtx &fc, const FastMem *m, int field) {
 #if MTB_SMEM_RAY
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(fc.ray_base + (unsigned)(field * fc.stride_bytes)));
-  return v;
-#else
-  return m->w[field];
+  if (MTB_SMEM_HIT || field < kFmT) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(fc.ray_base + (unsigned)(field * fc.stride_bytes)));
+    return v;
+  }
 #endif
+  return m->w[field];
 }
 __device__ __forceinline__ void FmStore(const FastCtx &fc, FastMem *m, int field, double v) {
 #if MTB_SMEM_RAY
-  asm volatile("st.shared.f64 [%0], %1;" : : "r"(fc.ray_base + (unsigned)(field * fc.stride_bytes)), "d"(v));
-#else
-  m->w[field] = v;
+  if (MTB_SMEM_HIT || field < kFmT) {
+    asm volatile("st.shared.f64 [%0], %1;" : : "r"(fc.ray_base + (unsigned)(field * fc.stride_bytes)), "d"(v));
+    return;
+  }
 #endif
+  m->w[field] = v;
 }
 __device__ __forceinline__ D3 FmLoad3(const FastCtx &fc, const FastMem *m, int field) {
   return Mk(FmLoad(fc, m, field), FmLoad(fc, m, field + 1), FmLoad(fc, m, field + 2));
@@ -1054,10 +1067,10 @@ __device__ __forceinline__ int Trace(const DeviceScene &sc, const D3 &o, const D
 // same fallback to the exact recursion.
 // ---------------------------------------------------------------------------------------------------
 #define MTB_DECLARE_FAST_CTX2(threads)                                                             \
-  __shared__ unsigned long long s_fast_scratch[2 * kFmWords * (threads)];                          \
+  __shared__ unsigned long long s_fast_scratch[2 * kFmSharedWords * (threads)];                    \
   const unsigned fast_base__ = (unsigned)__cvta_generic_to_shared(s_fast_scratch + threadIdx.x);   \
   const FastCtx fctx{0u, fast_base__, (threads) * 8};                                              \
-  const FastCtx fctx_b{0u, fast_base__ + (unsigned)(kFmWords * (threads) * 8), (threads) * 8}
+  const FastCtx fctx_b{0u, fast_base__ + (unsigned)(kFmSharedWords * (threads) * 8), (threads) * 8}
 
 struct PairQuery {
   bool active;     // in: there is a ray
@@ -1068,8 +1081,8 @@ struct PairQuery {
 };
 
 // Ray set-up of Trace(): stores the FP64 ray into the scratch column `fc`, returns the FP32 ray and the pruning limit.
-__device__ __forceinline__ bool FastSetup(const DeviceScene &sc, const D3 &o, const D3 &d, double t_limit, const FastCtx &fc, FastRay *fr,
-                                          float *prune0) {
+__device__ __forceinline__ bool FastSetup(const DeviceScene &sc, const D3 &o, const D3 &d, double t_limit, const FastCtx &fc, FastMem *m,
+                                          FastRay *fr, float *prune0) {
   const D3 inv = Mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
   const bool regular = isfinite(inv.x) && isfinite(inv.y) && isfinite(inv.z) && inv.x != 0.0 && inv.y != 0.0 && inv.z != 0.0 &&
                        isfinite(o.x) && isfinite(o.y) && isfinite(o.z);
@@ -1081,7 +1094,7 @@ __device__ __forceinline__ bool FastSetup(const DeviceScene &sc, const D3 &o, co
   FmStore(fc, nullptr, kFmO + 0, o.x), FmStore(fc, nullptr, kFmO + 1, o.y), FmStore(fc, nullptr, kFmO + 2, o.z);
   FmStore(fc, nullptr, kFmD + 0, d.x), FmStore(fc, nullptr, kFmD + 1, d.y), FmStore(fc, nullptr, kFmD + 2, d.z);
   FmStore(fc, nullptr, kFmInv + 0, inv.x), FmStore(fc, nullptr, kFmInv + 1, inv.y), FmStore(fc, nullptr, kFmInv + 2, inv.z);
-  FmStore(fc, nullptr, kFmLo2, CUDART_INF);
+  FmStore(fc, m, kFmLo2, CUDART_INF);
   fr->ix = (float)inv.x;
   fr->iy = (float)inv.y;
   fr->iz = (float)inv.z;
@@ -1099,8 +1112,9 @@ __device__ __forceinline__ void Trace2(const DeviceScene &sc, const D3 &oa, cons
   FastRay ra, rb;
   float prune_a = 0.f, prune_b = 0.f;
   qa->slot = qb->slot = -1;
-  qa->fast = qa->active && FastSetup(sc, oa, da, qa->t_limit, fca, &ra, &prune_a);
-  qb->fast = qb->active && FastSetup(sc, ob, db, qb->t_limit, fcb, &rb, &prune_b);
+  FastMem mem_a, mem_b;  // best hit of each walk (MTB_SMEM_HIT = 0)
+  qa->fast = qa->active && FastSetup(sc, oa, da, qa->t_limit, fca, &mem_a, &ra, &prune_a);
+  qb->fast = qb->active && FastSetup(sc, ob, db, qb->t_limit, fcb, &mem_b, &rb, &prune_b);
   if (qa->active) Count<DBG>(cnt, kRays);
   if (qb->active) Count<DBG>(cnt, kRays);
   unsigned long long stack_a[kFastLocalStack], stack_b[kFastLocalStack];
@@ -1173,7 +1187,10 @@ __device__ __forceinline__ void Trace2(const DeviceScene &sc, const D3 &oa, cons
       rr.sy = rr.inv.y < 0.0;
       rr.sz = rr.inv.z < 0.0;
       const unsigned leaf = ~(unsigned)lf;
-      for (unsigned s = leaf >> 3, e = s + (leaf & 7u); s < e; s++) TestSlotFast<DBG>(sc.gslots + s, rr, fck, nullptr, &slot, &prune, cnt);
+      FastMem *mk = k == 0 ? &mem_a : &mem_b;
+      MTB_FAST_BARRIER(mk);
+      for (unsigned s = leaf >> 3, e = s + (leaf & 7u); s < e; s++) TestSlotFast<DBG>(sc.gslots + s, rr, fck, mk, &slot, &prune, cnt);
+      MTB_FAST_BARRIER(mk);
       int node = kFastExit;
       if (k == 0) {
         slot_a = slot, prune_a = prune;
@@ -1209,9 +1226,10 @@ __device__ __forceinline__ void Trace2(const DeviceScene &sc, const D3 &oa, cons
     const FastCtx &fck = k == 0 ? fca : fcb;
     const int slot = k == 0 ? slot_a : slot_b;
     bool exact = !q->fast;
+    const FastMem *mk = k == 0 ? &mem_a : &mem_b;
     if (q->fast && slot >= 0) {
-      const double t = FmLoad(fck, nullptr, kFmT);
-      exact = FmLoad(fck, nullptr, kFmLo2) <= t + FmLoad(fck, nullptr, kFmE) || DegeneratePassage(sc, slot, fck, nullptr);
+      const double t = FmLoad(fck, mk, kFmT);
+      exact = FmLoad(fck, mk, kFmLo2) <= t + FmLoad(fck, mk, kFmE) || DegeneratePassage(sc, slot, fck, mk);
       q->t = t;
     }
     if (!exact) {

@@ -63,7 +63,12 @@ __device__ __forceinline__ void St3(double *p, const D3 &v) {
 #define MTB_BLOCK_EPILOGUE 0
 #endif
 #ifndef MTB_MEGA_MIN_BLOCKS
-#define MTB_MEGA_MIN_BLOCKS 14  // blocks per SM (72 registers); measured on one B200, C3, round 2: 14 -> 9.13 ms, 16 -> 9.38, 20 -> 10.3
+// Blocks per SM = registers per thread.  The frame time falls with every warp in flight as long as the node loop of
+// TraceFast stays free of spill code (B200, C3, ms): 10 blocks (96 registers) 10.50, 12 (80) 9.66, 14 (72) 9.07 - and,
+// once the FP32 ray's live range was split by hand (MTB_RAY_RELOAD, device_core.cuh) and the small per-pixel integers
+// moved into PixelState, so that 64 registers no longer put reloads into the node loop - 16 (64) 8.88, 18 (56) 9.00,
+// 20 (48) 9.14.
+#define MTB_MEGA_MIN_BLOCKS 16
 #endif
 
 constexpr unsigned kShadowMode = 1u, kInObject = 2u, kInShadow = 4u, kThrough = 8u;

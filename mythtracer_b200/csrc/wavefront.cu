@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(256) WfResolve(RenderParams rp, WfBuffers wf, 
 // activation table, or a wait that lasts absurdly long, sets ctrl[0]: every warp leaves and the repair launch
 // (RenderMega, same bytes) renders the frame.
 #ifndef MTB_QUEUE_MIN_BLOCKS
-#define MTB_QUEUE_MIN_BLOCKS 14  // 64-thread blocks at 72 registers, the megakernel's shape
+#define MTB_QUEUE_MIN_BLOCKS 16  // 64-thread blocks at 64 registers, the megakernel's shape (14 / 16 / 18 / 20 blocks: C3 9.77 / 9.36 / 9.38 / 9.42 ms)
 #endif
 constexpr unsigned kQueueSpinLimit = 1u << 22;
 #ifndef MTB_QUEUE_MIN_TICKET

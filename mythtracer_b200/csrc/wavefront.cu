@@ -498,6 +498,10 @@ struct alignas(16) QueueState {
   double m_o[3], m_d[3];                                       // its ray
   double P[3], normal[3], surface[3], reflected[3], color[3];  // shading context (mythtracer.cc:38-76)
   double ldir[3], seg_start[3], power[3];                      // shadow walk of the current light (mythtracer.cc:86-156)
+  double coef, light_distance;
+  unsigned long long path, sig;
+  int level, pixel, material, child_refl, child_refr, in_object;
+  unsigned segments, rays;
 };
 #define MTB_QSTATE_BARRIER() asm volatile("" : : "l"(&st) : "memory")
 __device__ __forceinline__ D3 Ld3q(const double *p) { return Mk(p[0], p[1], p[2]); }
@@ -594,10 +598,16 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
     const bool mine = lane < n;
     const int act = (int)(ticket + done + lane);
     done += n;
-    bool live = mine, failed = false, in_object = false;
-    int level = 0, pixel = -1;
-    double coef = 1.0;
-    unsigned long long path = 1ull;
+    bool live = mine, failed = false;
+    // what has to survive a traversal lives in `st` (local memory, explicit - see PixelState in megakernel.cu for why),
+    // including the scalars that are only touched between two traversals: a register each across the node loop is
+    // what pushes other values into spill slots at 64 registers
+    QueueState st;
+    st.in_object = 0;
+    st.level = 0;
+    st.pixel = -1;
+    st.coef = 1.0;
+    st.path = 1ull;
     D3 o = Mk(0.0, 0.0, 0.0), d = Mk(0.0, 0.0, 0.0);
     if (mine) {
       if (act < slots) {
@@ -607,7 +617,7 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
         const int px = (tile % rp.tiles_x) * 8 + (t & 7);
         const int py = strip * 8 + (t >> 3);
         live = tile >= 0 && px < rp.chunk_w && py < rp.chunk_h;
-        pixel = live ? py * rp.chunk_w + px : -1;
+        st.pixel = live ? py * rp.chunk_w + px : -1;
         const D3 start = Load3(rp.sensor), d_scan = Load3(rp.sensor + 3), d_pixel = Load3(rp.sensor + 6);
         o = Load3(rp.origin);
         d = Normalized(Add(Add(start, MulS(d_scan, (double)(rp.chunk_y + py))), MulS(d_pixel, (double)(rp.chunk_x + px))));
@@ -626,12 +636,12 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
         if (!failed) {
           o = LdCg3(wf.act_point + (size_t)act * 3);
           d = LdCg3(wf.act_dir + (size_t)act * 3);
-          coef = __ldcg(wf.act_coef + act);
-          path = __ldcg(wf.act_path + act);
-          pixel = __ldcg(wf.act_pixel + act);
+          st.coef = __ldcg(wf.act_coef + act);
+          st.path = __ldcg(wf.act_path + act);
+          st.pixel = __ldcg(wf.act_pixel + act);
           const int info = __ldcg(wf.act_info + act);
-          level = info & 0xff;
-          in_object = (info >> 8) != 0;
+          st.level = info & 0xff;
+          st.in_object = (info >> 8) != 0;
         }
       }
     }
@@ -644,15 +654,17 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
     // hits are shaded and their children queued (warp-wide), then every further iteration is one shadow segment of
     // the lanes that still walk.  What has to survive a traversal lives in `st` (local memory, explicit - see
     // PixelState in megakernel.cu for why); a handful of scalars stay in registers ----
-    QueueState st;
     St3q(st.m_o, o);
     St3q(st.m_d, d);
     St3q(st.color, Mk(0.0, 0.0, 0.0));
     bool walking = live, main_phase = true, lit = false, in_shadow = false, through = false;
-    int material = -2, li = 0, child_refl = -1, child_refr = -1;
-    unsigned segments = 0, rays = 0;
-    unsigned long long sig = 0ull;
-    double light_distance = 0.0;
+    int li = 0;
+    st.material = -2;
+    st.child_refl = -1;
+    st.child_refr = -1;
+    st.segments = 0;
+    st.rays = 0;
+    st.sig = 0ull;
     bool stop_all = false;
     for (;;) {
       int slot = -1;
@@ -667,13 +679,14 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
           const D3 seg = Ld3q(st.seg_start);
           td = Ld3q(st.ldir);
           to = Add(seg, MulS(td, 0.00001));                                     // mythtracer.cc:95-99
-          limit = light_distance = Dist(seg, Load3(sc.lights[li].position));   // mythtracer.cc:101-102
+          limit = Dist(seg, Load3(sc.lights[li].position));   // mythtracer.cc:101-102
+          st.light_distance = limit;
           Count<DBG>(cnt, kShadow);
         }
         MTB_QSTATE_BARRIER();
         slot = Trace<DBG>(sc, to, td, limit, &t, cnt, fctx);
         MTB_QSTATE_BARRIER();
-        rays++;
+        st.rays++;
       }
       if (main_phase) {
         // ---- results of the activations' own rays (mythtracer.cc:13-76); every lane of the warp is here ----
@@ -683,8 +696,8 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
         if (walking) {
           walking = false;
           if (slot < 0) {
-            if (level == 0 && rp.dbg != nullptr) {
-              mtb_debug *dbg = rp.dbg + pixel;
+            if (st.level == 0 && rp.dbg != nullptr) {
+              mtb_debug *dbg = rp.dbg + st.pixel;
               dbg->line_no = -1;
               dbg->pad_ = 0;
               dbg->point[0] = dbg->point[1] = dbg->point[2] = CUDART_NAN;
@@ -695,8 +708,8 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
             const D3 m_d = Ld3q(st.m_d);
             const D3 P = Add(Ld3q(st.m_o), MulS(m_d, t));
             const int line_no = __ldg(&sh->line_no);
-            if (level == 0 && rp.dbg != nullptr) {
-              mtb_debug *dbg = rp.dbg + pixel;
+            if (st.level == 0 && rp.dbg != nullptr) {
+              mtb_debug *dbg = rp.dbg + st.pixel;
               dbg->line_no = line_no;
               dbg->pad_ = 0;
               dbg->point[0] = P.x;
@@ -704,7 +717,7 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
               dbg->point[2] = P.z;
             }
             if (rp.sig_hits != nullptr) {
-              atomicAdd(reinterpret_cast<unsigned long long *>(rp.sig_hits) + pixel, Mix64(path, 1ull, (unsigned long long)(long long)line_no));
+              atomicAdd(reinterpret_cast<unsigned long long *>(rp.sig_hits) + st.pixel, Mix64(st.path, 1ull, (unsigned long long)(long long)line_no));
             }
             Count<DBG>(cnt, kShade);
             const D3 v0 = Load3(sr->vert), v1 = Load3(sr->vert + 3), v2 = Load3(sr->vert + 6);
@@ -734,11 +747,11 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
               St3q(st.normal, normal);
               St3q(st.surface, surface);
               St3q(st.reflected, reflected);
-              material = mtl;
+              st.material = mtl;
               lit = true;
-              if (level < rp.max_depth) {
+              if (st.level < rp.max_depth) {
                 refl = m->reflectance;
-                do_reflect = refl > 0.0 && coef > 0.01 && !in_object;  // mythtracer.cc:181-184
+                do_reflect = refl > 0.0 && st.coef > 0.01 && !st.in_object;  // mythtracer.cc:181-184
                 do_refract = m->transparency > 0.0;                    // mythtracer.cc:192
               }
             }
@@ -768,11 +781,11 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
                 Count<DBG>(cnt, kReflect);
                 Store3(wf.act_point + (size_t)c * 3, Add(P, MulS(reflected, 0.0001)));  // mythtracer.cc:70-75
                 Store3(wf.act_dir + (size_t)c * 3, reflected);
-                wf.act_coef[c] = coef * refl;
-                wf.act_path[c] = path * 2ull;
-                wf.act_pixel[c] = pixel;
-                wf.act_info[c] = (level + 1) | (in_object ? 256 : 0);
-                child_refl = c;
+                wf.act_coef[c] = st.coef * refl;
+                wf.act_path[c] = st.path * 2ull;
+                wf.act_pixel[c] = st.pixel;
+                wf.act_info[c] = (st.level + 1) | (st.in_object ? 256 : 0);
+                st.child_refl = c;
               }
               if (do_refract) {
                 const int c = (int)(base + n_refl + (unsigned)__popc(refr_mask & below));
@@ -780,15 +793,15 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
                 const D3 rdir = Normalized(m_d);                                      // mythtracer.cc:208-212
                 Store3(wf.act_point + (size_t)c * 3, Add(P, MulS(rdir, 0.00001)));    // mythtracer.cc:214-218
                 Store3(wf.act_dir + (size_t)c * 3, rdir);
-                wf.act_coef[c] = coef;
-                wf.act_path[c] = path * 2ull + 1ull;
-                wf.act_pixel[c] = pixel;
-                wf.act_info[c] = (level + 1) | (in_object ? 0 : 256);
-                child_refr = c;
+                wf.act_coef[c] = st.coef;
+                wf.act_path[c] = st.path * 2ull + 1ull;
+                wf.act_pixel[c] = st.pixel;
+                wf.act_info[c] = (st.level + 1) | (st.in_object ? 0 : 256);
+                st.child_refr = c;
               }
               __threadfence();
-              if (child_refl >= 0) asm volatile("st.volatile.global.u32 [%0], %1;" : : "l"(wf.act_ready + child_refl), "r"(epoch) : "memory");
-              if (child_refr >= 0) asm volatile("st.volatile.global.u32 [%0], %1;" : : "l"(wf.act_ready + child_refr), "r"(epoch) : "memory");
+              if (st.child_refl >= 0) asm volatile("st.volatile.global.u32 [%0], %1;" : : "l"(wf.act_ready + st.child_refl), "r"(epoch) : "memory");
+              if (st.child_refr >= 0) asm volatile("st.volatile.global.u32 [%0], %1;" : : "l"(wf.act_ready + st.child_refr), "r"(epoch) : "memory");
             }
           }
         }
@@ -797,18 +810,18 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
         if (lane == 0u) atomicAdd(wf.qctl + kQPending, 0u - n);
         // the links and the material are final now
         if (mine) {
-          wf.act_mtl[act] = material;
-          wf.act_refl[act] = child_refl;
-          wf.act_refr[act] = child_refr;
+          wf.act_mtl[act] = st.material;
+          wf.act_refl[act] = st.child_refl;
+          wf.act_refr[act] = st.child_refr;
         }
         walking = lit && sc.n_lights > 0;
       } else if (walking) {
         // ---- one shadow segment came back (mythtracer.cc:104-156) ----
         bool light_done = false;
-        segments++;
+        st.segments++;
         if (slot < 0) {
           light_done = true;
-        } else if (t > light_distance) {
+        } else if (t > st.light_distance) {
           light_done = true;
         } else {
           const int smtl = __ldg(&sc.shade[slot].material);
@@ -841,8 +854,8 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
         if (light_done) {
           // ---- this light is settled: Phong terms (mythtracer.cc:159-177) ----
           const mtb_light *lt = sc.lights + li;
-          const mtb_material *m = sc.materials + material;
-          sig += Mix64(path, 2ull + (unsigned long long)li, (in_shadow ? 1ull : 0ull) | ((unsigned long long)segments << 1));
+          const mtb_material *m = sc.materials + st.material;
+          st.sig += Mix64(st.path, 2ull + (unsigned long long)li, (in_shadow ? 1ull : 0ull) | ((unsigned long long)st.segments << 1));
           const D3 lamb = Load3(lt->ambient);
           D3 power = Ld3q(st.power);
           power.x = SMax(power.x, lamb.x);
@@ -875,7 +888,7 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
         St3q(st.seg_start, P);
         in_shadow = false;
         through = false;
-        segments = 0;
+        st.segments = 0;
       }
     }
     if (__any_sync(0xffffffffu, stop_all)) {
@@ -885,10 +898,10 @@ __global__ void __launch_bounds__(kBlockThreads, MTB_QUEUE_MIN_BLOCKS) WfQueue(D
     if (mine) {
       Store3(wf.act_color + (size_t)act * 3, Ld3q(st.color));
       if (live) {
-        traced += rays;
-        if (lit && rp.sig_shadow != nullptr && sc.n_lights > 0) atomicAdd(reinterpret_cast<unsigned long long *>(rp.sig_shadow) + pixel, sig);
-        if (rp.n_rays != nullptr) atomicAdd(rp.n_rays + pixel, rays);
-        WfChargeTile(rp, pixel, rays);
+        traced += st.rays;
+        if (lit && rp.sig_shadow != nullptr && sc.n_lights > 0) atomicAdd(reinterpret_cast<unsigned long long *>(rp.sig_shadow) + st.pixel, st.sig);
+        if (rp.n_rays != nullptr) atomicAdd(rp.n_rays + st.pixel, st.rays);
+        WfChargeTile(rp, st.pixel, st.rays);
       }
     }
   }

@@ -7,12 +7,11 @@ run() { # name nproc steps
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $2 --steps $3 --warmup 5 > gpurun_out/${TAG}_$1.json 2> gpurun_out/${TAG}_$1.err; echo "$1 rc=$?"
 }
 run n8 8 20
-run n8_long 8 200
 run n4 4 20
 run n2 2 20
 timeout 900 python bench.py --gpus 8 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_inproc8.json 2> gpurun_out/${TAG}_inproc8.err; echo "inproc8 rc=$?"
 timeout 600 python tools/inproc_scaling.py C5 1,8 > gpurun_out/${TAG}_inproc_c5.jsonl 2> gpurun_out/${TAG}_inproc_c5.err; echo "inproc C5 rc=$?"; cat gpurun_out/${TAG}_inproc_c5.jsonl
-for f in gpurun_out/${TAG}_n8.json gpurun_out/${TAG}_n8_long.json gpurun_out/${TAG}_n4.json gpurun_out/${TAG}_n2.json gpurun_out/${TAG}_inproc8.json; do python - "$f" <<'PY'
+for f in gpurun_out/${TAG}_n8.json gpurun_out/${TAG}_n4.json gpurun_out/${TAG}_n2.json gpurun_out/${TAG}_inproc8.json; do python - "$f" <<'PY'
 import json,sys
 try:
     j=json.load(open(sys.argv[1]))

@@ -147,6 +147,10 @@ typedef struct {
  * form; measured on B200 with the shadow rays of the C3 frame it is 6 % SLOWER, so the
  * renderers do not use it. */
 #define MTB_FLAG_PAIR_RAYS 16384u
+/* Chained rays (measurement aid): mtb_intersect_rays walks rays 2i and 2i+1 in one thread, BACK TO BACK inside one node
+ * loop (csrc/device_core.cuh, TraceChain); with MTB_FLAG_PAIR_RAYS also set: the same two rays by two ordinary calls,
+ * the baseline of that comparison.  Results are identical to the one-ray-per-thread form. */
+#define MTB_FLAG_CHAIN_RAYS 32768u
 #define MTB_FLAG_NO_TILE_ORDER 32u /* megakernel: always launch tiles in scanline order (A/B of the cost-aware launch order) */
 
 /* ---- life cycle -------------------------------------------------------------------------------- */

@@ -45,6 +45,7 @@ MTB_FLAG_HYBRID = 2048
 MTB_FLAG_DEVICE_BVH = 4096
 MTB_FLAG_QUEUE = 8192
 MTB_FLAG_PAIR_RAYS = 16384
+MTB_FLAG_CHAIN_RAYS = 32768
 MAX_RECURSION_LEVEL = 5  # reference mythtracer.h:11 (a run-time argument here)
 FRAME_HANDLE_BYTES = 64
 

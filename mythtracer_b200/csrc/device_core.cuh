@@ -1241,6 +1241,124 @@ __device__ __forceinline__ void Trace2(const DeviceScene &sc, const D3 &oa, cons
     }
   }
 }
+
+// ---------------------------------------------------------------------------------------------------
+// A CHAIN of rays per lane.  A warp's Trace iteration lasts as long as the longest walk of its 32 lanes (mean 34 node
+// visits, per-warp maximum ~80: hence 14 of 32 lanes active).  When a lane has several independent queries at hand -
+// the first shadow segments of one hit towards all lights - it can walk them back to back INSIDE one node loop, so
+// that the warp waits for max(len0 + len1) over its lanes instead of max(len0) + max(len1).  Each ray is answered
+// exactly as Trace() answers it (same candidates, exact tests, certification, fallback to the exact recursion).
+// ---------------------------------------------------------------------------------------------------
+struct ChainRay {
+  double o[3], d[3];
+  double t_limit;  // in
+  double t;        // out
+  int slot;        // out: canonical slot, -1: none
+  int pad_;
+};
+
+template <bool DBG>
+__device__ __forceinline__ void TraceChain(const DeviceScene &sc, ChainRay *rays, int n, unsigned long long *cnt, const FastCtx &fc) {
+  constexpr int kNeedsExact = -2;
+  FastMem mem;
+  FastRay fr_store;
+  const FastRay *r_mem = &fr_store;
+  asm volatile("" : "+l"(r_mem) : : "memory");
+  unsigned long long stack[kFastLocalStack];
+  int sp = 0, slot = -1, node = kFastExit, k = -1;
+  float prune = 0.f;
+  for (;;) {
+    if (node == kFastExit) {
+      if (k >= 0) {  // ray k is finished: certify it (TraceFast's epilogue)
+        bool amb = false;
+        if (slot >= 0) {
+          MTB_FAST_BARRIER(&mem);
+          const double t = FmLoad(fc, &mem, kFmT);
+          amb = FmLoad(fc, &mem, kFmLo2) <= t + FmLoad(fc, &mem, kFmE) || DegeneratePassage(sc, slot, fc, &mem);
+          rays[k].t = t;
+        }
+        rays[k].slot = amb ? kNeedsExact : slot;
+        Count<DBG>(cnt, amb ? kFallback : kFast);
+      }
+      bool fast = false;
+      while (!fast && ++k < n) {  // next ray of the chain that the fast traversal can answer
+        Count<DBG>(cnt, kRays);
+        fast = FastSetup(sc, Load3(rays[k].o), Load3(rays[k].d), rays[k].t_limit, fc, &mem, &fr_store, &prune);
+        if (!fast) rays[k].slot = kNeedsExact;
+      }
+      if (!fast) break;
+      sp = 0;
+      slot = -1;
+      node = 0;
+      MTB_FAST_BARRIER(&mem);
+    }
+    const FastRay r = *r_mem;
+    while (node >= 0) {
+      float4 q0, q1, q2;
+      int2 kids;
+      {
+        const Bvh2Node *np_ = sc.gnodes + node;
+        float w8, w9, w10, w11;
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w), "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w)
+                     : "l"(np_));
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w), "=f"(w8), "=f"(w9), "=f"(w10), "=f"(w11)
+                     : "l"(reinterpret_cast<const char *>(np_) + 32));
+        kids.x = __float_as_int(w8);
+        kids.y = __float_as_int(w9);
+      }
+      Count<DBG>(cnt, kBvh, 2);
+      float tl, tr;
+      const bool hl = FastBox(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, prune, &tl);
+      const bool hr = FastBox(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, prune, &tr);
+      if (hl && hr) {
+        const bool right_first = tr < tl;
+        stack[sp++] = ((unsigned long long)__float_as_uint(right_first ? tl : tr) << 32) | (unsigned)(right_first ? kids.x : kids.y);
+        node = right_first ? kids.y : kids.x;
+      } else if (hl) {
+        node = kids.x;
+      } else if (hr) {
+        node = kids.y;
+      } else {
+        node = kFastExit;
+        while (sp > 0) {
+          const unsigned long long top = stack[--sp];
+          if (__uint_as_float((unsigned)(top >> 32)) <= prune) {
+            node = (int)(unsigned)top;
+            break;
+          }
+        }
+      }
+    }
+    if (node == kFastExit) continue;
+    {
+      MTB_FAST_BARRIER(&mem);
+      Ray rr;
+      rr.o = FmLoad3(fc, &mem, kFmO);
+      rr.inv = FmLoad3(fc, &mem, kFmInv);
+      rr.sx = rr.inv.x < 0.0;
+      rr.sy = rr.inv.y < 0.0;
+      rr.sz = rr.inv.z < 0.0;
+      const unsigned leaf = ~(unsigned)node;
+      for (unsigned s = leaf >> 3, e = s + (leaf & 7u); s < e; s++) TestSlotFast<DBG>(sc.gslots + s, rr, fc, &mem, &slot, &prune, cnt);
+      MTB_FAST_BARRIER(&mem);
+    }
+    node = kFastExit;
+    while (sp > 0) {
+      const unsigned long long top = stack[--sp];
+      if (__uint_as_float((unsigned)(top >> 32)) <= prune) {
+        node = (int)(unsigned)top;
+        break;
+      }
+    }
+  }
+  // rays the fast traversal did not answer or could not certify: the exact recursion, one by one
+#pragma unroll 1
+  for (int i = 0; i < n; i++) {
+    if (rays[i].slot == kNeedsExact) rays[i].slot = TraceExactCold<DBG>(sc, Load3(rays[i].o), Load3(rays[i].d), &rays[i].t, cnt);
+  }
+}
 #endif
 
 // ---------------------------------------------------------------------------------------------------

@@ -511,6 +511,69 @@ __global__ void __launch_bounds__(64) IntersectPairKernel(DeviceScene sc, Inters
   }
 }
 
+// Rays 2i and 2i + 1 by one thread: CHAINED = back to back inside one node loop (TraceChain), else by two ordinary
+// Trace calls (the warp reconverges in between) - the A/B of chaining, same threads, same rays.
+template <bool DBG, bool CHAINED>
+__global__ void __launch_bounds__(64) IntersectChainKernel(DeviceScene sc, IntersectParams ip) {
+  MTB_DECLARE_FAST_CTX(64);
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  unsigned long long cnt_store[DBG ? kNumCounters : 1];
+  unsigned long long *cnt = cnt_store;
+  if (DBG) {
+    for (int k = 0; k < kNumCounters; k++) cnt[k] = 0;
+  }
+  if (i < ip.n) {
+    ChainRay rays[2];
+    const int n = i + 1 < ip.n ? 2 : 1;
+    for (int k = 0; k < n; k++) {
+      for (int a = 0; a < 3; a++) {
+        rays[k].o[a] = ip.origins[(i + k) * 3 + a];
+        rays[k].d[a] = ip.dirs[(i + k) * 3 + a];
+      }
+      rays[k].t_limit = CUDART_INF;
+      rays[k].slot = -1;
+      rays[k].t = 0.0;
+    }
+    if (CHAINED) {
+      ChainRay *rp = rays;
+      asm volatile("" : "+l"(rp) : : "memory");
+      TraceChain<DBG>(sc, rp, n, cnt, fctx);
+      asm volatile("" : : "l"(rp) : "memory");
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < n; k++) {
+        rays[k].slot = Trace<DBG>(sc, Load3(rays[k].o), Load3(rays[k].d), CUDART_INF, &rays[k].t, cnt, fctx);
+        __syncwarp();
+      }
+    }
+#pragma unroll 1
+    for (int k = 0; k < n; k++) {
+      const int64_t r = i + k;
+      if (rays[k].slot < 0) {
+        ip.tri_index[r] = -1;
+        if (ip.t != nullptr) ip.t[r] = CUDART_NAN;
+        if (ip.point != nullptr) ip.point[r * 3 + 0] = ip.point[r * 3 + 1] = ip.point[r * 3 + 2] = CUDART_NAN;
+      } else {
+        ip.tri_index[r] = sc.slots[rays[k].slot].tri;
+        if (ip.t != nullptr) ip.t[r] = rays[k].t;
+        if (ip.point != nullptr) {
+          const D3 p = Add(Load3(rays[k].o), MulS(Load3(rays[k].d), rays[k].t));
+          ip.point[r * 3 + 0] = p.x;
+          ip.point[r * 3 + 1] = p.y;
+          ip.point[r * 3 + 2] = p.z;
+        }
+      }
+    }
+  }
+  if (DBG && ip.counters != nullptr) {
+    for (int k = 0; k < kNumCounters; k++) {
+      unsigned long long v = cnt[k];
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+      if ((threadIdx.x & 31u) == 0u && v != 0ull) atomicAdd(ip.counters + k, v);
+    }
+  }
+}
+
 // Counting sort of the tiles by cost bucket (log2 of the ray count, most expensive first).  One block.
 // heavy_k (nullable): receives how many leading tiles of the order - the most expensive ones - together carry
 // `heavy_share_q16` / 65536 of the frame's rays (whole buckets, then part of the next one), at most k_max tiles: the
@@ -620,14 +683,24 @@ void LaunchRenderMega(const DeviceScene &sc, const RenderParams &rp, int n_block
   }
 }
 
-void LaunchIntersect(const DeviceScene &sc, const IntersectParams &ip, bool debug_build, bool pairs, cudaStream_t stream) {
+void LaunchIntersect(const DeviceScene &sc, const IntersectParams &ip, bool debug_build, int mode, cudaStream_t stream) {
   if (ip.n <= 0) return;
-  if (pairs) {
-    const int blocks = (int)(((ip.n + 1) / 2 + 63) / 64);
+  const int pair_blocks = (int)(((ip.n + 1) / 2 + 63) / 64);
+  if (mode == 1) {
     if (debug_build) {
-      IntersectPairKernel<true><<<blocks, 64, 0, stream>>>(sc, ip);
+      IntersectPairKernel<true><<<pair_blocks, 64, 0, stream>>>(sc, ip);
     } else {
-      IntersectPairKernel<false><<<blocks, 64, 0, stream>>>(sc, ip);
+      IntersectPairKernel<false><<<pair_blocks, 64, 0, stream>>>(sc, ip);
+    }
+    return;
+  }
+  if (mode >= 2) {
+    if (debug_build) {
+      if (mode == 2) IntersectChainKernel<true, true><<<pair_blocks, 64, 0, stream>>>(sc, ip);
+      else IntersectChainKernel<true, false><<<pair_blocks, 64, 0, stream>>>(sc, ip);
+    } else {
+      if (mode == 2) IntersectChainKernel<false, true><<<pair_blocks, 64, 0, stream>>>(sc, ip);
+      else IntersectChainKernel<false, false><<<pair_blocks, 64, 0, stream>>>(sc, ip);
     }
     return;
   }

@@ -778,9 +778,9 @@ def test_sibling_entry_tie_on_the_device(product_lib, oracle_mod):
 
 
 def test_two_rays_per_lane_gives_the_same_answers(product_lib, oracle_mod, scene_dir):
-    """MTB_FLAG_PAIR_RAYS (Trace2: one thread walks rays 2i and 2i+1 in one loop) against the oracle: random rays,
+    """MTB_FLAG_PAIR_RAYS (Trace2: one thread walks rays 2i and 2i+1 in one loop) and MTB_FLAG_CHAIN_RAYS against the oracle: random rays,
     axis-parallel ones (literal path), rays from outside, and an odd count (the last thread has one ray)."""
-    from mythtracer_b200 import MTB_FLAG_COUNT_WORK, MTB_FLAG_PAIR_RAYS
+    from mythtracer_b200 import MTB_FLAG_CHAIN_RAYS, MTB_FLAG_COUNT_WORK, MTB_FLAG_PAIR_RAYS
     files, cfg = scenes.config_scene("C2", scene_dir, scale=0.2)
     mt, orc = _load_pair(product_lib, oracle_mod, files, 3)
     rng = np.random.default_rng(12)
@@ -790,7 +790,9 @@ def test_two_rays_per_lane_gives_the_same_answers(product_lib, oracle_mod, scene
     cpu = orc.intersect(o, d)
     hit = cpu["tri"] >= 0
     assert hit.sum() > 5000
-    for flags in (MTB_FLAG_PAIR_RAYS, MTB_FLAG_PAIR_RAYS | MTB_FLAG_COUNT_WORK):
+    # (MTB_FLAG_CHAIN_RAYS: the two rays of a thread back to back inside one node loop, TraceChain; both flags: by two calls)
+    for flags in (MTB_FLAG_PAIR_RAYS, MTB_FLAG_PAIR_RAYS | MTB_FLAG_COUNT_WORK, MTB_FLAG_CHAIN_RAYS, MTB_FLAG_CHAIN_RAYS | MTB_FLAG_COUNT_WORK,
+                  MTB_FLAG_CHAIN_RAYS | MTB_FLAG_PAIR_RAYS):
         mt.set_flags(flags)
         gpu = mt.intersect_rays(o, d, want_stats=True)
         assert np.array_equal(gpu["tri"], cpu["tri"]), flags

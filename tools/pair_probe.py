@@ -1,10 +1,11 @@
 """Two rays per lane: does it pay?  Shadow-like rays of the C3 frame (primary hit point -> light 0 / light 1, all
-pixels) through mtb_intersect_rays, one ray per thread against two rays per thread (MTB_FLAG_PAIR_RAYS).  Results
-must be identical; kernel time is what is compared."""
+pixels) through mtb_intersect_rays: one ray per thread; two rays per thread in lock step (MTB_FLAG_PAIR_RAYS, Trace2);
+two rays per thread by two ordinary calls; two rays per thread back to back inside one node loop (MTB_FLAG_CHAIN_RAYS,
+TraceChain).  Results must be identical; kernel time is what is compared."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from mythtracer_b200 import MythTracer, Light, scenegen, MTB_FLAG_MEGAKERNEL, MTB_FLAG_PAIR_RAYS, MTB_FLAG_COUNT_WORK
+from mythtracer_b200 import MythTracer, Light, scenegen, MTB_FLAG_MEGAKERNEL, MTB_FLAG_PAIR_RAYS, MTB_FLAG_CHAIN_RAYS, MTB_FLAG_COUNT_WORK
 
 name = sys.argv[1] if len(sys.argv) > 1 else "C3"
 files, cfg = scenegen.generate_config(name, "/tmp/mtb_scenes")
@@ -35,7 +36,9 @@ o2 = np.stack([rays[0][0], rays[1][0]], 1).reshape(-1, 3)
 d2 = np.stack([rays[0][1], rays[1][1]], 1).reshape(-1, 3)
 out = {"config": name, "pixels": int(n), "rays": int(2 * n)}
 res = {}
-for label, flags, o, d in (("single", MTB_FLAG_MEGAKERNEL, o1, d1), ("pair", MTB_FLAG_MEGAKERNEL | MTB_FLAG_PAIR_RAYS, o2, d2)):
+for label, flags, o, d in (("single", MTB_FLAG_MEGAKERNEL, o1, d1), ("pair", MTB_FLAG_MEGAKERNEL | MTB_FLAG_PAIR_RAYS, o2, d2),
+                           ("two_calls", MTB_FLAG_MEGAKERNEL | MTB_FLAG_PAIR_RAYS | MTB_FLAG_CHAIN_RAYS, o2, d2),
+                           ("chain", MTB_FLAG_MEGAKERNEL | MTB_FLAG_CHAIN_RAYS, o2, d2)):
     mt.set_flags(flags)
     ms = []
     for it in range(5):
@@ -52,7 +55,11 @@ t2 = res["pair"]["t"].reshape(-1, 2)
 k1 = res["single"]["tri"].reshape(-1, 2, 32).transpose(0, 2, 1).reshape(-1, 2)
 k2 = res["pair"]["tri"].reshape(-1, 2)
 out["identical"] = bool(np.array_equal(k1, k2) and np.array_equal(t1, t2, equal_nan=True))
+for label in ("two_calls", "chain"):
+    out["identical"] = out["identical"] and bool(np.array_equal(k1, res[label]["tri"].reshape(-1, 2)) and
+                                                 np.array_equal(t1, res[label]["t"].reshape(-1, 2), equal_nan=True))
 out["speedup"] = round(out["single"]["best_ms"] / out["pair"]["best_ms"], 3)
+out["chain_vs_two_calls"] = round(out["two_calls"]["best_ms"] / out["chain"]["best_ms"], 3)
 print(json.dumps(out))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/pair_probe_%s.json" % name, "w"), indent=1)

@@ -25,7 +25,32 @@ static int Fail(const char *what) {
   return 1;
 }
 
+// tri <in.bin> <out.bin>: records of 15 doubles (3 vertices, ray origin, ray direction) -> records of 5 doubles
+// (hit flag, distance, hit point) from Triangle::IntersectRay called through Primitive*.
+static int TriangleBatch(const char *in_path, const char *out_path) {
+  FILE *in = fopen(in_path, "rb"), *out = fopen(out_path, "wb");
+  if (!in || !out) return Fail("tri: files");
+  double rec[15];
+  while (fread(rec, sizeof(double), 15, in) == 15) {
+    Triangle tri;
+    for (int v = 0; v < 3; v++) tri.vertex[v] = {rec[3 * v], rec[3 * v + 1], rec[3 * v + 2]};
+    tri.CacheAABB();
+    const Primitive *prim = &tri;
+    V3D point{};
+    double res[5] = {0, 0, 0, 0, 0};
+    if (prim->IntersectRay(Ray({rec[9], rec[10], rec[11]}, {rec[12], rec[13], rec[14]}), &point, &res[1])) {
+      res[0] = 1.0;
+      res[2] = point.v[0], res[3] = point.v[1], res[4] = point.v[2];
+    }
+    fwrite(res, sizeof(double), 5, out);
+  }
+  fclose(in);
+  fclose(out);
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  if (argc >= 4 && strcmp(argv[1], "tri") == 0) return TriangleBatch(argv[2], argv[3]);
   if (argc < 3) return Fail("usage");
   MythTracer mt;
   if (!mt.LoadObj(argv[2])) return Fail("LoadObj");

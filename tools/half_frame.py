@@ -1,4 +1,5 @@
-"""Times the wavefront / megakernel on a 1/world partition of the C3 frame on ONE GPU (scaling diagnosis)."""
+"""Times the wavefront / megakernel on a 1/world partition of the C3 frame on ONE GPU (scaling diagnosis).
+   half_frame.py <world> <mega|queue|wf|hybrid|auto> [rank,rank,...]   (default: ranks 0 and 1)"""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,7 +12,8 @@ mt.GetScene().lights = [Light.from_tuple(l) for l in files.lights]; mt.push_ligh
 W, H = cfg["width"], cfg["height"]
 s = torch.cuda.Stream(); torch.cuda.set_stream(s)
 buf = torch.zeros((tiles.padded_height(H, world), W, 3), dtype=torch.uint8, device="cuda")
-for rank in range(min(world, 2)):
+ranks = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else list(range(min(world, 2)))
+for rank in ranks:
     mt.set_partition(rank, world)
     ts = []
     for it in range(16):

@@ -198,6 +198,7 @@ struct mtb_context {
   int64_t device_bytes = 0;
   std::atomic<uint64_t> launches{0};  // kernels of this library launched so far (mtb_launch_count)
   bool no_peer_store = false;         // MTB_NO_PEER_STORE=1: gather with peer copies instead of direct tile stores (A/B)
+  bool no_host_store = false;         // MTB_NO_HOST_STORE=1: copy the frame to a pinned host buffer instead of storing tiles into it (A/B)
   int l2_persist_mb = 0;              // MTB_L2_PERSIST_MB=n: pin the scene BVH's nodes in n MB of persisting L2 (A/B)
   bool device_bvh = false;            // the scene BVH of the current scene was built on the devices (device_build.cu)
   int64_t atlas_bytes = 0;            // layered texture array as allocated on a device
@@ -746,8 +747,21 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
   // the frame on device 0 that receives every device's tiles
   DeviceState &dev0 = ctx->dev[0];
   MTB_CUDA(ctx, cudaSetDevice(dev0.device));
-  if (d_rgb_user == nullptr) MTB_CUDA(ctx, dev0.rgb.Reserve(npx * 3));
-  uint8_t *const rgb_target = d_rgb_user != nullptr ? static_cast<uint8_t *>(d_rgb_user) : dev0.rgb.ptr;
+  // A pinned host frame (mtb_host_alloc, cudaHostAlloc, a registered buffer) is mapped into the device's address space
+  // under unified addressing: with one device the kernels then store their finished tile rows (aligned 8-byte stores)
+  // straight into it over PCIe, overlapped with the rendering, and the frame-sized device-to-host copy at the end of
+  // the step disappears.  Pageable host memory and multi-device contexts take the copy.  MTB_NO_HOST_STORE=1 is the A/B.
+  uint8_t *host_direct = nullptr;
+  if (rgb_host != nullptr && d_rgb_user == nullptr && n_dev == 1 && !ctx->no_host_store && (chunk_w & 7) == 0 &&
+      (reinterpret_cast<uintptr_t>(rgb_host) & 7u) == 0u) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, rgb_host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr) {
+      host_direct = static_cast<uint8_t *>(attr.devicePointer);
+    }
+    cudaGetLastError();  // (an unregistered pointer is not an error here)
+  }
+  if (d_rgb_user == nullptr && host_direct == nullptr) MTB_CUDA(ctx, dev0.rgb.Reserve(npx * 3));
+  uint8_t *const rgb_target = d_rgb_user != nullptr ? static_cast<uint8_t *>(d_rgb_user) : (host_direct != nullptr ? host_direct : dev0.rgb.ptr);
   // direct peer stores need a mapping of the target in the storing device's address space: the context's own frame
   // (cudaMalloc) has one wherever peer access is on; a caller's buffer may come from an allocator without one
   std::vector<char> peer_store((size_t)n_dev, 0);
@@ -946,7 +960,7 @@ int RenderImpl(mtb_context *ctx, const mtb_camera *cam, int image_w, int image_h
       if (rc != MTB_OK) return rc;
     }
   }
-  if (rgb_host != nullptr) MTB_CUDA(ctx, cudaMemcpyAsync(rgb_host, rgb0, npx * 3, cudaMemcpyDeviceToHost, s0));
+  if (rgb_host != nullptr && host_direct == nullptr) MTB_CUDA(ctx, cudaMemcpyAsync(rgb_host, rgb0, npx * 3, cudaMemcpyDeviceToHost, s0));
   if (dbg_host != nullptr) {
     MTB_CUDA(ctx, cudaMemcpyAsync(dbg_host, d0.dbg.ptr, npx * sizeof(mtb_debug), cudaMemcpyDeviceToHost, s0));
   }
@@ -1043,6 +1057,8 @@ int mtb_create(mtb_context **out, const int *devices, int n_devices) {
   {  // development knobs (A/B measurements, tests that force a queue overflow)
     const char *v = getenv("MTB_NO_PEER_STORE");
     ctx->no_peer_store = v != nullptr && v[0] == '1';
+    const char *hs = getenv("MTB_NO_HOST_STORE");
+    ctx->no_host_store = hs != nullptr && hs[0] == '1';
     const char *l2 = getenv("MTB_L2_PERSIST_MB");
     ctx->l2_persist_mb = l2 != nullptr ? atoi(l2) : 0;
     const char *qf = getenv("MTB_WF_QUEUE_FACTOR"), *af = getenv("MTB_WF_ACT_FACTOR");

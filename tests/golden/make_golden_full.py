@@ -4,8 +4,8 @@
 
 * C2 (textured, 1280x720) and C3 (BASELINE.json configs[2], 1920x1080, depth 5, 2 lights): the WHOLE frame.
 * C4 (2 M triangles, 1920x1080): the WHOLE frame (~30 minutes of 8 cores).
-* C5: full-width bands of 8 rows spread over the frame height, together 12.6 % of the frame (`C5:full` = the whole
-  frame, ~2.5 hours).
+* C5 (the C3 scene at 3840x2160, 4 lights, depth 8): the WHOLE frame (~2 hours of 8 cores).
+(A config can also be sampled: set its BANDS entry to a number of full-width bands of 8 rows.)
 
 Per config it writes tests/golden/full_<cfg>.npz with what the reference returned through its public API
 (RayTrace(WorkChunk*) with output_debug, mythtracer.cc:280-312,24-36): the RGB24 bytes, the per-pixel
@@ -30,7 +30,7 @@ from oracle import oracle_py  # noqa: E402
 SCENE_DIR = os.environ.get("MTB_SCENE_DIR", "/tmp/mtb_scenes")
 BAND_ROWS = 8
 # (number of bands of 8 rows) per config; None = the whole frame
-BANDS = {"C2": None, "C3": None, "C4": None, "C5": 34}
+BANDS = {"C2": None, "C3": None, "C4": None, "C5": None}
 
 
 def sha(a) -> str:
